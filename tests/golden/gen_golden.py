@@ -1,0 +1,113 @@
+"""Generate golden vectors FROM THE UNMODIFIED REFERENCE (run in the build container only;
+/root/reference does not exist on the GPU box).  Output: tests/golden/*.npz (committed).
+
+    python tests/golden/gen_golden.py
+"""
+import os, sys, io, contextlib
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import ref_shim  # noqa
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print('wrote', name, sum(np.asarray(v).nbytes for v in out.values()) // 1024, 'KiB')
+
+
+def main():
+    torch.set_num_threads(8)
+    ref_shim.patch_cuda_noop()
+    m = ref_shim.import_reference('deblurring-diffusion-pytorch', 'deblurring_diffusion_pytorch')
+
+    # ---- (1) small ConvNeXt Unet: forward, L1 loss, gradients -------------------------
+    torch.manual_seed(0)
+    unet = quiet(m.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    # make LayerNorm affine / biases non-trivial so every term is exercised
+    with torch.no_grad():
+        for n, p in unet.named_parameters():
+            if n.endswith('.g'):
+                p.add_(0.1 * torch.randn_like(p))
+            if n.endswith('.b'):
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {k: v.clone() for k, v in unet.state_dict().items()}
+    torch.manual_seed(1234)
+    x = torch.rand(2, 3, 32, 32) * 2 - 1
+    t = torch.tensor([0, 7], dtype=torch.long)
+    target = torch.rand(2, 3, 32, 32) * 2 - 1
+    y = unet(x, t)
+    loss = (target - y).abs().mean()
+    loss.backward()
+    # full gradient for small tensors; strided subsample + norm for large ones (keeps the fixture small)
+    grads = {}
+    for n, p in unet.named_parameters():
+        g = p.grad.reshape(-1)
+        if g.numel() <= 4096:
+            grads['grad:' + n] = p.grad.clone()
+        else:
+            stride = g.numel() // 2048
+            grads['gsub:' + n] = g[::stride].clone()
+            grads['gnorm:' + n] = g.double().norm().float()
+    save('unet_small', x=x, t=t, target=target, y=y, loss=loss,
+         **{'sd:' + k: v for k, v in sd.items()}, **grads)
+
+    # ---- (2) q_sample for every blur routine (+discrete) ------------------------------
+    ident = torch.nn.Identity()
+    cases = [
+        ('Incremental', 5, 0.4, 6), ('Constant', 11, 7.0, 6), ('Constant_reflect', 5, 1.5, 6),
+        ('Exponential_reflect', 7, 0.1, 8), ('Exponential', 7, 0.1, 8),
+        ('Special_6_routine', 11, 0.0, 6),
+    ]
+    out = {}
+    torch.manual_seed(7)
+    xq = torch.rand(4, 3, 16, 16) * 2 - 1
+    for routine, ks, std, T in cases:
+        for discrete in (False, True):
+            gd = m.GaussianDiffusion(ident, image_size=16, device_of_kernel='cpu', channels=3,
+                                     timesteps=T, kernel_std=std, kernel_size=ks,
+                                     blur_routine=routine, discrete=discrete)
+            tt = torch.tensor([0, T - 1, 2, 1], dtype=torch.long)
+            q = gd.q_sample(xq, tt)
+            key = '%s|%d|%g|%d|%d' % (routine, ks, std, T, int(discrete))
+            out['q:' + key] = q
+            out['t:' + key] = tt
+            out['w:' + key] = torch.stack([k.weight[0, 0] for k in gd.gaussian_kernels]) \
+                if routine != 'Individual_Incremental' else torch.zeros(1)
+    save('qsample', x=xq, **out)
+
+    # ---- (3) sample(): Algorithm 1 ('default') and Algorithm 2 ('x0_step_down') -------
+    torch.manual_seed(3)
+    out = {}
+    xs = torch.rand(2, 3, 32, 32) * 2 - 1
+    for routine, ks, std, T, samp, discrete in [
+        ('Exponential_reflect', 7, 0.15, 4, 'x0_step_down', False),
+        ('Constant', 5, 1.0, 3, 'default', False),
+        ('Incremental', 5, 0.5, 3, 'x0_step_down', True),
+    ]:
+        gd = m.GaussianDiffusion(unet, image_size=32, device_of_kernel='cpu', channels=3,
+                                 timesteps=T, kernel_std=std, kernel_size=ks, blur_routine=routine,
+                                 sampling_routine=samp, discrete=discrete)
+        xt, dr, img = quiet(gd.sample, batch_size=2, img=xs)
+        key = '%s|%d|%g|%d|%s|%d' % (routine, ks, std, T, samp, int(discrete))
+        out['xt:' + key], out['dr:' + key], out['img:' + key] = xt, dr, img
+        tt = torch.tensor([T - 1, 0])
+        with torch.no_grad():
+            out['loss:' + key] = gd.p_losses(xs, tt)
+    save('sample_small', x=xs, **out)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,113 @@
+"""Pins the oracle (oracle/*.py) against golden vectors produced by the unmodified reference
+(tests/golden/gen_golden.py).  CPU only."""
+import os
+import numpy as np
+import torch
+import pytest
+
+import unet_oracle as UO
+import deblur_oracle as DO
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def load(name):
+    z = np.load(os.path.join(G, name + '.npz'))
+    return {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+
+
+def rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_unet_forward_loss_grads_match_reference():
+    g = load('unet_small')
+    sd = {k[3:]: v.clone().requires_grad_(True) for k, v in g.items() if k.startswith('sd:')}
+    y = UO.unet_forward(sd, g['x'], g['t'])
+    assert rel(y.detach(), g['y']) < 2e-6
+    loss = (g['target'] - y).abs().mean()
+    assert abs(loss.item() - g['loss'].item()) < 1e-6
+    loss.backward()
+    n = 0
+    for k, v in g.items():
+        if k.startswith('grad:'):
+            assert rel(sd[k[5:]].grad, v) < 2e-5, k
+            n += 1
+        elif k.startswith('gsub:'):
+            gr = sd[k[5:]].grad.reshape(-1)
+            stride = gr.numel() // 2048
+            assert rel(gr[::stride], v) < 2e-5, k
+            assert abs(gr.double().norm().item() / g['gnorm:' + k[5:]].item() - 1) < 1e-5
+            n += 1
+    assert n == len(sd)
+
+
+def test_make_state_dict_has_reference_keys_and_shapes():
+    g = load('unet_small')
+    ref = {k[3:]: tuple(v.shape) for k, v in g.items() if k.startswith('sd:')}
+    mine = {k: tuple(v.shape) for k, v in UO.make_unet_state_dict(32, (1, 2), 3).items()}
+    assert ref == mine
+
+
+def _cases(prefix, g):
+    return sorted(k[len(prefix):] for k in g if k.startswith(prefix))
+
+
+def test_blur_weights_and_q_sample_match_reference():
+    g = load('qsample')
+    x = g['x']
+    for key in _cases('q:', g):
+        routine, ks, std, T, disc = key.split('|')
+        o = DO.DeblurOracle(None, image_size=16, channels=3, timesteps=int(T), kernel_std=float(std),
+                            kernel_size=int(ks), blur_routine=routine, discrete=bool(int(disc)))
+        w = torch.stack(o.kernels2d)
+        assert torch.equal(w, g['w:' + key]), key          # taps bit-exact vs reference+shim
+        q = o.q_sample(x, g['t:' + key])
+        if int(disc):
+            # 8-bit truncation can flip one level on a last-ulp difference; allow <=1 level on <0.1% of pixels
+            d = (q - g['q:' + key]).abs()
+            assert d.max() <= 2 / 255 + 1e-6 and (d > 1e-6).float().mean() < 1e-3, key
+        else:
+            assert torch.allclose(q, g['q:' + key], atol=2e-6, rtol=0), key
+
+
+def test_sample_and_p_losses_match_reference():
+    g = load('sample_small')
+    u = load('unet_small')
+    sd = {k[3:]: v for k, v in u.items() if k.startswith('sd:')}
+    fn = lambda x, t: UO.unet_forward(sd, x, t)
+    for key in _cases('img:', g):
+        routine, ks, std, T, samp, disc = key.split('|')
+        o = DO.DeblurOracle(fn, image_size=32, channels=3, timesteps=int(T), kernel_std=float(std),
+                            kernel_size=int(ks), blur_routine=routine, sampling_routine=samp,
+                            discrete=bool(int(disc)))
+        xt, dr, img = o.sample(2, g['x'])
+        assert rel(xt, g['xt:' + key]) < 1e-5, key
+        assert rel(dr, g['dr:' + key]) < 1e-5, key
+        assert rel(img, g['img:' + key]) < 1e-4, key
+        with torch.no_grad():
+            loss = o.p_losses(g['x'], torch.tensor([int(T) - 1, 0]))
+        assert abs(loss.item() - g['loss:' + key].item()) < (2e-3 if int(disc) else 1e-5), key
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference only in build container')
+def test_oracle_matches_live_reference_config1_mnist():
+    """BASELINE config 1: MNIST-shaped 1x32x32, T=20, k=11, sigma=7, Constant, B=4, full-size Unet."""
+    import ref_shim, io, contextlib
+    m = ref_shim.import_reference('deblurring-diffusion-pytorch', 'deblurring_diffusion_pytorch')
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        unet = m.Unet(dim=64, dim_mults=(1, 2, 4, 8), channels=1)
+    gd = m.GaussianDiffusion(unet, image_size=32, device_of_kernel='cpu', channels=1, timesteps=20,
+                             kernel_std=7.0, kernel_size=11, blur_routine='Constant', loss_type='l1')
+    torch.manual_seed(1234)
+    x = torch.rand(4, 1, 32, 32) * 2 - 1
+    t = torch.randint(0, 20, (4,))
+    with torch.no_grad():
+        ref_loss = gd.p_losses(x, t)
+    sd = unet.state_dict()
+    o = DO.DeblurOracle(lambda a, b: UO.unet_forward(sd, a, b), image_size=32, channels=1, timesteps=20,
+                        kernel_std=7.0, kernel_size=11, blur_routine='Constant')
+    with torch.no_grad():
+        loss = o.p_losses(x, t)
+    assert abs(loss.item() - ref_loss.item()) < 1e-5
