@@ -1,0 +1,72 @@
+"""ctypes binding of libcolddiff.so (the C ABI in include/colddiff.h).
+
+The product path has NO fallback: if the shared library (built in-tree by
+__graft_entry__.build() / `make -C cold_diffusion_models_b200/csrc`) is missing, importing
+this module raises.  All pointers passed down are raw device pointers of torch tensors; the
+stream is torch's current CUDA stream.
+"""
+import ctypes as C
+import os
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libcolddiff.so')
+CD_MAX_TAPS = 16
+CONV_SIMT, CONV_TC = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+
+
+class ColdDiffError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("libcolddiff.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`"
+                      % LIB_PATH)
+lib = C.CDLL(LIB_PATH)
+
+
+class ConvSrc(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('ld', C.c_int32), ('C', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('ntaps', C.c_int32), ('dy', C.c_int32 * CD_MAX_TAPS), ('dx', C.c_int32 * CD_MAX_TAPS),
+                ('w', C.c_void_p), ('w_per_batch', C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [('B', C.c_int32), ('Hg', C.c_int32), ('Wg', C.c_int32), ('sy', C.c_int32), ('sx', C.c_int32),
+                ('Cout', C.c_int32), ('nsrc', C.c_int32), ('s', ConvSrc * 2),
+                ('out', C.c_void_p), ('out_ld', C.c_int32), ('Ho', C.c_int32), ('Wo', C.c_int32),
+                ('oys', C.c_int32), ('oxs', C.c_int32), ('oy0', C.c_int32), ('ox0', C.c_int32),
+                ('bias', C.c_void_p), ('resid', C.c_void_p), ('resid_ld', C.c_int32),
+                ('act', C.c_int32), ('round_tf32', C.c_int32),
+                ('out2', C.c_void_p), ('out2_ld', C.c_int32)]
+
+
+lib.cd_version.restype = C.c_int
+lib.cd_last_error.argtypes = [C.c_char_p, C.c_size_t]
+
+
+def _check(rc, what):
+    if rc != 0:
+        buf = C.create_string_buffer(512)
+        lib.cd_last_error(buf, 512)
+        raise ColdDiffError("%s failed (%d): %s" % (what, rc, buf.value.decode()))
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def call(name, *args):
+    _check(getattr(lib, name)(*args), name)
+
+
+EXPORTS = [
+    'cd_version', 'cd_last_error', 'cd_conv_fwd', 'cd_conv_wgrad', 'cd_pack_weight', 'cd_unpack_wgrad',
+]

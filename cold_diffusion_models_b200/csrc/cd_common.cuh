@@ -1,0 +1,52 @@
+// Internal helpers shared by the libcolddiff translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/colddiff.h"
+
+#ifndef CD_HOST_ONLY
+#if !defined(__CUDA_ARCH__) || (__CUDA_ARCH__ >= 1000)
+#else
+#error "libcolddiff is written for sm_100a only"
+#endif
+#endif
+
+// ---- error plumbing (thread-local text, negative return codes) --------------------------------
+void cd_set_error(const char* fmt, ...);
+#define CD_FAIL(...) do { cd_set_error(__VA_ARGS__); return -1; } while (0)
+#define CD_REQUIRE(cond, ...) do { if (!(cond)) { cd_set_error(__VA_ARGS__); return -1; } } while (0)
+#define CD_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+    cd_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); return -2; } } while (0)
+#define CD_LAUNCH_CHECK() CD_CUDA(cudaGetLastError())
+
+static inline int cd_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+// ---- small device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float cd_gelu(float x) {           // exact erf GELU == nn.GELU()
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float cd_gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float cd_round_tf32(float x) {     // RN (ties away), as cvt.rna.tf32.f32
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float cd_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float cd_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif

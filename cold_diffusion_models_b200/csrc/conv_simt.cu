@@ -1,0 +1,319 @@
+// fp32 CUDA-core implementation of the tap-list convolution contract in colddiff.h.
+// Used (a) where channel counts are not tensor-core shaped (3-channel image edges), (b) as the
+// on-device fp32 cross-check of the tcgen05 path, (c) for the weight gradient until the tcgen05
+// wgrad lands.  64 pixels x 64 out-channels per CTA, 4x4 register tile per thread.
+#include "cd_common.cuh"
+
+namespace {
+
+struct SimtSrc {
+  const float* src; int ld, C, H, W, ntaps, wpb;
+  const float* w;
+  int dy[CD_MAX_TAPS], dx[CD_MAX_TAPS];
+};
+struct SimtParams {
+  int B, Hg, Wg, sy, sx, Cout, nsrc;
+  SimtSrc s[2];
+  float* out; int out_ld, Ho, Wo, oys, oxs, oy0, ox0;
+  const float* bias; const float* resid; int resid_ld; int act, round_tf32;
+  float* out2; int out2_ld;
+  int tiles_per_img;
+};
+
+constexpr int TM = 64, TNc = 64, TK = 16;
+
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const SimtParams p) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TNc + 4];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / p.tiles_per_img;
+  const int m0 = (blockIdx.x % p.tiles_per_img) * TM;
+  const int co0 = blockIdx.y * TNc;
+  const int npix = p.Hg * p.Wg;
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[4][4] = {};
+
+  // loader mapping: element (row = tid / 4, k-quad = tid % 4)
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  const int lm = m0 + lrow;
+  const bool lvalid = lm < npix;
+  const int lgy = lvalid ? lm / p.Wg : 0, lgx = lvalid ? lm % p.Wg : 0;
+
+  for (int s = 0; s < p.nsrc; ++s) {
+    const SimtSrc& S = p.s[s];
+    for (int tap = 0; tap < S.ntaps; ++tap) {
+      const int iy = lgy * p.sy + S.dy[tap], ix = lgx * p.sx + S.dx[tap];
+      const bool inb = lvalid && iy >= 0 && iy < S.H && ix >= 0 && ix < S.W;
+      const float* arow = S.src + ((static_cast<long long>(b) * S.H + iy) * S.W + ix) * S.ld;
+      const float* wrow = S.w + ((static_cast<long long>(S.wpb ? b : 0) * S.ntaps + tap) * p.Cout + (co0 + lrow)) * S.C;
+      const bool wvalid = (co0 + lrow) < p.Cout;
+      for (int k0 = 0; k0 < S.C; k0 += TK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + lk + j;
+          As[lk + j][lrow] = (inb && k < S.C) ? arow[k] : 0.f;
+          Bs[lk + j][lrow] = (wvalid && k < S.C) ? wrow[k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+          float a[4], w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= npix) continue;
+    const int gy = m / p.Wg, gx = m % p.Wg;
+    const long long pix = (static_cast<long long>(b) * p.Ho + (gy * p.oys + p.oy0)) * p.Wo + (gx * p.oxs + p.ox0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co >= p.Cout) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[co];
+      if (p.resid) v += p.resid[pix * p.resid_ld + co];
+      if (p.out2) p.out2[pix * p.out2_ld + co] = v;
+      if (p.act == CD_ACT_GELU) v = cd_gelu(v);
+      if (p.round_tf32) v = cd_round_tf32(v);
+      p.out[pix * p.out_ld + co] = v;
+    }
+  }
+}
+
+// dW[tap][co][ci] += sum_pix dout[pix][co] * src[pix(tap)][ci]
+struct WgradParams {
+  int B, Hg, Wg, sy, sx, Cout, C, H, W, ld, ntaps;
+  int dy[CD_MAX_TAPS], dx[CD_MAX_TAPS];
+  const float* src; const float* dout; int dout_ld, Ho, Wo, oys, oxs, oy0, ox0;
+  float* dw;
+  int splits, pix_per_split;
+};
+
+__global__ void __launch_bounds__(256)
+wgrad_simt_kernel(const WgradParams p) {
+  __shared__ float As[TK][TM + 4];   // dout chunk  [pix][co]
+  __shared__ float Bs[TK][TNc + 4];  // src chunk   [pix][ci]
+  const int tid = threadIdx.x;
+  const int co0 = blockIdx.x * TM, ci0 = blockIdx.y * TNc;
+  const int tap = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int tx = tid % 16, ty = tid / 16;
+  const long long total = static_cast<long long>(p.B) * p.Hg * p.Wg;
+  const long long pbeg = static_cast<long long>(split) * p.pix_per_split;
+  long long pend = pbeg + p.pix_per_split; if (pend > total) pend = total;
+  float acc[4][4] = {};
+  // loader: pixel row = tid / 16 (16 pixels per chunk), channel quad = (tid % 16) * 4
+  const int lp = tid >> 4, lc = (tid & 15) * 4;
+  for (long long q0 = pbeg; q0 < pend; q0 += TK) {
+    const long long q = q0 + lp;
+    float a[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
+    if (q < pend) {
+      const int gx = static_cast<int>(q % p.Wg);
+      const long long r = q / p.Wg;
+      const int gy = static_cast<int>(r % p.Hg), b = static_cast<int>(r / p.Hg);
+      const long long opix = (static_cast<long long>(b) * p.Ho + (gy * p.oys + p.oy0)) * p.Wo + (gx * p.oxs + p.ox0);
+      const float* drow = p.dout + opix * p.dout_ld;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (co0 + lc + j < p.Cout) a[j] = drow[co0 + lc + j];
+      const int iy = gy * p.sy + p.dy[tap], ix = gx * p.sx + p.dx[tap];
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+        const float* srow = p.src + ((static_cast<long long>(b) * p.H + iy) * p.W + ix) * p.ld;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ci0 + lc + j < p.C) s[j] = srow[ci0 + lc + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { As[lp][lc + j] = a[j]; Bs[lp][lc + j] = s[j]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float av[4], sv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = As[k][ty * 4 + i]; sv[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], sv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= p.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + tx * 4 + j;
+      if (ci >= p.C) continue;
+      atomicAdd(p.dw + (static_cast<long long>(tap) * p.Cout + co) * p.C + ci, acc[i][j]);
+    }
+  }
+}
+
+// column sums: out[c] += sum_rows x[row*ld + c]
+__global__ void colsum_kernel(const float* x, int ld, long long rows, int C, float* out, long long rows_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;   // 8 row lanes
+  const long long r0 = blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block; if (r1 > rows) r1 = rows;
+  float s = 0.f;
+  if (c < C) for (long long r = r0 + ry; r < r1; r += 8) s += x[r * ld + c];
+  __shared__ float sm[8][33];
+  sm[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+    atomicAdd(out + c, t);
+  }
+}
+
+// weight repack kernels -----------------------------------------------------------------------
+struct TapList { int ky[CD_MAX_TAPS], kx[CD_MAX_TAPS]; };
+__global__ void pack_weight_kernel(const float* w, int O, int I, int KH, int KW, int transposed_conv, int mode,
+                                   const TapList tl, int ntaps, int round_tf32, float* packed) {
+  const int* ky = tl.ky; const int* kx = tl.kx;
+  // forward operand: packed[t][o][i] ; dgrad operand: packed[t][i][o]
+  const int N = mode == 0 ? O : I, K = mode == 0 ? I : O;
+  const long long total = static_cast<long long>(ntaps) * N * K;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % K);
+    const int n = static_cast<int>((idx / K) % N);
+    const int t = static_cast<int>(idx / (static_cast<long long>(K) * N));
+    const int o = mode == 0 ? n : k, i = mode == 0 ? k : n;
+    // reference storage: Conv2d (O,I,KH,KW); ConvTranspose2d (I,O,KH,KW)
+    const long long src = transposed_conv ? ((static_cast<long long>(i) * O + o) * KH + ky[t]) * KW + kx[t]
+                                          : ((static_cast<long long>(o) * I + i) * KH + ky[t]) * KW + kx[t];
+    float v = w[src];
+    if (round_tf32) v = cd_round_tf32(v);
+    packed[idx] = v;
+  }
+}
+__global__ void unpack_wgrad_kernel(const float* packed, int O, int I, int KH, int KW, int transposed_conv,
+                                    const TapList tl, int ntaps, float* wg, int accumulate) {
+  const int* ky = tl.ky; const int* kx = tl.kx;
+  const long long total = static_cast<long long>(ntaps) * O * I;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % I);
+    const int o = static_cast<int>((idx / I) % O);
+    const int t = static_cast<int>(idx / (static_cast<long long>(I) * O));
+    const long long dst = transposed_conv ? ((static_cast<long long>(i) * O + o) * KH + ky[t]) * KW + kx[t]
+                                          : ((static_cast<long long>(o) * I + i) * KH + ky[t]) * KW + kx[t];
+    if (accumulate) wg[dst] += packed[idx]; else wg[dst] = packed[idx];
+  }
+}
+
+}  // namespace
+
+int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st);
+
+static int conv_fwd_simt(const CdConvDesc* d, cudaStream_t st) {
+  SimtParams p{};
+  p.B = d->B; p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.Cout = d->Cout; p.nsrc = d->nsrc;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const CdConvSrc& c = d->s[s];
+    CD_REQUIRE(c.ntaps >= 1 && c.ntaps <= CD_MAX_TAPS, "conv_simt: bad ntaps");
+    p.s[s].src = c.src; p.s[s].ld = c.ld; p.s[s].C = c.C; p.s[s].H = c.H; p.s[s].W = c.W;
+    p.s[s].ntaps = c.ntaps; p.s[s].wpb = c.w_per_batch; p.s[s].w = c.w;
+    for (int t = 0; t < c.ntaps; ++t) { p.s[s].dy[t] = c.dy[t]; p.s[s].dx[t] = c.dx[t]; }
+  }
+  p.out = d->out; p.out_ld = d->out_ld; p.Ho = d->Ho; p.Wo = d->Wo; p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0;
+  p.bias = d->bias; p.resid = d->resid; p.resid_ld = d->resid_ld; p.act = d->act; p.round_tf32 = d->round_tf32;
+  p.out2 = d->out2; p.out2_ld = d->out2_ld;
+  p.tiles_per_img = cd_cdiv(d->Hg * d->Wg, TM);
+  dim3 grid(d->B * p.tiles_per_img, cd_cdiv(d->Cout, TNc));
+  conv_simt_kernel<<<grid, 256, 0, st>>>(p);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_conv_fwd(const CdConvDesc* d, int impl, void* stream) {
+  CD_REQUIRE(d != nullptr, "cd_conv_fwd: null descriptor");
+  CD_REQUIRE(d->nsrc >= 1 && d->nsrc <= 2, "cd_conv_fwd: nsrc must be 1 or 2");
+  CD_REQUIRE(d->B > 0 && d->Hg > 0 && d->Wg > 0 && d->Cout > 0, "cd_conv_fwd: empty problem");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == CD_CONV_TC) return cd_conv_fwd_tc(d, st);
+  if (impl == CD_CONV_SIMT) return conv_fwd_simt(d, st);
+  CD_FAIL("cd_conv_fwd: unknown impl %d", impl);
+}
+
+extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, float* db,
+                             int impl, void* stream) {
+  (void)impl;
+  CD_REQUIRE(d && d->nsrc == 1 && !d->s[0].w_per_batch, "cd_conv_wgrad: single shared-weight source only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const CdConvSrc& c = d->s[0];
+  WgradParams p{};
+  p.B = d->B; p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.Cout = d->Cout;
+  p.C = c.C; p.H = c.H; p.W = c.W; p.ld = c.ld; p.ntaps = c.ntaps;
+  for (int t = 0; t < c.ntaps; ++t) { p.dy[t] = c.dy[t]; p.dx[t] = c.dx[t]; }
+  p.src = c.src; p.dout = dout; p.dout_ld = dout_ld; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0; p.dw = dw;
+  const long long total = static_cast<long long>(d->B) * d->Hg * d->Wg;
+  const int tiles = cd_cdiv(d->Cout, TM) * cd_cdiv(c.C, TNc) * c.ntaps;
+  int splits = cd_cdiv(148 * 4, tiles);
+  const int max_splits = cd_cdiv(total, 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.pix_per_split = cd_cdiv(cd_cdiv(total, splits), TK) * TK;
+  dim3 grid(cd_cdiv(d->Cout, TM), cd_cdiv(c.C, TNc), c.ntaps * splits);
+  wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);
+  CD_LAUNCH_CHECK();
+  if (db) {
+    const long long rows = static_cast<long long>(d->B) * d->Ho * d->Wo;
+    CD_REQUIRE(d->oys == 1 && d->oxs == 1, "cd_conv_wgrad: bias gradient needs a dense output grid");
+    const long long rpb = 4096;
+    dim3 g2(cd_cdiv(d->Cout, 32), cd_cdiv(rows, rpb));
+    colsum_kernel<<<g2, 256, 0, st>>>(dout, dout_ld, rows, d->Cout, db, rpb);
+    CD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* stream) {
+  const long long rpb = 4096;
+  dim3 g2(cd_cdiv(C, 32), cd_cdiv(rows, rpb));
+  colsum_kernel<<<g2, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, C, out, rpb);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_pack_weight(const float* w, int O, int I, int KH, int KW, int transposed_conv, int mode,
+                              const int32_t* ky, const int32_t* kx, int ntaps, int round_tf32,
+                              float* packed, void* stream) {
+  CD_REQUIRE(ntaps >= 1 && ntaps <= CD_MAX_TAPS, "cd_pack_weight: bad ntaps");
+  TapList tl{}; for (int t = 0; t < ntaps; ++t) { tl.ky[t] = ky[t]; tl.kx[t] = kx[t]; }
+  const long long total = static_cast<long long>(ntaps) * O * I;
+  int blocks = cd_cdiv(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, O, I, KH, KW, transposed_conv, mode,
+                                                                          tl, ntaps, round_tf32, packed);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_unpack_wgrad(const float* packed, int O, int I, int KH, int KW, int transposed_conv,
+                               const int32_t* ky, const int32_t* kx, int ntaps, float* w_grad, int accumulate,
+                               void* stream) {
+  CD_REQUIRE(ntaps >= 1 && ntaps <= CD_MAX_TAPS, "cd_unpack_wgrad: bad ntaps");
+  TapList tl{}; for (int t = 0; t < ntaps; ++t) { tl.ky[t] = ky[t]; tl.kx[t] = kx[t]; }
+  const long long total = static_cast<long long>(ntaps) * O * I;
+  int blocks = cd_cdiv(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  unpack_wgrad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, O, I, KH, KW, transposed_conv,
+                                                                            tl, ntaps, w_grad, accumulate);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

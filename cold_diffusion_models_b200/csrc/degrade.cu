@@ -1,0 +1,262 @@
+// Degradation operators D(x,t) for the Gaussian-blur family and the Algorithm-2 update, the loss
+// and the fused Adam+EMA step (all HBM / on-chip bound fp32).
+//
+// Reference: every blur step is nn.Conv2d(C,C,k,groups=C,padding_mode=circular|reflect) with a
+// separable Gaussian (DB:348-389); q_sample applies steps 0..t_b sequentially on the whole batch and
+// stacks all of them (DB:927-953); x0_step_down sampling recomputes D(xhat,t) and D(xhat,t-1) from
+// scratch every step (DB:436-451).  Because each step is linear, separable and boundary-closed, the
+// cumulative degradation of one S x S plane is  A_t X A_t^T  with a precomputed S x S operator A_t
+// (host side: cold_diffusion_models_b200/degradation.py builds A_t in float64 from the fp32 taps).
+// One CTA owns one (b,c) plane: X, A_t and the intermediate live in shared memory, so HBM traffic is
+// the algorithmic minimum (read plane + operator, write plane) and D(x,t) costs two S^3 fp32 matmuls
+// regardless of t -- instead of t sequential 2-D stencils.
+#include "cd_common.cuh"
+
+namespace {
+
+// C(S x S) = A(S x S, row-major, ld = S) * Bm(S x S, row stride ldb), each thread 4x4 micro-tiles.
+// Result micro-tile (i..i+3, j..j+3) is handed to `sink(i, j, acc)`.
+template <typename Sink>
+__device__ __forceinline__ void matmul_tiles(const float* __restrict__ A, const float* __restrict__ Bm, int ldb,
+                                             int S, Sink sink) {
+  const int tj_n = S >> 2;
+  const int ntiles = tj_n * tj_n;
+  for (int tile = threadIdx.x; tile < ntiles; tile += blockDim.x) {
+    const int i0 = (tile / tj_n) * 4, j0 = (tile % tj_n) * 4;
+    float acc[4][4] = {};
+#pragma unroll 4
+    for (int k = 0; k < S; ++k) {
+      const float4 bv = *reinterpret_cast<const float4*>(Bm + k * ldb + j0);
+      const float a0 = A[(i0 + 0) * S + k], a1 = A[(i0 + 1) * S + k], a2 = A[(i0 + 2) * S + k], a3 = A[(i0 + 3) * S + k];
+      acc[0][0] = fmaf(a0, bv.x, acc[0][0]); acc[0][1] = fmaf(a0, bv.y, acc[0][1]); acc[0][2] = fmaf(a0, bv.z, acc[0][2]); acc[0][3] = fmaf(a0, bv.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, bv.x, acc[1][0]); acc[1][1] = fmaf(a1, bv.y, acc[1][1]); acc[1][2] = fmaf(a1, bv.z, acc[1][2]); acc[1][3] = fmaf(a1, bv.w, acc[1][3]);
+      acc[2][0] = fmaf(a2, bv.x, acc[2][0]); acc[2][1] = fmaf(a2, bv.y, acc[2][1]); acc[2][2] = fmaf(a2, bv.z, acc[2][2]); acc[2][3] = fmaf(a2, bv.w, acc[2][3]);
+      acc[3][0] = fmaf(a3, bv.x, acc[3][0]); acc[3][1] = fmaf(a3, bv.y, acc[3][1]); acc[3][2] = fmaf(a3, bv.z, acc[3][2]); acc[3][3] = fmaf(a3, bv.w, acc[3][3]);
+    }
+    sink(i0, j0, acc);
+  }
+}
+
+__device__ __forceinline__ void load_plane(float* dst, int ldd, const float* __restrict__ src, int S) {
+  const int nv = (S * S) >> 2;
+  const int per_row = S >> 2;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const int r = i / per_row, c = (i % per_row) * 4;
+    *reinterpret_cast<float4*>(dst + r * ldd + c) = __ldg(reinterpret_cast<const float4*>(src) + i);
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = cd_warp_sum(v);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += scratch[i];
+  return t;
+}
+
+// Z = A X A^T for one plane, result left in Zs (row stride ldp) as Z (not transposed).
+//   step 1: Yt[j][i] = (A X)[i][j]            (written transposed, padded stride)
+//   step 2: Z^T[j][i] = sum_k A[j][k] Yt[k][i] -> Zs[i][j]
+__device__ __forceinline__ void plane_apply(const float* As, const float* Xs, float* Yt, float* Zs, int S, int ldp) {
+  matmul_tiles(As, Xs, ldp, S, [&](int i0, int j0, float (&acc)[4][4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Yt[(j0 + b) * ldp + i0 + a] = acc[a][b];
+  });
+  __syncthreads();
+  matmul_tiles(As, Yt, ldp, S, [&](int j0, int i0, float (&acc)[4][4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Zs[(i0 + b) * ldp + j0 + a] = acc[a][b];
+  });
+  __syncthreads();
+}
+
+// smem layout: As[S*S] | Xs[S*ldp] | Yt[S*ldp] | scratch[32]   (Zs aliases Xs after step 1... no: Xs is
+// read only in step 1, Zs written in step 2 -> Zs = Xs)
+__global__ void __launch_bounds__(256)
+blur_apply_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ ops,
+                  const long long* __restrict__ t, int t_scalar, int S, int T, int collapse_last, int quantize) {
+  extern __shared__ __align__(16) float sm[];
+  const int ldp = S + 4;
+  float* As = sm; float* Xs = As + S * S; float* Yt = Xs + S * ldp; float* scratch = Yt + S * ldp;
+  const int plane = blockIdx.x;            // b * C + c
+  const int b = blockIdx.y;                // grid = (C, B): plane index = b * C + blockIdx.x
+  const long long pl = static_cast<long long>(b) * gridDim.x + plane;
+  const float* xp = x + pl * S * S;
+  float* op = out + pl * S * S;
+  const int idx = t ? static_cast<int>(t[b]) : t_scalar;
+  load_plane(Xs, ldp, xp, S);
+  if (idx >= 0) load_plane(As, S, ops + static_cast<long long>(idx) * S * S, S);
+  __syncthreads();
+  if (idx >= 0) plane_apply(As, Xs, Yt, Xs, S, ldp);
+  float mean = 0.f;
+  const bool collapse = collapse_last && idx == T - 1;
+  if (collapse) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) s += Xs[(i / S) * ldp + (i % S)];
+    mean = block_sum(s, scratch) / (S * S);
+  }
+  const int per_row = S >> 2;
+  for (int i = threadIdx.x; i < (S * S) >> 2; i += blockDim.x) {
+    const int r = i / per_row, c = (i % per_row) * 4;
+    float4 v = *reinterpret_cast<const float4*>(Xs + r * ldp + c);
+    if (collapse) v = make_float4(mean, mean, mean, mean);
+    if (quantize) {
+      float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {          // DB:954-958, same op order, truncation toward zero
+        float q = (f[k] + 1.f) * 0.5f;
+        q = q * 255.f;
+        q = static_cast<float>(static_cast<int>(q)) / 255.f;
+        f[k] = q * 2.f - 1.f;
+      }
+    }
+    reinterpret_cast<float4*>(op)[i] = v;
+  }
+}
+
+// out = xt - A_hi xhat A_hi^T + A_lo xhat A_lo^T   (index -1 = identity)
+__global__ void __launch_bounds__(256)
+blur_step_down_kernel(const float* __restrict__ xt, const float* __restrict__ xhat, float* __restrict__ out,
+                      const float* __restrict__ ops, int t_hi, int t_lo, int S, int T, int collapse_last) {
+  extern __shared__ __align__(16) float sm[];
+  const int ldp = S + 4;
+  float* As = sm; float* Xs = As + S * S; float* Yt = Xs + S * ldp; float* Zs = Yt + S * ldp; float* scratch = Zs + S * ldp;
+  const long long pl = static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x;
+  const float* xh = xhat + pl * S * S;
+  const int per_row = S >> 2;
+  load_plane(Xs, ldp, xh, S);
+  // ---- high index term ----
+  if (t_hi >= 0) load_plane(As, S, ops + static_cast<long long>(t_hi) * S * S, S);
+  __syncthreads();
+  if (t_hi >= 0) plane_apply(As, Xs, Yt, Zs, S, ldp);
+  else {
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) Zs[(i / S) * ldp + (i % S)] = Xs[(i / S) * ldp + (i % S)];
+    __syncthreads();
+  }
+  float mean_hi = 0.f;
+  const bool collapse = collapse_last && t_hi == T - 1;
+  if (collapse) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) s += Zs[(i / S) * ldp + (i % S)];
+    mean_hi = block_sum(s, scratch) / (S * S);
+  }
+  // d = xt - Zhi   (kept in registers: each thread owns fixed float4 slots)
+  float4 d[16];   // S <= 128: (128*128/4)/256 = 16 slots per thread
+  int nslot = 0;
+  for (int i = threadIdx.x; i < (S * S) >> 2; i += blockDim.x, ++nslot) {
+    const int r = i / per_row, c = (i % per_row) * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xt + pl * S * S) + i);
+    float4 z = *reinterpret_cast<const float4*>(Zs + r * ldp + c);
+    if (collapse) z = make_float4(mean_hi, mean_hi, mean_hi, mean_hi);
+    d[nslot] = make_float4(a.x - z.x, a.y - z.y, a.z - z.z, a.w - z.w);
+  }
+  __syncthreads();
+  // ---- low index term ----
+  if (t_lo >= 0) {
+    load_plane(As, S, ops + static_cast<long long>(t_lo) * S * S, S);
+    __syncthreads();
+    plane_apply(As, Xs, Yt, Zs, S, ldp);
+  }
+  const float* Zlo = t_lo >= 0 ? Zs : Xs;
+  nslot = 0;
+  for (int i = threadIdx.x; i < (S * S) >> 2; i += blockDim.x, ++nslot) {
+    const int r = i / per_row, c = (i % per_row) * 4;
+    const float4 z = *reinterpret_cast<const float4*>(Zlo + r * ldp + c);
+    float4 o = d[nslot];
+    o.x += z.x; o.y += z.y; o.z += z.z; o.w += z.w;
+    reinterpret_cast<float4*>(out + pl * S * S)[i] = o;
+  }
+}
+
+// ---- loss -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+loss_kernel(const float* __restrict__ x0, const float* __restrict__ xhat, long long n, int mode, float inv_n,
+            float grad_scale, float* __restrict__ loss, float* __restrict__ dxhat) {
+  __shared__ float scratch[8];
+  float s = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = xhat[i] - x0[i];
+    if (mode == 0) { s += fabsf(d); if (dxhat) dxhat[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n * grad_scale; }
+    else { s += d * d; if (dxhat) dxhat[i] = 2.f * d * inv_n * grad_scale; }
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
+}
+
+// ---- Adam (+EMA) ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                float* __restrict__ ema, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                int ema_mode, float ema_beta, float grad_scale) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;          // torch: exp_avg.lerp_(grad, 1-beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float pi = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (ema_mode == 1) ema[i] = pi;
+    else if (ema_mode == 2) ema[i] = ema[i] * ema_beta + (1.f - ema_beta) * pi;
+  }
+}
+
+}  // namespace
+
+static size_t blur_smem(int S, int planes) { return sizeof(float) * (size_t(S) * S + size_t(planes) * S * (S + 4) + 32); }
+
+extern "C" int cd_blur_apply(const float* x, float* out, const float* ops, const int64_t* t, int t_scalar,
+                             int B, int C, int S, int T, int collapse_last, int quantize, void* stream) {
+  CD_REQUIRE(S % 4 == 0 && S >= 4 && S <= 128, "cd_blur_apply: image size %d unsupported (need S%%4==0, S<=128)", S);
+  const size_t smem = blur_smem(S, 2);
+  static size_t attr = 0;
+  if (smem > attr) { CD_CUDA(cudaFuncSetAttribute(blur_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  dim3 grid(C, B);
+  blur_apply_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, out, ops, reinterpret_cast<const long long*>(t),
+                                                                          t_scalar, S, T, collapse_last, quantize);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_blur_step_down(const float* xt, const float* xhat, float* out, const float* ops,
+                                 int t_hi, int t_lo, int B, int C, int S, int T, int collapse_last, void* stream) {
+  CD_REQUIRE(S % 4 == 0 && S >= 4 && S <= 128, "cd_blur_step_down: image size %d unsupported", S);
+  const size_t smem = blur_smem(S, 3);
+  static size_t attr = 0;
+  if (smem > attr) { CD_CUDA(cudaFuncSetAttribute(blur_step_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  dim3 grid(C, B);
+  blur_step_down_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(xt, xhat, out, ops, t_hi, t_lo, S, T, collapse_last);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_loss_fwd_bwd(const float* x0, const float* xhat, int64_t n, int mode, float grad_scale,
+                               float* loss, float* dxhat, void* stream) {
+  CD_REQUIRE(mode == 0 || mode == 1, "cd_loss_fwd_bwd: mode must be 0 (l1) or 1 (l2)");
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  loss_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x0, xhat, n, mode, 1.0f / static_cast<float>(n), grad_scale, loss, dxhat);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                                float lr, float beta1, float beta2, float eps, int step,
+                                int ema_mode, float ema_beta, float grad_scale, void* stream) {
+  CD_REQUIRE(step >= 1, "cd_adam_ema_step: step counts from 1");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  adam_ema_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
+                                                                       ema_mode, ema_beta, grad_scale);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

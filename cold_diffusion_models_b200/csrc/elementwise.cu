@@ -1,0 +1,473 @@
+// HBM-bound pieces of the Unet forward (NHWC fp32): depthwise 7x7 + time-conditioning + channel
+// LayerNorm (ConvNextBlock head, DB:145,159-162,111-121), PreNorm LayerNorm (DB:123-131), the time
+// MLP (DB:91-103,209-216,140-143), the LinearAttention softmax/context reduction (DB:176-187), the
+// final 1x1 projection to image channels (DB:253) and NCHW<->NHWC boundary conversion.
+#include "cd_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// dwconv7x7 + bias + cond + LayerNorm.  One thread = 8 consecutive x-pixels x 4 channels.
+// blockDim = (C/4) * strips; LN statistics reduced across the C/4 threads of a strip.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStrip = 8;
+
+template <bool kNorm>
+__global__ void __launch_bounds__(256)
+dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C,
+                  const float* __restrict__ wdw, const float* __restrict__ bdw, const float* __restrict__ cond,
+                  const float* __restrict__ g, const float* __restrict__ beta, float eps,
+                  float* __restrict__ y, int y_ld, float* __restrict__ stats, float* __restrict__ hpre, int hpre_ld,
+                  int round_tf32) {
+  extern __shared__ float red[];                 // [strips][warps_per_strip][kStrip]
+  const int cq = C >> 2;                         // channel quads (threads per strip)
+  const int strip_in_block = threadIdx.x / cq;
+  const int q = threadIdx.x % cq;
+  const int strips_per_block = blockDim.x / cq;
+  const int strips_x = W / kStrip;
+  const long long strip = static_cast<long long>(blockIdx.x) * strips_per_block + strip_in_block;
+  const long long nstrips = static_cast<long long>(B) * H * strips_x;
+  const bool active = strip < nstrips;
+  const int sx = active ? static_cast<int>(strip % strips_x) : 0;
+  const long long rr = active ? strip / strips_x : 0;
+  const int yy = static_cast<int>(rr % H), b = static_cast<int>(rr / H);
+  const int x0 = sx * kStrip, c0 = q * 4;
+
+  float4 acc[kStrip];
+#pragma unroll
+  for (int i = 0; i < kStrip; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float* w0 = wdw + (c0 + 0) * 49; const float* w1 = wdw + (c0 + 1) * 49;
+    const float* w2 = wdw + (c0 + 2) * 49; const float* w3 = wdw + (c0 + 3) * 49;
+#pragma unroll 1
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = yy + ky - 3;
+      if (iy < 0 || iy >= H) continue;
+      float4 wv[7];
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) wv[kx] = make_float4(__ldg(w0 + ky * 7 + kx), __ldg(w1 + ky * 7 + kx),
+                                                          __ldg(w2 + ky * 7 + kx), __ldg(w3 + ky * 7 + kx));
+      const float* row = x + ((static_cast<long long>(b) * H + iy) * W) * x_ld + c0;
+#pragma unroll
+      for (int ix = 0; ix < kStrip + 6; ++ix) {
+        const int gx = x0 + ix - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < W) v = *reinterpret_cast<const float4*>(row + static_cast<long long>(gx) * x_ld);
+#pragma unroll
+        for (int ox = 0; ox < kStrip; ++ox) {
+          const int kx = ix - ox;
+          if (kx >= 0 && kx < 7) {
+            acc[ox].x = fmaf(v.x, wv[kx].x, acc[ox].x); acc[ox].y = fmaf(v.y, wv[kx].y, acc[ox].y);
+            acc[ox].z = fmaf(v.z, wv[kx].z, acc[ox].z); acc[ox].w = fmaf(v.w, wv[kx].w, acc[ox].w);
+          }
+        }
+      }
+    }
+    float4 add = *reinterpret_cast<const float4*>(bdw + c0);
+    if (cond) {
+      const float4 cv = *reinterpret_cast<const float4*>(cond + static_cast<long long>(b) * C + c0);
+      add.x += cv.x; add.y += cv.y; add.z += cv.z; add.w += cv.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kStrip; ++i) { acc[i].x += add.x; acc[i].y += add.y; acc[i].z += add.z; acc[i].w += add.w; }
+  }
+  const long long pix0 = (static_cast<long long>(b) * H + yy) * W + x0;
+  if (hpre && active) {
+#pragma unroll
+    for (int i = 0; i < kStrip; ++i) *reinterpret_cast<float4*>(hpre + (pix0 + i) * hpre_ld + c0) = acc[i];
+  }
+  if (kNorm) {
+    // two-pass statistics over the C channels of each of the kStrip pixels
+    const int width = cq < 32 ? cq : 32;           // lanes sharing a strip inside a warp
+    const int wps = (cq + 31) / 32;                // warps per strip
+    const int warp_in_strip = q >> 5;
+    float mean[kStrip], rstd[kStrip];
+    for (int pass = 0; pass < 2; ++pass) {
+      float part[kStrip];
+#pragma unroll
+      for (int i = 0; i < kStrip; ++i) {
+        float s;
+        if (pass == 0) s = acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+        else {
+          const float a = acc[i].x - mean[i], bb = acc[i].y - mean[i], c = acc[i].z - mean[i], d = acc[i].w - mean[i];
+          s = a * a + bb * bb + c * c + d * d;
+        }
+        for (int o = width >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        part[i] = s;
+      }
+      if (wps > 1) {
+        __syncthreads();
+        if ((q & 31) == 0) {
+#pragma unroll
+          for (int i = 0; i < kStrip; ++i) red[(strip_in_block * wps + warp_in_strip) * kStrip + i] = part[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kStrip; ++i) {
+          float s = 0.f;
+          for (int w = 0; w < wps; ++w) s += red[(strip_in_block * wps + w) * kStrip + i];
+          part[i] = s;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kStrip; ++i) {
+        if (pass == 0) mean[i] = part[i] / C;
+        else rstd[i] = rsqrtf(part[i] / C + eps);
+      }
+    }
+    if (active) {
+      const float4 gv = *reinterpret_cast<const float4*>(g + c0);
+      const float4 bv = *reinterpret_cast<const float4*>(beta + c0);
+#pragma unroll
+      for (int i = 0; i < kStrip; ++i) {
+        float4 o;
+        o.x = (acc[i].x - mean[i]) * rstd[i] * gv.x + bv.x; o.y = (acc[i].y - mean[i]) * rstd[i] * gv.y + bv.y;
+        o.z = (acc[i].z - mean[i]) * rstd[i] * gv.z + bv.z; o.w = (acc[i].w - mean[i]) * rstd[i] * gv.w + bv.w;
+        if (round_tf32) { o.x = cd_round_tf32(o.x); o.y = cd_round_tf32(o.y); o.z = cd_round_tf32(o.z); o.w = cd_round_tf32(o.w); }
+        *reinterpret_cast<float4*>(y + (pix0 + i) * y_ld + c0) = o;
+        if (stats && q == 0) { stats[(pix0 + i) * 2] = mean[i]; stats[(pix0 + i) * 2 + 1] = rstd[i]; }
+      }
+    }
+  } else if (active) {
+#pragma unroll
+    for (int i = 0; i < kStrip; ++i) {
+      float4 o = acc[i];
+      if (round_tf32) { o.x = cd_round_tf32(o.x); o.y = cd_round_tf32(o.y); o.z = cd_round_tf32(o.z); o.w = cd_round_tf32(o.w); }
+      *reinterpret_cast<float4*>(y + (pix0 + i) * y_ld + c0) = o;
+    }
+  }
+}
+
+// generic (any C, e.g. the 1/3-channel image): one thread per pixel, loops channels; LN optional.
+__global__ void dwconv7_small_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C,
+                                     const float* __restrict__ wdw, const float* __restrict__ bdw,
+                                     const float* __restrict__ cond, const float* __restrict__ g,
+                                     const float* __restrict__ beta, float eps, float* __restrict__ y, int y_ld,
+                                     float* __restrict__ stats, float* __restrict__ hpre, int hpre_ld, int round_tf32) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long npix = static_cast<long long>(B) * H * W;
+  if (pix >= npix) return;
+  const int xx = static_cast<int>(pix % W);
+  const int yy = static_cast<int>((pix / W) % H);
+  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  float hbuf[16];
+  float mean = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float a = bdw[c] + (cond ? cond[static_cast<long long>(b) * C + c] : 0.f);
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = yy + ky - 3;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = xx + kx - 3;
+        if (ix < 0 || ix >= W) continue;
+        a = fmaf(x[((static_cast<long long>(b) * H + iy) * W + ix) * x_ld + c], wdw[c * 49 + ky * 7 + kx], a);
+      }
+    }
+    hbuf[c] = a; mean += a;
+    if (hpre) hpre[pix * hpre_ld + c] = a;
+  }
+  if (g) {
+    mean /= C;
+    float var = 0.f;
+    for (int c = 0; c < C; ++c) var += (hbuf[c] - mean) * (hbuf[c] - mean);
+    const float rstd = rsqrtf(var / C + eps);
+    for (int c = 0; c < C; ++c) hbuf[c] = (hbuf[c] - mean) * rstd * g[c] + beta[c];
+    if (stats) { stats[pix * 2] = mean; stats[pix * 2 + 1] = rstd; }
+  }
+  for (int c = 0; c < C; ++c) y[pix * y_ld + c] = round_tf32 ? cd_round_tf32(hbuf[c]) : hbuf[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel LayerNorm: one warp per pixel, channels held in registers (C <= 1024, C % 4 == 0)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int x_ld, long long npix, int C, const float* __restrict__ g,
+                 const float* __restrict__ beta, float eps, float* __restrict__ y, int y_ld,
+                 float* __restrict__ stats, int round_tf32) {
+  const long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int lane = threadIdx.x & 31;
+  const int nq = C >> 2;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int qd = lane + i * 32;
+    if (qd < nq) { v[i] = *reinterpret_cast<const float4*>(x + pix * x_ld + qd * 4); s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  }
+  const float mean = cd_warp_sum(s) / C;
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int qd = lane + i * 32;
+    if (qd < nq) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      s2 += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(cd_warp_sum(s2) / C + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int qd = lane + i * 32;
+    if (qd < nq) {
+      const float4 gv = *reinterpret_cast<const float4*>(g + qd * 4);
+      const float4 bv = *reinterpret_cast<const float4*>(beta + qd * 4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gv.x + bv.x; o.y = (v[i].y - mean) * rstd * gv.y + bv.y;
+      o.z = (v[i].z - mean) * rstd * gv.z + bv.z; o.w = (v[i].w - mean) * rstd * gv.w + bv.w;
+      if (round_tf32) { o.x = cd_round_tf32(o.x); o.y = cd_round_tf32(o.y); o.z = cd_round_tf32(o.z); o.w = cd_round_tf32(o.w); }
+      *reinterpret_cast<float4*>(y + pix * y_ld + qd * 4) = o;
+    }
+  }
+  if (stats && lane == 0) { stats[pix * 2] = mean; stats[pix * 2 + 1] = rstd; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// time MLP: one block per batch element
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+time_mlp_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ w1, const float* __restrict__ b1,
+                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ wc,
+                const float* __restrict__ bc, int sumC, float* __restrict__ sinemb, float* __restrict__ hid_pre,
+                float* __restrict__ temb, float* __restrict__ cond_all) {
+  extern __shared__ float sm[];          // emb[dim] | hid[4dim] | gt[dim]
+  float* emb = sm; float* hid = sm + dim; float* gt = hid + 4 * dim;
+  const int b = blockIdx.x;
+  const float tv = static_cast<float>(t[b]);
+  const int half = dim / 2;
+  const float k = logf(10000.f) / (half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf(-k * i);
+    const float a = tv * f;
+    emb[i] = sinf(a); emb[i + half] = cosf(a);
+  }
+  __syncthreads();
+  if (sinemb) for (int i = threadIdx.x; i < dim; i += blockDim.x) sinemb[b * dim + i] = emb[i];
+  for (int o = threadIdx.x; o < 4 * dim; o += blockDim.x) {
+    float a = b1[o];
+    for (int i = 0; i < dim; ++i) a = fmaf(w1[o * dim + i], emb[i], a);
+    if (hid_pre) hid_pre[b * 4 * dim + o] = a;
+    hid[o] = cd_gelu(a);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < dim; o += blockDim.x) {
+    float a = b2[o];
+    for (int i = 0; i < 4 * dim; ++i) a = fmaf(w2[o * 4 * dim + i], hid[i], a);
+    temb[b * dim + o] = a;
+    gt[o] = cd_gelu(a);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < sumC; o += blockDim.x) {
+    float a = bc[o];
+    for (int i = 0; i < dim; ++i) a = fmaf(wc[static_cast<long long>(o) * dim + i], gt[i], a);
+    cond_all[static_cast<long long>(b) * sumC + o] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LinearAttention: k-softmax statistics and context.  qkv NHWC [B][n][ld], q|k|v at 0|128|256.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  // valid for any sign mix: positive floats order as ints, negative floats order reversed as uints
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256)
+kmax_kernel(const float* __restrict__ qkv, int ld, int n, int pix_per_block, float* __restrict__ kmax) {
+  const int b = blockIdx.y;
+  const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int p0 = blockIdx.x * pix_per_block;
+  int p1 = p0 + pix_per_block; if (p1 > n) p1 = n;
+  float m = -INFINITY;
+  for (int p = p0 + half; p < p1; p += 2) m = fmaxf(m, qkv[(static_cast<long long>(b) * n + p) * ld + 128 + c]);
+  atomic_max_float(kmax + b * 128 + c, m);
+}
+
+constexpr int kCtxP = 32;   // pixels per smem chunk
+__global__ void __launch_bounds__(256)
+context_kernel(const float* __restrict__ qkv, int ld, int n, int pix_per_block, const float* __restrict__ kmax,
+               float* __restrict__ ksum, float* __restrict__ ctx) {
+  __shared__ float es[kCtxP][128];
+  __shared__ float vs[kCtxP][128];
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  int p1 = p0 + pix_per_block; if (p1 > n) p1 = n;
+  const int tid = threadIdx.x;
+  const int h = tid >> 6, d4 = ((tid & 63) >> 3) * 4, e4 = (tid & 7) * 4;
+  const int lc = tid & 127, lhalf = tid >> 7;
+  const float mx = kmax[b * 128 + lc];
+  float acc[4][4] = {};
+  float esum = 0.f;
+  for (int q0 = p0; q0 < p1; q0 += kCtxP) {
+    for (int pp = lhalf; pp < kCtxP; pp += 2) {
+      const int p = q0 + pp;
+      float e = 0.f, v = 0.f;
+      if (p < p1) {
+        const float* row = qkv + (static_cast<long long>(b) * n + p) * ld;
+        e = __expf(row[128 + lc] - mx);
+        v = row[256 + lc];
+      }
+      es[pp][lc] = e; vs[pp][lc] = v; esum += e;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = 0; pp < kCtxP; ++pp) {
+      const float4 ev = *reinterpret_cast<const float4*>(&es[pp][h * 32 + d4]);
+      const float4 vv = *reinterpret_cast<const float4*>(&vs[pp][h * 32 + e4]);
+      const float e[4] = {ev.x, ev.y, ev.z, ev.w}, v[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(e[i], v[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  atomicAdd(ksum + b * 128 + lc, esum);
+  float* cb = ctx + (static_cast<long long>(b) * 4 + h) * 1024;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(cb + (d4 + i) * 32 + e4 + j, acc[i][j]);
+}
+
+// weff[b][co][h*32+d] = scale * sum_e w_out[co][h*32+e] * ctx[b][h][d][e] / ksum[b][h*32+d]
+__global__ void weff_kernel(const float* __restrict__ ctx, const float* __restrict__ ksum, const float* __restrict__ w_out,
+                            int dim, float scale, int round_tf32, float* __restrict__ weff) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dim * 128) return;
+  const int co = idx >> 7, hd = idx & 127, h = hd >> 5, d = hd & 31;
+  const float* crow = ctx + ((static_cast<long long>(b) * 4 + h) * 32 + d) * 32;
+  const float* wrow = w_out + co * 128 + h * 32;
+  float a = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) a = fmaf(wrow[e], crow[e], a);
+  a = a * scale / ksum[b * 128 + hd];
+  weff[(static_cast<long long>(b) * dim + co) * 128 + hd] = round_tf32 ? cd_round_tf32(a) : a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// final 1x1 conv to image channels, NHWC -> NCHW; and NCHW -> NHWC (padded ld) input conversion
+// ---------------------------------------------------------------------------------------------
+__global__ void conv1x1_to_nchw_kernel(const float* __restrict__ x, int ld, int B, int HW, int C,
+                                       const float* __restrict__ w, const float* __restrict__ bias, int Co,
+                                       const float* __restrict__ resid, float* __restrict__ out) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= static_cast<long long>(B) * HW) return;
+  const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
+  const float* row = x + pix * ld;
+  for (int co = 0; co < Co; ++co) {
+    float a = bias ? bias[co] : 0.f;
+    for (int c = 0; c < C; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      const float4 wv = *reinterpret_cast<const float4*>(w + co * C + c);
+      a = fmaf(v.x, wv.x, a); a = fmaf(v.y, wv.y, a); a = fmaf(v.z, wv.z, a); a = fmaf(v.w, wv.w, a);
+    }
+    const long long o = (static_cast<long long>(b) * Co + co) * HW + p;
+    if (resid) a += resid[o];
+    out[o] = a;
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ out, int ld) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= static_cast<long long>(B) * HW) return;
+  const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
+  for (int c = 0; c < ld; ++c) out[pix * ld + c] = c < C ? x[(static_cast<long long>(b) * C + c) * HW + p] : 0.f;
+}
+
+}  // namespace
+
+extern "C" int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, int C,
+                                 const float* w_dw, const float* b_dw, const float* cond,
+                                 const float* g, const float* beta, float eps, float* y, int y_ld,
+                                 float* stats, float* hpre, int hpre_ld, int round_tf32, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cq = C / 4;
+  const bool fast = (C % 4 == 0) && cq >= 8 && cq <= 256 && (cq & (cq - 1)) == 0 && (W % kStrip == 0) &&
+                    (x_ld % 4 == 0) && (y_ld % 4 == 0) && (!hpre || hpre_ld % 4 == 0);
+  if (fast) {
+    const int strips_per_block = 256 / cq;
+    const long long nstrips = static_cast<long long>(B) * H * (W / kStrip);
+    const int blocks = cd_cdiv(nstrips, strips_per_block);
+    const size_t smem = sizeof(float) * strips_per_block * ((cq + 31) / 32) * kStrip;
+    if (g) dwconv7_ln_kernel<true><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+    else dwconv7_ln_kernel<false><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+  } else {
+    CD_REQUIRE(C <= 16, "cd_dwconv7_ln_fwd: unsupported channel count %d (W=%d)", C, W);
+    const long long npix = static_cast<long long>(B) * H * W;
+    dwconv7_small_kernel<<<cd_cdiv(npix, 128), 128, 0, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+  }
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
+                                float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream) {
+  CD_REQUIRE(C % 4 == 0 && C <= 1024 && x_ld % 4 == 0 && y_ld % 4 == 0, "cd_layernorm_fwd: unsupported C=%d", C);
+  layernorm_kernel<<<cd_cdiv(npix, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_ld, npix, C, g, beta, eps, y, y_ld, stats, round_tf32);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_time_mlp_fwd(const int64_t* t, int B, int dim, const float* w1, const float* b1,
+                               const float* w2, const float* b2, const float* wc, const float* bc, int sumC,
+                               float* sinemb, float* hid_pre, float* temb, float* cond_all, void* stream) {
+  const size_t smem = sizeof(float) * 6 * dim;
+  time_mlp_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(t), dim, w1, b1, w2, b2,
+                                                                     wc, bc, sumC, sinemb, hid_pre, temb, cond_all);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_linattn_context(const float* qkv, int ld, int B, int n, float* kmax, float* ksum, float* ctx,
+                                  void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // kmax starts at -inf, ksum/ctx at zero (async memsets: stream-ordered and graph-capturable)
+  CD_CUDA(cudaMemsetAsync(ksum, 0, sizeof(float) * B * 128, st));
+  CD_CUDA(cudaMemsetAsync(ctx, 0, sizeof(float) * B * 4096, st));
+  {
+    typedef CUresult (*MemsetD32Async)(CUdeviceptr, unsigned int, size_t, CUstream);
+    static MemsetD32Async fn = nullptr;
+    if (!fn) {
+      void* p = nullptr; cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuMemsetD32Async", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        fn = reinterpret_cast<MemsetD32Async>(p);
+    }
+    CD_REQUIRE(fn != nullptr, "cuMemsetD32Async unavailable");
+    CD_REQUIRE(fn(reinterpret_cast<CUdeviceptr>(kmax), 0xFF800000u, static_cast<size_t>(B) * 128, st) == CUDA_SUCCESS,
+               "cuMemsetD32Async failed");
+  }
+  int ppb = 512; if (ppb > n) ppb = n;
+  dim3 grid(cd_cdiv(n, ppb), B);
+  kmax_kernel<<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax);
+  CD_LAUNCH_CHECK();
+  context_kernel<<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax, ksum, ctx);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_linattn_weff(const float* ctx, const float* ksum, const float* w_out, int B, int dim, float scale,
+                               int round_tf32, float* weff, void* stream) {
+  dim3 grid(cd_cdiv(dim * 128, 256), B);
+  weff_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx, ksum, w_out, dim, scale, round_tf32, weff);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_conv1x1_to_nchw(const float* x, int ld, int B, int H, int W, int C, const float* w,
+                                  const float* b, int Co, const float* resid_nchw, float* out_nchw, void* stream) {
+  CD_REQUIRE(C % 4 == 0 && ld % 4 == 0, "cd_conv1x1_to_nchw: C must be a multiple of 4");
+  const long long npix = static_cast<long long>(B) * H * W;
+  conv1x1_to_nchw_kernel<<<cd_cdiv(npix, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, B, H * W, C, w, b, Co, resid_nchw, out_nchw);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* out, int ld, void* stream) {
+  const long long npix = static_cast<long long>(B) * H * W;
+  nchw_to_nhwc_kernel<<<cd_cdiv(npix, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, B, C, H * W, out, ld);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

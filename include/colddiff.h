@@ -1,0 +1,169 @@
+/*
+ * colddiff.h -- C ABI of libcolddiff.so: the B200 (sm_100a) engine behind the Cold-Diffusion
+ * hot path (GaussianDiffusion.p_losses training step + x0_step_down / ddim sampling around the
+ * UNet restoration operator R(x,t) and the degradation operators D(x,t)).
+ *
+ * The upstream reference (arpitbansal297/Cold-Diffusion-Models) is pure Python/PyTorch and has NO
+ * FFI / plugin interface of its own.  The boundary callers depend on is the
+ * Python class surface of each *_diffusion_pytorch package; cold_diffusion_models_b200/ mirrors
+ * that surface and calls the entry points below through ctypes.  Every entry point cites the
+ * reference code it replaces (DB = deblurring-diffusion-pytorch/deblurring_diffusion_pytorch/
+ * deblurring_diffusion_pytorch.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - the library never allocates device memory and never synchronises: the caller passes
+ *     outputs/workspaces (torch caching allocator) and a cudaStream_t (as void*);
+ *   - return value: 0 = ok, <0 = error (text via cd_last_error); no exceptions cross the ABI;
+ *   - activations inside the engine are NHWC fp32 ("pixel rows" of `ld` floats, channel slice
+ *     selected by offsetting the base pointer); reference-facing images are NCHW fp32;
+ *   - no global mutable state except a per-process cache of the driver entry point used to
+ *     encode TMA descriptors.
+ */
+#ifndef COLDDIFF_H_
+#define COLDDIFF_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CD_ABI_VERSION 1
+#define CD_MAX_TAPS 16
+
+int cd_version(void);
+/* copies the calling thread's last error text; returns its length */
+int cd_last_error(char* buf, size_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense convolution as an implicit GEMM over a "tap list" (replaces nn.Conv2d 3x3 / 1x1 /
+ * 4x4 stride 2 and nn.ConvTranspose2d 4x4 stride 2 in Unet: DB:105-109,149-154,173-174,253;
+ * also their data-gradients, which are the same contraction with transposed/flipped weights).
+ *
+ *   out[b, gy*oys+oy0, gx*oxs+ox0, co] = act( bias[co] + resid[...] +
+ *        sum_{s<nsrc} sum_{t<ntaps[s]} sum_{ci<C[s]}
+ *            src[s][b, gy*sy+dy[s][t], gx*sx+dx[s][t], ci] * w[s][(b*wb) , t, co, ci] )
+ *   for (gy,gx) in the Hg x Wg GEMM pixel grid; reads outside the source image are zero.
+ *
+ * impl: CD_CONV_TC = tcgen05/TMA tensor-core kernel (kind::tf32, fp32 accumulate in TMEM;
+ *       needs C[s] % 32 == 0 and 16-byte aligned rows), CD_CONV_SIMT = fp32 CUDA-core kernel
+ *       (any shape; used for 3-channel image edges and as the on-device cross-check).
+ * ------------------------------------------------------------------------------------------ */
+enum { CD_CONV_SIMT = 0, CD_CONV_TC = 1 };
+enum { CD_ACT_NONE = 0, CD_ACT_GELU = 1 };
+
+typedef struct {
+  const float* src;       /* NHWC base of the channel slice                         */
+  int32_t ld;             /* floats between consecutive pixels                      */
+  int32_t C;              /* channels contracted from this source                   */
+  int32_t H, W;           /* source image size                                      */
+  int32_t ntaps;
+  int32_t dy[CD_MAX_TAPS], dx[CD_MAX_TAPS];
+  const float* w;         /* packed weights [wb? B:1][ntaps][Cout][C], C contiguous */
+  int32_t w_per_batch;    /* 1: a separate weight set per batch element             */
+} CdConvSrc;
+
+typedef struct {
+  int32_t B, Hg, Wg;      /* GEMM pixel grid                                        */
+  int32_t sy, sx;         /* source stride                                          */
+  int32_t Cout;
+  int32_t nsrc;
+  CdConvSrc s[2];
+  float* out; int32_t out_ld; int32_t Ho, Wo;
+  int32_t oys, oxs, oy0, ox0;
+  const float* bias;      /* [Cout] or NULL                                         */
+  const float* resid; int32_t resid_ld; /* same pixel mapping as out, or NULL       */
+  int32_t act;
+  int32_t round_tf32;     /* round outputs to TF32 (RN) so the next TC conv sees RN operands */
+  float* out2; int32_t out2_ld; /* optional second output: the pre-activation (for backward) */
+} CdConvDesc;
+
+int cd_conv_fwd(const CdConvDesc* d, int impl, void* stream);
+
+/* weight-gradient of the same contraction (single source, single weight set):
+ *   dw[t, co, ci] (+)= sum_{b,gy,gx} dout[b, gy*oys+oy0, gx*oxs+ox0, co] * src[b, gy*sy+dy[t], gx*sx+dx[t], ci]
+ * dw is the packed [ntaps][Cout][C] layout; accumulate!=0 adds into dw (else dw must be zeroed by
+ * the caller; the kernel uses atomics across pixel splits). db (optional) += sum dout.           */
+int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, float* db,
+                  int impl, void* stream);
+
+/* repack reference-layout weights: OIHW (transposed_conv=0) or IOHW (nn.ConvTranspose2d,
+ * transposed_conv=1) -> packed [tap][N][K].  mode 0: forward operand (N=out ch, K=in ch);
+ * mode 1: data-gradient operand (N=in ch, K=out ch). Tap order is given by (ky,kx) lists.     */
+int cd_pack_weight(const float* w, int O, int I, int KH, int KW, int transposed_conv, int mode,
+                   const int32_t* ky, const int32_t* kx, int ntaps, int round_tf32,
+                   float* packed, void* stream);
+/* inverse for gradients: packed [tap][O][I] -> OIHW / IOHW (accumulating) */
+int cd_unpack_wgrad(const float* packed, int O, int I, int KH, int KW, int transposed_conv,
+                    const int32_t* ky, const int32_t* kx, int ntaps, float* w_grad, int accumulate,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ConvNeXt block front half (DB:145, 140-143/159-162, 111-121/148):
+ *   y = LayerNorm_c( dwconv7x7(x) + b_dw + cond[b,:] ) * g + beta      (norm / cond optional)
+ * x,y NHWC. x_nchw!=0: x is the reference-layout NCHW image (first block, C = image channels).
+ * stats (optional, [B*H*W][2] = mean, rstd) is saved for backward; h_pre (optional) the
+ * pre-norm value.
+ * ------------------------------------------------------------------------------------------ */
+int cd_dwconv7_ln_fwd(const float* x, int x_ld, int x_nchw, int B, int H, int W, int C,
+                      const float* w_dw /*[C][49]*/, const float* b_dw /*[C]*/,
+                      const float* cond /*[B][C] or NULL*/,
+                      const float* g, const float* beta /*[C] or NULL: no norm*/,
+                      float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream);
+
+/* channel LayerNorm alone (PreNorm in front of LinearAttention, DB:123-131) */
+int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
+                     float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream);
+
+/* time embedding (DB:91-103, 209-216) + every block's GELU->Linear conditioning (DB:140-143):
+ *   temb = W2 gelu(W1 sinemb(t) + b1) + b2 ; cond_all[b, :] = Wc gelu(temb[b]) + bc
+ * Wc/bc are the row-concatenation of all blocks' mlp.1 weights ([sumC][dim]).               */
+int cd_time_mlp_fwd(const int64_t* t, int B, int dim, const float* w1, const float* b1,
+                    const float* w2, const float* b2, const float* wc, const float* bc, int sumC,
+                    float* sinemb /*[B][dim]*/, float* hid_pre /*[B][4dim]*/, float* temb /*[B][dim]*/,
+                    float* cond_all /*[B][sumC]*/, void* stream);
+
+/* LinearAttention core (DB:176-187) on qkv NHWC [B][n][384] (q|k|v, head-major 4x32):
+ *   ctx[b,h,d,e] = sum_n softmax_n(k[b,h,d,:])[n] * v[b,h,e,n]
+ *   weff[b, co, h*32+d] = scale * sum_e w_out[co, h*32+e] * ctx[b,h,d,e]
+ * so that to_out(out) == conv1x1(q, weff[b]) (a per-batch-weight tap-list convolution).
+ * kmax/ksum ([B][128]) are saved for backward.                                              */
+int cd_linattn_context(const float* qkv, int ld, int B, int n, float* kmax, float* ksum,
+                       float* ctx /*[B][4][32][32]*/, void* stream);
+int cd_linattn_weff(const float* ctx, const float* w_out /*[dim][128]*/, int B, int dim, float scale,
+                    int round_tf32, float* weff /*[B][dim][128]*/, void* stream);
+
+/* final 1x1 conv to image channels + optional residual, NHWC -> reference NCHW (DB:253,279-282) */
+int cd_conv1x1_to_nchw(const float* x, int ld, int B, int H, int W, int C, const float* w /*[Co][C]*/,
+                       const float* b, int Co, const float* resid_nchw, float* out_nchw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Degradation D(x,t) for the Gaussian-blur family (DB:348-389 kernels; DB:927-960 q_sample;
+ * DB:436-451 Algorithm-2 update).  Every blur step is separable with circular or reflect
+ * boundary handling, hence the cumulative degradation of a plane X is  A_t X A_t^T  with a
+ * precomputed S x S operator per step (ops: [T][S][S], row-major, ops[t] = K_t ... K_0).
+ *   cd_blur_apply     : out[b,c] = A_{t_b} x[b,c] A_{t_b}^T    (t_b < 0: copy)  -- q_sample / opt
+ *   cd_blur_step_down : out = x_t - A_t xhat A_t^T + A_{t-1} xhat A_{t-1}^T    -- DB:451
+ * Images are reference-layout NCHW planes.  collapse_last: `discrete` mean-collapse for the
+ * last operator index (DB:938-940); quantize: 8-bit truncation (DB:954-958).
+ * ------------------------------------------------------------------------------------------ */
+int cd_blur_apply(const float* x, float* out, const float* ops, const int64_t* t, int t_scalar,
+                  int B, int C, int S, int T, int collapse_last, int quantize, void* stream);
+int cd_blur_step_down(const float* xt, const float* xhat, float* out, const float* ops,
+                      int t_hi, int t_lo, int B, int C, int S, int T, int collapse_last, void* stream);
+
+/* loss (DB:968-971): mode 0 = L1 mean, 1 = L2 mean; writes *loss (device) and dL/dxhat*scale */
+int cd_loss_fwd_bwd(const float* x0, const float* xhat, int64_t n, int mode, float grad_scale,
+                    float* loss /*device scalar, accumulated*/, float* dxhat, void* stream);
+
+/* Adam (torch defaults, DB:1117) + EMA (DB:73-81) fused multi-tensor step on flat buffers */
+int cd_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                     float lr, float beta1, float beta2, float eps, int step,
+                     int ema_mode /*0 none,1 copy,2 lerp*/, float ema_beta, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLDDIFF_H_ */

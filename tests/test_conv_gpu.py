@@ -1,0 +1,184 @@
+"""GPU parity of the tap-list convolution (tcgen05 TC path and fp32 SIMT path) through the C ABI,
+against torch's fp64 CPU convolution on identical inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32_rn(x):
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def nhwc(x):   # NCHW -> contiguous [B,H,W,C]
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from cold_diffusion_models_b200 import ops
+    return ops
+
+
+CASES = [
+    # (B, Cin, Cout, H, W, k, pad)
+    (2, 64, 128, 32, 32, 3, 1),
+    (1, 64, 64, 128, 128, 3, 1),
+    (3, 256, 512, 16, 16, 3, 1),
+    (4, 64, 64, 8, 8, 3, 1),
+    (2, 128, 96, 16, 16, 1, 0),
+    (2, 32, 384, 32, 32, 1, 0),
+    (5, 64, 64, 4, 4, 3, 1),
+]
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('case', CASES)
+def test_conv_stride1(ops, case, impl):
+    B, Ci, Co, H, W, k, pad = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = tf32_rn(torch.randn(B, Ci, H, W, generator=g))
+    w = tf32_rn(torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5)
+    b = torch.randn(Co, generator=g)
+    r = torch.randn(B, Co, H, W, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=pad) + r.double()
+    ref_act = F.gelu(ref)
+    xd, wd, bd, rd = nhwc(x).cuda(), w.cuda(), b.cuda(), nhwc(r).cuda()
+    taps = ops.taps_conv(k, pad)
+    pw = ops.pack_weight(wd, taps, round_tf32=False)
+    out = torch.empty(B, H, W, Co, device='cuda')
+    pre = torch.empty(B, H, W, Co, device='cuda')
+    d = ops.make_conv_desc([(ops.View(xd), taps, pw, False)], ops.View(out), (B, H, W), Cout=Co, bias=bd,
+                           resid=ops.View(rd), act=ops.ACT_GELU, out2=ops.View(pre))
+    ops.conv_fwd(d, ops.CONV_TC if impl == 'tc' else ops.CONV_SIMT)
+    torch.cuda.synchronize()
+    assert rel(nchw(pre.cpu()), ref) < 1e-5
+    assert rel(nchw(out.cpu()), ref_act) < 1e-5
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_conv_two_sources_channel_slices(ops, impl):
+    """3x3 over h plus the 1x1 res_conv over x accumulated in one GEMM (ConvNextBlock tail, DB:151-154,164);
+    sources/outputs are channel slices of wider NHWC buffers."""
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C1, C2, Co = 2, 16, 16, 128, 64, 64
+    hbuf = tf32_rn(torch.randn(B, H, W, C1 + 32, generator=g))
+    xbuf = tf32_rn(torch.randn(B, H, W, C2 + 64, generator=g))
+    w1 = tf32_rn(torch.randn(Co, C1, 3, 3, generator=g) * 0.03)
+    w2 = tf32_rn(torch.randn(Co, C2, 1, 1, generator=g) * 0.1)
+    bias = torch.randn(Co, generator=g)
+    h = hbuf[..., 32:].permute(0, 3, 1, 2).double()
+    x = xbuf[..., 64:].permute(0, 3, 1, 2).double()
+    ref = F.conv2d(h, w1.double(), bias.double(), padding=1) + F.conv2d(x, w2.double())
+    hd, xd = hbuf.cuda(), xbuf.cuda()
+    t3, t1 = ops.taps_conv(3, 1), ops.taps_conv(1, 0)
+    p1, p2 = ops.pack_weight(w1.cuda(), t3, round_tf32=False), ops.pack_weight(w2.cuda(), t1, round_tf32=False)
+    obuf = torch.zeros(B, H, W, 2 * Co, device='cuda')
+    d = ops.make_conv_desc([(ops.View(hd, 32, C1), t3, p1, False), (ops.View(xd, 64, C2), t1, p2, False)],
+                           ops.View(obuf, Co, Co), (B, H, W), Cout=Co, bias=bias.cuda(), round_tf32=True)
+    ops.conv_fwd(d, ops.CONV_TC if impl == 'tc' else ops.CONV_SIMT)
+    torch.cuda.synchronize()
+    o = obuf.cpu()
+    assert o[..., :Co].abs().max() == 0
+    got = o[..., Co:].permute(0, 3, 1, 2)
+    assert rel(got, ref) < 4e-4                      # output rounded to TF32
+    assert torch.equal(got, tf32_rn(got))
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_conv_4x4_stride2_and_transpose(ops, impl):
+    """Downsample nn.Conv2d(C,C,4,2,1) (DB:108-109) via strided TMA boxes and Upsample
+    nn.ConvTranspose2d(C,C,4,2,1) (DB:105-106) as four output-parity tap lists."""
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W = 2, 64, 32, 32
+    im = ops.CONV_TC if impl == 'tc' else ops.CONV_SIMT
+    x = tf32_rn(torch.randn(B, C, H, W, generator=g))
+    w = tf32_rn(torch.randn(C, C, 4, 4, generator=g) / (C * 16) ** 0.5)
+    b = torch.randn(C, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1)
+    xd = nhwc(x).cuda()
+    taps = ops.taps_conv(4, 1)
+    pw = ops.pack_weight(w.cuda(), taps, round_tf32=False)
+    out = torch.empty(B, H // 2, W // 2, C, device='cuda')
+    d = ops.make_conv_desc([(ops.View(xd), taps, pw, False)], ops.View(out), (B, H // 2, W // 2), stride=2,
+                           Cout=C, bias=b.cuda())
+    ops.conv_fwd(d, im)
+    torch.cuda.synchronize()
+    assert rel(nchw(out.cpu()), ref) < 3e-6
+    # transpose conv: weight layout (in, out, 4, 4)
+    wt = tf32_rn(torch.randn(C, C, 4, 4, generator=g) / (C * 4) ** 0.5)
+    reft = F.conv_transpose2d(x.double(), wt.double(), b.double(), stride=2, padding=1)
+    outt = torch.empty(B, 2 * H, 2 * W, C, device='cuda')
+    for py in (0, 1):
+        for px in (0, 1):
+            tp = ops.taps_convT4_parity(py, px)
+            pwt = ops.pack_weight(wt.cuda(), tp, transposed_conv=True, round_tf32=False)
+            d = ops.make_conv_desc([(ops.View(xd), tp, pwt, False)], ops.View(outt), (B, H, W), Cout=C,
+                                   bias=b.cuda(), out_map=(2, 2, py, px))
+            ops.conv_fwd(d, im)
+    torch.cuda.synchronize()
+    assert rel(nchw(outt.cpu()), reft) < 3e-6
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_conv_per_batch_weights(ops, impl):
+    """to_out(einsum(context, q)) folded into a per-batch 1x1 convolution (DB:183-187)."""
+    g = torch.Generator().manual_seed(11)
+    B, C, Co, H, W = 3, 128, 64, 16, 16
+    q = tf32_rn(torch.randn(B, H, W, 384, generator=g))
+    weff = tf32_rn(torch.randn(B, Co, C, generator=g) * 0.1)
+    res = torch.randn(B, H, W, Co, generator=g)
+    bias = torch.randn(Co, generator=g)
+    ref = torch.einsum('bhwc,boc->bhwo', q[..., :C].double(), weff.double()) + bias.double() + res.double()
+    out = torch.empty(B, H, W, Co, device='cuda')
+    tp = ops.taps_conv(1, 0)
+    d = ops.make_conv_desc([(ops.View(q.cuda(), 0, C), tp, weff.cuda(), True)], ops.View(out), (B, H, W),
+                           Cout=Co, bias=bias.cuda(), resid=ops.View(res.cuda()))
+    ops.conv_fwd(d, ops.CONV_TC if impl == 'tc' else ops.CONV_SIMT)
+    torch.cuda.synchronize()
+    assert rel(out.cpu(), ref) < 3e-6
+
+
+def test_tf32_operand_rounding_probe(ops):
+    """Diagnostic (always passes): how does the TC path treat UNROUNDED fp32 operands under FLOAT32 vs
+    TFLOAT32 tensor maps?  Written to gpurun_out/tf32_probe.txt for DESIGN.md."""
+    import os
+    from cold_diffusion_models_b200._lib import lib
+    g = torch.Generator().manual_seed(21)
+    B, Ci, Co, H, W = 2, 128, 128, 32, 32
+    x = torch.randn(B, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) / (Ci * 9) ** 0.5
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    ref_rn = F.conv2d(tf32_rn(x).double(), tf32_rn(w).double(), padding=1)
+    ref_tr = F.conv2d((x.view(torch.int32) & ~0x1FFF).view(torch.float32).double(),
+                      (w.view(torch.int32) & ~0x1FFF).view(torch.float32).double(), padding=1)
+    taps = ops.taps_conv(3, 1)
+    lines = []
+    for mode in (0, 1):
+        lib.cd_conv_tc_set_tf32_maps(mode)
+        pw = ops.pack_weight(w.cuda(), taps, round_tf32=False)
+        out = torch.empty(B, H, W, Co, device='cuda')
+        d = ops.make_conv_desc([(ops.View(nhwc(x).cuda()), taps, pw, False)], ops.View(out), (B, H, W), Cout=Co)
+        try:
+            ops.conv_fwd(d, ops.CONV_TC)
+            torch.cuda.synchronize()
+            o = nchw(out.cpu())
+            lines.append('map_dtype=%s rel_vs_fp64=%.3e rel_vs_rn=%.3e rel_vs_trunc=%.3e' % (
+                'TFLOAT32' if mode else 'FLOAT32', rel(o, ref), rel(o, ref_rn), rel(o, ref_tr)))
+        except Exception as e:  # noqa
+            lines.append('map_dtype=%d failed: %s' % (mode, e))
+    lib.cd_conv_tc_set_tf32_maps(1)
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/tf32_probe.txt', 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    print('\n'.join(lines))
