@@ -3,5 +3,7 @@
 Host code is Python/PyTorch (device memory, streams, torch.distributed); all arithmetic runs in
 hand-written sm_100a CUDA behind the C ABI in include/colddiff.h (libcolddiff.so)."""
 from . import _lib  # noqa: F401  (raises if the CUDA library has not been built)
+from .unet import Unet
+from .deblurring import GaussianDiffusion
 
-__all__ = ['_lib']
+__all__ = ['Unet', 'GaussianDiffusion']

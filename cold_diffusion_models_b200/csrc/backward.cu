@@ -1,0 +1,398 @@
+// Backward kernels of the HBM-bound Unet pieces (the dense-conv gradients reuse the tap-list
+// convolution contract: dgrad = cd_conv_fwd with transposed/flipped packed weights, wgrad =
+// cd_conv_wgrad).  Everything here is fp32 on NHWC activations.
+#include "cd_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// channel LayerNorm backward (DB:111-121): warp per pixel.
+//   xhat = (h - mean) * rstd ; dxh = dy * g ; dh = rstd * (dxh - mean_c(dxh) - xhat * mean_c(dxh * xhat)) (+ addend)
+//   dg[c] += sum_pix dy * xhat ; dbeta[c] += sum_pix dy
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ h, int h_ld,
+                     const float* __restrict__ stats, const float* __restrict__ g, long long npix, int C,
+                     const float* __restrict__ addend, int addend_ld, float* __restrict__ dh, int dh_ld,
+                     float* __restrict__ dg, float* __restrict__ dbeta, int pix_per_block) {
+  extern __shared__ float red[];   // [2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nq = C >> 2;
+  float4 ag[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block; if (p1 > npix) p1 = npix;
+  for (long long pix = p0 + warp; pix < p1; pix += nwarp) {
+    const float mean = stats[pix * 2], rstd = stats[pix * 2 + 1];
+    float4 dv[8], xh[8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int qd = lane + i * 32;
+      if (qd < nq) {
+        const float4 d = *reinterpret_cast<const float4*>(dy + pix * dy_ld + qd * 4);
+        const float4 hv = *reinterpret_cast<const float4*>(h + pix * h_ld + qd * 4);
+        const float4 gv = *reinterpret_cast<const float4*>(g + qd * 4);
+        xh[i] = make_float4((hv.x - mean) * rstd, (hv.y - mean) * rstd, (hv.z - mean) * rstd, (hv.w - mean) * rstd);
+        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+        dv[i] = make_float4(d.x * gv.x, d.y * gv.y, d.z * gv.z, d.w * gv.w);
+        s1 += dv[i].x + dv[i].y + dv[i].z + dv[i].w;
+        s2 += dv[i].x * xh[i].x + dv[i].y * xh[i].y + dv[i].z * xh[i].z + dv[i].w * xh[i].w;
+      }
+    }
+    s1 = cd_warp_sum(s1) / C; s2 = cd_warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int qd = lane + i * 32;
+      if (qd < nq) {
+        float4 o;
+        o.x = rstd * (dv[i].x - s1 - xh[i].x * s2); o.y = rstd * (dv[i].y - s1 - xh[i].y * s2);
+        o.z = rstd * (dv[i].z - s1 - xh[i].z * s2); o.w = rstd * (dv[i].w - s1 - xh[i].w * s2);
+        if (addend) {
+          const float4 a = *reinterpret_cast<const float4*>(addend + pix * addend_ld + qd * 4);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        *reinterpret_cast<float4*>(dh + pix * dh_ld + qd * 4) = o;
+      }
+    }
+  }
+  // block reduction of the parameter gradients, one atomicAdd per channel per block
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int qd = lane + i * 32;
+    if (qd < nq) {
+      atomicAdd(&red[qd * 4 + 0], ag[i].x); atomicAdd(&red[qd * 4 + 1], ag[i].y);
+      atomicAdd(&red[qd * 4 + 2], ag[i].z); atomicAdd(&red[qd * 4 + 3], ag[i].w);
+      atomicAdd(&red[C + qd * 4 + 0], ab[i].x); atomicAdd(&red[C + qd * 4 + 1], ab[i].y);
+      atomicAdd(&red[C + qd * 4 + 2], ab[i].z); atomicAdd(&red[C + qd * 4 + 3], ab[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(dg + i, red[i]); atomicAdd(dbeta + i, red[C + i]); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 7x7 weight gradient: dw[c][ky*7+kx] += sum_{b,y,x} dh[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]
+// block = (b, group of R rows, 32-channel slab); rows staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwR = 4;
+__global__ void __launch_bounds__(256)
+dwconv7_wgrad_kernel(const float* __restrict__ dh, int dh_ld, const float* __restrict__ x, int x_ld,
+                     int B, int H, int W, int C, float* __restrict__ dw) {
+  extern __shared__ float sm[];                // dhs[W][33] | xs[7][W+6][33]
+  const int Wp = W + 6;
+  float* dhs = sm;
+  float* xs = sm + W * 33;
+  const int c0 = blockIdx.x * 32;
+  const int cn = min(32, C - c0);
+  const int ygroups = (H + kDwR - 1) / kDwR;
+  const int b = blockIdx.y / ygroups, y0 = (blockIdx.y % ygroups) * kDwR;
+  // each thread owns outputs o = threadIdx.x + 256*j (o = tap*32 + c), j < 7 (49*32 = 1568 <= 1792)
+  float acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+  for (int yy = y0; yy < min(H, y0 + kDwR); ++yy) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * 32; i += blockDim.x) {
+      const int px = i >> 5, c = i & 31;
+      dhs[px * 33 + c] = c < cn ? dh[((static_cast<long long>(b) * H + yy) * W + px) * dh_ld + c0 + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 7 * Wp * 32; i += blockDim.x) {
+      const int c = i & 31;
+      const int px = (i >> 5) % Wp, ky = (i >> 5) / Wp;
+      const int iy = yy + ky - 3, ix = px - 3;
+      float v = 0.f;
+      if (c < cn && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = x[((static_cast<long long>(b) * H + iy) * W + ix) * x_ld + c0 + c];
+      xs[(ky * Wp + px) * 33 + c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int o = threadIdx.x + 256 * j;
+      if (o < 49 * 32) {
+        const int c = o & 31, tap = o >> 5, ky = tap / 7, kx = tap % 7;
+        const float* xr = xs + (ky * Wp + kx) * 33 + c;
+        float a = 0.f;
+        for (int px = 0; px < W; ++px) a = fmaf(dhs[px * 33 + c], xr[px * 33], a);
+        acc[j] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int o = threadIdx.x + 256 * j;
+    if (o < 49 * 32) {
+      const int c = o & 31, tap = o >> 5;
+      if (c < cn) atomicAdd(dw + (c0 + c) * 49 + tap, acc[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched column sums: out[b*out_ld + c] += sum_{rows of image b} x[(b*rows + r)*ld + c]
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_batched_kernel(const float* __restrict__ x, int ld, long long rows, int C, float* __restrict__ out,
+                                      int out_ld, long long rows_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const long long r0 = blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block; if (r1 > rows) r1 = rows;
+  float s = 0.f;
+  if (c < C) for (long long r = r0 + ry; r < r1; r += 8) s += x[(static_cast<long long>(b) * rows + r) * ld + c];
+  __shared__ float smr[8][33];
+  smr[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += smr[i][threadIdx.x & 31];
+    atomicAdd(out + static_cast<long long>(b) * out_ld + c, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LinearAttention backward, small per-(b) part.  Inputs: dweff[b][co][hd], ctx (un-normalised), ksum, w_out.
+//   ctxn[h][d][e] = ctx / ksum[h*32+d]
+//   dW_out[co][h*32+e] += scale * sum_d dweff[b][co][h*32+d] * ctxn[b][h][d][e]         (atomic over b)
+//   dctxn[b][h][d][e]   = scale * sum_co dweff[b][co][h*32+d] * w_out[co][h*32+e]
+//   rowdot[b][h*32+d]   = sum_e dctxn * ctxn
+// grid = B, block = 256
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_bwd_small_kernel(const float* __restrict__ dweff, const float* __restrict__ ctx, const float* __restrict__ ksum,
+                      const float* __restrict__ w_out, int dim, float scale, float* __restrict__ dw_out,
+                      float* __restrict__ dctxn, float* __restrict__ rowdot) {
+  const int b = blockIdx.x;
+  const float* dwe = dweff + static_cast<long long>(b) * dim * 128;
+  const float* cb = ctx + static_cast<long long>(b) * 4096;
+  // dctxn: 4096 outputs, each sum over co
+  for (int o = threadIdx.x; o < 4096; o += blockDim.x) {
+    const int e = o & 31, d = (o >> 5) & 31, h = o >> 10;
+    float a = 0.f;
+    for (int co = 0; co < dim; ++co) a = fmaf(dwe[co * 128 + h * 32 + d], w_out[co * 128 + h * 32 + e], a);
+    dctxn[static_cast<long long>(b) * 4096 + o] = a * scale;
+  }
+  // dW_out: dim*128 outputs, each sum over d
+  for (int o = threadIdx.x; o < dim * 128; o += blockDim.x) {
+    const int he = o & 127, co = o >> 7, h = he >> 5, e = he & 31;
+    float a = 0.f;
+    for (int d = 0; d < 32; ++d)
+      a = fmaf(dwe[co * 128 + h * 32 + d], cb[(h * 32 + d) * 32 + e] / ksum[b * 128 + h * 32 + d], a);
+    atomicAdd(dw_out + o, a * scale);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 128; o += blockDim.x) {
+    float a = 0.f;
+    const float inv = 1.f / ksum[b * 128 + o];
+    for (int e = 0; e < 32; ++e) a = fmaf(dctxn[static_cast<long long>(b) * 4096 + o * 32 + e], cb[o * 32 + e] * inv, a);
+    rowdot[b * 128 + o] = a;
+  }
+}
+
+// per-pixel part: dk[n][hd] = P * (sum_e dctxn[hd][e] v[n][h,e] - rowdot[hd]),  P = exp(k-kmax)/ksum
+//                 dv[n][he] = sum_d P[n][h,d] dctxn[h,d][e]
+// block handles 32 pixels of one image; dctxn (16 KB) staged in shared memory.
+__global__ void __launch_bounds__(256)
+attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __restrict__ kmax,
+                   const float* __restrict__ ksum, const float* __restrict__ dctxn, const float* __restrict__ rowdot,
+                   float* __restrict__ dqkv, int dld) {
+  __shared__ float dc[4096];
+  __shared__ float ps[32][129];
+  __shared__ float vs[32][129];
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) dc[i] = dctxn[static_cast<long long>(b) * 4096 + i];
+  for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
+    const int pp = i >> 7, c = i & 127;
+    const int p = p0 + pp;
+    float pv = 0.f, vv = 0.f;
+    if (p < n) {
+      const float* row = qkv + (static_cast<long long>(b) * n + p) * ld;
+      pv = __expf(row[128 + c] - kmax[b * 128 + c]) / ksum[b * 128 + c];
+      vv = row[256 + c];
+    }
+    ps[pp][c] = pv; vs[pp][c] = vv;
+  }
+  __syncthreads();
+  // 32 pixels x 128 channels = 4096 outputs of each kind; thread handles 16 of each
+  for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
+    const int pp = i >> 7, c = i & 127, h = c >> 5, j = c & 31;
+    const int p = p0 + pp;
+    if (p >= n) continue;
+    float dk = 0.f, dv = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < 32; ++e) {
+      dk = fmaf(dc[(h * 32 + j) * 32 + e], vs[pp][h * 32 + e], dk);       // c = (h, d=j)
+      dv = fmaf(ps[pp][h * 32 + e], dc[(h * 32 + e) * 32 + j], dv);       // c = (h, e=j), sum over d=e
+    }
+    float* orow = dqkv + (static_cast<long long>(b) * n + p) * dld;
+    orow[128 + c] = ps[pp][c] * (dk - rowdot[b * 128 + c]);
+    orow[256 + c] = dv;
+  }
+}
+
+// transpose per-batch weff [B][dim][128] -> [B][128][dim]
+__global__ void transpose_weff_kernel(const float* __restrict__ w, int dim, float* __restrict__ wt) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dim * 128) return;
+  const int co = i >> 7, hd = i & 127;
+  wt[(static_cast<long long>(b) * 128 + hd) * dim + co] = w[static_cast<long long>(b) * dim * 128 + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// final 1x1 projection backward: dx[pix][c] = sum_co dout[b][co][pix] w[co][c]; dw[co][c], db[co]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+conv1x1_to_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int ld, int B, int HW, int C,
+                           const float* __restrict__ w, int Co, float* __restrict__ dx, int dx_ld,
+                           float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float red[];      // [Co][C] + [Co]
+  for (int i = threadIdx.x; i < Co * C + Co; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = pix < static_cast<long long>(B) * HW;
+  if (valid) {
+    const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
+    float dv[8];
+    for (int co = 0; co < Co; ++co) dv[co] = dout[(static_cast<long long>(b) * Co + co) * HW + p];
+    for (int c = 0; c < C; ++c) {
+      float a = 0.f;
+      for (int co = 0; co < Co; ++co) a = fmaf(dv[co], w[co * C + c], a);
+      dx[pix * dx_ld + c] = a;
+    }
+  }
+  // parameter gradients: warp-reduce over the 32 pixels of each warp, then shared atomics
+  const int lane = threadIdx.x & 31;
+  for (int co = 0; co < Co; ++co) {
+    float dvv = 0.f;
+    if (valid) {
+      const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
+      dvv = dout[(static_cast<long long>(b) * Co + co) * HW + p];
+    }
+    const float sb = cd_warp_sum(dvv);
+    if (lane == 0) atomicAdd(&red[Co * C + co], sb);
+    for (int c = 0; c < C; ++c) {
+      const float s = cd_warp_sum(valid ? dvv * x[pix * ld + c] : 0.f);
+      if (lane == 0) atomicAdd(&red[co * C + c], s);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Co * C; i += blockDim.x) atomicAdd(dw + i, red[i]);
+  for (int i = threadIdx.x; i < Co; i += blockDim.x) atomicAdd(db + i, red[Co * C + i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiny dense helpers for the time-MLP backward
+// ---------------------------------------------------------------------------------------------
+// C[m][n] (+)= sum_k A(m,k) * B(k,n); A(m,k) = transA ? A[k*lda+m] : A[m*lda+k]; same for B
+__global__ void small_gemm_kernel(const float* __restrict__ A, int lda, int transA, const float* __restrict__ Bm, int ldb,
+                                  int transB, float* __restrict__ Cm, int ldc, int M, int N, int K, int accumulate) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * N) return;
+  const int n = static_cast<int>(idx % N), m = static_cast<int>(idx / N);
+  float a = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float av = transA ? A[static_cast<long long>(k) * lda + m] : A[static_cast<long long>(m) * lda + k];
+    const float bv = transB ? Bm[static_cast<long long>(n) * ldb + k] : Bm[static_cast<long long>(k) * ldb + n];
+    a = fmaf(av, bv, a);
+  }
+  float* o = Cm + static_cast<long long>(m) * ldc + n;
+  *o = accumulate ? *o + a : a;
+}
+// y[i] = dy[i] * gelu'(pre[i])   (y may alias dy);  act_out (optional) = gelu(pre)
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, long long n,
+                                float* __restrict__ y, float* __restrict__ act_out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p = pre[i];
+  if (act_out) act_out[i] = cd_gelu(p);
+  if (y) y[i] = dy[i] * cd_gelu_grad(p);
+}
+
+}  // namespace
+
+extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int h_ld, const float* stats,
+                                const float* g, int64_t npix, int C, const float* addend, int addend_ld,
+                                float* dh, int dh_ld, float* dg, float* dbeta, void* stream) {
+  CD_REQUIRE(C % 4 == 0 && C <= 1024 && dy_ld % 4 == 0 && h_ld % 4 == 0 && dh_ld % 4 == 0, "cd_layernorm_bwd: unsupported C=%d", C);
+  int ppb = 256;
+  const int blocks = cd_cdiv(npix, ppb);
+  layernorm_bwd_kernel<<<blocks, 256, sizeof(float) * 2 * C, static_cast<cudaStream_t>(stream)>>>(
+      dy, dy_ld, h, h_ld, stats, g, npix, C, addend, addend_ld, dh, dh_ld, dg, dbeta, ppb);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_dwconv7_wgrad(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C,
+                                float* dw, void* stream) {
+  const size_t smem = sizeof(float) * (size_t(W) * 33 + size_t(7) * (W + 6) * 33);
+  CD_REQUIRE(smem <= 200 * 1024, "cd_dwconv7_wgrad: image width %d too large", W);
+  static size_t attr = 0;
+  if (smem > attr) { CD_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  dim3 grid(cd_cdiv(C, 32), B * cd_cdiv(H, kDwR));
+  dwconv7_wgrad_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dh, dh_ld, x, x_ld, B, H, W, C, dw);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_colsum_batched(const float* x, int ld, int B, int64_t rows, int C, float* out, int out_ld, void* stream) {
+  const long long rpb = 2048;
+  dim3 grid(cd_cdiv(C, 32), cd_cdiv(rows, rpb), B);
+  colsum_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, C, out, out_ld, rpb);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_linattn_bwd_small(const float* dweff, const float* ctx, const float* ksum, const float* w_out,
+                                    int B, int dim, float scale, float* dw_out, float* dctxn, float* rowdot, void* stream) {
+  attn_bwd_small_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(dweff, ctx, ksum, w_out, dim, scale, dw_out, dctxn, rowdot);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_linattn_bwd_kv(const float* qkv, int ld, int B, int n, const float* kmax, const float* ksum,
+                                 const float* dctxn, const float* rowdot, float* dqkv, int dld, void* stream) {
+  dim3 grid(cd_cdiv(n, 32), B);
+  attn_bwd_kv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(qkv, ld, n, kmax, ksum, dctxn, rowdot, dqkv, dld);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_transpose_weff(const float* weff, int B, int dim, float* weff_t, void* stream) {
+  dim3 grid(cd_cdiv(dim * 128, 256), B);
+  transpose_weff_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(weff, dim, weff_t);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_conv1x1_to_nchw_bwd(const float* dout_nchw, const float* x, int ld, int B, int H, int W, int C,
+                                      const float* w, int Co, float* dx, int dx_ld, float* dw, float* db, void* stream) {
+  CD_REQUIRE(Co <= 8, "cd_conv1x1_to_nchw_bwd: at most 8 image channels");
+  const long long npix = static_cast<long long>(B) * H * W;
+  const size_t smem = sizeof(float) * (size_t(Co) * C + Co);
+  conv1x1_to_nchw_bwd_kernel<<<cd_cdiv(npix, 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
+                                                                                                 dx, dx_ld, dw, db);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_small_gemm(const float* A, int lda, int transA, const float* Bm, int ldb, int transB,
+                             float* Cm, int ldc, int M, int N, int K, int accumulate, void* stream) {
+  const long long total = static_cast<long long>(M) * N;
+  small_gemm_kernel<<<cd_cdiv(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, transA, Bm, ldb, transB, Cm, ldc, M, N, K, accumulate);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_gelu_bwd(const float* dy, const float* pre, int64_t n, float* y, float* act_out, void* stream) {
+  gelu_bwd_kernel<<<cd_cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, pre, n, y, act_out);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

@@ -15,7 +15,7 @@ constexpr int kStrip = 8;
 template <bool kNorm>
 __global__ void __launch_bounds__(256)
 dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C,
-                  const float* __restrict__ wdw, const float* __restrict__ bdw, const float* __restrict__ cond,
+                  const float* __restrict__ wdw, const float* __restrict__ bdw, const float* __restrict__ cond, int cond_ld,
                   const float* __restrict__ g, const float* __restrict__ beta, float eps,
                   float* __restrict__ y, int y_ld, float* __restrict__ stats, float* __restrict__ hpre, int hpre_ld,
                   int round_tf32) {
@@ -65,7 +65,7 @@ dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, in
     }
     float4 add = *reinterpret_cast<const float4*>(bdw + c0);
     if (cond) {
-      const float4 cv = *reinterpret_cast<const float4*>(cond + static_cast<long long>(b) * C + c0);
+      const float4 cv = *reinterpret_cast<const float4*>(cond + static_cast<long long>(b) * cond_ld + c0);
       add.x += cv.x; add.y += cv.y; add.z += cv.z; add.w += cv.w;
     }
 #pragma unroll
@@ -141,7 +141,7 @@ dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, in
 // generic (any C, e.g. the 1/3-channel image): one thread per pixel, loops channels; LN optional.
 __global__ void dwconv7_small_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C,
                                      const float* __restrict__ wdw, const float* __restrict__ bdw,
-                                     const float* __restrict__ cond, const float* __restrict__ g,
+                                     const float* __restrict__ cond, int cond_ld, const float* __restrict__ g,
                                      const float* __restrict__ beta, float eps, float* __restrict__ y, int y_ld,
                                      float* __restrict__ stats, float* __restrict__ hpre, int hpre_ld, int round_tf32) {
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -153,7 +153,7 @@ __global__ void dwconv7_small_kernel(const float* __restrict__ x, int x_ld, int 
   float hbuf[16];
   float mean = 0.f;
   for (int c = 0; c < C; ++c) {
-    float a = bdw[c] + (cond ? cond[static_cast<long long>(b) * C + c] : 0.f);
+    float a = bdw[c] + (cond ? cond[static_cast<long long>(b) * cond_ld + c] : 0.f);
     for (int ky = 0; ky < 7; ++ky) {
       const int iy = yy + ky - 3;
       if (iy < 0 || iy >= H) continue;
@@ -380,7 +380,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, i
 }  // namespace
 
 extern "C" int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, int C,
-                                 const float* w_dw, const float* b_dw, const float* cond,
+                                 const float* w_dw, const float* b_dw, const float* cond, int cond_ld,
                                  const float* g, const float* beta, float eps, float* y, int y_ld,
                                  float* stats, float* hpre, int hpre_ld, int round_tf32, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -392,12 +392,12 @@ extern "C" int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, 
     const long long nstrips = static_cast<long long>(B) * H * (W / kStrip);
     const int blocks = cd_cdiv(nstrips, strips_per_block);
     const size_t smem = sizeof(float) * strips_per_block * ((cq + 31) / 32) * kStrip;
-    if (g) dwconv7_ln_kernel<true><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
-    else dwconv7_ln_kernel<false><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+    if (g) dwconv7_ln_kernel<true><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+    else dwconv7_ln_kernel<false><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
   } else {
     CD_REQUIRE(C <= 16, "cd_dwconv7_ln_fwd: unsupported channel count %d (W=%d)", C, W);
     const long long npix = static_cast<long long>(B) * H * W;
-    dwconv7_small_kernel<<<cd_cdiv(npix, 128), 128, 0, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+    dwconv7_small_kernel<<<cd_cdiv(npix, 128), 128, 0, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
   }
   CD_LAUNCH_CHECK();
   return 0;

@@ -1,0 +1,335 @@
+"""UnetEngine -- host-side schedule of the sm_100a kernels that execute the reference `Unet.forward`
+(DB:256-282) on NHWC fp32 activations.  Python here only sequences C-ABI calls (include/colddiff.h) on
+torch's current stream and owns device buffers; it performs no arithmetic.
+
+Data layout in HBM
+  * activations: NHWC fp32, one buffer per tensor; skip connections are never copied -- the down-path
+    attention writes its output straight into the second channel half of the up-path concat buffer and
+    the Upsample transpose-conv writes into the first half (replaces torch.cat, DB:274);
+  * dense conv weights: packed [tap][Cout][Cin] fp32 (K-major rows for TMA/UMMA), repacked from the
+    reference OIHW parameters whenever they change; TF32 rounding happens in the TMA unit on load;
+  * time conditioning of all 16 blocks is one [B][sumC] matrix produced by a single kernel.
+"""
+import ctypes as C
+import torch
+
+from . import ops
+from .ops import View, CONV_TC, CONV_SIMT, ACT_NONE, ACT_GELU
+from ._lib import call, ptr, stream
+
+T3 = ops.taps_conv(3, 1)
+T1 = ops.taps_conv(1, 0)
+T4 = ops.taps_conv(4, 1)
+T3D = ops.taps_conv_dgrad(3, 1)
+TPAR = {(py, px): ops.taps_convT4_parity(py, px) for py in (0, 1) for px in (0, 1)}
+
+
+def _tc_ok(*chans):
+    return all(c % 32 == 0 for c in chans)
+
+
+class BlockSpec:
+    """one ConvNextBlock (DB:135-165)"""
+
+    def __init__(self, name, mod, cond_off):
+        self.name = name
+        self.mod = mod
+        self.din = mod.ds_conv.weight.shape[0]
+        self.dmid = mod.net[1].weight.shape[0]
+        self.dout = mod.net[3].weight.shape[0]
+        self.has_norm = hasattr(mod.net[0], 'g')
+        self.has_res = hasattr(mod.res_conv, 'weight')
+        self.cond_off = cond_off if mod.mlp is not None else None
+
+
+class AttnSpec:
+    """Residual(PreNorm(LinearAttention)) (DB:83-89,123-131,167-187)"""
+
+    def __init__(self, name, mod):
+        self.name = name
+        self.norm = mod.fn.norm
+        self.attn = mod.fn.fn
+        self.dim = self.norm.g.shape[1]
+
+
+class UnetEngine:
+    def __init__(self, unet):
+        self.unet = unet
+        self.dev = next(unet.parameters()).device
+        self.channels = unet.channels
+        self.dim = unet.dim
+        self._bufs = {}
+        self._packed = {}
+        self._dirty = True
+        self._version = None
+        self.conv_impl = CONV_TC
+        # ---- static program ----
+        off = 0
+        self.blocks = {}
+
+        def mk(name, mod):
+            nonlocal off
+            bs = BlockSpec(name, mod, off)
+            if mod.mlp is not None:
+                off += (bs.din + 3) // 4 * 4          # keep every block's slice 16-byte aligned
+            self.blocks[name] = bs
+            return bs
+
+        self.levels_down = []
+        for i, (b0, b1, at, dn) in enumerate(unet.downs):
+            self.levels_down.append((mk('downs.%d.0' % i, b0), mk('downs.%d.1' % i, b1),
+                                     AttnSpec('downs.%d.2' % i, at), dn if hasattr(dn, 'weight') else None))
+        self.mid1 = mk('mid_block1', unet.mid_block1)
+        self.mid_attn = AttnSpec('mid_attn', unet.mid_attn)
+        self.mid2 = mk('mid_block2', unet.mid_block2)
+        self.levels_up = []
+        for i, (b0, b1, at, up) in enumerate(unet.ups):
+            self.levels_up.append((mk('ups.%d.0' % i, b0), mk('ups.%d.1' % i, b1),
+                                   AttnSpec('ups.%d.2' % i, at), up if hasattr(up, 'weight') else None))
+        self.final_block = mk('final_conv.0', unet.final_conv[0])
+        self.final_proj = unet.final_conv[1]
+        self.sumC = off
+        self.cond_blocks = [b for b in self.blocks.values() if b.cond_off is not None]
+
+    # ------------------------------------------------------------------------------------------
+    def mark_weights_dirty(self):
+        self._dirty = True
+
+    def param_list(self):
+        return [p for p in self.unet.parameters()]
+
+    def buf(self, name, shape, zero=False):
+        key = (name, tuple(shape))
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(shape, device=self.dev, dtype=torch.float32)
+            self._bufs[key] = t
+        return t
+
+    def _params_version(self):
+        return tuple(p._version for p in self.unet.parameters())
+
+    def prepare_weights(self, force=False):
+        """(re)pack reference-layout parameters into kernel layouts when they changed."""
+        ver = self._params_version()
+        if not (force or self._dirty or ver != self._version):
+            return
+        P = self._packed
+        with torch.no_grad():
+            for name, bs in self.blocks.items():
+                m = bs.mod
+                P[name + '.w1'] = ops.pack_weight(m.net[1].weight, T3, round_tf32=False, out=P.get(name + '.w1'))
+                P[name + '.w2'] = ops.pack_weight(m.net[3].weight, T3, round_tf32=False, out=P.get(name + '.w2'))
+                if bs.has_res:
+                    P[name + '.wr'] = ops.pack_weight(m.res_conv.weight, T1, round_tf32=False, out=P.get(name + '.wr'))
+                    # bias of the fused [conv2 | res_conv] GEMM
+                    b = P.get(name + '.b2r')
+                    if b is None:
+                        b = P[name + '.b2r'] = torch.empty_like(m.net[3].bias)
+                    torch.add(m.net[3].bias, m.res_conv.bias, out=b)
+            for spec in self._attn_specs():
+                a = spec.attn
+                P[spec.name + '.wqkv'] = ops.pack_weight(a.to_qkv.weight, T1, round_tf32=False, out=P.get(spec.name + '.wqkv'))
+            for i, lv in enumerate(self.levels_down):
+                if lv[3] is not None:
+                    P['downs.%d.3' % i] = ops.pack_weight(lv[3].weight, T4, round_tf32=False, out=P.get('downs.%d.3' % i))
+            for i, lv in enumerate(self.levels_up):
+                if lv[3] is not None:
+                    for k, tp in TPAR.items():
+                        key = 'ups.%d.3.%d%d' % (i, k[0], k[1])
+                        P[key] = ops.pack_weight(lv[3].weight, tp, transposed_conv=True, round_tf32=False, out=P.get(key))
+            if self.cond_blocks:
+                wc = P.get('cond.w')
+                if wc is None:
+                    wc = P['cond.w'] = torch.zeros(self.sumC, self.dim, device=self.dev)
+                    P['cond.b'] = torch.zeros(self.sumC, device=self.dev)
+                for bs in self.cond_blocks:
+                    wc[bs.cond_off:bs.cond_off + bs.din].copy_(bs.mod.mlp[1].weight)
+                    P['cond.b'][bs.cond_off:bs.cond_off + bs.din].copy_(bs.mod.mlp[1].bias)
+        self._dirty = False
+        self._version = ver
+
+    def _attn_specs(self):
+        out = [lv[2] for lv in self.levels_down] + [self.mid_attn] + [lv[2] for lv in self.levels_up]
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # forward pieces.  `save` is None for inference; a dict for training (tensors kept for backward)
+    # ------------------------------------------------------------------------------------------
+    def _conv(self, desc, tc):
+        ops.conv_fwd(desc, self.conv_impl if tc else CONV_SIMT)
+
+    def _block(self, bs, xv, outv, cond_all, save, tag):
+        B, H, W = xv.B, xv.H, xv.W
+        m = bs.mod
+        P = self._packed
+        uniq = bs.name if save is not None else tag
+        ld_in = bs.din if bs.din % 4 == 0 else 4
+        hn = self.buf('hn.' + uniq, (B, H, W, ld_in))
+        stats = hpre = None
+        if save is not None:
+            if bs.has_norm:
+                stats = self.buf('st.' + bs.name, (B, H, W, 2))
+                hpre = self.buf('hp.' + bs.name, (B, H, W, ld_in))
+        cond = None
+        if bs.cond_off is not None:
+            cond = C.c_void_p(cond_all.data_ptr() + 4 * bs.cond_off)
+        g = m.net[0].g if bs.has_norm else None
+        be = m.net[0].b if bs.has_norm else None
+        call('cd_dwconv7_ln_fwd', C.c_void_p(xv.addr()), xv.ld, B, H, W, bs.din, ptr(m.ds_conv.weight), ptr(m.ds_conv.bias),
+             cond if cond is not None else C.c_void_p(0), self.sumC, ptr(g), ptr(be), C.c_float(1e-5), ptr(hn), ld_in,
+             ptr(stats), ptr(hpre), ld_in, 0, stream())
+        hv = View(hn, 0, bs.din)
+        u = self.buf('u.' + uniq, (B, H, W, bs.dmid))
+        pre = self.buf('pre.' + bs.name, (B, H, W, bs.dmid)) if save is not None else None
+        d1 = ops.make_conv_desc([(hv, T3, P[bs.name + '.w1'], False)], View(u), (B, H, W), Cout=bs.dmid,
+                                bias=m.net[1].bias, act=ACT_GELU, out2=View(pre) if pre is not None else None)
+        self._conv(d1, _tc_ok(bs.din))
+        uv = View(u)
+        if bs.has_res:
+            if _tc_ok(bs.din):
+                d2 = ops.make_conv_desc([(uv, T3, P[bs.name + '.w2'], False), (xv, T1, P[bs.name + '.wr'], False)],
+                                        outv, (B, H, W), Cout=bs.dout, bias=P[bs.name + '.b2r'])
+                self._conv(d2, True)
+            else:
+                dr = ops.make_conv_desc([(xv, T1, P[bs.name + '.wr'], False)], outv, (B, H, W), Cout=bs.dout,
+                                        bias=P[bs.name + '.b2r'])
+                self._conv(dr, False)
+                d2 = ops.make_conv_desc([(uv, T3, P[bs.name + '.w2'], False)], outv, (B, H, W), Cout=bs.dout, resid=outv)
+                self._conv(d2, True)
+        else:
+            d2 = ops.make_conv_desc([(uv, T3, P[bs.name + '.w2'], False)], outv, (B, H, W), Cout=bs.dout,
+                                    bias=m.net[3].bias, resid=xv)
+            self._conv(d2, True)
+        if save is not None:
+            save[bs.name] = dict(x=xv, hn=hv, u=uv, pre=View(pre), stats=stats, hpre=hpre, out=outv)
+
+    def _attn(self, spec, xv, outv, save, tag):
+        B, H, W = xv.B, xv.H, xv.W
+        n = H * W
+        dim = spec.dim
+        uniq = spec.name if save is not None else tag
+        xn = self.buf('xn.' + uniq, (B, H, W, dim))
+        stats = self.buf('ast.' + spec.name, (B, H, W, 2)) if save is not None else None
+        call('cd_layernorm_fwd', C.c_void_p(xv.addr()), xv.ld, C.c_int64(B * n), dim, ptr(spec.norm.g), ptr(spec.norm.b),
+             C.c_float(1e-5), ptr(xn), dim, ptr(stats), 0, stream())
+        qkv = self.buf('qkv.' + uniq, (B, H, W, 384))
+        dq = ops.make_conv_desc([(View(xn), T1, self._packed[spec.name + '.wqkv'], False)], View(qkv), (B, H, W), Cout=384)
+        self._conv(dq, True)
+        kmax = self.buf('kmax.' + uniq, (B, 128))
+        ksum = self.buf('ksum.' + uniq, (B, 128))
+        ctx = self.buf('ctx.' + uniq, (B, 4, 32, 32))
+        weff = self.buf('weff.' + uniq, (B, dim, 128))
+        call('cd_linattn_context', ptr(qkv), 384, B, n, ptr(kmax), ptr(ksum), ptr(ctx), stream())
+        call('cd_linattn_weff', ptr(ctx), ptr(ksum), ptr(spec.attn.to_out.weight), B, dim, C.c_float(spec.attn.scale), 0,
+             ptr(weff), stream())
+        do = ops.make_conv_desc([(View(qkv, 0, 128), T1, weff, True)], outv, (B, H, W), Cout=dim,
+                                bias=spec.attn.to_out.bias, resid=xv)
+        self._conv(do, n >= 128)
+        if save is not None:
+            save[spec.name] = dict(x=xv, xn=View(xn), qkv=qkv, kmax=kmax, ksum=ksum, ctx=ctx, weff=weff, stats=stats, out=outv)
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x, time, save=None, out=None):
+        """x (B,C,H,W) NCHW fp32 cuda, time (B,) int64 -> (B,out_dim,H,W) NCHW."""
+        unet = self.unet
+        B, Cc, H, W = x.shape
+        assert Cc == self.channels
+        x = x.contiguous().float()
+        time = time.to(device=x.device, dtype=torch.int64).contiguous()
+        self.prepare_weights()
+        P = self._packed
+        ld0 = Cc if Cc % 4 == 0 else 4
+        x0 = self.buf('x0', (B, H, W, ld0))
+        call('cd_nchw_to_nhwc', ptr(x), B, Cc, H, W, ptr(x0), ld0, stream())
+        cond_all = None
+        if unet.time_mlp is not None:
+            dim = self.dim
+            cond_all = self.buf('cond_all', (B, max(self.sumC, 1)))
+            temb = self.buf('temb', (B, dim))
+            sinemb = self.buf('sinemb', (B, dim)) if save is not None else None
+            hid = self.buf('hid_pre', (B, 4 * dim)) if save is not None else None
+            l1, l2 = unet.time_mlp[1], unet.time_mlp[3]
+            call('cd_time_mlp_fwd', ptr(time), B, dim, ptr(l1.weight), ptr(l1.bias), ptr(l2.weight), ptr(l2.bias),
+                 ptr(P['cond.w']), ptr(P['cond.b']), self.sumC, ptr(sinemb), ptr(hid), ptr(temb), ptr(cond_all), stream())
+            if save is not None:
+                save['time'] = dict(sinemb=sinemb, hid=hid, temb=temb, cond_all=cond_all, t=time)
+        nd = len(self.levels_down)
+        nu = len(self.levels_up)
+        # spatial size and channels per down level
+        xv = View(x0, 0, Cc)
+        skips = []
+        h, w = H, W
+        for i, (b0, b1, at, dn) in enumerate(self.levels_down):
+            c = b0.dout
+            a = self.buf('d%d.a' % i, (B, h, w, c))
+            self._block(b0, xv, View(a), cond_all, save, 'L%d' % i)
+            bb = self.buf('d%d.b' % i, (B, h, w, c))
+            self._block(b1, View(a), View(bb), cond_all, save, 'L%d' % i)
+            # attention output = skip connection: lives in the concat buffer of the consuming up level
+            k = nd - 1 - i                       # up level that pops this skip
+            if k < nu:
+                cat = self.buf('cat%d' % k, (B, h, w, 2 * c))
+                sv = View(cat, c, c)
+            else:
+                sv = View(self.buf('d%d.s' % i, (B, h, w, c)))
+            self._attn(at, View(bb), sv, save, 'L%d' % i)
+            skips.append(sv)
+            if dn is not None:
+                nxt = self.buf('d%d.dn' % i, (B, h // 2, w // 2, c))
+                dd = ops.make_conv_desc([(sv, T4, P['downs.%d.3' % i], False)], View(nxt), (B, h // 2, w // 2), stride=2,
+                                        Cout=c, bias=dn.bias)
+                self._conv(dd, True)
+                if save is not None:
+                    save['downs.%d.3' % i] = dict(x=sv, out=View(nxt))
+                xv = View(nxt)
+                h, w = h // 2, w // 2
+            else:
+                xv = sv
+        cm = self.mid1.dout
+        m1 = self.buf('mid.a', (B, h, w, cm))
+        self._block(self.mid1, xv, View(m1), cond_all, save, 'M')
+        m2 = self.buf('mid.b', (B, h, w, cm))
+        self._attn(self.mid_attn, View(m1), View(m2), save, 'M')
+        # mid_block2 writes the first half of the first concat buffer
+        if nu > 0:
+            cat0 = self.buf('cat0', (B, h, w, 2 * cm))
+            xo = View(cat0, 0, cm)
+        else:
+            xo = View(self.buf('mid.c', (B, h, w, cm)))
+        self._block(self.mid2, View(m2), xo, cond_all, save, 'M')
+        xv = xo
+        for k, (b0, b1, at, up) in enumerate(self.levels_up):
+            cat = self.buf('cat%d' % k, (B, h, w, b0.din))
+            a = self.buf('u%d.a' % k, (B, h, w, b0.dout))
+            self._block(b0, View(cat), View(a), cond_all, save, 'U%d' % k)
+            bb = self.buf('u%d.b' % k, (B, h, w, b0.dout))
+            self._block(b1, View(a), View(bb), cond_all, save, 'U%d' % k)
+            cc = self.buf('u%d.c' % k, (B, h, w, b0.dout))
+            self._attn(at, View(bb), View(cc), save, 'U%d' % k)
+            xv = View(cc)
+            if up is not None:
+                c = b0.dout
+                if k + 1 < nu:
+                    nb = self.levels_up[k + 1][0]
+                    tgt = View(self.buf('cat%d' % (k + 1), (B, 2 * h, 2 * w, nb.din)), 0, c)
+                else:
+                    tgt = View(self.buf('up_last', (B, 2 * h, 2 * w, c)))
+                for (py, px), tp in TPAR.items():
+                    du = ops.make_conv_desc([(xv, tp, P['ups.%d.3.%d%d' % (k, py, px)], False)], tgt, (B, h, w), Cout=c,
+                                            bias=up.bias, out_map=(2, 2, py, px))
+                    self._conv(du, True)
+                if save is not None:
+                    save['ups.%d.3' % k] = dict(x=xv, out=tgt)
+                xv = tgt
+                h, w = 2 * h, 2 * w
+        fo = self.buf('final.a', (B, h, w, self.final_block.dout))
+        self._block(self.final_block, xv, View(fo), None, save, 'F')
+        od = self.final_proj.weight.shape[0]
+        if out is None:
+            out = torch.empty(B, od, h, w, device=x.device, dtype=torch.float32)
+        call('cd_conv1x1_to_nchw', ptr(fo), fo.shape[-1], B, h, w, fo.shape[-1], ptr(self.final_proj.weight),
+             ptr(self.final_proj.bias), od, ptr(x) if unet.residual else C.c_void_p(0), ptr(out), stream())
+        if save is not None:
+            save['final'] = dict(x=View(fo), x_in=x)
+        return out

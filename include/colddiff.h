@@ -93,25 +93,25 @@ int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld, float* dw
  * transposed_conv=1) -> packed [tap][N][K].  mode 0: forward operand (N=out ch, K=in ch);
  * mode 1: data-gradient operand (N=in ch, K=out ch). Tap order is given by (ky,kx) lists.     */
 int cd_pack_weight(const float* w, int O, int I, int KH, int KW, int transposed_conv, int mode,
-                   const int32_t* ky, const int32_t* kx, int ntaps, int round_tf32,
+                   const int32_t* host_ky, const int32_t* host_kx, int ntaps, int round_tf32,
                    float* packed, void* stream);
 /* inverse for gradients: packed [tap][O][I] -> OIHW / IOHW (accumulating) */
 int cd_unpack_wgrad(const float* packed, int O, int I, int KH, int KW, int transposed_conv,
-                    const int32_t* ky, const int32_t* kx, int ntaps, float* w_grad, int accumulate,
+                    const int32_t* host_ky, const int32_t* host_kx, int ntaps, float* w_grad, int accumulate,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * ConvNeXt block front half (DB:145, 140-143/159-162, 111-121/148):
- *   y = LayerNorm_c( dwconv7x7(x) + b_dw + cond[b,:] ) * g + beta      (norm / cond optional)
- * x,y NHWC. x_nchw!=0: x is the reference-layout NCHW image (first block, C = image channels).
- * stats (optional, [B*H*W][2] = mean, rstd) is saved for backward; h_pre (optional) the
- * pre-norm value.
+ *   h = dwconv7x7(x) + b_dw + cond[b,:] ;  y = LayerNorm_c(h) * g + beta   (g==NULL: y = h)
+ * x,y NHWC.  stats (optional, [B*H*W][2] = mean, rstd) and hpre (optional, h) are saved for the
+ * backward pass.
  * ------------------------------------------------------------------------------------------ */
-int cd_dwconv7_ln_fwd(const float* x, int x_ld, int x_nchw, int B, int H, int W, int C,
+int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, int C,
                       const float* w_dw /*[C][49]*/, const float* b_dw /*[C]*/,
-                      const float* cond /*[B][C] or NULL*/,
+                      const float* cond /*[B][cond_ld] or NULL*/, int cond_ld,
                       const float* g, const float* beta /*[C] or NULL: no norm*/,
-                      float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream);
+                      float eps, float* y, int y_ld, float* stats, float* hpre, int hpre_ld,
+                      int round_tf32, void* stream);
 
 /* channel LayerNorm alone (PreNorm in front of LinearAttention, DB:123-131) */
 int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
@@ -125,19 +125,26 @@ int cd_time_mlp_fwd(const int64_t* t, int B, int dim, const float* w1, const flo
                     float* sinemb /*[B][dim]*/, float* hid_pre /*[B][4dim]*/, float* temb /*[B][dim]*/,
                     float* cond_all /*[B][sumC]*/, void* stream);
 
-/* LinearAttention core (DB:176-187) on qkv NHWC [B][n][384] (q|k|v, head-major 4x32):
- *   ctx[b,h,d,e] = sum_n softmax_n(k[b,h,d,:])[n] * v[b,h,e,n]
- *   weff[b, co, h*32+d] = scale * sum_e w_out[co, h*32+e] * ctx[b,h,d,e]
- * so that to_out(out) == conv1x1(q, weff[b]) (a per-batch-weight tap-list convolution).
- * kmax/ksum ([B][128]) are saved for backward.                                              */
+/* LinearAttention core (DB:176-187) on qkv NHWC [B][n][ld] (q|k|v at channel 0|128|256, 4 heads x 32):
+ *   ctx[b,h,d,e]  = sum_n exp(k[b,h,d,n] - kmax[b,h,d]) * v[b,h,e,n]      (un-normalised)
+ *   ksum[b,h,d]   = sum_n exp(k[b,h,d,n] - kmax[b,h,d])
+ *   weff[b, co, h*32+d] = scale * sum_e w_out[co, h*32+e] * ctx[b,h,d,e] / ksum[b,h,d]
+ * so that to_out(einsum(context, q*scale)) == conv1x1(q, weff[b]) -- a per-batch-weight tap-list
+ * convolution (cd_conv_fwd with w_per_batch=1).  kmax/ksum ([B][128]) are kept for backward. */
 int cd_linattn_context(const float* qkv, int ld, int B, int n, float* kmax, float* ksum,
                        float* ctx /*[B][4][32][32]*/, void* stream);
-int cd_linattn_weff(const float* ctx, const float* w_out /*[dim][128]*/, int B, int dim, float scale,
-                    int round_tf32, float* weff /*[B][dim][128]*/, void* stream);
+int cd_linattn_weff(const float* ctx, const float* ksum, const float* w_out /*[dim][128]*/, int B, int dim,
+                    float scale, int round_tf32, float* weff /*[B][dim][128]*/, void* stream);
 
 /* final 1x1 conv to image channels + optional residual, NHWC -> reference NCHW (DB:253,279-282) */
 int cd_conv1x1_to_nchw(const float* x, int ld, int B, int H, int W, int C, const float* w /*[Co][C]*/,
                        const float* b, int Co, const float* resid_nchw, float* out_nchw, void* stream);
+/* reference NCHW image -> NHWC with zero-padded pixel stride ld (>= C) */
+int cd_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* out, int ld, void* stream);
+/* out[c] += sum_rows x[row*ld + c]  (bias / LayerNorm-beta gradients) */
+int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* stream);
+/* diagnostic switch: 1 (default) = TFLOAT32 tensor maps (TMA rounds fp32->tf32 RN on load) */
+int cd_conv_tc_set_tf32_maps(int enable);
 
 /* ------------------------------------------------------------------------------------------
  * Degradation D(x,t) for the Gaussian-blur family (DB:348-389 kernels; DB:927-960 q_sample;
