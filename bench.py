@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Cold-Diffusion hot path on B200 (contract: see the task brief).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference algorithm (oracle port) on the host cores
+
+Workload (BASELINE.json config 3, "C3"): CelebA-128 deblurring, Unet(dim 64, mults (1,2,4,8), 3 channels),
+T=200, Exponential_reflect k=15 std=0.01, x0_step_down; synthetic U(-1,1) images, random-init weights.
+A "step" is ONE optimizer step of Trainer.train (DB:1188-1204): 2 micro-batches x 32 images per GPU of
+p_losses forward + backward, one gradient all-reduce (N>1), fused Adam + EMA.  `value` = images/sec over all
+GPUs with the batches already resident in HBM; `e2e` = the same through the public Trainer.train_step call with
+pinned-host batches copied H2D and the loss read back D2H inside the timed region.  The second half of the
+metric (200-step sample images/sec) is measured on a bounded number of reverse steps and reported in
+`sample`; nothing is skipped inside a timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C3 = dict(dim=64, dim_mults=(1, 2, 4, 8), channels=3, image_size=128, timesteps=200, kernel_size=15, kernel_std=0.01,
+          blur_routine='Exponential_reflect', sampling_routine='x0_step_down', batch=32, accum=2)
+FWD_GFLOP_PER_IMG = 67.41          # BASELINE.md section 2 (torch FlopCounterMode on the reference Unet)
+TRAIN_GFLOP_PER_IMG = 3 * FWD_GFLOP_PER_IMG
+
+
+def read_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        import statistics
+        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows if len(r) >= 6)]
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference algorithm (oracle port; the reference itself is pure Python
+# under /root/reference, absent on the GPU box) on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_train_sample(batch=2, steps=1, warmup=0, threads=None):
+    """times p_losses forward + backward + Adam of config 3 on the CPU at a bounded batch; -> (img/s, info)"""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import unet_oracle as UO
+    import deblur_oracle as DO
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = {k: v.clone().requires_grad_(True) for k, v in UO.make_unet_state_dict(C3['dim'], C3['dim_mults'], C3['channels']).items()}
+    orc = DO.DeblurOracle(lambda a, b: UO.unet_forward(sd, a, b), image_size=C3['image_size'], channels=3,
+                          timesteps=C3['timesteps'], kernel_std=C3['kernel_std'], kernel_size=C3['kernel_size'],
+                          blur_routine=C3['blur_routine'], sampling_routine=C3['sampling_routine'])
+    opt = torch.optim.Adam(list(sd.values()), lr=2e-5)
+    g = torch.Generator().manual_seed(1234)
+    times = []
+    for it in range(warmup + steps):
+        x = torch.rand(batch, 3, 128, 128, generator=g) * 2 - 1
+        t = torch.randint(0, C3['timesteps'], (batch,), generator=g)
+        t0 = time.time()
+        loss = orc.p_losses(x, t)
+        loss.backward()
+        opt.step(); opt.zero_grad()
+        if it >= warmup:
+            times.append(time.time() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, dict(cores=threads, sample='p_losses fwd+bwd+Adam, config-3 network, batch %d x %d step(s), T=200 q_sample' % (batch, steps),
+                             ms_per_step=sec * 1e3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    v, info = cpu_train_sample(batch=2, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    line = {"impl": "reference", "metric": "training-step images/sec (CelebA-128 deblur UNet)", "value": v, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info['ms_per_step'],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3 train step (bounded sample: batch 2 per step on host cores)", "image": "3x128x128", "T": 200},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": info['cores'], "kind": "port", "sample": info['sample']},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--sample-steps', type=int, default=10, help='reverse steps timed for the sampling half of the metric')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import io
+    import contextlib
+    import torch
+    import torch.distributed as dist
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200 import _lib
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    W = max(3, args.warmup)
+    K = args.steps
+
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        unet = cdm.Unet(dim=C3['dim'], dim_mults=C3['dim_mults'], channels=C3['channels']).to(dev)
+        diffusion = cdm.GaussianDiffusion(unet, image_size=C3['image_size'], device_of_kernel='cuda', channels=3,
+                                          timesteps=C3['timesteps'], loss_type='l1', kernel_std=C3['kernel_std'],
+                                          kernel_size=C3['kernel_size'], blur_routine=C3['blur_routine'],
+                                          train_routine='Final', sampling_routine=C3['sampling_routine'], discrete=False).to(dev)
+        trainer = cdm.Trainer(diffusion, None, image_size=128, train_batch_size=C3['batch'], train_lr=2e-5,
+                              train_num_steps=10 ** 9, gradient_accumulate_every=C3['accum'], ema_decay=0.995, fp16=False,
+                              results_folder='/tmp/colddiff_bench_results', dataset='synthetic')
+    B, A = C3['batch'], C3['accum']
+    img_per_step = B * A
+
+    # distinct batches so consecutive steps never re-read the same inputs; activations (>3 GB/step) exceed the 126 MB L2
+    g = torch.Generator().manual_seed(1234 + rank)
+    nb = 4
+    host = [torch.rand(B, 3, 128, 128, generator=g).mul_(2).sub_(1).pin_memory() for _ in range(nb * A)]
+    resident = [h.to(dev) for h in host]
+    torch.manual_seed(1234 + rank)          # per-rank RNG stream for t (DB:980)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms
+
+    def step_resident(s):
+        trainer.train_step(batches=[resident[(s * A + i) % (nb * A)] for i in range(A)])
+        trainer.step += 1
+
+    losses = []
+
+    def step_e2e(s):
+        loss = trainer.train_step(batches=[host[(s * A + i) % (nb * A)] for i in range(A)])
+        trainer.step += 1
+        losses.append(loss.item())           # D2H read of the step's result
+
+    for s in range(W):
+        step_resident(s)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.reset_launch_count()
+    ms = timed(step_resident, K)
+    launches = _lib.launch_count()
+    ms_e2e = timed(step_e2e, K)
+    if sampler:
+        sampler.stop_flag = True
+    value = img_per_step * world * K / (ms / 1e3)
+    e2e = img_per_step * world * K / (ms_e2e / 1e3)
+
+    # ---- sampling half of the metric: x0_step_down reverse steps (UNet forward + Algorithm-2 update) -----------
+    ema = trainer.ema_model
+    S = args.sample_steps
+    ema.denoise_fn.eval()
+    xs = resident[0]
+    with torch.no_grad():
+        img = ema.opt(xs)                                    # x_T = D(x, T)
+        t = C3['timesteps']
+
+        def rev(s):
+            nonlocal img, t
+            step = torch.full((B,), t - 1, dtype=torch.long, device=dev)
+            x0 = ema.denoise_fn(img, step)
+            img = ema._reverse_step(img, x0, t)
+            t -= 1
+        for s in range(3):
+            rev(s)
+        ms_s = timed(rev, S)
+    sample_ms_per_rev_step = ms_s / S
+    sample_img_s = B * world / (sample_ms_per_rev_step * C3['timesteps'] / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 tap-list convolution), CUDA events around every launch --------
+    peaks, peak_kind = read_peaks()
+    roof = None
+    if rank == 0:
+        eng = unet.engine
+        eng.profile_convs = []
+        step_resident(0)
+        torch.cuda.synchronize()
+        tot_ms = sum(a.elapsed_time(b) for (a, b, f) in eng.profile_convs)
+        tot_fl = sum(f for (a, b, f) in eng.profile_convs)
+        n_launch = len(eng.profile_convs)
+        eng.profile_convs = None
+        tf32_peak = peaks['bf16_tflops_sustained'] / 2.0     # kind::tf32 runs at half the bf16 rate
+        ach = tot_fl / (tot_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::tf32 implicit GEMM; fwd + dgrad launches)",
+                "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                "peak_source": "%s bf16_tflops_sustained / 2 (TF32 rate)" % peak_kind, "launches_timed": n_launch,
+                "share_of_step_ms": tot_ms / (ms / K)}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, info = cpu_train_sample(batch=2, steps=1, warmup=0)
+            cpu = {"value": v, "unit": "images/s", "cores": info['cores'], "kind": "port", "sample": info['sample']}
+        line = {
+            "metric": "training-step images/sec (CelebA-128 deblur UNet; 200-step sample images/sec in `sample`)",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": "C3: CelebA-128 deblur train step = 2 micro-batches x 32 img/GPU (p_losses fwd+bwd) + grad all-reduce + Adam + EMA",
+                       "net": "Unet(dim=64, dim_mults=(1,2,4,8), channels=3)", "T": 200, "blur": "Exponential_reflect k=15 std=0.01",
+                       "global_batch": img_per_step * world, "parallelism": "dp%d" % world,
+                       "l2": "inputs rotate over 4 distinct batch sets; per-step activations (>3 GB) exceed the 126 MB L2"},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": img_per_step * 3 * 128 * 128 * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": losses[-1] if losses else None},
+            "sample": {"value": sample_img_s, "unit": "images/s (200-step x0_step_down, batch 32/GPU)",
+                       "ms_per_reverse_step": sample_ms_per_rev_step, "reverse_steps_timed": S,
+                       "note": "per-step cost is t-independent (cumulative-operator degradation), so 200 steps = 200 x this"},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary() if sampler else None,
+            "train_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -5,5 +5,6 @@ hand-written sm_100a CUDA behind the C ABI in include/colddiff.h (libcolddiff.so
 from . import _lib  # noqa: F401  (raises if the CUDA library has not been built)
 from .unet import Unet
 from .deblurring import GaussianDiffusion
+from .trainer import Trainer
 
-__all__ = ['Unet', 'GaussianDiffusion']
+__all__ = ['Unet', 'GaussianDiffusion', 'Trainer']

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libcolddiff.so')
 CD_MAX_TAPS = 16
 CONV_SIMT, CONV_TC = 0, 1
-ACT_NONE, ACT_GELU = 0, 1
+ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2
 
 
 class ColdDiffError(RuntimeError):
@@ -39,7 +39,8 @@ class ConvDesc(C.Structure):
                 ('oys', C.c_int32), ('oxs', C.c_int32), ('oy0', C.c_int32), ('ox0', C.c_int32),
                 ('bias', C.c_void_p), ('resid', C.c_void_p), ('resid_ld', C.c_int32),
                 ('act', C.c_int32), ('round_tf32', C.c_int32),
-                ('out2', C.c_void_p), ('out2_ld', C.c_int32)]
+                ('out2', C.c_void_p), ('out2_ld', C.c_int32),
+                ('aux', C.c_void_p), ('aux_ld', C.c_int32)]
 
 
 lib.cd_version.restype = C.c_int
@@ -63,8 +64,24 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_LAUNCHES = {'cd_linattn_context': 2, 'cd_conv_wgrad': 2, 'cd_version': 0, 'cd_last_error': 0}
+_launch_count = 0
+
+
 def call(name, *args):
+    global _launch_count
+    _launch_count += _LAUNCHES.get(name, 1)
     _check(getattr(lib, name)(*args), name)
+
+
+def reset_launch_count():
+    global _launch_count
+    _launch_count = 0
+
+
+def launch_count():
+    """kernels launched through the C ABI since the last reset (each entry point launches >= 1 kernel)"""
+    return _launch_count
 
 
 EXPORTS = [

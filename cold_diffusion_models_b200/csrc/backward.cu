@@ -203,8 +203,8 @@ attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __
                    const float* __restrict__ ksum, const float* __restrict__ dctxn, const float* __restrict__ rowdot,
                    float* __restrict__ dqkv, int dld) {
   __shared__ float dc[4096];
-  __shared__ float ps[32][129];
-  __shared__ float vs[32][129];
+  __shared__ float ps[32][128];
+  __shared__ float vs[32][128];
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * 32;
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) dc[i] = dctxn[static_cast<long long>(b) * 4096 + i];
@@ -316,7 +316,23 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __res
   if (y) y[i] = dy[i] * cd_gelu_grad(p);
 }
 
+// out[pix][c] = a[pix][c] + b[pix][c]
+__global__ void add_kernel(const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
+                           float* __restrict__ out, int out_ld, long long npix, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  const long long pix = i / C; const int c = static_cast<int>(i % C);
+  out[pix * out_ld + c] = a[pix * a_ld + c] + b[pix * b_ld + c];
+}
+
 }  // namespace
+
+extern "C" int cd_add(const float* a, int a_ld, const float* b, int b_ld, float* out, int out_ld, int64_t npix, int C,
+                      void* stream) {
+  add_kernel<<<cd_cdiv(npix * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, a_ld, b, b_ld, out, out_ld, npix, C);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int h_ld, const float* stats,
                                 const float* g, int64_t npix, int C, const float* addend, int addend_ld,

@@ -17,6 +17,7 @@ struct SimtParams {
   float* out; int out_ld, Ho, Wo, oys, oxs, oy0, ox0;
   const float* bias; const float* resid; int resid_ld; int act, round_tf32;
   float* out2; int out2_ld;
+  const float* aux; int aux_ld;
   int tiles_per_img;
 };
 
@@ -85,6 +86,7 @@ conv_simt_kernel(const SimtParams p) {
       if (p.resid) v += p.resid[pix * p.resid_ld + co];
       if (p.out2) p.out2[pix * p.out2_ld + co] = v;
       if (p.act == CD_ACT_GELU) v = cd_gelu(v);
+      else if (p.act == CD_ACT_GELU_BWD) v *= cd_gelu_grad(p.aux[pix * p.aux_ld + co]);
       if (p.round_tf32) v = cd_round_tf32(v);
       p.out[pix * p.out_ld + co] = v;
     }
@@ -98,6 +100,7 @@ struct WgradParams {
   const float* src; const float* dout; int dout_ld, Ho, Wo, oys, oxs, oy0, ox0;
   float* dw;
   int splits, pix_per_split;
+  int per_batch;   // splits never cross images; dw indexed [b][tap][co][ci]
 };
 
 __global__ void __launch_bounds__(256)
@@ -108,9 +111,19 @@ wgrad_simt_kernel(const WgradParams p) {
   const int co0 = blockIdx.x * TM, ci0 = blockIdx.y * TNc;
   const int tap = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const int tx = tid % 16, ty = tid / 16;
-  const long long total = static_cast<long long>(p.B) * p.Hg * p.Wg;
-  const long long pbeg = static_cast<long long>(split) * p.pix_per_split;
-  long long pend = pbeg + p.pix_per_split; if (pend > total) pend = total;
+  long long total = static_cast<long long>(p.B) * p.Hg * p.Wg;
+  long long pbeg = static_cast<long long>(split) * p.pix_per_split;
+  long long pend = pbeg + p.pix_per_split;
+  int wb = 0;
+  if (p.per_batch) {                       // split = b * splits_per_img + s
+    const long long per_img = static_cast<long long>(p.Hg) * p.Wg;
+    const int spi = p.splits / p.B;
+    wb = split / spi;
+    pbeg = wb * per_img + static_cast<long long>(split % spi) * p.pix_per_split;
+    pend = pbeg + p.pix_per_split;
+    total = (wb + 1) * per_img;
+  }
+  if (pend > total) pend = total;
   float acc[4][4] = {};
   // loader: pixel row = tid / 16 (16 pixels per chunk), channel quad = (tid % 16) * 4
   const int lp = tid >> 4, lc = (tid & 15) * 4;
@@ -155,7 +168,7 @@ wgrad_simt_kernel(const WgradParams p) {
     for (int j = 0; j < 4; ++j) {
       const int ci = ci0 + tx * 4 + j;
       if (ci >= p.C) continue;
-      atomicAdd(p.dw + (static_cast<long long>(tap) * p.Cout + co) * p.C + ci, acc[i][j]);
+      atomicAdd(p.dw + ((static_cast<long long>(wb) * p.ntaps + tap) * p.Cout + co) * p.C + ci, acc[i][j]);
     }
   }
 }
@@ -232,7 +245,8 @@ static int conv_fwd_simt(const CdConvDesc* d, cudaStream_t st) {
   }
   p.out = d->out; p.out_ld = d->out_ld; p.Ho = d->Ho; p.Wo = d->Wo; p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0;
   p.bias = d->bias; p.resid = d->resid; p.resid_ld = d->resid_ld; p.act = d->act; p.round_tf32 = d->round_tf32;
-  p.out2 = d->out2; p.out2_ld = d->out2_ld;
+  p.out2 = d->out2; p.out2_ld = d->out2_ld; p.aux = d->aux; p.aux_ld = d->aux_ld;
+  CD_REQUIRE(d->act != CD_ACT_GELU_BWD || d->aux, "conv_simt: GELU_BWD needs aux");
   p.tiles_per_img = cd_cdiv(d->Hg * d->Wg, TM);
   dim3 grid(d->B * p.tiles_per_img, cd_cdiv(d->Cout, TNc));
   conv_simt_kernel<<<grid, 256, 0, st>>>(p);
@@ -253,7 +267,7 @@ extern "C" int cd_conv_fwd(const CdConvDesc* d, int impl, void* stream) {
 extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, float* db,
                              int impl, void* stream) {
   (void)impl;
-  CD_REQUIRE(d && d->nsrc == 1 && !d->s[0].w_per_batch, "cd_conv_wgrad: single shared-weight source only");
+  CD_REQUIRE(d && d->nsrc == 1, "cd_conv_wgrad: single source only");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const CdConvSrc& c = d->s[0];
   WgradParams p{};
@@ -268,8 +282,18 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   const int max_splits = cd_cdiv(total, 256);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
+  p.per_batch = c.w_per_batch;
+  if (c.w_per_batch) {
+    const long long per_img = static_cast<long long>(d->Hg) * d->Wg;
+    int spi = cd_cdiv(splits, d->B); if (spi < 1) spi = 1;
+    p.pix_per_split = cd_cdiv(cd_cdiv(per_img, spi), TK) * TK;
+    spi = cd_cdiv(per_img, p.pix_per_split);
+    splits = spi * d->B;
+  } else {
+    p.pix_per_split = cd_cdiv(cd_cdiv(total, splits), TK) * TK;
+    splits = cd_cdiv(total, p.pix_per_split);
+  }
   p.splits = splits;
-  p.pix_per_split = cd_cdiv(cd_cdiv(total, splits), TK) * TK;
   dim3 grid(cd_cdiv(d->Cout, TM), cd_cdiv(c.C, TNc), c.ntaps * splits);
   wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);
   CD_LAUNCH_CHECK();

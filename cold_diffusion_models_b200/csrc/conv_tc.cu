@@ -41,6 +41,7 @@ struct TcParams {
   const float* resid; int resid_ld;
   int act; int round_tf32;
   float* out2; int out2_ld;
+  const float* aux; int aux_ld;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -238,6 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       float* orow = p.out + pix * p.out_ld;
       const float* rrow = p.resid ? p.resid + pix * p.resid_ld : nullptr;
       float* o2row = p.out2 ? p.out2 + pix * p.out2_ld : nullptr;
+      const float* arow = p.aux ? p.aux + pix * p.aux_ld : nullptr;
 
       const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
       mbar_wait(&tmem_full[acc], accph);
@@ -264,6 +266,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               }
               if (o2row) *reinterpret_cast<float4*>(o2row + co0 + c + j) = v;
               if (p.act == CD_ACT_GELU) { v.x = cd_gelu(v.x); v.y = cd_gelu(v.y); v.z = cd_gelu(v.z); v.w = cd_gelu(v.w); }
+              else if (p.act == CD_ACT_GELU_BWD) {
+                const float4 a = *reinterpret_cast<const float4*>(arow + co0 + c + j);
+                v.x *= cd_gelu_grad(a.x); v.y *= cd_gelu_grad(a.y); v.z *= cd_gelu_grad(a.z); v.w *= cd_gelu_grad(a.w);
+              }
               if (p.round_tf32) { v.x = cd_round_tf32(v.x); v.y = cd_round_tf32(v.y); v.z = cd_round_tf32(v.z); v.w = cd_round_tf32(v.w); }
               *reinterpret_cast<float4*>(orow + co0 + c + j) = v;
             }
@@ -274,6 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               if (rrow) v += rrow[co0 + c + j];
               if (o2row) o2row[co0 + c + j] = v;
               if (p.act == CD_ACT_GELU) v = cd_gelu(v);
+              else if (p.act == CD_ACT_GELU_BWD) v *= cd_gelu_grad(arow[co0 + c + j]);
               if (p.round_tf32) v = cd_round_tf32(v);
               orow[co0 + c + j] = v;
             }
@@ -366,7 +373,8 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   p.out = d->out; p.out_ld = d->out_ld; p.Ho = d->Ho; p.Wo = d->Wo;
   p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0;
   p.bias = d->bias; p.resid = d->resid; p.resid_ld = d->resid_ld; p.act = d->act; p.round_tf32 = d->round_tf32;
-  p.out2 = d->out2; p.out2_ld = d->out2_ld;
+  p.out2 = d->out2; p.out2_ld = d->out2_ld; p.aux = d->aux; p.aux_ld = d->aux_ld;
+  CD_REQUIRE(d->act != CD_ACT_GELU_BWD || (d->aux && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0 && d->aux_ld % 4 == 0), "conv_tc: GELU_BWD needs an aligned aux");
   CD_REQUIRE((reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && d->out_ld % 4 == 0, "conv_tc: out must be 16B aligned");
   CD_REQUIRE(!d->resid || ((reinterpret_cast<uintptr_t>(d->resid) & 15) == 0 && d->resid_ld % 4 == 0), "conv_tc: resid alignment");
   CD_REQUIRE(!d->out2 || ((reinterpret_cast<uintptr_t>(d->out2) & 15) == 0 && d->out2_ld % 4 == 0), "conv_tc: out2 alignment");

@@ -121,54 +121,49 @@ blur_apply_kernel(const float* __restrict__ x, float* __restrict__ out, const fl
   }
 }
 
-// out = xt - A_hi xhat A_hi^T + A_lo xhat A_lo^T   (index -1 = identity)
+// out = xt - A_hi xhat A_hi^T + A_lo xhat A_lo^T   (index -1 = identity).
+// smem: As | Xs | Yt (Z overwrites Xs; xhat is re-read from L2 for the second term) = 196 KB at S = 128.
 __global__ void __launch_bounds__(256)
 blur_step_down_kernel(const float* __restrict__ xt, const float* __restrict__ xhat, float* __restrict__ out,
                       const float* __restrict__ ops, int t_hi, int t_lo, int S, int T, int collapse_last) {
   extern __shared__ __align__(16) float sm[];
   const int ldp = S + 4;
-  float* As = sm; float* Xs = As + S * S; float* Yt = Xs + S * ldp; float* Zs = Yt + S * ldp; float* scratch = Zs + S * ldp;
+  float* As = sm; float* Xs = As + S * S; float* Yt = Xs + S * ldp; float* scratch = Yt + S * ldp;
   const long long pl = static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x;
   const float* xh = xhat + pl * S * S;
   const int per_row = S >> 2;
+  // ---- high index term: Xs <- A_hi xhat A_hi^T ----
   load_plane(Xs, ldp, xh, S);
-  // ---- high index term ----
   if (t_hi >= 0) load_plane(As, S, ops + static_cast<long long>(t_hi) * S * S, S);
   __syncthreads();
-  if (t_hi >= 0) plane_apply(As, Xs, Yt, Zs, S, ldp);
-  else {
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) Zs[(i / S) * ldp + (i % S)] = Xs[(i / S) * ldp + (i % S)];
-    __syncthreads();
-  }
+  if (t_hi >= 0) plane_apply(As, Xs, Yt, Xs, S, ldp);
   float mean_hi = 0.f;
   const bool collapse = collapse_last && t_hi == T - 1;
   if (collapse) {
     float s = 0.f;
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) s += Zs[(i / S) * ldp + (i % S)];
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) s += Xs[(i / S) * ldp + (i % S)];
     mean_hi = block_sum(s, scratch) / (S * S);
   }
-  // d = xt - Zhi   (kept in registers: each thread owns fixed float4 slots)
-  float4 d[16];   // S <= 128: (128*128/4)/256 = 16 slots per thread
+  // d = xt - Zhi   (kept in registers: each thread owns fixed float4 slots; S <= 128 -> <= 16 slots)
+  float4 d[16];
   int nslot = 0;
   for (int i = threadIdx.x; i < (S * S) >> 2; i += blockDim.x, ++nslot) {
     const int r = i / per_row, c = (i % per_row) * 4;
     const float4 a = __ldg(reinterpret_cast<const float4*>(xt + pl * S * S) + i);
-    float4 z = *reinterpret_cast<const float4*>(Zs + r * ldp + c);
+    float4 z = *reinterpret_cast<const float4*>(Xs + r * ldp + c);
     if (collapse) z = make_float4(mean_hi, mean_hi, mean_hi, mean_hi);
     d[nslot] = make_float4(a.x - z.x, a.y - z.y, a.z - z.z, a.w - z.w);
   }
   __syncthreads();
-  // ---- low index term ----
-  if (t_lo >= 0) {
-    load_plane(As, S, ops + static_cast<long long>(t_lo) * S * S, S);
-    __syncthreads();
-    plane_apply(As, Xs, Yt, Zs, S, ldp);
-  }
-  const float* Zlo = t_lo >= 0 ? Zs : Xs;
+  // ---- low index term: Xs <- A_lo xhat A_lo^T ----
+  load_plane(Xs, ldp, xh, S);
+  if (t_lo >= 0) load_plane(As, S, ops + static_cast<long long>(t_lo) * S * S, S);
+  __syncthreads();
+  if (t_lo >= 0) plane_apply(As, Xs, Yt, Xs, S, ldp);
   nslot = 0;
   for (int i = threadIdx.x; i < (S * S) >> 2; i += blockDim.x, ++nslot) {
     const int r = i / per_row, c = (i % per_row) * 4;
-    const float4 z = *reinterpret_cast<const float4*>(Zlo + r * ldp + c);
+    const float4 z = *reinterpret_cast<const float4*>(Xs + r * ldp + c);
     float4 o = d[nslot];
     o.x += z.x; o.y += z.y; o.z += z.z; o.w += z.w;
     reinterpret_cast<float4*>(out + pl * S * S)[i] = o;
@@ -210,7 +205,20 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
   }
 }
 
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, long long n, float beta, int mode) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    ema[i] = mode == 1 ? p[i] : ema[i] * beta + (1.f - beta) * p[i];
+}
+
 }  // namespace
+
+extern "C" int cd_ema_update(float* ema, const float* p, int64_t n, float beta, int mode, void* stream) {
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 16) blocks = 148 * 16; if (blocks < 1) blocks = 1;
+  ema_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(ema, p, n, beta, mode);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
 
 static size_t blur_smem(int S, int planes) { return sizeof(float) * (size_t(S) * S + size_t(planes) * S * (S + 4) + 32); }
 
@@ -230,7 +238,7 @@ extern "C" int cd_blur_apply(const float* x, float* out, const float* ops, const
 extern "C" int cd_blur_step_down(const float* xt, const float* xhat, float* out, const float* ops,
                                  int t_hi, int t_lo, int B, int C, int S, int T, int collapse_last, void* stream) {
   CD_REQUIRE(S % 4 == 0 && S >= 4 && S <= 128, "cd_blur_step_down: image size %d unsupported", S);
-  const size_t smem = blur_smem(S, 3);
+  const size_t smem = blur_smem(S, 2);
   static size_t attr = 0;
   if (smem > attr) { CD_CUDA(cudaFuncSetAttribute(blur_step_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   dim3 grid(C, B);

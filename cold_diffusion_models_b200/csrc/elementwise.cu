@@ -18,7 +18,7 @@ dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, in
                   const float* __restrict__ wdw, const float* __restrict__ bdw, const float* __restrict__ cond, int cond_ld,
                   const float* __restrict__ g, const float* __restrict__ beta, float eps,
                   float* __restrict__ y, int y_ld, float* __restrict__ stats, float* __restrict__ hpre, int hpre_ld,
-                  int round_tf32) {
+                  int round_tf32, int flip, const float* __restrict__ addend, int addend_ld) {
   extern __shared__ float red[];                 // [strips][warps_per_strip][kStrip]
   const int cq = C >> 2;                         // channel quads (threads per strip)
   const int strip_in_block = threadIdx.x / cq;
@@ -45,8 +45,10 @@ dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, in
       if (iy < 0 || iy >= H) continue;
       float4 wv[7];
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) wv[kx] = make_float4(__ldg(w0 + ky * 7 + kx), __ldg(w1 + ky * 7 + kx),
-                                                          __ldg(w2 + ky * 7 + kx), __ldg(w3 + ky * 7 + kx));
+      for (int kx = 0; kx < 7; ++kx) {
+        const int wi = flip ? 48 - (ky * 7 + kx) : ky * 7 + kx;
+        wv[kx] = make_float4(__ldg(w0 + wi), __ldg(w1 + wi), __ldg(w2 + wi), __ldg(w3 + wi));
+      }
       const float* row = x + ((static_cast<long long>(b) * H + iy) * W) * x_ld + c0;
 #pragma unroll
       for (int ix = 0; ix < kStrip + 6; ++ix) {
@@ -63,7 +65,7 @@ dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, in
         }
       }
     }
-    float4 add = *reinterpret_cast<const float4*>(bdw + c0);
+    float4 add = bdw ? *reinterpret_cast<const float4*>(bdw + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (cond) {
       const float4 cv = *reinterpret_cast<const float4*>(cond + static_cast<long long>(b) * cond_ld + c0);
       add.x += cv.x; add.y += cv.y; add.z += cv.z; add.w += cv.w;
@@ -72,6 +74,13 @@ dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, in
     for (int i = 0; i < kStrip; ++i) { acc[i].x += add.x; acc[i].y += add.y; acc[i].z += add.z; acc[i].w += add.w; }
   }
   const long long pix0 = (static_cast<long long>(b) * H + yy) * W + x0;
+  if (addend && active) {
+#pragma unroll
+    for (int i = 0; i < kStrip; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(addend + (pix0 + i) * addend_ld + c0);
+      acc[i].x += a.x; acc[i].y += a.y; acc[i].z += a.z; acc[i].w += a.w;
+    }
+  }
   if (hpre && active) {
 #pragma unroll
     for (int i = 0; i < kStrip; ++i) *reinterpret_cast<float4*>(hpre + (pix0 + i) * hpre_ld + c0) = acc[i];
@@ -143,7 +152,8 @@ __global__ void dwconv7_small_kernel(const float* __restrict__ x, int x_ld, int 
                                      const float* __restrict__ wdw, const float* __restrict__ bdw,
                                      const float* __restrict__ cond, int cond_ld, const float* __restrict__ g,
                                      const float* __restrict__ beta, float eps, float* __restrict__ y, int y_ld,
-                                     float* __restrict__ stats, float* __restrict__ hpre, int hpre_ld, int round_tf32) {
+                                     float* __restrict__ stats, float* __restrict__ hpre, int hpre_ld, int round_tf32,
+                                     int flip, const float* __restrict__ addend, int addend_ld) {
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long npix = static_cast<long long>(B) * H * W;
   if (pix >= npix) return;
@@ -153,14 +163,15 @@ __global__ void dwconv7_small_kernel(const float* __restrict__ x, int x_ld, int 
   float hbuf[16];
   float mean = 0.f;
   for (int c = 0; c < C; ++c) {
-    float a = bdw[c] + (cond ? cond[static_cast<long long>(b) * cond_ld + c] : 0.f);
+    float a = (bdw ? bdw[c] : 0.f) + (cond ? cond[static_cast<long long>(b) * cond_ld + c] : 0.f);
+    if (addend) a += addend[pix * addend_ld + c];
     for (int ky = 0; ky < 7; ++ky) {
       const int iy = yy + ky - 3;
       if (iy < 0 || iy >= H) continue;
       for (int kx = 0; kx < 7; ++kx) {
         const int ix = xx + kx - 3;
         if (ix < 0 || ix >= W) continue;
-        a = fmaf(x[((static_cast<long long>(b) * H + iy) * W + ix) * x_ld + c], wdw[c * 49 + ky * 7 + kx], a);
+        a = fmaf(x[((static_cast<long long>(b) * H + iy) * W + ix) * x_ld + c], wdw[c * 49 + (flip ? 48 - (ky * 7 + kx) : ky * 7 + kx)], a);
       }
     }
     hbuf[c] = a; mean += a;
@@ -382,22 +393,23 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, i
 extern "C" int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, int C,
                                  const float* w_dw, const float* b_dw, const float* cond, int cond_ld,
                                  const float* g, const float* beta, float eps, float* y, int y_ld,
-                                 float* stats, float* hpre, int hpre_ld, int round_tf32, void* stream) {
+                                 float* stats, float* hpre, int hpre_ld, int round_tf32, int flip,
+                                 const float* addend, int addend_ld, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int cq = C / 4;
   const bool fast = (C % 4 == 0) && cq >= 8 && cq <= 256 && (cq & (cq - 1)) == 0 && (W % kStrip == 0) &&
-                    (x_ld % 4 == 0) && (y_ld % 4 == 0) && (!hpre || hpre_ld % 4 == 0);
+                    (x_ld % 4 == 0) && (y_ld % 4 == 0) && (!hpre || hpre_ld % 4 == 0) && (!addend || addend_ld % 4 == 0);
   if (fast) {
     const int strips_per_block = 256 / cq;
     const long long nstrips = static_cast<long long>(B) * H * (W / kStrip);
     const int blocks = cd_cdiv(nstrips, strips_per_block);
     const size_t smem = sizeof(float) * strips_per_block * ((cq + 31) / 32) * kStrip;
-    if (g) dwconv7_ln_kernel<true><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
-    else dwconv7_ln_kernel<false><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+    if (g) dwconv7_ln_kernel<true><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32, flip, addend, addend_ld);
+    else dwconv7_ln_kernel<false><<<blocks, 256, smem, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32, flip, addend, addend_ld);
   } else {
     CD_REQUIRE(C <= 16, "cd_dwconv7_ln_fwd: unsupported channel count %d (W=%d)", C, W);
     const long long npix = static_cast<long long>(B) * H * W;
-    dwconv7_small_kernel<<<cd_cdiv(npix, 128), 128, 0, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32);
+    dwconv7_small_kernel<<<cd_cdiv(npix, 128), 128, 0, st>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32, flip, addend, addend_ld);
   }
   CD_LAUNCH_CHECK();
   return 0;

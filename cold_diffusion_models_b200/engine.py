@@ -28,6 +28,10 @@ def _tc_ok(*chans):
     return all(c % 32 == 0 for c in chans)
 
 
+class _BackwardHolder:
+    """placeholder base; engine_bwd.BackwardMixin's methods are grafted on at import time (avoids a cycle)"""
+
+
 class BlockSpec:
     """one ConvNextBlock (DB:135-165)"""
 
@@ -52,7 +56,7 @@ class AttnSpec:
         self.dim = self.norm.g.shape[1]
 
 
-class UnetEngine:
+class UnetEngine(_BackwardHolder):
     def __init__(self, unet):
         self.unet = unet
         self.dev = next(unet.parameters()).device
@@ -156,8 +160,19 @@ class UnetEngine:
     # ------------------------------------------------------------------------------------------
     # forward pieces.  `save` is None for inference; a dict for training (tensors kept for backward)
     # ------------------------------------------------------------------------------------------
+    profile_convs = None          # bench.py: list of (event0, event1, flops) per tensor-core conv launch
+
     def _conv(self, desc, tc):
-        ops.conv_fwd(desc, self.conv_impl if tc else CONV_SIMT)
+        impl = self.conv_impl if tc else CONV_SIMT
+        if self.profile_convs is not None and impl == CONV_TC:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.conv_fwd(desc, impl)
+            e1.record()
+            k = sum(desc.s[i].ntaps * desc.s[i].C for i in range(desc.nsrc))
+            self.profile_convs.append((e0, e1, 2.0 * desc.B * desc.Hg * desc.Wg * desc.Cout * k))
+            return
+        ops.conv_fwd(desc, impl)
 
     def _block(self, bs, xv, outv, cond_all, save, tag):
         B, H, W = xv.B, xv.H, xv.W
@@ -178,7 +193,7 @@ class UnetEngine:
         be = m.net[0].b if bs.has_norm else None
         call('cd_dwconv7_ln_fwd', C.c_void_p(xv.addr()), xv.ld, B, H, W, bs.din, ptr(m.ds_conv.weight), ptr(m.ds_conv.bias),
              cond if cond is not None else C.c_void_p(0), self.sumC, ptr(g), ptr(be), C.c_float(1e-5), ptr(hn), ld_in,
-             ptr(stats), ptr(hpre), ld_in, 0, stream())
+             ptr(stats), ptr(hpre), ld_in, 0, 0, C.c_void_p(0), 0, stream())
         hv = View(hn, 0, bs.din)
         u = self.buf('u.' + uniq, (B, H, W, bs.dmid))
         pre = self.buf('pre.' + bs.name, (B, H, W, bs.dmid)) if save is not None else None
@@ -333,3 +348,9 @@ class UnetEngine:
         if save is not None:
             save['final'] = dict(x=View(fo), x_in=x)
         return out
+
+
+from .engine_bwd import BackwardMixin as _BM  # noqa: E402
+for _k, _v in _BM.__dict__.items():
+    if not _k.startswith('__'):
+        setattr(_BackwardHolder, _k, _v)

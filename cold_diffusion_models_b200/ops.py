@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import lib, ptr, stream, call, ConvDesc, ConvSrc, CONV_SIMT, CONV_TC, ACT_NONE, ACT_GELU
+from ._lib import lib, ptr, stream, call, ConvDesc, ConvSrc, CONV_SIMT, CONV_TC, ACT_NONE, ACT_GELU, ACT_GELU_BWD
 
 
 # --------------------------------------------------------------------------------------------
@@ -90,7 +90,7 @@ class View:
 
 
 def make_conv_desc(srcs, out, grid, *, stride=1, Cout, bias=None, resid=None, act=ACT_NONE,
-                   round_tf32=False, out_map=(1, 1, 0, 0), out2=None):
+                   round_tf32=False, out_map=(1, 1, 0, 0), out2=None, aux=None):
     """srcs: list of (View, taps[(ky,kx,dy,dx)], packed_w, w_per_batch); out/resid/out2: View;
     grid: (B, Hg, Wg)."""
     d = ConvDesc()
@@ -116,6 +116,8 @@ def make_conv_desc(srcs, out, grid, *, stride=1, Cout, bias=None, resid=None, ac
     d.round_tf32 = int(round_tf32)
     if out2 is not None:
         d.out2 = out2.addr(); d.out2_ld = out2.ld
+    if aux is not None:
+        d.aux = aux.addr(); d.aux_ld = aux.ld
     d._keep = keep
     return d
 

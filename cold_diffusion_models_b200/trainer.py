@@ -1,0 +1,233 @@
+"""Drop-in `Trainer` for the *_diffusion_pytorch packages (reference: DB:1057-1236) on the B200 engine.
+
+Same constructor keywords, attributes (`model`, `ema_model`, `opt`, `dl`, `ds`, `step`) and methods
+(`train`, `save`, `load`, `step_ema`, `reset_parameters`) and the same checkpoint format
+{'step','model','ema'} with reference state_dict keys.  What differs is execution:
+
+  * one process per GPU (torchrun); gradients live in ONE flat fp32 buffer that is all-reduced with a single
+    NCCL call per optimizer step (the reference's nn.DataParallel re-broadcasts all parameters and reduce-adds
+    all gradients every micro-step, DB:1192 + celebA_128.py:102);
+  * Adam (torch defaults, DB:1117) + the EMA update (DB:73-81,1134-1138) + gradient zeroing are one fused
+    multi-tensor kernel (cd_adam_ema_step) over flat parameter / moment / EMA buffers;
+  * parameters and EMA parameters are views of flat buffers, so `state_dict()` stays reference-shaped.
+"""
+import copy
+import ctypes as C
+from functools import partial  # noqa: F401
+from pathlib import Path
+
+import torch
+from torch.utils import data
+
+from ._lib import call, ptr, stream
+
+
+def cycle(dl):
+    while True:
+        for d in dl:
+            yield d
+
+
+def _unwrap(m):
+    return m.module if hasattr(m, 'module') else m
+
+
+class SyntheticImages(data.Dataset):
+    """x ~ U(-1,1) fp32 NCHW images of the configured shape (matches ToTensor()*2-1, DB:994-995)."""
+
+    def __init__(self, image_size, channels=3, length=1 << 30, seed=1234):
+        self.shape = (channels, image_size, image_size)
+        self.length = length
+        self.seed = seed
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed + i)
+        return torch.rand(self.shape, generator=g) * 2 - 1
+
+
+class ImageFolderDataset(data.Dataset):
+    """folder of images -> (C,H,W) fp32 in [-1,1] (reference Dataset / Dataset_Aug1, DB:983-1026)."""
+
+    def __init__(self, folder, image_size, exts=('jpg', 'jpeg', 'png'), augment=False):
+        from torchvision import transforms
+        self.paths = [p for ext in exts for p in Path(f'{folder}').glob(f'**/*.{ext}')]
+        ops_ = []
+        if augment:
+            ops_ += [transforms.Resize((int(image_size * 1.12), int(image_size * 1.12))), transforms.RandomCrop(image_size),
+                     transforms.RandomHorizontalFlip()]
+        else:
+            ops_ += [transforms.Resize((int(image_size * 1.12), int(image_size * 1.12))), transforms.CenterCrop(image_size)]
+        ops_ += [transforms.ToTensor(), transforms.Lambda(lambda t: (t * 2) - 1)]
+        self.transform = transforms.Compose(ops_)
+
+    def __len__(self):
+        return len(self.paths)
+
+    def __getitem__(self, index):
+        from PIL import Image
+        return self.transform(Image.open(self.paths[index]))
+
+
+class FusedAdamEMA:
+    """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) + EMA as one kernel over flat buffers."""
+
+    def __init__(self, engine, ema_engine=None, lr=2e-5, betas=(0.9, 0.999), eps=1e-8):
+        self.engine, self.ema_engine = engine, ema_engine
+        engine.flatten_params()
+        if ema_engine is not None:
+            ema_engine.flatten_params()
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps)]
+        self.m = torch.zeros_like(engine.flat_param)
+        self.v = torch.zeros_like(engine.flat_param)
+        self.t = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.engine.flat_grad.zero_()
+
+    def step(self, ema_mode=0, ema_beta=0.0, grad_scale=1.0):
+        g = self.param_groups[0]
+        self.t += 1
+        e = self.engine
+        ema = self.ema_engine.flat_param if (self.ema_engine is not None and ema_mode) else None
+        call('cd_adam_ema_step', ptr(e.flat_param), ptr(e.flat_grad), ptr(self.m), ptr(self.v), ptr(ema),
+             C.c_int64(e.flat_param.numel()), C.c_float(g['lr']), C.c_float(g['betas'][0]), C.c_float(g['betas'][1]),
+             C.c_float(g['eps']), self.t, int(ema_mode) if ema is not None else 0, C.c_float(ema_beta),
+             C.c_float(grad_scale), stream())
+        e.mark_weights_dirty()
+        if ema is not None:
+            self.ema_engine.mark_weights_dirty()
+
+    def state_dict(self):
+        return dict(t=self.t, m=self.m, v=self.v, param_groups=self.param_groups)
+
+    def load_state_dict(self, sd):
+        self.t = sd['t']; self.m.copy_(sd['m']); self.v.copy_(sd['v'])
+
+
+class Trainer(object):
+    def __init__(self, diffusion_model, folder, *, ema_decay=0.995, image_size=128, train_batch_size=32, train_lr=2e-5,
+                 train_num_steps=100000, gradient_accumulate_every=2, fp16=False, step_start_ema=2000,
+                 update_ema_every=10, save_and_sample_every=1000, results_folder='./results', load_path=None,
+                 dataset=None, shuffle=True):
+        super().__init__()
+        if fp16:
+            raise NotImplementedError("fp16/apex path of the reference is dead code (fp16=False in every driver)")
+        self.model = diffusion_model
+        self.ema_decay = ema_decay
+        self.ema_model = copy.deepcopy(self.model)
+        self.update_ema_every = update_ema_every
+        self.step_start_ema = step_start_ema
+        self.save_and_sample_every = save_and_sample_every
+        self.batch_size = train_batch_size
+        self.image_size = image_size
+        self.gradient_accumulate_every = gradient_accumulate_every
+        self.train_num_steps = train_num_steps
+
+        core = _unwrap(self.model)
+        channels = getattr(core, 'channels', 3)
+        if folder is None or dataset == 'synthetic':
+            self.ds = SyntheticImages(image_size, channels)
+            self.dl = cycle(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=False, pin_memory=True,
+                                            num_workers=0, drop_last=True))
+        else:
+            aug = dataset in ('mnist', 'cifar10', 'flower', 'celebA', 'AFHQ')
+            print(dataset, "DA used" if aug else "")
+            self.ds = ImageFolderDataset(folder, image_size, augment=aug)
+            self.dl = cycle(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=shuffle, pin_memory=True,
+                                            num_workers=8 if aug else 16, drop_last=True))
+        self._unet = core.denoise_fn
+        self._ema_unet = _unwrap(self.ema_model).denoise_fn
+        self.opt = FusedAdamEMA(self._unet.engine, self._ema_unet.engine, lr=train_lr)
+        self.step = 0
+        self.results_folder = Path(results_folder)
+        self.results_folder.mkdir(exist_ok=True)
+        self.fp16 = fp16
+        self.reset_parameters()
+        if load_path is not None:
+            self.load(load_path)
+        self._world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+
+    # ---- reference API ------------------------------------------------------------------------------
+    def reset_parameters(self):
+        self.ema_model.load_state_dict(self.model.state_dict())
+
+    def step_ema(self):
+        """stand-alone EMA update (the training loop fuses this into the optimizer kernel)."""
+        if self.step < self.step_start_ema:
+            self.reset_parameters()
+            return
+        e, m = self._ema_unet.engine, self._unet.engine
+        call('cd_ema_update', ptr(e.flat_param), ptr(m.flat_param), C.c_int64(e.flat_param.numel()),
+             C.c_float(self.ema_decay), 2, stream())
+        e.mark_weights_dirty()
+
+    def save(self, itrs=None):
+        d = {'step': self.step, 'model': self.model.state_dict(), 'ema': self.ema_model.state_dict()}
+        name = 'model.pt' if itrs is None else f'model_{itrs}.pt'
+        torch.save(d, str(self.results_folder / name))
+
+    def load(self, load_path):
+        print("Loading : ", load_path)
+        d = torch.load(load_path, map_location='cpu')
+        self.step = d['step']
+        self.model.load_state_dict(_match_prefix(d['model'], self.model))
+        self.ema_model.load_state_dict(_match_prefix(d['ema'], self.ema_model))
+
+    # ---- hot loop --------------------------------------------------------------------------------------
+    def train_step(self, batches=None):
+        """one optimizer step = gradient_accumulate_every micro-batches (DB:1188-1204). Returns mean loss (tensor)."""
+        u_loss = None
+        for i in range(self.gradient_accumulate_every):
+            d = batches[i] if batches is not None else next(self.dl)
+            d = d.cuda(non_blocking=True)
+            loss = torch.mean(self.model(d))
+            u_loss = loss.detach() if u_loss is None else u_loss + loss.detach()
+            (loss / self.gradient_accumulate_every).backward()
+        eng = self._unet.engine
+        scale = 1.0
+        if self._world > 1:
+            torch.distributed.all_reduce(eng.flat_grad)          # one NCCL all-reduce per optimizer step
+            scale = 1.0 / self._world
+        ema_mode = 0
+        if self.step % self.update_ema_every == 0:
+            ema_mode = 1 if self.step < self.step_start_ema else 2
+        self.opt.step(ema_mode=ema_mode, ema_beta=self.ema_decay, grad_scale=scale)
+        self.opt.zero_grad()
+        return u_loss / self.gradient_accumulate_every
+
+    def train(self):
+        acc_loss = 0
+        while self.step < self.train_num_steps:
+            loss = self.train_step()
+            if self.step % 100 == 0:
+                print(f'{self.step}: {loss.item()}')
+            acc_loss = acc_loss + loss
+            if self.step != 0 and self.step % self.save_and_sample_every == 0:
+                from torchvision import utils
+                milestone = self.step // self.save_and_sample_every
+                og_img = next(self.dl).cuda()
+                xt, direct_recons, all_images = _unwrap(self.ema_model).sample(batch_size=self.batch_size, img=og_img)
+                for name, img in (('og', og_img), ('recon', all_images), ('direct_recons', direct_recons), ('xt', xt)):
+                    utils.save_image((img + 1) * 0.5, str(self.results_folder / f'sample-{name}-{milestone}.png'), nrow=6)
+                acc_loss = acc_loss / (self.save_and_sample_every + 1)
+                print(f'Mean of last {self.step}: {float(acc_loss)}')
+                acc_loss = 0
+                self.save()
+                if self.step % (self.save_and_sample_every * 100) == 0:
+                    self.save(self.step)
+            self.step += 1
+        print('training completed')
+
+
+def _match_prefix(sd, model):
+    """accept checkpoints saved with or without the DataParallel `module.` prefix (DB:1039-1055)."""
+    want = any(k.startswith('module.') for k in model.state_dict().keys())
+    have = any(k.startswith('module.') for k in sd.keys())
+    if want == have:
+        return sd
+    if have:
+        return {k[len('module.'):]: v for k, v in sd.items()}
+    return {'module.' + k: v for k, v in sd.items()}

@@ -136,6 +136,15 @@ class Unet(nn.Module):
             self._engine = UnetEngine(self)
         return self._engine
 
+    def __deepcopy__(self, memo):
+        # the engine (packed weights, workspaces) is per-instance device state: never cloned (Trainer's EMA copy)
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == '_engine' else copy.deepcopy(v, memo)
+        return new
+
     def _apply(self, fn, *a, **k):
         self._engine = None                     # parameters moved/cast: rebuild packed weights lazily
         return super()._apply(fn, *a, **k)

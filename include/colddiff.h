@@ -52,7 +52,7 @@ int cd_last_error(char* buf, size_t n);
  *       (any shape; used for 3-channel image edges and as the on-device cross-check).
  * ------------------------------------------------------------------------------------------ */
 enum { CD_CONV_SIMT = 0, CD_CONV_TC = 1 };
-enum { CD_ACT_NONE = 0, CD_ACT_GELU = 1 };
+enum { CD_ACT_NONE = 0, CD_ACT_GELU = 1, CD_ACT_GELU_BWD = 2 /* out = acc * gelu'(aux) : dgrad through GELU */ };
 
 typedef struct {
   const float* src;       /* NHWC base of the channel slice                         */
@@ -78,6 +78,7 @@ typedef struct {
   int32_t act;
   int32_t round_tf32;     /* round outputs to TF32 (RN) so the next TC conv sees RN operands */
   float* out2; int32_t out2_ld; /* optional second output: the pre-activation (for backward) */
+  const float* aux; int32_t aux_ld; /* CD_ACT_GELU_BWD: saved pre-activation, same pixel mapping as out */
 } CdConvDesc;
 
 int cd_conv_fwd(const CdConvDesc* d, int impl, void* stream);
@@ -88,6 +89,8 @@ int cd_conv_fwd(const CdConvDesc* d, int impl, void* stream);
  * the caller; the kernel uses atomics across pixel splits). db (optional) += sum dout.           */
 int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, float* db,
                   int impl, void* stream);
+/* with d->s[0].w_per_batch = 1 the gradient is kept per batch element: dw[b][t][co][ci] (used for the
+ * per-batch effective weights of LinearAttention). */
 
 /* repack reference-layout weights: OIHW (transposed_conv=0) or IOHW (nn.ConvTranspose2d,
  * transposed_conv=1) -> packed [tap][N][K].  mode 0: forward operand (N=out ch, K=in ch);
@@ -111,7 +114,8 @@ int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, int C,
                       const float* cond /*[B][cond_ld] or NULL*/, int cond_ld,
                       const float* g, const float* beta /*[C] or NULL: no norm*/,
                       float eps, float* y, int y_ld, float* stats, float* hpre, int hpre_ld,
-                      int round_tf32, void* stream);
+                      int round_tf32, int flip /*1: rotate the 7x7 kernel by 180 deg (data-gradient)*/,
+                      const float* addend, int addend_ld /*optional NHWC tensor added to h*/, void* stream);
 
 /* channel LayerNorm alone (PreNorm in front of LinearAttention, DB:123-131) */
 int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
@@ -147,6 +151,34 @@ int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* str
 int cd_conv_tc_set_tf32_maps(int enable);
 
 /* ------------------------------------------------------------------------------------------
+ * Backward of the HBM-bound pieces (autograd of the reference modules restated as kernels).
+ * ------------------------------------------------------------------------------------------ */
+/* LayerNorm (DB:111-121): dh = dLN(dy) (+addend); dg, dbeta accumulated (+=) */
+int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int h_ld, const float* stats,
+                     const float* g, int64_t npix, int C, const float* addend, int addend_ld,
+                     float* dh, int dh_ld, float* dg, float* dbeta, void* stream);
+/* depthwise 7x7 weight gradient: dw[c][49] += sum dh * shifted(x) */
+int cd_dwconv7_wgrad(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C,
+                     float* dw, void* stream);
+/* out[b*out_ld + c] += sum over the `rows` pixels of image b of x[.., c]  (time-conditioning gradient) */
+int cd_colsum_batched(const float* x, int ld, int B, int64_t rows, int C, float* out, int out_ld, void* stream);
+/* LinearAttention backward (see cd_linattn_context): per-batch small part and per-pixel k/v part */
+int cd_linattn_bwd_small(const float* dweff, const float* ctx, const float* ksum, const float* w_out,
+                         int B, int dim, float scale, float* dw_out, float* dctxn, float* rowdot, void* stream);
+int cd_linattn_bwd_kv(const float* qkv, int ld, int B, int n, const float* kmax, const float* ksum,
+                      const float* dctxn, const float* rowdot, float* dqkv, int dld, void* stream);
+int cd_transpose_weff(const float* weff, int B, int dim, float* weff_t, void* stream);
+int cd_conv1x1_to_nchw_bwd(const float* dout_nchw, const float* x, int ld, int B, int H, int W, int C,
+                           const float* w, int Co, float* dx, int dx_ld, float* dw, float* db, void* stream);
+/* tiny dense helpers (time-MLP backward): C (+)= op(A) op(B);  y = dy * gelu'(pre), act_out = gelu(pre) */
+int cd_small_gemm(const float* A, int lda, int transA, const float* B, int ldb, int transB,
+                  float* C, int ldc, int M, int N, int K, int accumulate, void* stream);
+int cd_gelu_bwd(const float* dy, const float* pre, int64_t n, float* y, float* act_out, void* stream);
+/* out = a + b on NHWC channel slices (sum of two gradient branches) */
+int cd_add(const float* a, int a_ld, const float* b, int b_ld, float* out, int out_ld, int64_t npix, int C,
+           void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Degradation D(x,t) for the Gaussian-blur family (DB:348-389 kernels; DB:927-960 q_sample;
  * DB:436-451 Algorithm-2 update).  Every blur step is separable with circular or reflect
  * boundary handling, hence the cumulative degradation of a plane X is  A_t X A_t^T  with a
@@ -169,6 +201,9 @@ int cd_loss_fwd_bwd(const float* x0, const float* xhat, int64_t n, int mode, flo
 int cd_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
                      float lr, float beta1, float beta2, float eps, int step,
                      int ema_mode /*0 none,1 copy,2 lerp*/, float ema_beta, float grad_scale, void* stream);
+
+/* stand-alone EMA (DB:73-81): mode 1 copy, 2 lerp */
+int cd_ema_update(float* ema, const float* p, int64_t n, float beta, int mode, void* stream);
 
 #ifdef __cplusplus
 }
