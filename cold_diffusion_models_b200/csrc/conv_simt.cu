@@ -232,6 +232,7 @@ __global__ void unpack_wgrad_kernel(const float* packed, int O, int I, int KH, i
 }  // namespace
 
 int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st);
+int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, cudaStream_t st);
 
 static int conv_fwd_simt(const CdConvDesc* d, cudaStream_t st) {
   SimtParams p{};
@@ -266,10 +267,16 @@ extern "C" int cd_conv_fwd(const CdConvDesc* d, int impl, void* stream) {
 
 extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, float* db,
                              int impl, void* stream) {
-  (void)impl;
   CD_REQUIRE(d && d->nsrc == 1, "cd_conv_wgrad: single source only");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const CdConvSrc& c = d->s[0];
+  bool done = false;
+  if (impl == CD_CONV_TC) {
+    const int rc = cd_conv_wgrad_tc(d, dout, dout_ld, dw, st);
+    if (rc < 0) return rc;
+    done = (rc == 0);                       // rc == 1: not tensor-core shaped -> fp32 CUDA-core kernel below
+  }
+  if (!done) {
   WgradParams p{};
   p.B = d->B; p.Hg = d->Hg; p.Wg = d->Wg; p.sy = d->sy; p.sx = d->sx; p.Cout = d->Cout;
   p.C = c.C; p.H = c.H; p.W = c.W; p.ld = c.ld; p.ntaps = c.ntaps;
@@ -297,6 +304,7 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   dim3 grid(cd_cdiv(d->Cout, TM), cd_cdiv(c.C, TNc), c.ntaps * splits);
   wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);
   CD_LAUNCH_CHECK();
+  }
   if (db) {
     const long long rows = static_cast<long long>(d->B) * d->Ho * d->Wo;
     CD_REQUIRE(d->oys == 1 && d->oxs == 1, "cd_conv_wgrad: bias gradient needs a dense output grid");

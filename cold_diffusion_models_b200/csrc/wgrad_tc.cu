@@ -1,0 +1,343 @@
+// tcgen05 weight-gradient of the tap-list convolution (replaces cuDNN wgrad behind loss.backward() for the
+// dense convolutions of the reference Unet, DB:149-154,173-174,105-109):
+//
+//   dW[tap][co][ci] += sum_{pixels p} dY[p][co] * X[p (+) tap][ci]
+//
+// as a GEMM whose K dimension is the PIXEL axis: D[128 co x BN ci] (fp32, TMEM) += A^T B with both operands
+// "MN-major" in shared memory -- NHWC rows are exactly that: one 128-byte swizzled row per pixel holding 32
+// channels.  dY tiles ({32 co, CW px, R rows} TMA boxes) and X tiles land in SWIZZLE_128B smem and are
+// consumed by tcgen05.mma.kind::tf32 eight pixels (K = 8) at a time.  One CTA owns (co tile, ci tile, tap
+// group, pixel split) and keeps one TMEM accumulator per tap of its group (<= 4 x 128 columns); with
+// `halo` mode the dx = -1/0/+1 taps of a 3x3 kernel share ONE X tile that carries a one-pixel halo and are
+// addressed by shifting the descriptor start by whole 128-byte rows.  Partial sums of the pixel splits are
+// combined with vector red.global.add.f32.
+#include "cd_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxTaps = 4;      // taps (accumulators) per CTA
+constexpr int kMaxGroups = 4;
+
+struct WgParams {
+  int B, Hg, Wg;
+  int CW, R, KR;                  // pixel chunk: CW x R = KR K-rows of A per stage
+  int chunks_x, chunks_y, total_chunks, chunks_per_split, splits;
+  int Cout, Cin;
+  int tiles_co, tiles_ci;
+  int ngroups;
+  int ntaps[kMaxGroups];
+  int nloads[kMaxGroups];
+  int tap_index[kMaxGroups][kMaxTaps];
+  int tap_load[kMaxGroups][kMaxTaps];
+  int tap_shift[kMaxGroups][kMaxTaps];    // K-row shift inside the (halo) X tile
+  int load_dy[kMaxGroups][kMaxTaps], load_dx[kMaxGroups][kMaxTaps];
+  int halo;                       // extra pixels per row in the X box (0 or 2)
+  int sy, sx;                     // X coordinate = g*s + d
+  int oys, oxs, oy0, ox0;         // dY coordinate = g*os + o0
+  int base_offset_mode;           // descriptor base_offset for row-shifted starts: 0 = none, 1 = (addr >> 7) & 7
+  float* dw;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// MN-major operand for 32-bit (tf32) data: the only layout UMMA accepts is SWIZZLE_128B_BASE32B -- 128-byte rows (32
+// channels of one pixel), 32-byte swizzle atoms, pattern period 4 rows (512 B) -- which is what a TMA tensor map with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.  32-channel chunks are `lbo` bytes apart, 4-pixel groups 512 B apart.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_off & 7u) << 49;
+  d |= static_cast<uint64_t>(1) << 61;                          // SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
+                const WgParams p, int stages, int a_bytes, int b_bytes, int b_tx_bytes) {
+  constexpr int NCH = BN / 32;                    // ci chunks of the B operand
+  // instruction descriptor: D=f32, A=B=tf32, A and B MN-major, N=BN, M=128
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                              (uint32_t(BN >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int g = blockIdx.z;
+  const int nl = p.nloads[g], nt = p.ntaps[g];
+  const int stage_bytes = a_bytes + nl * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + stages;
+  uint64_t* done_bar = bars + 2 * stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 512;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tile = blockIdx.x;
+  const int co0 = (tile % p.tiles_co) * 128, ci0 = (tile / p.tiles_co) * BN;
+  const int split = blockIdx.y;
+  const int c_beg = split * p.chunks_per_split;
+  int c_end = c_beg + p.chunks_per_split; if (c_end > p.total_chunks) c_end = p.total_chunks;
+  const int nchunks = c_end - c_beg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nchunks; ++it) {
+        const int c = c_beg + it;
+        const int cx = c % p.chunks_x;
+        const int cy = (c / p.chunks_x) % p.chunks_y;
+        const int n = c / (p.chunks_x * p.chunks_y);
+        const int gx0 = cx * p.CW, gy0 = cy * p.R;
+        const uint32_t stage = it % stages, ph = (it / stages) & 1u;
+        mbar_wait(&empty_bar[stage], ph ^ 1u);
+        mbar_expect_tx(&full_bar[stage], a_bytes + nl * b_tx_bytes);
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)              // dY: 4 chunks of 32 out-channels
+          tma_load_4d(sa + ch * (a_bytes / 4), &mapDY, &full_bar[stage], co0 + ch * 32, gx0 * p.oxs + p.ox0, gy0 * p.oys + p.oy0, n);
+        for (int l = 0; l < nl; ++l) {
+          const uint32_t sb = sa + a_bytes + l * b_bytes;
+          const int xin = gx0 * p.sx + p.load_dx[g][l], yin = gy0 * p.sy + p.load_dy[g][l];
+          for (int ch = 0; ch < NCH; ++ch)
+            tma_load_4d(sb + ch * (b_bytes / NCH), &mapX, &full_bar[stage], ci0 + ch * 32, xin, yin, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t a_lbo = a_bytes / 4, b_lbo = b_bytes / NCH;
+      const int ksteps_row = p.CW / 8;              // MMAs per image row of the chunk
+      for (int it = 0; it < nchunks; ++it) {
+        const uint32_t stage = it % stages, ph = (it / stages) & 1u;
+        mbar_wait(&full_bar[stage], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        for (int t = 0; t < nt; ++t) {
+          const uint32_t sb = sa + a_bytes + p.tap_load[g][t] * b_bytes;
+          for (int r = 0; r < p.R; ++r) {
+            for (int j = 0; j < ksteps_row; ++j) {
+              const uint32_t arow = r * p.CW + j * 8;
+              const uint32_t brow = r * (p.CW + p.halo) + j * 8 + p.tap_shift[g][t];
+              const uint32_t aaddr = sa + arow * 128, baddr = sb + brow * 128;
+              const uint32_t boff = p.base_offset_mode == 1 ? ((baddr >> 7) & 7u) : (p.base_offset_mode == 2 ? ((baddr >> 7) & 3u) : 0u);
+              const uint64_t da = make_mnmajor_sw128_desc(aaddr, a_lbo, 0);
+              const uint64_t db = make_mnmajor_sw128_desc(baddr, b_lbo, boff);
+              mma_tf32(tmem_base + t * BN, da, db, kIdesc, (it | r | j) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        tc_commit(&empty_bar[stage]);
+      }
+      tc_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (nchunks > 0) {
+      for (int t = 0; t < nt; ++t) {
+        float* wrow = p.dw + (static_cast<long long>(p.tap_index[g][t]) * p.Cout + co) * p.Cin;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + t * BN + c + (static_cast<uint32_t>(q * 32) << 16), r);
+          if (co < p.Cout && ci0 + c < p.Cin) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(wrow + ci0 + c + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int g_wg_mode = 1;      // 0: one X tile per tap; 1 (default, verified on B200: profiles/wgrad_modes_r01.txt): dx taps share one halo
+                        // tile via row-shifted descriptor starts, base_offset 0; 2/3: probes with base_offset=(addr>>7)&7 / &3 (wrong)
+int g_sms = 0;
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+extern "C" int cd_wgrad_tc_set_mode(int mode) { g_wg_mode = mode; return 0; }
+
+// returns 1 if the problem is not tensor-core shaped (caller falls back to the SIMT kernel), 0 on success, <0 on error
+int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, cudaStream_t st) {
+  const CdConvSrc& c = d->s[0];
+  if (c.w_per_batch || c.C % 32 != 0 || d->Cout % 32 != 0 || c.ld % 4 != 0 || dout_ld % 4 != 0) return 1;
+  if (!is_pow2(d->Wg) || d->Wg < 8 || !is_pow2(d->Hg)) return 1;
+  if ((reinterpret_cast<uintptr_t>(c.src) & 15) || (reinterpret_cast<uintptr_t>(dout) & 15) || (reinterpret_cast<uintptr_t>(dw) & 15)) return 1;
+  EncodeTiledFn enc = get_encode();
+  CD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!g_sms) { int dev = 0; CD_CUDA(cudaGetDevice(&dev)); CD_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev)); }
+
+  WgParams p{};
+  p.B = d->B; p.Hg = d->Hg; p.Wg = d->Wg; p.Cout = d->Cout; p.Cin = c.C;
+  p.sy = d->sy; p.sx = d->sx; p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0;
+  p.dw = dw;
+  const int BN = c.C >= 128 ? 128 : 64;
+  // ---- tap groups ----
+  const bool is3x3 = (c.ntaps == 9 && d->sy == 1 && d->sx == 1);
+  bool shape3 = is3x3;
+  if (is3x3) for (int t = 0; t < 9; ++t) if (c.dy[t] != t / 3 - 1 || c.dx[t] != t % 3 - 1) shape3 = false;
+  const bool halo = shape3 && g_wg_mode != 0;
+  p.halo = halo ? 2 : 0;
+  p.base_offset_mode = (g_wg_mode == 2) ? 1 : (g_wg_mode == 3 ? 2 : 0);
+  if (halo) {
+    p.ngroups = 3;
+    for (int gk = 0; gk < 3; ++gk) {
+      p.ntaps[gk] = 3; p.nloads[gk] = 1; p.load_dy[gk][0] = gk - 1; p.load_dx[gk][0] = -1;
+      for (int k = 0; k < 3; ++k) { p.tap_index[gk][k] = gk * 3 + k; p.tap_load[gk][k] = 0; p.tap_shift[gk][k] = k; }
+    }
+  } else {
+    const int per = c.ntaps <= 4 ? c.ntaps : (c.ntaps == 9 ? 3 : 4);
+    if (c.ntaps % per != 0 || c.ntaps / per > kMaxGroups) return 1;
+    p.ngroups = c.ntaps / per;
+    for (int gk = 0; gk < p.ngroups; ++gk) {
+      p.ntaps[gk] = per; p.nloads[gk] = per;
+      for (int k = 0; k < per; ++k) {
+        const int t = gk * per + k;
+        p.tap_index[gk][k] = t; p.tap_load[gk][k] = k; p.tap_shift[gk][k] = 0;
+        p.load_dy[gk][k] = c.dy[t]; p.load_dx[gk][k] = c.dx[t];
+      }
+    }
+  }
+  const int max_taps = p.ntaps[0], max_loads = p.nloads[0];
+  if (max_taps * BN > 512) return 1;
+  // ---- pixel chunking: KR K-rows per stage ----
+  int KR = (max_loads <= 1) ? 64 : 32;
+  if (static_cast<long long>(d->Hg) * d->Wg < KR) KR = d->Hg * d->Wg;
+  if (KR < 8) return 1;
+  p.CW = d->Wg < KR ? d->Wg : KR;
+  p.R = KR / p.CW;
+  p.KR = KR;
+  if (p.CW * d->sx > 256 || p.CW * d->oxs > 256) return 1;
+  p.chunks_x = d->Wg / p.CW; p.chunks_y = d->Hg / p.R;
+  p.total_chunks = d->B * p.chunks_x * p.chunks_y;
+  p.tiles_co = cd_cdiv(d->Cout, 128); p.tiles_ci = cd_cdiv(c.C, BN);
+  const int tiles = p.tiles_co * p.tiles_ci;
+  int splits = cd_cdiv(2 * g_sms, tiles * p.ngroups);
+  const int max_splits = cd_cdiv(p.total_chunks, 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.chunks_per_split = cd_cdiv(p.total_chunks, splits);
+  p.splits = cd_cdiv(p.total_chunks, p.chunks_per_split);
+  const int a_bytes = 4 * KR * 128;
+  const int b_rows = p.R * (p.CW + p.halo);
+  const int b_rows_pad = (b_rows + 7) / 8 * 8;                 // keep every chunk base 1024-byte aligned
+  const int b_bytes = (BN / 32) * b_rows_pad * 128;
+  const int b_tx = (BN / 32) * b_rows * 128;                   // bytes the TMA unit actually writes per X tile
+  const int stage_bytes = a_bytes + max_loads * b_bytes;
+  int stages = (200 * 1024) / stage_bytes; if (stages > 6) stages = 6;
+  if (stages < 2) return 1;
+  const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
+
+  CUtensorMap mapDY, mapX;
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)dout_ld * 4, (cuuint64_t)dout_ld * 4 * d->Wo, (cuuint64_t)dout_ld * 4 * d->Wo * d->Ho};
+    cuuint32_t box[4] = {32, (cuuint32_t)(p.CW * d->oxs), (cuuint32_t)(p.R * d->oys), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->oxs, (cuuint32_t)d->oys, 1};
+    CUresult r = enc(&mapDY, dt, 4, const_cast<float*>(dout), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dY) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)c.ld * 4, (cuuint64_t)c.ld * 4 * c.W, (cuuint64_t)c.ld * 4 * c.W * c.H};
+    cuuint32_t box[4] = {32, (cuuint32_t)((p.CW + p.halo) * d->sx), (cuuint32_t)(p.R * d->sy), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->sx, (cuuint32_t)d->sy, 1};
+    CUresult r = enc(&mapX, dt, 4, const_cast<float*>(c.src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(X) failed: %d", (int)r);
+  }
+  dim3 grid(tiles, p.splits, p.ngroups);
+  if (BN == 128) {
+    CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_tc_kernel<128><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
+  } else {
+    CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_tc_kernel<64><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
+  }
+  CD_LAUNCH_CHECK();
+  return 0;
+}

@@ -102,7 +102,7 @@ class BackwardMixin:
             dwp.zero_()
         d = ops.make_conv_desc([(src, taps, dwp, False)], dout, grid, stride=stride, Cout=Cout, out_map=out_map)
         bias_ok = bias_param is not None and out_map == (1, 1, 0, 0)
-        ops.conv_wgrad(d, dout, dwp, bias_param if bias_ok else None)
+        ops.conv_wgrad(d, dout, dwp, bias_param if bias_ok else None, impl=self.conv_impl)
         if not direct:
             ops.unpack_wgrad(dwp, taps, wgrad_param, transposed_conv=transposed_conv, accumulate=True)
 

@@ -147,6 +147,8 @@ int cd_conv1x1_to_nchw(const float* x, int ld, int B, int H, int W, int C, const
 int cd_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* out, int ld, void* stream);
 /* out[c] += sum_rows x[row*ld + c]  (bias / LayerNorm-beta gradients) */
 int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* stream);
+/* diagnostic switch for the tcgen05 wgrad: 0 = one X tile per tap, 1/2 = shared halo tile (base_offset 0 / computed) */
+int cd_wgrad_tc_set_mode(int mode);
 /* diagnostic switch: 1 (default) = TFLOAT32 tensor maps (TMA rounds fp32->tf32 RN on load) */
 int cd_conv_tc_set_tf32_maps(int enable);
 

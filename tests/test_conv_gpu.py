@@ -182,3 +182,80 @@ def test_tf32_operand_rounding_probe(ops):
     with open('gpurun_out/tf32_probe.txt', 'w') as f:
         f.write('\n'.join(lines) + '\n')
     print('\n'.join(lines))
+
+
+WG_CASES = [
+    # (B, Cin, Cout, H, W, kind)
+    (2, 64, 128, 32, 32, '3x3'),
+    (1, 128, 64, 128, 128, '3x3'),
+    (3, 256, 512, 16, 16, '3x3'),
+    (2, 128, 384, 16, 16, '1x1'),
+    (2, 64, 64, 32, 32, '4x4s2'),
+    (2, 64, 64, 16, 16, 'convT'),
+    (4, 64, 64, 8, 8, '3x3'),
+]
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2, 3])
+@pytest.mark.parametrize('case', WG_CASES)
+def test_wgrad_tc_matches_fp64(ops, case, mode):
+    """tcgen05 weight gradient (pixel-axis GEMM, MN-major operands) vs fp64; mode 0 = one X tile per tap,
+    1/2 = dx taps share one halo tile addressed by row-shifted descriptors (base_offset 0 / computed)."""
+    import os
+    from cold_diffusion_models_b200._lib import lib
+    B, Ci, Co, H, W, kind = case
+    g = torch.Generator().manual_seed(17)
+    x = tf32_rn(torch.randn(B, Ci, H, W, generator=g))
+    lib.cd_wgrad_tc_set_mode(mode)
+    try:
+        if kind in ('3x3', '1x1'):
+            k, pad = (3, 1) if kind == '3x3' else (1, 0)
+            w = torch.zeros(Co, Ci, k, k, dtype=torch.double, requires_grad=True)
+            y = F.conv2d(x.double(), w, padding=pad)
+            dy = tf32_rn(torch.randn(y.shape, generator=g))
+            (y * dy.double()).sum().backward()
+            taps = ops.taps_conv(k, pad)
+            dwp = torch.zeros(len(taps), Co, Ci, device='cuda')
+            dyv = ops.View(nhwc(dy).cuda())
+            d = ops.make_conv_desc([(ops.View(nhwc(x).cuda()), taps, dwp, False)], dyv, (B, H, W), Cout=Co)
+            ops.conv_wgrad(d, dyv, dwp, None, impl=ops.CONV_TC)
+            wg = torch.zeros(Co, Ci, k, k, device='cuda')
+            ops.unpack_wgrad(dwp, taps, wg, accumulate=False)
+            ref = w.grad
+        elif kind == '4x4s2':
+            w = torch.zeros(Co, Ci, 4, 4, dtype=torch.double, requires_grad=True)
+            y = F.conv2d(x.double(), w, stride=2, padding=1)
+            dy = tf32_rn(torch.randn(y.shape, generator=g))
+            (y * dy.double()).sum().backward()
+            taps = ops.taps_conv(4, 1)
+            dwp = torch.zeros(16, Co, Ci, device='cuda')
+            dyv = ops.View(nhwc(dy).cuda())
+            d = ops.make_conv_desc([(ops.View(nhwc(x).cuda()), taps, dwp, False)], dyv, (B, H // 2, W // 2), stride=2, Cout=Co)
+            ops.conv_wgrad(d, dyv, dwp, None, impl=ops.CONV_TC)
+            wg = torch.zeros(Co, Ci, 4, 4, device='cuda')
+            ops.unpack_wgrad(dwp, taps, wg, accumulate=False)
+            ref = w.grad
+        else:
+            w = torch.zeros(Ci, Co, 4, 4, dtype=torch.double, requires_grad=True)
+            y = F.conv_transpose2d(x.double(), w, stride=2, padding=1)
+            dy = tf32_rn(torch.randn(y.shape, generator=g))
+            (y * dy.double()).sum().backward()
+            wg = torch.zeros(Ci, Co, 4, 4, device='cuda')
+            dyv = ops.View(nhwc(dy).cuda())
+            for py in (0, 1):
+                for px in (0, 1):
+                    tp = ops.taps_convT4_parity(py, px)
+                    dwp = torch.zeros(4, Co, Ci, device='cuda')
+                    d = ops.make_conv_desc([(ops.View(nhwc(x).cuda()), tp, dwp, False)], dyv, (B, H, W), Cout=Co, out_map=(2, 2, py, px))
+                    ops.conv_wgrad(d, dyv, dwp, None, impl=ops.CONV_TC)
+                    ops.unpack_wgrad(dwp, tp, wg, transposed_conv=True, accumulate=True)
+            ref = w.grad
+        torch.cuda.synchronize()
+        e = rel(wg.cpu(), ref)
+        os.makedirs('gpurun_out', exist_ok=True)
+        with open('gpurun_out/wgrad_modes.txt', 'a') as f:
+            f.write('mode %d case %s rel %.3e\n' % (mode, case, e))
+        if mode in (0, 1):   # modes 2-3 only probe the descriptor base_offset field and are expected to be wrong
+            assert e < 1e-5, e
+    finally:
+        lib.cd_wgrad_tc_set_mode(1)
