@@ -77,60 +77,42 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __res
 
 // ---------------------------------------------------------------------------------------------
 // depthwise 7x7 weight gradient: dw[c][ky*7+kx] += sum_{b,y,x} dh[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]
-// block = (b, group of R rows, 32-channel slab); rows staged in shared memory.
+// thread = (channel, ky): slides along x with a 7-wide register window of the input row, so every pixel costs one
+// dh load + one x load (128-byte coalesced across the 32 channels of a warp, L1-resident across ky) and 7 FMAs.
+// block = (b, group of kDwR rows, 32-channel slab) x 7 ky.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDwR = 4;
-__global__ void __launch_bounds__(256)
+constexpr int kDwR = 16;
+__global__ void __launch_bounds__(224)
 dwconv7_wgrad_kernel(const float* __restrict__ dh, int dh_ld, const float* __restrict__ x, int x_ld,
                      int B, int H, int W, int C, float* __restrict__ dw) {
-  extern __shared__ float sm[];                // dhs[W][33] | xs[7][W+6][33]
-  const int Wp = W + 6;
-  float* dhs = sm;
-  float* xs = sm + W * 33;
-  const int c0 = blockIdx.x * 32;
-  const int cn = min(32, C - c0);
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ky = threadIdx.x >> 5;                 // 0..6
   const int ygroups = (H + kDwR - 1) / kDwR;
   const int b = blockIdx.y / ygroups, y0 = (blockIdx.y % ygroups) * kDwR;
-  // each thread owns outputs o = threadIdx.x + 256*j (o = tap*32 + c), j < 7 (49*32 = 1568 <= 1792)
-  float acc[7];
-#pragma unroll
-  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+  if (c >= C) return;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int yy = y0; yy < min(H, y0 + kDwR); ++yy) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < W * 32; i += blockDim.x) {
-      const int px = i >> 5, c = i & 31;
-      dhs[px * 33 + c] = c < cn ? dh[((static_cast<long long>(b) * H + yy) * W + px) * dh_ld + c0 + c] : 0.f;
-    }
-    for (int i = threadIdx.x; i < 7 * Wp * 32; i += blockDim.x) {
-      const int c = i & 31;
-      const int px = (i >> 5) % Wp, ky = (i >> 5) / Wp;
-      const int iy = yy + ky - 3, ix = px - 3;
-      float v = 0.f;
-      if (c < cn && iy >= 0 && iy < H && ix >= 0 && ix < W)
-        v = x[((static_cast<long long>(b) * H + iy) * W + ix) * x_ld + c0 + c];
-      xs[(ky * Wp + px) * 33 + c] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int o = threadIdx.x + 256 * j;
-      if (o < 49 * 32) {
-        const int c = o & 31, tap = o >> 5, ky = tap / 7, kx = tap % 7;
-        const float* xr = xs + (ky * Wp + kx) * 33 + c;
-        float a = 0.f;
-        for (int px = 0; px < W; ++px) a = fmaf(dhs[px * 33 + c], xr[px * 33], a);
-        acc[j] += a;
-      }
+    const int iy = yy + ky - 3;
+    if (iy < 0 || iy >= H) continue;
+    const float* drow = dh + ((static_cast<long long>(b) * H + yy) * W) * dh_ld + c;
+    const float* xrow = x + ((static_cast<long long>(b) * H + iy) * W) * x_ld + c;
+    // window w[k] = x[px + k - 3]
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    float w3 = xrow[0];
+    float w4 = W > 1 ? xrow[x_ld] : 0.f;
+    float w5 = W > 2 ? xrow[2 * x_ld] : 0.f;
+    float w6;
+#pragma unroll 4
+    for (int px = 0; px < W; ++px) {
+      w6 = (px + 3 < W) ? xrow[static_cast<long long>(px + 3) * x_ld] : 0.f;
+      const float d = drow[static_cast<long long>(px) * dh_ld];
+      acc[0] = fmaf(d, w0, acc[0]); acc[1] = fmaf(d, w1, acc[1]); acc[2] = fmaf(d, w2, acc[2]); acc[3] = fmaf(d, w3, acc[3]);
+      acc[4] = fmaf(d, w4, acc[4]); acc[5] = fmaf(d, w5, acc[5]); acc[6] = fmaf(d, w6, acc[6]);
+      w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
     }
   }
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const int o = threadIdx.x + 256 * j;
-    if (o < 49 * 32) {
-      const int c = o & 31, tap = o >> 5;
-      if (c < cn) atomicAdd(dw + (c0 + c) * 49 + tap, acc[j]);
-    }
-  }
+  for (int kx = 0; kx < 7; ++kx) atomicAdd(dw + c * 49 + ky * 7 + kx, acc[kx]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -168,47 +150,62 @@ __global__ void __launch_bounds__(256)
 attn_bwd_small_kernel(const float* __restrict__ dweff, const float* __restrict__ ctx, const float* __restrict__ ksum,
                       const float* __restrict__ w_out, int dim, float scale, float* __restrict__ dw_out,
                       float* __restrict__ dctxn, float* __restrict__ rowdot) {
-  const int b = blockIdx.x;
-  const float* dwe = dweff + static_cast<long long>(b) * dim * 128;
-  const float* cb = ctx + static_cast<long long>(b) * 4096;
-  // dctxn: 4096 outputs, each sum over co
-  for (int o = threadIdx.x; o < 4096; o += blockDim.x) {
-    const int e = o & 31, d = (o >> 5) & 31, h = o >> 10;
-    float a = 0.f;
-    for (int co = 0; co < dim; ++co) a = fmaf(dwe[co * 128 + h * 32 + d], w_out[co * 128 + h * 32 + e], a);
-    dctxn[static_cast<long long>(b) * 4096 + o] = a * scale;
-  }
-  // dW_out: dim*128 outputs, each sum over d
-  for (int o = threadIdx.x; o < dim * 128; o += blockDim.x) {
-    const int he = o & 127, co = o >> 7, h = he >> 5, e = he & 31;
-    float a = 0.f;
-    for (int d = 0; d < 32; ++d)
-      a = fmaf(dwe[co * 128 + h * 32 + d], cb[(h * 32 + d) * 32 + e] / ksum[b * 128 + h * 32 + d], a);
-    atomicAdd(dw_out + o, a * scale);
+  // one block per (head, batch element)
+  __shared__ float cn[32][33];     // ctxn[d][e]
+  __shared__ float dcs[32][33];    // dctxn[d][e]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const float* dwe = dweff + static_cast<long long>(b) * dim * 128 + h * 32;     // [co][d], row stride 128
+  const float* wo = w_out + h * 32;                                              // [co][e], row stride 128
+  const float* cb = ctx + (static_cast<long long>(b) * 4 + h) * 1024;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const int d = i >> 5, e = i & 31;
+    cn[d][e] = cb[i] / ksum[b * 128 + h * 32 + d];
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < 128; o += blockDim.x) {
+  // dctxn[d][e] = scale * sum_co dweff[co][d] * w_out[co][e]  : thread -> (d, e quad)
+  {
+    const int d = threadIdx.x >> 3, e4 = (threadIdx.x & 7) * 4;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int co = 0; co < dim; ++co) {
+      const float dv = dwe[co * 128 + d];
+      const float4 wv = *reinterpret_cast<const float4*>(wo + co * 128 + e4);
+      a0 = fmaf(dv, wv.x, a0); a1 = fmaf(dv, wv.y, a1); a2 = fmaf(dv, wv.z, a2); a3 = fmaf(dv, wv.w, a3);
+    }
+    dcs[d][e4] = a0 * scale; dcs[d][e4 + 1] = a1 * scale; dcs[d][e4 + 2] = a2 * scale; dcs[d][e4 + 3] = a3 * scale;
+  }
+  __syncthreads();
+  float* dout = dctxn + (static_cast<long long>(b) * 4 + h) * 1024;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) dout[i] = dcs[i >> 5][i & 31];
+  if (threadIdx.x < 32) {
     float a = 0.f;
-    const float inv = 1.f / ksum[b * 128 + o];
-    for (int e = 0; e < 32; ++e) a = fmaf(dctxn[static_cast<long long>(b) * 4096 + o * 32 + e], cb[o * 32 + e] * inv, a);
-    rowdot[b * 128 + o] = a;
+    for (int e = 0; e < 32; ++e) a = fmaf(dcs[threadIdx.x][e], cn[threadIdx.x][e], a);
+    rowdot[b * 128 + h * 32 + threadIdx.x] = a;
+  }
+  // dW_out[co][h*32+e] += scale * sum_d dweff[co][d] * ctxn[d][e]
+  for (int o = threadIdx.x; o < dim * 32; o += blockDim.x) {
+    const int co = o >> 5, e = o & 31;
+    float a = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 32; ++d) a = fmaf(dwe[co * 128 + d], cn[d][e], a);
+    atomicAdd(dw_out + co * 128 + h * 32 + e, a * scale);
   }
 }
 
 // per-pixel part: dk[n][hd] = P * (sum_e dctxn[hd][e] v[n][h,e] - rowdot[hd]),  P = exp(k-kmax)/ksum
 //                 dv[n][he] = sum_d P[n][h,d] dctxn[h,d][e]
 // block handles 32 pixels of one image; dctxn (16 KB) staged in shared memory.
+constexpr int kKvPix = 24;
 __global__ void __launch_bounds__(256)
 attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __restrict__ kmax,
                    const float* __restrict__ ksum, const float* __restrict__ dctxn, const float* __restrict__ rowdot,
                    float* __restrict__ dqkv, int dld) {
-  __shared__ float dc[4096];
-  __shared__ float ps[32][128];
-  __shared__ float vs[32][128];
+  __shared__ float dc[128][33];    // dctxn[(h,d)][e], padded: lanes walk the (h,d) axis
+  __shared__ float ps[kKvPix][128];
+  __shared__ float vs[kKvPix][128];
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * 32;
-  for (int i = threadIdx.x; i < 4096; i += blockDim.x) dc[i] = dctxn[static_cast<long long>(b) * 4096 + i];
-  for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
+  const int p0 = blockIdx.x * kKvPix;
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) dc[i >> 5][i & 31] = dctxn[static_cast<long long>(b) * 4096 + i];
+  for (int i = threadIdx.x; i < kKvPix * 128; i += blockDim.x) {
     const int pp = i >> 7, c = i & 127;
     const int p = p0 + pp;
     float pv = 0.f, vv = 0.f;
@@ -221,15 +218,15 @@ attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __
   }
   __syncthreads();
   // 32 pixels x 128 channels = 4096 outputs of each kind; thread handles 16 of each
-  for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kKvPix * 128; i += blockDim.x) {
     const int pp = i >> 7, c = i & 127, h = c >> 5, j = c & 31;
     const int p = p0 + pp;
     if (p >= n) continue;
     float dk = 0.f, dv = 0.f;
 #pragma unroll 8
     for (int e = 0; e < 32; ++e) {
-      dk = fmaf(dc[(h * 32 + j) * 32 + e], vs[pp][h * 32 + e], dk);       // c = (h, d=j)
-      dv = fmaf(ps[pp][h * 32 + e], dc[(h * 32 + e) * 32 + j], dv);       // c = (h, e=j), sum over d=e
+      dk = fmaf(dc[h * 32 + j][e], vs[pp][h * 32 + e], dk);       // c = (h, d=j)
+      dv = fmaf(ps[pp][h * 32 + e], dc[h * 32 + e][j], dv);       // c = (h, e=j), sum over d=e
     }
     float* orow = dqkv + (static_cast<long long>(b) * n + p) * dld;
     orow[128 + c] = ps[pp][c] * (dk - rowdot[b * 128 + c]);
@@ -249,43 +246,51 @@ __global__ void transpose_weff_kernel(const float* __restrict__ w, int dim, floa
 // ---------------------------------------------------------------------------------------------
 // final 1x1 projection backward: dx[pix][c] = sum_co dout[b][co][pix] w[co][c]; dw[co][c], db[co]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// thread = (pixel group, channel): x reads are coalesced over channels, dout is a warp broadcast
+__global__ void __launch_bounds__(256)
 conv1x1_to_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int ld, int B, int HW, int C,
                            const float* __restrict__ w, int Co, float* __restrict__ dx, int dx_ld,
-                           float* __restrict__ dw, float* __restrict__ db) {
-  extern __shared__ float red[];      // [Co][C] + [Co]
-  for (int i = threadIdx.x; i < Co * C + Co; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool valid = pix < static_cast<long long>(B) * HW;
-  if (valid) {
-    const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
-    float dv[8];
-    for (int co = 0; co < Co; ++co) dv[co] = dout[(static_cast<long long>(b) * Co + co) * HW + p];
-    for (int c = 0; c < C; ++c) {
-      float a = 0.f;
-      for (int co = 0; co < Co; ++co) a = fmaf(dv[co], w[co * C + c], a);
-      dx[pix * dx_ld + c] = a;
-    }
-  }
-  // parameter gradients: warp-reduce over the 32 pixels of each warp, then shared atomics
-  const int lane = threadIdx.x & 31;
-  for (int co = 0; co < Co; ++co) {
-    float dvv = 0.f;
-    if (valid) {
+                           float* __restrict__ dw, float* __restrict__ db, int pix_per_block) {
+  extern __shared__ float red[];      // [groups][Co][C]
+  const int groups = blockDim.x / C;
+  const int c = threadIdx.x % C, gq = threadIdx.x / C;
+  const long long npix = static_cast<long long>(B) * HW;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
+  long long p1 = p0 + pix_per_block; if (p1 > npix) p1 = npix;
+  float wv[8], acc[8], accb[8];
+  for (int co = 0; co < Co; ++co) { wv[co] = w[co * C + c]; acc[co] = 0.f; accb[co] = 0.f; }
+  if (gq < groups) {
+    for (long long pix = p0 + gq; pix < p1; pix += groups) {
       const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
-      dvv = dout[(static_cast<long long>(b) * Co + co) * HW + p];
+      const float xv = x[pix * ld + c];
+      float d = 0.f;
+      for (int co = 0; co < Co; ++co) {
+        const float dv = dout[(static_cast<long long>(b) * Co + co) * HW + p];
+        d = fmaf(dv, wv[co], d);
+        acc[co] = fmaf(dv, xv, acc[co]);
+        accb[co] += dv;
+      }
+      dx[pix * dx_ld + c] = d;
     }
-    const float sb = cd_warp_sum(dvv);
-    if (lane == 0) atomicAdd(&red[Co * C + co], sb);
-    for (int c = 0; c < C; ++c) {
-      const float s = cd_warp_sum(valid ? dvv * x[pix * ld + c] : 0.f);
-      if (lane == 0) atomicAdd(&red[co * C + c], s);
-    }
+    for (int co = 0; co < Co; ++co) red[(gq * Co + co) * C + c] = acc[co];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Co * C; i += blockDim.x) atomicAdd(dw + i, red[i]);
-  for (int i = threadIdx.x; i < Co; i += blockDim.x) atomicAdd(db + i, red[Co * C + i]);
+  if (gq == 0) {
+    for (int co = 0; co < Co; ++co) {
+      float t = 0.f;
+      for (int k = 0; k < groups; ++k) t += red[(k * Co + co) * C + c];
+      atomicAdd(dw + co * C + c, t);
+    }
+  }
+  // bias gradient: channel-0 threads of every group hold partial sums over their pixels
+  __syncthreads();
+  if (c == 0 && gq < groups) for (int co = 0; co < Co; ++co) red[gq * Co + co] = accb[co];
+  __syncthreads();
+  if (threadIdx.x < Co) {
+    float t = 0.f;
+    for (int k = 0; k < groups; ++k) t += red[k * Co + threadIdx.x];
+    atomicAdd(db + threadIdx.x, t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -348,12 +353,8 @@ extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int 
 
 extern "C" int cd_dwconv7_wgrad(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C,
                                 float* dw, void* stream) {
-  const size_t smem = sizeof(float) * (size_t(W) * 33 + size_t(7) * (W + 6) * 33);
-  CD_REQUIRE(smem <= 200 * 1024, "cd_dwconv7_wgrad: image width %d too large", W);
-  static size_t attr = 0;
-  if (smem > attr) { CD_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   dim3 grid(cd_cdiv(C, 32), B * cd_cdiv(H, kDwR));
-  dwconv7_wgrad_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(dh, dh_ld, x, x_ld, B, H, W, C, dw);
+  dwconv7_wgrad_kernel<<<grid, 224, 0, static_cast<cudaStream_t>(stream)>>>(dh, dh_ld, x, x_ld, B, H, W, C, dw);
   CD_LAUNCH_CHECK();
   return 0;
 }
@@ -368,14 +369,14 @@ extern "C" int cd_colsum_batched(const float* x, int ld, int B, int64_t rows, in
 
 extern "C" int cd_linattn_bwd_small(const float* dweff, const float* ctx, const float* ksum, const float* w_out,
                                     int B, int dim, float scale, float* dw_out, float* dctxn, float* rowdot, void* stream) {
-  attn_bwd_small_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(dweff, ctx, ksum, w_out, dim, scale, dw_out, dctxn, rowdot);
+  attn_bwd_small_kernel<<<dim3(4, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(dweff, ctx, ksum, w_out, dim, scale, dw_out, dctxn, rowdot);
   CD_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int cd_linattn_bwd_kv(const float* qkv, int ld, int B, int n, const float* kmax, const float* ksum,
                                  const float* dctxn, const float* rowdot, float* dqkv, int dld, void* stream) {
-  dim3 grid(cd_cdiv(n, 32), B);
+  dim3 grid(cd_cdiv(n, kKvPix), B);
   attn_bwd_kv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(qkv, ld, n, kmax, ksum, dctxn, rowdot, dqkv, dld);
   CD_LAUNCH_CHECK();
   return 0;
@@ -390,11 +391,13 @@ extern "C" int cd_transpose_weff(const float* weff, int B, int dim, float* weff_
 
 extern "C" int cd_conv1x1_to_nchw_bwd(const float* dout_nchw, const float* x, int ld, int B, int H, int W, int C,
                                       const float* w, int Co, float* dx, int dx_ld, float* dw, float* db, void* stream) {
-  CD_REQUIRE(Co <= 8, "cd_conv1x1_to_nchw_bwd: at most 8 image channels");
+  CD_REQUIRE(Co <= 8 && C <= 256, "cd_conv1x1_to_nchw_bwd: at most 8 image channels / 256 features");
   const long long npix = static_cast<long long>(B) * H * W;
-  const size_t smem = sizeof(float) * (size_t(Co) * C + Co);
-  conv1x1_to_nchw_bwd_kernel<<<cd_cdiv(npix, 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
-                                                                                                 dx, dx_ld, dw, db);
+  const int groups = 256 / C;
+  const size_t smem = sizeof(float) * size_t(groups) * Co * C;
+  const int ppb = 1024;
+  conv1x1_to_nchw_bwd_kernel<<<cd_cdiv(npix, ppb), 256, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
+                                                                                                 dx, dx_ld, dw, db, ppb);
   CD_LAUNCH_CHECK();
   return 0;
 }

@@ -93,6 +93,60 @@ conv_simt_kernel(const SimtParams p) {
   }
 }
 
+// Image-edge convolution (Cin <= 4, e.g. the 3-channel input of the first ConvNextBlock): one thread per pixel keeps the
+// whole receptive field (taps x Cin <= 36 values) in registers; weights [K][Cout] are broadcast from shared memory.
+constexpr int kSmallK = 36;
+__global__ void __launch_bounds__(128)
+conv_smallc_kernel(const SimtParams p) {
+  extern __shared__ float ws[];                    // [K][Cout]
+  const SimtSrc& S = p.s[0];
+  const int K = S.ntaps * S.C;
+  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
+    const int co = i % p.Cout, k = i / p.Cout, tap = k / S.C, c = k % S.C;
+    ws[i] = S.w[(static_cast<long long>(tap) * p.Cout + co) * S.C + c];
+  }
+  __syncthreads();
+  const long long gp = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.B) * p.Hg * p.Wg;
+  if (gp >= total) return;
+  const int gx = static_cast<int>(gp % p.Wg);
+  const int gy = static_cast<int>((gp / p.Wg) % p.Hg);
+  const int b = static_cast<int>(gp / (static_cast<long long>(p.Wg) * p.Hg));
+  float patch[kSmallK];
+#pragma unroll
+  for (int k = 0; k < kSmallK; ++k) patch[k] = 0.f;
+  for (int tap = 0; tap < S.ntaps; ++tap) {
+    const int iy = gy * p.sy + S.dy[tap], ix = gx * p.sx + S.dx[tap];
+    if (iy < 0 || iy >= S.H || ix < 0 || ix >= S.W) continue;
+    const float* row = S.src + ((static_cast<long long>(b) * S.H + iy) * S.W + ix) * S.ld;
+    for (int c = 0; c < S.C; ++c) patch[tap * S.C + c] = row[c];
+  }
+  const long long pix = (static_cast<long long>(b) * p.Ho + (gy * p.oys + p.oy0)) * p.Wo + (gx * p.oxs + p.ox0);
+  for (int co = 0; co < p.Cout; co += 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kSmallK; ++k) {
+      if (k < K) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[k * p.Cout + co]);
+        a[0] = fmaf(patch[k], wv.x, a[0]); a[1] = fmaf(patch[k], wv.y, a[1]);
+        a[2] = fmaf(patch[k], wv.z, a[2]); a[3] = fmaf(patch[k], wv.w, a[3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = a[j];
+      if (p.bias) v += p.bias[co + j];
+      if (p.resid) v += p.resid[pix * p.resid_ld + co + j];
+      if (p.out2) p.out2[pix * p.out2_ld + co + j] = v;
+      if (p.act == CD_ACT_GELU) v = cd_gelu(v);
+      else if (p.act == CD_ACT_GELU_BWD) v *= cd_gelu_grad(p.aux[pix * p.aux_ld + co + j]);
+      if (p.round_tf32) v = cd_round_tf32(v);
+      a[j] = v;
+    }
+    *reinterpret_cast<float4*>(p.out + pix * p.out_ld + co) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+}
+
 // dW[tap][co][ci] += sum_pix dout[pix][co] * src[pix(tap)][ci]
 struct WgradParams {
   int B, Hg, Wg, sy, sx, Cout, C, H, W, ld, ntaps;
@@ -248,6 +302,17 @@ static int conv_fwd_simt(const CdConvDesc* d, cudaStream_t st) {
   p.bias = d->bias; p.resid = d->resid; p.resid_ld = d->resid_ld; p.act = d->act; p.round_tf32 = d->round_tf32;
   p.out2 = d->out2; p.out2_ld = d->out2_ld; p.aux = d->aux; p.aux_ld = d->aux_ld;
   CD_REQUIRE(d->act != CD_ACT_GELU_BWD || d->aux, "conv_simt: GELU_BWD needs aux");
+  const CdConvSrc& c0 = d->s[0];
+  if (d->nsrc == 1 && c0.C <= 4 && c0.ntaps * c0.C <= kSmallK && !c0.w_per_batch && d->Cout % 4 == 0 && d->Cout <= 512 &&
+      d->out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) {
+    const long long total = static_cast<long long>(d->B) * d->Hg * d->Wg;
+    const size_t smem = sizeof(float) * c0.ntaps * c0.C * d->Cout;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) { CD_CUDA(cudaFuncSetAttribute(conv_smallc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    conv_smallc_kernel<<<cd_cdiv(total, 128), 128, smem, st>>>(p);
+    CD_LAUNCH_CHECK();
+    return 0;
+  }
   p.tiles_per_img = cd_cdiv(d->Hg * d->Wg, TM);
   dim3 grid(d->B * p.tiles_per_img, cd_cdiv(d->Cout, TNc));
   conv_simt_kernel<<<grid, 256, 0, st>>>(p);

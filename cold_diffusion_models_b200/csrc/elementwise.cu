@@ -343,19 +343,26 @@ context_kernel(const float* __restrict__ qkv, int ld, int n, int pix_per_block, 
 }
 
 // weff[b][co][h*32+d] = scale * sum_e w_out[co][h*32+e] * ctx[b][h][d][e] / ksum[b][h*32+d]
-__global__ void weff_kernel(const float* __restrict__ ctx, const float* __restrict__ ksum, const float* __restrict__ w_out,
-                            int dim, float scale, int round_tf32, float* __restrict__ weff) {
-  const int b = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= dim * 128) return;
-  const int co = idx >> 7, hd = idx & 127, h = hd >> 5, d = hd & 31;
-  const float* crow = ctx + ((static_cast<long long>(b) * 4 + h) * 32 + d) * 32;
-  const float* wrow = w_out + co * 128 + h * 32;
-  float a = 0.f;
-#pragma unroll
-  for (int e = 0; e < 32; ++e) a = fmaf(wrow[e], crow[e], a);
-  a = a * scale / ksum[b * 128 + hd];
-  weff[(static_cast<long long>(b) * dim + co) * 128 + hd] = round_tf32 ? cd_round_tf32(a) : a;
+// block = (head, batch element): the normalised 32x32 context is staged in shared memory.
+__global__ void __launch_bounds__(256)
+weff_kernel(const float* __restrict__ ctx, const float* __restrict__ ksum, const float* __restrict__ w_out,
+            int dim, float scale, int round_tf32, float* __restrict__ weff) {
+  __shared__ float cn[32][33];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const float* cb = ctx + (static_cast<long long>(b) * 4 + h) * 1024;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const int d = i >> 5, e = i & 31;
+    cn[d][e] = cb[i] * scale / ksum[b * 128 + h * 32 + d];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < dim * 32; o += blockDim.x) {
+    const int co = o >> 5, d = o & 31;
+    const float* wrow = w_out + co * 128 + h * 32;
+    float a = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < 32; ++e) a = fmaf(__ldg(wrow + e), cn[d][e], a);
+    weff[(static_cast<long long>(b) * dim + co) * 128 + h * 32 + d] = round_tf32 ? cd_round_tf32(a) : a;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -462,8 +469,7 @@ extern "C" int cd_linattn_context(const float* qkv, int ld, int B, int n, float*
 
 extern "C" int cd_linattn_weff(const float* ctx, const float* ksum, const float* w_out, int B, int dim, float scale,
                                int round_tf32, float* weff, void* stream) {
-  dim3 grid(cd_cdiv(dim * 128, 256), B);
-  weff_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx, ksum, w_out, dim, scale, round_tf32, weff);
+  weff_kernel<<<dim3(4, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx, ksum, w_out, dim, scale, round_tf32, weff);
   CD_LAUNCH_CHECK();
   return 0;
 }

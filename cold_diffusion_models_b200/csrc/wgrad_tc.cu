@@ -36,6 +36,8 @@ struct WgParams {
   int sy, sx;                     // X coordinate = g*s + d
   int oys, oxs, oy0, ox0;         // dY coordinate = g*os + o0
   int base_offset_mode;           // descriptor base_offset for row-shifted starts: 0 = none, 1 = (addr >> 7) & 7
+  int per_batch, chunks_per_img, splits_per_img;   // per-batch weights: splits never cross images
+  long long dw_batch_stride;
   float* dw;
 };
 
@@ -133,9 +135,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
   const int tile = blockIdx.x;
   const int co0 = (tile % p.tiles_co) * 128, ci0 = (tile / p.tiles_co) * BN;
   const int split = blockIdx.y;
-  const int c_beg = split * p.chunks_per_split;
+  int c_beg = split * p.chunks_per_split;
   int c_end = c_beg + p.chunks_per_split; if (c_end > p.total_chunks) c_end = p.total_chunks;
-  const int nchunks = c_end - c_beg;
+  long long dw_off = 0;
+  if (p.per_batch) {
+    const int n = split / p.splits_per_img, sp = split % p.splits_per_img;
+    c_beg = n * p.chunks_per_img + sp * p.chunks_per_split;
+    c_end = c_beg + p.chunks_per_split;
+    if (c_end > (n + 1) * p.chunks_per_img) c_end = (n + 1) * p.chunks_per_img;
+    dw_off = n * p.dw_batch_stride;
+  }
+  const int nchunks = c_end > c_beg ? c_end - c_beg : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -194,7 +204,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
     tc_fence_after();
     if (nchunks > 0) {
       for (int t = 0; t < nt; ++t) {
-        float* wrow = p.dw + (static_cast<long long>(p.tap_index[g][t]) * p.Cout + co) * p.Cin;
+        float* wrow = p.dw + dw_off + (static_cast<long long>(p.tap_index[g][t]) * p.Cout + co) * p.Cin;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
           uint32_t r[32];
@@ -242,7 +252,7 @@ extern "C" int cd_wgrad_tc_set_mode(int mode) { g_wg_mode = mode; return 0; }
 // returns 1 if the problem is not tensor-core shaped (caller falls back to the SIMT kernel), 0 on success, <0 on error
 int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, cudaStream_t st) {
   const CdConvSrc& c = d->s[0];
-  if (c.w_per_batch || c.C % 32 != 0 || d->Cout % 32 != 0 || c.ld % 4 != 0 || dout_ld % 4 != 0) return 1;
+  if (c.C % 32 != 0 || d->Cout % 32 != 0 || c.ld % 4 != 0 || dout_ld % 4 != 0) return 1;
   if (!is_pow2(d->Wg) || d->Wg < 8 || !is_pow2(d->Hg)) return 1;
   if ((reinterpret_cast<uintptr_t>(c.src) & 15) || (reinterpret_cast<uintptr_t>(dout) & 15) || (reinterpret_cast<uintptr_t>(dw) & 15)) return 1;
   EncodeTiledFn enc = get_encode();
@@ -300,6 +310,15 @@ int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float*
   if (splits < 1) splits = 1;
   p.chunks_per_split = cd_cdiv(p.total_chunks, splits);
   p.splits = cd_cdiv(p.total_chunks, p.chunks_per_split);
+  if (c.w_per_batch) {
+    p.per_batch = 1;
+    p.chunks_per_img = p.chunks_x * p.chunks_y;
+    int spi = cd_cdiv(splits, d->B); if (spi < 1) spi = 1; if (spi > p.chunks_per_img) spi = p.chunks_per_img;
+    p.chunks_per_split = cd_cdiv(p.chunks_per_img, spi);
+    p.splits_per_img = cd_cdiv(p.chunks_per_img, p.chunks_per_split);
+    p.splits = p.splits_per_img * d->B;
+    p.dw_batch_stride = static_cast<long long>(c.ntaps) * d->Cout * c.C;
+  }
   const int a_bytes = 4 * KR * 128;
   const int b_rows = p.R * (p.CW + p.halo);
   const int b_rows_pad = (b_rows + 7) / 8 * 8;                 // keep every chunk base 1024-byte aligned

@@ -17,6 +17,24 @@ from .engine import T1, T3, T4, T3D, TPAR, _tc_ok
 NULL = C.c_void_p(0)
 
 
+def flat_offsets(named_numels):
+    """[(name, numel)] -> ({name: (offset, numel)}, total) with every slice 16-byte aligned: the layout shared by the
+    flat parameter / gradient / Adam-moment / EMA buffers and by the single NCCL all-reduce."""
+    table, off = {}, 0
+    for n, k in named_numels:
+        table[n] = (off, k)
+        off += (k + 3) // 4 * 4
+    return table, off
+
+
+def allreduce_mean_(flat_grad, world):
+    """the one collective of the training step: sum-all-reduce the flat gradient; returns the 1/world scale that the
+    fused Adam kernel applies (DB:1192: the loss is a mean of equal-size per-replica means)."""
+    if world > 1:
+        torch.distributed.all_reduce(flat_grad)
+    return 1.0 / world
+
+
 class BackwardMixin:
     # ------------------------------------------------------------------------------------------
     # gradient storage
@@ -25,14 +43,12 @@ class BackwardMixin:
         if getattr(self, 'flat_grad', None) is not None:
             return
         params = list(self.unet.named_parameters())
-        total = sum((p.numel() + 3) // 4 * 4 for _, p in params)
+        self._offsets, total = flat_offsets([(n, p.numel()) for n, p in params])
         self.flat_grad = torch.zeros(total, device=self.dev, dtype=torch.float32)
         self.G = {}
-        off = 0
         for n, p in params:
-            self.G[n] = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += (p.numel() + 3) // 4 * 4          # 16-byte aligned slices
-        self._pnames = {id(p): n for n, p in params}
+            off, k = self._offsets[n]
+            self.G[n] = self.flat_grad[off:off + k].view_as(p)
 
     def flatten_params(self):
         """rebind every parameter's storage to a slice of ONE flat fp32 buffer (same offsets as flat_grad) so the
@@ -41,13 +57,12 @@ class BackwardMixin:
         if getattr(self, 'flat_param', None) is not None:
             return
         self.flat_param = torch.zeros_like(self.flat_grad)
-        off = 0
         with torch.no_grad():
             for n, p in self.unet.named_parameters():
-                v = self.flat_param[off:off + p.numel()].view_as(p)
+                off, k = self._offsets[n]
+                v = self.flat_param[off:off + k].view_as(p)
                 v.copy_(p.data)
                 p.data = v
-                off += (p.numel() + 3) // 4 * 4
         self.mark_weights_dirty()
 
     def attach_grads(self):
@@ -137,9 +152,12 @@ class BackwardMixin:
             dh = dhn
         # ---- time conditioning + depthwise bias ----
         if bs.cond_off is not None:
-            call('cd_colsum_batched', ptr(dh), ld_in, B, C.c_int64(H * W), bs.din,
-                 C.c_void_p(self._dcond.data_ptr() + 4 * bs.cond_off), self.sumC, stream())
-        call('cd_colsum', ptr(dh), ld_in, C.c_int64(B * H * W), bs.din, ptr(G[pn + '.ds_conv.bias']), stream())
+            dslice = C.c_void_p(self._dcond.data_ptr() + 4 * bs.cond_off)
+            call('cd_colsum_batched', ptr(dh), ld_in, B, C.c_int64(H * W), bs.din, dslice, self.sumC, stream())
+            # d(ds_conv.bias) = sum_b dcond[b]  (same per-pixel gradient, already reduced over pixels)
+            call('cd_colsum', dslice, self.sumC, C.c_int64(B), bs.din, ptr(G[pn + '.ds_conv.bias']), stream())
+        else:
+            call('cd_colsum', ptr(dh), ld_in, C.c_int64(B * H * W), bs.din, ptr(G[pn + '.ds_conv.bias']), stream())
         call('cd_dwconv7_wgrad', ptr(dh), ld_in, C.c_void_p(xv.addr()), xv.ld, B, H, W, bs.din,
              ptr(G[pn + '.ds_conv.weight']), stream())
         if not need_dx:
@@ -174,7 +192,7 @@ class BackwardMixin:
         dweff.zero_()
         qv = View(qkv, 0, 128)
         d = ops.make_conv_desc([(qv, T1, dweff, True)], dyv, grid, Cout=dim)
-        ops.conv_wgrad(d, dyv, dweff, None)
+        ops.conv_wgrad(d, dyv, dweff, None, impl=self.conv_impl)
         dctxn = self.buf('g.dctxn', (B, 4, 32, 32))
         rowdot = self.buf('g.rowdot', (B, 128))
         call('cd_linattn_bwd_small', ptr(dweff), ptr(ctx), ptr(ksum), ptr(a.to_out.weight), B, dim, C.c_float(a.scale),

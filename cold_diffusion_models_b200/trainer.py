@@ -187,10 +187,8 @@ class Trainer(object):
             u_loss = loss.detach() if u_loss is None else u_loss + loss.detach()
             (loss / self.gradient_accumulate_every).backward()
         eng = self._unet.engine
-        scale = 1.0
-        if self._world > 1:
-            torch.distributed.all_reduce(eng.flat_grad)          # one NCCL all-reduce per optimizer step
-            scale = 1.0 / self._world
+        from .engine_bwd import allreduce_mean_
+        scale = allreduce_mean_(eng.flat_grad, self._world)      # one NCCL all-reduce per optimizer step
         ema_mode = 0
         if self.step % self.update_ema_every == 0:
             ema_mode = 1 if self.step < self.step_start_ema else 2

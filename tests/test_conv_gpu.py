@@ -259,3 +259,20 @@ def test_wgrad_tc_matches_fp64(ops, case, mode):
             assert e < 1e-5, e
     finally:
         lib.cd_wgrad_tc_set_mode(1)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('hw', [16, 64])
+def test_wgrad_per_batch(ops, impl, hw):
+    """per-batch weight gradient dweff[b][co][hd] = sum_pix dy[b,pix,co] * q[b,pix,hd] (LinearAttention backward)."""
+    g = torch.Generator().manual_seed(23)
+    B, dim = 3, 64
+    q = tf32_rn(torch.randn(B, hw, hw, 384, generator=g))
+    dy = tf32_rn(torch.randn(B, hw, hw, dim, generator=g))
+    ref = torch.einsum('bhwo,bhwc->boc', dy.double(), q[..., :128].double())
+    dweff = torch.zeros(B, dim, 128, device='cuda')
+    dyv = ops.View(dy.cuda())
+    d = ops.make_conv_desc([(ops.View(q.cuda(), 0, 128), ops.taps_conv(1, 0), dweff, True)], dyv, (B, hw, hw), Cout=dim)
+    ops.conv_wgrad(d, dyv, dweff, None, impl=ops.CONV_TC if impl == 'tc' else ops.CONV_SIMT)
+    torch.cuda.synchronize()
+    assert rel(dweff.cpu(), ref) < 1e-5
