@@ -10,6 +10,9 @@ namespace {
 //   xhat = (h - mean) * rstd ; dxh = dy * g ; dh = rstd * (dxh - mean_c(dxh) - xhat * mean_c(dxh * xhat)) (+ addend)
 //   dg[c] += sum_pix dy * xhat ; dbeta[c] += sum_pix dy
 // ---------------------------------------------------------------------------------------------
+// lanes are split into groups of G = min(32, C/4) (a power of two): each group owns one pixel per iteration, each lane
+// C/(4G) float4 slots; two iterations are in flight per warp so the load->reduce->store chain is not latency-bound.
+template <int NQ>     // float4 slots per lane
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ h, int h_ld,
                      const float* __restrict__ stats, const float* __restrict__ g, long long npix, int C,
@@ -18,35 +21,46 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __res
   extern __shared__ float red[];   // [2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int nq = C >> 2;
-  float4 ag[8], ab[8];
+  const int G = nq < 32 ? nq : 32;               // lanes per pixel
+  const int ppw = 32 / G;                         // pixels per warp iteration
+  const int sub = lane / G, gl = lane % G;
+  float4 ag[NQ], ab[NQ], gv[NQ];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NQ; ++i) {
+    ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0);
+    const int qd = gl + i * G;
+    gv[i] = qd < nq ? *reinterpret_cast<const float4*>(g + qd * 4) : make_float4(0, 0, 0, 0);
+  }
   const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
   long long p1 = p0 + pix_per_block; if (p1 > npix) p1 = npix;
-  for (long long pix = p0 + warp; pix < p1; pix += nwarp) {
-    const float mean = stats[pix * 2], rstd = stats[pix * 2 + 1];
-    float4 dv[8], xh[8];
+  for (long long base = p0 + static_cast<long long>(warp) * ppw; base < p1; base += static_cast<long long>(nwarp) * ppw) {
+    const long long pix = base + sub;
+    const bool valid = pix < p1;
+    float mean = 0.f, rstd = 0.f;
+    if (valid) { mean = stats[pix * 2]; rstd = stats[pix * 2 + 1]; }
+    float4 dv[NQ], xh[NQ];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int qd = lane + i * 32;
-      if (qd < nq) {
+    for (int i = 0; i < NQ; ++i) {
+      const int qd = gl + i * G;
+      dv[i] = make_float4(0, 0, 0, 0); xh[i] = make_float4(0, 0, 0, 0);
+      if (valid && qd < nq) {
         const float4 d = *reinterpret_cast<const float4*>(dy + pix * dy_ld + qd * 4);
         const float4 hv = *reinterpret_cast<const float4*>(h + pix * h_ld + qd * 4);
-        const float4 gv = *reinterpret_cast<const float4*>(g + qd * 4);
         xh[i] = make_float4((hv.x - mean) * rstd, (hv.y - mean) * rstd, (hv.z - mean) * rstd, (hv.w - mean) * rstd);
         ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
         ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-        dv[i] = make_float4(d.x * gv.x, d.y * gv.y, d.z * gv.z, d.w * gv.w);
+        dv[i] = make_float4(d.x * gv[i].x, d.y * gv[i].y, d.z * gv[i].z, d.w * gv[i].w);
         s1 += dv[i].x + dv[i].y + dv[i].z + dv[i].w;
         s2 += dv[i].x * xh[i].x + dv[i].y * xh[i].y + dv[i].z * xh[i].z + dv[i].w * xh[i].w;
       }
     }
-    s1 = cd_warp_sum(s1) / C; s2 = cd_warp_sum(s2) / C;
+    for (int o = G >> 1; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    s1 /= C; s2 /= C;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int qd = lane + i * 32;
-      if (qd < nq) {
+    for (int i = 0; i < NQ; ++i) {
+      const int qd = gl + i * G;
+      if (valid && qd < nq) {
         float4 o;
         o.x = rstd * (dv[i].x - s1 - xh[i].x * s2); o.y = rstd * (dv[i].y - s1 - xh[i].y * s2);
         o.z = rstd * (dv[i].z - s1 - xh[i].z * s2); o.w = rstd * (dv[i].w - s1 - xh[i].w * s2);
@@ -62,8 +76,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __res
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int qd = lane + i * 32;
+  for (int i = 0; i < NQ; ++i) {
+    const int qd = gl + i * G;
     if (qd < nq) {
       atomicAdd(&red[qd * 4 + 0], ag[i].x); atomicAdd(&red[qd * 4 + 1], ag[i].y);
       atomicAdd(&red[qd * 4 + 2], ag[i].z); atomicAdd(&red[qd * 4 + 3], ag[i].w);
@@ -77,42 +91,55 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __res
 
 // ---------------------------------------------------------------------------------------------
 // depthwise 7x7 weight gradient: dw[c][ky*7+kx] += sum_{b,y,x} dh[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]
-// thread = (channel, ky): slides along x with a 7-wide register window of the input row, so every pixel costs one
-// dh load + one x load (128-byte coalesced across the 32 channels of a warp, L1-resident across ky) and 7 FMAs.
-// block = (b, group of kDwR rows, 32-channel slab) x 7 ky.
+// block = (b, TY x TX pixel tile, 32-channel slab): the dh tile and the x tile with its 3-pixel halo are staged in
+// shared memory once; warp ky (7 warps, lane = channel) slides along x with a 7-wide register window of input row
+// y+ky-3, so every pixel costs two conflict-free LDS and 7 FMAs.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDwR = 16;
-__global__ void __launch_bounds__(224)
+constexpr int kDwSeg = 4;                        // x segments per tile row: 7 ky x 4 segments = 28 warps per block
+__global__ void __launch_bounds__(224 * kDwSeg)
 dwconv7_wgrad_kernel(const float* __restrict__ dh, int dh_ld, const float* __restrict__ x, int x_ld,
-                     int B, int H, int W, int C, float* __restrict__ dw) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ky = threadIdx.x >> 5;                 // 0..6
-  const int ygroups = (H + kDwR - 1) / kDwR;
-  const int b = blockIdx.y / ygroups, y0 = (blockIdx.y % ygroups) * kDwR;
-  if (c >= C) return;
+                     int B, int H, int W, int C, float* __restrict__ dw, int TY, int TX) {
+  extern __shared__ float sm[];                  // xs[(TY+6)][(TX+6)][32] | ds[TY][TX][32]
+  const int XW = TX + 6;
+  float* xs = sm;
+  float* ds = sm + (TY + 6) * XW * 32;
+  const int lane = threadIdx.x & 31, ky = (threadIdx.x >> 5) % 7, seg = (threadIdx.x >> 5) / 7;
+  const int c0 = blockIdx.x * 32;
+  const int tiles_x = W / TX, tiles_y = H / TY;
+  const int tx = blockIdx.y % tiles_x, ty = (blockIdx.y / tiles_x) % tiles_y, b = blockIdx.y / (tiles_x * tiles_y);
+  const int x0 = tx * TX, y0 = ty * TY;
+  const bool cvalid = c0 + lane < C;
+  for (int i = threadIdx.x; i < (TY + 6) * XW * 32; i += blockDim.x) {
+    const int cc = i & 31, px = (i >> 5) % XW, ry = (i >> 5) / XW;
+    const int iy = y0 + ry - 3, ix = x0 + px - 3;
+    float v = 0.f;
+    if (c0 + cc < C && iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<long long>(b) * H + iy) * W + ix) * x_ld + c0 + cc];
+    xs[i] = v;
+  }
+  for (int i = threadIdx.x; i < TY * TX * 32; i += blockDim.x) {
+    const int cc = i & 31, px = (i >> 5) % TX, ry = (i >> 5) / TX;
+    ds[i] = (c0 + cc < C) ? dh[((static_cast<long long>(b) * H + y0 + ry) * W + x0 + px) * dh_ld + c0 + cc] : 0.f;
+  }
+  __syncthreads();
   float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int yy = y0; yy < min(H, y0 + kDwR); ++yy) {
-    const int iy = yy + ky - 3;
-    if (iy < 0 || iy >= H) continue;
-    const float* drow = dh + ((static_cast<long long>(b) * H + yy) * W) * dh_ld + c;
-    const float* xrow = x + ((static_cast<long long>(b) * H + iy) * W) * x_ld + c;
-    // window w[k] = x[px + k - 3]
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-    float w3 = xrow[0];
-    float w4 = W > 1 ? xrow[x_ld] : 0.f;
-    float w5 = W > 2 ? xrow[2 * x_ld] : 0.f;
-    float w6;
+  const int TS = TX / kDwSeg, px0 = seg * TS;       // this warp's pixel columns [px0, px0 + TS)
+  for (int ry = 0; ry < TY; ++ry) {
+    const float* xr = xs + ((ry + ky) * XW + px0) * 32 + lane;  // input row y0+ry+ky-3, starting at x0+px0-3
+    const float* dr = ds + (ry * TX + px0) * 32 + lane;
+    float w0 = xr[0], w1 = xr[32], w2 = xr[64], w3 = xr[96], w4 = xr[128], w5 = xr[160], w6;
 #pragma unroll 4
-    for (int px = 0; px < W; ++px) {
-      w6 = (px + 3 < W) ? xrow[static_cast<long long>(px + 3) * x_ld] : 0.f;
-      const float d = drow[static_cast<long long>(px) * dh_ld];
+    for (int px = 0; px < TS; ++px) {
+      w6 = xr[(px + 6) * 32];
+      const float d = dr[px * 32];
       acc[0] = fmaf(d, w0, acc[0]); acc[1] = fmaf(d, w1, acc[1]); acc[2] = fmaf(d, w2, acc[2]); acc[3] = fmaf(d, w3, acc[3]);
       acc[4] = fmaf(d, w4, acc[4]); acc[5] = fmaf(d, w5, acc[5]); acc[6] = fmaf(d, w6, acc[6]);
       w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
     }
   }
+  if (cvalid) {
 #pragma unroll
-  for (int kx = 0; kx < 7; ++kx) atomicAdd(dw + c * 49 + ky * 7 + kx, acc[kx]);
+    for (int kx = 0; kx < 7; ++kx) atomicAdd(dw + (c0 + lane) * 49 + ky * 7 + kx, acc[kx]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -343,18 +370,36 @@ extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int 
                                 const float* g, int64_t npix, int C, const float* addend, int addend_ld,
                                 float* dh, int dh_ld, float* dg, float* dbeta, void* stream) {
   CD_REQUIRE(C % 4 == 0 && C <= 1024 && dy_ld % 4 == 0 && h_ld % 4 == 0 && dh_ld % 4 == 0, "cd_layernorm_bwd: unsupported C=%d", C);
-  int ppb = 256;
+  const int nq = C / 4;
+  CD_REQUIRE((nq & (nq - 1)) == 0 || nq >= 32, "cd_layernorm_bwd: C/4 must be a power of two below 128 channels (C=%d)", C);
+  int ppb = 512;
   const int blocks = cd_cdiv(npix, ppb);
-  layernorm_bwd_kernel<<<blocks, 256, sizeof(float) * 2 * C, static_cast<cudaStream_t>(stream)>>>(
-      dy, dy_ld, h, h_ld, stats, g, npix, C, addend, addend_ld, dh, dh_ld, dg, dbeta, ppb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = sizeof(float) * 2 * C;
+  const int slots = nq <= 32 ? 1 : cd_cdiv(nq, 32);
+#define CD_LNB(N) layernorm_bwd_kernel<N><<<blocks, 256, smem, st>>>(dy, dy_ld, h, h_ld, stats, g, npix, C, addend, addend_ld, dh, dh_ld, dg, dbeta, ppb)
+  if (slots == 1) CD_LNB(1); else if (slots == 2) CD_LNB(2); else if (slots <= 4) CD_LNB(4); else CD_LNB(8);
+#undef CD_LNB
   CD_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int cd_dwconv7_wgrad(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C,
                                 float* dw, void* stream) {
-  dim3 grid(cd_cdiv(C, 32), B * cd_cdiv(H, kDwR));
-  dwconv7_wgrad_kernel<<<grid, 224, 0, static_cast<cudaStream_t>(stream)>>>(dh, dh_ld, x, x_ld, B, H, W, C, dw);
+  // tile: TX = min(W, 64); TY as large as fits ~190 KB of shared memory (both divide the image)
+  int TX = W < 64 ? W : 64;
+  while (W % TX) --TX;
+  CD_REQUIRE(TX % kDwSeg == 0, "cd_dwconv7_wgrad: image width %d unsupported", W);
+  int TY = H < 16 ? H : 16;
+  while (H % TY) --TY;
+  auto bytes = [&](int ty) { return sizeof(float) * 32 * (size_t(ty + 6) * (TX + 6) + size_t(ty) * TX); };
+  while (TY > 1 && bytes(TY) > 190 * 1024) { --TY; while (H % TY) --TY; }
+  const size_t smem = bytes(TY);
+  CD_REQUIRE(smem <= 200 * 1024, "cd_dwconv7_wgrad: tile does not fit (W=%d)", W);
+  static size_t attr = 0;
+  if (smem > attr) { CD_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  dim3 grid(cd_cdiv(C, 32), B * (H / TY) * (W / TX));
+  dwconv7_wgrad_kernel<<<grid, 224 * kDwSeg, smem, static_cast<cudaStream_t>(stream)>>>(dh, dh_ld, x, x_ld, B, H, W, C, dw, TY, TX);
   CD_LAUNCH_CHECK();
   return 0;
 }

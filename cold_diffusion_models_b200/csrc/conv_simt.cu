@@ -227,6 +227,54 @@ wgrad_simt_kernel(const WgradParams p) {
   }
 }
 
+// weight gradient for image-edge convolutions (Cin <= 4): thread = output channel, the receptive fields of a chunk of
+// pixels are staged in shared memory and broadcast; dout reads are coalesced over channels.
+__global__ void __launch_bounds__(128)
+wgrad_smallc_kernel(const WgradParams p) {
+  __shared__ float patch[64][kSmallK + 1];
+  __shared__ long long opix_s[64];
+  const int co = blockIdx.y * 128 + threadIdx.x;
+  const int K = p.ntaps * p.C;
+  const long long total = static_cast<long long>(p.B) * p.Hg * p.Wg;
+  const long long pbeg = static_cast<long long>(blockIdx.x) * p.pix_per_split;
+  long long pend = pbeg + p.pix_per_split; if (pend > total) pend = total;
+  float acc[kSmallK];
+#pragma unroll
+  for (int k = 0; k < kSmallK; ++k) acc[k] = 0.f;
+  const int hw = p.Hg * p.Wg;
+  for (long long q0 = pbeg; q0 < pend; q0 += 64) {
+    __syncthreads();
+    // stage the receptive fields: thread -> (pixel pp, tap group); 64 pixels x ntaps taps over 128 threads
+    for (int i = threadIdx.x; i < 64 * p.ntaps; i += blockDim.x) {
+      const int pp = i & 63, tap = i >> 6;
+      const long long q = q0 + pp;
+      const bool valid = q < pend;
+      const int b = valid ? static_cast<int>(q / hw) : 0;
+      const int rem = valid ? static_cast<int>(q - static_cast<long long>(b) * hw) : 0;
+      const int gy = rem / p.Wg, gx = rem - gy * p.Wg;
+      if (tap == 0) opix_s[pp] = (static_cast<long long>(b) * p.Ho + (gy * p.oys + p.oy0)) * p.Wo + (gx * p.oxs + p.ox0);
+      const int iy = gy * p.sy + p.dy[tap], ix = gx * p.sx + p.dx[tap];
+      const bool inb = valid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      const float* row = p.src + ((static_cast<long long>(b) * p.H + iy) * p.W + ix) * p.ld;
+      for (int c = 0; c < p.C; ++c) patch[pp][tap * p.C + c] = inb ? row[c] : 0.f;
+    }
+    __syncthreads();
+    if (co < p.Cout) {
+      const int np = static_cast<int>(pend - q0 < 64 ? pend - q0 : 64);
+      for (int pp = 0; pp < np; ++pp) {
+        const float d = p.dout[opix_s[pp] * p.dout_ld + co];
+#pragma unroll
+        for (int k = 0; k < kSmallK; ++k) if (k < K) acc[k] = fmaf(d, patch[pp][k], acc[k]);
+      }
+    }
+  }
+  if (co < p.Cout) {
+#pragma unroll
+    for (int k = 0; k < kSmallK; ++k)
+      if (k < K) atomicAdd(p.dw + (static_cast<long long>(k / p.C) * p.Cout + co) * p.C + (k % p.C), acc[k]);
+  }
+}
+
 // column sums: out[c] += sum_rows x[row*ld + c]
 __global__ void colsum_kernel(const float* x, int ld, long long rows, int C, float* out, long long rows_per_block) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -349,6 +397,13 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   p.src = c.src; p.dout = dout; p.dout_ld = dout_ld; p.Ho = d->Ho; p.Wo = d->Wo;
   p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0; p.dw = dw;
   const long long total = static_cast<long long>(d->B) * d->Hg * d->Wg;
+  if (c.C <= 4 && c.ntaps * c.C <= kSmallK && !c.w_per_batch) {
+    int splits = cd_cdiv(total, 2048); if (splits > 148 * 4) splits = 148 * 4; if (splits < 1) splits = 1;
+    p.pix_per_split = cd_cdiv(total, splits);
+    dim3 grid(cd_cdiv(total, p.pix_per_split), cd_cdiv(d->Cout, 128));
+    wgrad_smallc_kernel<<<grid, 128, 0, st>>>(p);
+    CD_LAUNCH_CHECK();
+  } else {
   const int tiles = cd_cdiv(d->Cout, TM) * cd_cdiv(c.C, TNc) * c.ntaps;
   int splits = cd_cdiv(148 * 4, tiles);
   const int max_splits = cd_cdiv(total, 256);
@@ -369,6 +424,7 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   dim3 grid(cd_cdiv(d->Cout, TM), cd_cdiv(c.C, TNc), c.ntaps * splits);
   wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);
   CD_LAUNCH_CHECK();
+  }
   }
   if (db) {
     const long long rows = static_cast<long long>(d->B) * d->Ho * d->Wo;

@@ -9,17 +9,18 @@
 // packed weight slab [tap][Cout][Cin] (K-major), a 3-D TMA box {32, BN, 1}.  Both land in
 // 128-byte-swizzled shared memory and feed tcgen05.mma.kind::tf32 straight from descriptors.
 //
-// Warp roles (192 threads, persistent over output tiles, static round-robin schedule):
+// Warp roles (576 threads, persistent over output tiles, static round-robin schedule):
 //   warp 0 : TMA producer (one lane)            -- full/empty mbarrier ring, STAGES deep
 //   warp 1 : TMEM allocator + MMA issuer (one lane), 2 accumulator buffers in TMEM
-//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns, +bias, (+GELU), (+residual),
-//              optional TF32 rounding for the next conv, 128-byte row stores
+//   warps 2-17: epilogue -- tcgen05.ld 32 lanes x 32 columns, +bias, (+GELU), (+residual), (x GELU'),
+//              128-byte row stores; 4 warps per TMEM lane quarter, each taking every 4th column chunk
 // so the epilogue of tile i overlaps the mainloop of tile i+1.
 #include "cd_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;                // 4 TMEM lane quarters x 4 column groups
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                 // fp32 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kTileM * 128;       // 16 KiB per stage
@@ -149,7 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], kEpiWarps); mbar_init(&tmem_empty[1], kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -219,8 +220,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..17) =====================
+    // The epilogue (TMEM -> regs -> bias/GELU/residual -> global) costs about as many issue slots per tile as the
+    // MMAs of a 3x3 tile take cycles, so it is spread over 16 warps: warp w serves TMEM lane quarter w % 4 and the
+    // 32-column chunks cg, cg + 4, ... (ncu r01: 4 epilogue warps left the tensor pipe 15-30 % busy).
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int cg = (warp - 2) >> 2;                  // column group 0..3
     const int m = q * 32 + lane;                     // accumulator row == pixel within the tile
     const int xx = m % p.TW;
     const int yy = (m / p.TW) % p.TH;
@@ -246,7 +251,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = cg * 32; c < BN; c += 32 * (kEpiWarps / 4)) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         if (valid && co0 + c < p.Cout) {

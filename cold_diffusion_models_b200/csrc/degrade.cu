@@ -268,3 +268,52 @@ extern "C" int cd_adam_ema_step(float* p, const float* g, float* m, float* v, fl
   CD_LAUNCH_CHECK();
   return 0;
 }
+
+// -------------------------------------------------------------------------------------------------------------
+// Gaussian-noise ("hot") baseline of denoising-diffusion-pytorch (DN = denoising-diffusion-pytorch/
+// denoising_diffusion_pytorch/denoising_diffusion_pytorch.py): q_sample = per-sample lerp with the cosine-schedule
+// coefficients (DN:517-522) and the ddim / x0_step_down reverse step (DN:383-434), one elementwise kernel each,
+// same operation order as the reference.
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void noise_lerp_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const long long* __restrict__ t,
+                                  int t_scalar, const float* __restrict__ sa, const float* __restrict__ sb, long long per_sample,
+                                  long long n, float* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tt = t ? static_cast<int>(t[i / per_sample]) : t_scalar;
+    out[i] = sa[tt] * x1[i] + sb[tt] * x2[i];
+  }
+}
+// mode 0: ddim (x2 estimated from x_t), mode 1: x0_step_down (x2 = the fixed initial noise)
+__global__ void noise_step_kernel(const float* __restrict__ img, const float* __restrict__ x1, const float* __restrict__ noise,
+                                  int mode, int t, const float* __restrict__ sa, const float* __restrict__ sb, long long n,
+                                  float* __restrict__ out) {
+  const float a1 = sa[t - 1], b1 = sb[t - 1];
+  const float a2 = t - 1 != 0 ? sa[t - 2] : 0.f, b2 = t - 1 != 0 ? sb[t - 2] : 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float xv = x1[i], im = img[i];
+    const float x2 = mode == 0 ? (im - a1 * xv) / b1 : noise[i];
+    const float xt_bar = a1 * xv + b1 * x2;
+    const float xt_sub1 = (t - 1 != 0) ? a2 * xv + b2 * x2 : xv;
+    out[i] = im - xt_bar + xt_sub1;
+  }
+}
+}  // namespace
+
+extern "C" int cd_noise_lerp(const float* x1, const float* x2, const int64_t* t, int t_scalar, const float* sqrt_ac,
+                             const float* sqrt_1mac, int64_t per_sample, int64_t n, float* out, void* stream) {
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  noise_lerp_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x1, x2, reinterpret_cast<const long long*>(t), t_scalar,
+                                                                         sqrt_ac, sqrt_1mac, per_sample, n, out);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_noise_step(const float* img, const float* x1_bar, const float* noise, int mode, int t, const float* sqrt_ac,
+                             const float* sqrt_1mac, int64_t n, float* out, void* stream) {
+  CD_REQUIRE(t >= 1 && (mode == 0 || (mode == 1 && noise)), "cd_noise_step: bad arguments");
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  noise_step_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, x1_bar, noise, mode, t, sqrt_ac, sqrt_1mac, n, out);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

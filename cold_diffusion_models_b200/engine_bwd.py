@@ -130,9 +130,16 @@ class BackwardMixin:
         pn = bs.name
         grid = (B, H, W)
         # ---- conv2 (+ res_conv) ----
-        self._wgrad(uv, T3, bs.dout, grid, dyv, G[pn + '.net.3.weight'], G[pn + '.net.3.bias'], key=pn + '.w2')
         if bs.has_res:
-            self._wgrad(xv, T1, bs.dout, grid, dyv, G[pn + '.res_conv.weight'], G[pn + '.res_conv.bias'], key=pn + '.wr')
+            # conv2 and res_conv add into the same output: one column sum of dy feeds both bias gradients
+            tmp = self.buf('g.dbias', (max(b_.dout for b_ in self.blocks.values()),))
+            tmp.zero_()
+            self._wgrad(uv, T3, bs.dout, grid, dyv, G[pn + '.net.3.weight'], tmp, key=pn + '.w2')
+            self._wgrad(xv, T1, bs.dout, grid, dyv, G[pn + '.res_conv.weight'], None, key=pn + '.wr')
+            for leaf in ('.net.3.bias', '.res_conv.bias'):
+                call('cd_add', ptr(G[pn + leaf]), bs.dout, ptr(tmp), bs.dout, ptr(G[pn + leaf]), bs.dout, C.c_int64(1), bs.dout, stream())
+        else:
+            self._wgrad(uv, T3, bs.dout, grid, dyv, G[pn + '.net.3.weight'], G[pn + '.net.3.bias'], key=pn + '.w2')
         dpre = self.buf('g.pre.%dx%dx%d' % (H, W, bs.dmid), (B, H, W, bs.dmid))
         d = ops.make_conv_desc([(dyv, T3D, P[pn + '.w2T'], False)], View(dpre), grid, Cout=bs.dmid,
                                act=ACT_GELU_BWD, aux=prev)

@@ -177,13 +177,16 @@ class Trainer(object):
         self.ema_model.load_state_dict(_match_prefix(d['ema'], self.ema_model))
 
     # ---- hot loop --------------------------------------------------------------------------------------
+    def _loss(self, d):
+        return torch.mean(self.model(d))                       # DB:1192
+
     def train_step(self, batches=None):
         """one optimizer step = gradient_accumulate_every micro-batches (DB:1188-1204). Returns mean loss (tensor)."""
         u_loss = None
         for i in range(self.gradient_accumulate_every):
             d = batches[i] if batches is not None else next(self.dl)
             d = d.cuda(non_blocking=True)
-            loss = torch.mean(self.model(d))
+            loss = self._loss(d)
             u_loss = loss.detach() if u_loss is None else u_loss + loss.detach()
             (loss / self.gradient_accumulate_every).backward()
         eng = self._unet.engine
@@ -218,6 +221,14 @@ class Trainer(object):
                     self.save(self.step)
             self.step += 1
         print('training completed')
+
+
+class DenoisingTrainer(Trainer):
+    """Trainer of denoising_diffusion_pytorch: forward(x1, x2) with x2 = randn_like(x1) (DN:738-741); the noise is
+    drawn on the device instead of on the host."""
+
+    def _loss(self, d):
+        return torch.mean(self.model(d, torch.randn_like(d)))
 
 
 def _match_prefix(sd, model):

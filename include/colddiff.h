@@ -204,6 +204,14 @@ int cd_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, i
                      float lr, float beta1, float beta2, float eps, int step,
                      int ema_mode /*0 none,1 copy,2 lerp*/, float ema_beta, float grad_scale, void* stream);
 
+/* Gaussian-noise baseline (denoising-diffusion-pytorch/denoising_diffusion_pytorch/denoising_diffusion_pytorch.py, "DN"):
+ *   cd_noise_lerp : q_sample = sqrt_ac[t_b] x1 + sqrt_1mac[t_b] x2                                  (DN:517-522)
+ *   cd_noise_step : one reverse step img - xt_bar + xt_sub1_bar; mode 0 'ddim' (x2 from x_t, DN:377-381, 392-412),
+ *                   mode 1 'x0_step_down' (x2 = fixed noise, DN:414-432)                                              */
+int cd_noise_lerp(const float* x1, const float* x2, const int64_t* t, int t_scalar, const float* sqrt_ac,
+                  const float* sqrt_1mac, int64_t per_sample, int64_t n, float* out, void* stream);
+int cd_noise_step(const float* img, const float* x1_bar, const float* noise, int mode, int t, const float* sqrt_ac,
+                  const float* sqrt_1mac, int64_t n, float* out, void* stream);
 /* stand-alone EMA (DB:73-81): mode 1 copy, 2 lerp */
 int cd_ema_update(float* ema, const float* p, int64_t n, float beta, int mode, void* stream);
 

@@ -56,12 +56,17 @@ def install_stubs():
         tgm.image = img
         sys.modules["torchgeometry"] = tgm
         sys.modules["torchgeometry.image"] = img
-    for name in ("matplotlib", "matplotlib.pyplot", "kornia", "kornia.color", "imageio", "pytorch_msssim"):
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.image", "kornia", "kornia.color", "imageio", "pytorch_msssim",
+                 "cv2"):
         if name not in sys.modules:
             try:
                 __import__(name)
             except Exception:
-                sys.modules[name] = types.ModuleType(name)
+                m = types.ModuleType(name)
+                m.__path__ = []                      # lets `import pkg.sub` resolve to the stubbed sub-modules
+                sys.modules[name] = m
+                if '.' in name:
+                    setattr(sys.modules[name.split('.')[0]], name.split('.')[1], m)
 
 
 def import_reference(pkg_dir, module):

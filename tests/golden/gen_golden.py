@@ -108,6 +108,28 @@ def main():
             out['loss:' + key] = gd.p_losses(xs, tt)
     save('sample_small', x=xs, **out)
 
+    # ---- (4) Gaussian-noise baseline (denoising-diffusion-pytorch): q_sample, p_losses, gen_sample ----
+    dn = ref_shim.import_reference('denoising-diffusion-pytorch', 'denoising_diffusion_pytorch')
+    torch.manual_seed(11)
+    out = {}
+    x1 = torch.rand(2, 3, 32, 32) * 2 - 1
+    x2 = torch.randn(2, 3, 32, 32)
+    unet_dn = quiet(dn.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet_dn.load_state_dict(sd)          # same small network as (1): identical architecture and keys
+    for samp in ('ddim', 'x0_step_down'):
+        gd = dn.GaussianDiffusion(unet_dn, image_size=32, channels=3, timesteps=5, loss_type='l1', sampling_routine=samp)
+        tt = torch.tensor([4, 0])
+        out['q:' + samp] = gd.q_sample(x1, x2, tt)
+        with torch.no_grad():
+            out['loss:' + samp] = gd.p_losses(x1, x2, tt)
+        n, dr, img = quiet(gd.gen_sample, batch_size=2, img=x2)
+        out['dr:' + samp], out['img:' + samp] = dr, img
+    gd = dn.GaussianDiffusion(unet_dn, image_size=32, channels=3, timesteps=5)
+    xt, dr, img = quiet(gd.sample, batch_size=2, img=x2)
+    out['sample_dr'], out['sample_img'] = dr, img
+    out['sqrt_ac'], out['sqrt_1mac'] = gd.sqrt_alphas_cumprod, gd.sqrt_one_minus_alphas_cumprod
+    save('denoise_small', x1=x1, x2=x2, **out)
+
 
 if __name__ == '__main__':
     main()

@@ -90,6 +90,26 @@ def test_sample_and_p_losses_match_reference():
         assert abs(loss.item() - g['loss:' + key].item()) < (2e-3 if int(disc) else 1e-5), key
 
 
+def test_denoise_oracle_matches_reference():
+    import denoise_oracle as NO
+    g = load('denoise_small')
+    u = load('unet_small')
+    sd = {k[3:]: v for k, v in u.items() if k.startswith('sd:')}
+    fn = lambda x, t: UO.unet_forward(sd, x, t)
+    for samp in ('ddim', 'x0_step_down'):
+        o = NO.DenoiseOracle(fn, image_size=32, timesteps=5, sampling_routine=samp)
+        assert torch.allclose(o.sa, g['sqrt_ac'], atol=1e-7) and torch.allclose(o.sb, g['sqrt_1mac'], atol=1e-7)
+        tt = torch.tensor([4, 0])
+        assert torch.allclose(o.q_sample(g['x1'], g['x2'], tt), g['q:' + samp], atol=1e-6)
+        with torch.no_grad():
+            assert abs(o.p_losses(g['x1'], g['x2'], tt).item() - g['loss:' + samp].item()) < 1e-5
+        _, dr, img = o.gen_sample(2, g['x2'])
+        assert rel(dr, g['dr:' + samp]) < 1e-5 and rel(img, g['img:' + samp]) < 1e-4
+    o = NO.DenoiseOracle(fn, image_size=32, timesteps=5)
+    _, dr, img = o.sample(2, g['x2'])
+    assert rel(dr, g['sample_dr']) < 1e-5 and rel(img, g['sample_img']) < 1e-4
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference only in build container')
 def test_oracle_matches_live_reference_config1_mnist():
     """BASELINE config 1: MNIST-shaped 1x32x32, T=20, k=11, sigma=7, Constant, B=4, full-size Unet."""

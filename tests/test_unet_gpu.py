@@ -108,3 +108,23 @@ def test_unet_full_size_matches_oracle():
     with torch.no_grad():
         y32 = u(x.cuda(), t.cuda())
     assert rel(y32, ref) < 3e-5
+
+
+def test_denoising_package_matches_reference_golden(small):
+    """denoising_diffusion_pytorch drop-in: q_sample, p_losses, gen_sample ('ddim' / 'x0_step_down'), sample."""
+    from cold_diffusion_models_b200.denoising_diffusion_pytorch import GaussianDiffusion
+    g = load('denoise_small')
+    _, sd, u = small
+    x1, x2 = g['x1'].cuda(), g['x2'].cuda()
+    for samp in ('ddim', 'x0_step_down'):
+        gd = GaussianDiffusion(u, image_size=32, channels=3, timesteps=5, loss_type='l1', sampling_routine=samp).cuda()
+        assert torch.allclose(gd.sqrt_alphas_cumprod.cpu(), g['sqrt_ac'], atol=1e-7)
+        tt = torch.tensor([4, 0]).cuda()
+        assert torch.allclose(gd.q_sample(x1, x2, tt).cpu(), g['q:' + samp], atol=1e-6)
+        with torch.no_grad():
+            assert abs(gd.p_losses(x1, x2, tt).item() - g['loss:' + samp].item()) < 3e-4
+        n, dr, img = gd.gen_sample(batch_size=2, img=x2)
+        assert rel(dr, g['dr:' + samp]) < 1e-3 and rel(img, g['img:' + samp]) < 2e-3, samp
+    gd = GaussianDiffusion(u, image_size=32, channels=3, timesteps=5).cuda()
+    xt, dr, img = gd.sample(batch_size=2, img=x2)
+    assert rel(dr, g['sample_dr']) < 1e-3 and rel(img, g['sample_img']) < 2e-3
