@@ -234,11 +234,12 @@ def main():
     # ---- roofline of the dominant kernel (tcgen05 tap-list convolution), CUDA events around every launch --------
     peaks, peak_kind = read_peaks()
     roof = None
+    eng = unet.engine
     if rank == 0:
-        eng = unet.engine
         eng.profile_convs = []
-        step_resident(0)
-        torch.cuda.synchronize()
+    step_resident(0)                      # every rank takes part (the step contains the gradient all-reduce)
+    torch.cuda.synchronize()
+    if rank == 0:
         tot_ms = sum(a.elapsed_time(b) for (a, b, f) in eng.profile_convs)
         tot_fl = sum(f for (a, b, f) in eng.profile_convs)
         n_launch = len(eng.profile_convs)

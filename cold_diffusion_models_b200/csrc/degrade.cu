@@ -317,3 +317,69 @@ extern "C" int cd_noise_step(const float* img, const float* x1_bar, const float*
   CD_LAUNCH_CHECK();
   return 0;
 }
+
+// -------------------------------------------------------------------------------------------------------------
+// Gaussian-mask fading (defading-diffusion-pytorch/defading_diffusion_pytorch/defading_diffusion_gaussian.py, "DFG"):
+// D(x,t) = x * prod_{i<=t} K_i with K_i = (1 - g_i / max g_i)[1:,1:] (DFG:328-352).  masks: cumulative products
+// [T][MS][MS] (MS = S, or 2S for the 'Random_*' routines where every sample uses its own S x S window at offset
+// (rx[b], ry[b]), DFG:359-367, 499-507 -- integer indexing, bit-exact).  idx < 0 = identity.
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ float mask_at(const float* __restrict__ masks, int idx, int MS, int y, int x) {
+  return idx < 0 ? 1.f : masks[(static_cast<long long>(idx) * MS + y) * MS + x];
+}
+__device__ __forceinline__ float quantize8(float v) {            // DFG:380-384 / DB:954-958
+  float q = (v + 1.f) * 0.5f;
+  q = q * 255.f;
+  q = static_cast<float>(static_cast<int>(q)) / 255.f;
+  return q * 2.f - 1.f;
+}
+__global__ void mask_apply_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ masks,
+                                  const long long* __restrict__ t, int t_scalar, const long long* __restrict__ rx,
+                                  const long long* __restrict__ ry, int B, int C, int S, int MS, int quantize) {
+  const long long n = static_cast<long long>(B) * C * S * S;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(i % S), yy = static_cast<int>((i / S) % S);
+    const int b = static_cast<int>(i / (static_cast<long long>(S) * S * C));
+    const int idx = t ? static_cast<int>(t[b]) : t_scalar;
+    const int oy = rx ? static_cast<int>(rx[b]) : 0, ox = ry ? static_cast<int>(ry[b]) : 0;   // reference: rows <- rand_x, cols <- rand_y
+    float v = x[i] * mask_at(masks, idx, MS, yy + oy, xx + ox);
+    if (quantize) v = quantize8(v);
+    out[i] = v;
+  }
+}
+__global__ void mask_step_down_kernel(const float* __restrict__ xt, const float* __restrict__ xhat, float* __restrict__ out,
+                                      const float* __restrict__ masks, int idx_hi, int idx_lo, const long long* __restrict__ rx,
+                                      const long long* __restrict__ ry, int B, int C, int S, int MS) {
+  const long long n = static_cast<long long>(B) * C * S * S;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(i % S), yy = static_cast<int>((i / S) % S);
+    const int b = static_cast<int>(i / (static_cast<long long>(S) * S * C));
+    const int oy = rx ? static_cast<int>(rx[b]) : 0, ox = ry ? static_cast<int>(ry[b]) : 0;
+    const float xv = xhat[i];
+    const float hi = xv * mask_at(masks, idx_hi, MS, yy + oy, xx + ox);
+    const float lo = xv * mask_at(masks, idx_lo, MS, yy + oy, xx + ox);
+    out[i] = xt[i] - hi + lo;
+  }
+}
+}  // namespace
+
+extern "C" int cd_mask_apply(const float* x, float* out, const float* masks, const int64_t* t, int t_scalar,
+                             const int64_t* rx, const int64_t* ry, int B, int C, int S, int MS, int quantize, void* stream) {
+  const long long n = static_cast<long long>(B) * C * S * S;
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  mask_apply_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, masks, reinterpret_cast<const long long*>(t), t_scalar,
+      reinterpret_cast<const long long*>(rx), reinterpret_cast<const long long*>(ry), B, C, S, MS, quantize);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_mask_step_down(const float* xt, const float* xhat, float* out, const float* masks, int idx_hi, int idx_lo,
+                                 const int64_t* rx, const int64_t* ry, int B, int C, int S, int MS, void* stream) {
+  const long long n = static_cast<long long>(B) * C * S * S;
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  mask_step_down_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(xt, xhat, out, masks, idx_hi, idx_lo,
+      reinterpret_cast<const long long*>(rx), reinterpret_cast<const long long*>(ry), B, C, S, MS);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

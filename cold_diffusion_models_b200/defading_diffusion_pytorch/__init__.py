@@ -1,0 +1,6 @@
+"""same exports as the reference package defading_diffusion_pytorch/__init__.py (the DDPM `Model` is a next-round row)"""
+from ..unet import Unet
+from ..defading import GaussianDiffusion
+from ..trainer import Trainer
+
+__all__ = ['GaussianDiffusion', 'Unet', 'Trainer']

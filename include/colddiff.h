@@ -212,6 +212,15 @@ int cd_noise_lerp(const float* x1, const float* x2, const int64_t* t, int t_scal
                   const float* sqrt_1mac, int64_t per_sample, int64_t n, float* out, void* stream);
 int cd_noise_step(const float* img, const float* x1_bar, const float* noise, int mode, int t, const float* sqrt_ac,
                   const float* sqrt_1mac, int64_t n, float* out, void* stream);
+/* Gaussian-mask fading (defading-diffusion-pytorch/defading_diffusion_pytorch/defading_diffusion_gaussian.py, "DFG"):
+ * masks = cumulative products of the fade kernels [T][MS][MS]; rx/ry (optional, int64 [B]) = per-sample window
+ * offsets of the 'Random_*' routines (DFG:359-367); index -1 = identity.
+ *   cd_mask_apply     : out = x * M[t_b] (+ 8-bit truncation when quantize)     -- q_sample / sample head (DFG:371-384, 495-533)
+ *   cd_mask_step_down : out = x_t - xhat * M[idx_hi] + xhat * M[idx_lo]         -- DFG:410-420                      */
+int cd_mask_apply(const float* x, float* out, const float* masks, const int64_t* t, int t_scalar,
+                  const int64_t* rx, const int64_t* ry, int B, int C, int S, int MS, int quantize, void* stream);
+int cd_mask_step_down(const float* xt, const float* xhat, float* out, const float* masks, int idx_hi, int idx_lo,
+                      const int64_t* rx, const int64_t* ry, int B, int C, int S, int MS, void* stream);
 /* stand-alone EMA (DB:73-81): mode 1 copy, 2 lerp */
 int cd_ema_update(float* ema, const float* p, int64_t n, float beta, int mode, void* stream);
 

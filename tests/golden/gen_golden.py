@@ -130,6 +130,53 @@ def main():
     out['sqrt_ac'], out['sqrt_1mac'] = gd.sqrt_alphas_cumprod, gd.sqrt_one_minus_alphas_cumprod
     save('denoise_small', x1=x1, x2=x2, **out)
 
+    # ---- (5) resolution (super-resolution) package: q_sample, p_losses, sample ----------------------------
+    rs = ref_shim.import_reference('resolution-diffusion-pytorch', 'resolution_diffusion_pytorch')
+    torch.manual_seed(21)
+    out = {}
+    xr = torch.rand(2, 3, 32, 32) * 2 - 1
+    unet_rs = quiet(rs.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet_rs.load_state_dict(sd)
+    for routine, T, samp in [('Incremental_factor_2', 4, 'x0_step_down'), ('Incremental_area_factor_2', 5, 'default'),
+                             ('Incremental_bilinear', 6, 'x0_step_down'), ('Incremental_bicubic_with_blur', 3, 'x0_step_down')]:
+        gd = rs.GaussianDiffusion(unet_rs, image_size=32, device_of_kernel='cpu', channels=3, timesteps=T, loss_type='l1',
+                                  resolution_routine=routine, train_routine='Final', sampling_routine=samp)
+        tt = torch.tensor([T - 1, 1])
+        key = '%s|%d|%s' % (routine, T, samp)
+        out['q:' + key] = gd.q_sample(xr, tt)
+        with torch.no_grad():
+            out['loss:' + key] = gd.p_losses(xr, tt)
+        xt, dr, img = quiet(gd.sample, batch_size=2, img=xr)
+        out['xt:' + key], out['dr:' + key], out['img:' + key] = xt, dr, img
+    save('resolution_small', x=xr, **out)
+
+    # ---- (6) defading (Gaussian mask) package ---------------------------------------------------------------
+    df = ref_shim.import_reference('defading-diffusion-pytorch', 'defading_diffusion_pytorch')
+    torch.manual_seed(31)
+    out = {}
+    xf = torch.rand(2, 3, 32, 32) * 2 - 1
+    unet_df = quiet(df.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet_df.load_state_dict(sd)
+    for routine, T, samp, disc in [('Incremental', 4, 'x0_step_down', False), ('Constant', 3, 'default', False),
+                                   ('Random_Incremental', 4, 'x0_step_down', False), ('Incremental', 3, 'x0_step_down', True)]:
+        gd = df.GaussianDiffusion(unet_df, image_size=32, device_of_kernel='cpu', channels=3, timesteps=T, loss_type='l1',
+                                  kernel_std=0.6, initial_mask=3, fade_routine=routine, sampling_routine=samp, discrete=disc)
+        key = '%s|%d|%s|%d' % (routine, T, samp, int(disc))
+        tt = torch.tensor([T - 1, 0])
+        torch.manual_seed(77)                       # the reference draws the window offsets inside q_sample / sample
+        rx = torch.randint(0, 33, (2,)); ry = torch.randint(0, 33, (2,))
+        torch.manual_seed(77)
+        out['q:' + key] = gd.q_sample(xf, tt)
+        torch.manual_seed(77)
+        with torch.no_grad():
+            out['loss:' + key] = gd.p_losses(xf, tt)
+        torch.manual_seed(77)
+        xt, dr, img = quiet(gd.sample, batch_size=2, faded_recon_sample=xf)
+        out['xt:' + key], out['dr:' + key], out['img:' + key] = xt, dr, img
+        out['rx:' + key], out['ry:' + key] = rx, ry
+        out['k:' + key] = gd.fade_kernels
+    save('defading_small', x=xf, **out)
+
 
 if __name__ == '__main__':
     main()

@@ -110,6 +110,46 @@ def test_denoise_oracle_matches_reference():
     assert rel(dr, g['sample_dr']) < 1e-5 and rel(img, g['sample_img']) < 1e-4
 
 
+def test_resolution_oracle_matches_reference():
+    import resolution_oracle as RO
+    g = load('resolution_small')
+    u = load('unet_small')
+    sd = {k[3:]: v for k, v in u.items() if k.startswith('sd:')}
+    fn = lambda x, t: UO.unet_forward(sd, x, t)
+    for key in _cases('img:', g):
+        routine, T, samp = key.split('|')
+        o = RO.ResolutionOracle(fn, image_size=32, timesteps=int(T), resolution_routine=routine, sampling_routine=samp)
+        tt = torch.tensor([int(T) - 1, 1])
+        assert torch.allclose(o.q_sample(g['x'], tt), g['q:' + key], atol=1e-6), key
+        with torch.no_grad():
+            assert abs(o.p_losses(g['x'], tt).item() - g['loss:' + key].item()) < 1e-5
+        xt, dr, img = o.sample(2, g['x'])
+        assert rel(xt, g['xt:' + key]) < 1e-6 and rel(dr, g['dr:' + key]) < 1e-5 and rel(img, g['img:' + key]) < 1e-4, key
+
+
+def test_defading_oracle_matches_reference():
+    import defading_oracle as FO
+    g = load('defading_small')
+    u = load('unet_small')
+    sd = {k[3:]: v for k, v in u.items() if k.startswith('sd:')}
+    fn = lambda x, t: UO.unet_forward(sd, x, t)
+    for key in _cases('img:', g):
+        routine, T, samp, disc = key.split('|')
+        o = FO.DefadeOracle(fn, image_size=32, timesteps=int(T), kernel_std=0.6, initial_mask=3, fade_routine=routine,
+                            sampling_routine=samp, discrete=bool(int(disc)))
+        assert torch.equal(o.fade_kernels, g['k:' + key]), key            # masks bit-exact
+        rx, ry = (g['rx:' + key], g['ry:' + key]) if 'Random' in routine else (None, None)
+        tt = torch.tensor([int(T) - 1, 0])
+        q = o.q_sample(g['x'], tt, rx, ry)
+        if int(disc):
+            assert (q - g['q:' + key]).abs().max() <= 2 / 255 + 1e-6
+        else:
+            assert torch.allclose(q, g['q:' + key], atol=1e-6), key
+        xt, dr, img = o.sample(2, g['x'], rx=rx, ry=ry)
+        tol = 5e-3 if int(disc) else 1e-4
+        assert rel(xt, g['xt:' + key]) < tol and rel(dr, g['dr:' + key]) < tol and rel(img, g['img:' + key]) < max(tol, 1e-4), key
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference only in build container')
 def test_oracle_matches_live_reference_config1_mnist():
     """BASELINE config 1: MNIST-shaped 1x32x32, T=20, k=11, sigma=7, Constant, B=4, full-size Unet."""

@@ -128,3 +128,45 @@ def test_denoising_package_matches_reference_golden(small):
     gd = GaussianDiffusion(u, image_size=32, channels=3, timesteps=5).cuda()
     xt, dr, img = gd.sample(batch_size=2, img=x2)
     assert rel(dr, g['sample_dr']) < 1e-3 and rel(img, g['sample_img']) < 2e-3
+
+
+def test_resolution_package_matches_reference_golden(small):
+    """resolution_diffusion_pytorch drop-in (interpolate-based pixelation as cumulative operators)."""
+    from cold_diffusion_models_b200.resolution_diffusion_pytorch import GaussianDiffusion
+    g = load('resolution_small')
+    _, sd, u = small
+    x = g['x'].cuda()
+    for key in sorted(k[4:] for k in g if k.startswith('img:')):
+        routine, T, samp = key.split('|')
+        gd = GaussianDiffusion(u, image_size=32, device_of_kernel='cuda', channels=3, timesteps=int(T), loss_type='l1',
+                               resolution_routine=routine, train_routine='Final', sampling_routine=samp).cuda()
+        tt = torch.tensor([int(T) - 1, 1]).cuda()
+        assert torch.allclose(gd.q_sample(x, tt).cpu(), g['q:' + key], atol=3e-6), key
+        with torch.no_grad():
+            assert abs(gd.p_losses(x, tt).item() - g['loss:' + key].item()) < 3e-4, key
+        xt, dr, img = gd.sample(batch_size=2, img=x)
+        assert rel(xt, g['xt:' + key]) < 1e-5 and rel(dr, g['dr:' + key]) < 1e-3 and rel(img, g['img:' + key]) < 2e-3, key
+
+
+def test_defading_package_matches_reference_golden(small):
+    """defading_diffusion_pytorch drop-in (Gaussian masks; per-sample random windows indexed inside the kernel)."""
+    from cold_diffusion_models_b200.defading_diffusion_pytorch import GaussianDiffusion
+    g = load('defading_small')
+    _, sd, u = small
+    x = g['x'].cuda()
+    for key in sorted(k[4:] for k in g if k.startswith('img:')):
+        routine, T, samp, disc = key.split('|')
+        gd = GaussianDiffusion(u, image_size=32, device_of_kernel='cuda', channels=3, timesteps=int(T), loss_type='l1',
+                               kernel_std=0.6, initial_mask=3, fade_routine=routine, sampling_routine=samp,
+                               discrete=bool(int(disc))).cuda()
+        assert torch.equal(gd.fade_kernels.cpu(), g['k:' + key]), key
+        off = (g['rx:' + key].cuda(), g['ry:' + key].cuda()) if 'Random' in routine else (None, None)
+        tt = torch.tensor([int(T) - 1, 0]).cuda()
+        q = gd.q_sample(x, tt, _offsets=off).cpu()
+        if int(disc):
+            assert (q - g['q:' + key]).abs().max() <= 2 / 255 + 1e-6
+        else:
+            assert torch.allclose(q, g['q:' + key], atol=2e-6), key
+        xt, dr, img = gd.sample(batch_size=2, faded_recon_sample=x, _offsets=off)
+        tol = 1e-2 if int(disc) else 2e-3
+        assert rel(xt, g['xt:' + key]) < (tol if int(disc) else 1e-5) and rel(dr, g['dr:' + key]) < tol and rel(img, g['img:' + key]) < tol, key
