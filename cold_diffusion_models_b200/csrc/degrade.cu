@@ -383,3 +383,90 @@ extern "C" int cd_mask_step_down(const float* xt, const float* xhat, float* out,
   CD_LAUNCH_CHECK();
   return 0;
 }
+
+// -------------------------------------------------------------------------------------------------------------
+// Decolorization / Snow forward processes of snowification/ (== decolor-diffusion/) diffusion/forward_process_impl.py
+// ("FP") with the per-sample masked stepping of diffusion/diffusion.py ("SN", SN:195-245, 344-388):
+//  * decolor: every step is a per-pixel C x C channel mix f I + (1-f)/C 11^T (FP:150-163); the cumulative mix after
+//    steps 0..i is tabulated ([T][C][C]) so D(x, t_b) is one mat-vec per pixel with a PER-SAMPLE index (t_b = -1 =
+//    untouched row, SN:349-355); the masked loops of sample_one_step collapse to per-sample indices t_b-1 / t_b-2.
+//  * snow: D depends on the clean image only (FP:361-372): clip(bright_i(og) + snow_i + rot180(snow_i), 0, 1)*2-1.
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void chanmix_kernel(const float* __restrict__ xt, const float* __restrict__ xsrc, float* __restrict__ out,
+                               const float* __restrict__ mats, const long long* __restrict__ t_hi, const long long* __restrict__ t_lo,
+                               int hi_off, int lo_off, int B, int C, long long HW, int mode) {
+  // mode 0: out = M[t_hi+hi_off] xsrc ; mode 1: out = xt - M[t_hi+hi_off] xsrc + M[t_lo+lo_off] xsrc   (index < 0 = identity)
+  const long long n = static_cast<long long>(B) * HW;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / HW);
+    const long long p = i % HW;
+    const int ih = static_cast<int>(t_hi[b]) + hi_off;
+    const int il = mode ? static_cast<int>(t_lo[b]) + lo_off : -1;
+    float v[8];
+    for (int c = 0; c < C; ++c) v[c] = xsrc[(static_cast<long long>(b) * C + c) * HW + p];
+    for (int co = 0; co < C; ++co) {
+      float hi = v[co], lo = v[co];
+      if (ih >= 0) { hi = 0.f; for (int c = 0; c < C; ++c) hi = fmaf(mats[(ih * C + co) * C + c], v[c], hi); }
+      if (il >= 0) { lo = 0.f; for (int c = 0; c < C; ++c) lo = fmaf(mats[(il * C + co) * C + c], v[c], lo); }
+      const long long o = (static_cast<long long>(b) * C + co) * HW + p;
+      out[o] = mode ? xt[o] - hi + lo : hi;
+    }
+  }
+}
+__global__ void snow_kernel(const float* __restrict__ xt, const float* __restrict__ og, float* __restrict__ out,
+                            const float* __restrict__ snow, const float* __restrict__ br, const long long* __restrict__ t_hi,
+                            const long long* __restrict__ t_lo, int hi_off, int lo_off, int B, int H, int W, int snow_batch,
+                            int fix_brightness, int mode) {
+  // snow: [T][snow_batch][3][H][W]; rot180 is an index flip.  3-channel RGB only (kornia rgb_to_grayscale weights).
+  const long long HW = static_cast<long long>(H) * W, n = static_cast<long long>(B) * HW;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / HW);
+    const long long p = i % HW, pr = HW - 1 - p;
+    const int sb = snow_batch > 1 ? b : 0;
+    float r[3], g3[3];
+    for (int c = 0; c < 3; ++c) r[c] = (og[(static_cast<long long>(b) * 3 + c) * HW + p] + 1.f) / 2.f;
+    const float gray = (0.299f * r[0] + 0.587f * r[1] + 0.114f * r[2]) * 1.5f + 0.5f;
+    for (int c = 0; c < 3; ++c) g3[c] = fmaxf(r[c], gray);
+    const int ih = static_cast<int>(t_hi[b]) + hi_off;
+    const int il = mode ? static_cast<int>(t_lo[b]) + lo_off : -1;
+    for (int c = 0; c < 3; ++c) {
+      const long long o = (static_cast<long long>(b) * 3 + c) * HW + p;
+      float res[2];
+      const int idx[2] = {ih, il};
+      for (int k = 0; k < 2; ++k) {
+        if (idx[k] < 0) { res[k] = og[o]; continue; }
+        const float bc = br[idx[k]];
+        const float base = fix_brightness ? r[c] : bc * r[c] + (1.f - bc) * g3[c];
+        const float* sl = snow + ((static_cast<long long>(idx[k]) * snow_batch + sb) * 3 + c) * HW;
+        const float sn = fminf(fmaxf(base + sl[p] + sl[pr], 0.f), 1.f);
+        res[k] = sn * 2.f - 1.f;
+      }
+      out[o] = mode ? xt[o] - res[0] + res[1] : res[0];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int cd_chanmix(const float* xt, const float* xsrc, float* out, const float* mats, const int64_t* t_hi,
+                          const int64_t* t_lo, int hi_off, int lo_off, int B, int C, int64_t HW, int mode, void* stream) {
+  CD_REQUIRE(C <= 8 && t_hi && (mode == 0 || (xt && t_lo)), "cd_chanmix: bad arguments");
+  const long long n = static_cast<long long>(B) * HW;
+  int blocks = cd_cdiv(n, 256 * 2); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  chanmix_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(xt, xsrc, out, mats, reinterpret_cast<const long long*>(t_hi),
+      reinterpret_cast<const long long*>(t_lo), hi_off, lo_off, B, C, HW, mode);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_snow(const float* xt, const float* og, float* out, const float* snow, const float* br_coef, const int64_t* t_hi,
+                       const int64_t* t_lo, int hi_off, int lo_off, int B, int H, int W, int snow_batch, int fix_brightness,
+                       int mode, void* stream) {
+  CD_REQUIRE(t_hi && (mode == 0 || (xt && t_lo)), "cd_snow: bad arguments");
+  const long long n = static_cast<long long>(B) * H * W;
+  int blocks = cd_cdiv(n, 256 * 2); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  snow_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(xt, og, out, snow, br_coef, reinterpret_cast<const long long*>(t_hi),
+      reinterpret_cast<const long long*>(t_lo), hi_off, lo_off, B, H, W, snow_batch, fix_brightness, mode);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

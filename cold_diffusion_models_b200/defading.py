@@ -64,7 +64,7 @@ class GaussianDiffusion(nn.Module):
         ry = torch.randint(0, self.image_size + 1, (batch,), device=device).long()
         return rx, ry
 
-    def _apply(self, x, idx, rx, ry, per_sample_t=None, quantize=False):
+    def _fade(self, x, idx, rx, ry, per_sample_t=None, quantize=False):
         x = x.contiguous().float()
         B, Cc, S, _ = x.shape
         out = torch.empty_like(x)
@@ -77,7 +77,7 @@ class GaussianDiffusion(nn.Module):
         with torch.no_grad():
             rx, ry = _offsets if _offsets is not None else self._offsets(x_start.size(0), x_start.device)
             t = t.to(device=x_start.device, dtype=torch.int64).contiguous()
-            return self._apply(x_start, -1, rx, ry, per_sample_t=t, quantize=self.discrete)
+            return self._fade(x_start, -1, rx, ry, per_sample_t=t, quantize=self.discrete)
 
     def p_losses(self, x_start, t):
         x_fade = self.q_sample(x_start=x_start, t=t)
@@ -101,7 +101,7 @@ class GaussianDiffusion(nn.Module):
         rx, ry = _offsets if _offsets is not None else self._offsets(batch_size, x.device)
         if t is None:
             t = self.num_timesteps
-        x = self._apply(x, t - 1, rx, ry, quantize=self.discrete)
+        x = self._fade(x, t - 1, rx, ry, quantize=self.discrete)
         xt = x
         direct_recons = None
         recon = None
@@ -113,7 +113,7 @@ class GaussianDiffusion(nn.Module):
             if direct_recons is None:
                 direct_recons = recon
             if self.sampling_routine == 'default':
-                x = self._apply(recon, t - 2, rx, ry)
+                x = self._fade(recon, t - 2, rx, ry)
             elif self.sampling_routine == 'x0_step_down':
                 out = torch.empty_like(x)
                 call('cd_mask_step_down', ptr(x.contiguous()), ptr(recon.contiguous()), ptr(out), ptr(self._masks_cum),

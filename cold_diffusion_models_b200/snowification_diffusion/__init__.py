@@ -1,0 +1,6 @@
+"""snowification/diffusion (== decolor-diffusion/diffusion) surface: GaussianDiffusion, Trainer, forward processes"""
+from ..snowification import GaussianDiffusion, DeColorization, Snow, ForwardProcessBase
+from ..trainer import Trainer
+from ..unet import Unet
+
+__all__ = ['GaussianDiffusion', 'Trainer', 'DeColorization', 'Snow', 'ForwardProcessBase', 'Unet']

@@ -221,6 +221,17 @@ int cd_mask_apply(const float* x, float* out, const float* masks, const int64_t*
                   const int64_t* rx, const int64_t* ry, int B, int C, int S, int MS, int quantize, void* stream);
 int cd_mask_step_down(const float* xt, const float* xhat, float* out, const float* masks, int idx_hi, int idx_lo,
                       const int64_t* rx, const int64_t* ry, int B, int C, int S, int MS, void* stream);
+/* Decolorization / Snow forward processes (snowification/diffusion/forward_process_impl.py "FP", diffusion.py "SN") with
+ * PER-SAMPLE step indices (masked stepping, SN:195-245; t_b = -1 rows untouched, SN:349-355).  index = t[b] + off, < 0 = identity.
+ *   mode 0: out = D(src, t_hi+hi_off)                       (q_sample SN:344-388 / degradation of the input SN:271-274)
+ *   mode 1: out = xt - D(src, t_hi+hi_off) + D(src, t_lo+lo_off)   (x0_step_down, SN:226-238)
+ * cd_chanmix: D = cumulative C x C channel mix mats[idx] (FP:150-163,189-195).  cd_snow: D(og, i) = clip(bright_i(og) + snow_i +
+ * rot180(snow_i), 0, 1)*2-1 with snow [T][snow_batch][3][H][W] (FP:361-372).                                                   */
+int cd_chanmix(const float* xt, const float* xsrc, float* out, const float* mats, const int64_t* t_hi,
+               const int64_t* t_lo, int hi_off, int lo_off, int B, int C, int64_t HW, int mode, void* stream);
+int cd_snow(const float* xt, const float* og, float* out, const float* snow, const float* br_coef, const int64_t* t_hi,
+            const int64_t* t_lo, int hi_off, int lo_off, int B, int H, int W, int snow_batch, int fix_brightness,
+            int mode, void* stream);
 /* stand-alone EMA (DB:73-81): mode 1 copy, 2 lerp */
 int cd_ema_update(float* ema, const float* p, int64_t n, float beta, int mode, void* stream);
 

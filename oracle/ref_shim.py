@@ -56,7 +56,7 @@ def install_stubs():
         tgm.image = img
         sys.modules["torchgeometry"] = tgm
         sys.modules["torchgeometry.image"] = img
-    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.image", "kornia", "kornia.color", "imageio", "pytorch_msssim",
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.image", "kornia", "kornia.color", "kornia.color.gray", "kornia.color.rgb", "kornia.color.xyz", "imageio", "pytorch_msssim", "sklearn", "sklearn.mixture", "lpips",
                  "cv2"):
         if name not in sys.modules:
             try:
@@ -65,15 +65,29 @@ def install_stubs():
                 m = types.ModuleType(name)
                 m.__path__ = []                      # lets `import pkg.sub` resolve to the stubbed sub-modules
                 sys.modules[name] = m
+                if name == 'kornia.color' or name == 'kornia':
+                    pass
                 if name == 'pytorch_msssim':
                     m.ssim = lambda *a, **k: None          # evaluation-only import of the reference (never called here)
                 if '.' in name:
                     setattr(sys.modules[name.split('.')[0]], name.split('.')[1], m)
 
 
+def _rgb_to_grayscale(image):
+    # kornia.color.gray.rgb_to_grayscale (un-pinned upstream): 0.299 R + 0.587 G + 0.114 B, keepdim channel
+    r, g, b = image[..., 0:1, :, :], image[..., 1:2, :, :], image[..., 2:3, :, :]
+    return 0.299 * r + 0.587 * g + 0.114 * b
+
+
 def import_reference(pkg_dir, module):
     """pkg_dir e.g. 'deblurring-diffusion-pytorch'; module e.g. 'deblurring_diffusion_pytorch'."""
     install_stubs()
+    if 'kornia.color.gray' in sys.modules and not hasattr(sys.modules['kornia.color.gray'], 'rgb_to_grayscale'):
+        sys.modules['kornia.color.gray'].rgb_to_grayscale = _rgb_to_grayscale
+        for modname, fns in (('kornia.color', ('rgb_to_lab', 'lab_to_rgb')), ('kornia.color.rgb', ('linear_rgb_to_rgb', 'rgb_to_linear_rgb')),
+                             ('kornia.color.xyz', ('rgb_to_xyz', 'xyz_to_rgb'))):
+            for fn in fns:
+                setattr(sys.modules[modname], fn, lambda *a, **k: None)   # Lab colour path (--to_lab) is never exercised
     p = os.path.join(REF_ROOT, pkg_dir)
     if not os.path.isdir(p):
         raise RuntimeError("reference not present at %s (only available in the build container)" % p)

@@ -177,6 +177,32 @@ def main():
         out['k:' + key] = gd.fade_kernels
     save('defading_small', x=xf, **out)
 
+    # ---- (7) snowification / decolor package (masked per-sample stepping) ----------------------------------
+    sn = ref_shim.import_reference('snowification', 'diffusion')
+    torch.manual_seed(41)
+    out = {}
+    xs2 = torch.rand(3, 3, 32, 32) * 2 - 1
+    for fpt, kw, T, samp in [('Decolorization', dict(decolor_routine='Linear', decolor_total_remove=True), 5, 'x0_step_down'),
+                             ('Decolorization', dict(decolor_routine='Constant', decolor_ema_factor=0.8, decolor_total_remove=False), 4, 'default'),
+                             ('Snow', dict(snow_level=1, results_folder='/tmp'), 4, 'x0_step_down'),
+                             ('Snow', dict(snow_level=3, fix_brightness=True, results_folder='/tmp'), 3, 'default')]:
+        gd = quiet(sn.GaussianDiffusion, unet, image_size=(32, 32) if fpt == 'Snow' else 32, device_of_kernel='cpu', channels=3,
+                   timesteps=T, loss_type='l1', forward_process_type=fpt, train_routine='Final', sampling_routine=samp, **kw)
+        key = '%s|%s|%d|%s' % (fpt, '-'.join('%s=%s' % (k, v) for k, v in sorted(kw.items()) if k != 'results_folder'), T, samp)
+        tt = torch.tensor([T - 1, -1, 1])
+        out['q:' + key] = gd.q_sample(xs2, tt)
+        with torch.no_grad():
+            out['loss:' + key] = gd.p_losses(xs2, torch.tensor([T - 1, 0, 1]))
+        tmix = torch.tensor([T - 1, 1, 2])
+        x1, d1 = quiet(gd.sample_one_step, xs2, tmix)
+        out['one_x:' + key], out['one_dr:' + key] = x1, d1
+        r = quiet(gd.sample, batch_size=3, img=xs2)
+        out['xt:' + key], out['dr:' + key], out['img:' + key] = r['xt'], r['direct_recons'], r['recon']
+        if fpt == 'Snow':
+            out['snow:' + key] = torch.stack(gd.forward_process.snow)
+            out['br:' + key] = torch.tensor(gd.forward_process.br_coef_list)
+    save('snow_small', x=xs2, **out)
+
 
 if __name__ == '__main__':
     main()

@@ -150,6 +150,42 @@ def test_defading_oracle_matches_reference():
         assert rel(xt, g['xt:' + key]) < tol and rel(dr, g['dr:' + key]) < tol and rel(img, g['img:' + key]) < max(tol, 1e-4), key
 
 
+def _snow_cfg(key):
+    fpt, kws, T, samp = key.split('|')
+    kw = {}
+    for item in kws.split('-'):
+        k, v = item.split('=')
+        kw[k] = (v == 'True') if v in ('True', 'False') else (float(v) if '.' in v else (int(v) if v.isdigit() else v))
+    return fpt, kw, int(T), samp
+
+
+def test_snow_decolor_oracle_and_host_tables_match_reference():
+    import snow_oracle as SO
+    from cold_diffusion_models_b200.snowification import DeColorization, Snow
+    g = load('snow_small')
+    u = load('unet_small')
+    sd = {k[3:]: v for k, v in u.items() if k.startswith('sd:')}
+    fn = lambda x, t: UO.unet_forward(sd, x, t)
+    for key in _cases('img:', g):
+        fpt, kw, T, samp = _snow_cfg(key)
+        if fpt == 'Decolorization':
+            host = DeColorization(num_timesteps=T, **kw)
+            fp = SO.DecolorFP(host.factors)
+        else:
+            host = Snow(image_size=(32, 32), num_timesteps=T, snow_level=kw.get('snow_level', 1), fix_brightness=kw.get('fix_brightness', False))
+            assert torch.allclose(host.snow_t, g['snow:' + key], atol=1e-6), key     # host snow-layer generator == reference layers
+            assert torch.allclose(host.br_t, g['br:' + key], atol=1e-7)
+            fp = SO.SnowFP(host.snow_t, host.br_coef_list, fix_brightness=host.fix_brightness)
+        o = SO.SnowOracle(fn, fp, timesteps=T, sampling_routine=samp)
+        assert torch.allclose(o.q_sample(g['x'], torch.tensor([T - 1, -1, 1])), g['q:' + key], atol=2e-6), key
+        with torch.no_grad():
+            assert abs(o.p_losses(g['x'], torch.tensor([T - 1, 0, 1])).item() - g['loss:' + key].item()) < 1e-5
+        x1, d1 = o.sample_one_step(g['x'], torch.tensor([T - 1, 1, 2]))
+        assert rel(x1, g['one_x:' + key]) < 1e-5 and rel(d1, g['one_dr:' + key]) < 1e-5, key
+        r = o.sample(3, g['x'])
+        assert rel(r['xt'], g['xt:' + key]) < 1e-6 and rel(r['direct_recons'], g['dr:' + key]) < 1e-5 and rel(r['recon'], g['img:' + key]) < 1e-4, key
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference only in build container')
 def test_oracle_matches_live_reference_config1_mnist():
     """BASELINE config 1: MNIST-shaped 1x32x32, T=20, k=11, sigma=7, Constant, B=4, full-size Unet."""

@@ -170,3 +170,28 @@ def test_defading_package_matches_reference_golden(small):
         xt, dr, img = gd.sample(batch_size=2, faded_recon_sample=x, _offsets=off)
         tol = 1e-2 if int(disc) else 2e-3
         assert rel(xt, g['xt:' + key]) < (tol if int(disc) else 1e-5) and rel(dr, g['dr:' + key]) < tol and rel(img, g['img:' + key]) < tol, key
+
+
+def test_snowification_package_matches_reference_golden(small):
+    """snowification / decolor drop-in: per-sample masked stepping folded into per-sample operator indices."""
+    from cold_diffusion_models_b200.snowification_diffusion import GaussianDiffusion
+    g = load('snow_small')
+    _, sd, u = small
+    x = g['x'].cuda()
+    for key in sorted(k[4:] for k in g if k.startswith('img:')):
+        fpt, kws, T, samp = key.split('|')
+        T = int(T)
+        kw = {}
+        for item in kws.split('-'):
+            k, v = item.split('=')
+            kw[k] = (v == 'True') if v in ('True', 'False') else (float(v) if '.' in v else (int(v) if v.isdigit() else v))
+        gd = GaussianDiffusion(u, image_size=(32, 32) if fpt == 'Snow' else 32, device_of_kernel='cuda', channels=3, timesteps=T,
+                               loss_type='l1', forward_process_type=fpt, train_routine='Final', sampling_routine=samp, **kw).cuda()
+        q = gd.q_sample(x, torch.tensor([T - 1, -1, 1]).cuda())
+        assert torch.allclose(q.cpu(), g['q:' + key], atol=3e-6), key
+        with torch.no_grad():
+            assert abs(gd.p_losses(x, torch.tensor([T - 1, 0, 1]).cuda()).item() - g['loss:' + key].item()) < 3e-4, key
+        x1, d1 = gd.sample_one_step(x, torch.tensor([T - 1, 1, 2]).cuda())
+        assert rel(d1, g['one_dr:' + key]) < 1e-3 and rel(x1, g['one_x:' + key]) < 2e-3, key
+        r = gd.sample(batch_size=3, img=x)
+        assert rel(r['xt'], g['xt:' + key]) < 1e-5 and rel(r['direct_recons'], g['dr:' + key]) < 1e-3 and rel(r['recon'], g['img:' + key]) < 3e-3, key
