@@ -96,49 +96,69 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __res
 // y+ky-3, so every pixel costs two conflict-free LDS and 7 FMAs.
 // ---------------------------------------------------------------------------------------------
 constexpr int kDwSeg = 4;                        // x segments per tile row: 7 ky x 4 segments = 28 warps per block
+constexpr int kDwTilesPerBlock = 8;              // consecutive tiles reduced in registers before touching global memory
 __global__ void __launch_bounds__(224 * kDwSeg)
 dwconv7_wgrad_kernel(const float* __restrict__ dh, int dh_ld, const float* __restrict__ x, int x_ld,
                      int B, int H, int W, int C, float* __restrict__ dw, int TY, int TX) {
   extern __shared__ float sm[];                  // xs[(TY+6)][(TX+6)][32] | ds[TY][TX][32]
+  __shared__ float red[49][32];
   const int XW = TX + 6;
   float* xs = sm;
   float* ds = sm + (TY + 6) * XW * 32;
   const int lane = threadIdx.x & 31, ky = (threadIdx.x >> 5) % 7, seg = (threadIdx.x >> 5) / 7;
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int c0 = blockIdx.x * 32;
   const int tiles_x = W / TX, tiles_y = H / TY;
-  const int tx = blockIdx.y % tiles_x, ty = (blockIdx.y / tiles_x) % tiles_y, b = blockIdx.y / (tiles_x * tiles_y);
-  const int x0 = tx * TX, y0 = ty * TY;
+  const int ntiles = B * tiles_x * tiles_y;
   const bool cvalid = c0 + lane < C;
-  for (int i = threadIdx.x; i < (TY + 6) * XW * 32; i += blockDim.x) {
-    const int cc = i & 31, px = (i >> 5) % XW, ry = (i >> 5) / XW;
-    const int iy = y0 + ry - 3, ix = x0 + px - 3;
-    float v = 0.f;
-    if (c0 + cc < C && iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<long long>(b) * H + iy) * W + ix) * x_ld + c0 + cc];
-    xs[i] = v;
-  }
-  for (int i = threadIdx.x; i < TY * TX * 32; i += blockDim.x) {
-    const int cc = i & 31, px = (i >> 5) % TX, ry = (i >> 5) / TX;
-    ds[i] = (c0 + cc < C) ? dh[((static_cast<long long>(b) * H + y0 + ry) * W + x0 + px) * dh_ld + c0 + cc] : 0.f;
-  }
-  __syncthreads();
-  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int TS = TX / kDwSeg, px0 = seg * TS;       // this warp's pixel columns [px0, px0 + TS)
-  for (int ry = 0; ry < TY; ++ry) {
-    const float* xr = xs + ((ry + ky) * XW + px0) * 32 + lane;  // input row y0+ry+ky-3, starting at x0+px0-3
-    const float* dr = ds + (ry * TX + px0) * 32 + lane;
-    float w0 = xr[0], w1 = xr[32], w2 = xr[64], w3 = xr[96], w4 = xr[128], w5 = xr[160], w6;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int tile = blockIdx.y * kDwTilesPerBlock; tile < min(ntiles, (static_cast<int>(blockIdx.y) + 1) * kDwTilesPerBlock); ++tile) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int x0 = tx * TX, y0 = ty * TY;
+    __syncthreads();                                // previous tile fully consumed
+    // staging: one warp per tile row (lane = channel, 128-byte coalesced LDGSTS), whole tile in flight before the wait
+    for (int ry = wid; ry < TY + 6; ry += nw) {
+      const int iy = y0 + ry - 3;
+      const bool rowok = cvalid && iy >= 0 && iy < H;
+      const float* src = x + ((static_cast<long long>(b) * H + (rowok ? iy : 0)) * W) * x_ld + c0 + (cvalid ? lane : 0);
+      float* dst = xs + (ry * XW) * 32 + lane;
+      for (int px = 0; px < XW; ++px) {
+        const int ix = x0 + px - 3;
+        const bool ok = rowok && ix >= 0 && ix < W;
+        cd_cp_async4(dst + px * 32, src + static_cast<long long>(ok ? ix : 0) * x_ld, ok);
+      }
+    }
+    for (int ry = wid; ry < TY; ry += nw) {
+      const float* src = dh + ((static_cast<long long>(b) * H + y0 + ry) * W + x0) * dh_ld + c0 + (cvalid ? lane : 0);
+      float* dst = ds + (ry * TX) * 32 + lane;
+      for (int px = 0; px < TX; ++px) cd_cp_async4(dst + px * 32, src + static_cast<long long>(px) * dh_ld, cvalid);
+    }
+    cd_cp_async_wait_all();
+    __syncthreads();
+    for (int ry = 0; ry < TY; ++ry) {
+      const float* xr = xs + ((ry + ky) * XW + px0) * 32 + lane;  // input row y0+ry+ky-3, starting at x0+px0-3
+      const float* dr = ds + (ry * TX + px0) * 32 + lane;
+      float w0 = xr[0], w1 = xr[32], w2 = xr[64], w3 = xr[96], w4 = xr[128], w5 = xr[160], w6;
 #pragma unroll 4
-    for (int px = 0; px < TS; ++px) {
-      w6 = xr[(px + 6) * 32];
-      const float d = dr[px * 32];
-      acc[0] = fmaf(d, w0, acc[0]); acc[1] = fmaf(d, w1, acc[1]); acc[2] = fmaf(d, w2, acc[2]); acc[3] = fmaf(d, w3, acc[3]);
-      acc[4] = fmaf(d, w4, acc[4]); acc[5] = fmaf(d, w5, acc[5]); acc[6] = fmaf(d, w6, acc[6]);
-      w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+      for (int px = 0; px < TS; ++px) {
+        w6 = xr[(px + 6) * 32];
+        const float d = dr[px * 32];
+        acc[0] = fmaf(d, w0, acc[0]); acc[1] = fmaf(d, w1, acc[1]); acc[2] = fmaf(d, w2, acc[2]); acc[3] = fmaf(d, w3, acc[3]);
+        acc[4] = fmaf(d, w4, acc[4]); acc[5] = fmaf(d, w5, acc[5]); acc[6] = fmaf(d, w6, acc[6]);
+        w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+      }
     }
   }
-  if (cvalid) {
+  // block reduction over the x segments, then ONE atomic per (channel, tap) per block
+  for (int i = threadIdx.x; i < 49 * 32; i += blockDim.x) red[i / 32][i % 32] = 0.f;
+  __syncthreads();
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) atomicAdd(dw + (c0 + lane) * 49 + ky * 7 + kx, acc[kx]);
+  for (int kx = 0; kx < 7; ++kx) atomicAdd(&red[ky * 7 + kx][lane], acc[kx]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 49 * 32; i += blockDim.x) {
+    const int tap = i / 32, cl = i % 32;
+    if (c0 + cl < C) atomicAdd(dw + (c0 + cl) * 49 + tap, red[tap][cl]);
   }
 }
 
@@ -386,19 +406,19 @@ extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int 
 
 extern "C" int cd_dwconv7_wgrad(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C,
                                 float* dw, void* stream) {
-  // tile: TX = min(W, 64); TY as large as fits ~190 KB of shared memory (both divide the image)
-  int TX = W < 64 ? W : 64;
+  // tile: TX = min(W, 32), TY <= 8 so that two blocks (2 x 28 warps) fit one SM (~100 KB of shared memory each)
+  int TX = W < 32 ? W : 32;
   while (W % TX) --TX;
   CD_REQUIRE(TX % kDwSeg == 0, "cd_dwconv7_wgrad: image width %d unsupported", W);
-  int TY = H < 16 ? H : 16;
+  int TY = H < 8 ? H : 8;
   while (H % TY) --TY;
   auto bytes = [&](int ty) { return sizeof(float) * 32 * (size_t(ty + 6) * (TX + 6) + size_t(ty) * TX); };
-  while (TY > 1 && bytes(TY) > 190 * 1024) { --TY; while (H % TY) --TY; }
+  while (TY > 1 && bytes(TY) > 110 * 1024) { --TY; while (H % TY) --TY; }
   const size_t smem = bytes(TY);
   CD_REQUIRE(smem <= 200 * 1024, "cd_dwconv7_wgrad: tile does not fit (W=%d)", W);
   static size_t attr = 0;
   if (smem > attr) { CD_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  dim3 grid(cd_cdiv(C, 32), B * (H / TY) * (W / TX));
+  dim3 grid(cd_cdiv(C, 32), cd_cdiv(B * (H / TY) * (W / TX), kDwTilesPerBlock));
   dwconv7_wgrad_kernel<<<grid, 224 * kDwSeg, smem, static_cast<cudaStream_t>(stream)>>>(dh, dh_ld, x, x_ld, B, H, W, C, dw, TY, TX);
   CD_LAUNCH_CHECK();
   return 0;

@@ -39,6 +39,13 @@ __device__ __forceinline__ float cd_round_tf32(float x) {     // RN (ties away),
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// asynchronous 4-byte global->shared copy (LDGSTS); !valid zero-fills the destination (src-size 0)
+__device__ __forceinline__ void cd_cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cd_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float cd_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

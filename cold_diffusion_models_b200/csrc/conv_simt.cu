@@ -261,10 +261,15 @@ wgrad_smallc_kernel(const WgradParams p) {
     __syncthreads();
     if (co < p.Cout) {
       const int np = static_cast<int>(pend - q0 < 64 ? pend - q0 : 64);
-      for (int pp = 0; pp < np; ++pp) {
-        const float d = p.dout[opix_s[pp] * p.dout_ld + co];
+      for (int pp0 = 0; pp0 < np; pp0 += 8) {          // 8 independent dout loads in flight per thread
+        float d[8];
 #pragma unroll
-        for (int k = 0; k < kSmallK; ++k) if (k < K) acc[k] = fmaf(d, patch[pp][k], acc[k]);
+        for (int u = 0; u < 8; ++u) d[u] = (pp0 + u < np) ? p.dout[opix_s[pp0 + u] * p.dout_ld + co] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int k = 0; k < kSmallK; ++k) if (k < K) acc[k] = fmaf(d[u], patch[(pp0 + u) & 63][k], acc[k]);
+        }
       }
     }
   }
@@ -292,6 +297,63 @@ __global__ void colsum_kernel(const float* x, int ld, long long rows, int C, flo
     for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
     atomicAdd(out + c, t);
   }
+}
+
+// vectorised column sums (C % 4 == 0): a warp covers 32/G rows x G float4 channel-quads (G = min(32, C/4) rounded up to a
+// power of two), four independent 16-byte loads in flight per thread; partial sums meet in shared memory.
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const float* __restrict__ x, int ld, long long rows, int C, float* __restrict__ out, long long rows_per_block, int G) {
+  extern __shared__ float red[];                 // [C]
+  const int nq = C >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int rpw = 32 / G;                        // rows per warp pass
+  const int gl = lane % G, sub = lane / G;
+  const int qd = blockIdx.x * G + gl;            // channel quad handled by this lane
+  const long long r0 = blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block; if (r1 > rows) r1 = rows;
+  float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+  const long long stride = static_cast<long long>(nwarp) * rpw;
+  if (qd < nq) {
+    long long r = r0 + static_cast<long long>(warp) * rpw + sub;
+    for (; r + 3 * stride < r1; r += 4 * stride) {
+      const float4 v0 = *reinterpret_cast<const float4*>(x + r * ld + qd * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(x + (r + stride) * ld + qd * 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(x + (r + 2 * stride) * ld + qd * 4);
+      const float4 v3 = *reinterpret_cast<const float4*>(x + (r + 3 * stride) * ld + qd * 4);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;  a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;  a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; r < r1; r += stride) {
+      const float4 v0 = *reinterpret_cast<const float4*>(x + r * ld + qd * 4);
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+  }
+  a0.x += a1.x + a2.x + a3.x; a0.y += a1.y + a2.y + a3.y; a0.z += a1.z + a2.z + a3.z; a0.w += a1.w + a2.w + a3.w;
+  for (int i = threadIdx.x; i < G * 4; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  if (qd < nq) {
+    atomicAdd(&red[gl * 4 + 0], a0.x); atomicAdd(&red[gl * 4 + 1], a0.y); atomicAdd(&red[gl * 4 + 2], a0.z); atomicAdd(&red[gl * 4 + 3], a0.w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * 4; i += blockDim.x) {
+    const int c = blockIdx.x * G * 4 + i;
+    if (c < C) atomicAdd(out + c, red[i]);
+  }
+}
+
+static int launch_colsum(const float* x, int ld, long long rows, int C, float* out, cudaStream_t st) {
+  if (C % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && rows >= 64) {
+    const int nq = C / 4;
+    int G = 1; while (G < nq && G < 32) G <<= 1;
+    long long rpb = 1024;
+    dim3 g2(cd_cdiv(nq, G), cd_cdiv(rows, rpb));
+    colsum_vec_kernel<<<g2, 256, sizeof(float) * G * 4, st>>>(x, ld, rows, C, out, rpb, G);
+  } else {
+    const long long rpb = 4096;
+    dim3 g2(cd_cdiv(C, 32), cd_cdiv(rows, rpb));
+    colsum_kernel<<<g2, 256, 0, st>>>(x, ld, rows, C, out, rpb);
+  }
+  return 0;
 }
 
 // weight repack kernels -----------------------------------------------------------------------
@@ -398,7 +460,7 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0; p.dw = dw;
   const long long total = static_cast<long long>(d->B) * d->Hg * d->Wg;
   if (c.C <= 4 && c.ntaps * c.C <= kSmallK && !c.w_per_batch) {
-    int splits = cd_cdiv(total, 2048); if (splits > 148 * 4) splits = 148 * 4; if (splits < 1) splits = 1;
+    int splits = cd_cdiv(total, 512); if (splits > 148 * 16) splits = 148 * 16; if (splits < 1) splits = 1;
     p.pix_per_split = cd_cdiv(total, splits);
     dim3 grid(cd_cdiv(total, p.pix_per_split), cd_cdiv(d->Cout, 128));
     wgrad_smallc_kernel<<<grid, 128, 0, st>>>(p);
@@ -429,18 +491,14 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   if (db) {
     const long long rows = static_cast<long long>(d->B) * d->Ho * d->Wo;
     CD_REQUIRE(d->oys == 1 && d->oxs == 1, "cd_conv_wgrad: bias gradient needs a dense output grid");
-    const long long rpb = 4096;
-    dim3 g2(cd_cdiv(d->Cout, 32), cd_cdiv(rows, rpb));
-    colsum_kernel<<<g2, 256, 0, st>>>(dout, dout_ld, rows, d->Cout, db, rpb);
+    launch_colsum(dout, dout_ld, rows, d->Cout, db, st);
     CD_LAUNCH_CHECK();
   }
   return 0;
 }
 
 extern "C" int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* stream) {
-  const long long rpb = 4096;
-  dim3 g2(cd_cdiv(C, 32), cd_cdiv(rows, rpb));
-  colsum_kernel<<<g2, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, C, out, rpb);
+  launch_colsum(x, ld, rows, C, out, static_cast<cudaStream_t>(stream));
   CD_LAUNCH_CHECK();
   return 0;
 }

@@ -373,6 +373,11 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   CD_REQUIRE(p.TW * d->sx <= 256 && p.TH * d->sy <= 256, "conv_tc: strided box too large");
   p.tiles_x = d->Wg / p.TW; p.tiles_y = d->Hg / p.TH; p.tiles_n = cd_cdiv(d->B, p.TN);
   int BN = (d->Cout % 256 == 0) ? 256 : (d->Cout > 64 ? 128 : 64);
+  // small spatial sizes (16^2, 32^2) give few M tiles: prefer a narrower N tile while that still fills the 148 SMs better
+  {
+    const long long mt = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
+    if (BN == 256 && mt * (d->Cout / 256) < g_num_sms && d->Cout % 128 == 0) BN = 128;
+  }
   p.tiles_co = cd_cdiv(d->Cout, BN);
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_co;
   p.out = d->out; p.out_ld = d->out_ld; p.Ho = d->Ho; p.Wo = d->Wo;

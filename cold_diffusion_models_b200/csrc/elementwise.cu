@@ -147,6 +147,69 @@ dwconv7_ln_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// depthwise 7x7 (+bias +cond +addend), shared-memory tiled: block = 32-channel slab x (TY x TX) pixel tile whose input
+// (with the 3-pixel halo) is staged once; warp = output row, lane = channel.  A thread walks the input columns of its
+// row band: each new column (7 LDS) feeds the 7 output pixels in flight (49 FMA); finished pixels leave through a
+// 7-deep accumulator shift -- no re-reads, stores are 128-byte coalesced.  FMA-bound (49 FMA / pixel / channel).
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwTY = 8;
+__global__ void __launch_bounds__(32 * kDwTY)
+dwconv7_tile_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C,
+                    const float* __restrict__ wdw, const float* __restrict__ bdw, const float* __restrict__ cond, int cond_ld,
+                    float* __restrict__ out, int out_ld, int flip, const float* __restrict__ addend, int addend_ld, int TX, int TY) {
+  extern __shared__ float xs[];                  // [(TY+6)][(TX+6)][32]
+  const int XW = TX + 6;
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, c = c0 + lane;
+  const bool cvalid = c < C;
+  const int tiles_x = W / TX, tiles_y = H / TY;
+  const int tx = blockIdx.y % tiles_x, ty = (blockIdx.y / tiles_x) % tiles_y, b = blockIdx.y / (tiles_x * tiles_y);
+  const int x0 = tx * TX, y0 = ty * TY;
+  for (int r = ry; r < TY + 6; r += kDwTY) {
+    const int iy = y0 + r - 3;
+    const bool rowok = cvalid && iy >= 0 && iy < H;
+    const float* src = x + ((static_cast<long long>(b) * H + (rowok ? iy : 0)) * W) * x_ld + (cvalid ? c : 0);
+    float* dst = xs + (r * XW) * 32 + lane;
+    for (int px = 0; px < XW; ++px) {                       // LDGSTS: all copies of the tile are in flight together
+      const int ix = x0 + px - 3;
+      const bool ok = rowok && ix >= 0 && ix < W;
+      cd_cp_async4(dst + px * 32, src + static_cast<long long>(ok ? ix : 0) * x_ld, ok);
+    }
+  }
+  float w[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) w[k] = cvalid ? __ldg(wdw + c * 49 + (flip ? 48 - k : k)) : 0.f;
+  float add = (cvalid && bdw) ? bdw[c] : 0.f;
+  if (cvalid && cond) add += cond[static_cast<long long>(b) * cond_ld + c];
+  cd_cp_async_wait_all();
+  __syncthreads();
+  if (ry >= TY) return;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* band = xs + (ry * XW) * 32 + lane;          // rows ry .. ry+6 of the staged tile = input rows y-3 .. y+3
+  const long long orow = (static_cast<long long>(b) * H + y0 + ry) * W + x0;
+  for (int cx = 0; cx < XW; ++cx) {                          // staged column cx = input x0 + cx - 3
+    float col[7];
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) col[ky] = band[(ky * XW + cx) * 32];
+    // slot o holds output pixel (x0 + cx - o); this column is its kx = o tap
+#pragma unroll
+    for (int o = 0; o < 7; ++o) {
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) acc[o] = fmaf(w[ky * 7 + o], col[ky], acc[o]);
+    }
+    const int px = cx - 6;                                   // output pixel completed by this column (tile-local)
+    if (px >= 0 && cvalid) {
+      float v = acc[6] + add;
+      if (addend) v += addend[(orow + px) * addend_ld + c];
+      out[(orow + px) * out_ld + c] = v;
+    }
+#pragma unroll
+    for (int o = 6; o > 0; --o) acc[o] = acc[o - 1];
+    acc[0] = 0.f;
+  }
+}
+
 // generic (any C, e.g. the 1/3-channel image): one thread per pixel, loops channels; LN optional.
 __global__ void dwconv7_small_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C,
                                      const float* __restrict__ wdw, const float* __restrict__ bdw,
@@ -189,38 +252,45 @@ __global__ void dwconv7_small_kernel(const float* __restrict__ x, int x_ld, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// channel LayerNorm: one warp per pixel, channels held in registers (C <= 1024, C % 4 == 0)
+// channel LayerNorm: lanes are split into groups of G = min(32, C/4) (power of two); each group owns one pixel,
+// each lane NQ float4 slots (C <= 1024, C % 4 == 0).  In place (y == x) is allowed.
 // ---------------------------------------------------------------------------------------------
+template <int NQ>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int x_ld, long long npix, int C, const float* __restrict__ g,
                  const float* __restrict__ beta, float eps, float* __restrict__ y, int y_ld,
                  float* __restrict__ stats, int round_tf32) {
-  const long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= npix) return;
   const int lane = threadIdx.x & 31;
   const int nq = C >> 2;
-  float4 v[8];
+  const int G = nq < 32 ? nq : 32;
+  const int ppw = 32 / G, sub = lane / G, gl = lane % G;
+  const long long pix = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ppw + sub;
+  const bool valid = pix < npix;
+  float4 v[NQ];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int qd = lane + i * 32;
-    if (qd < nq) { v[i] = *reinterpret_cast<const float4*>(x + pix * x_ld + qd * 4); s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  for (int i = 0; i < NQ; ++i) {
+    const int qd = gl + i * G;
+    v[i] = make_float4(0, 0, 0, 0);
+    if (valid && qd < nq) { v[i] = *reinterpret_cast<const float4*>(x + pix * x_ld + qd * 4); s += v[i].x + v[i].y + v[i].z + v[i].w; }
   }
-  const float mean = cd_warp_sum(s) / C;
+  for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
   float s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int qd = lane + i * 32;
-    if (qd < nq) {
+  for (int i = 0; i < NQ; ++i) {
+    const int qd = gl + i * G;
+    if (valid && qd < nq) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       s2 += a * a + b * b + c * c + d * d;
     }
   }
-  const float rstd = rsqrtf(cd_warp_sum(s2) / C + eps);
+  for (int o = G >> 1; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const float rstd = rsqrtf(s2 / C + eps);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int qd = lane + i * 32;
-    if (qd < nq) {
+  for (int i = 0; i < NQ; ++i) {
+    const int qd = gl + i * G;
+    if (valid && qd < nq) {
       const float4 gv = *reinterpret_cast<const float4*>(g + qd * 4);
       const float4 bv = *reinterpret_cast<const float4*>(beta + qd * 4);
       float4 o;
@@ -230,7 +300,7 @@ layernorm_kernel(const float* __restrict__ x, int x_ld, long long npix, int C, c
       *reinterpret_cast<float4*>(y + pix * y_ld + qd * 4) = o;
     }
   }
-  if (stats && lane == 0) { stats[pix * 2] = mean; stats[pix * 2 + 1] = rstd; }
+  if (stats && valid && gl == 0) { stats[pix * 2] = mean; stats[pix * 2 + 1] = rstd; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -425,7 +495,30 @@ extern "C" int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, 
 extern "C" int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
                                 float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream) {
   CD_REQUIRE(C % 4 == 0 && C <= 1024 && x_ld % 4 == 0 && y_ld % 4 == 0, "cd_layernorm_fwd: unsupported C=%d", C);
-  layernorm_kernel<<<cd_cdiv(npix, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_ld, npix, C, g, beta, eps, y, y_ld, stats, round_tf32);
+  const int nq = C / 4;
+  CD_REQUIRE((nq & (nq - 1)) == 0 || nq >= 32, "cd_layernorm_fwd: C/4 must be a power of two below 128 channels (C=%d)", C);
+  const int G = nq < 32 ? nq : 32, ppw = 32 / G, slots = nq <= 32 ? 1 : cd_cdiv(nq, 32);
+  const int blocks = cd_cdiv(npix, 8 * ppw);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CD_LNF(N) layernorm_kernel<N><<<blocks, 256, 0, st>>>(x, x_ld, npix, C, g, beta, eps, y, y_ld, stats, round_tf32)
+  if (slots == 1) CD_LNF(1); else if (slots == 2) CD_LNF(2); else if (slots <= 4) CD_LNF(4); else CD_LNF(8);
+#undef CD_LNF
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_dwconv7_fwd(const float* x, int x_ld, int B, int H, int W, int C, const float* w_dw, const float* b_dw,
+                              const float* cond, int cond_ld, float* out, int out_ld, int flip, const float* addend,
+                              int addend_ld, void* stream) {
+  int TX = W < 32 ? W : 32;
+  int TY = H < kDwTY ? H : kDwTY;
+  CD_REQUIRE(W % TX == 0 && H % TY == 0, "cd_dwconv7_fwd: unsupported image size %dx%d", H, W);
+  const size_t smem = sizeof(float) * 32 * size_t(TY + 6) * (TX + 6);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) { CD_CUDA(cudaFuncSetAttribute(dwconv7_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  dim3 grid(cd_cdiv(C, 32), B * (H / TY) * (W / TX));
+  dwconv7_tile_kernel<<<grid, 32 * kDwTY, smem, static_cast<cudaStream_t>(stream)>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld,
+                                                                                  out, out_ld, flip, addend, addend_ld, TX, TY);
   CD_LAUNCH_CHECK();
   return 0;
 }

@@ -293,7 +293,7 @@ int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float*
   const int max_taps = p.ntaps[0], max_loads = p.nloads[0];
   if (max_taps * BN > 512) return 1;
   // ---- pixel chunking: KR K-rows per stage ----
-  int KR = (max_loads <= 1) ? 64 : 32;
+  int KR = (max_loads <= 1) ? 64 : 32;           // (KR = 32 everywhere measured 25 % slower: r01 bench_8)
   if (static_cast<long long>(d->Hg) * d->Wg < KR) KR = d->Hg * d->Wg;
   if (KR < 8) return 1;
   p.CW = d->Wg < KR ? d->Wg : KR;

@@ -191,9 +191,19 @@ class UnetEngine(_BackwardHolder):
             cond = C.c_void_p(cond_all.data_ptr() + 4 * bs.cond_off)
         g = m.net[0].g if bs.has_norm else None
         be = m.net[0].b if bs.has_norm else None
-        call('cd_dwconv7_ln_fwd', C.c_void_p(xv.addr()), xv.ld, B, H, W, bs.din, ptr(m.ds_conv.weight), ptr(m.ds_conv.bias),
-             cond if cond is not None else C.c_void_p(0), self.sumC, ptr(g), ptr(be), C.c_float(1e-5), ptr(hn), ld_in,
-             ptr(stats), ptr(hpre), ld_in, 0, 0, C.c_void_p(0), 0, stream())
+        condp = cond if cond is not None else C.c_void_p(0)
+        if bs.din % 32 == 0:
+            # tiled depthwise conv -> h ; channel LayerNorm as its own HBM pass (training keeps h for the backward anyway)
+            h = hpre if (hpre is not None) else hn
+            call('cd_dwconv7_fwd', C.c_void_p(xv.addr()), xv.ld, B, H, W, bs.din, ptr(m.ds_conv.weight), ptr(m.ds_conv.bias),
+                 condp, self.sumC, ptr(h), ld_in, 0, C.c_void_p(0), 0, stream())
+            if bs.has_norm:
+                call('cd_layernorm_fwd', ptr(h), ld_in, C.c_int64(B * H * W), bs.din, ptr(g), ptr(be), C.c_float(1e-5),
+                     ptr(hn), ld_in, ptr(stats), 0, stream())
+        else:
+            call('cd_dwconv7_ln_fwd', C.c_void_p(xv.addr()), xv.ld, B, H, W, bs.din, ptr(m.ds_conv.weight), ptr(m.ds_conv.bias),
+                 condp, self.sumC, ptr(g), ptr(be), C.c_float(1e-5), ptr(hn), ld_in,
+                 ptr(stats), ptr(hpre), ld_in, 0, 0, C.c_void_p(0), 0, stream())
         hv = View(hn, 0, bs.din)
         u = self.buf('u.' + uniq, (B, H, W, bs.dmid))
         pre = self.buf('pre.' + bs.name, (B, H, W, bs.dmid)) if save is not None else None

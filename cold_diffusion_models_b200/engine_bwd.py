@@ -178,8 +178,12 @@ class BackwardMixin:
         else:
             addv = dyv
         dx = self.buf('g.x.' + pn, (B, H, W, ld_in))
-        call('cd_dwconv7_ln_fwd', ptr(dh), ld_in, B, H, W, bs.din, ptr(m.ds_conv.weight), NULL, NULL, 0, NULL, NULL,
-             C.c_float(0.0), ptr(dx), ld_in, NULL, NULL, 0, 0, 1, C.c_void_p(addv.addr()), addv.ld, stream())
+        if bs.din % 32 == 0:
+            call('cd_dwconv7_fwd', ptr(dh), ld_in, B, H, W, bs.din, ptr(m.ds_conv.weight), NULL, NULL, 0, ptr(dx), ld_in, 1,
+                 C.c_void_p(addv.addr()), addv.ld, stream())
+        else:
+            call('cd_dwconv7_ln_fwd', ptr(dh), ld_in, B, H, W, bs.din, ptr(m.ds_conv.weight), NULL, NULL, 0, NULL, NULL,
+                 C.c_float(0.0), ptr(dx), ld_in, NULL, NULL, 0, 0, 1, C.c_void_p(addv.addr()), addv.ld, stream())
         return View(dx, 0, bs.din)
 
     def _attn_bwd(self, spec, save, dyv):

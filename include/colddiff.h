@@ -117,7 +117,12 @@ int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, int C,
                       int round_tf32, int flip /*1: rotate the 7x7 kernel by 180 deg (data-gradient)*/,
                       const float* addend, int addend_ld /*optional NHWC tensor added to h*/, void* stream);
 
-/* channel LayerNorm alone (PreNorm in front of LinearAttention, DB:123-131) */
+/* depthwise 7x7 + bias + cond (+addend) without the norm, shared-memory tiled (the production path for C >= 32; the
+ * LayerNorm then runs as cd_layernorm_fwd on its output, which training keeps anyway as `hpre`).  flip=1: data-gradient. */
+int cd_dwconv7_fwd(const float* x, int x_ld, int B, int H, int W, int C, const float* w_dw, const float* b_dw,
+                   const float* cond, int cond_ld, float* out, int out_ld, int flip, const float* addend,
+                   int addend_ld, void* stream);
+/* channel LayerNorm alone (PreNorm in front of LinearAttention, DB:123-131; also the ConvNextBlock norm) */
 int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
                      float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream);
 
