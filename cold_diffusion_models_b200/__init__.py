@@ -6,5 +6,6 @@ from . import _lib  # noqa: F401  (raises if the CUDA library has not been built
 from .unet import Unet
 from .deblurring import GaussianDiffusion
 from .trainer import Trainer
+from .model2 import Model
 
-__all__ = ['Unet', 'GaussianDiffusion', 'Trainer']
+__all__ = ['Unet', 'Model', 'GaussianDiffusion', 'Trainer']

@@ -582,3 +582,192 @@ extern "C" int cd_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float
   CD_LAUNCH_CHECK();
   return 0;
 }
+
+// =============================================================================================================
+// DDPM-style `Model` (Model2.py, "M2") forward pieces: GroupNorm(32, eps 1e-6) [+ per-(b,c) time-embedding add]
+// [+ swish] (M2:27-33,114-123), row softmax of the AttnBlock (M2:172-175), nearest 2x upsample (M2:47-48), batched
+// transpose (value matrix of the AttnBlock, M2:178-181) and NHWC -> NCHW for the 3-channel output.
+// =============================================================================================================
+namespace {
+// one block per batch element: pass 1 accumulates per-group sum / sum of squares (fp32), pass 2 normalises.
+__global__ void __launch_bounds__(512)
+groupnorm_kernel(const float* __restrict__ x, int x_ld, int HW, int C, int groups, const float* __restrict__ cond, int cond_ld,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int swish,
+                 float* __restrict__ y, int y_ld) {
+  extern __shared__ float sm[];                 // sum[groups] | sq[groups]
+  float* gsum = sm; float* gsq = sm + groups;
+  const int b = blockIdx.x;
+  const int nq = C >> 2, cg = C / groups;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const long long base = static_cast<long long>(b) * HW;
+  // thread -> (pixel lane, channel quad): consecutive threads walk consecutive quads of one pixel (coalesced)
+  const int q = threadIdx.x % nq, pl = threadIdx.x / nq, np = blockDim.x / nq;
+  float4 cadd = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cond && pl < np) cadd = *reinterpret_cast<const float4*>(cond + static_cast<long long>(b) * cond_ld + q * 4);
+  if (pl < np) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = pl; p < HW; p += np) {
+      float4 v = *reinterpret_cast<const float4*>(x + (base + p) * x_ld + q * 4);
+      v.x += cadd.x; v.y += cadd.y; v.z += cadd.z; v.w += cadd.w;
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
+    }
+    if (cg >= 4) {                               // the whole quad lies in one group
+      atomicAdd(&gsum[(q * 4) / cg], s[0] + s[1] + s[2] + s[3]);
+      atomicAdd(&gsq[(q * 4) / cg], s2[0] + s2[1] + s2[2] + s2[3]);
+    } else {
+      for (int j = 0; j < 4; ++j) { atomicAdd(&gsum[(q * 4 + j) / cg], s[j]); atomicAdd(&gsq[(q * 4 + j) / cg], s2[j]); }
+    }
+  }
+  __syncthreads();
+  const float inv_n = 1.f / (static_cast<float>(HW) * cg);
+  if (pl < np) {
+    float mean[4], rstd[4];
+    for (int j = 0; j < 4; ++j) {
+      const int g = (q * 4 + j) / cg;
+      mean[j] = gsum[g] * inv_n;
+      const float var = fmaxf(gsq[g] * inv_n - mean[j] * mean[j], 0.f);
+      rstd[j] = rsqrtf(var + eps);
+    }
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + q * 4);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + q * 4);
+    for (int p = pl; p < HW; p += np) {
+      float4 v = *reinterpret_cast<const float4*>(x + (base + p) * x_ld + q * 4);
+      float o[4] = {(v.x + cadd.x - mean[0]) * rstd[0] * gm.x + bt.x, (v.y + cadd.y - mean[1]) * rstd[1] * gm.y + bt.y,
+                    (v.z + cadd.z - mean[2]) * rstd[2] * gm.z + bt.z, (v.w + cadd.w - mean[3]) * rstd[3] * gm.w + bt.w};
+      if (swish) for (int j = 0; j < 4; ++j) o[j] = o[j] / (1.f + __expf(-o[j]));
+      *reinterpret_cast<float4*>(y + (base + p) * y_ld + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// softmax over the last dimension of [rows][n] (row stride ld), scale applied first; warp per row
+__global__ void softmax_rows_kernel(float* __restrict__ s, int ld, long long rows, int n, float scale) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float* r = s + row * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < n; j += 32) m = fmaxf(m, r[j] * scale);
+  m = cd_warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) { const float e = expf(r[j] * scale - m); r[j] = e; sum += e; }
+  sum = cd_warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < n; j += 32) r[j] *= inv;
+}
+
+// [B][R][Cc] (row stride ld) -> [B][Cc][R]
+__global__ void transpose_batched_kernel(const float* __restrict__ src, int ld, int R, int Cc, float* __restrict__ dst) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < R && c < Cc) ? src[(static_cast<long long>(b) * R + r) * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) dst[(static_cast<long long>(b) * Cc + c) * R + r] = t[threadIdx.x][i];
+  }
+}
+
+__global__ void upsample_nearest2x_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C, float* __restrict__ y, int y_ld) {
+  const int nq = C >> 2;
+  const long long total = static_cast<long long>(B) * 4 * H * W * nq;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % nq);
+    const long long op = i / nq;
+    const int ox = static_cast<int>(op % (2 * W)), oy = static_cast<int>((op / (2 * W)) % (2 * H)), b = static_cast<int>(op / (4LL * H * W));
+    const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<long long>(b) * H + oy / 2) * W + ox / 2) * x_ld + q * 4);
+    *reinterpret_cast<float4*>(y + op * y_ld + q * 4) = v;
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int ld, int B, int HW, int C, float* __restrict__ out) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= static_cast<long long>(B) * HW) return;
+  const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
+  for (int c = 0; c < C; ++c) out[(static_cast<long long>(b) * C + c) * HW + p] = x[pix * ld + c];
+}
+
+// generalised time MLP: emb(dim) -> hid (act) -> tdim ; cond_all = Wc act(temb) + bc.  act: 0 gelu, 1 swish
+__global__ void __launch_bounds__(256)
+time_mlp2_kernel(const long long* __restrict__ t, int dim, int hid, int tdim, int act, const float* __restrict__ w1,
+                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                 const float* __restrict__ wc, const float* __restrict__ bc, int sumC, float* __restrict__ temb,
+                 float* __restrict__ cond_all) {
+  extern __shared__ float sm[];          // emb[dim] | h[hid] | gt[tdim]
+  float* emb = sm; float* h = sm + dim; float* gt = h + hid;
+  const int b = blockIdx.x;
+  const float tv = static_cast<float>(t[b]);
+  const int half = dim / 2;
+  const float k = logf(10000.f) / (half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) { const float a = tv * expf(-k * i); emb[i] = sinf(a); emb[i + half] = cosf(a); }
+  if ((dim & 1) && threadIdx.x == 0) emb[dim - 1] = 0.f;
+  __syncthreads();
+  for (int o = threadIdx.x; o < hid; o += blockDim.x) {
+    float a = b1[o];
+    for (int i = 0; i < dim; ++i) a = fmaf(w1[o * dim + i], emb[i], a);
+    h[o] = act ? a / (1.f + expf(-a)) : cd_gelu(a);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < tdim; o += blockDim.x) {
+    float a = b2[o];
+    for (int i = 0; i < hid; ++i) a = fmaf(w2[o * hid + i], h[i], a);
+    if (temb) temb[b * tdim + o] = a;
+    gt[o] = act ? a / (1.f + expf(-a)) : cd_gelu(a);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < sumC; o += blockDim.x) {
+    float a = bc[o];
+    for (int i = 0; i < tdim; ++i) a = fmaf(wc[static_cast<long long>(o) * tdim + i], gt[i], a);
+    cond_all[static_cast<long long>(b) * sumC + o] = a;
+  }
+}
+}  // namespace
+
+extern "C" int cd_groupnorm_fwd(const float* x, int x_ld, int B, int64_t HW, int C, int groups, const float* cond, int cond_ld,
+                                const float* gamma, const float* beta, float eps, int swish, float* y, int y_ld, void* stream) {
+  CD_REQUIRE(C % 4 == 0 && C % groups == 0 && C / 4 <= 512 && x_ld % 4 == 0 && y_ld % 4 == 0 && (!cond || cond_ld % 4 == 0),
+             "cd_groupnorm_fwd: unsupported C=%d groups=%d", C, groups);
+  groupnorm_kernel<<<B, 512, sizeof(float) * 2 * groups, static_cast<cudaStream_t>(stream)>>>(x, x_ld, (int)HW, C, groups, cond, cond_ld,
+                                                                                           gamma, beta, eps, swish, y, y_ld);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cd_softmax_rows(float* s, int ld, int64_t rows, int n, float scale, void* stream) {
+  softmax_rows_kernel<<<cd_cdiv(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, ld, rows, n, scale);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cd_transpose_batched(const float* src, int ld, int B, int R, int C, float* dst, void* stream) {
+  dim3 grid(cd_cdiv(C, 32), cd_cdiv(R, 32), B), block(32, 8);
+  transpose_batched_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(src, ld, R, C, dst);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cd_upsample_nearest2x(const float* x, int x_ld, int B, int H, int W, int C, float* y, int y_ld, void* stream) {
+  CD_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && y_ld % 4 == 0, "cd_upsample_nearest2x: C must be a multiple of 4");
+  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 4);
+  int blocks = cd_cdiv(total, 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample_nearest2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_ld, B, H, W, C, y, y_ld);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cd_nhwc_to_nchw(const float* x, int ld, int B, int H, int W, int C, float* out, void* stream) {
+  const long long npix = static_cast<long long>(B) * H * W;
+  nhwc_to_nchw_kernel<<<cd_cdiv(npix, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, B, H * W, C, out);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cd_time_mlp2_fwd(const int64_t* t, int B, int dim, int hid, int tdim, int act, const float* w1, const float* b1,
+                                const float* w2, const float* b2, const float* wc, const float* bc, int sumC, float* temb,
+                                float* cond_all, void* stream) {
+  const size_t smem = sizeof(float) * (dim + hid + tdim);
+  time_mlp2_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(t), dim, hid, tdim, act, w1, b1,
+                                                                     w2, b2, wc, bc, sumC, temb, cond_all);
+  CD_LAUNCH_CHECK();
+  return 0;
+}

@@ -2,5 +2,6 @@
 from ..unet import Unet
 from ..deblurring import GaussianDiffusion
 from ..trainer import Trainer
+from ..model2 import Model
 
-__all__ = ['GaussianDiffusion', 'Unet', 'Trainer']
+__all__ = ['GaussianDiffusion', 'Unet', 'Trainer', 'Model']

@@ -237,6 +237,25 @@ int cd_chanmix(const float* xt, const float* xsrc, float* out, const float* mats
 int cd_snow(const float* xt, const float* og, float* out, const float* snow, const float* br_coef, const int64_t* t_hi,
             const int64_t* t_lo, int hi_off, int lo_off, int B, int H, int W, int snow_batch, int fix_brightness,
             int mode, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * DDPM-style `Model` (deblurring-diffusion-pytorch/deblurring_diffusion_pytorch/Model2.py, "M2") forward pieces; the dense
+ * convolutions (3x3, 1x1 q/k/v/proj/nin_shortcut, asymmetric-pad stride-2 Downsample, and the two batched matmuls of AttnBlock
+ * as per-batch-weight 1x1 tap-list convolutions) run through cd_conv_fwd.
+ * ------------------------------------------------------------------------------------------ */
+/* GroupNorm(groups, eps) of (x + cond[b,c]) [* swish] on NHWC (M2:32-33, 114-123) */
+int cd_groupnorm_fwd(const float* x, int x_ld, int B, int64_t HW, int C, int groups, const float* cond, int cond_ld,
+                     const float* gamma, const float* beta, float eps, int swish, float* y, int y_ld, void* stream);
+/* in-place softmax(scale * s) over the last dimension of [rows][n] (M2:172-175) */
+int cd_softmax_rows(float* s, int ld, int64_t rows, int n, float scale, void* stream);
+/* [B][R][C] -> [B][C][R] */
+int cd_transpose_batched(const float* src, int ld, int B, int R, int C, float* dst, void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest') on NHWC (M2:47-48) */
+int cd_upsample_nearest2x(const float* x, int x_ld, int B, int H, int W, int C, float* y, int y_ld, void* stream);
+int cd_nhwc_to_nchw(const float* x, int ld, int B, int H, int W, int C, float* out, void* stream);
+/* get_timestep_embedding -> dense0 -> act -> dense1 (= temb) ; cond_all = Wc act(temb) + bc (all blocks' temb_proj) (M2:6-24,289-294,122) */
+int cd_time_mlp2_fwd(const int64_t* t, int B, int dim, int hid, int tdim, int act, const float* w1, const float* b1,
+                     const float* w2, const float* b2, const float* wc, const float* bc, int sumC, float* temb,
+                     float* cond_all, void* stream);
 /* stand-alone EMA (DB:73-81): mode 1 copy, 2 lerp */
 int cd_ema_update(float* ema, const float* p, int64_t n, float beta, int mode, void* stream);
 

@@ -203,6 +203,25 @@ def main():
             out['br:' + key] = torch.tensor(gd.forward_process.br_coef_list)
     save('snow_small', x=xs2, **out)
 
+    # ---- (8) DDPM-style `Model` (Model2.py), eval mode, + Special_6_routine sampling (BASELINE config 2 shape) ----
+    torch.manual_seed(51)
+    mkw = dict(resolution=16, in_channels=3, out_ch=3, ch=32, ch_mult=(1, 2), num_res_blocks=2, attn_resolutions=(8,), dropout=0.1)
+    model = m.Model(**mkw).eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'norm' in n:
+                p.add_(0.1 * torch.randn_like(p))
+    msd = {k: v.clone() for k, v in model.state_dict().items()}
+    xm = torch.rand(3, 3, 16, 16) * 2 - 1
+    tm = torch.tensor([0, 3, 5])
+    with torch.no_grad():
+        ym = model(xm, tm)
+    gdm = m.GaussianDiffusion(model, image_size=16, device_of_kernel='cpu', channels=3, timesteps=6, loss_type='l1', kernel_std=0.1,
+                              kernel_size=3, blur_routine='Special_6_routine', train_routine='Final', sampling_routine='x0_step_down')
+    xt, dr, img = quiet(gdm.sample, batch_size=3, img=xm)
+    model.eval()
+    save('model2_small', x=xm, t=tm, y=ym, s_xt=xt, s_dr=dr, s_img=img, **{'sd:' + k: v for k, v in msd.items()})
+
 
 if __name__ == '__main__':
     main()

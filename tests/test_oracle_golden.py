@@ -186,6 +186,20 @@ def test_snow_decolor_oracle_and_host_tables_match_reference():
         assert rel(r['xt'], g['xt:' + key]) < 1e-6 and rel(r['direct_recons'], g['dr:' + key]) < 1e-5 and rel(r['recon'], g['img:' + key]) < 1e-4, key
 
 
+def test_model2_oracle_matches_reference():
+    import model2_oracle as MO
+    g = load('model2_small')
+    sd = {k[3:]: v for k, v in g.items() if k.startswith('sd:')}
+    with torch.no_grad():
+        y = MO.model_forward(sd, g['x'], g['t'], ch=32, num_resolutions=2, num_res_blocks=2)
+    assert rel(y, g['y']) < 2e-6
+    fn = lambda x, t: MO.model_forward(sd, x, t, ch=32, num_resolutions=2, num_res_blocks=2)
+    o = DO.DeblurOracle(fn, image_size=16, channels=3, timesteps=6, kernel_std=0.1, kernel_size=3, blur_routine='Special_6_routine',
+                        sampling_routine='x0_step_down')
+    xt, dr, img = o.sample(3, g['x'])
+    assert rel(xt, g['s_xt']) < 1e-5 and rel(dr, g['s_dr']) < 1e-5 and rel(img, g['s_img']) < 1e-4
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference only in build container')
 def test_oracle_matches_live_reference_config1_mnist():
     """BASELINE config 1: MNIST-shaped 1x32x32, T=20, k=11, sigma=7, Constant, B=4, full-size Unet."""

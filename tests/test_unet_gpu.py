@@ -195,3 +195,29 @@ def test_snowification_package_matches_reference_golden(small):
         assert rel(d1, g['one_dr:' + key]) < 1e-3 and rel(x1, g['one_x:' + key]) < 2e-3, key
         r = gd.sample(batch_size=3, img=x)
         assert rel(r['xt'], g['xt:' + key]) < 1e-5 and rel(r['direct_recons'], g['dr:' + key]) < 1e-3 and rel(r['recon'], g['img:' + key]) < 3e-3, key
+
+
+def test_ddpm_model_forward_and_sampling_match_reference_golden():
+    """`Model` (Model2.py DDPM UNet: GroupNorm+swish ResnetBlocks, softmax AttnBlock, asymmetric-pad Downsample, nearest Upsample)
+    in eval mode, and Special_6_routine x0_step_down sampling around it (BASELINE config 2 shape at reduced size)."""
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200.ops import CONV_SIMT
+    g = load('model2_small')
+    sd = {k[3:]: v for k, v in g.items() if k.startswith('sd:')}
+    model = cdm.Model(resolution=16, in_channels=3, out_ch=3, ch=32, ch_mult=(1, 2), num_res_blocks=2, attn_resolutions=(8,), dropout=0.1)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        y = model(g['x'].cuda(), g['t'].cuda())
+        assert rel(y, g['y']) < 1e-3
+        model.conv_impl = CONV_SIMT
+        y32 = model(g['x'].cuda(), g['t'].cuda())
+        model.conv_impl = 1
+        assert rel(y32, g['y']) < 3e-5
+    gd = cdm.GaussianDiffusion(model, image_size=16, device_of_kernel='cuda', channels=3, timesteps=6, loss_type='l1', kernel_std=0.1,
+                               kernel_size=3, blur_routine='Special_6_routine', train_routine='Final', sampling_routine='x0_step_down').cuda()
+    xt, dr, img = gd.sample(batch_size=3, img=g['x'].cuda())
+    assert rel(xt, g['s_xt']) < 1e-5 and rel(dr, g['s_dr']) < 1e-3 and rel(img, g['s_img']) < 3e-3
+    with pytest.raises(NotImplementedError):
+        model.train()(g['x'].cuda(), g['t'].cuda())
