@@ -255,7 +255,8 @@ class Model(nn.Module):
             self._conv(ops.make_conv_desc([(View(hn), T1, P[name + '.' + leaf], False)], View(t), (B, H, W), Cout=c, bias=getattr(a, leaf).bias))
         tc = n >= 128 and n % 32 == 0
         s = self._buf('as.%d' % n, (B, H, W, n))                       # scores[b, i, j] = sum_c q[b,i,c] k[b,j,c]: weights = k[b] ([n][c])
-        self._conv(ops.make_conv_desc([(View(q), T1, k, True)], View(s), (B, H, W), Cout=n), tc)
+        # the scores feed exp(): keep them in fp32 CUDA cores (the reference's torch.bmm is fp32 too: matmul.allow_tf32=False)
+        self._conv(ops.make_conv_desc([(View(q), T1, k, True)], View(s), (B, H, W), Cout=n), False)
         call('cd_softmax_rows', ptr(s), n, C.c_int64(B * n), n, C.c_float(int(c) ** (-0.5)), stream())
         vt = self._buf('avt.%dx%d' % (n, c), (B, c, n))                # v^T per image: the [Cout=c][Cin=n] weight slab of the second matmul
         call('cd_transpose_batched', ptr(v), c, B, n, c, ptr(vt), stream())

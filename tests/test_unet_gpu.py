@@ -218,6 +218,11 @@ def test_ddpm_model_forward_and_sampling_match_reference_golden():
     gd = cdm.GaussianDiffusion(model, image_size=16, device_of_kernel='cuda', channels=3, timesteps=6, loss_type='l1', kernel_std=0.1,
                                kernel_size=3, blur_routine='Special_6_routine', train_routine='Final', sampling_routine='x0_step_down').cuda()
     xt, dr, img = gd.sample(batch_size=3, img=g['x'].cuda())
-    assert rel(xt, g['s_xt']) < 1e-5 and rel(dr, g['s_dr']) < 1e-3 and rel(img, g['s_img']) < 3e-3
+    # TF32 convolutions (what the reference's own GPU path uses): ~1e-3 on the network output, compounding over the 6 reverse steps
+    assert rel(xt, g['s_xt']) < 1e-5 and rel(dr, g['s_dr']) < 2e-3 and rel(img, g['s_img']) < 4e-3
+    model.conv_impl = CONV_SIMT          # fp32 path: tight
+    xt, dr, img = gd.sample(batch_size=3, img=g['x'].cuda())
+    model.conv_impl = 1
+    assert rel(dr, g['s_dr']) < 3e-5 and rel(img, g['s_img']) < 2e-4
     with pytest.raises(NotImplementedError):
         model.train()(g['x'].cuda(), g['t'].cuda())
