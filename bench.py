@@ -231,6 +231,60 @@ def main():
     sample_ms_per_rev_step = ms_s / S
     sample_img_s = B * world / (sample_ms_per_rev_step * C3['timesteps'] / 1e3)
 
+    # ---- the other BASELINE configs that fit one GPU, as context (rank 0 only; not the headline, bounded to a few steps) ----
+    others = {}
+    if rank == 0:
+        try:
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                # config 2: CIFAR-10 32x32 deblur, DDPM `Model`, T=50 Special_6_routine, x0_step_down sampling, batch 128
+                m2 = cdm.Model(resolution=32, in_channels=3, out_ch=3, ch=128, ch_mult=(1, 2, 2, 2), num_res_blocks=2,
+                               attn_resolutions=(16,), dropout=0.1).to(dev).eval()
+                g2 = cdm.GaussianDiffusion(m2, image_size=32, device_of_kernel='cuda', channels=3, timesteps=50, loss_type='l1',
+                                           kernel_std=0.1, kernel_size=3, blur_routine='Special_6_routine', train_routine='Final',
+                                           sampling_routine='x0_step_down').to(dev)
+                xb = torch.rand(128, 3, 32, 32, device=dev) * 2 - 1
+                img2 = g2.opt(xb)
+                t2 = [50]
+
+                def rev2(s_):
+                    nonlocal img2
+                    st = torch.full((128,), t2[0] - 1, dtype=torch.long, device=dev)
+                    img2 = g2._reverse_step(img2, m2(img2, st), t2[0])
+                    t2[0] -= 1
+                for s_ in range(3):
+                    rev2(s_)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for s_ in range(5):
+                    rev2(s_)
+                e1.record(); torch.cuda.synchronize()
+                ms2 = e0.elapsed_time(e1) / 5
+                others['C2_cifar10_Model_sample'] = {"ms_per_reverse_step": ms2, "images_per_sec_50_step_sample": 128 / (ms2 * 50 / 1e3), "batch": 128}
+                del m2, g2
+                # config 5: AFHQ-128 denoising baseline, cosine T=200, ddim sampling, batch 32 (same Unet, reverse step = 1 fused kernel)
+                from cold_diffusion_models_b200.denoising_diffusion_pytorch import GaussianDiffusion as DNGD
+                g5 = DNGD(trainer.ema_model.denoise_fn, image_size=128, channels=3, timesteps=200, loss_type='l1', sampling_routine='ddim').to(dev)
+                im5 = torch.randn(B, 3, 128, 128, device=dev)
+                t5 = [200]
+
+                def rev5(s_):
+                    nonlocal im5
+                    st = torch.full((B,), t5[0] - 1, dtype=torch.long, device=dev)
+                    im5 = g5._step(im5, g5.denoise_fn(im5, st), None, 0, t5[0])
+                    t5[0] -= 1
+                for s_ in range(2):
+                    rev5(s_)
+                torch.cuda.synchronize()
+                e0.record()
+                for s_ in range(5):
+                    rev5(s_)
+                e1.record(); torch.cuda.synchronize()
+                ms5 = e0.elapsed_time(e1) / 5
+                others['C5_afhq_denoise_ddim_sample'] = {"ms_per_reverse_step": ms5, "images_per_sec_200_step_sample": B / (ms5 * 200 / 1e3), "batch": B}
+        except Exception as e:  # context only: never let it break the headline line
+            others['error'] = repr(e)[:200]
+
     # ---- roofline of the dominant kernel (tcgen05 tap-list convolution), CUDA events around every launch --------
     peaks, peak_kind = read_peaks()
     roof = None
@@ -274,6 +328,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": sampler.summary() if sampler else None,
             "train_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
+            "other_configs": others,
         }
         print(json.dumps(line))
     if world > 1:
