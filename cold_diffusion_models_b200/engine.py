@@ -162,8 +162,15 @@ class UnetEngine(_BackwardHolder):
     # ------------------------------------------------------------------------------------------
     profile_convs = None          # bench.py: list of (event0, event1, flops) per tensor-core conv launch
 
+    @staticmethod
+    def _tc_geometry_ok(desc):
+        """the tcgen05 kernels tile the pixel grid with power-of-two boxes; other image sizes use the fp32 CUDA-core kernel"""
+        w, h = desc.Wg, desc.Hg
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        return (w % 128 == 0) if w >= 128 else (pow2(w) and pow2(h))
+
     def _conv(self, desc, tc):
-        impl = self.conv_impl if tc else CONV_SIMT
+        impl = self.conv_impl if (tc and self._tc_geometry_ok(desc)) else CONV_SIMT
         if self.profile_convs is not None and impl == CONV_TC:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

@@ -138,8 +138,10 @@ class Trainer(object):
             self.ds = ImageFolderDataset(folder, image_size, augment=aug)
             self.dl = cycle(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=shuffle, pin_memory=True,
                                             num_workers=8 if aug else 16, drop_last=True))
-        self._unet = core.denoise_fn
-        self._ema_unet = _unwrap(self.ema_model).denoise_fn
+        # the restoration network is `denoise_fn` in every package except defading (`defade_fn`, DFG:303)
+        net_of = lambda m_: m_.denoise_fn if hasattr(m_, 'denoise_fn') else m_.defade_fn
+        self._unet = net_of(core)
+        self._ema_unet = net_of(_unwrap(self.ema_model))
         self.opt = FusedAdamEMA(self._unet.engine, self._ema_unet.engine, lr=train_lr)
         self.step = 0
         self.results_folder = Path(results_folder)

@@ -228,3 +228,34 @@ def test_ddpm_model_forward_and_sampling_match_reference_golden():
     assert rel(dr, g['s_dr']) < 3e-5 and rel(img, g['s_img']) < 2e-4
     with pytest.raises(NotImplementedError):
         model.train()(g['x'].cuda(), g['t'].cuda())
+
+
+def test_baseline_config1_mnist_shape_train_step_vs_oracle():
+    """BASELINE config 1: MNIST-shaped 1x32x32, T=20, k=11, sigma=7, 'Constant', batch 4, full-size Unet(channels=1):
+    p_losses forward + backward on the engine vs the CPU oracle's loss and autograd gradients (fp32 path, L1 loss)."""
+    import unet_oracle as UO
+    import deblur_oracle as DO
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200.ops import CONV_SIMT
+    sd = UO.make_unet_state_dict(64, (1, 2, 4, 8), 1, seed=2)
+    u = make_unet(64, (1, 2, 4, 8), 1, sd)
+    kw = dict(image_size=32, channels=1, timesteps=20, kernel_std=7.0, kernel_size=11, blur_routine='Constant')
+    gd = cdm.GaussianDiffusion(u, device_of_kernel='cuda', loss_type='l1', **kw).cuda()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(4, 1, 32, 32, generator=g) * 2 - 1
+    t = torch.randint(0, 20, (4,), generator=g)
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    orc = DO.DeblurOracle(lambda a, b: UO.unet_forward(ref, a, b), **kw)
+    ref_loss = orc.p_losses(x, t)
+    ref_loss.backward()
+    # tensor-core path: loss within the TF32 tolerance
+    loss = gd.p_losses(x.cuda(), t.cuda())
+    assert abs(loss.item() - ref_loss.item()) < 1e-3
+    # fp32 path: loss and every gradient
+    u.engine.conv_impl = CONV_SIMT
+    loss = gd.p_losses(x.cuda(), t.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_loss.item()) < 2e-5
+    worst = max((rel(p.grad, ref[n].grad), n) for n, p in u.named_parameters())
+    assert worst[0] < 5e-4, worst
