@@ -262,6 +262,39 @@ class UnetEngine(_BackwardHolder):
             save[spec.name] = dict(x=xv, xn=View(xn), qkv=qkv, kmax=kmax, ksum=ksum, ctx=ctx, weff=weff, stats=stats, out=outv)
 
     # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the inference forward (sampling loops call R(x_t, t) hundreds of times with identical shapes:
+    # ~150 kernel launches collapse into one graph launch; matters when the batch is small and the step is launch-bound)
+    # ------------------------------------------------------------------------------------------
+    use_cuda_graph = False
+    _graphs = None
+
+    def enable_cuda_graph(self, flag=True):
+        self.use_cuda_graph = bool(flag)
+        self._graphs = {}
+
+    def forward_graphed(self, x, time):
+        key = (tuple(x.shape), self._params_version())
+        g = self._graphs.get(key)
+        if g is None:
+            self.prepare_weights()
+            sx = x.contiguous().float().clone()
+            st = time.to(device=x.device, dtype=torch.int64).contiguous().clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up outside capture: allocates every workspace
+                for _ in range(2):
+                    self.forward(sx, st)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                so = self.forward(sx, st)
+            g = self._graphs[key] = (graph, sx, st, so)
+        graph, sx, st, so = g
+        sx.copy_(x)
+        st.copy_(time)
+        graph.replay()
+        return so.clone()
+
     def forward(self, x, time, save=None, out=None):
         """x (B,C,H,W) NCHW fp32 cuda, time (B,) int64 -> (B,out_dim,H,W) NCHW."""
         unet = self.unet

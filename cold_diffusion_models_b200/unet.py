@@ -162,4 +162,6 @@ class Unet(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .autograd import UnetFunction
             return UnetFunction.apply(self, x, time, *self.engine.param_list())
+        if self.engine.use_cuda_graph:
+            return self.engine.forward_graphed(x, time)
         return self.engine.forward(x, time)

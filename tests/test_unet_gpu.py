@@ -259,3 +259,34 @@ def test_baseline_config1_mnist_shape_train_step_vs_oracle():
     assert abs(loss.item() - ref_loss.item()) < 2e-5
     worst = max((rel(p.grad, ref[n].grad), n) for n, p in u.named_parameters())
     assert worst[0] < 5e-4, worst
+
+
+def test_cuda_graph_replay_of_the_sampling_forward(small):
+    """the inference forward captured once as a CUDA graph and replayed with new inputs equals the eager launches bit for bit"""
+    g, sd, u = small
+    x = g['x'].cuda()
+    with torch.no_grad():
+        eager = [u(x * s, torch.tensor([k, 7 - k]).cuda()).clone() for k, s in ((0, 1.0), (3, 0.5), (5, -1.0))]
+        u.engine.enable_cuda_graph(True)
+        try:
+            graphed = [u(x * s, torch.tensor([k, 7 - k]).cuda()).clone() for k, s in ((0, 1.0), (3, 0.5), (5, -1.0))]
+        finally:
+            u.engine.enable_cuda_graph(False)
+    for a, b in zip(eager, graphed):
+        assert torch.equal(a, b)
+
+
+def test_all_sample_gen_sample_consistency(small):
+    """all_sample (DB:609-689) walks the same trajectory as sample (DB:393-455); gen_sample with noise_level 0 equals sample."""
+    import cold_diffusion_models_b200 as cdm
+    g, sd, u = small
+    x = g['x'].cuda()
+    gd = cdm.GaussianDiffusion(u, image_size=32, device_of_kernel='cuda', channels=3, timesteps=4, kernel_std=0.15, kernel_size=7,
+                               blur_routine='Exponential_reflect', sampling_routine='x0_step_down').cuda()
+    xt, dr, img = gd.sample(batch_size=2, img=x)
+    X0, Xt = gd.all_sample(batch_size=2, img=x)
+    assert len(X0) == 5 and len(Xt) == 4
+    assert torch.equal(Xt[0], xt) and torch.equal(X0[0], dr) and torch.equal(X0[-1], img)
+    xt2, dr2, img2 = gd.gen_sample(batch_size=2, img=x, noise_level=0)
+    assert torch.equal(img2, img)
+    assert torch.equal(gd.opt(x), xt)
