@@ -338,10 +338,16 @@ time_mlp_kernel(const long long* __restrict__ t, int dim, const float* __restric
     gt[o] = cd_gelu(a);
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < sumC; o += blockDim.x) {
-    float a = bc[o];
-    for (int i = 0; i < dim; ++i) a = fmaf(wc[static_cast<long long>(o) * dim + i], gt[i], a);
-    cond_all[static_cast<long long>(b) * sumC + o] = a;
+  // all blocks' conditioning rows: one warp per output row, lanes stride the (coalesced) weight row
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = warp; o < sumC; o += nw) {
+      const float* wr = wc + static_cast<long long>(o) * dim;
+      float a = 0.f;
+      for (int i = lane; i < dim; i += 32) a = fmaf(wr[i], gt[i], a);
+      a = cd_warp_sum(a);
+      if (lane == 0) cond_all[static_cast<long long>(b) * sumC + o] = a + bc[o];
+    }
   }
 }
 

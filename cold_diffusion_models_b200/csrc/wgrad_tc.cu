@@ -325,7 +325,7 @@ int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float*
   const int b_bytes = (BN / 32) * b_rows_pad * 128;
   const int b_tx = (BN / 32) * b_rows * 128;                   // bytes the TMA unit actually writes per X tile
   const int stage_bytes = a_bytes + max_loads * b_bytes;
-  int stages = (200 * 1024) / stage_bytes; if (stages > 6) stages = 6;
+  int stages = (224 * 1024) / stage_bytes; if (stages > 6) stages = 6;   // 3 x 68 KB halo stages fit the 227 KB carve-out
   if (stages < 2) return 1;
   const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
 
