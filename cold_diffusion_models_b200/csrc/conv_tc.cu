@@ -348,6 +348,23 @@ int launch(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 
 extern "C" int cd_conv_tc_set_tf32_maps(int enable) { g_tf32_map_dtype = enable ? 1 : 0; return 0; }
 
+int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st);   // conv_tc2.cu: SM-pair (cta_group::2) variant
+static int g_use_2cta = 1;
+extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   // 0 off, 1 where the cost model prefers it, 2 wherever eligible
+
+// Tile-shape choice.  Cost model: waves over the SMs x columns per tile / relative MMA issue rate of that tile shape.  The
+// rates are the measured TFLOP/s of the long-K convolutions of the config-3 network (profiles/conv_shapes_2cta_r01.txt):
+// SM-pair 256x256 ~ 660-690, 128x256 ~ 610-645, 128x128 ~ 490-505, 128x64 ~ 265.
+static double tc_cost(long long m_tiles, int Cout, int BN, bool pair, int sms) {
+  if (pair) {
+    const long long tiles = ((m_tiles + 1) / 2) * (Cout / 256), slots = sms / 2;
+    return double((tiles + slots - 1) / slots) * 256.0;
+  }
+  const long long tiles = m_tiles * ((Cout + BN - 1) / BN);
+  const double rate = BN == 256 ? 0.92 : (BN == 128 ? 0.75 : 0.40);
+  return double((tiles + sms - 1) / sms) * BN / rate;
+}
+
 int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   EncodeTiledFn enc = get_encode();
   CD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
@@ -373,10 +390,15 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   CD_REQUIRE(p.TW * d->sx <= 256 && p.TH * d->sy <= 256, "conv_tc: strided box too large");
   p.tiles_x = d->Wg / p.TW; p.tiles_y = d->Hg / p.TH; p.tiles_n = cd_cdiv(d->B, p.TN);
   int BN = (d->Cout % 256 == 0) ? 256 : (d->Cout > 64 ? 128 : 64);
-  // small spatial sizes (16^2, 32^2) give few M tiles: prefer a narrower N tile while that still fills the 148 SMs better
-  {
+  if (BN == 256) {
+    // small spatial sizes (16^2, 32^2) give few M tiles: take the narrower N tile only when it saves whole waves
     const long long mt = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
-    if (BN == 256 && mt * (d->Cout / 256) < g_num_sms && d->Cout % 128 == 0) BN = 128;
+    double best = tc_cost(mt, d->Cout, 256, false, g_num_sms);
+    if (tc_cost(mt, d->Cout, 128, false, g_num_sms) < best) { BN = 128; best = tc_cost(mt, d->Cout, 128, false, g_num_sms); }
+    if (g_use_2cta && g_tf32_map_dtype && mt >= 2 && (g_use_2cta == 2 || tc_cost(mt, d->Cout, 256, true, g_num_sms) < best)) {
+      const int r2 = cd_conv_fwd_tc2(d, st);
+      if (r2 <= 0) return r2;                                 // 1 = not eligible: stay on the 1-CTA kernel
+    }
   }
   p.tiles_co = cd_cdiv(d->Cout, BN);
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_co;

@@ -319,6 +319,59 @@ extern "C" int cd_noise_step(const float* img, const float* x1_bar, const float*
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// Fade-to-colour generation (defading-generation-diffusion-pytorch/defading_diffusion_pytorch/defading_diffusion_pytorch.py,
+// "DFGEN"): the schedule is a per-PIXEL weight, alphas[t][y][x] = cumulative product of the fade kernels (DFGEN:320-344),
+// q_sample = alphas[t_b] * x1 + one_minus_alphas[t_b] * x2 (DFGEN:543-548), reverse step = img - xt_bar + xt_sub1_bar with
+// the fixed end image x2 (DFGEN:386-418).  Both weight tables are passed: in `reverse` mode the reference derives alphas from
+// one_minus_alphas, not the other way round.
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void fade_lerp_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const long long* __restrict__ t,
+                                 int t_scalar, const float* __restrict__ al, const float* __restrict__ om, int C, int HW,
+                                 long long n, float* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(i % HW);
+    const int tt = t ? static_cast<int>(t[i / (static_cast<long long>(HW) * C)]) : t_scalar;
+    const long long w = static_cast<long long>(tt) * HW + pix;
+    out[i] = al[w] * x1[i] + om[w] * x2[i];
+  }
+}
+__global__ void fade_step_kernel(const float* __restrict__ img, const float* __restrict__ x1, const float* __restrict__ x2,
+                                 int t, const float* __restrict__ al, const float* __restrict__ om, int HW, long long n,
+                                 float* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(i % HW);
+    const float xv = x1[i], ev = x2[i];
+    const long long w1 = static_cast<long long>(t - 1) * HW + pix;
+    const float xt_bar = al[w1] * xv + om[w1] * ev;
+    float xt_sub1 = xv;
+    if (t - 1 != 0) { const long long w2 = w1 - HW; xt_sub1 = al[w2] * xv + om[w2] * ev; }
+    out[i] = img[i] - xt_bar + xt_sub1;
+  }
+}
+}  // namespace
+
+extern "C" int cd_fade_lerp(const float* x1, const float* x2, const int64_t* t, int t_scalar, const float* alphas,
+                            const float* one_minus_alphas, int B, int C, int HW, float* out, void* stream) {
+  const long long n = static_cast<long long>(B) * C * HW;
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  fade_lerp_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x1, x2, reinterpret_cast<const long long*>(t), t_scalar,
+                                                                        alphas, one_minus_alphas, C, HW, n, out);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cd_fade_step(const float* img, const float* x1_bar, const float* x2, int t, const float* alphas,
+                            const float* one_minus_alphas, int B, int C, int HW, float* out, void* stream) {
+  CD_REQUIRE(t >= 1 && x2, "cd_fade_step: bad arguments");
+  const long long n = static_cast<long long>(B) * C * HW;
+  int blocks = cd_cdiv(n, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8; if (blocks < 1) blocks = 1;
+  fade_step_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, x1_bar, x2, t, alphas, one_minus_alphas, HW, n, out);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // Gaussian-mask fading (defading-diffusion-pytorch/defading_diffusion_pytorch/defading_diffusion_gaussian.py, "DFG"):
 // D(x,t) = x * prod_{i<=t} K_i with K_i = (1 - g_i / max g_i)[1:,1:] (DFG:328-352).  masks: cumulative products
 // [T][MS][MS] (MS = S, or 2S for the 'Random_*' routines where every sample uses its own S x S window at offset

@@ -79,8 +79,9 @@ class GaussianDiffusion(nn.Module):
         return [self.get_conv((k, k), (s, s), mode=m) for (k, s, m) in self._sched]
 
     # ---- degradation -------------------------------------------------------------------------------
-    def _apply_op(self, x, idx, *, per_sample_t=None, single=False, quantize=False):
-        """out = A_idx x A_idx^T per plane (idx < 0: identity).  per_sample_t: int64 (B,) indices."""
+    def _apply_op(self, x, idx, *, per_sample_t=None, single=False, quantize=False, collapse=True):
+        """out = A_idx x A_idx^T per plane (idx < 0: identity).  per_sample_t: int64 (B,) indices.
+        collapse=False skips the `discrete` mean-collapse at idx == T-1."""
         x = x.contiguous().float()
         B, Cc, H, W = x.shape
         assert H == W == self.image_size and Cc == self.channels
@@ -88,7 +89,7 @@ class GaussianDiffusion(nn.Module):
         ops = self._ops_single if single else self._ops_cum
         T = self.num_timesteps
         call('cd_blur_apply', ptr(x), ptr(out), ptr(ops), ptr(per_sample_t), int(idx), B, Cc, H, T,
-             int(self.discrete and not single), int(quantize), stream())
+             int(self.discrete and not single and collapse), int(quantize), stream())
         return out
 
     def _degrade_to(self, img, t):
@@ -136,12 +137,16 @@ class GaussianDiffusion(nn.Module):
                 return self._apply_op(x0_hat, (t - 2) % T, single=True)
             return self._apply_op(x0_hat, t - 2)
         elif self.sampling_routine == 'x0_step_down':
-            out = torch.empty_like(img)
-            B, Cc, H, W = img.shape
-            call('cd_blur_step_down', ptr(img.contiguous()), ptr(x0_hat.contiguous()), ptr(out), ptr(self._ops_cum),
-                 t - 1, t - 2, B, Cc, H, T, int(self.discrete), stream())
-            return out
+            return self._step_down(img, x0_hat, t)
         return x0_hat          # unknown routine: the reference leaves x = x0_hat
+
+    def _step_down(self, img, x0_hat, t):
+        """Algorithm 2: x_{t-1} = x_t - D(x0_hat, t) + D(x0_hat, t-1) with the cumulative operators (DB:436-451)."""
+        out = torch.empty_like(img)
+        B, Cc, H, W = img.shape
+        call('cd_blur_step_down', ptr(img.contiguous()), ptr(x0_hat.contiguous()), ptr(out), ptr(self._ops_cum),
+             t - 1, t - 2, B, Cc, H, self.num_timesteps, int(self.discrete), stream())
+        return out
 
     @torch.no_grad()
     def sample(self, batch_size=16, img=None, t=None, _noise=None):
@@ -177,7 +182,7 @@ class GaussianDiffusion(nn.Module):
         noise = torch.randn(shape, device=img.device) * noise_level
         return self.sample(batch_size=batch_size, img=img, t=t, _noise=noise)
 
-    gen_sample_2 = gen_sample      # DB:457-524 is line-for-line the same computation
+    gen_sample_2 = gen_sample      # DB:457-524 computes the same thing
 
     @torch.no_grad()
     def all_sample(self, batch_size=16, img=None, t=None, times=None, eval=True):
@@ -236,3 +241,73 @@ class GaussianDiffusion(nn.Module):
         X_0s.append(img)
         self.denoise_fn.train()
         return X_0s, X_ts
+
+    def _forward_trajectory(self, img, t):
+        """[x, D(x,1), ..., D(x,t)] of the cover figures: each entry from the cumulative operator in one launch
+        (the reference chains t convolutions, DB:707-711); no `discrete` collapse inside the forward pass."""
+        return [img] + [self._apply_op(img, i, collapse=False) for i in range(t)]
+
+    @torch.no_grad()
+    def forward_and_backward(self, batch_size=16, img=None, noise_level=0, t=None, times=None, eval=True):
+        """DB:691-770 -> (Forward, Backward, img)"""
+        if eval:
+            self.denoise_fn.eval()
+        if t is None:
+            t = self.num_timesteps
+        if times is None:
+            times = t
+        img = img.contiguous().float()
+        if self.blur_routine == 'Individual_Incremental':
+            Forward = [img]
+            img = self._apply_op(img, (t - 1) % self.num_timesteps, single=True)
+        else:
+            Forward = self._forward_trajectory(img, t)
+            img = Forward[-1]
+        Backward = []
+        if self.discrete:
+            img = torch.mean(img, [2, 3], keepdim=True).expand_as(img).contiguous()
+            img = img + torch.randn_like(img) * noise_level
+        while times:
+            step = torch.full((batch_size,), times - 1, dtype=torch.long, device=img.device)
+            x = self.denoise_fn(img, step)
+            Backward.append(img)
+            if self.train_routine == 'Final':
+                if self.blur_routine == 'Individual_Incremental' and self.sampling_routine in ('default', 'x0_step_down'):
+                    if times - 2 >= 0:          # the reference blurs `img`, not x (DB:735-737, 747-749)
+                        x = self._apply_op(img, times - 2, single=True)
+                else:
+                    x = self._reverse_step(img, x, times)
+            img = x
+            times = times - 1
+        return Forward, Backward, img
+
+    @torch.no_grad()
+    def forward_and_backward_2(self, batch_size=16, img=None, noise_level=0, eval=True):
+        """DB:772-861 -> (Forward, Backward_1, Backward_2, img_1, img_2): Algorithm 1 and Algorithm 2 from the same start"""
+        if eval:
+            self.denoise_fn.eval()
+        T = self.num_timesteps
+        img = img.contiguous().float()
+        Forward = self._forward_trajectory(img, T)
+        img = Forward[-1]
+        if self.discrete:
+            img = torch.mean(img, [2, 3], keepdim=True).expand_as(img).contiguous()
+            img = img + torch.randn_like(img) * noise_level
+        last_img = img
+        Backward_1, Backward_2 = [], []
+        times = T
+        while times:                            # Algorithm 1: x <- D(x0_hat, times-1)   (`img - img + ...`, DB:826)
+            step = torch.full((batch_size,), times - 1, dtype=torch.long, device=img.device)
+            x = self.denoise_fn(img, step)
+            Backward_1.append(img)
+            img = self._apply_op(x, times - 2, collapse=False)
+            times = times - 1
+        img_1 = img
+        times, img = T, last_img
+        while times:                            # Algorithm 2
+            step = torch.full((batch_size,), times - 1, dtype=torch.long, device=img.device)
+            x = self.denoise_fn(img, step)
+            Backward_2.append(img)
+            img = self._step_down(img, x, times)
+            times = times - 1
+        return Forward, Backward_1, Backward_2, img_1, img

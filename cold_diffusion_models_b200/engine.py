@@ -161,6 +161,7 @@ class UnetEngine(_BackwardHolder):
     # forward pieces.  `save` is None for inference; a dict for training (tensors kept for backward)
     # ------------------------------------------------------------------------------------------
     profile_convs = None          # bench.py: list of (event0, event1, flops) per tensor-core conv launch
+    profile_shapes = None         # tools/conv_shapes.py: (B, Hg, Wg, Cout, K, nsrc, per_batch) per entry of profile_convs
 
     @staticmethod
     def _tc_geometry_ok(desc):
@@ -178,6 +179,8 @@ class UnetEngine(_BackwardHolder):
             e1.record()
             k = sum(desc.s[i].ntaps * desc.s[i].C for i in range(desc.nsrc))
             self.profile_convs.append((e0, e1, 2.0 * desc.B * desc.Hg * desc.Wg * desc.Cout * k))
+            if self.profile_shapes is not None:
+                self.profile_shapes.append((desc.B, desc.Hg, desc.Wg, desc.Cout, k, desc.nsrc, desc.s[0].w_per_batch))
             return
         ops.conv_fwd(desc, impl)
 

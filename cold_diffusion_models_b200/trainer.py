@@ -127,17 +127,7 @@ class Trainer(object):
         self.train_num_steps = train_num_steps
 
         core = _unwrap(self.model)
-        channels = getattr(core, 'channels', 3)
-        if folder is None or dataset == 'synthetic':
-            self.ds = SyntheticImages(image_size, channels)
-            self.dl = cycle(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=False, pin_memory=True,
-                                            num_workers=0, drop_last=True))
-        else:
-            aug = dataset in ('mnist', 'cifar10', 'flower', 'celebA', 'AFHQ')
-            print(dataset, "DA used" if aug else "")
-            self.ds = ImageFolderDataset(folder, image_size, augment=aug)
-            self.dl = cycle(data.DataLoader(self.ds, batch_size=train_batch_size, shuffle=shuffle, pin_memory=True,
-                                            num_workers=8 if aug else 16, drop_last=True))
+        self.ds, self.dl = self._make_loader(folder, dataset, shuffle, seed=1234)
         # the restoration network is `denoise_fn` in every package except defading (`defade_fn`, DFG:303)
         net_of = lambda m_: m_.denoise_fn if hasattr(m_, 'denoise_fn') else m_.defade_fn
         self._unet = net_of(core)
@@ -151,6 +141,20 @@ class Trainer(object):
         if load_path is not None:
             self.load(load_path)
         self._world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+
+    _aug_datasets = ('mnist', 'cifar10', 'flower', 'celebA', 'AFHQ')     # `dataset` values that select Dataset_Aug1
+
+    def _make_loader(self, folder, dataset, shuffle, seed):
+        channels = getattr(_unwrap(self.model), 'channels', 3)
+        if folder is None or dataset == 'synthetic':
+            ds = SyntheticImages(self.image_size, channels, seed=seed)
+            return ds, cycle(data.DataLoader(ds, batch_size=self.batch_size, shuffle=False, pin_memory=True, num_workers=0,
+                                             drop_last=True))
+        aug = dataset in self._aug_datasets
+        print(dataset, "DA used" if aug else "")
+        ds = ImageFolderDataset(folder, self.image_size, augment=aug)
+        return ds, cycle(data.DataLoader(ds, batch_size=self.batch_size, shuffle=shuffle, pin_memory=True,
+                                         num_workers=8 if aug else 16, drop_last=True))
 
     # ---- reference API ------------------------------------------------------------------------------
     def reset_parameters(self):
@@ -179,15 +183,22 @@ class Trainer(object):
         self.ema_model.load_state_dict(_match_prefix(d['ema'], self.ema_model))
 
     # ---- hot loop --------------------------------------------------------------------------------------
+    def _next(self):
+        return next(self.dl)
+
     def _loss(self, d):
         return torch.mean(self.model(d))                       # DB:1192
+
+    def _sample_start(self):
+        """the image the periodic `sample` starts from (DB:1209)"""
+        return next(self.dl).cuda()
 
     def train_step(self, batches=None):
         """one optimizer step = gradient_accumulate_every micro-batches (DB:1188-1204). Returns mean loss (tensor)."""
         u_loss = None
         for i in range(self.gradient_accumulate_every):
-            d = batches[i] if batches is not None else next(self.dl)
-            d = d.cuda(non_blocking=True)
+            d = batches[i] if batches is not None else self._next()
+            d = tuple(x.cuda(non_blocking=True) for x in d) if isinstance(d, (tuple, list)) else d.cuda(non_blocking=True)
             loss = self._loss(d)
             u_loss = loss.detach() if u_loss is None else u_loss + loss.detach()
             (loss / self.gradient_accumulate_every).backward()
@@ -211,7 +222,7 @@ class Trainer(object):
             if self.step != 0 and self.step % self.save_and_sample_every == 0:
                 from torchvision import utils
                 milestone = self.step // self.save_and_sample_every
-                og_img = next(self.dl).cuda()
+                og_img = self._sample_start()
                 xt, direct_recons, all_images = _unwrap(self.ema_model).sample(batch_size=self.batch_size, img=og_img)
                 for name, img in (('og', og_img), ('recon', all_images), ('direct_recons', direct_recons), ('xt', xt)):
                     utils.save_image((img + 1) * 0.5, str(self.results_folder / f'sample-{name}-{milestone}.png'), nrow=6)
@@ -231,6 +242,48 @@ class DenoisingTrainer(Trainer):
 
     def _loss(self, d):
         return torch.mean(self.model(d, torch.randn_like(d)))
+
+    def _sample_start(self):
+        return torch.randn(self.batch_size, getattr(_unwrap(self.model), 'channels', 3), self.image_size, self.image_size,
+                           device='cuda')                       # DN:757-762
+
+
+class DemixingTrainer(Trainer):
+    """Trainer of demixing_diffusion_pytorch: two image folders, forward(x1, x2) on one batch of each (DM:600-772)."""
+    _aug_datasets = ('train',)
+
+    def __init__(self, diffusion_model, folder1, folder2, **kw):
+        load_path = kw.pop('load_path', None)
+        super().__init__(diffusion_model, folder1, **kw)
+        self.ds1, self.dl1 = self.ds, self.dl
+        self.ds2, self.dl2 = self._make_loader(folder2, kw.get('dataset'), kw.get('shuffle', True), seed=4321)
+        if load_path is not None:
+            self.load(load_path)
+
+    def _next(self):
+        return next(self.dl1), next(self.dl2)
+
+    def _loss(self, d):
+        return torch.mean(self.model(d[0], d[1]))               # DM:726-728
+
+    def _sample_start(self):
+        return next(self.dl2).cuda()                            # DM:747
+
+
+class DefadingGenerationTrainer(Trainer):
+    """Trainer of the defading-generation package: the end image x2 is a constant random colour in [-0.5, 0.5)
+    per sample (DFGEN:768-776), drawn on the device instead of on the host."""
+    _aug_datasets = ('train',)
+
+    def _colour(self, like_batch):
+        c = torch.rand((like_batch, 3), device='cuda') - 0.5
+        return c[:, :, None, None].expand(like_batch, 3, self.image_size, self.image_size).contiguous()
+
+    def _loss(self, d):
+        return torch.mean(self.model(d, self._colour(d.shape[0])))
+
+    def _sample_start(self):
+        return self._colour(self.batch_size)                    # DFGEN:796-803
 
 
 def _match_prefix(sd, model):

@@ -156,6 +156,9 @@ int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* str
 int cd_wgrad_tc_set_mode(int mode);
 /* diagnostic switch: 1 (default) = TFLOAT32 tensor maps (TMA rounds fp32->tf32 RN on load) */
 int cd_conv_tc_set_tf32_maps(int enable);
+/* SM-pair (tcgen05 cta_group::2, 256 pixels x 256 channels per pair) variant of the tap-list convolution:
+ * 0 = off, 1 = where the tile cost model prefers it, 2 = wherever the problem is eligible (tests) */
+int cd_conv_tc_set_2cta(int mode);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of the HBM-bound pieces (autograd of the reference modules restated as kernels).
@@ -217,6 +220,14 @@ int cd_noise_lerp(const float* x1, const float* x2, const int64_t* t, int t_scal
                   const float* sqrt_1mac, int64_t per_sample, int64_t n, float* out, void* stream);
 int cd_noise_step(const float* img, const float* x1_bar, const float* noise, int mode, int t, const float* sqrt_ac,
                   const float* sqrt_1mac, int64_t n, float* out, void* stream);
+/* Fade-to-colour generation (defading-generation-diffusion-pytorch/defading_diffusion_pytorch/defading_diffusion_pytorch.py,
+ * "DFGEN"): per-pixel schedule alphas / one_minus_alphas [T][HW] (DFGEN:320-344, 371-381).
+ *   cd_fade_lerp : q_sample = alphas[t_b] * x1 + one_minus_alphas[t_b] * x2 (t: int64 [B], or NULL -> t_scalar)  (DFGEN:543-548)
+ *   cd_fade_step : one reverse step img - xt_bar + xt_sub1_bar with the fixed end image x2            (DFGEN:386-418)     */
+int cd_fade_lerp(const float* x1, const float* x2, const int64_t* t, int t_scalar, const float* alphas,
+                 const float* one_minus_alphas, int B, int C, int HW, float* out, void* stream);
+int cd_fade_step(const float* img, const float* x1_bar, const float* x2, int t, const float* alphas,
+                 const float* one_minus_alphas, int B, int C, int HW, float* out, void* stream);
 /* Gaussian-mask fading (defading-diffusion-pytorch/defading_diffusion_pytorch/defading_diffusion_gaussian.py, "DFG"):
  * masks = cumulative products of the fade kernels [T][MS][MS]; rx/ry (optional, int64 [B]) = per-sample window
  * offsets of the 'Random_*' routines (DFG:359-367); index -1 = identity.

@@ -155,3 +155,64 @@ class DeblurOracle:
             img = x
             t -= 1
         return xt, direct_recons, img
+
+    # ---- cover-figure trajectories (DB:691-861), non-'Individual_Incremental' routines ----------------------
+    def _cum(self, x, n):
+        for i in range(n):
+            x = self.blur_step(i, x)
+        return x
+
+    def _alg2(self, img, x, times):
+        x_times = x
+        for i in range(times):
+            x_times = self.blur_step(i, x_times)
+            if self.discrete and i == (self.num_timesteps - 1):
+                x_times = self._collapse(x_times)
+        return img - x_times + self._cum(x, times - 1)
+
+    @torch.no_grad()
+    def forward_and_backward(self, batch_size, img, t=None, times=None):
+        """DB:691-770 with noise_level = 0 -> (Forward, Backward, img)"""
+        t = t or self.num_timesteps
+        times = times or t
+        Forward = [img]
+        for i in range(t):
+            img = self.blur_step(i, img)
+            Forward.append(img)
+        if self.discrete:
+            img = self._collapse(img)
+        Backward = []
+        while times:
+            step = torch.full((batch_size,), times - 1, dtype=torch.long)
+            x = self.denoise_fn(img, step)
+            Backward.append(img)
+            if self.sampling_routine == 'default':
+                x = self._cum(x, times - 1)
+            elif self.sampling_routine == 'x0_step_down':
+                x = self._alg2(img, x, times)
+            img = x
+            times -= 1
+        return Forward, Backward, img
+
+    @torch.no_grad()
+    def forward_and_backward_2(self, batch_size, img):
+        """DB:772-861 with noise_level = 0 -> (Forward, Backward_1, Backward_2, img_1, img_2)"""
+        T = self.num_timesteps
+        Forward = [img]
+        for i in range(T):
+            img = self.blur_step(i, img)
+            Forward.append(img)
+        if self.discrete:
+            img = self._collapse(img)
+        last = img
+        outs = []
+        for alg in (1, 2):
+            img, times, B = last, T, []
+            while times:
+                step = torch.full((batch_size,), times - 1, dtype=torch.long)
+                x = self.denoise_fn(img, step)
+                B.append(img)
+                img = self._cum(x, times - 1) if alg == 1 else self._alg2(img, x, times)
+                times -= 1
+            outs.append((B, img))
+        return Forward, outs[0][0], outs[1][0], outs[0][1], outs[1][1]

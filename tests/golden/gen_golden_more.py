@@ -1,0 +1,98 @@
+"""Golden vectors FROM THE UNMODIFIED REFERENCE for the demixing and defading-generation packages and for the deblurring
+cover-figure trajectories (forward_and_backward / forward_and_backward_2).  Build container only (/root/reference is not on
+the GPU box).  Reuses the small Unet weights stored in unet_small.npz so the existing fixtures stay untouched.
+
+    python tests/golden/gen_golden_more.py     ->  tests/golden/{demixing_small,defading_gen_small,fb_small}.npz
+"""
+import os, sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa
+from gen_golden import quiet, save  # noqa
+
+
+def small_sd():
+    z = np.load(os.path.join(HERE, 'unet_small.npz'))
+    return {k[3:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd:')}
+
+
+def stack(lst):
+    return torch.stack([x.detach().cpu() for x in lst])
+
+
+def main():
+    torch.set_num_threads(8)
+    ref_shim.patch_cuda_noop()
+    sd = small_sd()
+
+    # ---- demixing ------------------------------------------------------------------------------------------
+    dm = ref_shim.import_reference('demixing-diffusion-pytorch', 'demixing_diffusion_pytorch')
+    unet = quiet(dm.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet.load_state_dict(sd)
+    torch.manual_seed(51)
+    x1 = torch.rand(2, 3, 32, 32) * 2 - 1
+    x2 = torch.rand(2, 3, 32, 32) * 2 - 1
+    gd = dm.GaussianDiffusion(unet, image_size=32, channels=3, timesteps=5, loss_type='l1')
+    out = {}
+    tt = torch.tensor([4, 1])
+    out['q'] = gd.q_sample(x1, x2, tt)
+    with torch.no_grad():
+        out['loss'] = gd.p_losses(x1, x2, tt)
+    _, out['gen_dr'], out['gen_img'] = quiet(gd.gen_sample, batch_size=2, img=x2, noise_level=0)
+    _, out['sample_dr'], out['sample_img'] = quiet(gd.sample, batch_size=2, img=x2)
+    F_, B_, img = quiet(gd.forward_and_backward, batch_size=2, img1=x1, img2=x2)
+    out['fb_F'], out['fb_B'], out['fb_img'] = stack(F_), stack(B_), img
+    X1, Xt = quiet(gd.all_sample, batch_size=2, img=x2)
+    out['all_X1'], out['all_Xt'] = stack(X1), stack(Xt)
+    save('demixing_small', x1=x1, x2=x2, **out)
+
+    # ---- defading generation -------------------------------------------------------------------------------
+    dg = ref_shim.import_reference('defading-generation-diffusion-pytorch', 'defading_diffusion_pytorch')
+    unet = quiet(dg.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet.load_state_dict(sd)
+    torch.manual_seed(61)
+    x1 = torch.rand(2, 3, 32, 32) * 2 - 1
+    col = (torch.rand(2, 3) - 0.5)[:, :, None, None].expand(2, 3, 32, 32).contiguous()
+    out = {}
+    for rev in (False, True):
+        gd = dg.GaussianDiffusion(unet, image_size=32, channels=3, timesteps=4, loss_type='l1', reverse=rev, kernel_std=0.6,
+                                  initial_mask=3)
+        k = 'rev%d:' % int(rev)
+        tt = torch.tensor([3, 0])
+        out[k + 'alphas'], out[k + 'one_minus_alphas'] = gd.alphas, gd.one_minus_alphas
+        out[k + 'q'] = gd.q_sample(x1, col, tt)
+        with torch.no_grad():
+            out[k + 'loss'] = gd.p_losses(x1, col, tt)
+        _, out[k + 'sample_dr'], out[k + 'sample_img'] = quiet(gd.sample, batch_size=2, img=col)
+        _, out[k + 'gen_dr'], out[k + 'gen_img'] = quiet(gd.gen_sample, batch_size=2, img=col, noise_level=0)
+        F_, B_, img = quiet(gd.forward_and_backward, batch_size=2, img1=x1, img2=col)
+        out[k + 'fb_F'], out[k + 'fb_B'], out[k + 'fb_img'] = stack(F_), stack(B_), img
+        X1, Xt = quiet(gd.all_sample, batch_size=2, img=col)
+        out[k + 'all_X1'], out[k + 'all_Xt'] = stack(X1), stack(Xt)
+    save('defading_gen_small', x1=x1, col=col, **out)
+
+    # ---- deblurring cover-figure trajectories --------------------------------------------------------------
+    db = ref_shim.import_reference('deblurring-diffusion-pytorch', 'deblurring_diffusion_pytorch')
+    unet = quiet(db.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet.load_state_dict(sd)
+    torch.manual_seed(71)
+    x = torch.rand(2, 3, 32, 32) * 2 - 1
+    out = {}
+    for routine, ks, std, T, samp in [('Exponential_reflect', 7, 0.15, 4, 'x0_step_down'), ('Constant', 5, 1.0, 3, 'default')]:
+        gd = db.GaussianDiffusion(unet, image_size=32, device_of_kernel='cpu', channels=3, timesteps=T, kernel_std=std,
+                                  kernel_size=ks, blur_routine=routine, sampling_routine=samp)
+        key = '%s|%d|%g|%d|%s' % (routine, ks, std, T, samp)
+        F_, B_, img = quiet(gd.forward_and_backward, batch_size=2, img=x)
+        out['F:' + key], out['B:' + key], out['img:' + key] = stack(F_), stack(B_), img
+        F2, B1, B2, i1, i2 = quiet(gd.forward_and_backward_2, batch_size=2, img=x)
+        out['F2:' + key], out['B1:' + key], out['B2:' + key], out['i1:' + key], out['i2:' + key] = stack(F2), stack(B1), stack(B2), i1, i2
+    save('fb_small', x=x, **out)
+
+
+if __name__ == '__main__':
+    main()

@@ -221,3 +221,66 @@ def test_oracle_matches_live_reference_config1_mnist():
     with torch.no_grad():
         loss = o.p_losses(x, t)
     assert abs(loss.item() - ref_loss.item()) < 1e-5
+
+
+def _small_fn():
+    u = load('unet_small')
+    sd = {k[3:]: v for k, v in u.items() if k.startswith('sd:')}
+    return lambda x, t: UO.unet_forward(sd, x, t)
+
+
+def test_demixing_oracle_matches_reference():
+    import demixing_oracle as MO
+    g = load('demixing_small')
+    o = MO.DemixingOracle(_small_fn(), image_size=32, timesteps=5)
+    x1, x2, tt = g['x1'], g['x2'], torch.tensor([4, 1])
+    assert torch.allclose(o.q_sample(x1, x2, tt), g['q'], atol=1e-6)
+    with torch.no_grad():
+        assert abs(o.p_losses(x1, x2, tt).item() - g['loss'].item()) < 1e-5
+    _, dr, img = o.gen_sample(2, x2)
+    assert rel(dr, g['gen_dr']) < 1e-5 and rel(img, g['gen_img']) < 1e-4
+    _, dr, img = o.sample(2, x2)
+    assert rel(dr, g['sample_dr']) < 1e-5 and rel(img, g['sample_img']) < 1e-4
+    F_, B_, img = o.forward_and_backward(2, x1, x2)
+    assert rel(torch.stack(F_), g['fb_F']) < 1e-6 and rel(torch.stack(B_), g['fb_B']) < 1e-4 and rel(img, g['fb_img']) < 1e-4
+    X1, Xt = o.all_sample(2, x2)
+    assert rel(torch.stack(X1), g['all_X1']) < 1e-4 and rel(torch.stack(Xt), g['all_Xt']) < 1e-4
+
+
+def test_defading_generation_oracle_matches_reference():
+    import defading_gen_oracle as GO
+    g = load('defading_gen_small')
+    fn = _small_fn()
+    x1, col, tt = g['x1'], g['col'], torch.tensor([3, 0])
+    for rev in (False, True):
+        k = 'rev%d:' % int(rev)
+        o = GO.DefadingGenOracle(fn, image_size=32, timesteps=4, reverse=rev, kernel_std=0.6, initial_mask=3)
+        assert torch.allclose(o.alphas, g[k + 'alphas'], atol=1e-6) and torch.allclose(o.one_minus_alphas, g[k + 'one_minus_alphas'], atol=1e-6)
+        assert torch.allclose(o.q_sample(x1, col, tt), g[k + 'q'], atol=2e-6)
+        with torch.no_grad():
+            assert abs(o.p_losses(x1, col, tt).item() - g[k + 'loss'].item()) < 1e-5
+        _, dr, img = o.sample(2, col)
+        assert rel(dr, g[k + 'sample_dr']) < 1e-5 and rel(img, g[k + 'sample_img']) < 1e-4
+        _, dr, img = o.gen_sample(2, col)
+        assert rel(dr, g[k + 'gen_dr']) < 1e-5 and rel(img, g[k + 'gen_img']) < 1e-4
+        F_, B_, img = o.forward_and_backward(2, x1, col)
+        assert rel(torch.stack(F_), g[k + 'fb_F']) < 1e-5 and rel(torch.stack(B_), g[k + 'fb_B']) < 1e-4 and rel(img, g[k + 'fb_img']) < 1e-4
+        X1, Xt = o.all_sample(2, col)
+        assert rel(torch.stack(X1), g[k + 'all_X1']) < 1e-4 and rel(torch.stack(Xt), g[k + 'all_Xt']) < 1e-4
+
+
+def test_deblur_cover_trajectories_match_reference():
+    g = load('fb_small')
+    fn = _small_fn()
+    x = g['x']
+    for key in _cases('img:', g):
+        routine, ks, std, T, samp = key.split('|')
+        o = DO.DeblurOracle(fn, image_size=32, channels=3, timesteps=int(T), kernel_std=float(std), kernel_size=int(ks),
+                            blur_routine=routine, sampling_routine=samp)
+        F_, B_, img = o.forward_and_backward(2, x)
+        assert rel(torch.stack(F_), g['F:' + key]) < 1e-5 and rel(torch.stack(B_), g['B:' + key]) < 1e-4, key
+        assert rel(img, g['img:' + key]) < 1e-4, key
+        F2, B1, B2, i1, i2 = o.forward_and_backward_2(2, x)
+        assert rel(torch.stack(F2), g['F2:' + key]) < 1e-5, key
+        assert rel(torch.stack(B1), g['B1:' + key]) < 1e-4 and rel(torch.stack(B2), g['B2:' + key]) < 1e-4, key
+        assert rel(i1, g['i1:' + key]) < 1e-4 and rel(i2, g['i2:' + key]) < 1e-4, key
