@@ -147,6 +147,91 @@ conv_smallc_kernel(const SimtParams p) {
   }
 }
 
+// Register-tiled variant (Cout % 4 == 0, Cout <= 128, Cout/4 a power of two): thread = 4 output channels with their
+// K = ntaps*C weights in registers; 256 threads cover 256/(Cout/4) pixels at a time, the receptive fields of a 64-pixel
+// chunk are staged in shared memory and read as broadcast LDS.128; a warp writes whole contiguous output rows.
+// (16*KQ FMAs per KQ LDS.128 instead of 4 per LDS.128, and coalesced stores instead of one pixel row per thread.)
+__device__ __forceinline__ void stage_patches(float* patch_f, int KP, long long q0, long long pend, const float* __restrict__ src,
+                                              int ld, int C, int H, int W, int Hg, int Wg, int sy, int sx, int ntaps,
+                                              const int* dyv, const int* dxv) {
+  const int hw = Hg * Wg;
+  for (int i = threadIdx.x; i < 64 * ntaps; i += blockDim.x) {
+    const int pp = i / ntaps, tap = i - pp * ntaps;
+    const long long q = q0 + pp;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < pend) {
+      const int qi = static_cast<int>(q);                  // callers guarantee B*Hg*Wg < 2^31
+      const int b = qi / hw, rem = qi - b * hw;
+      const int gy = rem / Wg, gx = rem - gy * Wg;
+      const int iy = gy * sy + dyv[tap], ix = gx * sx + dxv[tap];
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const float* row = src + ((static_cast<long long>(b) * H + iy) * W + ix) * ld;
+        for (int c = 0; c < C; ++c) v[c] = row[c];
+      }
+    }
+    for (int c = 0; c < C; ++c) patch_f[pp * KP + tap * C + c] = v[c];
+  }
+}
+
+template <int KQ>
+__global__ void __launch_bounds__(256, 1)
+conv_smallc4_kernel(const SimtParams p, int chunks_per_block) {
+  constexpr int KP = 4 * KQ;
+  __shared__ float4 patch[64][KQ];
+  const SimtSrc& S = p.s[0];
+  const int K = S.ntaps * S.C;
+  const int CQ = p.Cout >> 2, PG = 256 / CQ;
+  const int cq = threadIdx.x % CQ, pg = threadIdx.x / CQ;
+  float* patch_f = reinterpret_cast<float*>(&patch[0][0]);
+  for (int i = threadIdx.x; i < 64 * KP; i += 256) patch_f[i] = 0.f;       // padding entries k >= K stay zero
+  float w[4][KP];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      w[c][k] = k < K ? S.w[(static_cast<long long>(k / S.C) * p.Cout + cq * 4 + c) * S.C + (k % S.C)] : 0.f;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + cq * 4);
+  const long long total = static_cast<long long>(p.B) * p.Hg * p.Wg;
+  const int hw = p.Hg * p.Wg;
+  const long long cbeg = static_cast<long long>(blockIdx.x) * chunks_per_block;
+  for (long long ch = cbeg; ch < cbeg + chunks_per_block; ++ch) {
+    const long long q0 = ch * 64;
+    if (q0 >= total) break;
+    const long long pend = q0 + 64 < total ? q0 + 64 : total;
+    __syncthreads();
+    stage_patches(patch_f, KP, q0, pend, S.src, S.ld, S.C, S.H, S.W, p.Hg, p.Wg, p.sy, p.sx, S.ntaps, S.dy, S.dx);
+    __syncthreads();
+    const int np = static_cast<int>(pend - q0);
+    for (int pp = pg; pp < np; pp += PG) {
+      float a0 = bv.x, a1 = bv.y, a2 = bv.z, a3 = bv.w;
+#pragma unroll
+      for (int kq = 0; kq < KQ; ++kq) {
+        const float4 x = patch[pp][kq];
+        a0 = fmaf(x.x, w[0][4 * kq], a0); a0 = fmaf(x.y, w[0][4 * kq + 1], a0); a0 = fmaf(x.z, w[0][4 * kq + 2], a0); a0 = fmaf(x.w, w[0][4 * kq + 3], a0);
+        a1 = fmaf(x.x, w[1][4 * kq], a1); a1 = fmaf(x.y, w[1][4 * kq + 1], a1); a1 = fmaf(x.z, w[1][4 * kq + 2], a1); a1 = fmaf(x.w, w[1][4 * kq + 3], a1);
+        a2 = fmaf(x.x, w[2][4 * kq], a2); a2 = fmaf(x.y, w[2][4 * kq + 1], a2); a2 = fmaf(x.z, w[2][4 * kq + 2], a2); a2 = fmaf(x.w, w[2][4 * kq + 3], a2);
+        a3 = fmaf(x.x, w[3][4 * kq], a3); a3 = fmaf(x.y, w[3][4 * kq + 1], a3); a3 = fmaf(x.z, w[3][4 * kq + 2], a3); a3 = fmaf(x.w, w[3][4 * kq + 3], a3);
+      }
+      const long long q = q0 + pp;
+      const int b = static_cast<int>(q / hw);
+      const int rem = static_cast<int>(q - static_cast<long long>(b) * hw);
+      const int gy = rem / p.Wg, gx = rem - gy * p.Wg;
+      const long long pix = (static_cast<long long>(b) * p.Ho + (gy * p.oys + p.oy0)) * p.Wo + (gx * p.oxs + p.ox0);
+      float4 v = make_float4(a0, a1, a2, a3);
+      if (p.resid) { const float4 r = *reinterpret_cast<const float4*>(p.resid + pix * p.resid_ld + cq * 4); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+      if (p.out2) *reinterpret_cast<float4*>(p.out2 + pix * p.out2_ld + cq * 4) = v;
+      if (p.act == CD_ACT_GELU) { v.x = cd_gelu(v.x); v.y = cd_gelu(v.y); v.z = cd_gelu(v.z); v.w = cd_gelu(v.w); }
+      else if (p.act == CD_ACT_GELU_BWD) {
+        const float4 g = *reinterpret_cast<const float4*>(p.aux + pix * p.aux_ld + cq * 4);
+        v.x *= cd_gelu_grad(g.x); v.y *= cd_gelu_grad(g.y); v.z *= cd_gelu_grad(g.z); v.w *= cd_gelu_grad(g.w);
+      }
+      if (p.round_tf32) { v.x = cd_round_tf32(v.x); v.y = cd_round_tf32(v.y); v.z = cd_round_tf32(v.z); v.w = cd_round_tf32(v.w); }
+      *reinterpret_cast<float4*>(p.out + pix * p.out_ld + cq * 4) = v;
+    }
+  }
+}
+
 // dW[tap][co][ci] += sum_pix dout[pix][co] * src[pix(tap)][ci]
 struct WgradParams {
   int B, Hg, Wg, sy, sx, Cout, C, H, W, ld, ntaps;
@@ -280,6 +365,95 @@ wgrad_smallc_kernel(const WgradParams p) {
   }
 }
 
+// Register-tiled variant for Cout % 4 == 0, Cout <= 128: thread = 4 output channels x all K = ntaps*C (padded to 4*KQ)
+// taps, one float4 of dY per pixel per thread (a warp reads whole 512-byte dY rows), the receptive field comes from shared
+// memory as broadcast LDS.128 -- 16*KQ FMAs per (1 LDG.128 + KQ LDS.128).  Pixel groups of one block are reduced through
+// shared memory so that each block issues one atomicAdd per weight.  (The first kernel above issued one LDS per FMA and
+// ran ~9x off the HBM roofline on the 3->128 3x3 / 3->64 1x1 image-edge convolutions of the Unet.)
+template <int KQ>
+__global__ void __launch_bounds__(256, 1)
+wgrad_smallc4_kernel(const WgradParams p) {
+  constexpr int KP = 4 * KQ;
+  __shared__ float4 patch[64][KQ];
+  __shared__ float red[256 * 4 * 4];                       // [pixel group][cq][4 co][4 k] of one k-quad
+  const int CQ = p.Cout >> 2;                              // threads per pixel (<= 32)
+  const int PG = 256 / CQ;                                 // pixel groups per block
+  const int cq = threadIdx.x % CQ, pg = threadIdx.x / CQ;
+  const int K = p.ntaps * p.C;
+  const long long total = static_cast<long long>(p.B) * p.Hg * p.Wg;
+  const long long pbeg = static_cast<long long>(blockIdx.x) * p.pix_per_split;
+  long long pend = pbeg + p.pix_per_split; if (pend > total) pend = total;
+  float acc[4][KP];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[c][k] = 0.f;
+  const int hw = p.Hg * p.Wg;
+  float* patch_f = reinterpret_cast<float*>(&patch[0][0]);
+  for (int i = threadIdx.x; i < 64 * KP; i += 256) patch_f[i] = 0.f;       // padding entries k >= K stay zero
+  const int NPT = 64 / PG;                                 // pixels per thread per 64-pixel chunk (<= 8)
+  for (long long q0 = pbeg; q0 < pend; q0 += 64) {
+    // all dY rows of this thread for the chunk are requested first: one exposed DRAM latency per chunk, overlapped with
+    // the staging of the receptive fields (two-pixel trips left every trip latency-bound at one block per SM)
+    float4 d[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      d[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const long long q = q0 + pg + u * PG;
+      if (u < NPT && q < pend) {
+        const int qi = static_cast<int>(q);
+        const int b = qi / hw, rem = qi - b * hw;
+        const int gy = rem / p.Wg, gx = rem - gy * p.Wg;
+        const long long o = (static_cast<long long>(b) * p.Ho + (gy * p.oys + p.oy0)) * p.Wo + (gx * p.oxs + p.ox0);
+        d[u] = __ldg(reinterpret_cast<const float4*>(p.dout + o * p.dout_ld + cq * 4));
+      }
+    }
+    __syncthreads();
+    stage_patches(patch_f, KP, q0, pend, p.src, p.ld, p.C, p.H, p.W, p.Hg, p.Wg, p.sy, p.sx, p.ntaps, p.dy, p.dx);
+    __syncthreads();
+    const int np = static_cast<int>(pend - q0 < 64 ? pend - q0 : 64);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int pp = pg + u * PG;
+      if (u < NPT && pp < np) {
+        const float4 dv = d[u];
+#pragma unroll
+        for (int kq = 0; kq < KQ; ++kq) {
+          const float4 x = patch[pp][kq];
+          acc[0][4 * kq] = fmaf(dv.x, x.x, acc[0][4 * kq]); acc[0][4 * kq + 1] = fmaf(dv.x, x.y, acc[0][4 * kq + 1]);
+          acc[0][4 * kq + 2] = fmaf(dv.x, x.z, acc[0][4 * kq + 2]); acc[0][4 * kq + 3] = fmaf(dv.x, x.w, acc[0][4 * kq + 3]);
+          acc[1][4 * kq] = fmaf(dv.y, x.x, acc[1][4 * kq]); acc[1][4 * kq + 1] = fmaf(dv.y, x.y, acc[1][4 * kq + 1]);
+          acc[1][4 * kq + 2] = fmaf(dv.y, x.z, acc[1][4 * kq + 2]); acc[1][4 * kq + 3] = fmaf(dv.y, x.w, acc[1][4 * kq + 3]);
+          acc[2][4 * kq] = fmaf(dv.z, x.x, acc[2][4 * kq]); acc[2][4 * kq + 1] = fmaf(dv.z, x.y, acc[2][4 * kq + 1]);
+          acc[2][4 * kq + 2] = fmaf(dv.z, x.z, acc[2][4 * kq + 2]); acc[2][4 * kq + 3] = fmaf(dv.z, x.w, acc[2][4 * kq + 3]);
+          acc[3][4 * kq] = fmaf(dv.w, x.x, acc[3][4 * kq]); acc[3][4 * kq + 1] = fmaf(dv.w, x.y, acc[3][4 * kq + 1]);
+          acc[3][4 * kq + 2] = fmaf(dv.w, x.z, acc[3][4 * kq + 2]); acc[3][4 * kq + 3] = fmaf(dv.w, x.w, acc[3][4 * kq + 3]);
+        }
+      }
+    }
+  }
+  // block reduction over the pixel groups, one k-quad at a time: red[pg][cq*4 + c][4]
+  for (int kq = 0; kq < KQ; ++kq) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) if (q == kq) v = acc[c][4 * q + j];        // static register indexing
+        red[((pg * CQ + cq) * 4 + c) * 4 + j] = v;
+      }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.Cout * 4; i += 256) {                       // i = co*4 + j
+      float s = 0.f;
+      for (int g = 0; g < PG; ++g) s += red[g * p.Cout * 4 + i];
+      const int co = i >> 2, k = 4 * kq + (i & 3);
+      if (k < K) atomicAdd(p.dw + (static_cast<long long>(k / p.C) * p.Cout + co) * p.C + (k % p.C), s);
+    }
+  }
+}
+
 // column sums: out[c] += sum_rows x[row*ld + c]
 __global__ void colsum_kernel(const float* x, int ld, long long rows, int C, float* out, long long rows_per_block) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -393,6 +567,56 @@ __global__ void unpack_wgrad_kernel(const float* packed, int O, int I, int KH, i
   }
 }
 
+// Conv2d (O,I,KH,KW) <-> packed [tap][O][I] through a shared-memory tile of 256 (o,i) rows x KH*KW taps, so that both the
+// reference-layout side (contiguous KH*KW-float rows) and the packed side (contiguous (o,i) runs per tap) are coalesced.
+// The element-wise kernels above touch one side with a stride of KH*KW floats (9x sector inflation on the read-modify-write).
+constexpr int kMaxKHW = 16;
+__global__ void __launch_bounds__(256)
+unpack_wgrad_tiled_kernel(const float* __restrict__ packed, long long rows, int KHW, int KW, const TapList tl, int ntaps,
+                          float* __restrict__ wg, int accumulate) {
+  __shared__ float tile[256 * (kMaxKHW + 1)];
+  __shared__ int covered[kMaxKHW];
+  const int stride = KHW | 1;
+  const long long r0 = static_cast<long long>(blockIdx.x) * 256;
+  if (threadIdx.x < KHW) covered[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x < ntaps) covered[tl.ky[threadIdx.x] * KW + tl.kx[threadIdx.x]] = 1;
+  const long long r = r0 + threadIdx.x;
+  for (int t = 0; t < ntaps; ++t)
+    tile[threadIdx.x * stride + tl.ky[t] * KW + tl.kx[t]] = r < rows ? packed[static_cast<long long>(t) * rows + r] : 0.f;
+  __syncthreads();
+  const int nrows = static_cast<int>(rows - r0 < 256 ? rows - r0 : 256);
+  float* dst = wg + r0 * KHW;
+  for (int idx = threadIdx.x; idx < nrows * KHW; idx += 256) {
+    const int rr = idx / KHW, k = idx - rr * KHW;
+    if (covered[k]) {
+      const float v = tile[rr * stride + k];
+      dst[idx] = accumulate ? dst[idx] + v : v;
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+pack_weight_tiled_kernel(const float* __restrict__ w, long long rows, int KHW, int KW, const TapList tl, int ntaps,
+                         int round_tf32, float* __restrict__ packed) {
+  __shared__ float tile[256 * (kMaxKHW + 1)];
+  const int stride = KHW | 1;
+  const long long r0 = static_cast<long long>(blockIdx.x) * 256;
+  const int nrows = static_cast<int>(rows - r0 < 256 ? rows - r0 : 256);
+  const float* src = w + r0 * KHW;
+  for (int idx = threadIdx.x; idx < nrows * KHW; idx += 256) {
+    const int rr = idx / KHW, k = idx - rr * KHW;
+    tile[rr * stride + k] = src[idx];
+  }
+  __syncthreads();
+  const long long r = r0 + threadIdx.x;
+  if (r < rows)
+    for (int t = 0; t < ntaps; ++t) {
+      float v = tile[threadIdx.x * stride + tl.ky[t] * KW + tl.kx[t]];
+      if (round_tf32) v = cd_round_tf32(v);
+      packed[static_cast<long long>(t) * rows + r] = v;
+    }
+}
+
 }  // namespace
 
 int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st);
@@ -416,6 +640,25 @@ static int conv_fwd_simt(const CdConvDesc* d, cudaStream_t st) {
   if (d->nsrc == 1 && c0.C <= 4 && c0.ntaps * c0.C <= kSmallK && !c0.w_per_batch && d->Cout % 4 == 0 && d->Cout <= 512 &&
       d->out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) {
     const long long total = static_cast<long long>(d->B) * d->Hg * d->Wg;
+    const int cq = d->Cout >> 2;
+    const bool vec_ok = d->Cout <= 128 && (cq & (cq - 1)) == 0 && total >= 1024 && total < (1ll << 31) &&
+                        (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0) &&
+                        (!d->resid || (d->resid_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0)) &&
+                        (!d->out2 || (d->out2_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0)) &&
+                        (!d->aux || (d->aux_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0));
+    if (vec_ok) {
+      const long long chunks = cd_cdiv(total, 64);
+      long long blocks = 148 * 2; if (blocks > chunks) blocks = chunks;
+      const int cpb = cd_cdiv(chunks, blocks);
+      const int grid = cd_cdiv(chunks, cpb);
+      const int KQ = cd_cdiv(c0.ntaps * c0.C, 4);
+      if (KQ <= 1) conv_smallc4_kernel<1><<<grid, 256, 0, st>>>(p, cpb);
+      else if (KQ <= 3) conv_smallc4_kernel<3><<<grid, 256, 0, st>>>(p, cpb);
+      else if (KQ <= 7) conv_smallc4_kernel<7><<<grid, 256, 0, st>>>(p, cpb);
+      else conv_smallc4_kernel<9><<<grid, 256, 0, st>>>(p, cpb);
+      CD_LAUNCH_CHECK();
+      return 0;
+    }
     const size_t smem = sizeof(float) * c0.ntaps * c0.C * d->Cout;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) { CD_CUDA(cudaFuncSetAttribute(conv_smallc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
@@ -459,7 +702,20 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   p.src = c.src; p.dout = dout; p.dout_ld = dout_ld; p.Ho = d->Ho; p.Wo = d->Wo;
   p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0; p.dw = dw;
   const long long total = static_cast<long long>(d->B) * d->Hg * d->Wg;
-  if (c.C <= 4 && c.ntaps * c.C <= kSmallK && !c.w_per_batch) {
+  const int Ksm = c.ntaps * c.C;
+  const bool pow2_cq = d->Cout >= 4 && ((d->Cout >> 2) & ((d->Cout >> 2) - 1)) == 0;
+  if (c.C <= 4 && Ksm <= kSmallK && !c.w_per_batch && d->Cout % 4 == 0 && d->Cout <= 128 && pow2_cq &&
+      dout_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 && total >= 1024 && total < (1ll << 31)) {
+    int blocks = 148 * 2; if (blocks > cd_cdiv(total, 256)) blocks = cd_cdiv(total, 256);
+    p.pix_per_split = cd_cdiv(total, blocks);
+    const int grid = cd_cdiv(total, p.pix_per_split);
+    const int KQ = cd_cdiv(Ksm, 4);
+    if (KQ <= 1) wgrad_smallc4_kernel<1><<<grid, 256, 0, st>>>(p);
+    else if (KQ <= 3) wgrad_smallc4_kernel<3><<<grid, 256, 0, st>>>(p);
+    else if (KQ <= 7) wgrad_smallc4_kernel<7><<<grid, 256, 0, st>>>(p);
+    else wgrad_smallc4_kernel<9><<<grid, 256, 0, st>>>(p);
+    CD_LAUNCH_CHECK();
+  } else if (c.C <= 4 && c.ntaps * c.C <= kSmallK && !c.w_per_batch) {
     int splits = cd_cdiv(total, 512); if (splits > 148 * 16) splits = 148 * 16; if (splits < 1) splits = 1;
     p.pix_per_split = cd_cdiv(total, splits);
     dim3 grid(cd_cdiv(total, p.pix_per_split), cd_cdiv(d->Cout, 128));
@@ -509,6 +765,13 @@ extern "C" int cd_pack_weight(const float* w, int O, int I, int KH, int KW, int 
   CD_REQUIRE(ntaps >= 1 && ntaps <= CD_MAX_TAPS, "cd_pack_weight: bad ntaps");
   TapList tl{}; for (int t = 0; t < ntaps; ++t) { tl.ky[t] = ky[t]; tl.kx[t] = kx[t]; }
   const long long total = static_cast<long long>(ntaps) * O * I;
+  if (!transposed_conv && mode == 0 && KH * KW <= kMaxKHW) {
+    const long long rows = static_cast<long long>(O) * I;
+    pack_weight_tiled_kernel<<<cd_cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, rows, KH * KW, KW, tl, ntaps,
+                                                                                              round_tf32, packed);
+    CD_LAUNCH_CHECK();
+    return 0;
+  }
   int blocks = cd_cdiv(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, O, I, KH, KW, transposed_conv, mode,
                                                                           tl, ntaps, round_tf32, packed);
@@ -522,6 +785,13 @@ extern "C" int cd_unpack_wgrad(const float* packed, int O, int I, int KH, int KW
   CD_REQUIRE(ntaps >= 1 && ntaps <= CD_MAX_TAPS, "cd_unpack_wgrad: bad ntaps");
   TapList tl{}; for (int t = 0; t < ntaps; ++t) { tl.ky[t] = ky[t]; tl.kx[t] = kx[t]; }
   const long long total = static_cast<long long>(ntaps) * O * I;
+  if (!transposed_conv && KH * KW <= kMaxKHW) {
+    const long long rows = static_cast<long long>(O) * I;
+    unpack_wgrad_tiled_kernel<<<cd_cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, rows, KH * KW, KW, tl, ntaps,
+                                                                                               w_grad, accumulate);
+    CD_LAUNCH_CHECK();
+    return 0;
+  }
   int blocks = cd_cdiv(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
   unpack_wgrad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, O, I, KH, KW, transposed_conv,
                                                                             tl, ntaps, w_grad, accumulate);

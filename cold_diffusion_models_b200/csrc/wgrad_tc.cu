@@ -76,9 +76,11 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint
   d |= static_cast<uint64_t>(1) << 61;                          // SWIZZLE_128B_BASE32B
   return d;
 }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+// same instruction without the "memory" clobber: volatile asm statements keep their order among themselves (barrier waits,
+// fences, commits), and ordinary loads of the constant descriptor table may then be scheduled across the MMAs
+__device__ __forceinline__ void mma_tf32_nomem(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc));
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -105,6 +107,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                               (uint32_t(BN >> 3) << 17) | (uint32_t(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
+  __shared__ uint4 mma_tab[kMaxTaps * 8 + 1];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int g = blockIdx.z;
@@ -171,27 +174,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
       }
     }
   } else if (warp == 1) {
+    // ---- MMA issuer.  The operand offsets of the MMAs of one chunk do not depend on the chunk: tabulate them once
+    // (one entry per MMA: A / B start offsets in 16-byte units, B descriptor high word, accumulator column, accumulate flag)
+    // so that the single issuing thread spends one LDS.128 + two adds per tcgen05.mma -- a 128x128x8 TF32 MMA lasts ~64 clk,
+    // a 128x64x8 one ~32 clk, and descriptor arithmetic in the loop was what bounded the issue rate.
+    const uint32_t a_lbo = a_bytes / 4, b_lbo = b_bytes / NCH;
+    const int ksteps_row = p.CW / 8;                // MMAs per image row of the chunk
+    const int per_tap = p.R * ksteps_row;
+    const int nmma = nt * per_tap;                  // <= kMaxTaps * 8
+    if (lane == 0) mma_tab[nmma] = make_uint4(0, 0, 0, 0);
+    if (lane < nmma) {
+      const int t = lane / per_tap, r = (lane % per_tap) / ksteps_row, j = lane % ksteps_row;
+      const uint32_t arow = r * p.CW + j * 8;
+      const uint32_t brow = r * (p.CW + p.halo) + j * 8 + p.tap_shift[g][t];
+      const uint32_t boffs = p.tap_load[g][t] * b_bytes + brow * 128;      // stage bases are 1024-byte aligned
+      const uint32_t bo = p.base_offset_mode == 1 ? ((boffs >> 7) & 7u) : (p.base_offset_mode == 2 ? ((boffs >> 7) & 3u) : 0u);
+      const uint64_t dbt = make_mnmajor_sw128_desc(0, b_lbo, bo);
+      mma_tab[lane] = make_uint4((arow * 128) >> 4, boffs >> 4, static_cast<uint32_t>(dbt >> 32),
+                                 static_cast<uint32_t>(t * BN) | ((r | j) != 0 ? 0x10000u : 0u));
+    }
+    __syncwarp();
     if (lane == 0) {
-      const uint32_t a_lbo = a_bytes / 4, b_lbo = b_bytes / NCH;
-      const int ksteps_row = p.CW / 8;              // MMAs per image row of the chunk
+      const uint64_t da_t = make_mnmajor_sw128_desc(0, a_lbo, 0);
+      const uint32_t da_hi = static_cast<uint32_t>(da_t >> 32), da_lo = static_cast<uint32_t>(da_t);
+      const uint32_t db_lo = static_cast<uint32_t>(make_mnmajor_sw128_desc(0, b_lbo, 0));
       for (int it = 0; it < nchunks; ++it) {
         const uint32_t stage = it % stages, ph = (it / stages) & 1u;
         mbar_wait(&full_bar[stage], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-        for (int t = 0; t < nt; ++t) {
-          const uint32_t sb = sa + a_bytes + p.tap_load[g][t] * b_bytes;
-          for (int r = 0; r < p.R; ++r) {
-            for (int j = 0; j < ksteps_row; ++j) {
-              const uint32_t arow = r * p.CW + j * 8;
-              const uint32_t brow = r * (p.CW + p.halo) + j * 8 + p.tap_shift[g][t];
-              const uint32_t aaddr = sa + arow * 128, baddr = sb + brow * 128;
-              const uint32_t boff = p.base_offset_mode == 1 ? ((baddr >> 7) & 7u) : (p.base_offset_mode == 2 ? ((baddr >> 7) & 3u) : 0u);
-              const uint64_t da = make_mnmajor_sw128_desc(aaddr, a_lbo, 0);
-              const uint64_t db = make_mnmajor_sw128_desc(baddr, b_lbo, boff);
-              mma_tf32(tmem_base + t * BN, da, db, kIdesc, (it | r | j) != 0 ? 1u : 0u);
-            }
-          }
+        const uint32_t sa16 = smem_u32(smem + stage * stage_bytes) >> 4;     // < 2^14: no carry into the LBO field
+        const uint32_t alo = da_lo + sa16, blo = db_lo + sa16 + (a_bytes >> 4);
+        const uint32_t first = it == 0 ? 0u : 0x10000u;
+        uint4 e = mma_tab[0];
+#pragma unroll 4
+        for (int i = 0; i < nmma; ++i) {
+          const uint4 en = mma_tab[i + 1];          // table has one spare entry; prefetched so the LDS latency is off the issue path
+          const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (alo + e.x);
+          const uint64_t db = (static_cast<uint64_t>(e.z) << 32) | (blo + e.y);
+          mma_tf32_nomem(tmem_base + (e.w & 0xFFFFu), da, db, kIdesc, (e.w | first) & 0x10000u);
+          e = en;
         }
         tc_commit(&empty_bar[stage]);
       }
@@ -249,6 +270,33 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 extern "C" int cd_wgrad_tc_set_mode(int mode) { g_wg_mode = mode; return 0; }
 
+// K-split policy.  One CTA owns (Cout tile, Cin tile, tap group, pixel range); it runs alone on its SM (the stages fill the
+// shared memory) and its red.add epilogue is not overlapped, so the launch costs waves x (chunks_per_split * t_chunk + t_over).
+//   0: 2 waves rounded up (first version)   1 / 2: at most 1 / 2 full waves   3: minimise the modelled cost
+static int g_split_policy = 3;
+static int g_split_over_clk = 12000;     // fixed cost per CTA in SM clocks (prologue + first-load latency + red.add epilogue)
+extern "C" int cd_wgrad_tc_set_split(int policy, int over_clk) { g_split_policy = policy; if (over_clk > 0) g_split_over_clk = over_clk; return 0; }
+
+static int choose_splits(int tg, int total_chunks, int max_splits, int sms, double chunk_clk) {
+  if (max_splits < 1) max_splits = 1;
+  int s;
+  if (g_split_policy == 0) s = cd_cdiv(2 * sms, tg);
+  else if (g_split_policy == 1) s = sms / tg;
+  else if (g_split_policy == 2) s = 2 * sms / tg;
+  else {
+    double best = 1e30; s = 1;
+    for (int c = 1; c <= max_splits && c * tg <= 4 * sms + tg; ++c) {
+      const int cps = cd_cdiv(total_chunks, c);
+      const int real = cd_cdiv(total_chunks, cps);
+      const double cost = double(cd_cdiv(static_cast<long long>(tg) * real, sms)) * (cps * chunk_clk + g_split_over_clk);
+      if (cost < best) { best = cost; s = c; }
+    }
+  }
+  if (s > max_splits) s = max_splits;
+  if (s < 1) s = 1;
+  return s;
+}
+
 // returns 1 if the problem is not tensor-core shaped (caller falls back to the SIMT kernel), 0 on success, <0 on error
 int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, cudaStream_t st) {
   const CdConvSrc& c = d->s[0];
@@ -304,10 +352,16 @@ int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float*
   p.total_chunks = d->B * p.chunks_x * p.chunks_y;
   p.tiles_co = cd_cdiv(d->Cout, 128); p.tiles_ci = cd_cdiv(c.C, BN);
   const int tiles = p.tiles_co * p.tiles_ci;
-  int splits = cd_cdiv(2 * g_sms, tiles * p.ngroups);
-  const int max_splits = cd_cdiv(p.total_chunks, 8);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  // MMAs of one chunk: taps x KR/8 k-steps, 128 x BN x 8 each (~68 clk at BN = 128: 128 B/clk of shared-memory operand reads)
+  const double chunk_clk = double(max_taps) * (KR / 8) * (BN == 128 ? 68.0 : 40.0);
+  int splits;
+  if (c.w_per_batch) {
+    const int cpi = p.chunks_x * p.chunks_y;
+    const int spi0 = choose_splits(tiles * p.ngroups * d->B, cpi, cpi, g_sms, chunk_clk);
+    splits = spi0 * d->B;
+  } else {
+    splits = choose_splits(tiles * p.ngroups, p.total_chunks, cd_cdiv(p.total_chunks, 8), g_sms, chunk_clk);
+  }
   p.chunks_per_split = cd_cdiv(p.total_chunks, splits);
   p.splits = cd_cdiv(p.total_chunks, p.chunks_per_split);
   if (c.w_per_batch) {

@@ -105,6 +105,8 @@ class BackwardMixin:
         self._bwd_version = ver
 
     # ------------------------------------------------------------------------------------------
+    profile_wgrads = None
+
     def _wgrad(self, src, taps, Cout, grid, dout, wgrad_param, bias_param, *, stride=1, out_map=(1, 1, 0, 0),
                transposed_conv=False, key=None):
         """accumulate the weight (and bias) gradient of one tap-list convolution into reference-layout grads."""
@@ -117,7 +119,16 @@ class BackwardMixin:
             dwp.zero_()
         d = ops.make_conv_desc([(src, taps, dwp, False)], dout, grid, stride=stride, Cout=Cout, out_map=out_map)
         bias_ok = bias_param is not None and out_map == (1, 1, 0, 0)
-        ops.conv_wgrad(d, dout, dwp, bias_param if bias_ok else None, impl=self.conv_impl)
+        if self.profile_wgrads is not None:                 # tools/wgrad_shapes.py: time the weight-gradient GEMM alone
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.conv_wgrad(d, dout, dwp, None, impl=self.conv_impl)
+            e1.record()
+            self.profile_wgrads.append((e0, e1, (grid[0], grid[1], grid[2], Cout, src.C, nt, stride)))
+            if bias_ok:
+                call('cd_colsum', C.c_void_p(dout.addr()), dout.ld, C.c_int64(grid[0] * grid[1] * grid[2]), Cout, ptr(bias_param), stream())
+        else:
+            ops.conv_wgrad(d, dout, dwp, bias_param if bias_ok else None, impl=self.conv_impl)
         if not direct:
             ops.unpack_wgrad(dwp, taps, wgrad_param, transposed_conv=transposed_conv, accumulate=True)
 

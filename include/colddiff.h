@@ -154,6 +154,9 @@ int cd_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* out, int 
 int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* stream);
 /* diagnostic switch for the tcgen05 wgrad: 0 = one X tile per tap, 1/2 = shared halo tile (base_offset 0 / computed) */
 int cd_wgrad_tc_set_mode(int mode);
+/* K-split policy of the tcgen05 wgrad: 0 = two waves rounded up, 1 / 2 = at most one / two full waves of CTAs,
+ * 3 (default) = minimise waves x (chunks_per_split x t_chunk + over_clk); over_clk > 0 sets the per-CTA fixed cost (SM clocks) */
+int cd_wgrad_tc_set_split(int policy, int over_clk);
 /* diagnostic switch: 1 (default) = TFLOAT32 tensor maps (TMA rounds fp32->tf32 RN on load) */
 int cd_conv_tc_set_tf32_maps(int enable);
 /* SM-pair (tcgen05 cta_group::2, 256 pixels x 256 channels per pair) variant of the tap-list convolution:
