@@ -66,14 +66,47 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-_LAUNCHES = {'cd_linattn_context': 2, 'cd_conv_wgrad': 2, 'cd_version': 0, 'cd_last_error': 0}
+_LAUNCHES = {'cd_linattn_context': 2, 'cd_conv_wgrad': 2, 'cd_time_mlp_fwd': 2, 'cd_version': 0, 'cd_last_error': 0}
 _launch_count = 0
+
+
+_PROF_SHAPE_ARGS = {'cd_dwconv7_fwd': (2, 3, 4, 5), 'cd_dwconv7_wgrad': (4, 5, 6, 7), 'cd_layernorm_bwd': (6, 7),
+                    'cd_layernorm_fwd': (2, 3), 'cd_linattn_context': (2, 3), 'cd_linattn_bwd_kv': (2, 3)}
+_prof = None          # tools/op_profile.py: list of (name, event0, event1) while profiling, else None
 
 
 def call(name, *args):
     global _launch_count
     _launch_count += _LAUNCHES.get(name, 1)
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(getattr(lib, name)(*args), name)
+        e1.record()
+        idx = _PROF_SHAPE_ARGS.get(name)
+        if idx:                  # per-shape rows for the HBM-bound kernels: (B, H, W, C) / (npix, C) / (B, n)
+            name = name + str(tuple(int(getattr(args[i], 'value', args[i])) for i in idx))
+        _prof.append((name, e0, e1))
+        return
     _check(getattr(lib, name)(*args), name)
+
+
+def profile_start():
+    """time every C-ABI call with CUDA events on the current stream (in-situ, warm caches) until profile_stop()"""
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """-> {name: (calls, total_ms)}"""
+    global _prof
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _prof:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + e0.elapsed_time(e1))
+    _prof = None
+    return out
 
 
 def reset_launch_count():

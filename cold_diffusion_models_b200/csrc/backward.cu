@@ -240,44 +240,81 @@ attn_bwd_small_kernel(const float* __restrict__ dweff, const float* __restrict__
 
 // per-pixel part: dk[n][hd] = P * (sum_e dctxn[hd][e] v[n][h,e] - rowdot[hd]),  P = exp(k-kmax)/ksum
 //                 dv[n][he] = sum_d P[n][h,d] dctxn[h,d][e]
-// block handles 32 pixels of one image; dctxn (16 KB) staged in shared memory.
-constexpr int kKvPix = 24;
+// Two 32x32 GEMMs per head and pixel.  Block = kKvTiles tiles of 32 pixels of one image; dctxn is staged once per block in
+// both orientations, P and v of a tile transposed ([channel][pixel]) so that a thread owning 4 pixels x 4 channels feeds
+// 32 FMAs from 4 LDS.128 per step (the first version issued 2 scalar LDS per FMA and was shared-memory-issue bound:
+// 924 us at 128x128 against ~230 us of HBM traffic).
+constexpr int kKvPix = 32;
+constexpr int kKvTiles = 8;
+constexpr int kKvStride = 36;         // floats per channel row of the transposed tiles (16-byte aligned, 4-way store conflicts)
 __global__ void __launch_bounds__(256)
 attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __restrict__ kmax,
                    const float* __restrict__ ksum, const float* __restrict__ dctxn, const float* __restrict__ rowdot,
-                   float* __restrict__ dqkv, int dld) {
-  __shared__ float dc[128][33];    // dctxn[(h,d)][e], padded: lanes walk the (h,d) axis
-  __shared__ float ps[kKvPix][128];
-  __shared__ float vs[kKvPix][128];
+                   float* __restrict__ dqkv, int dld, int tiles) {
+  extern __shared__ float smkv[];
+  float* dcA = smkv;                         // [h*32+d][e]
+  float* dcB = dcA + 4096;                   // [h*32+e][d]
+  float* psT = dcB + 4096;                   // [h*32+d][pixel], stride kKvStride
+  float* vsT = psT + 128 * kKvStride;        // [h*32+e][pixel]
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * kKvPix;
-  for (int i = threadIdx.x; i < 4096; i += blockDim.x) dc[i >> 5][i & 31] = dctxn[static_cast<long long>(b) * 4096 + i];
-  for (int i = threadIdx.x; i < kKvPix * 128; i += blockDim.x) {
-    const int pp = i >> 7, c = i & 127;
-    const int p = p0 + pp;
-    float pv = 0.f, vv = 0.f;
-    if (p < n) {
-      const float* row = qkv + (static_cast<long long>(b) * n + p) * ld;
-      pv = __expf(row[128 + c] - kmax[b * 128 + c]) / ksum[b * 128 + c];
-      vv = row[256 + c];
-    }
-    ps[pp][c] = pv; vs[pp][c] = vv;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 4096; i += 256) {
+    const float v = dctxn[static_cast<long long>(b) * 4096 + i];
+    const int hd = i >> 5, e = i & 31;
+    dcA[i] = v;
+    dcB[((hd & ~31) + e) * 32 + (hd & 31)] = v;
   }
-  __syncthreads();
-  // 32 pixels x 128 channels = 4096 outputs of each kind; thread handles 16 of each
-  for (int i = threadIdx.x; i < kKvPix * 128; i += blockDim.x) {
-    const int pp = i >> 7, c = i & 127, h = c >> 5, j = c & 31;
-    const int p = p0 + pp;
-    if (p >= n) continue;
-    float dk = 0.f, dv = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < 32; ++e) {
-      dk = fmaf(dc[h * 32 + j][e], vs[pp][h * 32 + e], dk);       // c = (h, d=j)
-      dv = fmaf(ps[pp][h * 32 + e], dc[h * 32 + e][j], dv);       // c = (h, e=j), sum over d=e
+  const int cq = tid & 31, pq = tid >> 5;           // channel quad (h = cq/8, j4 = (cq%8)*4), pixel quad
+  const int h = cq >> 3, j4 = (cq & 7) * 4;
+  const int c4 = h * 32 + j4;
+  const float4 rd = *reinterpret_cast<const float4*>(rowdot + b * 128 + c4);
+  const int lc = tid & 127, lhalf = tid >> 7;
+  const float kmx = kmax[b * 128 + lc], kinv = 1.f / ksum[b * 128 + lc];
+  for (int tile = 0; tile < tiles; ++tile) {
+    const int p0 = (blockIdx.x * tiles + tile) * kKvPix;
+    if (p0 >= n) break;
+    __syncthreads();                                 // previous tile consumed (and dc staged)
+    for (int pp = lhalf; pp < kKvPix; pp += 2) {
+      const int p = p0 + pp;
+      float pv = 0.f, vv = 0.f;
+      if (p < n) {
+        const float* row = qkv + (static_cast<long long>(b) * n + p) * ld;
+        pv = __expf(row[128 + lc] - kmx) * kinv;
+        vv = row[256 + lc];
+      }
+      psT[lc * kKvStride + pp] = pv; vsT[lc * kKvStride + pp] = vv;
     }
-    float* orow = dqkv + (static_cast<long long>(b) * n + p) * dld;
-    orow[128 + c] = ps[pp][c] * (dk - rowdot[b * 128 + c]);
-    orow[256 + c] = dv;
+    __syncthreads();
+    float dk[4][4] = {}, dv[4][4] = {};               // [pixel][channel]
+#pragma unroll 4
+    for (int e = 0; e < 32; ++e) {
+      const float4 vq = *reinterpret_cast<const float4*>(vsT + (h * 32 + e) * kKvStride + pq * 4);   // v[4 px][h,e]
+      const float4 da = *reinterpret_cast<const float4*>(dcB + (h * 32 + e) * 32 + j4);            // dctxn[h, d=j4..][e]
+      const float4 pq4 = *reinterpret_cast<const float4*>(psT + (h * 32 + e) * kKvStride + pq * 4);  // P[4 px][h, d=e]
+      const float4 db = *reinterpret_cast<const float4*>(dcA + (h * 32 + e) * 32 + j4);            // dctxn[h, d=e][e'=j4..]
+      const float vp[4] = {vq.x, vq.y, vq.z, vq.w}, pp_[4] = {pq4.x, pq4.y, pq4.z, pq4.w};
+      const float a4[4] = {da.x, da.y, da.z, da.w}, b4[4] = {db.x, db.y, db.z, db.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dk[i][j] = fmaf(vp[i], a4[j], dk[i][j]); dv[i][j] = fmaf(pp_[i], b4[j], dv[i][j]); }
+    }
+    const float rdv[4] = {rd.x, rd.y, rd.z, rd.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + pq * 4 + i;
+      if (p < n) {
+        float* orow = dqkv + (static_cast<long long>(b) * n + p) * dld;
+        float4 ok, ov;
+        ok.x = psT[(c4 + 0) * kKvStride + pq * 4 + i] * (dk[i][0] - rdv[0]);
+        ok.y = psT[(c4 + 1) * kKvStride + pq * 4 + i] * (dk[i][1] - rdv[1]);
+        ok.z = psT[(c4 + 2) * kKvStride + pq * 4 + i] * (dk[i][2] - rdv[2]);
+        ok.w = psT[(c4 + 3) * kKvStride + pq * 4 + i] * (dk[i][3] - rdv[3]);
+        ov = make_float4(dv[i][0], dv[i][1], dv[i][2], dv[i][3]);
+        *reinterpret_cast<float4*>(orow + 128 + c4) = ok;
+        *reinterpret_cast<float4*>(orow + 256 + c4) = ov;
+      }
+    }
   }
 }
 
@@ -358,6 +395,23 @@ __global__ void small_gemm_kernel(const float* __restrict__ A, int lda, int tran
   float* o = Cm + static_cast<long long>(m) * ldc + n;
   *o = accumulate ? *o + a : a;
 }
+// long-K variant: grid (ceil(M*N/128), KS); every block reduces a K slice and adds it atomically (C zeroed by the host when
+// not accumulating).  The time-embedding backward has M*N = 2048 outputs over K ~ 6000 (all conditioning channels).
+__global__ void small_gemm_splitk_kernel(const float* __restrict__ A, int lda, int transA, const float* __restrict__ Bm, int ldb,
+                                         int transB, float* __restrict__ Cm, int ldc, int M, int N, int K, int kslice) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * N) return;
+  const int n = static_cast<int>(idx % N), m = static_cast<int>(idx / N);
+  const int k0 = blockIdx.y * kslice;
+  int k1 = k0 + kslice; if (k1 > K) k1 = K;
+  float a = 0.f;
+  for (int k = k0; k < k1; ++k) {
+    const float av = transA ? A[static_cast<long long>(k) * lda + m] : A[static_cast<long long>(m) * lda + k];
+    const float bv = transB ? Bm[static_cast<long long>(n) * ldb + k] : Bm[static_cast<long long>(k) * ldb + n];
+    a = fmaf(av, bv, a);
+  }
+  atomicAdd(Cm + static_cast<long long>(m) * ldc + n, a);
+}
 // y[i] = dy[i] * gelu'(pre[i])   (y may alias dy);  act_out (optional) = gelu(pre)
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, long long n,
                                 float* __restrict__ y, float* __restrict__ act_out) {
@@ -392,7 +446,10 @@ extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int 
   CD_REQUIRE(C % 4 == 0 && C <= 1024 && dy_ld % 4 == 0 && h_ld % 4 == 0 && dh_ld % 4 == 0, "cd_layernorm_bwd: unsupported C=%d", C);
   const int nq = C / 4;
   CD_REQUIRE((nq & (nq - 1)) == 0 || nq >= 32, "cd_layernorm_bwd: C/4 must be a power of two below 128 channels (C=%d)", C);
-  int ppb = 512;
+  // pixels per block: at most 512, but never fewer than ~4 blocks per SM (8192 pixels of the 16x16 level gave 16 blocks)
+  int ppb = static_cast<int>(npix / (148 * 4));
+  if (ppb > 512) ppb = 512;
+  if (ppb < 32) ppb = 32;
   const int blocks = cd_cdiv(npix, ppb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = sizeof(float) * 2 * C;
@@ -404,8 +461,14 @@ extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int 
   return 0;
 }
 
+int cd_dwconv7_wgrad_pipe(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C, float* dw, cudaStream_t st);
+
 extern "C" int cd_dwconv7_wgrad(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C,
                                 float* dw, void* stream) {
+  {
+    const int rc = cd_dwconv7_wgrad_pipe(dh, dh_ld, x, x_ld, B, H, W, C, dw, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;                           // 1: shape not eligible for the persistent kernel
+  }
   // tile: TX = min(W, 32), TY <= 8 so that two blocks (2 x 28 warps) fit one SM (~100 KB of shared memory each)
   int TX = W < 32 ? W : 32;
   while (W % TX) --TX;
@@ -441,8 +504,16 @@ extern "C" int cd_linattn_bwd_small(const float* dweff, const float* ctx, const 
 
 extern "C" int cd_linattn_bwd_kv(const float* qkv, int ld, int B, int n, const float* kmax, const float* ksum,
                                  const float* dctxn, const float* rowdot, float* dqkv, int dld, void* stream) {
-  dim3 grid(cd_cdiv(n, kKvPix), B);
-  attn_bwd_kv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(qkv, ld, n, kmax, ksum, dctxn, rowdot, dqkv, dld);
+  CD_REQUIRE(dld % 4 == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, "cd_linattn_bwd_kv: dqkv must be 16-byte aligned with dld %% 4 == 0");
+  const size_t smem = sizeof(float) * (2 * 4096 + 2 * 128 * kKvStride);
+  static bool attr = false;
+  if (!attr) { CD_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  // tiles per block: up to kKvTiles (amortises the 32 KB dctxn staging), fewer when that would leave SMs idle
+  int tiles = static_cast<int>(static_cast<long long>(cd_cdiv(n, kKvPix)) * B / (148 * 2));
+  if (tiles > kKvTiles) tiles = kKvTiles;
+  if (tiles < 1) tiles = 1;
+  dim3 grid(cd_cdiv(n, kKvPix * tiles), B);
+  attn_bwd_kv_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(qkv, ld, n, kmax, ksum, dctxn, rowdot, dqkv, dld, tiles);
   CD_LAUNCH_CHECK();
   return 0;
 }
@@ -470,6 +541,16 @@ extern "C" int cd_conv1x1_to_nchw_bwd(const float* dout_nchw, const float* x, in
 extern "C" int cd_small_gemm(const float* A, int lda, int transA, const float* Bm, int ldb, int transB,
                              float* Cm, int ldc, int M, int N, int K, int accumulate, void* stream) {
   const long long total = static_cast<long long>(M) * N;
+  if (K >= 512 && total <= 148 * 128) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!accumulate) CD_CUDA(cudaMemset2DAsync(Cm, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+    const int ks = cd_cdiv(148 * 4, cd_cdiv(total, 128));
+    const int kslice = cd_cdiv(K, ks);
+    dim3 grid(cd_cdiv(total, 128), cd_cdiv(K, kslice));
+    small_gemm_splitk_kernel<<<grid, 128, 0, st>>>(A, lda, transA, Bm, ldb, transB, Cm, ldc, M, N, K, kslice);
+    CD_LAUNCH_CHECK();
+    return 0;
+  }
   small_gemm_kernel<<<cd_cdiv(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, transA, Bm, ldb, transB, Cm, ldc, M, N, K, accumulate);
   CD_LAUNCH_CHECK();
   return 0;

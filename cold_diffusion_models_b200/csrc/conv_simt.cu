@@ -519,8 +519,12 @@ static int launch_colsum(const float* x, int ld, long long rows, int C, float* o
   if (C % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && rows >= 64) {
     const int nq = C / 4;
     int G = 1; while (G < nq && G < 32) G <<= 1;
-    long long rpb = 1024;
-    dim3 g2(cd_cdiv(nq, G), cd_cdiv(rows, rpb));
+    // rows per block: at most 1024, but aim for >= 4 blocks per SM (8192 rows x 512 channels gave 32 blocks)
+    const int xb = cd_cdiv(nq, G);
+    long long rpb = rows * xb / (148 * 4);
+    if (rpb > 1024) rpb = 1024;
+    if (rpb < 64) rpb = 64;
+    dim3 g2(xb, cd_cdiv(rows, rpb));
     colsum_vec_kernel<<<g2, 256, sizeof(float) * G * 4, st>>>(x, ld, rows, C, out, rpb, G);
   } else {
     const long long rpb = 4096;

@@ -43,6 +43,7 @@ struct TcParams {
   int act; int round_tf32;
   float* out2; int out2_ld;
   const float* aux; int aux_ld;
+  int vec8;                       // every epilogue pointer 32-byte aligned, every row stride a multiple of 8 floats
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -84,6 +85,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       " [%0], [%1, {%3, %4, %5}], [%2];"
       :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
          "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -256,7 +265,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tmem_ld32(taddr + c, r);
         if (valid && co0 + c < p.Cout) {
           const int nvalid = min(32, p.Cout - (co0 + c));
-          if (nvalid == 32) {
+          if (nvalid == 32 && p.vec8) {
+            // 256-bit accesses (STG.E.256 / LDG.E.256): one full 32-byte sector per lane and instruction -- with 128-bit stores
+            // every sector of the output row is written in two half-sector pieces by different instructions
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
+              if (p.bias) { float t[8]; ldg8(p.bias + co0 + c + j, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += t[e]; }
+              if (rrow) { float t[8]; ldg8(rrow + co0 + c + j, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += t[e]; }
+              if (o2row) stg8(o2row + co0 + c + j, v);
+              if (p.act == CD_ACT_GELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = cd_gelu(v[e]);
+              } else if (p.act == CD_ACT_GELU_BWD) {
+                float t[8]; ldg8(arow + co0 + c + j, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= cd_gelu_grad(t[e]);
+              }
+              if (p.round_tf32) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = cd_round_tf32(v[e]);
+              }
+              stg8(orow + co0 + c + j, v);
+            }
+          } else if (nvalid == 32) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
@@ -406,6 +444,10 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   p.oys = d->oys; p.oxs = d->oxs; p.oy0 = d->oy0; p.ox0 = d->ox0;
   p.bias = d->bias; p.resid = d->resid; p.resid_ld = d->resid_ld; p.act = d->act; p.round_tf32 = d->round_tf32;
   p.out2 = d->out2; p.out2_ld = d->out2_ld; p.aux = d->aux; p.aux_ld = d->aux_ld;
+  {
+    auto ok8 = [](const void* ptr, int ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 8 == 0); };
+    p.vec8 = ok8(d->out, d->out_ld) && ok8(d->out2, d->out2_ld) && ok8(d->resid, d->resid_ld) && ok8(d->aux, d->aux_ld) && ok8(d->bias, 8);
+  }
   CD_REQUIRE(d->act != CD_ACT_GELU_BWD || (d->aux && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0 && d->aux_ld % 4 == 0), "conv_tc: GELU_BWD needs an aligned aux");
   CD_REQUIRE((reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && d->out_ld % 4 == 0, "conv_tc: out must be 16B aligned");
   CD_REQUIRE(!d->resid || ((reinterpret_cast<uintptr_t>(d->resid) & 15) == 0 && d->resid_ld % 4 == 0), "conv_tc: resid alignment");

@@ -177,14 +177,21 @@ dwconv7_tile_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, 
       cd_cp_async4(dst + px * 32, src + static_cast<long long>(ok ? ix : 0) * x_ld, ok);
     }
   }
-  float w[49];
-#pragma unroll
-  for (int k = 0; k < 49; ++k) w[k] = cvalid ? __ldg(wdw + c * 49 + (flip ? 48 - k : k)) : 0.f;
+  // the 32 x 49 filter slab of this block is one contiguous run of wdw: copy it coalesced (a per-thread gather has a
+  // 49-float lane stride, 32 sectors per load, repeated by all 8 warps); row stride 49 is odd -> conflict-free reads
+  float* wsm = xs + (TY + 6) * XW * 32;
+  {
+    const int nw = (C - c0 < 32 ? C - c0 : 32) * 49;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) cd_cp_async4(wsm + i, wdw + static_cast<long long>(c0) * 49 + i, true);
+  }
   float add = (cvalid && bdw) ? bdw[c] : 0.f;
   if (cvalid && cond) add += cond[static_cast<long long>(b) * cond_ld + c];
   cd_cp_async_wait_all();
   __syncthreads();
   if (ry >= TY) return;
+  float w[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) w[k] = cvalid ? wsm[lane * 49 + (flip ? 48 - k : k)] : 0.f;
   float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float* band = xs + (ry * XW) * 32 + lane;          // rows ry .. ry+6 of the staged tile = input rows y-3 .. y+3
   const long long orow = (static_cast<long long>(b) * H + y0 + ry) * W + x0;
@@ -208,6 +215,199 @@ dwconv7_tile_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, 
     for (int o = 6; o > 0; --o) acc[o] = acc[o - 1];
     acc[0] = 0.f;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, double-buffered variant (C % 32 == 0, H >= 16): one block per SM walks (32-channel slab, TY x TX tile) work
+// items; while the 16 row-warps compute tile i from one shared-memory buffer, tile i+1 streams into the other with 16-byte
+// LDGSTS (zero-filled outside the image).  The one-tile-per-block kernel above exposed every tile's load latency (two
+// resident blocks per SM cannot cover it) and ran at ~22 % of the FMA rate it is bound by.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwPTY = 16;
+__device__ __forceinline__ void cd_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+// stage one (TY+6) x (TX+6) x 32-channel input tile (zero outside the image) with 16-byte LDGSTS; 8 lanes per pixel
+template <int TX>
+__device__ __forceinline__ void dw_issue_tile(float* buf, const float* __restrict__ base, int x_ld, int H, int W, int x0, int y0) {
+  constexpr int XW = TX + 6, YH = kDwPTY + 6;
+  for (int i = threadIdx.x; i < YH * XW * 8; i += 32 * kDwPTY) {
+    const int q = i & 7, cell = i >> 3;
+    const int r = cell / XW, px = cell - r * XW;        // XW is a compile-time constant: multiply-shift, no division
+    const int iy = y0 + r, ix = x0 + px;
+    const bool ok = static_cast<unsigned>(iy) < static_cast<unsigned>(H) && static_cast<unsigned>(ix) < static_cast<unsigned>(W);
+    cd_cp_async16(buf + cell * 32 + q * 4, base + (static_cast<long long>(ok ? iy : 0) * W + (ok ? ix : 0)) * x_ld + q * 4, ok);
+  }
+}
+
+template <int TX>
+__global__ void __launch_bounds__(32 * kDwPTY, 1)
+dwconv7_pipe_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, int C,
+                    const float* __restrict__ wdw, const float* __restrict__ bdw, const float* __restrict__ cond, int cond_ld,
+                    float* __restrict__ out, int out_ld, int flip, const float* __restrict__ addend, int addend_ld) {
+  extern __shared__ __align__(16) float xsp[];       // 2 x [(TY+6)][(TX+6)][32]
+  constexpr int TY = kDwPTY, XW = TX + 6, YH = TY + 6;
+  constexpr int tile_floats = YH * XW * 32;
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int tiles_x = W / TX, tiles_y = H / TY;
+  const int ntiles = B * tiles_x * tiles_y;
+  const int total = (C / 32) * ntiles;                 // slab-major: consecutive items of a block mostly share the filter slab
+
+  auto issue = [&](int item, float* buf) {
+    const int slab = item / ntiles, t = item - slab * ntiles;
+    const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+    dw_issue_tile<TX>(buf, x + static_cast<long long>(b) * H * W * x_ld + slab * 32, x_ld, H, W, tx * TX - 3, ty * TY - 3);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int item = blockIdx.x;
+  if (item >= total) return;
+  int bufi = 0;
+  issue(item, xsp);
+  float w[49];
+  int cur_slab = -1;
+  for (; item < total; item += gridDim.x) {
+    const int nxt = item + gridDim.x;
+    const float* buf = xsp + bufi * tile_floats;
+    if (nxt < total) {
+      issue(nxt, xsp + (bufi ^ 1) * tile_floats);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int slab = item / ntiles, t = item - slab * ntiles;
+    const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+    const int c = slab * 32 + lane;
+    if (slab != cur_slab) {
+      cur_slab = slab;
+#pragma unroll
+      for (int k = 0; k < 49; ++k) w[k] = __ldg(wdw + static_cast<long long>(c) * 49 + (flip ? 48 - k : k));
+    }
+    {
+      float add = bdw ? bdw[c] : 0.f;
+      if (cond) add += cond[static_cast<long long>(b) * cond_ld + c];
+      float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* band = buf + (ry * XW) * 32 + lane;
+      const long long opix = (static_cast<long long>(b) * H + ty * TY + ry) * W + tx * TX;
+      float* outp = out + opix * out_ld + c;
+      const float* addp = addend ? addend + opix * addend_ld + c : nullptr;
+      // fully unrolled: every LDS has an immediate offset, the 7-slot accumulator shift is register renaming
+#pragma unroll
+      for (int cx = 0; cx < XW; ++cx) {
+        float col[7];
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) col[ky] = band[(ky * XW + cx) * 32];
+#pragma unroll
+        for (int o = 0; o < 7; ++o) {
+#pragma unroll
+          for (int ky = 0; ky < 7; ++ky) acc[o] = fmaf(w[ky * 7 + o], col[ky], acc[o]);
+        }
+        if (cx >= 6) {
+          float v = acc[6] + add;
+          if (addp) { v += *addp; addp += addend_ld; }
+          *outp = v; outp += out_ld;
+        }
+#pragma unroll
+        for (int o = 6; o > 0; --o) acc[o] = acc[o - 1];
+        acc[0] = 0.f;
+      }
+    }
+    __syncthreads();                                   // buffer fully read before the next iteration's prefetch overwrites it
+    bufi ^= 1;
+  }
+}
+
+// Weight gradient with the same structure (the mirror image of the forward: 49 accumulators per channel, a 7x7 input window
+// slides along the row of the warp, one new column (7 LDS) + one dY value per pixel feed 49 FMAs).  Tiles of 16 x 16 outputs:
+// input tile + dY tile = 94 KB, double-buffered; accumulators live across all items of a slab and leave through one
+// shared-memory reduction over the 16 row-warps and one atomicAdd per (channel, tap) per block and slab.
+constexpr int kDwWTX = 16;
+__global__ void __launch_bounds__(32 * kDwPTY, 1)
+dwconv7_wgrad_pipe_kernel(const float* __restrict__ dh, int dh_ld, const float* __restrict__ x, int x_ld,
+                          int B, int H, int W, int C, float* __restrict__ dw) {
+  extern __shared__ __align__(16) float xsw[];       // 2 x ( [(TY+6)][(TX+6)][32] | [TY][TX][32] )
+  constexpr int TX = kDwWTX, TY = kDwPTY, XW = TX + 6, YH = TY + 6;
+  constexpr int x_floats = YH * XW * 32, d_floats = TY * TX * 32, buf_floats = x_floats + d_floats;
+  __shared__ float red[49][32];
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int tiles_x = W / TX, tiles_y = H / TY;
+  const int ntiles = B * tiles_x * tiles_y;
+  const int total = (C / 32) * ntiles;
+
+  auto issue = [&](int item, float* buf) {
+    const int slab = item / ntiles, t = item - slab * ntiles;
+    const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+    dw_issue_tile<TX>(buf, x + static_cast<long long>(b) * H * W * x_ld + slab * 32, x_ld, H, W, tx * TX - 3, ty * TY - 3);
+    const float* dbase = dh + ((static_cast<long long>(b) * H + ty * TY) * W + tx * TX) * dh_ld + slab * 32;
+    float* dbuf = buf + x_floats;
+    for (int i = threadIdx.x; i < TY * TX * 8; i += 32 * kDwPTY) {
+      const int q = i & 7, cell = i >> 3;
+      const int r = cell / TX, px = cell - r * TX;
+      cd_cp_async16(dbuf + cell * 32 + q * 4, dbase + (static_cast<long long>(r) * W + px) * dh_ld + q * 4, true);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto flush = [&](float (&acc)[49], int slab) {        // all threads of the block
+    for (int i = threadIdx.x; i < 49 * 32; i += blockDim.x) red[i >> 5][i & 31] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 49; ++k) { atomicAdd(&red[k][lane], acc[k]); acc[k] = 0.f; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 49 * 32; i += blockDim.x)
+      atomicAdd(dw + static_cast<long long>(slab * 32 + (i & 31)) * 49 + (i >> 5), red[i >> 5][i & 31]);
+    __syncthreads();
+  };
+
+  int item = blockIdx.x;
+  if (item >= total) return;
+  int bufi = 0;
+  issue(item, xsw);
+  float acc[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) acc[k] = 0.f;
+  int cur_slab = item / ntiles;
+  for (; item < total; item += gridDim.x) {
+    const int nxt = item + gridDim.x;
+    const float* buf = xsw + bufi * buf_floats;
+    if (nxt < total) {
+      issue(nxt, xsw + (bufi ^ 1) * buf_floats);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int slab = item / ntiles;
+    if (slab != cur_slab) { flush(acc, cur_slab); cur_slab = slab; }
+    {
+      const float* band = buf + (ry * XW) * 32 + lane;            // input rows ry .. ry+6 (image rows y-3 .. y+3)
+      const float* drow = buf + x_floats + (ry * TX) * 32 + lane;
+      float win[7][7];                                            // win[ky][kx] = x[y+ky-3][px+kx-3]
+#pragma unroll
+      for (int kx = 1; kx < 7; ++kx)
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) win[ky][kx] = band[(ky * XW + kx - 1) * 32];
+#pragma unroll
+      for (int px = 0; px < TX; ++px) {
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 6; ++kx) win[ky][kx] = win[ky][kx + 1];
+          win[ky][6] = band[(ky * XW + px + 6) * 32];
+        }
+        const float d = drow[px * 32];
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) acc[ky * 7 + kx] = fmaf(d, win[ky][kx], acc[ky * 7 + kx]);
+      }
+    }
+    __syncthreads();
+    bufi ^= 1;
+  }
+  flush(acc, cur_slab);
 }
 
 // generic (any C, e.g. the 1/3-channel image): one thread per pixel, loops channels; LN optional.
@@ -337,17 +537,28 @@ time_mlp_kernel(const long long* __restrict__ t, int dim, const float* __restric
     temb[b * dim + o] = a;
     gt[o] = cd_gelu(a);
   }
+}
+
+// conditioning rows of every ConvNextBlock (GELU -> Linear(dim, block_dim), DB:143-146) for all batch elements:
+// cond_all[b][o] = bc[o] + sum_i wc[o][i] * gelu(temb[b][i]).  grid (row chunks, B); one warp per output row, lanes stride the
+// (coalesced) weight row.  (Inside the one-block-per-sample kernel above these ~6000 rows were 466 us of serial work.)
+constexpr int kCondRows = 64;
+__global__ void __launch_bounds__(256)
+cond_proj_kernel(const float* __restrict__ temb, int dim, const float* __restrict__ wc, const float* __restrict__ bc, int sumC,
+                 float* __restrict__ cond_all) {
+  extern __shared__ float gt[];          // [dim]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) gt[i] = cd_gelu(temb[b * dim + i]);
   __syncthreads();
-  // all blocks' conditioning rows: one warp per output row, lanes stride the (coalesced) weight row
-  {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int o = warp; o < sumC; o += nw) {
-      const float* wr = wc + static_cast<long long>(o) * dim;
-      float a = 0.f;
-      for (int i = lane; i < dim; i += 32) a = fmaf(wr[i], gt[i], a);
-      a = cd_warp_sum(a);
-      if (lane == 0) cond_all[static_cast<long long>(b) * sumC + o] = a + bc[o];
-    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int o0 = blockIdx.x * kCondRows;
+  const int o1 = o0 + kCondRows < sumC ? o0 + kCondRows : sumC;
+  for (int o = o0 + warp; o < o1; o += nw) {
+    const float* wr = wc + static_cast<long long>(o) * dim;
+    float a = 0.f;
+    for (int i = lane; i < dim; i += 32) a = fmaf(wr[i], gt[i], a);
+    a = cd_warp_sum(a);
+    if (lane == 0) cond_all[static_cast<long long>(b) * sumC + o] = a + bc[o];
   }
 }
 
@@ -513,13 +724,55 @@ extern "C" int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, c
   return 0;
 }
 
+// returns 1 when the shape is not eligible (caller falls back to dwconv7_wgrad_kernel in backward.cu)
+int cd_dwconv7_wgrad_pipe(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C, float* dw, cudaStream_t st);
+static int g_dw_pipe = 1;     // 1: persistent double-buffered depthwise kernels where eligible; 0: one tile per block
+extern "C" int cd_dwconv7_set_pipe(int enable) { g_dw_pipe = enable; return 0; }
+
+int cd_dwconv7_wgrad_pipe(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C, float* dw, cudaStream_t st) {
+  if (!g_dw_pipe || C % 32 != 0 || H % kDwPTY != 0 || W % kDwWTX != 0 || x_ld % 4 != 0 || dh_ld % 4 != 0 ||
+      (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(dh) & 15) != 0) return 1;
+  const size_t smem = sizeof(float) * 2 * 32 * (size_t(kDwPTY + 6) * (kDwWTX + 6) + size_t(kDwPTY) * kDwWTX);
+  static bool attr = false;
+  if (!attr) { CD_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  static int sms = 0;
+  if (!sms) { int dev = 0; CD_CUDA(cudaGetDevice(&dev)); CD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+  const long long total = static_cast<long long>(C / 32) * B * (H / kDwPTY) * (W / kDwWTX);
+  const int grid = total < sms ? static_cast<int>(total) : sms;
+  dwconv7_wgrad_pipe_kernel<<<grid, 32 * kDwPTY, smem, st>>>(dh, dh_ld, x, x_ld, B, H, W, C, dw);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int cd_dwconv7_fwd(const float* x, int x_ld, int B, int H, int W, int C, const float* w_dw, const float* b_dw,
                               const float* cond, int cond_ld, float* out, int out_ld, int flip, const float* addend,
                               int addend_ld, void* stream) {
+  if (C % 32 == 0 && H % kDwPTY == 0 && W % 16 == 0 && x_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && g_dw_pipe) {
+    const int TXp = W % 32 == 0 ? 32 : 16;
+    const size_t smem = sizeof(float) * 2 * 32 * size_t(kDwPTY + 6) * (TXp + 6);
+    static bool attr_p = false;
+    if (!attr_p) {
+      CD_CUDA(cudaFuncSetAttribute(dwconv7_pipe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 2 * 32 * (kDwPTY + 6) * 38)));
+      CD_CUDA(cudaFuncSetAttribute(dwconv7_pipe_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 2 * 32 * (kDwPTY + 6) * 22)));
+      attr_p = true;
+    }
+    static int sms = 0;
+    if (!sms) { int dev = 0; CD_CUDA(cudaGetDevice(&dev)); CD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+    const long long total = static_cast<long long>(C / 32) * B * (H / kDwPTY) * (W / TXp);
+    const int grid = total < sms ? static_cast<int>(total) : sms;
+    if (TXp == 32)
+      dwconv7_pipe_kernel<32><<<grid, 32 * kDwPTY, smem, static_cast<cudaStream_t>(stream)>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld,
+                                                                                            out, out_ld, flip, addend, addend_ld);
+    else
+      dwconv7_pipe_kernel<16><<<grid, 32 * kDwPTY, smem, static_cast<cudaStream_t>(stream)>>>(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld,
+                                                                                            out, out_ld, flip, addend, addend_ld);
+    CD_LAUNCH_CHECK();
+    return 0;
+  }
   int TX = W < 32 ? W : 32;
   int TY = H < kDwTY ? H : kDwTY;
   CD_REQUIRE(W % TX == 0 && H % TY == 0, "cd_dwconv7_fwd: unsupported image size %dx%d", H, W);
-  const size_t smem = sizeof(float) * 32 * size_t(TY + 6) * (TX + 6);
+  const size_t smem = sizeof(float) * 32 * (size_t(TY + 6) * (TX + 6) + 49);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) { CD_CUDA(cudaFuncSetAttribute(dwconv7_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   dim3 grid(cd_cdiv(C, 32), B * (H / TY) * (W / TX));
@@ -536,6 +789,10 @@ extern "C" int cd_time_mlp_fwd(const int64_t* t, int B, int dim, const float* w1
   time_mlp_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(t), dim, w1, b1, w2, b2,
                                                                      wc, bc, sumC, sinemb, hid_pre, temb, cond_all);
   CD_LAUNCH_CHECK();
+  if (sumC > 0) {
+    cond_proj_kernel<<<dim3(cd_cdiv(sumC, kCondRows), B), 256, sizeof(float) * dim, static_cast<cudaStream_t>(stream)>>>(temb, dim, wc, bc, sumC, cond_all);
+    CD_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -122,6 +122,8 @@ int cd_dwconv7_ln_fwd(const float* x, int x_ld, int B, int H, int W, int C,
 int cd_dwconv7_fwd(const float* x, int x_ld, int B, int H, int W, int C, const float* w_dw, const float* b_dw,
                    const float* cond, int cond_ld, float* out, int out_ld, int flip, const float* addend,
                    int addend_ld, void* stream);
+/* diagnostic switch: 1 (default) = persistent double-buffered depthwise kernel where eligible, 0 = one tile per block */
+int cd_dwconv7_set_pipe(int enable);
 /* channel LayerNorm alone (PreNorm in front of LinearAttention, DB:123-131; also the ConvNextBlock norm) */
 int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
                      float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream);

@@ -262,7 +262,10 @@ def test_baseline_config1_mnist_shape_train_step_vs_oracle():
 
 
 def test_cuda_graph_replay_of_the_sampling_forward(small):
-    """the inference forward captured once as a CUDA graph and replayed with new inputs equals the eager launches bit for bit"""
+    """the inference forward captured once as a CUDA graph and replayed with new inputs equals the eager launches.
+    Not bit for bit: the LinearAttention context is accumulated with float atomics (order varies run to run, and a one-ulp
+    change can flip a TF32 rounding downstream; tools/determinism_probe.py measures <= 3e-4 absolute), so the comparison
+    uses the TF32 tolerance of the other parity tests."""
     g, sd, u = small
     x = g['x'].cuda()
     with torch.no_grad():
@@ -273,7 +276,7 @@ def test_cuda_graph_replay_of_the_sampling_forward(small):
         finally:
             u.engine.enable_cuda_graph(False)
     for a, b in zip(eager, graphed):
-        assert torch.equal(a, b)
+        assert rel(a, b) < 1e-3
 
 
 def test_all_sample_gen_sample_consistency(small):
@@ -286,7 +289,9 @@ def test_all_sample_gen_sample_consistency(small):
     xt, dr, img = gd.sample(batch_size=2, img=x)
     X0, Xt = gd.all_sample(batch_size=2, img=x)
     assert len(X0) == 5 and len(Xt) == 4
-    assert torch.equal(Xt[0], xt) and torch.equal(X0[0], dr) and torch.equal(X0[-1], img)
+    # the degradation is deterministic; the Unet forward accumulates the attention context with float atomics, so two
+    # runs agree to the TF32 tolerance, not bit for bit (see test_cuda_graph_replay_of_the_sampling_forward)
+    assert torch.equal(Xt[0], xt) and rel(X0[0], dr) < 1e-3 and rel(X0[-1], img) < 2e-3
     xt2, dr2, img2 = gd.gen_sample(batch_size=2, img=x, noise_level=0)
-    assert torch.equal(img2, img)
+    assert rel(img2, img) < 2e-3
     assert torch.equal(gd.opt(x), xt)
