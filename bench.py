@@ -300,8 +300,16 @@ def main():
         eng.profile_convs = None
         tf32_peak = peaks['bf16_tflops_sustained'] / 2.0     # kind::tf32 runs at half the bf16 rate
         ach = tot_fl / (tot_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::tf32 implicit GEMM; fwd + dgrad launches)",
-                "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+        # DRAM bytes per launch of the same kernels from the committed ncu capture (profiles/conv_tc_traffic_r01.json)
+        traffic = None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'conv_tc_traffic_r01.json')) as f:
+                traffic = json.load(f)['dram_bytes_per_launch']
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel (tcgen05 kind::tf32 implicit GEMM; fwd + dgrad launches)",
+                "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (ncu capture of one step, profiles/launches_step_r01_final.csv)",
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 rate)" % peak_kind, "launches_timed": n_launch,
                 "share_of_step_ms": tot_ms / (ms / K)}
 
