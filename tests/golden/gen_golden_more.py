@@ -93,6 +93,30 @@ def main():
         out['F2:' + key], out['B1:' + key], out['B2:' + key], out['i1:' + key], out['i2:' + key] = stack(F2), stack(B1), stack(B2), i1, i2
     save('fb_small', x=x, **out)
 
+    # ---- DDPM-style `Model` (Model2.py): L1-loss gradients of every parameter (dropout inactive: eval mode) -----------
+    z = np.load(os.path.join(HERE, 'model2_small.npz'))
+    msd = {k[3:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd:')}
+    model = db.Model(resolution=16, in_channels=3, out_ch=3, ch=32, ch_mult=(1, 2), num_res_blocks=2, attn_resolutions=(8,),
+                     dropout=0.1).eval()
+    model.load_state_dict(msd)
+    xm, tm = torch.from_numpy(np.asarray(z['x'])), torch.from_numpy(np.asarray(z['t']))
+    torch.manual_seed(81)
+    target = torch.rand(3, 3, 16, 16) * 2 - 1
+    y = model(xm, tm)
+    loss = (target - y).abs().mean()
+    loss.backward()
+    grads = {}
+    for n, p_ in model.named_parameters():
+        g = p_.grad.reshape(-1)
+        if g.numel() <= 4096:
+            grads['grad:' + n] = p_.grad.clone()
+        else:
+            stride = g.numel() // 2048
+            grads['gsub:' + n] = g[::stride].clone()
+            grads['gnorm:' + n] = g.double().norm().float()
+    loss2 = ((target - y) ** 2).mean()
+    save('model2_grads_small', target=target, loss=loss.detach(), loss_l2=loss2.detach(), **grads)
+
 
 if __name__ == '__main__':
     main()

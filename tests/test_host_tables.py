@@ -1,0 +1,54 @@
+"""CPU checks of the host-side tables the product path builds (no kernels run): they must equal what the unmodified
+reference builds (tests/golden/*.npz), independently of the oracle."""
+import os
+import numpy as np
+import torch
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def load(name):
+    z = np.load(os.path.join(G, name + '.npz'))
+    return {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+
+
+def test_defading_generation_schedule_tables_match_reference():
+    from cold_diffusion_models_b200.defading_generation import get_kernels_with_schedule, get_reverse_kernels_with_schedule
+    g = load('defading_gen_small')
+    a = get_kernels_with_schedule(4, 32, 0.6, 3)
+    assert tuple(a.shape) == tuple(g['rev0:alphas'].shape) == (4, 1, 32, 32)
+    assert torch.allclose(a, g['rev0:alphas'], atol=1e-6) and torch.allclose(1. - a, g['rev0:one_minus_alphas'], atol=1e-6)
+    om = get_reverse_kernels_with_schedule(4, 32, 0.6, 3)
+    assert torch.allclose(om, g['rev1:one_minus_alphas'], atol=1e-6) and torch.allclose(1. - om, g['rev1:alphas'], atol=1e-6)
+    # the last reverse entry is the un-faded image (all ones), the first the product of the first T-1 kernels
+    assert torch.equal(om[-1], torch.ones(1, 32, 32))
+
+
+def test_cosine_schedule_of_the_demixing_package_matches_reference():
+    from cold_diffusion_models_b200.denoising import cosine_beta_schedule
+    g = load('denoise_small')
+    ac = torch.cumprod(1. - cosine_beta_schedule(5), axis=0)
+    assert torch.allclose(torch.sqrt(ac), g['sqrt_ac'], atol=1e-7) and torch.allclose(torch.sqrt(1. - ac), g['sqrt_1mac'], atol=1e-7)
+
+
+def test_package_exports_mirror_the_reference_inits():
+    import cold_diffusion_models_b200 as root
+    from cold_diffusion_models_b200 import (deblurring_diffusion_pytorch, denoising_diffusion_pytorch, resolution_diffusion_pytorch,
+                                            defading_diffusion_pytorch, defading_generation_diffusion_pytorch,
+                                            demixing_diffusion_pytorch, snowification_diffusion)
+    for pkg in (denoising_diffusion_pytorch, defading_generation_diffusion_pytorch, demixing_diffusion_pytorch):
+        assert set(pkg.__all__) == {'GaussianDiffusion', 'Unet', 'Trainer'}
+        for n in pkg.__all__:
+            assert hasattr(pkg, n)
+    for n in ('GaussianDiffusion', 'Unet', 'Trainer', 'Model'):
+        assert hasattr(deblurring_diffusion_pytorch, n) and hasattr(root, n)
+    # constructor keywords of the two-input packages (DM:311-322, DFGEN:348-361)
+    import inspect
+    kw = inspect.signature(demixing_diffusion_pytorch.GaussianDiffusion.__init__).parameters
+    assert list(kw)[1:] == ['denoise_fn', 'image_size', 'channels', 'timesteps', 'loss_type', 'train_routine', 'sampling_routine', 'discrete']
+    kw = inspect.signature(defading_generation_diffusion_pytorch.GaussianDiffusion.__init__).parameters
+    assert list(kw)[1:] == ['denoise_fn', 'image_size', 'channels', 'timesteps', 'loss_type', 'train_routine', 'sampling_routine',
+                            'reverse', 'kernel_std', 'initial_mask']
+    assert kw['kernel_std'].default == 0.15 and kw['initial_mask'].default == 11 and kw['reverse'].default is False
+    kw = inspect.signature(demixing_diffusion_pytorch.GaussianDiffusion.gen_sample).parameters
+    assert list(kw)[1:] == ['batch_size', 'img', 'noise_level', 't']

@@ -284,3 +284,28 @@ def test_deblur_cover_trajectories_match_reference():
         assert rel(torch.stack(F2), g['F2:' + key]) < 1e-5, key
         assert rel(torch.stack(B1), g['B1:' + key]) < 1e-4 and rel(torch.stack(B2), g['B2:' + key]) < 1e-4, key
         assert rel(i1, g['i1:' + key]) < 1e-4 and rel(i2, g['i2:' + key]) < 1e-4, key
+
+
+def test_model2_oracle_gradients_match_reference():
+    """autograd through the functional restatement of Model2.py reproduces every parameter gradient of the reference `Model`
+    (L1 loss, dropout inactive) -- the checker for the Model training path."""
+    import model2_oracle as MO
+    g = load('model2_small')
+    gg = load('model2_grads_small')
+    sd = {k[3:]: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in g.items() if k.startswith('sd:')}
+    y = MO.model_forward(sd, g['x'], g['t'], ch=32, num_resolutions=2, num_res_blocks=2)
+    loss = (gg['target'] - y).abs().mean()
+    assert abs(loss.item() - gg['loss'].item()) < 1e-6
+    loss.backward()
+    n = 0
+    for k, v in gg.items():
+        if k.startswith('grad:'):
+            assert rel(sd[k[5:]].grad, v) < 3e-5, k
+            n += 1
+        elif k.startswith('gsub:'):
+            gr = sd[k[5:]].grad.reshape(-1)
+            stride = gr.numel() // 2048
+            assert rel(gr[::stride], v) < 3e-5, k
+            assert abs(gr.double().norm().item() / gg['gnorm:' + k[5:]].item() - 1) < 1e-5, k
+            n += 1
+    assert n == sum(1 for v in sd.values() if v.requires_grad)
