@@ -6,8 +6,8 @@ Forward schedule (NHWC fp32): GroupNorm(32)+swish kernels (the time-embedding pr
 tcgen05 tap-list convolutions for conv1/conv2/nin_shortcut/q/k/v/proj_out/Downsample (asymmetric zero pad = TMA
 out-of-bounds fill) and for the two batched matmuls of AttnBlock (per-batch-weight 1x1 convolutions: k is already
 the [n][C] weight slab, v is transposed once), a row-softmax kernel, and channel-sliced concat buffers instead of
-torch.cat.  Training (backward of GroupNorm / softmax attention, dropout RNG) is a next-round row: calling the model
-with autograd enabled raises.
+torch.cat.  Training (backward of GroupNorm / softmax attention, dropout) lives in model2_train.py and is reachable only
+with COLDDIFF_MODEL_TRAINING=1 until it has been validated on a B200; otherwise calling the model with autograd enabled raises.
 """
 import ctypes as C
 import torch
@@ -147,8 +147,40 @@ class Model(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = ({} if k in ('_bufs', '_packed') else (None if k == '_version' else copy.deepcopy(v, memo)))
+            new.__dict__[k] = ({} if k in ('_bufs', '_packed') else (None if k in ('_version', '_engine', '_bwd_version') else copy.deepcopy(v, memo)))
         return new
+
+    @property
+    def engine(self):
+        """flat parameter / gradient buffers for Trainer + FusedAdamEMA (training path, model2_train.py)"""
+        if getattr(self, '_engine', None) is None:
+            from .model2_train import ModelEngine
+            self._engine = ModelEngine(self)
+        return self._engine
+
+    def _plan(self, B, H):
+        """concat-buffer plan of forward(): every skip tensor is written straight into the second channel slice of the concat
+        buffer of the up block that pops it (first slice = the running h).  -> {'cat_bufs': [(buffer, hin, skip_ch)], 'skip_view'}"""
+        up_blocks = [(lv, ib) for lv in reversed(range(self.num_resolutions)) for ib in range(self.num_res_blocks + 1)]
+        skip_ch, skip_res = [self.ch], [H]
+        res = H
+        for i_level in range(self.num_resolutions):
+            for b in self.down[i_level].block:
+                skip_ch.append(b.out_channels); skip_res.append(res)
+            if i_level != self.num_resolutions - 1:
+                skip_ch.append(skip_ch[-1]); res //= 2; skip_res.append(res)
+        nsk = len(skip_ch)
+        cat_bufs = []
+        for j, (lv, ib) in enumerate(up_blocks):
+            blk = self.up[lv].block[ib]
+            sk = nsk - 1 - j
+            r = skip_res[sk]
+            cat_bufs.append((self._buf('cat.%d' % j, (B, r, r, blk.in_channels)), blk.in_channels - skip_ch[sk], skip_ch[sk]))
+
+        def skip_view(sk):
+            buf, hin, sc = cat_bufs[nsk - 1 - sk]
+            return View(buf, hin, sc)
+        return dict(cat_bufs=cat_bufs, skip_view=skip_view)
 
     def _buf(self, name, shape):
         key = (name, tuple(shape))
@@ -269,7 +301,11 @@ class Model(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("cold_diffusion_models_b200.Model runs on a B200 (CUDA) device only; got %s" % x.device)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("Model (DDPM UNet) is inference/sampling-only in this round; wrap calls in torch.no_grad()")
+            from . import model2_train
+            if not model2_train.enabled():
+                raise NotImplementedError("Model (DDPM UNet) is inference/sampling-only in this round; wrap calls in torch.no_grad() "
+                                          "(the training path of model2_train.py is not validated on a B200 yet: COLDDIFF_MODEL_TRAINING=1)")
+            return model2_train.ModelFunction.apply(self, x, t, *self.engine.param_list())
         assert x.shape[2] == x.shape[3] == self.resolution
         self._prepare()
         P = self._packed

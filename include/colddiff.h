@@ -275,6 +275,28 @@ int cd_time_mlp2_fwd(const int64_t* t, int B, int dim, int hid, int tdim, int ac
 /* stand-alone EMA (DB:73-81): mode 1 copy, 2 lerp */
 int cd_ema_update(float* ema, const float* p, int64_t n, float beta, int mode, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-mode pieces of the DDPM-style `Model` (Model2.py, "M2"); wired behind COLDDIFF_MODEL_TRAINING=1.
+ *   cd_groupnorm_bwd         : backward of GroupNorm(32, eps 1e-6) [+ swish] (M2:32-33,116-125); x is the forward input, cond the
+ *                              per-sample channel offset added before the norm (temb_proj row, M2:121); accumulates dgamma / dbeta,
+ *                              writes dx and (optionally) dcond[b][c] = sum over pixels of dx
+ *   cd_dropout               : y = x * keep / (1 - p) with a counter-based mask of (seed, element index) -- the same call with the
+ *                              same seed on the gradient is the backward (M2:125; torch's RNG stream is not reproduced)
+ *   cd_softmax_bwd_rows      : ds <- s * (ds - sum_j ds*s) * scale for s = softmax(scale * logits) (M2:172-175)
+ *   cd_upsample_nearest2x_bwd: sum of the four children (M2:47-48)
+ *   cd_swish                 : act_out = swish(pre) and / or y = dy * swish'(pre) (M2:27-29)
+ *   cd_timestep_embedding    : get_timestep_embedding (M2:6-24);  cd_linear_fwd: y = x W^T + b (M2:295-299, temb_proj M2:121)
+ * ------------------------------------------------------------------------------------------ */
+int cd_groupnorm_bwd(const float* x, int x_ld, int B, int64_t HW, int C, int groups, const float* cond, int cond_ld,
+                     const float* gamma, const float* beta, float eps, int swish, const float* dy, int dy_ld,
+                     float* dx, int dx_ld, float* dgamma, float* dbeta, float* dcond, int dcond_ld, void* stream);
+int cd_dropout(const float* x, int x_ld, int64_t npix, int C, float p, uint64_t seed, float* y, int y_ld, void* stream);
+int cd_softmax_bwd_rows(const float* s, float* ds, int ld, int64_t rows, int n, float scale, void* stream);
+int cd_upsample_nearest2x_bwd(const float* dy, int dy_ld, int B, int H, int W, int C, float* dx, int dx_ld, void* stream);
+int cd_swish(const float* dy, const float* pre, int64_t n, float* y, float* act_out, void* stream);
+int cd_timestep_embedding(const int64_t* t, int B, int dim, float* emb, void* stream);
+int cd_linear_fwd(const float* x, int K, const float* w, const float* bias, int M, int N, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,331 @@
+"""TEST INFRASTRUCTURE: a CPU emulation of the libcolddiff entry points used by the DDPM-style `Model` (numpy on raw addresses,
+same argument lists as include/colddiff.h).  It lets the host-side schedules in cold_diffusion_models_b200/model2.py and
+model2_train.py (buffer planning, gradient routing, tap lists, packed-weight layouts) run on CPU tensors, so their LOGIC can be
+checked against the reference-generated goldens without a GPU.  It says nothing about the CUDA kernels themselves -- those are
+checked by the `-m gpu` tests through the real library.  Never imported by the product."""
+import ctypes as C
+import math
+import numpy as np
+
+
+def _v(a):
+    if isinstance(a, (int, float)):
+        return a
+    if hasattr(a, 'value'):
+        return 0 if a.value is None else a.value
+    return a
+
+
+def _arr(addr, shape, strides_elems):
+    """numpy view of float32 memory at `addr` with the given shape / element strides"""
+    addr = _v(addr)
+    if not addr:
+        return None
+    n = 1 + sum((s - 1) * st for s, st in zip(shape, strides_elems))
+    flat = np.ctypeslib.as_array((C.c_float * n).from_address(addr))
+    return np.lib.stride_tricks.as_strided(flat, shape=shape, strides=tuple(4 * st for st in strides_elems))
+
+
+def _rows(addr, rows, Cc, ld):
+    return _arr(addr, (rows, Cc), (ld, 1))
+
+
+def _nhwc(addr, B, H, W, Cc, ld):
+    return _arr(addr, (B, H, W, Cc), (H * W * ld, W * ld, ld, 1))
+
+
+def _i64(addr, n):
+    return np.ctypeslib.as_array((C.c_int64 * n).from_address(_v(addr)))
+
+
+def _swish(z):
+    return z / (1.0 + np.exp(-z))
+
+
+def _swish_grad(z):
+    s = 1.0 / (1.0 + np.exp(-z))
+    return s * (1.0 + z * (1.0 - s))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tap-list convolution (forward / data gradient) and its weight gradient
+# ------------------------------------------------------------------------------------------------------------------
+def _gather(src, B, Hg, Wg, sy, sx, dy, dx):
+    """src[b, gy*sy+dy, gx*sx+dx, :] with zero fill outside the image -> [B, Hg, Wg, C] (float64)"""
+    H, W = src.shape[1], src.shape[2]
+    out = np.zeros((B, Hg, Wg, src.shape[3]), dtype=np.float64)
+    iy = np.arange(Hg) * sy + dy
+    ix = np.arange(Wg) * sx + dx
+    vy = np.where((iy >= 0) & (iy < H))[0]
+    vx = np.where((ix >= 0) & (ix < W))[0]
+    if len(vy) and len(vx):
+        out[np.ix_(np.arange(B), vy, vx)] = src[np.ix_(np.arange(B), iy[vy], ix[vx])]
+    return out
+
+
+def cd_conv_fwd(desc, impl, stream):
+    d = desc._obj if hasattr(desc, '_obj') else desc
+    B, Hg, Wg = d.B, d.Hg, d.Wg
+    acc = np.zeros((B, Hg, Wg, d.Cout), dtype=np.float64)
+    for si in range(d.nsrc):
+        s = d.s[si]
+        src = _nhwc(s.src, B, s.H, s.W, s.C, s.ld)
+        if s.w_per_batch:
+            w = _arr(s.w, (B, s.ntaps, d.Cout, s.C), (s.ntaps * d.Cout * s.C, d.Cout * s.C, s.C, 1))
+        else:
+            w = _arr(s.w, (s.ntaps, d.Cout, s.C), (d.Cout * s.C, s.C, 1))
+        for t in range(s.ntaps):
+            g = _gather(src, B, Hg, Wg, d.sy, d.sx, s.dy[t], s.dx[t])
+            if s.w_per_batch:
+                acc += np.einsum('bhwc,boc->bhwo', g, w[:, t].astype(np.float64))
+            else:
+                acc += np.einsum('bhwc,oc->bhwo', g, w[t].astype(np.float64))
+    if d.bias:
+        acc += _arr(d.bias, (d.Cout,), (1,)).astype(np.float64)
+    out_full = _nhwc(d.out, B, d.Ho, d.Wo, d.Cout, d.out_ld)
+    ys = np.arange(Hg) * d.oys + d.oy0
+    xs = np.arange(Wg) * d.oxs + d.ox0
+    sel = np.ix_(np.arange(B), ys, xs)
+    if d.resid:
+        acc += _nhwc(d.resid, B, d.Ho, d.Wo, d.Cout, d.resid_ld)[sel].astype(np.float64)
+    assert d.act == 0 and not d.out2, "emulator: activation / out2 epilogues are not used by Model"
+    out_full[sel] = acc.astype(np.float32)
+    return 0
+
+
+def cd_conv_wgrad(desc, dout, dout_ld, dw, db, impl, stream):
+    d = desc._obj if hasattr(desc, '_obj') else desc
+    B, Hg, Wg = d.B, d.Hg, d.Wg
+    s = d.s[0]
+    src = _nhwc(s.src, B, s.H, s.W, s.C, s.ld)
+    dy_full = _nhwc(dout, B, d.Ho, d.Wo, d.Cout, _v(dout_ld))
+    ys = np.arange(Hg) * d.oys + d.oy0
+    xs = np.arange(Wg) * d.oxs + d.ox0
+    dy = dy_full[np.ix_(np.arange(B), ys, xs)].astype(np.float64)
+    if s.w_per_batch:
+        w = _arr(dw, (B, s.ntaps, d.Cout, s.C), (s.ntaps * d.Cout * s.C, d.Cout * s.C, s.C, 1))
+    else:
+        w = _arr(dw, (s.ntaps, d.Cout, s.C), (d.Cout * s.C, s.C, 1))
+    for t in range(s.ntaps):
+        g = _gather(src, B, Hg, Wg, d.sy, d.sx, s.dy[t], s.dx[t])
+        if s.w_per_batch:
+            w[:, t] += np.einsum('bhwo,bhwc->boc', dy, g).astype(np.float32)
+        else:
+            w[t] += np.einsum('bhwo,bhwc->oc', dy, g).astype(np.float32)
+    if _v(db):
+        _arr(db, (d.Cout,), (1,))[:] += dy.sum(axis=(0, 1, 2)).astype(np.float32)
+    return 0
+
+
+def cd_pack_weight(w, O, I, KH, KW, transposed_conv, mode, ky, kx, ntaps, round_tf32, packed, stream):
+    if transposed_conv:
+        W = _arr(w, (I, O, KH, KW), (O * KH * KW, KH * KW, KW, 1)).transpose(1, 0, 2, 3)      # -> [o][i][ky][kx]
+    else:
+        W = _arr(w, (O, I, KH, KW), (I * KH * KW, KH * KW, KW, 1))
+    N, K = (O, I) if mode == 0 else (I, O)
+    P = _arr(packed, (ntaps, N, K), (N * K, K, 1))
+    for t in range(ntaps):
+        m = W[:, :, ky[t], kx[t]]
+        P[t] = m if mode == 0 else m.T
+    return 0
+
+
+def cd_unpack_wgrad(packed, O, I, KH, KW, transposed_conv, ky, kx, ntaps, w_grad, accumulate, stream):
+    assert not transposed_conv
+    P = _arr(packed, (ntaps, O, I), (O * I, I, 1))
+    G = _arr(w_grad, (O, I, KH, KW), (I * KH * KW, KH * KW, KW, 1))
+    for t in range(ntaps):
+        if accumulate:
+            G[:, :, ky[t], kx[t]] += P[t]
+        else:
+            G[:, :, ky[t], kx[t]] = P[t]
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GroupNorm, dropout, softmax, resampling, small dense pieces
+# ------------------------------------------------------------------------------------------------------------------
+def _gn_stats(x, B, HW, Cc, groups, eps):
+    xg = x.reshape(B, HW, groups, Cc // groups)
+    mean = xg.mean(axis=(1, 3), keepdims=True)
+    var = xg.var(axis=(1, 3), keepdims=True)
+    return xg, mean, 1.0 / np.sqrt(var + eps)
+
+
+def cd_groupnorm_fwd(x, x_ld, B, HW, Cc, groups, cond, cond_ld, gamma, beta, eps, swish, y, y_ld, stream):
+    HW = _v(HW); eps = _v(eps)
+    X = _arr(x, (B, HW, Cc), (HW * x_ld, x_ld, 1)).astype(np.float64)
+    if _v(cond):
+        X = X + _arr(cond, (B, Cc), (cond_ld, 1)).astype(np.float64)[:, None, :]
+    xg, mean, rstd = _gn_stats(X, B, HW, Cc, groups, eps)
+    xh = ((xg - mean) * rstd).reshape(B, HW, Cc)
+    z = xh * _arr(gamma, (Cc,), (1,)).astype(np.float64) + _arr(beta, (Cc,), (1,)).astype(np.float64)
+    _arr(y, (B, HW, Cc), (HW * y_ld, y_ld, 1))[:] = (_swish(z) if swish else z).astype(np.float32)
+    return 0
+
+
+def cd_groupnorm_bwd(x, x_ld, B, HW, Cc, groups, cond, cond_ld, gamma, beta, eps, swish, dy, dy_ld, dx, dx_ld, dgamma, dbeta,
+                     dcond, dcond_ld, stream):
+    HW = _v(HW); eps = _v(eps)
+    X = _arr(x, (B, HW, Cc), (HW * x_ld, x_ld, 1)).astype(np.float64)
+    if _v(cond):
+        X = X + _arr(cond, (B, Cc), (cond_ld, 1)).astype(np.float64)[:, None, :]
+    g = _arr(gamma, (Cc,), (1,)).astype(np.float64); bt = _arr(beta, (Cc,), (1,)).astype(np.float64)
+    xg, mean, rstd = _gn_stats(X, B, HW, Cc, groups, eps)
+    xh = ((xg - mean) * rstd).reshape(B, HW, Cc)
+    DY = _arr(dy, (B, HW, Cc), (HW * dy_ld, dy_ld, 1)).astype(np.float64)
+    dz = DY * _swish_grad(xh * g + bt) if swish else DY
+    _arr(dgamma, (Cc,), (1,))[:] += (dz * xh).sum(axis=(0, 1)).astype(np.float32)
+    _arr(dbeta, (Cc,), (1,))[:] += dz.sum(axis=(0, 1)).astype(np.float32)
+    dxh = (dz * g).reshape(B, HW, groups, Cc // groups)
+    xhg = xh.reshape(B, HW, groups, Cc // groups)
+    ma = dxh.mean(axis=(1, 3), keepdims=True)
+    mb = (dxh * xhg).mean(axis=(1, 3), keepdims=True)
+    DX = (rstd * (dxh - ma - xhg * mb)).reshape(B, HW, Cc)
+    _arr(dx, (B, HW, Cc), (HW * dx_ld, dx_ld, 1))[:] = DX.astype(np.float32)
+    if _v(dcond):
+        _arr(dcond, (B, Cc), (dcond_ld, 1))[:] = DX.sum(axis=1).astype(np.float32)
+    return 0
+
+
+def _uniform01(seed, idx):
+    with np.errstate(over='ignore'):
+        h = np.uint64(seed) ^ (idx.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        h ^= h >> np.uint64(33); h *= np.uint64(0xff51afd7ed558ccd); h ^= h >> np.uint64(33)
+        h *= np.uint64(0xc4ceb9fe1a85ec53); h ^= h >> np.uint64(33)
+    return (h >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def cd_dropout(x, x_ld, npix, Cc, p, seed, y, y_ld, stream):
+    npix, p, seed = _v(npix), np.float32(_v(p)), _v(seed)
+    X = _rows(x, npix, Cc, x_ld).copy()
+    keep = (_uniform01(seed, np.arange(npix * Cc)) >= p).reshape(npix, Cc)
+    _rows(y, npix, Cc, y_ld)[:] = X * keep * np.float32(1.0 / (1.0 - p))
+    return 0
+
+
+def cd_softmax_rows(s, ld, rows, n, scale, stream):
+    S = _rows(s, _v(rows), n, ld)
+    z = S.astype(np.float64) * _v(scale)
+    z = np.exp(z - z.max(axis=1, keepdims=True))
+    S[:] = (z / z.sum(axis=1, keepdims=True)).astype(np.float32)
+    return 0
+
+
+def cd_softmax_bwd_rows(s, ds, ld, rows, n, scale, stream):
+    S = _rows(s, _v(rows), n, ld).astype(np.float64)
+    D = _rows(ds, _v(rows), n, ld)
+    d = D.astype(np.float64)
+    D[:] = (S * (d - (d * S).sum(axis=1, keepdims=True)) * _v(scale)).astype(np.float32)
+    return 0
+
+
+def cd_transpose_batched(src, ld, B, R, Cc, dst, stream):
+    A = _arr(src, (B, R, Cc), (R * ld, ld, 1))
+    _arr(dst, (B, Cc, R), (Cc * R, R, 1))[:] = A.transpose(0, 2, 1)
+    return 0
+
+
+def cd_upsample_nearest2x(x, x_ld, B, H, W, Cc, y, y_ld, stream):
+    X = _nhwc(x, B, H, W, Cc, x_ld)
+    _nhwc(y, B, 2 * H, 2 * W, Cc, y_ld)[:] = X.repeat(2, axis=1).repeat(2, axis=2)
+    return 0
+
+
+def cd_upsample_nearest2x_bwd(dy, dy_ld, B, H, W, Cc, dx, dx_ld, stream):
+    D = _nhwc(dy, B, 2 * H, 2 * W, Cc, dy_ld).astype(np.float64)
+    _nhwc(dx, B, H, W, Cc, dx_ld)[:] = (D[:, 0::2, 0::2] + D[:, 0::2, 1::2] + D[:, 1::2, 0::2] + D[:, 1::2, 1::2]).astype(np.float32)
+    return 0
+
+
+def cd_add(a, a_ld, b, b_ld, out, out_ld, npix, Cc, stream):
+    npix = _v(npix)
+    res = _rows(a, npix, Cc, a_ld) + _rows(b, npix, Cc, b_ld)
+    _rows(out, npix, Cc, out_ld)[:] = res
+    return 0
+
+
+def cd_colsum(x, ld, rows, Cc, out, stream):
+    _arr(out, (Cc,), (1,))[:] += _rows(x, _v(rows), Cc, ld).astype(np.float64).sum(axis=0).astype(np.float32)
+    return 0
+
+
+def cd_small_gemm(A, lda, transA, Bm, ldb, transB, Cm, ldc, M, N, K, accumulate, stream):
+    a = _arr(A, (K, M), (lda, 1)).T if transA else _arr(A, (M, K), (lda, 1))
+    b = _arr(Bm, (N, K), (ldb, 1)).T if transB else _arr(Bm, (K, N), (ldb, 1))
+    c = _arr(Cm, (M, N), (ldc, 1))
+    r = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+    c[:] = c + r if accumulate else r
+    return 0
+
+
+def cd_swish(dy, pre, n, y, act_out, stream):
+    n = _v(n)
+    p = _arr(pre, (n,), (1,)).astype(np.float64)
+    if _v(act_out):
+        _arr(act_out, (n,), (1,))[:] = _swish(p).astype(np.float32)
+    if _v(y):
+        _arr(y, (n,), (1,))[:] = (_arr(dy, (n,), (1,)).astype(np.float64) * _swish_grad(p)).astype(np.float32)
+    return 0
+
+
+def cd_timestep_embedding(t, B, dim, emb, stream):
+    tt = _i64(t, B).astype(np.float32)
+    half = dim // 2
+    f = np.exp(np.arange(half, dtype=np.float32) * np.float32(-(math.log(10000) / (half - 1))))
+    a = tt[:, None] * f[None, :]
+    E = _arr(emb, (B, dim), (dim, 1))
+    E[:, :half] = np.sin(a); E[:, half:2 * half] = np.cos(a)
+    if dim % 2:
+        E[:, -1] = 0
+    return 0
+
+
+def cd_linear_fwd(x, K, w, bias, M, N, y, stream):
+    r = _arr(x, (M, K), (K, 1)).astype(np.float64) @ _arr(w, (N, K), (K, 1)).astype(np.float64).T
+    if _v(bias):
+        r = r + _arr(bias, (N,), (1,)).astype(np.float64)
+    _arr(y, (M, N), (N, 1))[:] = r.astype(np.float32)
+    return 0
+
+
+def cd_nchw_to_nhwc(x, B, Cc, H, W, out, ld, stream):
+    X = _arr(x, (B, Cc, H, W), (Cc * H * W, H * W, W, 1))
+    O = _nhwc(out, B, H, W, ld, ld)
+    O[:] = 0
+    O[..., :Cc] = X.transpose(0, 2, 3, 1)
+    return 0
+
+
+def cd_nhwc_to_nchw(x, ld, B, H, W, Cc, out, stream):
+    _arr(out, (B, Cc, H, W), (Cc * H * W, H * W, W, 1))[:] = _nhwc(x, B, H, W, Cc, ld).transpose(0, 3, 1, 2)
+    return 0
+
+
+_TABLE = {k: v for k, v in globals().items() if k.startswith('cd_')}
+
+
+def call(name, *args):
+    fn = _TABLE.get(name)
+    if fn is None:
+        raise NotImplementedError("abi_emulator: %s is not emulated" % name)
+    rc = fn(*args)
+    assert rc == 0
+
+
+class patched:
+    """context manager: route the host modules' `call` / `stream` to the emulator (CPU tensors)"""
+
+    def __enter__(self):
+        from cold_diffusion_models_b200 import ops, model2, model2_train
+        self._mods = (ops, model2, model2_train)
+        self._saved = [(m, m.call, m.stream) for m in self._mods]
+        for m in self._mods:
+            m.call = call
+            m.stream = lambda: None
+        return self
+
+    def __exit__(self, *exc):
+        for m, c, s in self._saved:
+            m.call, m.stream = c, s
+        return False
