@@ -38,6 +38,16 @@ def _i64(addr, n):
     return np.ctypeslib.as_array((C.c_int64 * n).from_address(_v(addr)))
 
 
+def _gelu(x):
+    from scipy.special import erf
+    return 0.5 * x * (1.0 + erf(x / math.sqrt(2.0)))
+
+
+def _gelu_grad(x):
+    from scipy.special import erf
+    return 0.5 * (1.0 + erf(x / math.sqrt(2.0))) + x * np.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi)
+
+
 def _swish(z):
     return z / (1.0 + np.exp(-z))
 
@@ -88,7 +98,12 @@ def cd_conv_fwd(desc, impl, stream):
     sel = np.ix_(np.arange(B), ys, xs)
     if d.resid:
         acc += _nhwc(d.resid, B, d.Ho, d.Wo, d.Cout, d.resid_ld)[sel].astype(np.float64)
-    assert d.act == 0 and not d.out2, "emulator: activation / out2 epilogues are not used by Model"
+    if d.out2:
+        _nhwc(d.out2, B, d.Ho, d.Wo, d.Cout, d.out2_ld)[sel] = acc.astype(np.float32)       # pre-activation, kept for the backward
+    if d.act == 1:                                          # CD_ACT_GELU
+        acc = _gelu(acc)
+    elif d.act == 2:                                        # CD_ACT_GELU_BWD: multiply by gelu'(saved pre-activation)
+        acc = acc * _gelu_grad(_nhwc(d.aux, B, d.Ho, d.Wo, d.Cout, d.aux_ld)[sel].astype(np.float64))
     out_full[sel] = acc.astype(np.float32)
     return 0
 
@@ -131,9 +146,11 @@ def cd_pack_weight(w, O, I, KH, KW, transposed_conv, mode, ky, kx, ntaps, round_
 
 
 def cd_unpack_wgrad(packed, O, I, KH, KW, transposed_conv, ky, kx, ntaps, w_grad, accumulate, stream):
-    assert not transposed_conv
     P = _arr(packed, (ntaps, O, I), (O * I, I, 1))
-    G = _arr(w_grad, (O, I, KH, KW), (I * KH * KW, KH * KW, KW, 1))
+    if transposed_conv:                                     # nn.ConvTranspose2d stores (I, O, KH, KW)
+        G = _arr(w_grad, (I, O, KH, KW), (O * KH * KW, KH * KW, KW, 1)).transpose(1, 0, 2, 3)
+    else:
+        G = _arr(w_grad, (O, I, KH, KW), (I * KH * KW, KH * KW, KW, 1))
     for t in range(ntaps):
         if accumulate:
             G[:, :, ky[t], kx[t]] += P[t]
@@ -302,6 +319,247 @@ def cd_nhwc_to_nchw(x, ld, B, H, W, Cc, out, stream):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# ConvNeXt Unet entry points (engine.py / engine_bwd.py)
+# ------------------------------------------------------------------------------------------------------------------
+def cd_time_mlp_fwd(t, B, dim, w1, b1, w2, b2, wc, bc, sumC, sinemb, hid_pre, temb, cond_all, stream):
+    tt = _i64(t, B).astype(np.float64)
+    half = dim // 2
+    f = np.exp(-(math.log(10000.0) / (half - 1)) * np.arange(half))
+    emb = np.concatenate([np.sin(tt[:, None] * f), np.cos(tt[:, None] * f)], axis=1)
+    if _v(sinemb):
+        _arr(sinemb, (B, dim), (dim, 1))[:] = emb.astype(np.float32)
+    hp = emb @ _arr(w1, (4 * dim, dim), (dim, 1)).astype(np.float64).T + _arr(b1, (4 * dim,), (1,))
+    if _v(hid_pre):
+        _arr(hid_pre, (B, 4 * dim), (4 * dim, 1))[:] = hp.astype(np.float32)
+    te = _gelu(hp) @ _arr(w2, (dim, 4 * dim), (4 * dim, 1)).astype(np.float64).T + _arr(b2, (dim,), (1,))
+    _arr(temb, (B, dim), (dim, 1))[:] = te.astype(np.float32)
+    if sumC > 0:
+        ca = _gelu(te) @ _arr(wc, (sumC, dim), (dim, 1)).astype(np.float64).T + _arr(bc, (sumC,), (1,))
+        _arr(cond_all, (B, sumC), (sumC, 1))[:] = ca.astype(np.float32)
+    return 0
+
+
+def _dwconv7(x, x_ld, B, H, W, Cc, w_dw, b_dw, cond, cond_ld, flip, addend, addend_ld):
+    X = _nhwc(x, B, H, W, Cc, x_ld)
+    Wd = _arr(w_dw, (Cc, 49), (49, 1)).astype(np.float64)
+    h = np.zeros((B, H, W, Cc), dtype=np.float64)
+    for k in range(49):
+        ky, kx = k // 7, k % 7
+        h += _gather(X, B, H, W, 1, 1, ky - 3, kx - 3) * Wd[:, 48 - k if flip else k]
+    if _v(b_dw):
+        h += _arr(b_dw, (Cc,), (1,)).astype(np.float64)
+    if _v(cond):
+        h += _arr(cond, (B, Cc), (cond_ld, 1)).astype(np.float64)[:, None, None, :]
+    if _v(addend):
+        h += _nhwc(addend, B, H, W, Cc, addend_ld).astype(np.float64)
+    return h
+
+
+def cd_dwconv7_fwd(x, x_ld, B, H, W, Cc, w_dw, b_dw, cond, cond_ld, out, out_ld, flip, addend, addend_ld, stream):
+    _nhwc(out, B, H, W, Cc, out_ld)[:] = _dwconv7(x, x_ld, B, H, W, Cc, w_dw, b_dw, cond, cond_ld, flip, addend, addend_ld).astype(np.float32)
+    return 0
+
+
+def _ln(h, g, beta, eps):
+    mean = h.mean(axis=-1, keepdims=True)
+    rstd = 1.0 / np.sqrt(h.var(axis=-1, keepdims=True) + eps)
+    return (h - mean) * rstd * g + beta, mean, rstd
+
+
+def cd_dwconv7_ln_fwd(x, x_ld, B, H, W, Cc, w_dw, b_dw, cond, cond_ld, g, beta, eps, y, y_ld, stats, hpre, hpre_ld, round_tf32, flip,
+                      addend, addend_ld, stream):
+    h = _dwconv7(x, x_ld, B, H, W, Cc, w_dw, b_dw, cond, cond_ld, flip, addend, addend_ld)
+    if _v(hpre):
+        _nhwc(hpre, B, H, W, Cc, hpre_ld)[:] = h.astype(np.float32)
+    if _v(g):
+        o, mean, rstd = _ln(h, _arr(g, (Cc,), (1,)).astype(np.float64), _arr(beta, (Cc,), (1,)).astype(np.float64), _v(eps))
+        if _v(stats):
+            st = _arr(stats, (B * H * W, 2), (2, 1))
+            st[:, 0] = mean.reshape(-1); st[:, 1] = rstd.reshape(-1)
+    else:
+        o = h
+    _nhwc(y, B, H, W, Cc, y_ld)[:] = o.astype(np.float32)
+    return 0
+
+
+def cd_layernorm_fwd(x, x_ld, npix, Cc, g, beta, eps, y, y_ld, stats, round_tf32, stream):
+    npix = _v(npix)
+    o, mean, rstd = _ln(_rows(x, npix, Cc, x_ld).astype(np.float64), _arr(g, (Cc,), (1,)).astype(np.float64),
+                        _arr(beta, (Cc,), (1,)).astype(np.float64), _v(eps))
+    if _v(stats):
+        st = _arr(stats, (npix, 2), (2, 1))
+        st[:, 0] = mean.reshape(-1); st[:, 1] = rstd.reshape(-1)
+    _rows(y, npix, Cc, y_ld)[:] = o.astype(np.float32)
+    return 0
+
+
+def cd_layernorm_bwd(dy, dy_ld, h, h_ld, stats, g, npix, Cc, addend, addend_ld, dh, dh_ld, dg, dbeta, stream):
+    npix = _v(npix)
+    st = _arr(stats, (npix, 2), (2, 1)).astype(np.float64)
+    xh = (_rows(h, npix, Cc, h_ld).astype(np.float64) - st[:, :1]) * st[:, 1:]
+    DY = _rows(dy, npix, Cc, dy_ld).astype(np.float64)
+    _arr(dg, (Cc,), (1,))[:] += (DY * xh).sum(axis=0).astype(np.float32)
+    _arr(dbeta, (Cc,), (1,))[:] += DY.sum(axis=0).astype(np.float32)
+    dv = DY * _arr(g, (Cc,), (1,)).astype(np.float64)
+    o = st[:, 1:] * (dv - dv.mean(axis=1, keepdims=True) - xh * (dv * xh).mean(axis=1, keepdims=True))
+    if _v(addend):
+        o = o + _rows(addend, npix, Cc, addend_ld).astype(np.float64)
+    _rows(dh, npix, Cc, dh_ld)[:] = o.astype(np.float32)
+    return 0
+
+
+def cd_linattn_context(qkv, ld, B, n, kmax, ksum, ctx, stream):
+    Q = _arr(qkv, (B, n, 384), (n * ld, ld, 1)).astype(np.float64)
+    k, v = Q[..., 128:256], Q[..., 256:384]
+    km = k.max(axis=1)
+    e = np.exp(k - km[:, None, :])
+    _arr(kmax, (B, 128), (128, 1))[:] = km.astype(np.float32)
+    _arr(ksum, (B, 128), (128, 1))[:] = e.sum(axis=1).astype(np.float32)
+    c = np.einsum('bnhd,bnhe->bhde', e.reshape(B, n, 4, 32), v.reshape(B, n, 4, 32))
+    _arr(ctx, (B, 4, 32, 32), (4096, 1024, 32, 1))[:] = c.astype(np.float32)
+    return 0
+
+
+def cd_linattn_weff(ctx, ksum, w_out, B, dim, scale, round_tf32, weff, stream):
+    c = _arr(ctx, (B, 4, 32, 32), (4096, 1024, 32, 1)).astype(np.float64)
+    ks = _arr(ksum, (B, 4, 32), (128, 32, 1)).astype(np.float64)
+    wo = _arr(w_out, (dim, 4, 32), (128, 32, 1)).astype(np.float64)
+    cn = c * _v(scale) / ks[..., None]
+    _arr(weff, (B, dim, 4, 32), (dim * 128, 128, 32, 1))[:] = np.einsum('ohe,bhde->bohd', wo, cn).astype(np.float32)
+    return 0
+
+
+def cd_conv1x1_to_nchw(x, ld, B, H, W, Cc, w, b, Co, resid_nchw, out_nchw, stream):
+    X = _arr(x, (B, H * W, Cc), (H * W * ld, ld, 1)).astype(np.float64)
+    o = np.einsum('bpc,oc->bop', X, _arr(w, (Co, Cc), (Cc, 1)).astype(np.float64))
+    if _v(b):
+        o += _arr(b, (Co,), (1,)).astype(np.float64)[None, :, None]
+    if _v(resid_nchw):
+        o += _arr(resid_nchw, (B, Co, H * W), (Co * H * W, H * W, 1)).astype(np.float64)
+    _arr(out_nchw, (B, Co, H * W), (Co * H * W, H * W, 1))[:] = o.astype(np.float32)
+    return 0
+
+
+def cd_conv1x1_to_nchw_bwd(dout_nchw, x, ld, B, H, W, Cc, w, Co, dx, dx_ld, dw, db, stream):
+    D = _arr(dout_nchw, (B, Co, H * W), (Co * H * W, H * W, 1)).astype(np.float64)
+    X = _arr(x, (B, H * W, Cc), (H * W * ld, ld, 1)).astype(np.float64)
+    _arr(dx, (B, H * W, Cc), (H * W * dx_ld, dx_ld, 1))[:] = np.einsum('bop,oc->bpc', D, _arr(w, (Co, Cc), (Cc, 1)).astype(np.float64)).astype(np.float32)
+    _arr(dw, (Co, Cc), (Cc, 1))[:] += np.einsum('bop,bpc->oc', D, X).astype(np.float32)
+    _arr(db, (Co,), (1,))[:] += D.sum(axis=(0, 2)).astype(np.float32)
+    return 0
+
+
+def cd_dwconv7_wgrad(dh, dh_ld, x, x_ld, B, H, W, Cc, dw, stream):
+    D = _nhwc(dh, B, H, W, Cc, dh_ld).astype(np.float64)
+    X = _nhwc(x, B, H, W, Cc, x_ld)
+    G = _arr(dw, (Cc, 49), (49, 1))
+    for k in range(49):
+        G[:, k] += (D * _gather(X, B, H, W, 1, 1, k // 7 - 3, k % 7 - 3)).sum(axis=(0, 1, 2)).astype(np.float32)
+    return 0
+
+
+def cd_colsum_batched(x, ld, B, rows, Cc, out, out_ld, stream):
+    rows = _v(rows)
+    _arr(out, (B, Cc), (out_ld, 1))[:] += _arr(x, (B, rows, Cc), (rows * ld, ld, 1)).astype(np.float64).sum(axis=1).astype(np.float32)
+    return 0
+
+
+def cd_linattn_bwd_small(dweff, ctx, ksum, w_out, B, dim, scale, dw_out, dctxn, rowdot, stream):
+    scale = _v(scale)
+    dwe = _arr(dweff, (B, dim, 4, 32), (dim * 128, 128, 32, 1)).astype(np.float64)
+    c = _arr(ctx, (B, 4, 32, 32), (4096, 1024, 32, 1)).astype(np.float64)
+    ks = _arr(ksum, (B, 4, 32), (128, 32, 1)).astype(np.float64)
+    wo = _arr(w_out, (dim, 4, 32), (128, 32, 1)).astype(np.float64)
+    cn = c / ks[..., None]
+    _arr(dw_out, (dim, 4, 32), (128, 32, 1))[:] += (scale * np.einsum('bohd,bhde->ohe', dwe, cn)).astype(np.float32)
+    dc = scale * np.einsum('bohd,ohe->bhde', dwe, wo)
+    _arr(dctxn, (B, 4, 32, 32), (4096, 1024, 32, 1))[:] = dc.astype(np.float32)
+    _arr(rowdot, (B, 4, 32), (128, 32, 1))[:] = (dc * cn).sum(axis=-1).astype(np.float32)
+    return 0
+
+
+def cd_linattn_bwd_kv(qkv, ld, B, n, kmax, ksum, dctxn, rowdot, dqkv, dld, stream):
+    Q = _arr(qkv, (B, n, 384), (n * ld, ld, 1)).astype(np.float64)
+    k, v = Q[..., 128:256].reshape(B, n, 4, 32), Q[..., 256:384].reshape(B, n, 4, 32)
+    km = _arr(kmax, (B, 4, 32), (128, 32, 1)).astype(np.float64)
+    ks = _arr(ksum, (B, 4, 32), (128, 32, 1)).astype(np.float64)
+    dc = _arr(dctxn, (B, 4, 32, 32), (4096, 1024, 32, 1)).astype(np.float64)
+    rd = _arr(rowdot, (B, 4, 32), (128, 32, 1)).astype(np.float64)
+    P = np.exp(k - km[:, None]) / ks[:, None]
+    dk = P * (np.einsum('bhde,bnhe->bnhd', dc, v) - rd[:, None])
+    dv = np.einsum('bnhd,bhde->bnhe', P, dc)
+    D = _arr(dqkv, (B, n, 384), (n * dld, dld, 1))
+    D[..., 128:256] = dk.reshape(B, n, 128).astype(np.float32)
+    D[..., 256:384] = dv.reshape(B, n, 128).astype(np.float32)
+    return 0
+
+
+def cd_transpose_weff(weff, B, dim, weff_t, stream):
+    _arr(weff_t, (B, 128, dim), (128 * dim, dim, 1))[:] = _arr(weff, (B, dim, 128), (dim * 128, 128, 1)).transpose(0, 2, 1)
+    return 0
+
+
+def cd_gelu_bwd(dy, pre, n, y, act_out, stream):
+    n = _v(n)
+    p = _arr(pre, (n,), (1,)).astype(np.float64)
+    if _v(act_out):
+        _arr(act_out, (n,), (1,))[:] = _gelu(p).astype(np.float32)
+    if _v(y):
+        _arr(y, (n,), (1,))[:] = (_arr(dy, (n,), (1,)).astype(np.float64) * _gelu_grad(p)).astype(np.float32)
+    return 0
+
+
+def cd_loss_fwd_bwd(x0, xhat, n, mode, grad_scale, loss, dxhat, stream):
+    n = _v(n)
+    d = _arr(xhat, (n,), (1,)).astype(np.float64) - _arr(x0, (n,), (1,)).astype(np.float64)
+    L = _arr(loss, (1,), (1,))
+    if mode == 0:
+        L[0] += np.float32(np.abs(d).mean())
+        g = np.sign(d) / n
+    else:
+        L[0] += np.float32((d * d).mean())
+        g = 2.0 * d / n
+    if _v(dxhat):
+        _arr(dxhat, (n,), (1,))[:] = (g * _v(grad_scale)).astype(np.float32)
+    return 0
+
+
+def cd_blur_apply(x, out, ops_, t, t_scalar, B, Cc, S, T, collapse_last, quantize, stream):
+    X = _arr(x, (B, Cc, S, S), (Cc * S * S, S * S, S, 1)).astype(np.float64)
+    A = _arr(ops_, (T, S, S), (S * S, S, 1)).astype(np.float64)
+    O = _arr(out, (B, Cc, S, S), (Cc * S * S, S * S, S, 1))
+    tt = _i64(t, B) if _v(t) else [t_scalar] * B
+    assert not collapse_last and not quantize, "emulator: `discrete` options are not emulated"
+    for b in range(B):
+        ti = int(tt[b])
+        O[b] = X[b].astype(np.float32) if ti < 0 else np.einsum('ij,cjk,lk->cil', A[ti], X[b], A[ti]).astype(np.float32)
+    return 0
+
+
+def cd_adam_ema_step(p, g, m, v, ema, n, lr, beta1, beta2, eps, step, ema_mode, ema_beta, grad_scale, stream):
+    n = _v(n); lr, b1, b2, eps, eb, gs = (np.float32(_v(a)) for a in (lr, beta1, beta2, eps, ema_beta, grad_scale))
+    P, Gr, M, V = (_arr(a, (n,), (1,)) for a in (p, g, m, v))
+    gi = Gr * gs
+    M[:] = b1 * M + (np.float32(1) - b1) * gi
+    V[:] = b2 * V + (np.float32(1) - b2) * gi * gi
+    bc1 = np.float32(1.0 - float(b1) ** step); bc2s = np.float32(math.sqrt(1.0 - float(b2) ** step))
+    P[:] = P - (lr / bc1) * (M / (np.sqrt(V) / bc2s + eps))
+    if ema_mode == 1:
+        _arr(ema, (n,), (1,))[:] = P
+    elif ema_mode == 2:
+        E = _arr(ema, (n,), (1,))
+        E[:] = E * eb + (np.float32(1) - eb) * P
+    return 0
+
+
+def cd_ema_update(ema, p, n, beta, mode, stream):
+    n = _v(n); b = np.float32(_v(beta))
+    E, P = _arr(ema, (n,), (1,)), _arr(p, (n,), (1,))
+    E[:] = P if mode == 1 else E * b + (np.float32(1) - b) * P
+    return 0
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith('cd_')}
 
 
@@ -317,8 +575,8 @@ class patched:
     """context manager: route the host modules' `call` / `stream` to the emulator (CPU tensors)"""
 
     def __enter__(self):
-        from cold_diffusion_models_b200 import ops, model2, model2_train
-        self._mods = (ops, model2, model2_train)
+        from cold_diffusion_models_b200 import ops, model2, model2_train, engine, engine_bwd, deblurring, trainer
+        self._mods = (ops, model2, model2_train, engine, engine_bwd, deblurring, trainer)
         self._saved = [(m, m.call, m.stream) for m in self._mods]
         for m in self._mods:
             m.call = call
