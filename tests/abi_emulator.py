@@ -538,6 +538,16 @@ def cd_blur_apply(x, out, ops_, t, t_scalar, B, Cc, S, T, collapse_last, quantiz
     return 0
 
 
+def cd_blur_step_down(xt, xhat, out, ops_, t_hi, t_lo, B, Cc, S, T, collapse_last, stream):
+    assert not collapse_last, "emulator: `discrete` options are not emulated"
+    shp, st = (B, Cc, S, S), (Cc * S * S, S * S, S, 1)
+    X, Xh = _arr(xt, shp, st).astype(np.float64), _arr(xhat, shp, st).astype(np.float64)
+    A = _arr(ops_, (T, S, S), (S * S, S, 1)).astype(np.float64)
+    D = lambda i: Xh if i < 0 else np.einsum('ij,bcjk,lk->bcil', A[i], Xh, A[i])
+    _arr(out, shp, st)[:] = (X - D(t_hi) + D(t_lo)).astype(np.float32)
+    return 0
+
+
 def cd_adam_ema_step(p, g, m, v, ema, n, lr, beta1, beta2, eps, step, ema_mode, ema_beta, grad_scale, stream):
     n = _v(n); lr, b1, b2, eps, eb, gs = (np.float32(_v(a)) for a in (lr, beta1, beta2, eps, ema_beta, grad_scale))
     P, Gr, M, V = (_arr(a, (n,), (1,)) for a in (p, g, m, v))

@@ -93,6 +93,23 @@ def main():
         out['F2:' + key], out['B1:' + key], out['B2:' + key], out['i1:' + key], out['i2:' + key] = stack(F2), stack(B1), stack(B2), i1, i2
     save('fb_small', x=x, **out)
 
+    # ---- the seventh blur routine, 'Individual_Incremental' (kernel size 2i+1, sigma 2k, DB:379-383): q_sample + sample ----
+    torch.manual_seed(91)
+    xi = torch.rand(2, 3, 32, 32) * 2 - 1
+    out = {}
+    for samp in ('default', 'x0_step_down'):
+        gd = db.GaussianDiffusion(unet, image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, kernel_std=0.1, kernel_size=3,
+                                  blur_routine='Individual_Incremental', sampling_routine=samp)
+        if samp == 'default':
+            for i, kconv in enumerate(gd.gaussian_kernels):
+                out['w%d' % i] = kconv.weight[0, 0]
+            out['q'] = gd.q_sample(xi, torch.tensor([3, 1]))
+            with torch.no_grad():
+                out['loss'] = gd.p_losses(xi, torch.tensor([3, 1]))
+        xt, dr, img = quiet(gd.sample, batch_size=2, img=xi)
+        out['xt:' + samp], out['dr:' + samp], out['img:' + samp] = xt, dr, img
+    save('individual_small', x=xi, **out)
+
     # ---- DDPM-style `Model` (Model2.py): L1-loss gradients of every parameter (dropout inactive: eval mode) -----------
     z = np.load(os.path.join(HERE, 'model2_small.npz'))
     msd = {k[3:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd:')}

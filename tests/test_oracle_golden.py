@@ -309,3 +309,21 @@ def test_model2_oracle_gradients_match_reference():
             assert abs(gr.double().norm().item() / gg['gnorm:' + k[5:]].item() - 1) < 1e-5, k
             n += 1
     assert n == sum(1 for v in sd.values() if v.requires_grad)
+
+
+def test_individual_incremental_routine_matches_reference():
+    """the seventh blur routine: kernel size 2i+1, sigma 2k, single-kernel head in `sample` (DB:379-383, 401-402, 429-430)"""
+    g = load('individual_small')
+    fn = _small_fn()
+    x = g['x']
+    for samp in ('default', 'x0_step_down'):
+        o = DO.DeblurOracle(fn, image_size=32, channels=3, timesteps=4, kernel_std=0.1, kernel_size=3,
+                            blur_routine='Individual_Incremental', sampling_routine=samp)
+        for i, w in enumerate(o.kernels2d):
+            assert torch.equal(w, g['w%d' % i])
+        tt = torch.tensor([3, 1])
+        assert torch.allclose(o.q_sample(x, tt), g['q'], atol=2e-6)
+        with torch.no_grad():
+            assert abs(o.p_losses(x, tt).item() - g['loss'].item()) < 1e-5
+        xt, dr, img = o.sample(2, x)
+        assert rel(xt, g['xt:' + samp]) < 1e-5 and rel(dr, g['dr:' + samp]) < 1e-5 and rel(img, g['img:' + samp]) < 1e-4, samp

@@ -91,6 +91,25 @@ def test_sample_and_loss_match_reference_golden(small):
         assert abs(loss.item() - g['loss:' + key].item()) < (3e-3 if int(disc) else 3e-4), key
 
 
+def test_individual_incremental_routine_matches_reference_golden(small):
+    """the seventh blur routine (kernel size 2i+1, sigma 2k; `sample` starts from the single step-t kernel, DB:379-383, 401-402)"""
+    import cold_diffusion_models_b200 as cdm
+    g = load('individual_small')
+    _, sd, u = small
+    x = g['x'].cuda()
+    for samp in ('default', 'x0_step_down'):
+        gd = cdm.GaussianDiffusion(u, image_size=32, device_of_kernel='cuda', channels=3, timesteps=4, kernel_std=0.1, kernel_size=3,
+                                   blur_routine='Individual_Incremental', sampling_routine=samp).cuda()
+        for i, kconv in enumerate(gd.gaussian_kernels):
+            assert torch.equal(kconv.weight[0, 0].cpu(), g['w%d' % i])
+        tt = torch.tensor([3, 1]).cuda()
+        assert torch.allclose(gd.q_sample(x, tt).cpu(), g['q'], atol=3e-6)
+        with torch.no_grad():
+            assert abs(gd.p_losses(x, tt).item() - g['loss'].item()) < 3e-4
+        xt, dr, img = gd.sample(batch_size=2, img=x)
+        assert rel(xt, g['xt:' + samp]) < 1e-5 and rel(dr, g['dr:' + samp]) < 1e-3 and rel(img, g['img:' + samp]) < 2e-3, samp
+
+
 def test_unet_full_size_matches_oracle():
     """BASELINE config 3 network (dim 64, mults (1,2,4,8), 3x128x128) against the CPU oracle, B=2."""
     import unet_oracle as UO

@@ -110,3 +110,23 @@ def test_trainer_step_equals_torch_adam_and_ema_on_the_emulated_abi(emu, monkeyp
         assert rel(new[k], ref[k].detach()) < 1e-5, k
         assert rel(ema[k], sd[k] * 0.9 + 0.1 * ref[k].detach()) < 1e-5, k
     assert float(tr.opt.engine.flat_grad.abs().max()) == 0.0
+
+
+def test_individual_incremental_routine_through_the_public_class(emu):
+    """q_sample / p_losses / sample of the seventh blur routine (per-step kernel sizes 1,3,5,7; `sample` starts from the single
+    step-t kernel, DB:401-402) on the emulated ABI against the reference"""
+    import cold_diffusion_models_b200 as cdm
+    g, gi = load('unet_small'), load('individual_small')
+    u = small_unet(g)
+    x = gi['x']
+    for samp in ('default', 'x0_step_down'):
+        gd = cdm.GaussianDiffusion(u, image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, kernel_std=0.1, kernel_size=3,
+                                   blur_routine='Individual_Incremental', sampling_routine=samp)
+        for i, kconv in enumerate(gd.gaussian_kernels):
+            assert torch.equal(kconv.weight[0, 0], gi['w%d' % i])
+        tt = torch.tensor([3, 1])
+        assert torch.allclose(gd.q_sample(x, tt), gi['q'], atol=3e-6)
+        with torch.no_grad():
+            assert abs(gd.p_losses(x, tt).item() - gi['loss'].item()) < 1e-5
+        xt, dr, img = gd.sample(batch_size=2, img=x)
+        assert rel(xt, gi['xt:' + samp]) < 1e-5 and rel(dr, gi['dr:' + samp]) < 1e-5 and rel(img, gi['img:' + samp]) < 1e-4, samp
