@@ -548,6 +548,125 @@ def cd_blur_step_down(xt, xhat, out, ops_, t_hi, t_lo, B, Cc, S, T, collapse_las
     return 0
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# degradations of the other packages (degrade.cu)
+# ------------------------------------------------------------------------------------------------------------------
+def _quantize8(v):
+    q = (v.astype(np.float32) + np.float32(1)) * np.float32(0.5) * np.float32(255)
+    return (np.trunc(q).astype(np.float32) / np.float32(255)) * np.float32(2) - np.float32(1)
+
+
+def cd_noise_lerp(x1, x2, t, t_scalar, sa, sb, per_sample, n, out, stream):
+    per_sample, n = _v(per_sample), _v(n)
+    B = n // per_sample
+    tt = _i64(t, B) if _v(t) else np.full(B, t_scalar)
+    T = int(tt.max()) + 1
+    a = _arr(sa, (T,), (1,))[tt][:, None]; b = _arr(sb, (T,), (1,))[tt][:, None]
+    _arr(out, (B, per_sample), (per_sample, 1))[:] = a * _arr(x1, (B, per_sample), (per_sample, 1)) + b * _arr(x2, (B, per_sample), (per_sample, 1))
+    return 0
+
+
+def cd_noise_step(img, x1_bar, noise, mode, t, sa, sb, n, out, stream):
+    n = _v(n)
+    A, Bc = _arr(sa, (t,), (1,)), _arr(sb, (t,), (1,))
+    im, xv = _arr(img, (n,), (1,)), _arr(x1_bar, (n,), (1,))
+    a1, b1 = A[t - 1], Bc[t - 1]
+    x2 = (im - a1 * xv) / b1 if mode == 0 else _arr(noise, (n,), (1,))
+    xt_bar = a1 * xv + b1 * x2
+    xt_sub1 = A[t - 2] * xv + Bc[t - 2] * x2 if t - 1 != 0 else xv
+    _arr(out, (n,), (1,))[:] = im - xt_bar + xt_sub1
+    return 0
+
+
+def cd_fade_lerp(x1, x2, t, t_scalar, alphas, one_minus, B, Cc, HW, out, stream):
+    tt = _i64(t, B) if _v(t) else np.full(B, t_scalar)
+    T = int(tt.max()) + 1
+    al = _arr(alphas, (T, HW), (HW, 1))[tt][:, None, :]; om = _arr(one_minus, (T, HW), (HW, 1))[tt][:, None, :]
+    shp, st = (B, Cc, HW), (Cc * HW, HW, 1)
+    _arr(out, shp, st)[:] = al * _arr(x1, shp, st) + om * _arr(x2, shp, st)
+    return 0
+
+
+def cd_fade_step(img, x1_bar, x2, t, alphas, one_minus, B, Cc, HW, out, stream):
+    al, om = _arr(alphas, (t, HW), (HW, 1)), _arr(one_minus, (t, HW), (HW, 1))
+    shp, st = (B, Cc, HW), (Cc * HW, HW, 1)
+    im, xv, ev = _arr(img, shp, st), _arr(x1_bar, shp, st), _arr(x2, shp, st)
+    xt_bar = al[t - 1] * xv + om[t - 1] * ev
+    xt_sub1 = al[t - 2] * xv + om[t - 2] * ev if t - 1 != 0 else xv
+    _arr(out, shp, st)[:] = im - xt_bar + xt_sub1
+    return 0
+
+
+def _mask_windows(masks, idx_per_b, rx, ry, B, S, MS, T):
+    M = _arr(masks, (T, MS, MS), (MS * MS, MS, 1))
+    out = np.ones((B, 1, S, S), dtype=np.float32)
+    for b in range(B):
+        i = int(idx_per_b[b])
+        if i >= 0:
+            oy = int(_i64(rx, B)[b]) if _v(rx) else 0
+            ox = int(_i64(ry, B)[b]) if _v(ry) else 0
+            out[b, 0] = M[i, oy:oy + S, ox:ox + S]
+    return out
+
+
+def cd_mask_apply(x, out, masks, t, t_scalar, rx, ry, B, Cc, S, MS, quantize, stream):
+    tt = _i64(t, B) if _v(t) else np.full(B, t_scalar)
+    Mw = _mask_windows(masks, tt, rx, ry, B, S, MS, max(int(tt.max()) + 1, 1))
+    shp, st = (B, Cc, S, S), (Cc * S * S, S * S, S, 1)
+    v = _arr(x, shp, st) * Mw
+    _arr(out, shp, st)[:] = _quantize8(v) if quantize else v
+    return 0
+
+
+def cd_mask_step_down(xt, xhat, out, masks, idx_hi, idx_lo, rx, ry, B, Cc, S, MS, stream):
+    T = max(idx_hi, idx_lo) + 1
+    hi = _mask_windows(masks, [idx_hi] * B, rx, ry, B, S, MS, max(T, 1))
+    lo = _mask_windows(masks, [idx_lo] * B, rx, ry, B, S, MS, max(T, 1))
+    shp, st = (B, Cc, S, S), (Cc * S * S, S * S, S, 1)
+    xv = _arr(xhat, shp, st)
+    _arr(out, shp, st)[:] = _arr(xt, shp, st) - xv * hi + xv * lo
+    return 0
+
+
+def cd_chanmix(xt, xsrc, out, mats, t_hi, t_lo, hi_off, lo_off, B, Cc, HW, mode, stream):
+    HW = _v(HW)
+    th = _i64(t_hi, B) + hi_off
+    tl = (_i64(t_lo, B) + lo_off) if mode else np.full(B, -1)
+    T = int(max(th.max(), tl.max())) + 1
+    M = _arr(mats, (max(T, 1), Cc, Cc), (Cc * Cc, Cc, 1)).astype(np.float64)
+    shp, st = (B, Cc, HW), (Cc * HW, HW, 1)
+    src, O = _arr(xsrc, shp, st).astype(np.float64), _arr(out, shp, st)
+    for b in range(B):
+        hi = src[b] if th[b] < 0 else M[th[b]] @ src[b]
+        lo = src[b] if tl[b] < 0 else M[tl[b]] @ src[b]
+        O[b] = (_arr(xt, shp, st)[b].astype(np.float64) - hi + lo if mode else hi).astype(np.float32)
+    return 0
+
+
+def cd_snow(xt, og, out, snow, br_coef, t_hi, t_lo, hi_off, lo_off, B, H, W, snow_batch, fix_brightness, mode, stream):
+    HW = H * W
+    th = _i64(t_hi, B) + hi_off
+    tl = (_i64(t_lo, B) + lo_off) if mode else np.full(B, -1)
+    T = int(max(th.max(), tl.max())) + 1
+    S = _arr(snow, (max(T, 1), snow_batch, 3, HW), (snow_batch * 3 * HW, 3 * HW, HW, 1))
+    br = _arr(br_coef, (max(T, 1),), (1,))
+    shp, st = (B, 3, HW), (3 * HW, HW, 1)
+    OG, O = _arr(og, shp, st), _arr(out, shp, st)
+    for b in range(B):
+        r = (OG[b] + np.float32(1)) / np.float32(2)
+        gray = (np.float32(0.299) * r[0] + np.float32(0.587) * r[1] + np.float32(0.114) * r[2]) * np.float32(1.5) + np.float32(0.5)
+        g3 = np.maximum(r, gray[None])
+        res = []
+        for i in (th[b], tl[b]):
+            if i < 0:
+                res.append(OG[b]); continue
+            base = r if fix_brightness else br[i] * r + (np.float32(1) - br[i]) * g3
+            sl = S[i, b if snow_batch > 1 else 0]
+            res.append(np.clip(base + sl + sl[:, ::-1], 0, 1) * np.float32(2) - np.float32(1))
+        O[b] = _arr(xt, shp, st)[b] - res[0] + res[1] if mode else res[0]
+    return 0
+
+
 def cd_adam_ema_step(p, g, m, v, ema, n, lr, beta1, beta2, eps, step, ema_mode, ema_beta, grad_scale, stream):
     n = _v(n); lr, b1, b2, eps, eb, gs = (np.float32(_v(a)) for a in (lr, beta1, beta2, eps, ema_beta, grad_scale))
     P, Gr, M, V = (_arr(a, (n,), (1,)) for a in (p, g, m, v))
@@ -585,8 +704,10 @@ class patched:
     """context manager: route the host modules' `call` / `stream` to the emulator (CPU tensors)"""
 
     def __enter__(self):
-        from cold_diffusion_models_b200 import ops, model2, model2_train, engine, engine_bwd, deblurring, trainer
-        self._mods = (ops, model2, model2_train, engine, engine_bwd, deblurring, trainer)
+        from cold_diffusion_models_b200 import (ops, model2, model2_train, engine, engine_bwd, deblurring, trainer, denoising,
+                                                resolution, defading, defading_generation, snowification)
+        self._mods = (ops, model2, model2_train, engine, engine_bwd, deblurring, trainer, denoising, resolution, defading,
+                      defading_generation, snowification)
         self._saved = [(m, m.call, m.stream) for m in self._mods]
         for m in self._mods:
             m.call = call
