@@ -814,7 +814,19 @@ extern "C" int cd_linattn_context(const float* qkv, int ld, int B, int n, float*
     CD_REQUIRE(fn(reinterpret_cast<CUdeviceptr>(kmax), 0xFF800000u, static_cast<size_t>(B) * 128, st) == CUDA_SUCCESS,
                "cuMemsetD32Async failed");
   }
-  int ppb = 512; if (ppb > n) ppb = n;
+  // pixels per block: one wave of resident blocks over the whole batch (a fixed 512 left the 64x64 level with 256 blocks
+  // and the 128x128 level with 1.15 waves); any value is correct, the kernels clamp to n and zero-fill the last chunk
+  static int slots = 0;
+  if (!slots) {
+    int dev = 0, sms = 0, occ = 0;
+    CD_CUDA(cudaGetDevice(&dev));
+    CD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, context_kernel, 256, 0));
+    slots = sms * (occ > 0 ? occ : 1);
+  }
+  int per_img = slots / (B > 0 ? B : 1); if (per_img < 1) per_img = 1;
+  int ppb = cd_cdiv(cd_cdiv(n, per_img), kCtxP) * kCtxP;
+  if (ppb < kCtxP) ppb = kCtxP;
   dim3 grid(cd_cdiv(n, ppb), B);
   kmax_kernel<<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax);
   CD_LAUNCH_CHECK();
