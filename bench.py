@@ -72,28 +72,34 @@ class ClockSampler(threading.Thread):
 # reference arm / cpu baseline: the reference algorithm (oracle port; the reference itself is pure Python
 # under /root/reference, absent on the GPU box) on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_train_sample(batch=2, steps=1, warmup=0, threads=None):
-    """times p_losses forward + backward + Adam of config 3 on the CPU at a bounded batch; -> (img/s, info)"""
+def cpu_train_sample(batch=2, steps=1, warmup=0, threads=None, device='cpu'):
+    """times p_losses forward + backward + Adam of config 3 with the eager-PyTorch restatement of the reference (oracle/) at a
+    bounded batch; -> (img/s, info).  device='cpu' is the contract's CPU baseline; device='cuda' (bench.py --impl reference
+    --reference-device cuda, informational) runs the same eager PyTorch code on the GPU, which is how the reference is deployed."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import unet_oracle as UO
     import deblur_oracle as DO
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    sd = {k: v.clone().requires_grad_(True) for k, v in UO.make_unet_state_dict(C3['dim'], C3['dim_mults'], C3['channels']).items()}
+    dev = torch.device(device)
+    sd = {k: v.clone().to(dev).requires_grad_(True) for k, v in UO.make_unet_state_dict(C3['dim'], C3['dim_mults'], C3['channels']).items()}
     orc = DO.DeblurOracle(lambda a, b: UO.unet_forward(sd, a, b), image_size=C3['image_size'], channels=3,
                           timesteps=C3['timesteps'], kernel_std=C3['kernel_std'], kernel_size=C3['kernel_size'],
-                          blur_routine=C3['blur_routine'], sampling_routine=C3['sampling_routine'])
+                          blur_routine=C3['blur_routine'], sampling_routine=C3['sampling_routine']).to(dev)
     opt = torch.optim.Adam(list(sd.values()), lr=2e-5)
     g = torch.Generator().manual_seed(1234)
+    sync = torch.cuda.synchronize if dev.type == 'cuda' else (lambda: None)
     times = []
     for it in range(warmup + steps):
-        x = torch.rand(batch, 3, 128, 128, generator=g) * 2 - 1
-        t = torch.randint(0, C3['timesteps'], (batch,), generator=g)
+        x = (torch.rand(batch, 3, 128, 128, generator=g) * 2 - 1).to(dev)
+        t = torch.randint(0, C3['timesteps'], (batch,), generator=g).to(dev)
+        sync()
         t0 = time.time()
         loss = orc.p_losses(x, t)
         loss.backward()
         opt.step(); opt.zero_grad()
+        sync()
         if it >= warmup:
             times.append(time.time() - t0)
     sec = sum(times) / len(times)
@@ -105,11 +111,15 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    v, info = cpu_train_sample(batch=2, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    on_gpu = args.reference_device == 'cuda'
+    v, info = cpu_train_sample(batch=32 if on_gpu else 2, steps=max(1, args.steps), warmup=max(1, args.warmup) if on_gpu else min(1, args.warmup),
+                               device=args.reference_device)
     line = {"impl": "reference", "metric": "training-step images/sec (CelebA-128 deblur UNet)", "value": v, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info['ms_per_step'],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3 train step (bounded sample: batch 2 per step on host cores)", "image": "3x128x128", "T": 200},
+            "config": {"workload": ("C3 micro-batch (32 images), eager PyTorch restatement on cuda:0" if on_gpu else
+                                    "C3 train step (bounded sample: batch 2 per step on host cores)"), "image": "3x128x128", "T": 200,
+                       "device": args.reference_device},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": info['cores'], "kind": "port", "sample": info['sample']},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -124,6 +134,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sample-steps', type=int, default=10, help='reverse steps timed for the sampling half of the metric')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--reference-device', default='cpu', choices=['cpu', 'cuda'],
+                    help="--impl reference only: 'cpu' (the contract) or 'cuda' = the same eager-PyTorch restatement on the GPU (informational)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

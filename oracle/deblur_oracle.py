@@ -68,6 +68,11 @@ class DeblurOracle:
         self.schedule = blur_schedule(blur_routine, self.num_timesteps, kernel_size, kernel_std)
         self.kernels2d = [gaussian_2d(k, s) for (k, s, _) in self.schedule]
 
+    def to(self, device):
+        """move the blur taps (the only tensors the oracle owns) -- lets bench.py time this eager-PyTorch restatement on a GPU too"""
+        self.kernels2d = [k.to(device) for k in self.kernels2d]
+        return self
+
     def blur_step(self, i, x):
         # nn.Conv2d(C, C, k, padding=(k-1)/2, padding_mode=mode, groups=C, bias=False) DB:351-361
         k, _, mode = self.schedule[i]
@@ -92,7 +97,7 @@ class DeblurOracle:
                 x = self._collapse(x)
             all_blurs.append(x)
         all_blurs = torch.stack(all_blurs)
-        choose = torch.stack([all_blurs[int(t[b]), b] for b in range(t.shape[0])])
+        choose = torch.stack([all_blurs[int(t[b]), b] for b in range(t.shape[0])])       # (DB:947-950: per-sample Python indexing)
         if self.discrete:
             choose = (choose + 1) * 0.5
             choose = choose * 255
