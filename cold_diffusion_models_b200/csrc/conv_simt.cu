@@ -624,7 +624,7 @@ pack_weight_tiled_kernel(const float* __restrict__ w, long long rows, int KHW, i
 }  // namespace
 
 int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st);
-int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, cudaStream_t st);
+int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, float* db, int* bias_done, cudaStream_t st);
 
 static int conv_fwd_simt(const CdConvDesc* d, cudaStream_t st) {
   SimtParams p{};
@@ -693,8 +693,9 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const CdConvSrc& c = d->s[0];
   bool done = false;
+  int bias_done = 0;
   if (impl == CD_CONV_TC) {
-    const int rc = cd_conv_wgrad_tc(d, dout, dout_ld, dw, st);
+    const int rc = cd_conv_wgrad_tc(d, dout, dout_ld, dw, db, &bias_done, st);
     if (rc < 0) return rc;
     done = (rc == 0);                       // rc == 1: not tensor-core shaped -> fp32 CUDA-core kernel below
   }
@@ -748,7 +749,7 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   CD_LAUNCH_CHECK();
   }
   }
-  if (db) {
+  if (db && !bias_done) {
     const long long rows = static_cast<long long>(d->B) * d->Ho * d->Wo;
     CD_REQUIRE(d->oys == 1 && d->oxs == 1, "cd_conv_wgrad: bias gradient needs a dense output grid");
     launch_colsum(dout, dout_ld, rows, d->Cout, db, st);

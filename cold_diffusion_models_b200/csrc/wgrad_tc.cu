@@ -39,6 +39,7 @@ struct WgParams {
   int per_batch, chunks_per_img, splits_per_img;   // per-batch weights: splits never cross images
   long long dw_batch_stride;
   float* dw;
+  float* db;                      // BIAS kernels only: db[co] += sum over all pixels of dY (nullptr: not fused)
 };
 
 // MN-major operand for 32-bit (tf32) data: the only layout UMMA accepts is SWIZZLE_128B_BASE32B -- 128-byte rows (32
@@ -64,7 +65,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN>
+// BIAS = true (opt-in, cd_wgrad_tc_set_bias_fusion): the CTAs of the first ci tile and first tap group also accumulate the bias
+// gradient db[co] = sum_pixels dY[p][co] with one extra 128 x 32 x 8 MMA per k-step against a tile of ones (TMEM columns after
+// the tap accumulators), replacing the separate column-sum pass over dY.  BIAS = false is the production kernel.
+template <int BN, bool BIAS>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
                 const WgParams p, int stages, int a_bytes, int b_bytes, int b_tx_bytes) {
@@ -72,14 +76,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
   // instruction descriptor: D=f32, A=B=tf32, A and B MN-major, N=BN, M=128
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                               (uint32_t(BN >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  constexpr uint32_t kIdescBias = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                  (uint32_t(32 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint4 mma_tab[kMaxTaps * 8 + 1];
+  __shared__ uint4 mma_tab[kMaxTaps * 8 + 8 + 1];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int g = blockIdx.z;
   const int nl = p.nloads[g], nt = p.ntaps[g];
   const int stage_bytes = a_bytes + nl * b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  float* ones = reinterpret_cast<float*>(smem + stages * stage_bytes);          // BIAS: 8 pixels x 32 channels of 1.0f (1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes + (BIAS ? 1024 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + stages;
   uint64_t* done_bar = bars + 2 * stages;
@@ -95,6 +102,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (BIAS) {
+    if (warp >= 2) for (int i = threadIdx.x - 64; i < 256; i += kThreads - 64) ones[i] = 1.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor-core (async) proxy
   }
   tc_fence_before();
   __syncthreads();
@@ -115,6 +126,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
     dw_off = n * p.dw_batch_stride;
   }
   const int nchunks = c_end > c_beg ? c_end - c_beg : 0;
+  const bool bias_cta = BIAS && p.db != nullptr && (tile / p.tiles_co) == 0 && g == 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -147,9 +159,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
     const uint32_t a_lbo = a_bytes / 4, b_lbo = b_bytes / NCH;
     const int ksteps_row = p.CW / 8;                // MMAs per image row of the chunk
     const int per_tap = p.R * ksteps_row;
-    const int nmma = nt * per_tap;                  // <= kMaxTaps * 8
+    const int ntap_mma = nt * per_tap;              // <= kMaxTaps * 8
+    const int nmma = ntap_mma + (bias_cta ? per_tap : 0);
     if (lane == 0) mma_tab[nmma] = make_uint4(0, 0, 0, 0);
-    if (lane < nmma) {
+    if (bias_cta && lane < per_tap) {               // bias entries: same A rows, B = the ones tile (flag bit 17), columns after the taps
+      const int r = lane / ksteps_row, j = lane % ksteps_row;
+      mma_tab[ntap_mma + lane] = make_uint4(((r * p.CW + j * 8) * 128) >> 4, 0, 0,
+                                            static_cast<uint32_t>(nt * BN) | ((r | j) != 0 ? 0x10000u : 0u) | 0x20000u);
+    }
+    if (lane < ntap_mma) {
       const int t = lane / per_tap, r = (lane % per_tap) / ksteps_row, j = lane % ksteps_row;
       const uint32_t arow = r * p.CW + j * 8;
       const uint32_t brow = r * (p.CW + p.halo) + j * 8 + p.tap_shift[g][t];
@@ -164,6 +182,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
       const uint64_t da_t = make_mnmajor_sw128_desc(0, a_lbo, 0);
       const uint32_t da_hi = static_cast<uint32_t>(da_t >> 32), da_lo = static_cast<uint32_t>(da_t);
       const uint32_t db_lo = static_cast<uint32_t>(make_mnmajor_sw128_desc(0, b_lbo, 0));
+      const uint64_t ones_desc = make_mnmajor_sw128_desc(smem_u32(ones), 1024, 0);
       for (int it = 0; it < nchunks; ++it) {
         const uint32_t stage = it % stages, ph = (it / stages) & 1u;
         mbar_wait(&full_bar[stage], ph);
@@ -176,8 +195,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
         for (int i = 0; i < nmma; ++i) {
           const uint4 en = mma_tab[i + 1];          // table has one spare entry; prefetched so the LDS latency is off the issue path
           const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (alo + e.x);
-          const uint64_t db = (static_cast<uint64_t>(e.z) << 32) | (blo + e.y);
-          mma_tf32_nomem(tmem_base + (e.w & 0xFFFFu), da, db, kIdesc, (e.w | first) & 0x10000u);
+          uint64_t db = (static_cast<uint64_t>(e.z) << 32) | (blo + e.y);
+          uint32_t idesc = kIdesc;
+          if (BIAS && (e.w & 0x20000u)) { db = ones_desc; idesc = kIdescBias; }
+          mma_tf32_nomem(tmem_base + (e.w & 0xFFFFu), da, db, idesc, (e.w | first) & 0x10000u);
           e = en;
         }
         tc_commit(&empty_bar[stage]);
@@ -203,6 +224,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
           }
         }
       }
+      if (BIAS && bias_cta) {                       // every column of the bias accumulator holds the same sum: take column 0
+        uint32_t r[32];
+        tmem_ld32(tmem_base + nt * BN + (static_cast<uint32_t>(q * 32) << 16), r);
+        if (co < p.Cout) atomicAdd(p.db + co, __uint_as_float(r[0]));
+      }
     }
   }
   tc_fence_before();
@@ -221,6 +247,10 @@ int g_sms = 0;
 }  // namespace
 
 extern "C" int cd_wgrad_tc_set_mode(int mode) { g_wg_mode = mode; return 0; }
+
+// opt-in: fold the bias gradient (column sums of dY) into the tcgen05 weight gradient.  Off by default: not yet run on a B200.
+static int g_wg_bias_fusion = 0;
+extern "C" int cd_wgrad_tc_set_bias_fusion(int enable) { g_wg_bias_fusion = enable; return 0; }
 
 // K-split policy.  One CTA owns (Cout tile, Cin tile, tap group, pixel range); it runs alone on its SM (the stages fill the
 // shared memory) and its red.add epilogue is not overlapped, so the launch costs waves x (chunks_per_split * t_chunk + t_over).
@@ -250,7 +280,8 @@ static int choose_splits(int tg, int total_chunks, int max_splits, int sms, doub
 }
 
 // returns 1 if the problem is not tensor-core shaped (caller falls back to the SIMT kernel), 0 on success, <0 on error
-int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, cudaStream_t st) {
+int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float* dw, float* db, int* bias_done, cudaStream_t st) {
+  if (bias_done) *bias_done = 0;
   const CdConvSrc& c = d->s[0];
   if (c.C % 32 != 0 || d->Cout % 32 != 0 || c.ld % 4 != 0 || dout_ld % 4 != 0) return 1;
   if (!is_pow2(d->Wg) || d->Wg < 8 || !is_pow2(d->Hg)) return 1;
@@ -333,7 +364,10 @@ int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float*
   const int stage_bytes = a_bytes + max_loads * b_bytes;
   int stages = (224 * 1024) / stage_bytes; if (stages > 6) stages = 6;   // 3 x 68 KB halo stages fit the 227 KB carve-out
   if (stages < 2) return 1;
-  const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
+  // bias fusion: dense output grid, one weight set, room for 32 more TMEM columns after the tap accumulators
+  const bool fuse_bias = g_wg_bias_fusion && db != nullptr && !c.w_per_batch && d->oys == 1 && d->oxs == 1 && max_taps * BN + 32 <= 512;
+  p.db = fuse_bias ? db : nullptr;
+  const size_t smem = size_t(stages) * stage_bytes + 1024 + 256 + (fuse_bias ? 1024 : 0);
 
   CUtensorMap mapDY, mapX;
   const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
@@ -356,12 +390,21 @@ int cd_conv_wgrad_tc(const CdConvDesc* d, const float* dout, int dout_ld, float*
     CD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(X) failed: %d", (int)r);
   }
   dim3 grid(tiles, p.splits, p.ngroups);
-  if (BN == 128) {
-    CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_tc_kernel<128><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
+  if (fuse_bias) {
+    if (BN == 128) {
+      CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      wgrad_tc_kernel<128, true><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
+    } else {
+      CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      wgrad_tc_kernel<64, true><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
+    }
+    if (bias_done) *bias_done = 1;
+  } else if (BN == 128) {
+    CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_tc_kernel<128, false><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
   } else {
-    CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_tc_kernel<64><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
+    CD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_tc_kernel<64, false><<<grid, kThreads, smem, st>>>(mapDY, mapX, p, stages, a_bytes, b_bytes, b_tx);
   }
   CD_LAUNCH_CHECK();
   return 0;

@@ -159,6 +159,8 @@ int cd_wgrad_tc_set_mode(int mode);
 /* K-split policy of the tcgen05 wgrad: 0 = two waves rounded up, 1 / 2 = at most one / two full waves of CTAs,
  * 3 (default) = minimise waves x (chunks_per_split x t_chunk + over_clk); over_clk > 0 sets the per-CTA fixed cost (SM clocks) */
 int cd_wgrad_tc_set_split(int policy, int over_clk);
+/* opt-in (default 0, not yet validated on a B200): fold the bias gradient (column sums of dY) into the tcgen05 weight gradient */
+int cd_wgrad_tc_set_bias_fusion(int enable);
 /* diagnostic switch: 1 (default) = TFLOAT32 tensor maps (TMA rounds fp32->tf32 RN on load) */
 int cd_conv_tc_set_tf32_maps(int enable);
 /* SM-pair (tcgen05 cta_group::2, 256 pixels x 256 channels per pair) variant of the tap-list convolution:
