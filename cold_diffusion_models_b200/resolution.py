@@ -90,9 +90,13 @@ class GaussianDiffusion(nn.Module):
         return out
 
     def q_sample(self, x_start, t):
-        """RS:630-652; rows with t_b = -1 are passed through (used by the 'Step' train routine at t = 0)."""
+        """RS:630-652.  Rows with t_b = -1 (the 'Step' train routine at t = 0, RS:745) were meant to pass through, but the
+        reference tests the loop index instead of t (`if step != -1`, RS:645), so they take `all_blurs[-1]`: the level
+        max(t) of that batch.  Reproduced here (two index ops on B int64 values, no host sync); when every t is -1 the
+        reference raises inside torch.stack -- that case passes the rows through instead."""
         with torch.no_grad():
             t = t.to(device=x_start.device, dtype=torch.int64).contiguous()
+            t = torch.where(t < 0, t.max().expand_as(t), t).contiguous()
             return self._apply_op(x_start, -1, per_sample_t=t)
 
     def _loss(self, a, b):

@@ -40,9 +40,31 @@ class ResolutionOracle:
         xs = torch.stack(xs)
         return torch.stack([xs[int(t[b]), b] for b in range(t.shape[0])])
 
-    def p_losses(self, x_start, t):
-        x_recon = self.denoise_fn(self.q_sample(x_start, t), t)
-        return (x_start - x_recon).abs().mean() if self.loss_type == 'l1' else F.mse_loss(x_start, x_recon)
+    def _loss(self, a, b):
+        return (a - b).abs().mean() if self.loss_type == 'l1' else F.mse_loss(a, b)
+
+    def p_losses(self, x_start, t, train_routine='Final'):
+        """RS:655-761: 'Final' and the five research routines (the random ones draw from torch's global generator like the
+        reference: same seed, same numbers)"""
+        r = train_routine
+        if r == 'Final':
+            return self._loss(x_start, self.denoise_fn(self.q_sample(x_start, t), t))
+        if r == 'Final_small_noise':
+            x_start = x_start + 0.001 * torch.randn_like(x_start)
+            return self._loss(x_start, self.denoise_fn(self.q_sample(x_start, t), t))
+        if r in ('Final_random_mean', 'Final_random_mean_and_actual'):
+            loss1 = self._loss(x_start, self.denoise_fn(self.q_sample(x_start, t), t)) if r.endswith('actual') else 0.0
+            new_mean = torch.randn_like(torch.mean(x_start, [2, 3]))[:, :, None, None]
+            x_start = x_start - torch.mean(x_start, [2, 3], keepdim=True) + new_mean
+            return loss1 + self._loss(x_start, self.denoise_fn(self.q_sample(x_start, t), t))
+        if r == 'Gradient_norm':          # the reference raises here (torch.linalg.norm rejects dim=(1,2,3), RS:738): intended semantics
+            x_blur = self.q_sample(x_start, t)
+            gradient = x_blur - x_start
+            norm = torch.linalg.norm(gradient.flatten(1), dim=1).reshape(-1, 1, 1, 1)
+            return self._loss(gradient / (norm + 1e-5), self.denoise_fn(x_blur, t))
+        if r == 'Step':
+            return self._loss(self.q_sample(x_start, t - 1), self.denoise_fn(self.q_sample(x_start, t), t))
+        raise UnboundLocalError(r)
 
     @torch.no_grad()
     def sample(self, batch_size, img, t=None):

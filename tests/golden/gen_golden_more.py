@@ -110,6 +110,24 @@ def main():
         out['xt:' + samp], out['dr:' + samp], out['img:' + samp] = xt, dr, img
     save('individual_small', x=xi, **out)
 
+    # ---- resolution package: the six train routines of p_losses (RS:655-761), incl. the t = 0 row of 'Step' (RS:645 quirk) ----
+    rs = ref_shim.import_reference('resolution-diffusion-pytorch', 'resolution_diffusion_pytorch')
+    unet_rs = quiet(rs.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet_rs.load_state_dict(sd)
+    torch.manual_seed(95)
+    xr = torch.rand(3, 3, 32, 32) * 2 - 1
+    out = {}
+    # ('Gradient_norm' raises inside torch.linalg.norm(dim=(1,2,3)) in the reference: no golden)
+    for routine in ('Final', 'Final_small_noise', 'Final_random_mean', 'Final_random_mean_and_actual', 'Step'):
+        for lt in ('l1', 'l2'):
+            gd = rs.GaussianDiffusion(unet_rs, image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, loss_type=lt,
+                                      resolution_routine='Incremental_factor_2', train_routine=routine, sampling_routine='x0_step_down')
+            torch.manual_seed(7)
+            with torch.no_grad():
+                out['loss:%s|%s' % (routine, lt)] = gd.p_losses(xr, torch.tensor([3, 0, 2]))
+    out['q_neg'] = gd.q_sample(xr, torch.tensor([2, -1, 1]))
+    save('resolution_train_small', x=xr, **out)
+
     # ---- DDPM-style `Model` (Model2.py): L1-loss gradients of every parameter (dropout inactive: eval mode) -----------
     z = np.load(os.path.join(HERE, 'model2_small.npz'))
     msd = {k[3:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd:')}

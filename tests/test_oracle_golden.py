@@ -327,3 +327,19 @@ def test_individual_incremental_routine_matches_reference():
             assert abs(o.p_losses(x, tt).item() - g['loss'].item()) < 1e-5
         xt, dr, img = o.sample(2, x)
         assert rel(xt, g['xt:' + samp]) < 1e-5 and rel(dr, g['dr:' + samp]) < 1e-5 and rel(img, g['img:' + samp]) < 1e-4, samp
+
+
+def test_resolution_train_routines_match_reference():
+    """the research train routines of the resolution package (RS:655-761) and the t = -1 quirk of its q_sample (RS:645)"""
+    import resolution_oracle as RO
+    g = load('resolution_train_small')
+    fn = _small_fn()
+    x, tt = g['x'], torch.tensor([3, 0, 2])
+    for key in _cases('loss:', g):
+        routine, lt = key.split('|')
+        o = RO.ResolutionOracle(fn, image_size=32, timesteps=4, resolution_routine='Incremental_factor_2', sampling_routine='x0_step_down',
+                                loss_type=lt)
+        torch.manual_seed(7)
+        with torch.no_grad():
+            assert abs(float(o.p_losses(x, tt, train_routine=routine)) - g['loss:' + key].item()) < 1e-5, key
+    assert torch.allclose(o.q_sample(x, torch.tensor([2, -1, 1])), g['q_neg'], atol=1e-6)

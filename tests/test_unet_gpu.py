@@ -167,6 +167,21 @@ def test_resolution_package_matches_reference_golden(small):
         assert rel(xt, g['xt:' + key]) < 1e-5 and rel(dr, g['dr:' + key]) < 1e-3 and rel(img, g['img:' + key]) < 2e-3, key
 
 
+def test_resolution_step_routine_and_negative_t_rows_match_reference_golden(small):
+    """'Step' train routine (RS:742-755; no random draws) and the t = -1 rows of q_sample, which take the level max(t) of the
+    batch in the reference (RS:645 tests the loop index instead of t)"""
+    from cold_diffusion_models_b200.resolution_diffusion_pytorch import GaussianDiffusion
+    g = load('resolution_train_small')
+    _, sd, u = small
+    x = g['x'].cuda()
+    for lt in ('l1', 'l2'):
+        gd = GaussianDiffusion(u, image_size=32, device_of_kernel='cuda', channels=3, timesteps=4, loss_type=lt,
+                               resolution_routine='Incremental_factor_2', train_routine='Step', sampling_routine='x0_step_down').cuda()
+        with torch.no_grad():
+            assert abs(gd.p_losses(x, torch.tensor([3, 0, 2]).cuda()).item() - g['loss:Step|' + lt].item()) < 3e-4, lt
+    assert torch.allclose(gd.q_sample(x, torch.tensor([2, -1, 1]).cuda()).cpu(), g['q_neg'], atol=3e-6)
+
+
 def test_defading_package_matches_reference_golden(small):
     """defading_diffusion_pytorch drop-in (Gaussian masks; per-sample random windows indexed inside the kernel)."""
     from cold_diffusion_models_b200.defading_diffusion_pytorch import GaussianDiffusion
