@@ -219,28 +219,54 @@ class GaussianDiffusion(nn.Module):
         self.denoise_fn.train()
         return X_0s, X_ts
 
+    def _range_operator(self, start, t):
+        """K_{t-1} ... K_{start} as a one-entry operator table (host float64 product, cached): the partial blur of
+        `sample_from_blur(start=...)`, DB:877-879"""
+        from .degradation import blur_matrix
+        import numpy as np
+        key = (start, t)
+        cache = self.__dict__.setdefault('_range_ops', {})
+        if key not in cache:
+            S = self.image_size
+            A = np.eye(S, dtype=np.float64)
+            for i in range(start, t):
+                k, sgm, mode = self._sched[i]
+                A = blur_matrix(self._taps[i].double().numpy(), S, mode) @ A
+            cache[key] = torch.from_numpy(A.astype(np.float32))[None].contiguous().to(self._ops_cum.device)
+        return cache[key]
+
     @torch.no_grad()
     def sample_from_blur(self, batch_size=16, img=None, t=None, times=None, eval=True, start=None):
-        """reverse process started from an already degraded image at step `t` (DB:863-925 without the re-blur)."""
+        """DB:863-925 -> (xt, direct_recons, img): blur with the kernels start .. t-1 only, then the reverse process from t"""
         if eval:
             self.denoise_fn.eval()
         if t is None:
             t = self.num_timesteps
-        if times is None:
-            times = t
-        X_0s, X_ts = [], []
-        while times:
-            step = torch.full((batch_size,), times - 1, dtype=torch.long, device=img.device)
+        if start is None:
+            start = 0
+        img = img.contiguous().float()
+        if start < t:
+            if start == 0 and self.blur_routine != 'Individual_Incremental':
+                img = self._apply_op(img, t - 1, collapse=False)
+            else:
+                B, Cc, H, W = img.shape
+                out = torch.empty_like(img)
+                call('cd_blur_apply', ptr(img), ptr(out), ptr(self._range_operator(start, t)), ptr(None), 0, B, Cc, H, 1, 0, 0, stream())
+                img = out
+        if self.discrete:
+            img = torch.mean(img, [2, 3], keepdim=True).expand_as(img).contiguous()
+        xt = img
+        direct_recons = None
+        while t:
+            step = torch.full((batch_size,), t - 1, dtype=torch.long, device=img.device)
             x = self.denoise_fn(img, step)
-            X_0s.append(x)
-            X_ts.append(img)
             if self.train_routine == 'Final':
-                x = self._reverse_step(img, x, times)
+                if direct_recons is None:
+                    direct_recons = x
+                x = self._reverse_step(img, x, t)
             img = x
-            times = times - 1
-        X_0s.append(img)
-        self.denoise_fn.train()
-        return X_0s, X_ts
+            t = t - 1
+        return xt, direct_recons, img
 
     def _forward_trajectory(self, img, t):
         """[x, D(x,1), ..., D(x,t)] of the cover figures: each entry from the cumulative operator in one launch

@@ -91,6 +91,14 @@ def main():
         out['F:' + key], out['B:' + key], out['img:' + key] = stack(F_), stack(B_), img
         F2, B1, B2, i1, i2 = quiet(gd.forward_and_backward_2, batch_size=2, img=x)
         out['F2:' + key], out['B1:' + key], out['B2:' + key], out['i1:' + key], out['i2:' + key] = stack(F2), stack(B1), stack(B2), i1, i2
+        for start in (0, 1):
+            xt, dr, img2 = quiet(gd.sample_from_blur, batch_size=2, img=x, start=start)
+            out['sfb_xt:%d:' % start + key], out['sfb_dr:%d:' % start + key], out['sfb_img:%d:' % start + key] = xt, dr, img2
+        X0s, Xts = quiet(gd.all_sample, batch_size=2, img=x)
+        out['all_X0:' + key], out['all_Xt:' + key] = stack(X0s), stack(Xts)
+        torch.manual_seed(17)
+        xt, dr, img3 = quiet(gd.gen_sample, batch_size=2, img=x, noise_level=0.05)
+        out['gen_xt:' + key], out['gen_img:' + key] = xt, img3
     save('fb_small', x=x, **out)
 
     # ---- the seventh blur routine, 'Individual_Incremental' (kernel size 2i+1, sigma 2k, DB:379-383): q_sample + sample ----

@@ -130,3 +130,25 @@ def test_individual_incremental_routine_through_the_public_class(emu):
             assert abs(gd.p_losses(x, tt).item() - gi['loss'].item()) < 1e-5
         xt, dr, img = gd.sample(batch_size=2, img=x)
         assert rel(xt, gi['xt:' + samp]) < 1e-5 and rel(dr, gi['dr:' + samp]) < 1e-5 and rel(img, gi['img:' + samp]) < 1e-4, samp
+
+
+def test_deblurring_sampling_helpers_through_the_public_class(emu):
+    """sample_from_blur (partial blur start .. t-1, DB:863-925), all_sample (DB:609-689) and gen_sample with noise (DB:526-593;
+    same torch seed -> same noise as the reference) on the emulated ABI against the reference"""
+    import cold_diffusion_models_b200 as cdm
+    g, gf = load('unet_small'), load('fb_small')
+    u = small_unet(g)
+    x = gf['x']
+    for key in sorted(k[4:] for k in gf if k.startswith('img:')):
+        routine, ks, std, T, samp = key.split('|')
+        gd = cdm.GaussianDiffusion(u, image_size=32, device_of_kernel='cpu', channels=3, timesteps=int(T), kernel_std=float(std),
+                                   kernel_size=int(ks), blur_routine=routine, sampling_routine=samp)
+        for start in (0, 1):
+            xt, dr, img = gd.sample_from_blur(batch_size=2, img=x, start=start)
+            pre = ':%d:' % start + key
+            assert rel(xt, gf['sfb_xt' + pre]) < 1e-5 and rel(dr, gf['sfb_dr' + pre]) < 1e-5 and rel(img, gf['sfb_img' + pre]) < 1e-4, pre
+        X0s, Xts = gd.all_sample(batch_size=2, img=x)
+        assert rel(torch.stack(X0s), gf['all_X0:' + key]) < 1e-4 and rel(torch.stack(Xts), gf['all_Xt:' + key]) < 1e-4, key
+        torch.manual_seed(17)
+        xt, dr, img = gd.gen_sample(batch_size=2, img=x, noise_level=0.05)
+        assert rel(xt, gf['gen_xt:' + key]) < 1e-5 and rel(img, gf['gen_img:' + key]) < 1e-4, key
