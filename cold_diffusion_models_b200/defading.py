@@ -122,3 +122,31 @@ class GaussianDiffusion(nn.Module):
             recon = x
             t -= 1
         return xt, direct_recons, recon
+
+    @torch.no_grad()
+    def all_sample(self, batch_size=16, faded_recon_sample=None, t=None, times=None, _offsets=None):
+        """DFG:428-494 -> (x0_list, xt_list): every step's reconstruction and the faded sample AFTER that step's update"""
+        x = faded_recon_sample
+        rx, ry = _offsets if _offsets is not None else self._offsets(batch_size, x.device)
+        if t is None:
+            t = self.num_timesteps
+        if times is None:
+            times = t
+        x = self._fade(x, t - 1, rx, ry, quantize=self.discrete)
+        B, Cc, S, _ = x.shape
+        MS = self._masks_cum.shape[-1]
+        x0_list, xt_list = [], []
+        while times:
+            step = torch.full((batch_size,), times - 1, dtype=torch.long, device=x.device)
+            recon = self.defade_fn(x, step)
+            x0_list.append(recon)
+            if self.sampling_routine == 'default':
+                x = self._fade(recon, times - 2, rx, ry)
+            elif self.sampling_routine == 'x0_step_down':
+                out = torch.empty_like(x)
+                call('cd_mask_step_down', ptr(x.contiguous()), ptr(recon.contiguous()), ptr(out), ptr(self._masks_cum),
+                     times - 1, times - 2, ptr(rx), ptr(ry), B, Cc, S, MS, stream())
+                x = out
+            xt_list.append(x)
+            times -= 1
+        return x0_list, xt_list

@@ -71,12 +71,17 @@ class GaussianDiffusion(nn.Module):
         self.resolution_routine = resolution_routine
         specs = step_specs(resolution_routine, self.num_timesteps, image_size)
         ops = np.zeros((len(specs), image_size, image_size), dtype=np.float32)
+        steps = np.zeros((len(specs), image_size, image_size), dtype=np.float32)
         A = np.eye(image_size)
         for i, (d, mode, blur) in enumerate(specs):
-            A = step_matrix(image_size, d, mode, blur) @ A
+            M = step_matrix(image_size, d, mode, blur)
+            steps[i] = M.astype(np.float32)
+            A = M @ A
             ops[i] = A.astype(np.float32)
         self.register_buffer('_ops_cum', torch.from_numpy(ops), persistent=False)
-        self.func = list(range(len(specs)))       # the reference exposes a list of per-step callables; kept as step ids
+        self.register_buffer('_ops_step', torch.from_numpy(steps), persistent=False)
+        # the reference exposes `func`: a list of per-step callables img -> degraded img (RS:389-414); same here, one launch each
+        self.func = [(lambda img, _i=i: self._apply_step(img, _i)) for i in range(len(specs))]
         self.train_routine = train_routine
         self.sampling_routine = sampling_routine
 
@@ -88,6 +93,18 @@ class GaussianDiffusion(nn.Module):
         call('cd_blur_apply', ptr(x), ptr(out), ptr(self._ops_cum), ptr(per_sample_t), int(idx), B, Cc, H, self.num_timesteps,
              0, 0, stream())
         return out
+
+    @torch.no_grad()
+    def _apply_step(self, x, i):
+        """func[i]: the single degradation step i alone"""
+        x = x.contiguous().float()
+        B, Cc, H, W = x.shape
+        out = torch.empty_like(x)
+        call('cd_blur_apply', ptr(x), ptr(out), ptr(self._ops_step), ptr(None), int(i), B, Cc, H, self.num_timesteps, 0, 0, stream())
+        return out
+
+    def get_funcs(self):
+        return self.func
 
     def q_sample(self, x_start, t):
         """RS:630-652.  Rows with t_b = -1 (the 'Step' train routine at t = 0, RS:745) were meant to pass through, but the
@@ -177,3 +194,57 @@ class GaussianDiffusion(nn.Module):
         if t is None:
             t = self.num_timesteps
         return self._apply_op(img, t - 1)
+
+    def _reverse_loop(self, batch_size, img, times, collect=None):
+        direct_recons = None
+        while times:
+            step = torch.full((batch_size,), times - 1, dtype=torch.long, device=img.device)
+            x = self.denoise_fn(img, step)
+            if collect is not None:
+                collect(x, img)
+            if direct_recons is None:
+                direct_recons = x
+            if self.train_routine == 'Final':
+                x = self._reverse_step(img, x, times)
+            img = x
+            times = times - 1
+        return direct_recons, img
+
+    @torch.no_grad()
+    def gen_sample(self, batch_size=16, img=None, t=None, times=None, noise_level=0):
+        """RS:460-503 -> (xt, direct_recons, img): the reverse process from a given (already degraded) image plus noise"""
+        if t is None:
+            t = self.num_timesteps
+        if times is None:
+            times = t
+        img = img.contiguous().float()
+        img = img + torch.randn_like(img) * noise_level
+        direct_recons, out = self._reverse_loop(batch_size, img, times)
+        return img, direct_recons, out
+
+    @torch.no_grad()
+    def all_sample(self, batch_size=16, img=None, t=None, times=None):
+        """RS:505-555 -> (X_0s, X_ts)"""
+        if t is None:
+            t = self.num_timesteps
+        if times is None:
+            times = t
+        img = self._apply_op(img, t - 1)
+        X_0s, X_ts = [], []
+        self._reverse_loop(batch_size, img, times, collect=lambda x, cur: (X_0s.append(x), X_ts.append(cur)))
+        return X_0s, X_ts
+
+    @torch.no_grad()
+    def forward_and_backward(self, batch_size=16, img=None, t=None, times=None, eval=True):
+        """RS:558-616 -> (Forward, Backward, img)"""
+        if eval:
+            self.denoise_fn.eval()
+        if t is None:
+            t = self.num_timesteps
+        if times is None:
+            times = t
+        img = img.contiguous().float()
+        Forward = [img] + [self._apply_op(img, i) for i in range(t)]
+        Backward = []
+        _, out = self._reverse_loop(batch_size, Forward[-1], times, collect=lambda x, cur: Backward.append(cur))
+        return Forward, Backward, out

@@ -319,3 +319,63 @@ class GaussianDiffusion(nn.Module):
             img = x
             t = t - 1
         return {'xt': xt, 'direct_recons': direct_recons, 'recon': img}
+
+    def _total_forward(self, img):
+        """forward_process.total_forward: decolor = every channel <- channel mean (FP:198-218, independent of the schedule);
+        snow = D(img, T-1) (FP:358-359)"""
+        if isinstance(self.forward_process, DeColorization):
+            img = img.contiguous().float()
+            B, Cc, H, W = img.shape
+            mat = torch.full((1, Cc, Cc), 1.0 / Cc, device=img.device, dtype=torch.float32)
+            zero = torch.zeros(B, dtype=torch.int64, device=img.device)
+            out = torch.empty_like(img)
+            call('cd_chanmix', ptr(None), ptr(img), ptr(out), ptr(mat), ptr(zero), ptr(None), 0, 0, B, Cc, C.c_int64(H * W), 0, stream())
+            return out
+        tt = torch.full((img.shape[0],), self.num_timesteps, dtype=torch.long, device=img.device)
+        return self._degrade(img, tt, -1)
+
+    @torch.no_grad()
+    def all_sample(self, batch_size=16, img=None, t=None, times=None, res_dict=None):
+        """SN:299-339 -> (X_0s, X_ts, init_pred_clone, img_forward_list); lists of CPU tensors.  (The reference does not pass
+        the clean image to sample_one_step here, so this helper only works for decolorization there; same here.)"""
+        self.forward_process.reset_parameters(batch_size=batch_size)
+        if t is None:
+            t = self.num_timesteps
+        if times is None:
+            times = t
+        img = self._total_forward(img)
+        X_0s, X_ts = [], []
+        while times:
+            step = torch.full((img.shape[0],), times - 1, dtype=torch.long, device=img.device)
+            img, direct_recons = self.sample_one_step(img, step)
+            X_0s.append(direct_recons.cpu())
+            X_ts.append(img.cpu())
+            times = times - 1
+        return X_0s, X_ts, None, []
+
+    @torch.no_grad()
+    def forward_and_backward(self, batch_size=16, img=None, t=None, times=None, eval=True):
+        """SN:450-490 -> (Forward, Backward, img): Algorithm 2 written with q_sample of the prediction"""
+        self.denoise_fn.eval()
+        if t is None:
+            t = self.num_timesteps
+        Forward = [img]
+        n_img = img
+        for i in range(t):
+            step = torch.full((batch_size,), i, dtype=torch.long, device=img.device)
+            n_img = self.q_sample(x_start=img, t=step)
+            Forward.append(n_img)
+        Backward = []
+        img = n_img
+        while t:
+            step = torch.full((batch_size,), t - 1, dtype=torch.long, device=img.device)
+            x1_bar = self.denoise_fn(img, step)
+            Backward.append(img)
+            xt_bar = self.q_sample(x_start=x1_bar, t=step)
+            xt_sub1_bar = x1_bar
+            if t - 1 != 0:
+                step2 = torch.full((batch_size,), t - 2, dtype=torch.long, device=img.device)
+                xt_sub1_bar = self.q_sample(x_start=xt_sub1_bar, t=step2)
+            img = img - xt_bar + xt_sub1_bar
+            t = t - 1
+        return Forward, Backward, img

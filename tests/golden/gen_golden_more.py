@@ -134,7 +134,56 @@ def main():
             with torch.no_grad():
                 out['loss:%s|%s' % (routine, lt)] = gd.p_losses(xr, torch.tensor([3, 0, 2]))
     out['q_neg'] = gd.q_sample(xr, torch.tensor([2, -1, 1]))
+    out['func1'] = gd.func[1](xr); out['func2of1'] = gd.func[2](out['func1'])
+    for samp in ('x0_step_down', 'default'):
+        gd = rs.GaussianDiffusion(unet_rs, image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, loss_type='l1',
+                                  resolution_routine='Incremental_factor_2', train_routine='Final', sampling_routine=samp)
+        xdeg = gd.opt(xr)
+        torch.manual_seed(23)
+        xt, dr, img = quiet(gd.gen_sample, batch_size=3, img=xdeg, noise_level=0.02)
+        out['gen_xt:' + samp], out['gen_dr:' + samp], out['gen_img:' + samp] = xt, dr, img
+        X0s, Xts = quiet(gd.all_sample, batch_size=3, img=xr)
+        out['all_X0:' + samp], out['all_Xt:' + samp] = stack(X0s), stack(Xts)
+        F_, B_, img = quiet(gd.forward_and_backward, batch_size=3, img=xr)
+        out['fb_F:' + samp], out['fb_B:' + samp], out['fb_img:' + samp] = stack(F_), stack(B_), img
     save('resolution_train_small', x=xr, **out)
+
+    # ---- defading all_sample (DFG:428-494) and snowification all_sample / forward_and_backward (SN:299-339, 450-490) -----------
+    df = ref_shim.import_reference('defading-diffusion-pytorch', 'defading_diffusion_pytorch')
+    unet_df = quiet(df.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet_df.load_state_dict(sd)
+    torch.manual_seed(97)
+    xf = torch.rand(2, 3, 32, 32) * 2 - 1
+    out = {}
+    for routine, T, samp in [('Incremental', 4, 'x0_step_down'), ('Constant', 3, 'default'), ('Random_Incremental', 4, 'x0_step_down')]:
+        gd = df.GaussianDiffusion(unet_df, image_size=32, device_of_kernel='cpu', channels=3, timesteps=T, loss_type='l1',
+                                  kernel_std=0.6, initial_mask=3, fade_routine=routine, sampling_routine=samp)
+        key = '%s|%d|%s' % (routine, T, samp)
+        torch.manual_seed(78)
+        out['rx:' + key] = torch.randint(0, 33, (2,)); out['ry:' + key] = torch.randint(0, 33, (2,))
+        torch.manual_seed(78)
+        x0l, xtl = quiet(gd.all_sample, batch_size=2, faded_recon_sample=xf)
+        out['x0:' + key], out['xt:' + key] = stack(x0l), stack(xtl)
+    save('defading_all_small', x=xf, **out)
+
+    sn = ref_shim.import_reference('snowification', 'diffusion')
+    unet_sn = quiet(db.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet_sn.load_state_dict(sd)
+    torch.manual_seed(99)
+    xs = torch.rand(3, 3, 32, 32) * 2 - 1
+    out = {}
+    for fpt, kw, T, samp in [('Decolorization', dict(decolor_routine='Linear', decolor_total_remove=True), 5, 'x0_step_down'),
+                             ('Decolorization', dict(decolor_routine='Constant', decolor_ema_factor=0.8, decolor_total_remove=False), 4, 'default'),
+                             ('Snow', dict(snow_level=1, results_folder='/tmp'), 4, 'x0_step_down')]:
+        gd = quiet(sn.GaussianDiffusion, unet_sn, image_size=(32, 32) if fpt == 'Snow' else 32, device_of_kernel='cpu', channels=3,
+                   timesteps=T, loss_type='l1', forward_process_type=fpt, train_routine='Final', sampling_routine=samp, **kw)
+        key = '%s|%s|%d|%s' % (fpt, '-'.join('%s=%s' % (k, v) for k, v in sorted(kw.items()) if k != 'results_folder'), T, samp)
+        if fpt == 'Decolorization':
+            X0, Xt, _, _ = quiet(gd.all_sample, batch_size=3, img=xs)
+            out['all_X0:' + key], out['all_Xt:' + key] = stack(X0), stack(Xt)
+        F_, B_, img = quiet(gd.forward_and_backward, batch_size=3, img=xs)
+        out['fb_F:' + key], out['fb_B:' + key], out['fb_img:' + key] = stack(F_), stack(B_), img
+    save('snow_more_small', x=xs, **out)
 
     # ---- DDPM-style `Model` (Model2.py): L1-loss gradients of every parameter (dropout inactive: eval mode) -----------
     z = np.load(os.path.join(HERE, 'model2_small.npz'))
