@@ -148,6 +148,22 @@ def main():
         out['fb_F:' + samp], out['fb_B:' + samp], out['fb_img:' + samp] = stack(F_), stack(B_), img
     save('resolution_train_small', x=xr, **out)
 
+    # ---- denoising baseline: all_sample (DN:474-515) and forward_and_backward (DN:437-472; noise drawn inside: seeded) -------
+    dn = ref_shim.import_reference('denoising-diffusion-pytorch', 'denoising_diffusion_pytorch')
+    unet_dn = quiet(dn.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    unet_dn.load_state_dict(sd)
+    torch.manual_seed(101)
+    xd = torch.rand(2, 3, 32, 32) * 2 - 1
+    nd = torch.randn(2, 3, 32, 32)
+    gd = dn.GaussianDiffusion(unet_dn, image_size=32, channels=3, timesteps=5, loss_type='l1')
+    out = {}
+    X1, X2, Xt = quiet(gd.all_sample, batch_size=2, img=nd)
+    out['all_X1'], out['all_X2'], out['all_Xt'] = stack(X1), stack(X2), stack(Xt)
+    torch.manual_seed(29)
+    F_, B_, img = quiet(gd.forward_and_backward, batch_size=2, img=xd)
+    out['fb_F'], out['fb_B'], out['fb_img'] = stack(F_), stack(B_), img
+    save('denoise_more_small', x=xd, noise=nd, **out)
+
     # ---- defading all_sample (DFG:428-494) and snowification all_sample / forward_and_backward (SN:299-339, 450-490) -----------
     df = ref_shim.import_reference('defading-diffusion-pytorch', 'defading_diffusion_pytorch')
     unet_df = quiet(df.Unet, dim=32, dim_mults=(1, 2), channels=3)
