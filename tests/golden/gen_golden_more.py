@@ -148,6 +148,31 @@ def main():
         out['fb_F:' + samp], out['fb_B:' + samp], out['fb_img:' + samp] = stack(F_), stack(B_), img
     save('resolution_train_small', x=xr, **out)
 
+    # ---- Unet constructor options used by the drivers' flags (--residual, --remove_time_embed) and out_dim (DB:192-200) ----
+    out = {}
+    torch.manual_seed(103)
+    xo = torch.rand(2, 3, 32, 32) * 2 - 1
+    to = torch.tensor([1, 6])
+    tgt5 = torch.rand(2, 5, 32, 32) * 2 - 1
+    for tag, kw in (('residual', dict(residual=True)), ('notime', dict(with_time_emb=False)), ('outdim', dict(out_dim=5))):
+        torch.manual_seed(0)
+        uo = quiet(db.Unet, dim=32, dim_mults=(1, 2), channels=3, **kw)
+        own = uo.state_dict()                      # weights: unet_small.npz wherever the key and shape exist there
+        uo.load_state_dict({k: (sd[k] if k in sd and sd[k].shape == v.shape else v) for k, v in own.items()})
+        y = uo(xo, to)
+        target = tgt5 if tag == 'outdim' else xo.flip(0)
+        loss = ((target - y) ** 2).mean()
+        loss.backward()
+        out[tag + ':y'], out[tag + ':loss'] = y.detach(), loss.detach()
+        for n, p_ in uo.state_dict().items():
+            if n not in sd or sd[n].shape != p_.shape:
+                out[tag + ':sd:' + n] = p_.clone()         # only what unet_small.npz does not hold (the out_dim = 5 projection)
+        for n, p_ in uo.named_parameters():
+            g_ = p_.grad.reshape(-1)
+            out[tag + ':gnorm:' + n] = g_.double().norm().float()
+            out[tag + ':gsub:' + n] = g_[::max(1, g_.numel() // 256)].clone()
+    save('unet_options_small', x=xo, t=to, tgt5=tgt5, **out)
+
     # ---- denoising baseline: all_sample (DN:474-515) and forward_and_backward (DN:437-472; noise drawn inside: seeded) -------
     dn = ref_shim.import_reference('denoising-diffusion-pytorch', 'denoising_diffusion_pytorch')
     unet_dn = quiet(dn.Unet, dim=32, dim_mults=(1, 2), channels=3)

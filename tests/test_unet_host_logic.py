@@ -152,3 +152,29 @@ def test_deblurring_sampling_helpers_through_the_public_class(emu):
         torch.manual_seed(17)
         xt, dr, img = gd.gen_sample(batch_size=2, img=x, noise_level=0.05)
         assert rel(xt, gf['gen_xt:' + key]) < 1e-5 and rel(img, gf['gen_img:' + key]) < 1e-4, key
+
+
+@pytest.mark.parametrize('tag,kw', [('residual', dict(residual=True)), ('notime', dict(with_time_emb=False)), ('outdim', dict(out_dim=5))])
+def test_unet_constructor_options(emu, tag, kw):
+    """Unet(residual=True) / Unet(with_time_emb=False) (the drivers' --residual / --remove_time_embed flags) / out_dim (DB:192-200):
+    forward, L2 loss and every parameter gradient against the reference"""
+    import cold_diffusion_models_b200 as cdm
+    g = load('unet_options_small')
+    with contextlib.redirect_stdout(io.StringIO()):
+        u = cdm.Unet(dim=32, dim_mults=(1, 2), channels=3, **kw)
+    pre = tag + ':sd:'
+    base = {k[3:]: v for k, v in load('unet_small').items() if k.startswith('sd:')}
+    extra = {k[len(pre):]: v for k, v in g.items() if k.startswith(pre)}
+    u.load_state_dict({k: extra.get(k, base.get(k)) for k in u.state_dict()})
+    y = u(g['x'], g['t'])
+    assert rel(y.detach(), g[tag + ':y']) < 2e-6
+    target = g['tgt5'] if tag == 'outdim' else g['x'].flip(0)
+    loss = ((target - y) ** 2).mean()
+    assert abs(loss.item() - g[tag + ':loss'].item()) < 1e-6
+    loss.backward()
+    worst = (-1.0, '')
+    for n, p_ in u.named_parameters():
+        gr = p_.grad.reshape(-1)
+        assert abs(gr.double().norm().item() - g[tag + ':gnorm:' + n].item()) <= 1e-4 * g[tag + ':gnorm:' + n].item() + 1e-9, n
+        worst = max(worst, (rel(gr[::max(1, gr.numel() // 256)], g[tag + ':gsub:' + n]), n))
+    assert worst[0] < 1e-4, worst
