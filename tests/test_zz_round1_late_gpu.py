@@ -1,0 +1,161 @@
+"""GPU parity tests added after the round-1 GPU budget was spent: every path below is checked on CPU against the same reference
+goldens through the emulated C ABI (tests/test_*_host_logic.py) but has not run on a B200 yet.  The file sorts last so that the
+already-validated GPU tests run first under `pytest -x`."""
+import io
+import contextlib
+import pytest
+import torch
+
+from test_unet_gpu import load, rel, make_unet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def small():
+    g = load('unet_small')
+    sd = {k[3:]: v for k, v in g.items() if k.startswith('sd:')}
+    return g, sd, make_unet(32, (1, 2), 3, sd)
+
+
+@pytest.fixture(scope='module')
+def unet(small):
+    return small[2]
+
+
+def stack(lst):
+    return torch.stack([x.detach().float().cpu() for x in lst])
+
+
+def test_individual_incremental_routine_matches_reference_golden(small):
+    """the seventh blur routine (kernel size 2i+1, sigma 2k; `sample` starts from the single step-t kernel, DB:379-383, 401-402)"""
+    import cold_diffusion_models_b200 as cdm
+    g = load('individual_small')
+    _, sd, u = small
+    x = g['x'].cuda()
+    for samp in ('default', 'x0_step_down'):
+        gd = cdm.GaussianDiffusion(u, image_size=32, device_of_kernel='cuda', channels=3, timesteps=4, kernel_std=0.1, kernel_size=3,
+                                   blur_routine='Individual_Incremental', sampling_routine=samp).cuda()
+        for i, kconv in enumerate(gd.gaussian_kernels):
+            assert torch.equal(kconv.weight[0, 0].cpu(), g['w%d' % i])
+        tt = torch.tensor([3, 1]).cuda()
+        assert torch.allclose(gd.q_sample(x, tt).cpu(), g['q'], atol=3e-6)
+        with torch.no_grad():
+            assert abs(gd.p_losses(x, tt).item() - g['loss'].item()) < 3e-4
+        xt, dr, img = gd.sample(batch_size=2, img=x)
+        assert rel(xt, g['xt:' + samp]) < 1e-5 and rel(dr, g['dr:' + samp]) < 1e-3 and rel(img, g['img:' + samp]) < 2e-3, samp
+
+
+def test_resolution_step_routine_and_negative_t_rows_match_reference_golden(small):
+    """'Step' train routine (RS:742-755; no random draws) and the t = -1 rows of q_sample, which take the level max(t) of the
+    batch in the reference (RS:645 tests the loop index instead of t)"""
+    from cold_diffusion_models_b200.resolution_diffusion_pytorch import GaussianDiffusion
+    g = load('resolution_train_small')
+    _, sd, u = small
+    x = g['x'].cuda()
+    for lt in ('l1', 'l2'):
+        gd = GaussianDiffusion(u, image_size=32, device_of_kernel='cuda', channels=3, timesteps=4, loss_type=lt,
+                               resolution_routine='Incremental_factor_2', train_routine='Step', sampling_routine='x0_step_down').cuda()
+        with torch.no_grad():
+            assert abs(gd.p_losses(x, torch.tensor([3, 0, 2]).cuda()).item() - g['loss:Step|' + lt].item()) < 3e-4, lt
+    assert torch.allclose(gd.q_sample(x, torch.tensor([2, -1, 1]).cuda()).cpu(), g['q_neg'], atol=3e-6)
+
+
+def test_deblur_sample_from_blur_and_all_sample_match_reference_golden(unet):
+    """sample_from_blur with a partial blur (start .. t-1, DB:863-925) and the all_sample lists (DB:609-689).  Multi-step
+    trajectories on the TF32 path: 4e-3 (the single-forward tolerance is 1e-3; errors compound over the reverse steps)"""
+    import cold_diffusion_models_b200 as cdm
+    g = load('fb_small')
+    x = g['x'].cuda()
+    for key in sorted(k[4:] for k in g if k.startswith('img:')):
+        routine, ks, std, T, samp = key.split('|')
+        gd = cdm.GaussianDiffusion(unet, image_size=32, device_of_kernel='cuda', channels=3, timesteps=int(T), kernel_std=float(std),
+                                   kernel_size=int(ks), blur_routine=routine, sampling_routine=samp).cuda()
+        for start in (0, 1):
+            xt, dr, img = gd.sample_from_blur(batch_size=2, img=x, start=start)
+            pre = ':%d:' % start + key
+            assert rel(xt, g['sfb_xt' + pre]) < 1e-5 and rel(dr, g['sfb_dr' + pre]) < 1e-3 and rel(img, g['sfb_img' + pre]) < 4e-3, pre
+        X0s, Xts = gd.all_sample(batch_size=2, img=x)
+        assert rel(stack(X0s), g['all_X0:' + key]) < 4e-3 and rel(stack(Xts), g['all_Xt:' + key]) < 4e-3, key
+
+
+def test_sampling_helpers_of_the_other_packages_match_reference_golden(unet):
+    """resolution all_sample / forward_and_backward / func[i] (RS:505-616, 389-414), defading all_sample (DFG:428-494),
+    snowification / decolor all_sample and forward_and_backward (SN:299-339, 450-490)"""
+    import io
+    import contextlib
+    from cold_diffusion_models_b200.resolution_diffusion_pytorch import GaussianDiffusion as RSGD
+    from cold_diffusion_models_b200.defading_diffusion_pytorch import GaussianDiffusion as DFGD
+    from cold_diffusion_models_b200.snowification_diffusion import GaussianDiffusion as SNGD
+    g = load('resolution_train_small')
+    x = g['x'].cuda()
+    for samp in ('x0_step_down', 'default'):
+        gd = RSGD(unet, image_size=32, device_of_kernel='cuda', channels=3, timesteps=4, loss_type='l1',
+                  resolution_routine='Incremental_factor_2', train_routine='Final', sampling_routine=samp).cuda()
+        X0s, Xts = gd.all_sample(batch_size=3, img=x)
+        assert rel(stack(X0s), g['all_X0:' + samp]) < 4e-3 and rel(stack(Xts), g['all_Xt:' + samp]) < 4e-3, samp
+        F_, B_, img = gd.forward_and_backward(batch_size=3, img=x)
+        assert rel(stack(F_), g['fb_F:' + samp]) < 1e-5 and rel(stack(B_), g['fb_B:' + samp]) < 4e-3 and rel(img, g['fb_img:' + samp]) < 4e-3, samp
+    f1 = gd.func[1](x)
+    assert torch.allclose(f1.cpu(), g['func1'], atol=3e-6) and torch.allclose(gd.func[2](f1).cpu(), g['func2of1'], atol=3e-6)
+
+    g = load('defading_all_small')
+    x = g['x'].cuda()
+    for key in sorted(k[3:] for k in g if k.startswith('x0:')):
+        routine, T, samp = key.split('|')
+        gd = DFGD(unet, image_size=32, device_of_kernel='cuda', channels=3, timesteps=int(T), loss_type='l1', kernel_std=0.6, initial_mask=3,
+                  fade_routine=routine, sampling_routine=samp).cuda()
+        off = (g['rx:' + key].cuda(), g['ry:' + key].cuda()) if 'Random' in routine else (None, None)
+        x0l, xtl = gd.all_sample(batch_size=2, faded_recon_sample=x, _offsets=off)
+        assert rel(stack(x0l), g['x0:' + key]) < 4e-3 and rel(stack(xtl), g['xt:' + key]) < 4e-3, key
+
+    g = load('snow_more_small')
+    x = g['x'].cuda()
+    for key in sorted(k[5:] for k in g if k.startswith('fb_F:')):
+        fpt, kws, T, samp = key.split('|')
+        kw = {}
+        for item in kws.split('-'):
+            k, v = item.split('=')
+            kw[k] = (v == 'True') if v in ('True', 'False') else (float(v) if '.' in v else (int(v) if v.isdigit() else v))
+        if fpt == 'Snow':
+            kw['results_folder'] = '/tmp'
+        with contextlib.redirect_stdout(io.StringIO()):
+            gd = SNGD(unet, image_size=(32, 32) if fpt == 'Snow' else 32, device_of_kernel='cuda', channels=3, timesteps=int(T),
+                      loss_type='l1', forward_process_type=fpt, train_routine='Final', sampling_routine=samp, **kw).cuda()
+        if fpt == 'Decolorization':
+            X0, Xt, _, _ = gd.all_sample(batch_size=3, img=x)
+            assert rel(stack(X0), g['all_X0:' + key]) < 4e-3 and rel(stack(Xt), g['all_Xt:' + key]) < 4e-3, key
+        F_, B_, img = gd.forward_and_backward(batch_size=3, img=x)
+        assert rel(stack(F_), g['fb_F:' + key]) < 1e-5 and rel(stack(B_), g['fb_B:' + key]) < 4e-3 and rel(img, g['fb_img:' + key]) < 4e-3, key
+
+
+@pytest.mark.parametrize('tag,kw', [('residual', dict(residual=True)), ('notime', dict(with_time_emb=False)), ('outdim', dict(out_dim=5))])
+def test_unet_constructor_options_match_reference_golden(tag, kw):
+    """Unet(residual=True) / Unet(with_time_emb=False) (the drivers' --residual / --remove_time_embed flags) / out_dim:
+    forward on the TF32 path (1e-3), forward + every gradient on the fp32 CUDA-core path against the reference"""
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200.ops import CONV_SIMT
+    g = load('unet_options_small')
+    with contextlib.redirect_stdout(io.StringIO()):
+        u = cdm.Unet(dim=32, dim_mults=(1, 2), channels=3, **kw)
+    pre = tag + ':sd:'
+    base = {k[3:]: v for k, v in load('unet_small').items() if k.startswith('sd:')}
+    extra = {k[len(pre):]: v for k, v in g.items() if k.startswith(pre)}
+    u.load_state_dict({k: extra.get(k, base.get(k)) for k in u.state_dict()})
+    u = u.cuda()
+    x, t = g['x'].cuda(), g['t'].cuda()
+    with torch.no_grad():
+        assert rel(u(x, t), g[tag + ':y']) < 1e-3
+    u.engine.conv_impl = CONV_SIMT
+    y = u(x, t)
+    assert rel(y.detach(), g[tag + ':y']) < 2e-5
+    target = (g['tgt5'] if tag == 'outdim' else g['x'].flip(0)).cuda()
+    loss = ((target - y) ** 2).mean()
+    assert abs(loss.item() - g[tag + ':loss'].item()) < 2e-5
+    loss.backward()
+    torch.cuda.synchronize()
+    worst = (-1.0, '')
+    for n, p_ in u.named_parameters():
+        gr = p_.grad.reshape(-1).cpu()
+        worst = max(worst, (rel(gr[::max(1, gr.numel() // 256)], g[tag + ':gsub:' + n]), n))
+    assert worst[0] < 5e-4, worst
