@@ -80,8 +80,7 @@ class GaussianDiffusion(nn.Module):
             ops[i] = A.astype(np.float32)
         self.register_buffer('_ops_cum', torch.from_numpy(ops), persistent=False)
         self.register_buffer('_ops_step', torch.from_numpy(steps), persistent=False)
-        # the reference exposes `func`: a list of per-step callables img -> degraded img (RS:389-414); same here, one launch each
-        self.func = [(lambda img, _i=i: self._apply_step(img, _i)) for i in range(len(specs))]
+        self._nsteps = len(specs)
         self.train_routine = train_routine
         self.sampling_routine = sampling_routine
 
@@ -102,6 +101,13 @@ class GaussianDiffusion(nn.Module):
         out = torch.empty_like(x)
         call('cd_blur_apply', ptr(x), ptr(out), ptr(self._ops_step), ptr(None), int(i), B, Cc, H, self.num_timesteps, 0, 0, stream())
         return out
+
+    @property
+    def func(self):
+        """the reference exposes `func`: a list of per-step callables img -> degraded img (RS:389-414); same here, one launch
+        each (built on access so that deep copies of the module bind to the copy)"""
+        import functools
+        return [functools.partial(self._apply_step, i=i) for i in range(self._nsteps)]
 
     def get_funcs(self):
         return self.func
