@@ -224,6 +224,9 @@ def main():
             out['all_X0:' + key], out['all_Xt:' + key] = stack(X0), stack(Xt)
         F_, B_, img = quiet(gd.forward_and_backward, batch_size=3, img=xs)
         out['fb_F:' + key], out['fb_B:' + key], out['fb_img:' + key] = stack(F_), stack(B_), img
+        if fpt == 'Decolorization':
+            xq = gd.q_sample(xs, torch.tensor([T - 1, 1, 2]))
+            out['ms:' + key] = quiet(gd.sample_multi_step, xq, torch.tensor([T - 1, 1, 2]), torch.tensor([1, 1, 0]))
     save('snow_more_small', x=xs, **out)
 
     # ---- DDPM-style `Model` (Model2.py): L1-loss gradients of every parameter (dropout inactive: eval mode) -----------
