@@ -229,6 +229,31 @@ def main():
             out['ms:' + key] = quiet(gd.sample_multi_step, xq, torch.tensor([T - 1, 1, 2]), torch.tensor([1, 1, 0]))
     save('snow_more_small', x=xs, **out)
 
+    # ---- checkpoint wire format: state_dict keys and shapes of every package's GaussianDiffusion (+ Model) ------------------
+    import json
+    fmt = {}
+
+    def record(tag, module):
+        fmt[tag] = {k: list(v.shape) for k, v in module.state_dict().items()}
+    mk = lambda mod: quiet(mod.Unet, dim=32, dim_mults=(1, 2), channels=3)
+    record('deblurring', db.GaussianDiffusion(mk(db), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, kernel_std=0.15,
+                                              kernel_size=7, blur_routine='Exponential_reflect'))
+    record('deblurring_model', db.GaussianDiffusion(db.Model(resolution=16, in_channels=3, out_ch=3, ch=32, ch_mult=(1, 2), num_res_blocks=2,
+                                                             attn_resolutions=(8,), dropout=0.1), image_size=16, device_of_kernel='cpu',
+                                                    channels=3, timesteps=3, kernel_std=0.1, kernel_size=3, blur_routine='Special_6_routine'))
+    record('resolution', rs.GaussianDiffusion(mk(rs), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4,
+                                              resolution_routine='Incremental_factor_2'))
+    record('defading', df.GaussianDiffusion(mk(df), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, kernel_std=0.6,
+                                            initial_mask=3, fade_routine='Incremental'))
+    record('denoising', dn.GaussianDiffusion(mk(dn), image_size=32, channels=3, timesteps=5))
+    record('demixing', dm.GaussianDiffusion(mk(dm), image_size=32, channels=3, timesteps=5))
+    record('defading_generation', dg.GaussianDiffusion(mk(dg), image_size=32, channels=3, timesteps=4, kernel_std=0.6, initial_mask=3))
+    record('decolor', quiet(sn.GaussianDiffusion, mk(db), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4,
+                            forward_process_type='Decolorization', decolor_routine='Linear'))
+    with open(os.path.join(HERE, 'state_dict_format.json'), 'w') as f:
+        json.dump(fmt, f, indent=0, sort_keys=True)
+    print('wrote state_dict_format.json', sum(len(v) for v in fmt.values()), 'keys')
+
     # ---- DDPM-style `Model` (Model2.py): L1-loss gradients of every parameter (dropout inactive: eval mode) -----------
     z = np.load(os.path.join(HERE, 'model2_small.npz'))
     msd = {k[3:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd:')}

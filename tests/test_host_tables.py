@@ -52,3 +52,39 @@ def test_package_exports_mirror_the_reference_inits():
     assert kw['kernel_std'].default == 0.15 and kw['initial_mask'].default == 11 and kw['reverse'].default is False
     kw = inspect.signature(demixing_diffusion_pytorch.GaussianDiffusion.gen_sample).parameters
     assert list(kw)[1:] == ['batch_size', 'img', 'noise_level', 't']
+
+
+def test_state_dict_wire_format_of_every_package_matches_the_reference():
+    """checkpoints are {'step','model','ema'} of GaussianDiffusion.state_dict() (DB:1140-1149): every key and shape the reference
+    writes must exist with the same shape here (tests/golden/state_dict_format.json, recorded from the unmodified reference)"""
+    import io, json, contextlib
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200 import (resolution_diffusion_pytorch as rs, defading_diffusion_pytorch as df,
+                                            denoising_diffusion_pytorch as dn, demixing_diffusion_pytorch as dm,
+                                            defading_generation_diffusion_pytorch as dg, snowification_diffusion as sn)
+    fmt = json.load(open(os.path.join(G, 'state_dict_format.json')))
+    with contextlib.redirect_stdout(io.StringIO()):
+        mk = lambda: cdm.Unet(dim=32, dim_mults=(1, 2), channels=3)
+        built = {
+            'deblurring': cdm.GaussianDiffusion(mk(), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, kernel_std=0.15,
+                                                kernel_size=7, blur_routine='Exponential_reflect'),
+            'deblurring_model': cdm.GaussianDiffusion(cdm.Model(resolution=16, in_channels=3, out_ch=3, ch=32, ch_mult=(1, 2), num_res_blocks=2,
+                                                                attn_resolutions=(8,), dropout=0.1), image_size=16, device_of_kernel='cpu',
+                                                      channels=3, timesteps=3, kernel_std=0.1, kernel_size=3, blur_routine='Special_6_routine'),
+            'resolution': rs.GaussianDiffusion(mk(), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4,
+                                               resolution_routine='Incremental_factor_2'),
+            'defading': df.GaussianDiffusion(mk(), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, kernel_std=0.6,
+                                             initial_mask=3, fade_routine='Incremental'),
+            'denoising': dn.GaussianDiffusion(mk(), image_size=32, channels=3, timesteps=5),
+            'demixing': dm.GaussianDiffusion(mk(), image_size=32, channels=3, timesteps=5),
+            'defading_generation': dg.GaussianDiffusion(mk(), image_size=32, channels=3, timesteps=4, kernel_std=0.6, initial_mask=3),
+            'decolor': sn.GaussianDiffusion(mk(), image_size=32, device_of_kernel='cpu', channels=3, timesteps=4,
+                                            forward_process_type='Decolorization', decolor_routine='Linear'),
+        }
+    for tag, ref in fmt.items():
+        mine = {k: list(v.shape) for k, v in built[tag].state_dict().items()}
+        missing = [k for k in ref if k not in mine]
+        extra = [k for k in mine if k not in ref]
+        assert not missing and not extra, (tag, missing[:5], extra[:5])
+        bad = [k for k in ref if mine[k] != ref[k]]
+        assert not bad, (tag, bad[:5])
