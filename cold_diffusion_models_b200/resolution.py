@@ -112,6 +112,21 @@ class GaussianDiffusion(nn.Module):
     def get_funcs(self):
         return self.func
 
+    @torch.no_grad()
+    def transform_func(self, img, dec_size, mode, do_blur=False):
+        """RS:354-387: one pixelation step with explicit parameters (shrink to S - dec_size with `mode`, back with nearest-exact,
+        optionally inside a 3x3 sigma-0.5 reflect blur).  The operator is tabulated on first use and applied in one launch."""
+        S = img.shape[2]
+        key = (S, int(dec_size), mode, bool(do_blur))
+        cache = self.__dict__.setdefault('_transform_ops', {})
+        if key not in cache:
+            cache[key] = torch.from_numpy(step_matrix(S, int(dec_size), mode, bool(do_blur)).astype(np.float32))[None].contiguous().to(img.device)
+        x = img.contiguous().float()
+        B, Cc, H, W = x.shape
+        out = torch.empty_like(x)
+        call('cd_blur_apply', ptr(x), ptr(out), ptr(cache[key]), ptr(None), 0, B, Cc, H, 1, 0, 0, stream())
+        return out
+
     def q_sample(self, x_start, t):
         """RS:630-652.  Rows with t_b = -1 (the 'Step' train routine at t = 0, RS:745) were meant to pass through, but the
         reference tests the loop index instead of t (`if step != -1`, RS:645), so they take `all_blurs[-1]`: the level

@@ -1,6 +1,6 @@
 """snowification/diffusion (== decolor-diffusion/diffusion) surface: GaussianDiffusion, Trainer, forward processes"""
 from ..snowification import GaussianDiffusion, DeColorization, Snow, ForwardProcessBase
-from ..trainer import Trainer
+from ..trainer import SnowificationTrainer as Trainer, get_dataset
 from ..unet import Unet
 
-__all__ = ['GaussianDiffusion', 'Trainer', 'DeColorization', 'Snow', 'ForwardProcessBase', 'Unet']
+__all__ = ['GaussianDiffusion', 'Trainer', 'DeColorization', 'Snow', 'ForwardProcessBase', 'Unet', 'get_dataset']

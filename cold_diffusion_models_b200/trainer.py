@@ -193,6 +193,10 @@ class Trainer(object):
         """the image the periodic `sample` starts from (DB:1209)"""
         return next(self.dl).cuda()
 
+    def _periodic_sample(self, og_img):
+        """-> (xt, direct_recons, recon) of the EMA model every `save_and_sample_every` steps (DB:1210)"""
+        return _unwrap(self.ema_model).sample(batch_size=self.batch_size, img=og_img)
+
     def train_step(self, batches=None):
         """one optimizer step = gradient_accumulate_every micro-batches (DB:1188-1204). Returns mean loss (tensor)."""
         u_loss = None
@@ -223,7 +227,7 @@ class Trainer(object):
                 from torchvision import utils
                 milestone = self.step // self.save_and_sample_every
                 og_img = self._sample_start()
-                xt, direct_recons, all_images = _unwrap(self.ema_model).sample(batch_size=self.batch_size, img=og_img)
+                xt, direct_recons, all_images = self._periodic_sample(og_img)
                 for name, img in (('og', og_img), ('recon', all_images), ('direct_recons', direct_recons), ('xt', xt)):
                     utils.save_image((img + 1) * 0.5, str(self.results_folder / f'sample-{name}-{milestone}.png'), nrow=6)
                 acc_loss = acc_loss / (self.save_and_sample_every + 1)
@@ -248,17 +252,36 @@ class DenoisingTrainer(Trainer):
                            device='cuda')                       # DN:757-762
 
 
+class DefadingTrainer(Trainer):
+    """Trainer of defading_diffusion_pytorch (DFG:654-811): its own defaults and `sample(batch_size, faded_recon_sample)`"""
+
+    def __init__(self, diffusion_model, folder, *, ema_decay=0.995, image_size=128, train_batch_size=32, train_lr=2e-5,
+                 train_num_steps=700000, gradient_accumulate_every=2, fp16=False, step_start_ema=2000, update_ema_every=10,
+                 save_and_sample_every=10000, results_folder='./results', load_path=None, dataset=None):
+        super().__init__(diffusion_model, folder, ema_decay=ema_decay, image_size=image_size, train_batch_size=train_batch_size,
+                         train_lr=train_lr, train_num_steps=train_num_steps, gradient_accumulate_every=gradient_accumulate_every,
+                         fp16=fp16, step_start_ema=step_start_ema, update_ema_every=update_ema_every,
+                         save_and_sample_every=save_and_sample_every, results_folder=results_folder, load_path=load_path,
+                         dataset=dataset)
+
+    def _periodic_sample(self, og_img):
+        return _unwrap(self.ema_model).sample(batch_size=self.batch_size, faded_recon_sample=og_img)      # DFG:789
+
+
 class DemixingTrainer(Trainer):
     """Trainer of demixing_diffusion_pytorch: two image folders, forward(x1, x2) on one batch of each (DM:600-772)."""
     _aug_datasets = ('train',)
 
-    def __init__(self, diffusion_model, folder1, folder2, **kw):
-        load_path = kw.pop('load_path', None)
-        super().__init__(diffusion_model, folder1, **kw)
+    def __init__(self, diffusion_model, folder1, folder2, *, ema_decay=0.995, image_size=128, train_batch_size=32, train_lr=2e-5,
+                 train_num_steps=100000, gradient_accumulate_every=2, fp16=False, step_start_ema=2000, update_ema_every=10,
+                 save_and_sample_every=1000, results_folder='./results', load_path=None, dataset=None, shuffle=True):
+        super().__init__(diffusion_model, folder1, ema_decay=ema_decay, image_size=image_size, train_batch_size=train_batch_size,
+                         train_lr=train_lr, train_num_steps=train_num_steps, gradient_accumulate_every=gradient_accumulate_every,
+                         fp16=fp16, step_start_ema=step_start_ema, update_ema_every=update_ema_every,
+                         save_and_sample_every=save_and_sample_every, results_folder=results_folder, load_path=load_path,
+                         dataset=dataset, shuffle=shuffle)
         self.ds1, self.dl1 = self.ds, self.dl
-        self.ds2, self.dl2 = self._make_loader(folder2, kw.get('dataset'), kw.get('shuffle', True), seed=4321)
-        if load_path is not None:
-            self.load(load_path)
+        self.ds2, self.dl2 = self._make_loader(folder2, dataset, shuffle, seed=4321)
 
     def _next(self):
         return next(self.dl1), next(self.dl2)
@@ -284,6 +307,106 @@ class DefadingGenerationTrainer(Trainer):
 
     def _sample_start(self):
         return self._colour(self.batch_size)                    # DFGEN:796-803
+
+
+def snow_get_transform(image_size, random_aug=False, resize=False):
+    """torchvision transform of snowification/diffusion/get_dataset.py:5-34 (and Dataset.get_transform, SN:502-528)"""
+    from torchvision import transforms
+    to_pm1 = [transforms.ToTensor(), transforms.Lambda(lambda t: (t * 2) - 1)]
+    if image_size[0] == 64:
+        return transforms.Compose([transforms.CenterCrop((128, 128)), transforms.Resize(image_size)] + to_pm1)
+    if not random_aug:
+        return transforms.Compose(([transforms.Resize(image_size)] if resize else []) + [transforms.CenterCrop(image_size)] + to_pm1)
+    jitter = transforms.ColorJitter(0.8, 0.8, 0.8, 0.2)
+    return transforms.Compose([transforms.RandomResizedCrop(size=image_size), transforms.RandomHorizontalFlip(),
+                               transforms.RandomApply([jitter], p=0.8)] + to_pm1)
+
+
+def get_dataset(name, folder, image_size, random_aug=False):
+    """torchvision datasets by name (snowification/diffusion/get_dataset.py:44-57); `download=True` of the reference needs a
+    network, the files must already be under `folder` here"""
+    from torchvision import datasets
+    tf = lambda **k: snow_get_transform(image_size, random_aug=random_aug, **k)
+    if name in ('cifar10_train', 'cifar10_test'):
+        return datasets.CIFAR10(folder, train=name.endswith('train'), transform=tf())
+    if name in ('CelebA_train', 'CelebA_test'):
+        return datasets.CelebA(folder, split=name.split('_')[1], transform=tf())
+    if name in ('flower_train', 'flower_test'):
+        return datasets.Flowers102(folder, split=name.split('_')[1], transform=tf(resize=True))
+    return None
+
+
+class SnowificationTrainer(Trainer):
+    """Trainer of snowification/diffusion (== decolor-diffusion/diffusion), SN:563-760: the image size comes from the model,
+    torchvision datasets by name, `sample()` returns a dict whose entries are all saved, `save(save_with_time_stamp)`."""
+
+    def __init__(self, diffusion_model, folder, *, ema_decay=0.995, image_size=128, train_batch_size=32, train_lr=2e-5,
+                 train_num_steps=100000, gradient_accumulate_every=2, fp16=False, step_start_ema=2000, update_ema_every=10,
+                 save_and_sample_every=5000, save_with_time_stamp_every=50000, results_folder='./results', load_path=None,
+                 random_aug=False, torchvision_dataset=False, dataset=None, to_lab=False, order_seed=-1):
+        if to_lab:
+            raise NotImplementedError("to_lab (kornia Lab colour path) is out of scope of the B200 engine")
+        core = _unwrap(diffusion_model)
+        size = core.image_size
+        self._size2 = tuple(size) if isinstance(size, (tuple, list)) else (size, size)
+        self.random_aug, self.torchvision_dataset, self.to_lab, self.order_seed = random_aug, torchvision_dataset, to_lab, int(order_seed)
+        self.save_with_time_stamp_every = save_with_time_stamp_every
+        self.num_timesteps = core.num_timesteps
+        super().__init__(diffusion_model, folder, ema_decay=ema_decay, image_size=self._size2[0], train_batch_size=train_batch_size,
+                         train_lr=train_lr, train_num_steps=train_num_steps, gradient_accumulate_every=gradient_accumulate_every,
+                         fp16=fp16, step_start_ema=step_start_ema, update_ema_every=update_ema_every,
+                         save_and_sample_every=save_and_sample_every, results_folder=results_folder, load_path=load_path,
+                         dataset=dataset, shuffle=True)
+        self.results_folder.mkdir(parents=True, exist_ok=True)
+        self.post_process_func = lambda x: x
+        self.data_loader = None
+
+    def _make_loader(self, folder, dataset, shuffle, seed):
+        if folder is None or dataset == 'synthetic':
+            return super()._make_loader(folder, dataset, shuffle, seed)
+        if self.torchvision_dataset:
+            ds = get_dataset(dataset, folder, self._size2, random_aug=self.random_aug)
+        else:
+            ds = ImageFolderDataset(folder, self._size2[0])
+            ds.transform = snow_get_transform(self._size2, random_aug=self.random_aug) if self._size2[0] != 256 else ds.transform
+        loader = data.DataLoader(ds, batch_size=self.batch_size, shuffle=True, pin_memory=True, num_workers=4)
+
+        def gen():
+            while True:
+                for d in loader:                          # torchvision datasets yield (image, label)
+                    yield d[0] if isinstance(d, (list, tuple)) else d
+        return ds, gen()
+
+    def _process_item(self, x):
+        return x[0] if isinstance(x, (list, tuple)) else x
+
+    def save(self, save_with_time_stamp=False):
+        d = {'step': self.step, 'model': self.model.state_dict(), 'ema': self.ema_model.state_dict()}
+        name = f'model_{self.step}.pt' if save_with_time_stamp else 'model.pt'
+        torch.save(d, str(self.results_folder / name))
+
+    def train(self):
+        import time
+        start_time = time.time()
+        while self.step < self.train_num_steps:
+            loss = self.train_step()
+            print(f'{self.step}: {loss.item()}')
+            if self.step != 0 and self.step % 100 == 0:
+                print(f'time for 100 steps: {time.time() - start_time}')
+                start_time = time.time()
+            if self.step != 0 and self.step % self.save_and_sample_every == 0:
+                from torchvision import utils
+                milestone = self.step // self.save_and_sample_every
+                og_img = self._sample_start()
+                sample_dict = _unwrap(self.ema_model).sample(batch_size=self.batch_size, img=og_img)
+                sample_dict['og'] = og_img
+                print(f'images saved: {sample_dict.keys()}')
+                for k, img in sample_dict.items():
+                    utils.save_image((img + 1) * 0.5, str(self.results_folder / f'sample-{k}-{milestone}.png'), nrow=6)
+                self.save()
+            if self.step != 0 and self.step % self.save_with_time_stamp_every == 0:
+                self.save(save_with_time_stamp=True)
+            self.step += 1
 
 
 def _match_prefix(sd, model):

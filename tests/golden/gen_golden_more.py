@@ -135,6 +135,7 @@ def main():
                 out['loss:%s|%s' % (routine, lt)] = gd.p_losses(xr, torch.tensor([3, 0, 2]))
     out['q_neg'] = gd.q_sample(xr, torch.tensor([2, -1, 1]))
     out['func1'] = gd.func[1](xr); out['func2of1'] = gd.func[2](out['func1'])
+    out['tf_bilinear5'] = gd.transform_func(xr, 5, 'bilinear'); out['tf_area16_blur'] = gd.transform_func(xr, 16, 'area', do_blur=True)
     for samp in ('x0_step_down', 'default'):
         gd = rs.GaussianDiffusion(unet_rs, image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, loss_type='l1',
                                   resolution_routine='Incremental_factor_2', train_routine='Final', sampling_routine=samp)
@@ -253,6 +254,34 @@ def main():
     with open(os.path.join(HERE, 'state_dict_format.json'), 'w') as f:
         json.dump(fmt, f, indent=0, sort_keys=True)
     print('wrote state_dict_format.json', sum(len(v) for v in fmt.values()), 'keys')
+
+    # ---- API surface: constructor / method signatures of every exported class ---------------------------------------------
+    import inspect
+
+    def sig(fn):
+        out_ = []
+        for n, p_ in inspect.signature(fn).parameters.items():
+            if n == 'self':
+                continue
+            d = None if p_.default is inspect._empty else repr(p_.default)
+            out_.append([n, str(p_.kind), d])
+        return out_
+    api = {}
+    for tag, mod, names in (('deblurring', db, ('Unet', 'GaussianDiffusion', 'Trainer', 'Model')), ('resolution', rs, ('Unet', 'GaussianDiffusion', 'Trainer')),
+                            ('defading', df, ('Unet', 'GaussianDiffusion', 'Trainer')), ('denoising', dn, ('Unet', 'GaussianDiffusion', 'Trainer')),
+                            ('demixing', dm, ('Unet', 'GaussianDiffusion', 'Trainer')), ('defading_generation', dg, ('Unet', 'GaussianDiffusion', 'Trainer')),
+                            ('snowification', sn, ('GaussianDiffusion', 'Trainer'))):
+        for cn in names:
+            cls = getattr(mod, cn)
+            entry = {'__init__': sig(cls.__init__)}
+            if cn == 'GaussianDiffusion':
+                for mn, fn in inspect.getmembers(cls, predicate=inspect.isfunction):
+                    if not mn.startswith('_'):
+                        entry[mn] = sig(fn)
+            api[tag + '.' + cn] = entry
+    with open(os.path.join(HERE, 'api_surface.json'), 'w') as f:
+        json.dump(api, f, indent=0, sort_keys=True)
+    print('wrote api_surface.json', len(api), 'classes')
 
     # ---- DDPM-style `Model` (Model2.py): L1-loss gradients of every parameter (dropout inactive: eval mode) -----------
     z = np.load(os.path.join(HERE, 'model2_small.npz'))

@@ -88,3 +88,39 @@ def test_state_dict_wire_format_of_every_package_matches_the_reference():
         assert not missing and not extra, (tag, missing[:5], extra[:5])
         bad = [k for k in ref if mine[k] != ref[k]]
         assert not bad, (tag, bad[:5])
+
+
+def test_api_surface_matches_the_reference():
+    """every constructor keyword (name, kind, default) of the exported classes and every public method of GaussianDiffusion with
+    its parameter names, as recorded from the unmodified reference (tests/golden/api_surface.json).  Extra parameters on our side
+    are allowed when they have defaults (private ones carry a leading underscore)."""
+    import inspect, json
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200 import (deblurring_diffusion_pytorch as db, resolution_diffusion_pytorch as rs,
+                                            defading_diffusion_pytorch as df, denoising_diffusion_pytorch as dn,
+                                            demixing_diffusion_pytorch as dm, defading_generation_diffusion_pytorch as dg,
+                                            snowification_diffusion as sn)
+    mods = dict(deblurring=db, resolution=rs, defading=df, denoising=dn, demixing=dm, defading_generation=dg, snowification=sn)
+    api = json.load(open(os.path.join(G, 'api_surface.json')))
+    problems = []
+    for key, entry in api.items():
+        tag, cn = key.split('.')
+        cls = getattr(mods[tag], cn)
+        for mn, ref in entry.items():
+            fn = getattr(cls, mn, None)
+            if fn is None:
+                problems.append((key, mn, 'missing'))
+                continue
+            mine = [(n, str(p.kind), None if p.default is inspect._empty else repr(p.default))
+                    for n, p in inspect.signature(fn).parameters.items() if n != 'self' and not n.startswith('_')]
+            ref = [tuple(r) for r in ref]
+            ref_names = {r[0] for r in ref}
+            extras = [m for m in mine if m[0] not in ref_names]
+            if any(m[2] is None for m in extras):
+                problems.append((key, mn, 'extra parameter without a default', extras))
+            mine = [m for m in mine if m[0] in ref_names]           # keyword supersets (e.g. `shuffle`) are fine
+            if [m[0] for m in mine] != [r[0] for r in ref]:
+                problems.append((key, mn, 'names', [m[0] for m in mine], [r[0] for r in ref]))
+            elif mn == '__init__' and mine != ref:
+                problems.append((key, mn, 'kinds/defaults', [m for m, r in zip(mine, ref) if m != r][:4]))
+    assert not problems, problems[:12]
