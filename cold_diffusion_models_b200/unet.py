@@ -155,10 +155,16 @@ class Unet(nn.Module):
             self._engine.mark_weights_dirty()
         return r
 
-    def forward(self, x, time):
-        """x: (B, C, H, W) fp32 NCHW on a CUDA device, time: (B,) int64  ->  (B, out_dim, H, W)   (DB:256-282)"""
+    def forward(self, x, time=None):
+        """x: (B, C, H, W) fp32 NCHW on a CUDA device, time: (B,) int64  ->  (B, out_dim, H, W)   (DB:256-282).
+        `time` may be omitted only when the network was built with with_time_emb=False (snowification's UnetConvNextBlock
+        declares `forward(x, time=None)`)."""
         if not x.is_cuda:
             raise RuntimeError("cold_diffusion_models_b200.Unet runs on a B200 (CUDA) device only; got %s" % x.device)
+        if time is None:
+            if self.time_mlp is not None:
+                raise TypeError("Unet.forward: `time` is required when the network has a time embedding")
+            time = torch.zeros(x.shape[0], dtype=torch.int64, device=x.device)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .autograd import UnetFunction
             return UnetFunction.apply(self, x, time, *self.engine.param_list())

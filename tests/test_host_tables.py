@@ -124,3 +124,24 @@ def test_api_surface_matches_the_reference():
             elif mn == '__init__' and mine != ref:
                 problems.append((key, mn, 'kinds/defaults', [m for m, r in zip(mine, ref) if m != r][:4]))
     assert not problems, problems[:12]
+
+
+def test_snowification_get_model_and_dataset_exports():
+    """`diffusion.model.get_model.get_model` / `diffusion.get_dataset` of the snowification package (get_model.py:4-38)"""
+    import io, contextlib
+    from cold_diffusion_models_b200.snowification_diffusion import get_model, get_dataset
+    from cold_diffusion_models_b200.snowification_diffusion.model.get_model import get_model as gm
+    from cold_diffusion_models_b200 import Unet, Model
+
+    class Args:
+        pass
+    a = Args(); a.model = 'UnetResNet'; a.dataset = 'cifar10_train'
+    m = get_model(a)
+    assert gm is get_model and isinstance(m, Model) and m.resolution == 32 and m.ch == 128
+    a.dataset = 'celebA_train'
+    assert get_model(a).resolution == 128
+    a.model = 'UnetConvNext'
+    with contextlib.redirect_stdout(io.StringIO()):
+        u = get_model(a, with_time_emb=False)
+    assert isinstance(u, Unet) and u.time_mlp is None
+    assert get_dataset('unknown', '/tmp', (32, 32)) is None
