@@ -298,6 +298,22 @@ def cd_timestep_embedding(t, B, dim, emb, stream):
     return 0
 
 
+def cd_time_mlp2_fwd(t, B, dim, hid, tdim, act, w1, b1, w2, b2, wc, bc, sumC, temb, cond_all, stream):
+    tt = _i64(t, B).astype(np.float64)
+    half = dim // 2
+    f = np.exp(-(math.log(10000.0) / (half - 1)) * np.arange(half))
+    emb = np.zeros((B, dim))
+    emb[:, :half] = np.sin(tt[:, None] * f); emb[:, half:2 * half] = np.cos(tt[:, None] * f)
+    fn = _swish if act else _gelu
+    h = fn(emb @ _arr(w1, (hid, dim), (dim, 1)).astype(np.float64).T + _arr(b1, (hid,), (1,)))
+    te = h @ _arr(w2, (tdim, hid), (hid, 1)).astype(np.float64).T + _arr(b2, (tdim,), (1,))
+    if _v(temb):
+        _arr(temb, (B, tdim), (tdim, 1))[:] = te.astype(np.float32)
+    ca = fn(te) @ _arr(wc, (sumC, tdim), (tdim, 1)).astype(np.float64).T + _arr(bc, (sumC,), (1,))
+    _arr(cond_all, (B, sumC), (sumC, 1))[:] = ca.astype(np.float32)
+    return 0
+
+
 def cd_linear_fwd(x, K, w, bias, M, N, y, stream):
     r = _arr(x, (M, K), (K, 1)).astype(np.float64) @ _arr(w, (N, K), (K, 1)).astype(np.float64).T
     if _v(bias):

@@ -42,6 +42,24 @@ def test_forward_schedule_on_the_emulated_abi(model_and_goldens, monkeypatch):
     assert rel(y, g['y']) < 2e-6
 
 
+def test_inference_forward_and_sampling_on_the_emulated_abi(model_and_goldens, monkeypatch):
+    """the production inference path of `Model` (fused time-embedding kernel, shared workspaces) and the Special_6_routine
+    x0_step_down sampling around it (BASELINE config 2 shape at reduced size) against the reference"""
+    import abi_emulator
+    import cold_diffusion_models_b200 as cdm
+    m, g, _ = model_and_goldens
+    m.eval()
+    monkeypatch.setattr(torch.Tensor, 'is_cuda', property(lambda self: True))
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    with abi_emulator.patched(), torch.no_grad():
+        y = m(g['x'], g['t'])
+        assert rel(y, g['y']) < 2e-6
+        gd = cdm.GaussianDiffusion(m, image_size=16, device_of_kernel='cpu', channels=3, timesteps=6, loss_type='l1', kernel_std=0.1,
+                                   kernel_size=3, blur_routine='Special_6_routine', train_routine='Final', sampling_routine='x0_step_down')
+        xt, dr, img = gd.sample(batch_size=3, img=g['x'])
+    assert rel(xt, g['s_xt']) < 1e-5 and rel(dr, g['s_dr']) < 1e-5 and rel(img, g['s_img']) < 1e-4
+
+
 def test_backward_schedule_reproduces_every_reference_gradient(model_and_goldens, monkeypatch):
     import abi_emulator
     m, g, gg = model_and_goldens
