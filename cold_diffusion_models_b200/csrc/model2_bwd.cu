@@ -196,6 +196,37 @@ __global__ void linear_kernel(const float* __restrict__ x, int K, const float* _
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Input pipeline (reference Dataset / Dataset_Aug1, DB:983-1026): the decoded, 1.12x-resized uint8 images stay resident in
+// HBM; a batch is gathered with a per-sample crop window and horizontal flip and converted like ToTensor()*2-1.
+//   out[b][c][y][x] = src[index[b]][oy[b] + y][ox[b] + (flip[b] ? S-1-x : x)][c] / 255 * 2 - 1
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void augment_u8_kernel(const unsigned char* __restrict__ src, int Hs, int Ws, const long long* __restrict__ index,
+                                  const int* __restrict__ oy, const int* __restrict__ ox, const int* __restrict__ flip,
+                                  int B, int S, float* __restrict__ out) {
+  const long long n = static_cast<long long>(B) * S * S;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % S), y = static_cast<int>((i / S) % S), b = static_cast<int>(i / (static_cast<long long>(S) * S));
+    const int sx = ox[b] + (flip[b] ? S - 1 - x : x), sy = oy[b] + y;
+    const unsigned char* px = src + ((static_cast<long long>(index[b]) * Hs + sy) * Ws + sx) * 3;
+    float* o = out + (static_cast<long long>(b) * 3 * S + y) * S + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[static_cast<long long>(c) * S * S] = (static_cast<float>(px[c]) / 255.f) * 2.f - 1.f;
+  }
+}
+}  // namespace
+
+extern "C" int cd_augment_u8(const uint8_t* src, int N, int Hs, int Ws, const int64_t* index, const int32_t* oy, const int32_t* ox,
+                             const int32_t* flip, int B, int S, float* out, void* stream) {
+  CD_REQUIRE(S <= Hs && S <= Ws && N >= 1 && B >= 1, "cd_augment_u8: crop %d does not fit the %dx%d source images", S, Hs, Ws);
+  const long long n = static_cast<long long>(B) * S * S;
+  int blocks = cd_cdiv(n, 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  augment_u8_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, Hs, Ws, reinterpret_cast<const long long*>(index), oy, ox, flip, B, S, out);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int cd_groupnorm_bwd(const float* x, int x_ld, int B, int64_t HW, int C, int groups, const float* cond, int cond_ld,
                                 const float* gamma, const float* beta, float eps, int swish, const float* dy, int dy_ld,
                                 float* dx, int dx_ld, float* dgamma, float* dbeta, float* dcond, int dcond_ld, void* stream) {

@@ -71,6 +71,61 @@ class ImageFolderDataset(data.Dataset):
         return self.transform(Image.open(self.paths[index]))
 
 
+class DeviceImageDataset:
+    """The reference's Dataset / Dataset_Aug1 (DB:983-1026: Resize to 1.12 x S, then CenterCrop or RandomCrop + RandomHorizontalFlip,
+    ToTensor()*2-1) with the decoded, resized uint8 images resident in HBM: a 202k-image CelebA-128 set is 12.4 GB of the 180 GB.
+    Decoding and the one-time resize run once on the host (PIL, like the reference's transforms); every batch is one gather
+    kernel (cd_augment_u8) with per-sample crop windows and flips drawn on the host -- no DataLoader workers, no H2D copy of
+    fp32 images.  Opt-in (`Trainer(..., dataset='device')` / `'device_aug'`); not yet run on a B200."""
+
+    def __init__(self, folder, image_size, augment=False, exts=('jpg', 'jpeg', 'png'), device='cuda', seed=0):
+        import numpy as np
+        from PIL import Image
+        from torchvision import transforms
+        self.image_size, self.augment = image_size, augment
+        self.paths = sorted(p for ext in exts for p in Path(f'{folder}').glob(f'**/*.{ext}'))
+        rs = int(image_size * 1.12)
+        resize = transforms.Resize((rs, rs))
+        imgs = [np.asarray(resize(Image.open(p).convert('RGB')), dtype=np.uint8) for p in self.paths]
+        self.src = torch.from_numpy(np.stack(imgs)).contiguous().to(device)          # [N][rs][rs][3] uint8
+        self.N, self.rs = len(imgs), rs
+        self.gen = torch.Generator().manual_seed(seed)
+        self._perm, self._pos = torch.randperm(self.N, generator=self.gen), 0
+
+    def __len__(self):
+        return self.N
+
+    def _indices(self, B, shuffle):
+        """the next B image indices of an endless pass over the set (reshuffled every epoch, like cycle(DataLoader(shuffle)))"""
+        out, need = [], B
+        while need > 0:
+            if self._pos >= self.N:
+                self._perm, self._pos = (torch.randperm(self.N, generator=self.gen) if shuffle else torch.arange(self.N)), 0
+            take = min(need, self.N - self._pos)
+            out.append(self._perm[self._pos:self._pos + take])
+            self._pos += take
+            need -= take
+        return torch.cat(out)
+
+    def batch(self, B, shuffle=True, index=None, oy=None, ox=None, flip=None):
+        """-> (B, 3, S, S) fp32 in [-1, 1] on the dataset's device"""
+        S, m = self.image_size, self.rs - self.image_size
+        index = self._indices(B, shuffle) if index is None else index
+        if oy is None:
+            if self.augment:                      # torchvision RandomCrop.get_params: i ~ U{0..h-th}, j ~ U{0..w-tw}; flip with p = 0.5
+                oy = torch.randint(0, m + 1, (B,), generator=self.gen); ox = torch.randint(0, m + 1, (B,), generator=self.gen)
+                flip = (torch.rand(B, generator=self.gen) < 0.5)
+            else:                                 # torchvision CenterCrop: int(round((h - th) / 2.))
+                c = int(round(m / 2.0))
+                oy = torch.full((B,), c); ox = torch.full((B,), c); flip = torch.zeros(B, dtype=torch.bool)
+        dev = self.src.device
+        index = index.to(dev, torch.int64).contiguous()
+        oy, ox, flip = (v.to(dev, torch.int32).contiguous() for v in (oy, ox, flip))
+        out = torch.empty(B, 3, S, S, device=dev, dtype=torch.float32)
+        call('cd_augment_u8', ptr(self.src), self.N, self.rs, self.rs, ptr(index), ptr(oy), ptr(ox), ptr(flip), B, S, ptr(out), stream())
+        return out
+
+
 class FusedAdamEMA:
     """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) + EMA as one kernel over flat buffers."""
 
@@ -150,6 +205,13 @@ class Trainer(object):
             ds = SyntheticImages(self.image_size, channels, seed=seed)
             return ds, cycle(data.DataLoader(ds, batch_size=self.batch_size, shuffle=False, pin_memory=True, num_workers=0,
                                              drop_last=True))
+        if dataset in ('device', 'device_aug'):            # images resident in HBM, batches gathered by cd_augment_u8
+            ds = DeviceImageDataset(folder, self.image_size, augment=(dataset == 'device_aug'))
+
+            def gen():
+                while True:
+                    yield ds.batch(self.batch_size, shuffle=shuffle)
+            return ds, gen()
         aug = dataset in self._aug_datasets
         print(dataset, "DA used" if aug else "")
         ds = ImageFolderDataset(folder, self.image_size, augment=aug)

@@ -299,6 +299,12 @@ int cd_swish(const float* dy, const float* pre, int64_t n, float* y, float* act_
 int cd_timestep_embedding(const int64_t* t, int B, int dim, float* emb, void* stream);
 int cd_linear_fwd(const float* x, int K, const float* w, const float* bias, int M, int N, float* y, void* stream);
 
+/* Input pipeline (reference Dataset / Dataset_Aug1, DB:983-1026) with the decoded uint8 images resident in HBM ([N][Hs][Ws][3]):
+ * out[b][c][y][x] = src[index[b]][oy[b]+y][ox[b] + (flip[b] ? S-1-x : x)][c] / 255 * 2 - 1   (RandomCrop / CenterCrop + flip + ToTensor*2-1).
+ * Opt-in (Trainer(dataset='device...')); not yet run on a B200. */
+int cd_augment_u8(const uint8_t* src, int N, int Hs, int Ws, const int64_t* index, const int32_t* oy, const int32_t* ox,
+                  const int32_t* flip, int B, int S, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -683,6 +683,20 @@ def cd_snow(xt, og, out, snow, br_coef, t_hi, t_lo, hi_off, lo_off, B, H, W, sno
     return 0
 
 
+def cd_augment_u8(src, N, Hs, Ws, index, oy, ox, flip, B, S, out, stream):
+    U = np.ctypeslib.as_array((C.c_uint8 * (N * Hs * Ws * 3)).from_address(_v(src))).reshape(N, Hs, Ws, 3)
+    idx = _i64(index, B)
+    i32 = lambda a: np.ctypeslib.as_array((C.c_int32 * B).from_address(_v(a)))
+    OY, OX, FL = i32(oy), i32(ox), i32(flip)
+    O = _arr(out, (B, 3, S, S), (3 * S * S, S * S, S, 1))
+    for b in range(B):
+        win = U[idx[b], OY[b]:OY[b] + S, OX[b]:OX[b] + S]
+        if FL[b]:
+            win = win[:, ::-1]
+        O[b] = ((win.astype(np.float32) / np.float32(255)) * np.float32(2) - np.float32(1)).transpose(2, 0, 1)
+    return 0
+
+
 def cd_adam_ema_step(p, g, m, v, ema, n, lr, beta1, beta2, eps, step, ema_mode, ema_beta, grad_scale, stream):
     n = _v(n); lr, b1, b2, eps, eb, gs = (np.float32(_v(a)) for a in (lr, beta1, beta2, eps, ema_beta, grad_scale))
     P, Gr, M, V = (_arr(a, (n,), (1,)) for a in (p, g, m, v))
