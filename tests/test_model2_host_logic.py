@@ -105,3 +105,47 @@ def test_dropout_mask_is_a_pure_function_of_seed_and_index():
     assert torch.equal(y1, y2) and not torch.equal(y1, y3)
     kept = (y1 != 0).float().mean().item()
     assert 0.85 < kept < 0.95 and abs(y1.max().item() - 1 / 0.9) < 1e-6
+
+
+def test_trainer_step_with_model_on_the_emulated_abi(model_and_goldens, monkeypatch, tmp_path):
+    """`Trainer` + fused Adam/EMA over the flat buffers of `Model` (ModelEngine): one optimizer step on two micro-batches equals
+    torch.optim.Adam on the oracle's autograd gradients; dropout inactive (eval mode) so both sides see the same network"""
+    import io, contextlib
+    import abi_emulator
+    import cold_diffusion_models_b200 as cdm
+    import model2_oracle as MO
+    import deblur_oracle as DO
+    m, g, _ = model_and_goldens
+    monkeypatch.setattr(torch.Tensor, 'is_cuda', property(lambda self: True))
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith('sd:')}
+    kw = dict(image_size=16, channels=3, timesteps=6, kernel_std=0.1, kernel_size=3, blur_routine='Special_6_routine', loss_type='l2')
+    with abi_emulator.patched(), contextlib.redirect_stdout(io.StringIO()):
+        gd = cdm.GaussianDiffusion(m, device_of_kernel='cpu', sampling_routine='x0_step_down', **kw)
+        tr = cdm.Trainer(gd, None, image_size=16, train_batch_size=3, train_lr=1e-3, gradient_accumulate_every=2,
+                         results_folder=str(tmp_path), dataset='synthetic', step_start_ema=0, update_ema_every=1, ema_decay=0.9)
+        m.eval(); tr.ema_model.denoise_fn.eval()
+        gen = torch.Generator().manual_seed(5)
+        xs = [torch.rand(3, 3, 16, 16, generator=gen) * 2 - 1 for _ in range(2)]
+        ts = [torch.tensor([5, 0, 2]), torch.tensor([1, 3, 4])]
+        ref = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+        orc = DO.DeblurOracle(lambda a, b: MO.model_forward(ref, a, b, ch=32, num_resolutions=2, num_res_blocks=2), **kw)
+        opt = torch.optim.Adam([v for v in ref.values() if v.requires_grad], lr=1e-3)
+        for x, t in zip(xs, ts):
+            (orc.p_losses(x, t) / 2).backward()
+        opt.step()
+        for x, t in zip(xs, ts):
+            (gd.p_losses(x, t) / 2).backward()
+        tr.opt.step(ema_mode=2, ema_beta=0.9)
+    new, ema = m.state_dict(), tr.ema_model.denoise_fn.state_dict()
+    checked = 0
+    for k, v in sd.items():
+        if not v.dtype.is_floating_point:
+            continue
+        if ref[k].grad.abs().max() < 1e-6:
+            continue      # gradient zero in exact arithmetic (see the gradient test): Adam turns the round-off into +-lr steps
+        # Adam's first step is lr * g / (|g| + eps): elements whose gradient is round-off-sized move by +-lr either way
+        assert rel(new[k], ref[k].detach()) < 2e-4, k
+        assert rel(ema[k], v * 0.9 + 0.1 * ref[k].detach()) < 2e-4, k
+        checked += 1
+    assert checked > 150
