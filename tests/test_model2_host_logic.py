@@ -149,3 +149,34 @@ def test_trainer_step_with_model_on_the_emulated_abi(model_and_goldens, monkeypa
         assert rel(ema[k], v * 0.9 + 0.1 * ref[k].detach()) < 2e-4, k
         checked += 1
     assert checked > 150
+
+
+def test_dropout_plumbing_of_the_training_path(model_and_goldens, monkeypatch):
+    """dropout active (train mode): the same host seed reproduces the forward, and the backward uses the forward's masks -- the
+    loss change along -grad matches the first-order prediction"""
+    import abi_emulator
+    m, g, _ = model_and_goldens
+    monkeypatch.setattr(torch.Tensor, 'is_cuda', property(lambda self: True))
+    for b in (b for _, b in m._resblocks()):
+        b.dropout.p = 0.3
+    m.train()
+    x, t = g['x'], g['t']
+    target = torch.zeros_like(x)
+    with abi_emulator.patched():
+        torch.manual_seed(5)
+        loss = ((target - m(x, t)) ** 2).mean()
+        loss.backward()
+        torch.manual_seed(6)
+        other = ((target - m(x, t)) ** 2).mean()
+        grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+        gnorm2 = sum((v.double() ** 2).sum().item() for v in grads.values())
+        eps = 1e-3 / gnorm2 ** 0.5
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                p.add_(grads[n], alpha=-eps)
+        m.engine.mark_weights_dirty()
+        torch.manual_seed(5)
+        loss2 = ((target - m(x, t)) ** 2).mean()
+    assert abs(other.item() - loss.item()) > 1e-6                       # different seed -> different masks
+    predicted = -eps * gnorm2
+    assert abs((loss2.item() - loss.item()) - predicted) < 0.1 * abs(predicted), (loss.item(), loss2.item(), predicted)
