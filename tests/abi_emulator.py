@@ -8,6 +8,15 @@ import math
 import numpy as np
 
 
+TF32_EMULATION = False      # True: tap-list convolutions launched with impl = CD_CONV_TC round both operands to TF32 (RN), like the
+                            # TFLOAT32 tensor maps do -- used to estimate the TF32-path error of a test before it runs on a GPU
+
+
+def _tf32(a):
+    i = np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(np.float32)
+
+
 def _v(a):
     if isinstance(a, (int, float)):
         return a
@@ -77,13 +86,18 @@ def cd_conv_fwd(desc, impl, stream):
     d = desc._obj if hasattr(desc, '_obj') else desc
     B, Hg, Wg = d.B, d.Hg, d.Wg
     acc = np.zeros((B, Hg, Wg, d.Cout), dtype=np.float64)
+    tf32 = TF32_EMULATION and _v(impl) == 1
     for si in range(d.nsrc):
         s = d.s[si]
         src = _nhwc(s.src, B, s.H, s.W, s.C, s.ld)
+        if tf32 and s.C % 32 == 0:
+            src = _tf32(src)
         if s.w_per_batch:
             w = _arr(s.w, (B, s.ntaps, d.Cout, s.C), (s.ntaps * d.Cout * s.C, d.Cout * s.C, s.C, 1))
         else:
             w = _arr(s.w, (s.ntaps, d.Cout, s.C), (d.Cout * s.C, s.C, 1))
+        if tf32 and s.C % 32 == 0:
+            w = _tf32(w)
         for t in range(s.ntaps):
             g = _gather(src, B, Hg, Wg, d.sy, d.sx, s.dy[t], s.dx[t])
             if s.w_per_batch:
