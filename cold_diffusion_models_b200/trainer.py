@@ -20,6 +20,7 @@ import torch
 from torch.utils import data
 
 from ._lib import call, ptr, stream
+from .evaluation import EvaluationMixin, SnowEvaluationMixin
 
 
 def cycle(dl):
@@ -162,7 +163,7 @@ class FusedAdamEMA:
         self.t = sd['t']; self.m.copy_(sd['m']); self.v.copy_(sd['v'])
 
 
-class Trainer(object):
+class Trainer(EvaluationMixin, object):
     def __init__(self, diffusion_model, folder, *, ema_decay=0.995, image_size=128, train_batch_size=32, train_lr=2e-5,
                  train_num_steps=100000, gradient_accumulate_every=2, fp16=False, step_start_ema=2000,
                  update_ema_every=10, save_and_sample_every=1000, results_folder='./results', load_path=None,
@@ -313,6 +314,31 @@ class DenoisingTrainer(Trainer):
         return torch.randn(self.batch_size, getattr(_unwrap(self.model), 'channels', 3), self.image_size, self.image_size,
                            device='cuda')                       # DN:757-762
 
+    _to_show = (2, 4, 16, 64, 128, 256, 384, 448, 480)          # DN:862
+    _cover_batches = 5                                          # DN:864
+
+
+class ResolutionTrainer(Trainer):
+    """Trainer of resolution_diffusion_pytorch (RS:842-1200): evaluation in batches of 200 (RS:1017) and its own
+    mixture-over-low-resolution-images generation routine."""
+
+    def fid_distance_decrease_from_manifold(self, fid_func, start=0, end=1000, bs=200, sanity_check=1):
+        return super().fid_distance_decrease_from_manifold(fid_func, start=start, end=end, bs=bs, sanity_check=sanity_check)
+
+    def sample_as_a_mean_blur_torch_gmm_ablation(self, torch_gmm=None, siz=2, ch=3, clusters=10, sample_at=6, noise=0,
+                                                 num_samples=6400, bs=64):
+        """mixture over the step-`sample_at` low-resolution images (area-averaged to siz x siz); draws are blown up with
+        nearest-exact interpolation and restored by `gen_sample` (RS:1117-1183)"""
+        import torch.nn.functional as F
+        H, W = self._image_size_hw()
+        ema = _unwrap(self.ema_model)
+        feats = self._dataset_features(lambda b: F.interpolate(ema.opt(b, t=sample_at), size=siz, mode='area').flatten(1))
+        model = self._fit_mixture(torch_gmm, feats, clusters)
+        og_x = model.sample(num_datapoints=num_samples).cuda().reshape(num_samples, 3, siz, siz)
+        og_x = F.interpolate(og_x, size=(H, W), mode='nearest-exact').float()
+        self._generate_to_folders(og_x, ch, bs, noise)
+        return model
+
 
 class DefadingTrainer(Trainer):
     """Trainer of defading_diffusion_pytorch (DFG:654-811): its own defaults and `sample(batch_size, faded_recon_sample)`"""
@@ -354,6 +380,17 @@ class DemixingTrainer(Trainer):
     def _sample_start(self):
         return next(self.dl2).cuda()                            # DM:747
 
+    _to_show = (2, 4, 16, 64, 128, 256, 384, 448, 480)          # DM:844
+    _cover_batches = 5                                          # DM:846
+
+    def _eval_batch(self):
+        return next(self.dl2).cuda()                            # DM:776: evaluation starts from the second domain
+
+    def _forward_backward(self, noise_level):
+        og1, og2 = next(self.dl1).cuda(), next(self.dl2).cuda()                                            # DM:848-852
+        F_, B_, final = _unwrap(self.ema_model).forward_and_backward(batch_size=self.batch_size, img1=og1, img2=og2)
+        return og1, F_, B_, final
+
 
 class DefadingGenerationTrainer(Trainer):
     """Trainer of the defading-generation package: the end image x2 is a constant random colour in [-0.5, 0.5)
@@ -369,6 +406,19 @@ class DefadingGenerationTrainer(Trainer):
 
     def _sample_start(self):
         return self._colour(self.batch_size)                    # DFGEN:796-803
+
+    _to_show = (8, 192, 256, 320, 384, 512, 640, 704, 748)      # DFGEN:913
+    _cover_batches = 5                                          # DFGEN:915
+
+    def _eval_batch(self):
+        c = self._colour(self.batch_size)
+        return c + 0.000001 * torch.randn_like(c)               # DFGEN:833-839
+
+    def _forward_backward(self, noise_level):
+        og1 = next(self.dl).cuda()                                                                          # DFGEN:917-928
+        F_, B_, final = _unwrap(self.ema_model).forward_and_backward(batch_size=self.batch_size, img1=og1,
+                                                                     img2=self._colour(self.batch_size))
+        return og1, F_, B_, final
 
 
 def snow_get_transform(image_size, random_aug=False, resize=False):
@@ -398,7 +448,7 @@ def get_dataset(name, folder, image_size, random_aug=False):
     return None
 
 
-class SnowificationTrainer(Trainer):
+class SnowificationTrainer(SnowEvaluationMixin, Trainer):
     """Trainer of snowification/diffusion (== decolor-diffusion/diffusion), SN:563-760: the image size comes from the model,
     torchvision datasets by name, `sample()` returns a dict whose entries are all saved, `save(save_with_time_stamp)`."""
 
@@ -414,6 +464,7 @@ class SnowificationTrainer(Trainer):
         self.random_aug, self.torchvision_dataset, self.to_lab, self.order_seed = random_aug, torchvision_dataset, to_lab, int(order_seed)
         self.save_with_time_stamp_every = save_with_time_stamp_every
         self.num_timesteps = core.num_timesteps
+        self.data_loader = None
         super().__init__(diffusion_model, folder, ema_decay=ema_decay, image_size=self._size2[0], train_batch_size=train_batch_size,
                          train_lr=train_lr, train_num_steps=train_num_steps, gradient_accumulate_every=gradient_accumulate_every,
                          fp16=fp16, step_start_ema=step_start_ema, update_ema_every=update_ema_every,
@@ -421,7 +472,6 @@ class SnowificationTrainer(Trainer):
                          dataset=dataset, shuffle=True)
         self.results_folder.mkdir(parents=True, exist_ok=True)
         self.post_process_func = lambda x: x
-        self.data_loader = None
 
     def _make_loader(self, folder, dataset, shuffle, seed):
         if folder is None or dataset == 'synthetic':
@@ -432,6 +482,7 @@ class SnowificationTrainer(Trainer):
             ds = ImageFolderDataset(folder, self._size2[0])
             ds.transform = snow_get_transform(self._size2, random_aug=self.random_aug) if self._size2[0] != 256 else ds.transform
         loader = data.DataLoader(ds, batch_size=self.batch_size, shuffle=True, pin_memory=True, num_workers=4)
+        self.data_loader = loader                               # SN:619: the un-cycled loader `test_from_data` walks
 
         def gen():
             while True:
