@@ -141,11 +141,15 @@ def calculate_fid_given_samples(samples, batch_size=50, device='cuda:0', dims=20
     """FID between `samples[0]` and `samples[1]` (tensors of images in [0, 1]); Fid/fid_score.py:343-356.
 
     `model` maps an image batch to (N, dims[, 1, 1]) features.  The reference builds pytorch-fid's InceptionV3 from weights
-    it downloads (Fid/inception.py:184-208); there is no network in the deployment this engine targets, so the feature
-    network must be handed in (any callable; e.g. an `InceptionV3` a user constructed from a local weight file)."""
+    it downloads (Fid/inception.py:184-208); there is no network in the deployment this engine targets, so either the
+    feature network is handed in (any callable) or $COLDDIFF_FID_WEIGHTS names a local copy of that weight file, from which
+    `InceptionV3` below is built."""
     if model is None:
-        raise RuntimeError("calculate_fid_given_samples needs model=<feature extractor>: the FID InceptionV3 weights are a "
-                           "download in the reference (Fid/inception.py) and are not bundled")
+        if os.environ.get('COLDDIFF_FID_WEIGHTS') is None:
+            raise RuntimeError("calculate_fid_given_samples needs model=<feature extractor> or $COLDDIFF_FID_WEIGHTS pointing at "
+                               "pytorch-fid's InceptionV3 weight file: the reference downloads it (Fid/inception.py), this "
+                               "engine does not")
+        model = InceptionV3([InceptionV3.BLOCK_INDEX_BY_DIM[dims]]).to(device)
     m1, s1 = calculate_activation_statistics(samples[0], model, batch_size, dims, device, num_workers)
     m2, s2 = calculate_activation_statistics(samples[1], model, batch_size, dims, device, num_workers)
     return calculate_frechet_distance(m1, s1, m2, s2)
@@ -870,3 +874,85 @@ class SnowEvaluationMixin:
         than 256 px are scored on 64 px copies (SN:1000-1145)"""
         return EvaluationMixin.fid_distance_decrease_from_manifold(self, fid_func, start=start, end=end, bs=bs,
                                                                    sanity_check=sanity_check)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# FID feature network (Fid/inception.py): torchvision's InceptionV3 with the pooling of the TensorFlow FID graph
+# ------------------------------------------------------------------------------------------------------------------------
+class InceptionV3(torch.nn.Module):
+    """Feature maps of the InceptionV3 used for FID (Fid/inception.py:16-164; a vendored copy of pytorch-fid upstream).
+
+    Same constructor, block indices and outputs as there.  The FID graph differs from torchvision's InceptionV3 only in the
+    pooling that feeds `branch_pool` of the A / C / E blocks: 3x3 average pooling that does not count the zero padding
+    (all of them but the last), 3x3 max pooling in the last block (Fid/inception.py:211-326).  Instead of re-deriving the
+    blocks, torchvision's modules are used as they are and the input of each `branch_pool` is corrected by hooks: average
+    pooling without the padding equals average pooling with it times 9 / (number of in-image taps), a fixed per-pixel factor;
+    the last block's `branch_pool` gets the max-pooled block input instead.
+
+    Weights: `weights_path` (or $COLDDIFF_FID_WEIGHTS) names a local copy of pytorch-fid's
+    `pt_inception-2015-12-05-6726825d.pth` (same parameter names as torchvision, 1008 classes).  Nothing is downloaded;
+    without a file the constructor raises unless `weights_path=False` (random initialisation, for tests)."""
+
+    DEFAULT_BLOCK_INDEX = 3
+    BLOCK_INDEX_BY_DIM = {64: 0, 192: 1, 768: 2, 2048: 3}
+
+    def __init__(self, output_blocks=(DEFAULT_BLOCK_INDEX,), resize_input=True, normalize_input=True, requires_grad=False,
+                 use_fid_inception=True, weights_path=None):
+        super().__init__()
+        import torchvision
+        self.resize_input, self.normalize_input = resize_input, normalize_input
+        self.output_blocks = sorted(output_blocks)
+        self.last_needed_block = max(output_blocks)
+        assert self.last_needed_block <= 3, 'Last possible output block index is 3'
+        net = torchvision.models.inception_v3(weights=None, aux_logits=False, num_classes=1008 if use_fid_inception else 1000,
+                                              init_weights=False)
+        if weights_path is None:
+            weights_path = os.environ.get('COLDDIFF_FID_WEIGHTS')
+        if weights_path is None:
+            raise RuntimeError("InceptionV3 needs weights_path=<pt_inception-2015-12-05-6726825d.pth> (or $COLDDIFF_FID_WEIGHTS); "
+                               "the reference downloads that file, this engine does not")
+        if weights_path is not False:
+            net.load_state_dict(torch.load(weights_path, map_location='cpu'))
+        pool = lambda: torch.nn.MaxPool2d(kernel_size=3, stride=2)
+        stages = [[net.Conv2d_1a_3x3, net.Conv2d_2a_3x3, net.Conv2d_2b_3x3, pool()],
+                  [net.Conv2d_3b_1x1, net.Conv2d_4a_3x3, pool()],
+                  [net.Mixed_5b, net.Mixed_5c, net.Mixed_5d, net.Mixed_6a, net.Mixed_6b, net.Mixed_6c, net.Mixed_6d, net.Mixed_6e],
+                  [net.Mixed_7a, net.Mixed_7b, net.Mixed_7c, torch.nn.AdaptiveAvgPool2d(output_size=(1, 1))]]
+        self.blocks = torch.nn.ModuleList(torch.nn.Sequential(*st) for st in stages[:self.last_needed_block + 1])
+        if use_fid_inception:
+            if self.last_needed_block >= 2:
+                for m in (net.Mixed_5b, net.Mixed_5c, net.Mixed_5d, net.Mixed_6b, net.Mixed_6c, net.Mixed_6d, net.Mixed_6e):
+                    m.branch_pool.register_forward_pre_hook(self._exclude_padding)
+            if self.last_needed_block >= 3:
+                net.Mixed_7b.branch_pool.register_forward_pre_hook(self._exclude_padding)
+                stash = {}
+                net.Mixed_7c.register_forward_pre_hook(lambda mod, args: stash.__setitem__('x', args[0]))
+                net.Mixed_7c.branch_pool.register_forward_pre_hook(
+                    lambda mod, args: (F.max_pool2d(stash.pop('x'), kernel_size=3, stride=1, padding=1),))
+        for p in self.parameters():
+            p.requires_grad = requires_grad
+
+    @staticmethod
+    def _exclude_padding(module, args):
+        """avg_pool2d(3, 1, 1) counted 9 taps everywhere; rescale so that only the taps inside the image count"""
+        x = args[0]
+        H, W = x.shape[-2:]
+        ny = torch.full((H,), 3.0, device=x.device, dtype=x.dtype)
+        nx = torch.full((W,), 3.0, device=x.device, dtype=x.dtype)
+        ny[0] -= 1; ny[-1] -= 1; nx[0] -= 1; nx[-1] -= 1          # a 1-pixel axis ends at 1 tap, as it should
+        return (x * (9.0 / (ny[:, None] * nx[None, :])),)
+
+    def forward(self, inp):
+        """inp: (B, 3, H, W) in [0, 1] -> list of the selected blocks' outputs, ascending by index"""
+        out, x = [], inp
+        if self.resize_input:
+            x = F.interpolate(x, size=(299, 299), mode='bilinear', align_corners=False)
+        if self.normalize_input:
+            x = 2 * x - 1
+        for idx, block in enumerate(self.blocks):
+            x = block(x)
+            if idx in self.output_blocks:
+                out.append(x)
+            if idx == self.last_needed_block:
+                break
+        return out

@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
 sys.path.insert(0, '/root/reference/deblurring-diffusion-pytorch')
 from Fid import fid_score  # noqa  (imports torchvision's inception definition; no weights are loaded)
 import scipy.linalg as _sl
@@ -53,6 +54,29 @@ def main():
     mu, sigma = fid_score.calculate_activation_statistics(imgs[:20], Wrapped(), batch_size=5, dims=12, device='cpu')
     out['acts:w'], out['acts:b'] = net.weight.detach().numpy(), net.bias.detach().numpy()
     out['acts:imgs'], out['acts:mu'], out['acts:sigma'] = imgs.numpy(), mu, sigma
+    # ---- FID feature network with a synthetic weight file (the real one is a download) ---------------------------------------
+    import torchvision
+    from Fid import inception as ref_inception
+    from fid_weights import synthetic_state
+    shapes = {k: v.shape for k, v in torchvision.models.inception_v3(weights=None, aux_logits=False, num_classes=1008,
+                                                                       init_weights=False).state_dict().items()}
+    state = synthetic_state(shapes)
+    ref_inception.load_state_dict_from_url = lambda *a, **k: state
+    net = ref_inception.InceptionV3([0, 1, 2, 3]).eval()
+    torch.manual_seed(11)
+    fid_imgs = torch.rand(2, 3, 48, 40)
+    with torch.no_grad():
+        feats = net(fid_imgs)
+    out['fid:imgs'] = fid_imgs.numpy()
+    for i, f in enumerate(feats):
+        out[f'fid:block{i}'] = (f if i == 3 else f.mean((2, 3))).numpy()           # spatial means of the big maps
+        print('block', i, tuple(f.shape), float(f.abs().mean()))
+    out['fid:block2_edge'] = feats[2][:, :16, 0, :].numpy()                          # border row: where the pooling differs
+    torch.manual_seed(12)
+    small_in = torch.rand(1, 3, 80, 96)
+    with torch.no_grad():
+        out['fid:small_in'] = small_in.numpy()
+        out['fid:small_block2'] = ref_inception.InceptionV3([2], resize_input=False, normalize_input=False).eval()(small_in)[0].numpy()
     np.savez_compressed(os.path.join(HERE, 'eval_small.npz'), **out)
     print('wrote eval_small.npz')
 

@@ -442,3 +442,42 @@ def test_trainer_method_surface_matches_the_reference():
                 problems.append((tag, mn, 'extra parameter without default', extras))
     assert not problems, problems
     assert skipped == _UNCALLED_LEFTOVERS
+
+
+def test_fid_inception_matches_the_reference_network():
+    """`evaluation.InceptionV3` (torchvision blocks + pooling hooks) against the reference's Fid/inception.py network, both loaded
+    with the same synthetic weight file (tests/golden/fid_weights.py); the border row of block 2 is where counting the padding
+    in the average pooling would show"""
+    import tempfile
+    import torchvision
+    from cold_diffusion_models_b200.evaluation import InceptionV3, calculate_fid_given_samples
+    sys.path.insert(0, G)
+    from fid_weights import synthetic_state
+    g = np.load(os.path.join(G, 'eval_small.npz'))
+    shapes = {k: v.shape for k, v in torchvision.models.inception_v3(weights=None, aux_logits=False, num_classes=1008,
+                                                                       init_weights=False).state_dict().items()}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'pt_inception.pth')
+        torch.save(synthetic_state(shapes), path)
+        net = InceptionV3([0, 1, 2, 3], weights_path=path).eval()
+        small = InceptionV3([2], resize_input=False, normalize_input=False, weights_path=path).eval()
+        os.environ['COLDDIFF_FID_WEIGHTS'] = path
+        try:
+            imgs = torch.from_numpy(g['fid:imgs'])
+            fid = calculate_fid_given_samples([imgs, imgs.flip(0)], batch_size=2, device='cpu', dims=64)
+        finally:
+            del os.environ['COLDDIFF_FID_WEIGHTS']
+    assert abs(fid) < 1e-6                                             # same set in another order
+    assert not any(p.requires_grad for p in net.parameters())
+    with torch.no_grad():
+        feats = net(torch.from_numpy(g['fid:imgs']))
+        sb2 = small(torch.from_numpy(g['fid:small_in']))[0]
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    for i, f in enumerate(feats):
+        got = (f if i == 3 else f.mean((2, 3))).numpy()
+        assert got.shape == g[f'fid:block{i}'].shape and rel(got, g[f'fid:block{i}']) < 1e-5, i
+    assert rel(feats[2][:, :16, 0, :].numpy(), g['fid:block2_edge']) < 1e-5
+    assert rel(sb2.numpy(), g['fid:small_block2']) < 1e-5
+    with pytest.raises(RuntimeError, match='weights_path'):
+        InceptionV3()
+    assert InceptionV3.BLOCK_INDEX_BY_DIM[2048] == 3
