@@ -159,3 +159,35 @@ def test_unet_constructor_options_match_reference_golden(tag, kw):
         gr = p_.grad.reshape(-1).cpu()
         worst = max(worst, (rel(gr[::max(1, gr.numel() // 256)], g[tag + ':gsub:' + n]), n))
     assert worst[0] < 5e-4, worst
+
+
+def test_evaluation_routines_on_the_gpu(unet, tmp_path, monkeypatch):
+    """the Trainer's evaluation methods (evaluation.py) over the real engine: files of `test_from_data`, the metric dictionary of
+    `fid_distance_decrease_from_manifold` equal to metrics recomputed from `all_sample`, SSIM on CUDA tensors equal to the CPU
+    value"""
+    import os
+    import numpy as np
+    from PIL import Image
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200.evaluation import ssim, rmse
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.RandomState(0)
+    (tmp_path / 'data').mkdir()
+    for i in range(9):
+        Image.fromarray(rng.randint(0, 256, (32, 32, 3), dtype=np.uint8)).save(str(tmp_path / 'data' / f'{i:02d}.png'))
+    gd = cdm.GaussianDiffusion(unet, image_size=32, device_of_kernel='cuda', channels=3, timesteps=3, kernel_std=0.15, kernel_size=5,
+                               blur_routine='Exponential_reflect', sampling_routine='x0_step_down').cuda()
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = cdm.Trainer(gd, str(tmp_path / 'data'), image_size=32, train_batch_size=4, results_folder=str(tmp_path / 'res'), shuffle=False)
+        X0s, Xts = tr.test_from_data('t')
+        out = tr.fid_distance_decrease_from_manifold(None, start=0, end=4, bs=4, sanity_check=0)
+    assert len(X0s) == 4 and len(Xts) == 3
+    for n in ('og-t.png', 'sample-0-t-x0.png', 'sample-2-t-xt.png', 'Gif-t-x0.gif'):
+        assert (tmp_path / 'res' / n).exists(), n
+    og = torch.stack([tr.ds[i] for i in range(1, 5)]).cuda()
+    A0, At = tr.ema_model.all_sample(batch_size=4, img=og)
+    u = lambda t: (t.float().cpu() + 1) * 0.5
+    assert out['blurred']['rmse'] == pytest.approx(float(rmse(u(og), u(At[0]))), abs=1e-5)       # the degradation is exact
+    assert out['deblurred']['ssim'] == pytest.approx(float(ssim(u(og), u(A0[-1]), data_range=1)), abs=5e-3)   # two TF32 runs
+    a, b = torch.rand(3, 3, 40, 40), torch.rand(3, 3, 40, 40)
+    assert float(ssim(a.cuda(), b.cuda(), data_range=1)) == pytest.approx(float(ssim(a, b, data_range=1)), abs=1e-5)
