@@ -1,7 +1,6 @@
 """Time the Unet forward (config 3 network) at a given batch; used under ncu for launch lists."""
 import sys, io, contextlib, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
 import torch
 import cold_diffusion_models_b200 as cdm
 

@@ -4,7 +4,7 @@ like the TFLOAT32 tensor maps), and prints the relative errors against the refer
 test first runs on a B200.  Conservative: single forward of the small net 5.8e-4 here, 3e-4 measured on the GPU.  Usage: python tools/tf32_estimate.py"""
 import os, sys, io, contextlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in ('', 'tests', 'oracle'):
+for p in ('', 'tests'):
     sys.path.insert(0, os.path.join(ROOT, p))
 import numpy as np, torch
 import abi_emulator
