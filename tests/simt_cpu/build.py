@@ -1,0 +1,139 @@
+"""TEST INFRASTRUCTURE: builds a CPU-executable copy of SIMT translation units of libcolddiff (see shim/cuda_runtime.h).
+
+`build(['model2_bwd.cu', ...])` rewrites the few CUDA-only constructs textually --
+    kernel<<<grid, block, smem, stream>>>(args)   ->  simt::launch(grid, block, smem, [&] { kernel(args); })
+    extern __shared__ T name[];                   ->  T* name = (T*)simt::dyn_smem();
+    asm [volatile](...);                          ->  simt::unsupported("inline PTX");
+-- and compiles the result with g++ together with the fiber scheduler into tests/simt_cpu/_build/lib<tag>.so, which exports
+the same extern "C" entry points as the CUDA library for those files.  Nothing here is shipped or imported by the package."""
+import hashlib
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, 'cold_diffusion_models_b200', 'csrc')
+OUT = os.path.join(HERE, '_build')
+
+
+def _match_forward(s, i, open_ch, close_ch):
+    """s[i] == open_ch -> index just past the matching close_ch (string / char literals skipped)"""
+    depth, j = 0, i
+    while j < len(s):
+        c = s[j]
+        if c == '"' or c == "'":
+            q = c
+            j += 1
+            while s[j] != q:
+                j += 2 if s[j] == '\\' else 1
+        elif c == open_ch:
+            depth += 1
+        elif c == close_ch:
+            depth -= 1
+            if depth == 0:
+                return j + 1
+        j += 1
+    raise ValueError('unbalanced %s' % open_ch)
+
+
+def _split_top(s):
+    parts, depth, cur = [], 0, ''
+    for c in s:
+        if c in '([{<':
+            depth += 1
+        elif c in ')]}>':
+            depth -= 1
+        if c == ',' and depth == 0:
+            parts.append(cur.strip()); cur = ''
+        else:
+            cur += c
+    parts.append(cur.strip())
+    return parts
+
+
+def _kernel_expr_start(s, end):
+    """index where the kernel name (with optional template arguments) that ends at `end` starts"""
+    j = end
+    while j > 0 and s[j - 1].isspace():
+        j -= 1
+    if s[j - 1] == '>':
+        depth = 0
+        while True:
+            j -= 1
+            if s[j] == '>':
+                depth += 1
+            elif s[j] == '<':
+                depth -= 1
+                if depth == 0:
+                    break
+        while j > 0 and s[j - 1].isspace():
+            j -= 1
+    while j > 0 and (s[j - 1].isalnum() or s[j - 1] in '_:'):
+        j -= 1
+    return j
+
+
+def rewrite(src):
+    src = src.replace('"../../include/colddiff.h"', '"%s"' % os.path.join(ROOT, 'include', 'colddiff.h'))
+    # dynamic shared memory
+    def dyn(m):
+        ty = re.sub(r'__align__\s*\(\s*\d+\s*\)', '', m.group(1)).strip()
+        return '%s* %s = reinterpret_cast<%s*>(simt::dyn_smem());' % (ty, m.group(2), ty)
+    src = re.sub(r'extern\s+__shared__\s+([^;\[\]]+?)\s+(\w+)\s*\[\s*\]\s*;', dyn, src)
+    # inline PTX
+    out, i = '', 0
+    for m in re.finditer(r'\basm\s*(volatile\s*)?\(', src):
+        if m.start() < i:
+            continue
+        end = _match_forward(src, m.end() - 1, '(', ')')
+        semi = src.index(';', end)
+        out += src[i:m.start()] + 'simt::unsupported("inline PTX")'
+        i = semi
+    src = out + src[i:]
+    # kernel launches
+    out, i = '', 0
+    while True:
+        k = src.find('<<<', i)
+        if k < 0:
+            break
+        start = _kernel_expr_start(src, k)
+        cfg_end = src.index('>>>', k)
+        cfg = _split_top(src[k + 3:cfg_end])
+        while len(cfg) < 3:
+            cfg.append('0')
+        a0 = src.index('(', cfg_end)
+        a1 = _match_forward(src, a0, '(', ')')
+        kernel, args = src[start:k].strip(), src[a0:a1]
+        out += src[i:start] + 'simt::launch(dim3(%s), dim3(%s), (size_t)(%s), [&] { %s%s; })' % (cfg[0], cfg[1], cfg[2], kernel, args)
+        i = a1
+    return out + src[i:]
+
+
+def build(units, tag=None, extra_flags=()):
+    os.makedirs(OUT, exist_ok=True)
+    tag = tag or '_'.join(os.path.splitext(u)[0] for u in units)
+    texts = {}
+    for name in list(units) + [f for f in os.listdir(CSRC) if f.endswith('.cuh')]:
+        texts[name] = rewrite(open(os.path.join(CSRC, name)).read())
+    runtime = open(os.path.join(HERE, 'simt.cpp')).read() + open(os.path.join(HERE, 'shim', 'cuda_runtime.h')).read()
+    digest = hashlib.sha1(('\0'.join(k + v for k, v in sorted(texts.items())) + runtime + ' '.join(extra_flags)).encode()).hexdigest()[:16]
+    lib = os.path.join(OUT, 'lib%s_%s.so' % (tag, digest))
+    if os.path.exists(lib):
+        return lib
+    srcs = []
+    for name, text in texts.items():
+        path = os.path.join(OUT, name if name.endswith('.cuh') else name + '.cpp')
+        with open(path, 'w') as f:
+            f.write(text)
+        if not name.endswith('.cuh'):
+            srcs.append(path)
+    cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-w', '-DCD_HOST_ONLY', '-I' + OUT, '-I' + os.path.join(HERE, 'shim'),
+           '-I' + HERE] + list(extra_flags) + srcs + [os.path.join(HERE, 'simt.cpp'), '-o', lib]
+    subprocess.check_call(cmd)
+    return lib
+
+
+if __name__ == '__main__':
+    import sys
+    print(build(sys.argv[1:] or ['model2_bwd.cu']))

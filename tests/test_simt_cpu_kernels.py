@@ -1,0 +1,162 @@
+"""The CUDA SOURCE of SIMT kernels that have not run on a B200 yet, executed on the CPU (tests/simt_cpu: the .cu file is compiled
+by g++ against a shim <cuda_runtime.h>, every CUDA thread is a fiber, barriers and warp shuffles are scheduling points) and
+compared with the numpy statement of the same entry point in tests/abi_emulator.py, which in turn is pinned to the reference
+goldens by tests/test_model2_host_logic.py.  Catches indexing, reduction and launch-geometry mistakes in the kernels themselves;
+says nothing about performance or about tcgen05 / TMA code (not executable this way)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'simt_cpu'))
+import abi_emulator as E  # noqa: E402
+
+
+def P(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+@pytest.fixture(scope='module')
+def m2lib():
+    import build
+    return C.CDLL(build.build(['model2_bwd.cu']))
+
+
+def both(lib, name, args_fn, outs):
+    """run `name` from the CPU-compiled CUDA source and from the numpy emulator on identical inputs; `outs` lists the output
+    tensors inside the dict args_fn() builds; returns [(cuda_src_result, emulator_result), ...]"""
+    res = []
+    for impl in (getattr(lib, name), getattr(E, name)):
+        d, args = args_fn()
+        rc = impl(*args)
+        assert rc == 0, (name, rc, lib.simt_last_error() if impl is not getattr(E, name) else '')
+        res.append([d[o].clone() for o in outs])
+    return list(zip(*res))
+
+
+def close(a, b, tol):
+    return float((a.double() - b.double()).abs().max()) <= tol * max(1.0, float(b.abs().max()))
+
+
+@pytest.mark.parametrize('B,HW,Cc,groups,swish,with_cond,pad', [(2, 64, 32, 32, 1, True, 0), (3, 16, 64, 32, 0, False, 8),
+                                                                 (1, 256, 128, 32, 1, True, 4), (2, 9, 96, 32, 1, False, 0)])
+def test_groupnorm_bwd_source(m2lib, B, HW, Cc, groups, swish, with_cond, pad):
+    g = torch.Generator().manual_seed(B * 1000 + HW + Cc)
+    ld = Cc + pad
+
+    def args():
+        d = dict(x=torch.randn(B * HW, ld, generator=g.manual_seed(1)), dy=torch.randn(B * HW, ld, generator=g.manual_seed(2)),
+                 cond=torch.randn(B, Cc, generator=g.manual_seed(3)) if with_cond else None,
+                 gamma=1 + 0.2 * torch.randn(Cc, generator=g.manual_seed(4)), beta=0.1 * torch.randn(Cc, generator=g.manual_seed(5)),
+                 dx=torch.full((B * HW, ld), 7.0), dgamma=torch.full((Cc,), 0.5), dbeta=torch.full((Cc,), -0.25),
+                 dcond=torch.full((B, Cc), 3.0) if with_cond else None)
+        a = (P(d['x']), ld, B, C.c_int64(HW), Cc, groups, P(d['cond']), Cc, P(d['gamma']), P(d['beta']), C.c_float(1e-6), swish,
+             P(d['dy']), ld, P(d['dx']), ld, P(d['dgamma']), P(d['dbeta']), P(d['dcond']), Cc, C.c_void_p(0))
+        return d, a
+    outs = ['dx', 'dgamma', 'dbeta'] + (['dcond'] if with_cond else [])
+    for name, (got, want) in zip(outs, both(m2lib, 'cd_groupnorm_bwd', args, outs)):
+        if name == 'dx':
+            got, want = got[:, :Cc], want[:, :Cc]
+        assert close(got, want, 3e-5), name
+
+
+def test_groupnorm_bwd_leaves_row_padding_alone(m2lib):
+    B, HW, Cc, ld = 2, 16, 32, 40
+    x, dy = torch.randn(B * HW, ld), torch.randn(B * HW, ld)
+    dx = torch.full((B * HW, ld), 7.0)
+    gamma, beta, dg, db = torch.ones(Cc), torch.zeros(Cc), torch.zeros(Cc), torch.zeros(Cc)
+    assert m2lib.cd_groupnorm_bwd(P(x), ld, B, C.c_int64(HW), Cc, 32, P(None), 0, P(gamma), P(beta), C.c_float(1e-6), 1, P(dy), ld,
+                                  P(dx), ld, P(dg), P(db), P(None), 0, C.c_void_p(0)) == 0
+    assert bool((dx[:, Cc:] == 7.0).all()) and bool((dx[:, :Cc] != 7.0).any())
+
+
+@pytest.mark.parametrize('npix,Cc,pad,p', [(37, 5, 3, 0.1), (1000, 64, 0, 0.5), (3, 1, 0, 0.0)])
+def test_dropout_source(m2lib, npix, Cc, pad, p):
+    ld = Cc + pad
+
+    def args():
+        d = dict(x=torch.randn(npix, ld, generator=torch.Generator().manual_seed(7)), y=torch.full((npix, ld), 9.0))
+        return d, (P(d['x']), ld, C.c_int64(npix), Cc, C.c_float(p), C.c_uint64(0x1234567890ABCDEF), P(d['y']), ld, C.c_void_p(0))
+    (got, want), = both(m2lib, 'cd_dropout', args, ['y'])
+    assert torch.equal(got, want)                                     # same hash, same mask, same scaling: bit-exact
+    if p > 0:
+        kept = float((got[:, :Cc] != 0).float().mean())
+        assert abs(kept - (1 - p)) < 0.08
+
+
+@pytest.mark.parametrize('rows,n,pad', [(5, 7, 1), (33, 64, 0), (8, 100, 4)])
+def test_softmax_bwd_rows_source(m2lib, rows, n, pad):
+    ld = n + pad
+
+    def args():
+        g = torch.Generator().manual_seed(3)
+        s = torch.softmax(torch.randn(rows, n, generator=g), dim=1)
+        d = dict(s=torch.nn.functional.pad(s, (0, pad)).contiguous(), ds=torch.nn.functional.pad(torch.randn(rows, n, generator=g), (0, pad), value=5.0).contiguous())
+        return d, (P(d['s']), P(d['ds']), ld, C.c_int64(rows), n, C.c_float(0.125), C.c_void_p(0))
+    (got, want), = both(m2lib, 'cd_softmax_bwd_rows', args, ['ds'])
+    assert close(got[:, :n], want[:, :n], 2e-6) and bool((got[:, n:] == 5.0).all())
+
+
+@pytest.mark.parametrize('B,H,W,Cc,pad', [(2, 3, 5, 8, 0), (1, 4, 4, 32, 4)])
+def test_upsample_bwd_source(m2lib, B, H, W, Cc, pad):
+    ld = Cc + pad
+
+    def args():
+        d = dict(dy=torch.randn(B * 4 * H * W, ld, generator=torch.Generator().manual_seed(5)), dx=torch.full((B * H * W, ld), 2.0))
+        return d, (P(d['dy']), ld, B, H, W, Cc, P(d['dx']), ld, C.c_void_p(0))
+    (got, want), = both(m2lib, 'cd_upsample_nearest2x_bwd', args, ['dx'])
+    assert close(got[:, :Cc], want[:, :Cc], 1e-6) and bool((got[:, Cc:] == 2.0).all())
+
+
+def test_swish_embedding_linear_sources(m2lib):
+    n = 1000
+
+    def a_swish():
+        g = torch.Generator().manual_seed(1)
+        d = dict(dy=torch.randn(n, generator=g), pre=3 * torch.randn(n, generator=g), y=torch.zeros(n), act=torch.zeros(n))
+        return d, (P(d['dy']), P(d['pre']), C.c_int64(n), P(d['y']), P(d['act']), C.c_void_p(0))
+    for got, want in both(m2lib, 'cd_swish', a_swish, ['y', 'act']):
+        assert close(got, want, 2e-6)
+
+    def a_swish_fwd_only():
+        d = dict(pre=torch.linspace(-6, 6, 50), act=torch.zeros(50))
+        return d, (P(None), P(d['pre']), C.c_int64(50), P(None), P(d['act']), C.c_void_p(0))
+    (got, want), = both(m2lib, 'cd_swish', a_swish_fwd_only, ['act'])
+    assert close(got, want, 2e-6)
+
+    for dim in (128, 32, 7):
+        def a_emb():
+            d = dict(t=torch.tensor([0, 1, 49, 999], dtype=torch.int64), emb=torch.full((4, dim), 4.0))
+            return d, (P(d['t']), 4, dim, P(d['emb']), C.c_void_p(0))
+        (got, want), = both(m2lib, 'cd_timestep_embedding', a_emb, ['emb'])
+        assert close(got, want, 2e-4), dim                         # sin / cos of arguments up to 999 in fp32
+
+    for M, K, N, bias in ((3, 128, 512, True), (2, 33, 5, False), (1, 512, 128, True)):
+        def a_lin():
+            g = torch.Generator().manual_seed(9)
+            d = dict(x=torch.randn(M, K, generator=g), w=torch.randn(N, K, generator=g) / K ** 0.5, b=torch.randn(N, generator=g) if bias else None,
+                     y=torch.zeros(M, N))
+            return d, (P(d['x']), K, P(d['w']), P(d['b']), M, N, P(d['y']), C.c_void_p(0))
+        (got, want), = both(m2lib, 'cd_linear_fwd', a_lin, ['y'])
+        assert close(got, want, 5e-6), (M, K, N)
+
+
+def test_augment_u8_source(m2lib):
+    N, Hs, Ws, B, S = 5, 20, 24, 4, 16
+
+    def args():
+        g = torch.Generator().manual_seed(2)
+        d = dict(src=torch.randint(0, 256, (N, Hs, Ws, 3), dtype=torch.uint8, generator=g), index=torch.tensor([4, 0, 2, 2], dtype=torch.int64),
+                 oy=torch.tensor([0, 4, 2, 1], dtype=torch.int32), ox=torch.tensor([8, 0, 3, 5], dtype=torch.int32),
+                 flip=torch.tensor([0, 1, 1, 0], dtype=torch.int32), out=torch.zeros(B, 3, S, S))
+        return d, (P(d['src']), N, Hs, Ws, P(d['index']), P(d['oy']), P(d['ox']), P(d['flip']), B, S, P(d['out']), C.c_void_p(0))
+    (got, want), = both(m2lib, 'cd_augment_u8', args, ['out'])
+    assert torch.equal(got, want)
+    d, a = args()
+    a = list(a); a[9] = 32                                            # crop larger than the source: refused, with a message
+    assert m2lib.cd_augment_u8(*a) == -1
+    m2lib.simt_last_error.restype = C.c_char_p
+    assert b'does not fit' in m2lib.simt_last_error()
