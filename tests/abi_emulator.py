@@ -5,6 +5,7 @@ checked against the reference-generated goldens without a GPU.  It says nothing 
 checked by the `-m gpu` tests through the real library.  Never imported by the product."""
 import ctypes as C
 import math
+import os
 import numpy as np
 
 
@@ -744,8 +745,33 @@ def call(name, *args):
     assert rc == 0
 
 
+_cpu_lib = None
+
+
+def call_cuda_source(name, *args):
+    """the same call executed by the library's own CUDA-core kernel SOURCES compiled for the CPU (tests/simt_cpu: every CUDA
+    thread a fiber; tensor-core entry points defer to the fp32 CUDA-core convolutions)"""
+    global _cpu_lib
+    if _cpu_lib is None:
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'simt_cpu'))
+        import build
+        _cpu_lib = C.CDLL(build.build_all())
+    rc = getattr(_cpu_lib, name)(*args)
+    if rc != 0:
+        buf = C.create_string_buffer(512)
+        _cpu_lib.cd_last_error(buf, 512)
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, buf.value.decode()))
+
+
 class patched:
-    """context manager: route the host modules' `call` / `stream` to the emulator (CPU tensors)"""
+    """context manager: route the host modules' `call` / `stream` to the emulator (CPU tensors).  backend 'numpy' (default) is
+    the numpy statement of every entry point in this file; 'cuda_source' (or COLDDIFF_ABI_BACKEND=cuda_source) executes the
+    CUDA kernel sources on the CPU instead."""
+
+    def __init__(self, backend=None):
+        self.backend = backend or os.environ.get('COLDDIFF_ABI_BACKEND', 'numpy')
+        assert self.backend in ('numpy', 'cuda_source')
 
     def __enter__(self):
         from cold_diffusion_models_b200 import (ops, model2, model2_train, engine, engine_bwd, deblurring, trainer, denoising,
@@ -754,7 +780,7 @@ class patched:
                       defading_generation, snowification)
         self._saved = [(m, m.call, m.stream) for m in self._mods]
         for m in self._mods:
-            m.call = call
+            m.call = call if self.backend == 'numpy' else call_cuda_source
             m.stream = lambda: None
         return self
 

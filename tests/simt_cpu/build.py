@@ -74,7 +74,22 @@ def _kernel_expr_start(s, end):
     return j
 
 
+# device helpers of the library whose bodies are inline PTX with a plain-C meaning on the CPU: asynchronous global->shared
+# copies complete at once (so commit / wait are no-ops), cvt.rna.tf32 is round-to-nearest-away on the low 13 mantissa bits
+_PTX_HELPER_BODIES = {
+    'cd_cp_async4': '{ if (valid) memcpy(smem_dst, gsrc, 4); else memset(smem_dst, 0, 4); }',
+    'cd_cp_async16': '{ if (valid) memcpy(smem_dst, gsrc, 16); else memset(smem_dst, 0, 16); }',
+    'cd_round_tf32': '{ unsigned u = __float_as_uint(x); u = (u + 0x1000u) & ~0x1FFFu; return __uint_as_float(u); }',
+}
+
+
 def rewrite(src):
+    for name, body in _PTX_HELPER_BODIES.items():
+        m = re.search(r'\b%s\s*\([^)]*\)\s*\{' % name, src)
+        if m:
+            end = _match_forward(src, m.end() - 1, '{', '}')
+            src = src[:m.end() - 1] + body + src[end:]
+    src = re.sub(r'asm\s+volatile\s*\(\s*"cp\.async\.(commit_group|wait_group\s+\d+|wait_all);"\s*:::\s*"memory"\s*\)', '(void)0', src)
     src = src.replace('"../../include/colddiff.h"', '"%s"' % os.path.join(ROOT, 'include', 'colddiff.h'))
     # dynamic shared memory
     def dyn(m):
@@ -110,13 +125,23 @@ def rewrite(src):
     return out + src[i:]
 
 
-def build(units, tag=None, extra_flags=()):
+SIMT_UNITS = ['api.cu', 'elementwise.cu', 'backward.cu', 'degrade.cu', 'conv_simt.cu', 'model2_bwd.cu']
+
+
+def build_all():
+    """every CUDA-core translation unit + the tensor-core stubs: a CPU library with the complete C ABI of include/colddiff.h"""
+    return build(SIMT_UNITS, tag='colddiff_cpu', extra_sources=[os.path.join(HERE, 'tc_stubs.cpp')])
+
+
+def build(units, tag=None, extra_flags=(), extra_sources=()):
     os.makedirs(OUT, exist_ok=True)
+    if 'api.cu' not in units:
+        units = ['api.cu'] + list(units)
     tag = tag or '_'.join(os.path.splitext(u)[0] for u in units)
     texts = {}
     for name in list(units) + [f for f in os.listdir(CSRC) if f.endswith('.cuh')]:
         texts[name] = rewrite(open(os.path.join(CSRC, name)).read())
-    runtime = open(os.path.join(HERE, 'simt.cpp')).read() + open(os.path.join(HERE, 'shim', 'cuda_runtime.h')).read()
+    runtime = ''.join(open(f).read() for f in [os.path.join(HERE, 'simt.cpp'), os.path.join(HERE, 'shim', 'cuda_runtime.h')] + list(extra_sources))
     digest = hashlib.sha1(('\0'.join(k + v for k, v in sorted(texts.items())) + runtime + ' '.join(extra_flags)).encode()).hexdigest()[:16]
     lib = os.path.join(OUT, 'lib%s_%s.so' % (tag, digest))
     if os.path.exists(lib):
@@ -128,12 +153,12 @@ def build(units, tag=None, extra_flags=()):
             f.write(text)
         if not name.endswith('.cuh'):
             srcs.append(path)
-    cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-w', '-DCD_HOST_ONLY', '-I' + OUT, '-I' + os.path.join(HERE, 'shim'),
-           '-I' + HERE] + list(extra_flags) + srcs + [os.path.join(HERE, 'simt.cpp'), '-o', lib]
+    cmd = ['g++', '-O2', '-g', '-std=c++17', '-fPIC', '-shared', '-w', '-DCD_HOST_ONLY', '-I' + OUT, '-I' + os.path.join(HERE, 'shim'),
+           '-I' + HERE, '-I' + os.path.join(ROOT, 'include')] + list(extra_flags) + srcs + list(extra_sources) + [os.path.join(HERE, 'simt.cpp'), '-o', lib]
     subprocess.check_call(cmd)
     return lib
 
 
 if __name__ == '__main__':
     import sys
-    print(build(sys.argv[1:] or ['model2_bwd.cu']))
+    print(build(sys.argv[1:]) if sys.argv[1:] else build_all())

@@ -73,6 +73,21 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 int simt_occupancy();                                                    // settable from the test (default 2)
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) {
   *n = simt_occupancy(); return cudaSuccess; }
+static inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t width, size_t height, cudaStream_t = nullptr) {
+  for (size_t r = 0; r < height; ++r) memset((char*)p + r * pitch, v, width);
+  return cudaSuccess; }
+// driver-API corner used by the library (cuMemsetD32Async through cudaGetDriverEntryPoint)
+typedef int CUresult;
+typedef unsigned long long CUdeviceptr;
+typedef void* CUstream;
+enum { CUDA_SUCCESS = 0 };
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+enum { cudaEnableDefault = 0 };
+static inline CUresult simt_cuMemsetD32Async(CUdeviceptr p, unsigned v, size_t n, CUstream) {
+  unsigned* q = reinterpret_cast<unsigned*>(p); for (size_t i = 0; i < n; ++i) q[i] = v; return CUDA_SUCCESS; }
+static inline cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, int, cudaDriverEntryPointQueryResult* q) {
+  if (strcmp(name, "cuMemsetD32Async") == 0) { *fn = (void*)&simt_cuMemsetD32Async; *q = cudaDriverEntryPointSuccess; return cudaSuccess; }
+  *fn = nullptr; *q = cudaDriverEntryPointSymbolNotFound; return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 

@@ -10,35 +10,73 @@
 uint3 threadIdx, blockIdx;
 dim3 blockDim(1), gridDim(1);
 
+// ---- context switch: callee-saved registers + stack pointer (no signal-mask system call, unlike swapcontext) ---------------
+#if defined(__x86_64__)
+extern "C" void simt_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl simt_switch
+.type simt_switch, @function
+simt_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size simt_switch, .-simt_switch
+)");
+#define SIMT_FAST_SWITCH 1
+#endif
+
 namespace {
 enum State { READY, AT_BLOCK, AT_WARP, DONE };
-struct Fiber { ucontext_t ctx; State st; char* stack; };
+#ifdef SIMT_FAST_SWITCH
+struct Fiber { void* sp; State st; };
+void* sched_sp;
+#else
+struct Fiber { ucontext_t ctx; State st; };
+ucontext_t sched_ctx;
+#endif
 const size_t kStack = 256 << 10;
 std::vector<Fiber> fibers;
 std::vector<char*> stacks;
-ucontext_t sched_ctx;
 int cur = -1, nthreads = 0;
 const std::function<void()>* body_fn = nullptr;
 std::vector<unsigned long long> slots;                 // one per thread (warp exchange buffers)
 std::vector<unsigned char> dyn;                        // dynamic shared memory of the running block
 int occupancy = 2;
-char last_error[512];
 
 void set_tid(int i) {
   threadIdx.x = i % blockDim.x;
   threadIdx.y = (i / blockDim.x) % blockDim.y;
   threadIdx.z = i / (blockDim.x * blockDim.y);
 }
+#ifdef SIMT_FAST_SWITCH
+void to_scheduler() { simt_switch(&fibers[cur].sp, sched_sp); }
+void to_fiber(int i) { simt_switch(&sched_sp, fibers[i].sp); }
+#else
+void to_scheduler() { swapcontext(&fibers[cur].ctx, &sched_ctx); }
+void to_fiber(int i) { swapcontext(&sched_ctx, &fibers[i].ctx); }
+#endif
 void trampoline() {
   (*body_fn)();
   fibers[cur].st = DONE;
-  swapcontext(&fibers[cur].ctx, &sched_ctx);
+  to_scheduler();
+  abort();                                             // a finished fiber is never resumed
 }
 void park(State s) {
   fibers[cur].st = s;
-  const int me = cur;
-  swapcontext(&fibers[me].ctx, &sched_ctx);
-  // resumed by the scheduler with cur == me and threadIdx restored
+  to_scheduler();                                      // resumed by the scheduler with cur and threadIdx restored
 }
 void run_block() {
   const int n = nthreads;
@@ -52,12 +90,23 @@ void run_block() {
   fibers.resize(n);
   slots.assign(n, 0);
   for (int i = 0; i < n; ++i) {
+    fibers[i].st = READY;
+#ifdef SIMT_FAST_SWITCH
+    // initial frame: six zeroed callee-saved registers, then the address `ret` jumps to; the slot above it plays the return
+    // address of trampoline, so that rsp % 16 == 8 at its entry as the ABI requires
+    uintptr_t top = ((uintptr_t)stacks[i] + kStack) & ~(uintptr_t)15;
+    void** sp = (void**)(top - 16);
+    sp[1] = nullptr;
+    sp[0] = (void*)&trampoline;
+    for (int r = 1; r <= 6; ++r) sp[-r] = nullptr;
+    fibers[i].sp = (void*)(sp - 6);
+#else
     getcontext(&fibers[i].ctx);
     fibers[i].ctx.uc_stack.ss_sp = stacks[i];
     fibers[i].ctx.uc_stack.ss_size = kStack;
     fibers[i].ctx.uc_link = &sched_ctx;
-    fibers[i].st = READY;
     makecontext(&fibers[i].ctx, trampoline, 0);
+#endif
   }
   int done = 0;
   while (done < n) {
@@ -65,7 +114,7 @@ void run_block() {
     for (int i = 0; i < n; ++i) {
       if (fibers[i].st != READY) continue;
       cur = i; set_tid(i);
-      swapcontext(&sched_ctx, &fibers[i].ctx);
+      to_fiber(i);
       ran = true;
       if (fibers[i].st == DONE) ++done;
     }
@@ -118,8 +167,3 @@ bool lane_alive(int lane) { const int i = (cur / 32) * 32 + lane; return i < nth
 void unsupported(const char* what) { fprintf(stderr, "simt-cpu: unsupported on the CPU: %s\n", what); abort(); }
 }  // namespace simt
 
-// error plumbing of libcolddiff (api.cu is not part of the CPU build)
-void cd_set_error(const char* fmt, ...) {
-  va_list ap; va_start(ap, fmt); vsnprintf(last_error, sizeof(last_error), fmt, ap); va_end(ap);
-}
-extern "C" const char* simt_last_error() { return last_error; }
