@@ -129,8 +129,12 @@ SIMT_UNITS = ['api.cu', 'elementwise.cu', 'backward.cu', 'degrade.cu', 'conv_sim
 
 
 def build_all():
-    """every CUDA-core translation unit + the tensor-core stubs: a CPU library with the complete C ABI of include/colddiff.h"""
-    return build(SIMT_UNITS, tag='colddiff_cpu', extra_sources=[os.path.join(HERE, 'tc_stubs.cpp')])
+    """every CUDA-core translation unit + the tensor-core stubs: a CPU library with the complete C ABI of include/colddiff.h.
+    SIMT_CPU_ASAN=1 builds it with AddressSanitizer (run python under LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+    ASAN_OPTIONS=detect_leaks=0): out-of-bounds accesses of the kernels to heap tensors / shared arrays then abort with a report."""
+    asan = os.environ.get('SIMT_CPU_ASAN') == '1'
+    return build(SIMT_UNITS, tag='colddiff_cpu_asan' if asan else 'colddiff_cpu', extra_sources=[os.path.join(HERE, 'tc_stubs.cpp')],
+                 extra_flags=('-fsanitize=address', '-fno-omit-frame-pointer', '-O1') if asan else ())
 
 
 def build(units, tag=None, extra_flags=(), extra_sources=()):

@@ -21,7 +21,9 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)
-#define __shared__ static
+// statically sized shared arrays live in their own section so that the scheduler can poison them (NaN pattern) before every
+// block: shared memory is uninitialised on the GPU, and a kernel that reads it before writing it then fails the parity tests
+#define __shared__ static __attribute__((section("simt_shared")))
 #define __constant__ static
 #define __align__(n) alignas(n)
 #ifndef __restrict__

@@ -7,6 +7,8 @@
 #include <vector>
 #include <stdarg.h>
 
+extern "C" char __start_simt_shared[] __attribute__((weak));
+extern "C" char __stop_simt_shared[] __attribute__((weak));
 uint3 threadIdx, blockIdx;
 dim3 blockDim(1), gridDim(1);
 
@@ -89,6 +91,9 @@ void run_block() {
   }
   fibers.resize(n);
   slots.assign(n, 0);
+  if (__start_simt_shared && __stop_simt_shared > __start_simt_shared)        // static __shared__ arrays: all-ones = NaN
+    memset(__start_simt_shared, 0xFF, __stop_simt_shared - __start_simt_shared);
+  if (!dyn.empty()) memset(dyn.data(), 0xFF, dyn.size());                      // dynamic shared memory likewise
   for (int i = 0; i < n; ++i) {
     fibers[i].st = READY;
 #ifdef SIMT_FAST_SWITCH
@@ -149,7 +154,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
   nthreads = (int)(block.x * block.y * block.z);
   if (nthreads <= 0 || nthreads > 1024) { fprintf(stderr, "simt-cpu: bad block size %d\n", nthreads); abort(); }
   body_fn = &body;
-  dyn.assign(dyn_smem_bytes + 16, 0xCD);                                 // poisoned, like uninitialised shared memory
+  dyn.assign(dyn_smem_bytes + 16, 0xFF);                                 // NaN-poisoned, like uninitialised shared memory
   for (unsigned z = 0; z < grid.z; ++z)
     for (unsigned y = 0; y < grid.y; ++y)
       for (unsigned x = 0; x < grid.x; ++x) {
