@@ -57,6 +57,9 @@ const std::function<void()>* body_fn = nullptr;
 std::vector<unsigned long long> slots;                 // one per thread (warp exchange buffers)
 std::vector<unsigned char> dyn;                        // dynamic shared memory of the running block
 int occupancy = 2;
+// threads of a block are resumed in ascending order, or descending with SIMT_CPU_ORDER=reverse: a missing barrier between a
+// shared-memory write and another thread's read shows as a poisoned (NaN) or stale value under at least one of the two orders
+bool reverse_order = getenv("SIMT_CPU_ORDER") && strcmp(getenv("SIMT_CPU_ORDER"), "reverse") == 0;
 
 void set_tid(int i) {
   threadIdx.x = i % blockDim.x;
@@ -116,7 +119,8 @@ void run_block() {
   int done = 0;
   while (done < n) {
     bool ran = false;
-    for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < n; ++k) {
+      const int i = reverse_order ? n - 1 - k : k;
       if (fibers[i].st != READY) continue;
       cur = i; set_tid(i);
       to_fiber(i);
@@ -146,6 +150,7 @@ void run_block() {
 
 int simt_occupancy() { return occupancy; }
 extern "C" void simt_set_occupancy(int n) { occupancy = n; }
+extern "C" void simt_set_reverse_order(int r) { reverse_order = r != 0; }
 
 namespace simt {
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {

@@ -19,10 +19,14 @@ def P(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-@pytest.fixture(scope='module')
-def m2lib():
+@pytest.fixture(scope='module', params=['ascending', 'descending'])
+def m2lib(request):
+    """threads of a block resumed in ascending / descending order: a missing barrier shows under at least one of them"""
     import build
-    return C.CDLL(build.build(['model2_bwd.cu']))
+    lib = C.CDLL(build.build(['model2_bwd.cu']))
+    lib.simt_set_reverse_order(int(request.param == 'descending'))
+    yield lib
+    lib.simt_set_reverse_order(0)
 
 
 def both(lib, name, args_fn, outs):
