@@ -66,7 +66,7 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-_LAUNCHES = {'cd_linattn_context': 2, 'cd_conv_wgrad': 2, 'cd_time_mlp_fwd': 2, 'cd_version': 0, 'cd_last_error': 0}
+_LAUNCHES = {'cd_linattn_context': 2, 'cd_conv_wgrad': 2, 'cd_time_mlp_fwd': 2, 'cd_time_mlp2_fwd': 2, 'cd_version': 0, 'cd_last_error': 0}
 _launch_count = 0
 
 

@@ -540,15 +540,19 @@ time_mlp_kernel(const long long* __restrict__ t, int dim, const float* __restric
 }
 
 // conditioning rows of every ConvNextBlock (GELU -> Linear(dim, block_dim), DB:143-146) for all batch elements:
-// cond_all[b][o] = bc[o] + sum_i wc[o][i] * gelu(temb[b][i]).  grid (row chunks, B); one warp per output row, lanes stride the
-// (coalesced) weight row.  (Inside the one-block-per-sample kernel above these ~6000 rows were 466 us of serial work.)
+// cond_all[b][o] = bc[o] + sum_i wc[o][i] * act(temb[b][i]), act = GELU (ConvNeXt Unet) or swish (DDPM Model, M2:121).
+// grid (row chunks, B); one warp per output row, lanes stride the (coalesced) weight row.  (Inside the one-block-per-sample
+// kernel above these ~6000 rows were 466 us of serial work.)
 constexpr int kCondRows = 64;
 __global__ void __launch_bounds__(256)
 cond_proj_kernel(const float* __restrict__ temb, int dim, const float* __restrict__ wc, const float* __restrict__ bc, int sumC,
-                 float* __restrict__ cond_all) {
+                 float* __restrict__ cond_all, int swish) {
   extern __shared__ float gt[];          // [dim]
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < dim; i += blockDim.x) gt[i] = cd_gelu(temb[b * dim + i]);
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const float a = temb[b * dim + i];
+    gt[i] = swish ? a / (1.f + expf(-a)) : cd_gelu(a);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int o0 = blockIdx.x * kCondRows;
@@ -790,7 +794,7 @@ extern "C" int cd_time_mlp_fwd(const int64_t* t, int B, int dim, const float* w1
                                                                      wc, bc, sumC, sinemb, hid_pre, temb, cond_all);
   CD_LAUNCH_CHECK();
   if (sumC > 0) {
-    cond_proj_kernel<<<dim3(cd_cdiv(sumC, kCondRows), B), 256, sizeof(float) * dim, static_cast<cudaStream_t>(stream)>>>(temb, dim, wc, bc, sumC, cond_all);
+    cond_proj_kernel<<<dim3(cd_cdiv(sumC, kCondRows), B), 256, sizeof(float) * dim, static_cast<cudaStream_t>(stream)>>>(temb, dim, wc, bc, sumC, cond_all, 0);
     CD_LAUNCH_CHECK();
   }
   return 0;
@@ -1001,6 +1005,38 @@ time_mlp2_kernel(const long long* __restrict__ t, int dim, int hid, int tdim, in
     cond_all[static_cast<long long>(b) * sumC + o] = a;
   }
 }
+// the two dense layers of the same MLP with one warp per output (lanes stride the weight row: coalesced), writing temb; the
+// conditioning rows then come from cond_proj_kernel across the whole grid
+__global__ void __launch_bounds__(256)
+time_mlp2_dense_kernel(const long long* __restrict__ t, int dim, int hid, int tdim, int act, const float* __restrict__ w1,
+                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                       float* __restrict__ temb) {
+  extern __shared__ float sm[];          // emb[dim] | h[hid]
+  float* emb = sm; float* h = sm + dim;
+  const int b = blockIdx.x;
+  const float tv = static_cast<float>(t[b]);
+  const int half = dim / 2;
+  const float k = logf(10000.f) / (half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) { const float a = tv * expf(-k * i); emb[i] = sinf(a); emb[i + half] = cosf(a); }
+  if ((dim & 1) && threadIdx.x == 0) emb[dim - 1] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = warp; o < hid; o += nw) {
+    const float* wr = w1 + static_cast<long long>(o) * dim;
+    float a = 0.f;
+    for (int i = lane; i < dim; i += 32) a = fmaf(wr[i], emb[i], a);
+    a = cd_warp_sum(a) + b1[o];
+    if (lane == 0) h[o] = act ? a / (1.f + expf(-a)) : cd_gelu(a);
+  }
+  __syncthreads();
+  for (int o = warp; o < tdim; o += nw) {
+    const float* wr = w2 + static_cast<long long>(o) * hid;
+    float a = 0.f;
+    for (int i = lane; i < hid; i += 32) a = fmaf(wr[i], h[i], a);
+    a = cd_warp_sum(a) + b2[o];
+    if (lane == 0) temb[b * tdim + o] = a;
+  }
+}
 }  // namespace
 
 extern "C" int cd_groupnorm_fwd(const float* x, int x_ld, int B, int64_t HW, int C, int groups, const float* cond, int cond_ld,
@@ -1040,6 +1076,17 @@ extern "C" int cd_nhwc_to_nchw(const float* x, int ld, int B, int H, int W, int 
 extern "C" int cd_time_mlp2_fwd(const int64_t* t, int B, int dim, int hid, int tdim, int act, const float* w1, const float* b1,
                                 const float* w2, const float* b2, const float* wc, const float* bc, int sumC, float* temb,
                                 float* cond_all, void* stream) {
+  if (temb) {        // with a temb buffer: dense layers per sample, conditioning rows over the whole grid (2 launches)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    time_mlp2_dense_kernel<<<B, 256, sizeof(float) * (dim + hid), st>>>(reinterpret_cast<const long long*>(t), dim, hid, tdim, act, w1, b1,
+                                                                     w2, b2, temb);
+    CD_LAUNCH_CHECK();
+    if (sumC > 0) {
+      cond_proj_kernel<<<dim3(cd_cdiv(sumC, kCondRows), B), 256, sizeof(float) * tdim, st>>>(temb, tdim, wc, bc, sumC, cond_all, act);
+      CD_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   const size_t smem = sizeof(float) * (dim + hid + tdim);
   time_mlp2_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(t), dim, hid, tdim, act, w1, b1,
                                                                      w2, b2, wc, bc, sumC, temb, cond_all);

@@ -315,7 +315,7 @@ class Model(nn.Module):
         cond_all = self._buf('cond', (B, self._sumC))
         d0, d1 = self.temb.dense[0], self.temb.dense[1]
         call('cd_time_mlp2_fwd', ptr(t), B, self.ch, self.temb_ch, self.temb_ch, 1, ptr(d0.weight), ptr(d0.bias), ptr(d1.weight), ptr(d1.bias),
-             ptr(P['cond.w']), ptr(P['cond.b']), self._sumC, C.c_void_p(0), ptr(cond_all), stream())
+             ptr(P['cond.w']), ptr(P['cond.b']), self._sumC, ptr(self._buf('temb', (B, self.temb_ch))), ptr(cond_all), stream())
         ld0 = Cin if Cin % 4 == 0 else 4
         x0 = self._buf('x0', (B, H, W, ld0))
         call('cd_nchw_to_nhwc', ptr(x), B, Cin, H, W, ptr(x0), ld0, stream())

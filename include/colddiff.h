@@ -270,7 +270,9 @@ int cd_transpose_batched(const float* src, int ld, int B, int R, int C, float* d
 /* F.interpolate(scale_factor=2, mode='nearest') on NHWC (M2:47-48) */
 int cd_upsample_nearest2x(const float* x, int x_ld, int B, int H, int W, int C, float* y, int y_ld, void* stream);
 int cd_nhwc_to_nchw(const float* x, int ld, int B, int H, int W, int C, float* out, void* stream);
-/* get_timestep_embedding -> dense0 -> act -> dense1 (= temb) ; cond_all = Wc act(temb) + bc (all blocks' temb_proj) (M2:6-24,289-294,122) */
+/* get_timestep_embedding -> dense0 -> act -> dense1 (= temb) ; cond_all = Wc act(temb) + bc (all blocks' temb_proj) (M2:6-24,289-294,122).
+ * temb ([B][tdim], optional output): when given, the dense layers run one block per sample and the sumC conditioning rows are
+ * spread over the whole grid (2 launches); with temb == NULL everything runs in one block per sample (1 launch, slow for large sumC). */
 int cd_time_mlp2_fwd(const int64_t* t, int B, int dim, int hid, int tdim, int act, const float* w1, const float* b1,
                      const float* w2, const float* b2, const float* wc, const float* bc, int sumC, float* temb,
                      float* cond_all, void* stream);

@@ -165,3 +165,27 @@ def test_augment_u8_source(m2lib):
     buf = C.create_string_buffer(256)
     m2lib.cd_last_error(buf, 256)
     assert b'does not fit' in buf.value
+
+
+@pytest.fixture(scope='module')
+def cpulib():
+    import build
+    return C.CDLL(build.build_all())
+
+
+@pytest.mark.parametrize('with_temb', [True, False])
+@pytest.mark.parametrize('B,dim,hid,tdim,act,sumC', [(3, 128, 512, 512, 1, 700), (2, 32, 128, 128, 1, 65), (2, 64, 256, 64, 0, 130), (1, 33, 40, 24, 1, 5)])
+def test_time_mlp2_source_both_paths(cpulib, with_temb, B, dim, hid, tdim, act, sumC):
+    """generalised time MLP (DDPM `Model`): the two-launch path taken when a temb buffer is given (dense layers warp-per-output,
+    conditioning rows over the grid) and the one-block-per-sample path without it, against the numpy statement"""
+    def args():
+        g = torch.Generator().manual_seed(dim + sumC)
+        r = lambda *s: torch.randn(*s, generator=g)
+        d = dict(t=torch.tensor([0, 17, 999][:B], dtype=torch.int64), w1=r(hid, dim) / dim ** 0.5, b1=0.1 * r(hid), w2=r(tdim, hid) / hid ** 0.5,
+                 b2=0.1 * r(tdim), wc=r(sumC, tdim) / tdim ** 0.5, bc=0.1 * r(sumC), temb=torch.full((B, tdim), 9.0) if with_temb else None,
+                 cond=torch.full((B, sumC), 9.0))
+        return d, (P(d['t']), B, dim, hid, tdim, act, P(d['w1']), P(d['b1']), P(d['w2']), P(d['b2']), P(d['wc']), P(d['bc']), sumC, P(d['temb']),
+                   P(d['cond']), C.c_void_p(0))
+    outs = ['cond'] + (['temb'] if with_temb else [])
+    for got, want in both(cpulib, 'cd_time_mlp2_fwd', args, outs):
+        assert close(got, want, 2e-4)            # sin / cos of arguments up to 999 in fp32, then three dense layers
