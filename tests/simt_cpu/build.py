@@ -160,6 +160,9 @@ def build(units, tag=None, extra_flags=(), extra_sources=()):
     cmd = ['g++', '-O2', '-g', '-std=c++17', '-fPIC', '-shared', '-w', '-DCD_HOST_ONLY', '-I' + OUT, '-I' + os.path.join(HERE, 'shim'),
            '-I' + HERE, '-I' + os.path.join(ROOT, 'include')] + list(extra_flags) + srcs + list(extra_sources) + [os.path.join(HERE, 'simt.cpp'), '-o', lib]
     subprocess.check_call(cmd)
+    for f in os.listdir(OUT):                                   # older builds of the same library
+        if f.startswith('lib%s_' % tag) and f.endswith('.so') and os.path.join(OUT, f) != lib and f[len('lib%s_' % tag):-3].isalnum():
+            os.remove(os.path.join(OUT, f))
     return lib
 
 
