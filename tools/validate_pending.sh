@@ -1,0 +1,18 @@
+#!/bin/bash
+# One gpurun call that runs everything written after the round-1 GPU budget was spent (NOTES.md, "Code that exists but has not
+# run on a B200 yet") plus the two measurements round 1 still owes.  Usage (about 12 GPU-minutes):
+#   gpurun --timeout 1500 -- 'bash tools/validate_pending.sh'
+# Every step has its own timeout and log under gpurun_out/pending/; a failing step does not stop the next one.
+mkdir -p gpurun_out/pending
+out=gpurun_out/pending
+step() { name=$1; shift; echo "== $name"; ( timeout "$TMO" "$@" ) > $out/$name.log 2>&1; echo "$name exit $?" | tee -a $out/summary.txt; tail -n 3 $out/$name.log; }
+: > $out/summary.txt
+TMO=600 step gpu_tests           python -m pytest tests -q -m gpu
+TMO=300 step model_training      env COLDDIFF_MODEL_TRAINING=1 python -m pytest tests/test_model2_train_gpu.py -q
+TMO=200 step wgrad_bias_fusion   env COLDDIFF_EXPERIMENTAL=1 python -m pytest tests/test_conv_gpu.py -q -k fused_bias
+TMO=300 step bench               python bench.py
+TMO=300 step eager_comparator    python bench.py --impl reference --reference-device cuda --steps 3 --warmup 2
+# wgrad with the bias column sums folded in (one extra N = 32 MMA per tile) against the separate cd_colsum launches
+TMO=200 step op_profile_default  python tools/op_profile.py
+grep -h '"metric"' $out/bench.log $out/eager_comparator.log > $out/bench_lines.json 2>/dev/null
+cat $out/summary.txt
