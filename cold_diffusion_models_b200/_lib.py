@@ -43,6 +43,14 @@ class ConvDesc(C.Structure):
                 ('aux', C.c_void_p), ('aux_ld', C.c_int32)]
 
 
+
+
+class RepackJob(C.Structure):          # CdRepackJob (include/colddiff.h): one row of the device-resident table of the batched repacks
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('O', C.c_int32), ('I', C.c_int32), ('KH', C.c_int32), ('KW', C.c_int32),
+                ('transposed_conv', C.c_int32), ('mode', C.c_int32), ('ntaps', C.c_int32), ('round_tf32', C.c_int32),
+                ('ky', C.c_int32 * CD_MAX_TAPS), ('kx', C.c_int32 * CD_MAX_TAPS), ('block0', C.c_int32), ('nblocks', C.c_int32)]
+
+
 lib.cd_version.restype = C.c_int
 if os.environ.get('COLDDIFF_2CTA') in ('0', '1', '2'):   # SM-pair (cta_group::2) convolution kernel, csrc/conv_tc2.cu; library default 1
     lib.cd_conv_tc_set_2cta(int(os.environ['COLDDIFF_2CTA']))

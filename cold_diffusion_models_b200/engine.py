@@ -24,6 +24,21 @@ T3D = ops.taps_conv_dgrad(3, 1)
 TPAR = {(py, px): ops.taps_convT4_parity(py, px) for py in (0, 1) for px in (0, 1)}
 
 
+_BATCHED_REPACK = None
+
+
+def batched_repack(enable=None):
+    """switch of the one-launch weight repacks (ops.RepackBatch: cd_pack_weight_batched / cd_unpack_wgrad_batched).  Default
+    from COLDDIFF_BATCHED_REPACK (off until the kernels have run on a B200; NOTES.md 'code that has not run on a B200 yet')."""
+    global _BATCHED_REPACK
+    if enable is not None:
+        _BATCHED_REPACK = bool(enable)
+    if _BATCHED_REPACK is None:
+        import os
+        _BATCHED_REPACK = os.environ.get('COLDDIFF_BATCHED_REPACK', '0') == '1'
+    return _BATCHED_REPACK
+
+
 def _tc_ok(*chans):
     return all(c % 32 == 0 for c in chans)
 
@@ -64,6 +79,7 @@ class UnetEngine(_BackwardHolder):
         self.dim = unet.dim
         self._bufs = {}
         self._packed = {}
+        self._batches = {}
         self._dirty = True
         self._version = None
         self.conv_impl = CONV_TC
@@ -113,19 +129,46 @@ class UnetEngine(_BackwardHolder):
     def _params_version(self):
         return tuple(p._version for p in self.unet.parameters())
 
+    def _pack(self, batch, key, w, taps, mode=0, transposed_conv=False):
+        """packed operand P[key] of weight `w`: launched at once, or queued on `batch` (ops.RepackBatch) when batching is on"""
+        P = self._packed
+        if batch is None:
+            P[key] = ops.pack_weight(w, taps, mode=mode, transposed_conv=transposed_conv, round_tf32=False, out=P.get(key))
+            return
+        out = P.get(key)
+        if out is None:
+            if transposed_conv:
+                I, O = w.shape[0], w.shape[1]
+            else:
+                O, I = w.shape[0], w.shape[1]
+            n, k = (O, I) if mode == 0 else (I, O)
+            out = P[key] = torch.empty((len(taps), n, k), device=w.device, dtype=torch.float32)
+        batch.add(w, taps, out, shape=tuple(w.shape), mode=mode, transposed_conv=transposed_conv, round_tf32=False)
+
+    def _repack_batch(self, name, kind):
+        """the persistent ops.RepackBatch `name` (emptied), or None when COLDDIFF_BATCHED_REPACK is off"""
+        if not batched_repack():
+            return None
+        b = self._batches.get(name)
+        if b is None:
+            b = self._batches[name] = ops.RepackBatch(kind)
+        b.clear()
+        return b
+
     def prepare_weights(self, force=False):
         """(re)pack reference-layout parameters into kernel layouts when they changed."""
         ver = self._params_version()
         if not (force or self._dirty or ver != self._version):
             return
         P = self._packed
+        batch = self._repack_batch('pack_fwd', 'pack')
         with torch.no_grad():
             for name, bs in self.blocks.items():
                 m = bs.mod
-                P[name + '.w1'] = ops.pack_weight(m.net[1].weight, T3, round_tf32=False, out=P.get(name + '.w1'))
-                P[name + '.w2'] = ops.pack_weight(m.net[3].weight, T3, round_tf32=False, out=P.get(name + '.w2'))
+                self._pack(batch, name + '.w1', m.net[1].weight, T3)
+                self._pack(batch, name + '.w2', m.net[3].weight, T3)
                 if bs.has_res:
-                    P[name + '.wr'] = ops.pack_weight(m.res_conv.weight, T1, round_tf32=False, out=P.get(name + '.wr'))
+                    self._pack(batch, name + '.wr', m.res_conv.weight, T1)
                     # bias of the fused [conv2 | res_conv] GEMM
                     b = P.get(name + '.b2r')
                     if b is None:
@@ -133,15 +176,15 @@ class UnetEngine(_BackwardHolder):
                     torch.add(m.net[3].bias, m.res_conv.bias, out=b)
             for spec in self._attn_specs():
                 a = spec.attn
-                P[spec.name + '.wqkv'] = ops.pack_weight(a.to_qkv.weight, T1, round_tf32=False, out=P.get(spec.name + '.wqkv'))
+                self._pack(batch, spec.name + '.wqkv', a.to_qkv.weight, T1)
             for i, lv in enumerate(self.levels_down):
                 if lv[3] is not None:
-                    P['downs.%d.3' % i] = ops.pack_weight(lv[3].weight, T4, round_tf32=False, out=P.get('downs.%d.3' % i))
+                    self._pack(batch, 'downs.%d.3' % i, lv[3].weight, T4)
             for i, lv in enumerate(self.levels_up):
                 if lv[3] is not None:
                     for k, tp in TPAR.items():
                         key = 'ups.%d.3.%d%d' % (i, k[0], k[1])
-                        P[key] = ops.pack_weight(lv[3].weight, tp, transposed_conv=True, round_tf32=False, out=P.get(key))
+                        self._pack(batch, key, lv[3].weight, tp, transposed_conv=True)
             if self.cond_blocks:
                 wc = P.get('cond.w')
                 if wc is None:
@@ -150,6 +193,8 @@ class UnetEngine(_BackwardHolder):
                 for bs in self.cond_blocks:
                     wc[bs.cond_off:bs.cond_off + bs.din].copy_(bs.mod.mlp[1].weight)
                     P['cond.b'][bs.cond_off:bs.cond_off + bs.din].copy_(bs.mod.mlp[1].bias)
+            if batch is not None:
+                batch.run()
         self._dirty = False
         self._version = ver
 

@@ -82,41 +82,51 @@ class BackwardMixin:
         ver = self._params_version()
         if getattr(self, '_bwd_version', None) == ver:
             return
-        P = self._packed
+        batch = self._repack_batch('pack_bwd', 'pack')
         with torch.no_grad():
             for name, bs in self.blocks.items():
                 m = bs.mod
-                P[name + '.w1T'] = ops.pack_weight(m.net[1].weight, T3D, mode=1, round_tf32=False, out=P.get(name + '.w1T'))
-                P[name + '.w2T'] = ops.pack_weight(m.net[3].weight, T3D, mode=1, round_tf32=False, out=P.get(name + '.w2T'))
+                self._pack(batch, name + '.w1T', m.net[1].weight, T3D, mode=1)
+                self._pack(batch, name + '.w2T', m.net[3].weight, T3D, mode=1)
                 if bs.has_res:
-                    P[name + '.wrT'] = ops.pack_weight(m.res_conv.weight, T1, mode=1, round_tf32=False, out=P.get(name + '.wrT'))
+                    self._pack(batch, name + '.wrT', m.res_conv.weight, T1, mode=1)
             for spec in self._attn_specs():
-                P[spec.name + '.wqkvT'] = ops.pack_weight(spec.attn.to_qkv.weight, T1, mode=1, round_tf32=False,
-                                                          out=P.get(spec.name + '.wqkvT'))
+                self._pack(batch, spec.name + '.wqkvT', spec.attn.to_qkv.weight, T1, mode=1)
             for i, lv in enumerate(self.levels_down):
                 if lv[3] is not None:
                     for k, tp in TPAR.items():
-                        key = 'downs.%d.3T.%d%d' % (i, k[0], k[1])
-                        P[key] = ops.pack_weight(lv[3].weight, tp, mode=1, round_tf32=False, out=P.get(key))
+                        self._pack(batch, 'downs.%d.3T.%d%d' % (i, k[0], k[1]), lv[3].weight, tp, mode=1)
             for i, lv in enumerate(self.levels_up):
                 if lv[3] is not None:
-                    key = 'ups.%d.3T' % i
-                    P[key] = ops.pack_weight(lv[3].weight, T4, mode=1, transposed_conv=True, round_tf32=False, out=P.get(key))
+                    self._pack(batch, 'ups.%d.3T' % i, lv[3].weight, T4, mode=1, transposed_conv=True)
+            if batch is not None:
+                batch.run()
         self._bwd_version = ver
 
     # ------------------------------------------------------------------------------------------
     profile_wgrads = None
+    _unpack_batch = None            # ops.RepackBatch of the running backward() when COLDDIFF_BATCHED_REPACK is on
+    _dwp_clean = None
 
     def _wgrad(self, src, taps, Cout, grid, dout, wgrad_param, bias_param, *, stride=1, out_map=(1, 1, 0, 0),
                transposed_conv=False, key=None):
         """accumulate the weight (and bias) gradient of one tap-list convolution into reference-layout grads."""
         nt = len(taps)
         direct = (nt == 1 and not transposed_conv)          # 1x1: packed layout == OIHW layout
+        ub = self._unpack_batch
         if direct:
             dwp = wgrad_param
         else:
             dwp = self.buf('dwp.' + key, (nt, Cout, src.C))
-            dwp.zero_()
+            # batched mode: the one-launch unpack at the end of backward() clears what it read, so a buffer is zero-filled
+            # here only when it is new or when the previous backward did not reach its unpack
+            if ub is None or self._dwp_clean.get(key) != dwp.data_ptr():
+                dwp.zero_()
+                if ub is not None:
+                    self._dwp_clean[key] = dwp.data_ptr()
+            if ub is not None:
+                assert key not in self._dwp_seen, "packed-gradient buffer %r used twice in one backward" % key
+                self._dwp_seen.add(key)
         d = ops.make_conv_desc([(src, taps, dwp, False)], dout, grid, stride=stride, Cout=Cout, out_map=out_map)
         bias_ok = bias_param is not None and out_map == (1, 1, 0, 0)
         if self.profile_wgrads is not None:                 # tools/wgrad_shapes.py: time the weight-gradient GEMM alone
@@ -130,7 +140,10 @@ class BackwardMixin:
         else:
             ops.conv_wgrad(d, dout, dwp, bias_param if bias_ok else None, impl=self.conv_impl)
         if not direct:
-            ops.unpack_wgrad(dwp, taps, wgrad_param, transposed_conv=transposed_conv, accumulate=True)
+            if ub is None:
+                ops.unpack_wgrad(dwp, taps, wgrad_param, transposed_conv=transposed_conv, accumulate=True)
+            else:
+                ub.add(dwp, taps, wgrad_param, shape=tuple(wgrad_param.shape), transposed_conv=transposed_conv)
 
     def _block_bwd(self, bs, save, dyv, need_dx=True):
         sv = save[bs.name]
@@ -244,6 +257,12 @@ class BackwardMixin:
         P, G = self._packed, self.G
         dout = dout.contiguous().float()
         B = dout.shape[0]
+        # packed weight gradients: unpacked one by one right after each wgrad, or (COLDDIFF_BATCHED_REPACK) all at once below
+        self._unpack_batch = self._repack_batch('unpack', 'unpack') if self.profile_wgrads is None else None
+        if self._unpack_batch is None or self._dwp_clean is None or getattr(self, '_dwp_pending', False):
+            self._dwp_clean = {}                    # a backward that raised half-way left partial sums behind: refill all
+        self._dwp_pending = self._unpack_batch is not None
+        self._dwp_seen = set()
         self._dcond = self.buf('g.dcond', (B, max(self.sumC, 1)))
         self._dcond.zero_()
         nd, nu = len(self.levels_down), len(self.levels_up)
@@ -311,6 +330,9 @@ class BackwardMixin:
         # ---- time MLP ----
         if unet.time_mlp is not None:
             self._time_bwd(save)
+        if self._unpack_batch is not None:
+            self._unpack_batch.run(accumulate=True, clear_src=True)
+            self._dwp_pending = False
 
     def _time_bwd(self, save):
         sv = save['time']

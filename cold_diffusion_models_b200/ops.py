@@ -59,6 +59,72 @@ def unpack_wgrad(packed, taps, w_grad, transposed_conv=False, accumulate=True):
          int(accumulate), stream())
 
 
+class RepackBatch:
+    """all weight repacks (kind 'pack') or all packed-gradient unpacks (kind 'unpack') of one pass in ONE launch
+    (cd_pack_weight_batched / cd_unpack_wgrad_batched).  add() has the argument meaning of pack_weight() / unpack_wgrad();
+    run() uploads the job table when the set of (source, destination) buffers changed (they are persistent buffers, so
+    normally once) and launches.  The block split mirrors the single-weight entry points: one block per 256 (o, i) rows
+    for Conv2d weights with KH*KW <= 16, an element-strided range otherwise."""
+
+    MAX_STRIDED_BLOCKS = 148 * 2
+
+    def __init__(self, kind):
+        assert kind in ('pack', 'unpack')
+        self.kind = kind
+        self._jobs = []
+        self._key = None
+        self._table = None
+        self._total = 0
+
+    def __len__(self):
+        return len(self._jobs)
+
+    def add(self, src, taps, dst, *, shape, mode=0, transposed_conv=False, round_tf32=False):
+        """shape = the reference-layout weight shape ((O,I,KH,KW), or (I,O,KH,KW) for nn.ConvTranspose2d)"""
+        if transposed_conv:
+            I, O, KH, KW = shape
+        else:
+            O, I, KH, KW = shape
+        assert 1 <= len(taps) <= _lib.CD_MAX_TAPS
+        self._jobs.append((src, dst, O, I, KH, KW, int(transposed_conv), int(mode), tuple((t[0], t[1]) for t in taps), int(round_tf32)))
+
+    def clear(self):
+        self._jobs = []
+
+    def _build(self, device):
+        n = len(self._jobs)
+        arr = (_lib.RepackJob * n)()
+        b0 = 0
+        for j, (src, dst, O, I, KH, KW, tr, mode, taps, rnd) in enumerate(self._jobs):
+            r = arr[j]
+            r.src, r.dst = src.data_ptr(), dst.data_ptr()
+            r.O, r.I, r.KH, r.KW, r.transposed_conv, r.mode, r.ntaps, r.round_tf32 = O, I, KH, KW, tr, mode, len(taps), rnd
+            for t, (ky, kx) in enumerate(taps):
+                r.ky[t], r.kx[t] = ky, kx
+            tiled = (not tr) and KH * KW <= 16 and (self.kind == 'unpack' or mode == 0)
+            if tiled:
+                nb = (O * I + 255) // 256
+            else:
+                nb = min((len(taps) * O * I + 1023) // 1024, self.MAX_STRIDED_BLOCKS)
+            r.block0, r.nblocks = b0, max(nb, 1)
+            b0 += r.nblocks
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._table = raw.to(device)
+        self._total = b0
+
+    def run(self, *, accumulate=True, clear_src=False):
+        if not self._jobs:
+            return
+        key = tuple((j[0].data_ptr(), j[1].data_ptr()) + j[2:] for j in self._jobs)
+        if key != self._key:
+            self._build(self._jobs[0][0].device)
+            self._key = key
+        if self.kind == 'pack':
+            call('cd_pack_weight_batched', ptr(self._table), len(self._jobs), self._total, stream())
+        else:
+            call('cd_unpack_wgrad_batched', ptr(self._table), len(self._jobs), self._total, int(accumulate), int(clear_src), stream())
+
+
 # --------------------------------------------------------------------------------------------
 # NHWC views: (tensor, channel offset, channels).  tensor is [B, H, W, ld] contiguous.
 # --------------------------------------------------------------------------------------------

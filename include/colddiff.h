@@ -103,6 +103,26 @@ int cd_unpack_wgrad(const float* packed, int O, int I, int KH, int KW, int trans
                     const int32_t* host_ky, const int32_t* host_kx, int ntaps, float* w_grad, int accumulate,
                     void* stream);
 
+/* The same two repacks for MANY weights in one launch (one optimizer step repacks ~64 convolution weights and
+ * unpacks ~98 packed weight gradients: as single launches they are launch/latency-bound, ~2 ms of a 61 ms step).
+ * `jobs` is a DEVICE array of njobs descriptors (built once by the caller; pointers are stable across steps);
+ * blocks [block0, block0 + nblocks) of the 256-thread grid of total_blocks work on job j, block0 ascending with j.
+ * nblocks is the caller's choice (any value >= 1 is correct for transposed_conv / mode 1 / KH*KW > 16 jobs, which
+ * stride over the elements; the other jobs need nblocks == ceil(O*I / 256): one 256-row tile per block).
+ * cd_unpack_wgrad_batched with clear_src != 0 also zeroes the packed gradient after reading it, which leaves the
+ * accumulation buffers of cd_conv_wgrad ready for the next backward pass without ~98 fill launches.          */
+typedef struct {
+  const float* src;       /* pack: reference-layout weight;  unpack: packed gradient [tap][O][I]               */
+  float* dst;             /* pack: packed operand;           unpack: reference-layout gradient                 */
+  int32_t O, I, KH, KW;
+  int32_t transposed_conv, mode, ntaps, round_tf32;     /* mode / round_tf32: pack only                       */
+  int32_t ky[CD_MAX_TAPS], kx[CD_MAX_TAPS];
+  int32_t block0, nblocks;
+} CdRepackJob;
+int cd_pack_weight_batched(const CdRepackJob* jobs, int njobs, int total_blocks, void* stream);
+int cd_unpack_wgrad_batched(const CdRepackJob* jobs, int njobs, int total_blocks, int accumulate, int clear_src,
+                            void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * ConvNeXt block front half (DB:145, 140-143/159-162, 111-121/148):
  *   h = dwconv7x7(x) + b_dw + cond[b,:] ;  y = LayerNorm_c(h) * g + beta   (g==NULL: y = h)

@@ -174,6 +174,43 @@ def cd_unpack_wgrad(packed, O, I, KH, KW, transposed_conv, ky, kx, ntaps, w_grad
     return 0
 
 
+class _RepackJob(C.Structure):          # CdRepackJob of include/colddiff.h, declared here independently of the package
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('O', C.c_int32), ('I', C.c_int32), ('KH', C.c_int32), ('KW', C.c_int32),
+                ('transposed_conv', C.c_int32), ('mode', C.c_int32), ('ntaps', C.c_int32), ('round_tf32', C.c_int32),
+                ('ky', C.c_int32 * 16), ('kx', C.c_int32 * 16), ('block0', C.c_int32), ('nblocks', C.c_int32)]
+
+
+def _jobs(jobs, njobs, total_blocks):
+    arr = (_RepackJob * njobs).from_address(_v(jobs))
+    b0 = 0
+    for j in arr:                       # the block ranges must tile [0, total_blocks) in job order
+        assert j.block0 == b0 and j.nblocks >= 1
+        b0 += j.nblocks
+    assert b0 == total_blocks
+    return arr
+
+
+def cd_pack_weight_batched(jobs, njobs, total_blocks, stream):
+    for j in _jobs(jobs, njobs, total_blocks):
+        if not j.transposed_conv and j.mode == 0 and j.KH * j.KW <= 16:
+            assert j.nblocks == (j.O * j.I + 255) // 256
+        rc = cd_pack_weight(j.src, j.O, j.I, j.KH, j.KW, j.transposed_conv, j.mode, list(j.ky), list(j.kx), j.ntaps, j.round_tf32,
+                            j.dst, stream)
+        assert rc == 0
+    return 0
+
+
+def cd_unpack_wgrad_batched(jobs, njobs, total_blocks, accumulate, clear_src, stream):
+    for j in _jobs(jobs, njobs, total_blocks):
+        if not j.transposed_conv and j.KH * j.KW <= 16:
+            assert j.nblocks == (j.O * j.I + 255) // 256
+        rc = cd_unpack_wgrad(j.src, j.O, j.I, j.KH, j.KW, j.transposed_conv, list(j.ky), list(j.kx), j.ntaps, j.dst, accumulate, stream)
+        assert rc == 0
+        if clear_src:
+            _arr(j.src, (j.ntaps * j.O * j.I,), (1,))[:] = 0.0
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GroupNorm, dropout, softmax, resampling, small dense pieces
 # ------------------------------------------------------------------------------------------------------------------

@@ -191,3 +191,52 @@ def test_evaluation_routines_on_the_gpu(unet, tmp_path, monkeypatch):
     assert out['deblurred']['ssim'] == pytest.approx(float(ssim(u(og), u(A0[-1]), data_range=1)), abs=5e-3)   # two TF32 runs
     a, b = torch.rand(3, 3, 40, 40), torch.rand(3, 3, 40, 40)
     assert float(ssim(a.cuda(), b.cuda(), data_range=1)) == pytest.approx(float(ssim(a, b, data_range=1)), abs=1e-5)
+
+
+def test_batched_repack_matches_the_single_launches():
+    """csrc/repack.cu (one launch for all weight repacks / packed-gradient unpacks, COLDDIFF_BATCHED_REPACK; off by default until
+    this test has passed on a B200): bit-exact against the single-weight entry points on a job table that takes every branch,
+    then the same Unet gradients with the switch on and off (float atomics in the weight-gradient kernels: TF32-level tolerance)"""
+    from cold_diffusion_models_b200 import ops, engine
+    from test_repack_batched import _job_set
+    from test_grads_gpu import _grads
+    for kind in ('pack', 'unpack'):
+        res = []
+        for batched in (False, True):
+            gen = torch.Generator().manual_seed(11)
+            batch, bufs = ops.RepackBatch(kind), []
+            for shape, taps, mode, tr, rnd in _job_set(kind):
+                O, I = (shape[1], shape[0]) if tr else (shape[0], shape[1])
+                w = torch.randn(shape, generator=gen).cuda()
+                n, k = (O, I) if mode == 0 else (I, O)
+                packed = torch.randn(len(taps), n, k, generator=gen).cuda()
+                if kind == 'pack':
+                    if batched:
+                        batch.add(w, taps, packed, shape=shape, mode=mode, transposed_conv=tr, round_tf32=rnd)
+                    else:
+                        ops.pack_weight(w, taps, mode=mode, transposed_conv=tr, round_tf32=bool(rnd), out=packed)
+                else:
+                    if batched:
+                        batch.add(packed, taps, w, shape=shape, transposed_conv=tr)
+                    else:
+                        ops.unpack_wgrad(packed, taps, w, transposed_conv=tr, accumulate=True)
+                bufs.append((w, packed))
+            batch.run(accumulate=True, clear_src=False)
+            torch.cuda.synchronize()
+            res.append(bufs)
+        for j, ((w0, p0), (w1, p1)) in enumerate(zip(*res)):
+            assert torch.equal(w0, w1) and torch.equal(p0, p1), (kind, j)
+    g = load('unet_small')
+    sd = {k[3:]: v for k, v in g.items() if k.startswith('sd:')}
+    grads = []
+    try:
+        for batched in (False, True):
+            engine.batched_repack(batched)
+            u = make_unet(32, (1, 2), 3, sd)
+            for _ in range(2):                                  # the second pass relies on the buffers the first unpack cleared
+                _grads(u, g['x'], g['t'], g['target'], 1)
+            grads.append({n: p.grad.detach().clone() for n, p in u.named_parameters()})
+    finally:
+        engine.batched_repack(False)
+    for n in grads[0]:
+        assert rel(grads[1][n], grads[0][n]) < 2e-3, n

@@ -14,5 +14,9 @@ TMO=300 step bench               python bench.py
 TMO=300 step eager_comparator    python bench.py --impl reference --reference-device cuda --steps 3 --warmup 2
 # wgrad with the bias column sums folded in (one extra N = 32 MMA per tile) against the separate cd_colsum launches
 TMO=200 step op_profile_default  python tools/op_profile.py
-grep -h '"metric"' $out/bench.log $out/eager_comparator.log > $out/bench_lines.json 2>/dev/null
+# one-launch weight repacks (csrc/repack.cu): same bench and op profile with the switch on; flip the default in engine.batched_repack
+# when the late GPU test (gpu_tests above: test_batched_repack_matches_the_single_launches) is green and this bench is not slower
+TMO=300 step bench_batched_repack      env COLDDIFF_BATCHED_REPACK=1 python bench.py
+TMO=200 step op_profile_batched_repack env COLDDIFF_BATCHED_REPACK=1 python tools/op_profile.py
+grep -h '"metric"' $out/bench.log $out/eager_comparator.log $out/bench_batched_repack.log > $out/bench_lines.json 2>/dev/null
 cat $out/summary.txt
