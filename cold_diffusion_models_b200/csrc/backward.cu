@@ -497,6 +497,8 @@ extern "C" int cd_colsum_batched(const float* x, int ld, int B, int64_t rows, in
 
 extern "C" int cd_linattn_bwd_small(const float* dweff, const float* ctx, const float* ksum, const float* w_out,
                                     int B, int dim, float scale, float* dw_out, float* dctxn, float* rowdot, void* stream) {
+  if (cd_linattn_staged_enabled(w_out, dweff))
+    return cd_linattn_bwd_small_staged(dweff, ctx, ksum, w_out, B, dim, scale, dw_out, dctxn, rowdot, static_cast<cudaStream_t>(stream));
   attn_bwd_small_kernel<<<dim3(4, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(dweff, ctx, ksum, w_out, dim, scale, dw_out, dctxn, rowdot);
   CD_LAUNCH_CHECK();
   return 0;

@@ -24,6 +24,13 @@ void cd_set_error(const char* fmt, ...);
 
 static inline int cd_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// linattn_small.cu: shared-memory-staged variants of the two per-(batch element, head) LinearAttention kernels (opt-in)
+int cd_linattn_staged_enabled(const void* a, const void* b);
+int cd_linattn_weff_staged(const float* ctx, const float* ksum, const float* w_out, int B, int dim, float scale,
+                           int round_tf32, float* weff, cudaStream_t st);
+int cd_linattn_bwd_small_staged(const float* dweff, const float* ctx, const float* ksum, const float* w_out, int B, int dim,
+                                float scale, float* dw_out, float* dctxn, float* rowdot, cudaStream_t st);
+
 #ifdef __CUDACC__
 // ---- small device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float cd_gelu(float x) {           // exact erf GELU == nn.GELU()

@@ -841,6 +841,8 @@ extern "C" int cd_linattn_context(const float* qkv, int ld, int B, int n, float*
 
 extern "C" int cd_linattn_weff(const float* ctx, const float* ksum, const float* w_out, int B, int dim, float scale,
                                int round_tf32, float* weff, void* stream) {
+  if (cd_linattn_staged_enabled(w_out, nullptr))
+    return cd_linattn_weff_staged(ctx, ksum, w_out, B, dim, scale, round_tf32, weff, static_cast<cudaStream_t>(stream));
   weff_kernel<<<dim3(4, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx, ksum, w_out, dim, scale, round_tf32, weff);
   CD_LAUNCH_CHECK();
   return 0;

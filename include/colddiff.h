@@ -181,6 +181,9 @@ int cd_wgrad_tc_set_mode(int mode);
 int cd_wgrad_tc_set_split(int policy, int over_clk);
 /* opt-in (default 0, not yet validated on a B200): fold the bias gradient (column sums of dY) into the tcgen05 weight gradient */
 int cd_wgrad_tc_set_bias_fusion(int enable);
+/* opt-in (default 0, not yet validated on a B200): shared-memory-staged kernels behind cd_linattn_weff / cd_linattn_bwd_small
+ * (csrc/linattn_small.cu; same arithmetic order as the default kernels) */
+int cd_linattn_set_staged(int enable);
 /* diagnostic switch: 1 (default) = TFLOAT32 tensor maps (TMA rounds fp32->tf32 RN on load) */
 int cd_conv_tc_set_tf32_maps(int enable);
 /* SM-pair (tcgen05 cta_group::2, 256 pixels x 256 channels per pair) variant of the tap-list convolution:

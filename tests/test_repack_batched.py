@@ -30,7 +30,7 @@ def load(name):
 @pytest.fixture(scope='module', params=['ascending', 'descending'])
 def cpulib(request):
     import build
-    lib = C.CDLL(build.build(['repack.cu']))
+    lib = C.CDLL(build.build_all())          # SIMT_CPU_ASAN=1 applies (tests/simt_cpu/build.py)
     lib.simt_set_reverse_order(int(request.param == 'descending'))
     yield lib
     lib.simt_set_reverse_order(0)

@@ -189,3 +189,39 @@ def test_time_mlp2_source_both_paths(cpulib, with_temb, B, dim, hid, tdim, act, 
     outs = ['cond'] + (['temb'] if with_temb else [])
     for got, want in both(cpulib, 'cd_time_mlp2_fwd', args, outs):
         assert close(got, want, 2e-4)            # sin / cos of arguments up to 999 in fp32, then three dense layers
+
+
+@pytest.mark.parametrize('B,dim', [(2, 64), (3, 512), (1, 40), (2, 100)])
+def test_linattn_staged_kernels_equal_the_default_ones(cpulib, B, dim):
+    """csrc/linattn_small.cu (cd_linattn_set_staged): the shared-memory-staged cd_linattn_weff / cd_linattn_bwd_small keep the
+    arithmetic order of the default kernels -> bit-identical results (the CPU execution runs the blocks, hence the float atomics
+    into dW_out, in the same order for both); both also agree with the numpy statement"""
+    g = torch.Generator().manual_seed(B * 7 + dim)
+    r = lambda *s: torch.randn(*s, generator=g)
+    ctx, ksum, w_out, dweff = r(B, 4, 32, 32), 1.0 + torch.rand(B, 128, generator=g) * 30, r(dim, 128) / 11, r(B, dim, 128)
+    res = {}
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for staged in (0, 1):
+            assert cpulib.cd_linattn_set_staged(staged) == 0
+            for rnd in (0, 1):
+                weff = torch.full((B, dim, 128), 7.0)
+                assert cpulib.cd_linattn_weff(P(ctx), P(ksum), P(w_out), B, dim, C.c_float(0.17), rnd, P(weff), C.c_void_p(0)) == 0
+                res[('weff', rnd, staged, order)] = weff
+            dw_out, dctxn, rowdot = 0.5 * torch.ones(dim, 128), torch.full((B, 4, 32, 32), 7.0), torch.full((B, 128), 7.0)
+            assert cpulib.cd_linattn_bwd_small(P(dweff), P(ctx), P(ksum), P(w_out), B, dim, C.c_float(0.17), P(dw_out), P(dctxn), P(rowdot),
+                                               C.c_void_p(0)) == 0
+            res[('bwd', 0, staged, order)] = torch.cat([dw_out.reshape(-1), dctxn.reshape(-1), rowdot.reshape(-1)])
+    cpulib.cd_linattn_set_staged(0)
+    cpulib.simt_set_reverse_order(0)
+    for key in [('weff', 0), ('weff', 1), ('bwd', 0)]:
+        base = res[key + (0, 0)]
+        for staged in (0, 1):
+            for order in (0, 1):
+                assert torch.equal(res[key + (staged, order)], base), (key, staged, order)
+    weff = torch.zeros(B, dim, 128)
+    assert E.cd_linattn_weff(P(ctx), P(ksum), P(w_out), B, dim, C.c_float(0.17), 0, P(weff), None) == 0
+    assert close(res[('weff', 0, 1, 0)], weff, 1e-5)
+    dw_out, dctxn, rowdot = 0.5 * torch.ones(dim, 128), torch.zeros(B, 4, 32, 32), torch.zeros(B, 128)
+    assert E.cd_linattn_bwd_small(P(dweff), P(ctx), P(ksum), P(w_out), B, dim, C.c_float(0.17), P(dw_out), P(dctxn), P(rowdot), None) == 0
+    assert close(res[('bwd', 0, 1, 0)], torch.cat([dw_out.reshape(-1), dctxn.reshape(-1), rowdot.reshape(-1)]), 1e-4)

@@ -240,3 +240,32 @@ def test_batched_repack_matches_the_single_launches():
         engine.batched_repack(False)
     for n in grads[0]:
         assert rel(grads[1][n], grads[0][n]) < 2e-3, n
+
+
+def test_linattn_staged_kernels_match_the_default_ones():
+    """csrc/linattn_small.cu (cd_linattn_set_staged / COLDDIFF_LINATTN_STAGED; off by default until this test has passed on a
+    B200): same arithmetic order as the default kernels, so weff / dctxn / rowdot are bit-identical and dW_out (float atomics over
+    the batch) agrees to rounding"""
+    import ctypes as C
+    from cold_diffusion_models_b200._lib import lib, ptr, stream, _check
+    gen = torch.Generator().manual_seed(3)
+    for B, dim in ((32, 64), (8, 512), (3, 100)):
+        ctx, ksum = torch.randn(B, 4, 32, 32, generator=gen).cuda(), (1 + 30 * torch.rand(B, 128, generator=gen)).cuda()
+        w_out, dweff = (torch.randn(dim, 128, generator=gen) / 11).cuda(), torch.randn(B, dim, 128, generator=gen).cuda()
+        res = []
+        try:
+            for staged in (0, 1):
+                lib.cd_linattn_set_staged(staged)
+                weff = [torch.full((B, dim, 128), 7.0).cuda() for _ in range(2)]
+                for rnd in (0, 1):
+                    _check(lib.cd_linattn_weff(ptr(ctx), ptr(ksum), ptr(w_out), B, dim, C.c_float(0.17), rnd, ptr(weff[rnd]), stream()), 'weff')
+                dw_out, dctxn, rowdot = torch.zeros(dim, 128).cuda(), torch.full((B, 4, 32, 32), 7.0).cuda(), torch.full((B, 128), 7.0).cuda()
+                _check(lib.cd_linattn_bwd_small(ptr(dweff), ptr(ctx), ptr(ksum), ptr(w_out), B, dim, C.c_float(0.17), ptr(dw_out), ptr(dctxn),
+                                                ptr(rowdot), stream()), 'bwd_small')
+                torch.cuda.synchronize()
+                res.append((weff[0], weff[1], dctxn, rowdot, dw_out))
+        finally:
+            lib.cd_linattn_set_staged(0)
+        for i in range(4):
+            assert torch.equal(res[0][i], res[1][i]), (B, dim, i)
+        assert rel(res[1][4], res[0][4]) < 1e-5, (B, dim)

@@ -18,5 +18,8 @@ TMO=200 step op_profile_default  python tools/op_profile.py
 # when the late GPU test (gpu_tests above: test_batched_repack_matches_the_single_launches) is green and this bench is not slower
 TMO=300 step bench_batched_repack      env COLDDIFF_BATCHED_REPACK=1 python bench.py
 TMO=200 step op_profile_batched_repack env COLDDIFF_BATCHED_REPACK=1 python tools/op_profile.py
-grep -h '"metric"' $out/bench.log $out/eager_comparator.log $out/bench_batched_repack.log > $out/bench_lines.json 2>/dev/null
+# shared-memory-staged per-(batch element, head) LinearAttention kernels (csrc/linattn_small.cu), alone and with the batched repacks
+TMO=200 step op_profile_linattn_staged env COLDDIFF_LINATTN_STAGED=1 python tools/op_profile.py
+TMO=300 step bench_all_switches        env COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 python bench.py
+grep -h '"metric"' $out/bench.log $out/eager_comparator.log $out/bench_batched_repack.log $out/bench_all_switches.log > $out/bench_lines.json 2>/dev/null
 cat $out/summary.txt
