@@ -296,6 +296,36 @@ def main():
                 others['C5_afhq_denoise_ddim_sample'] = {"ms_per_reverse_step": ms5, "images_per_sec_200_step_sample": B / (ms5 * 200 / 1e3), "batch": B}
         except Exception as e:  # context only: never let it break the headline line
             others['error'] = repr(e)[:200]
+        try:
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                # config 4: CelebA-128 resolution diffusion (avg-pool pixelate D), x0_step_down, batch 32, same Unet.  BASELINE's
+                # time_steps=200 is not constructible (RS:389-414: `Incremental*` shrinks by one pixel per step, <= 127 steps at
+                # 128x128), so T = 100 here
+                from cold_diffusion_models_b200.resolution_diffusion_pytorch import GaussianDiffusion as RSGD
+                T4 = 100
+                g4 = RSGD(trainer.ema_model.denoise_fn, image_size=128, device_of_kernel='cuda', channels=3, timesteps=T4, loss_type='l1',
+                          resolution_routine='Incremental_area', train_routine='Final', sampling_routine='x0_step_down').to(dev)
+                im4 = g4.opt(resident[0])
+                t4 = [T4]
+
+                def rev4(s_):
+                    nonlocal im4
+                    st = torch.full((B,), t4[0] - 1, dtype=torch.long, device=dev)
+                    im4 = g4._reverse_step(im4, g4.denoise_fn(im4, st), t4[0])
+                    t4[0] -= 1
+                for s_ in range(2):
+                    rev4(s_)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for s_ in range(5):
+                    rev4(s_)
+                e1.record(); torch.cuda.synchronize()
+                ms4 = e0.elapsed_time(e1) / 5
+                others['C4_celeba_resolution_sample'] = {"ms_per_reverse_step": ms4, "images_per_sec_100_step_sample": B / (ms4 * T4 / 1e3), "batch": B,
+                                                         "routine": "Incremental_area, T=100 (200 steps are not constructible at 128x128)"}
+        except Exception as e:
+            others['error_C4'] = repr(e)[:200]
 
     # ---- roofline of the dominant kernel (tcgen05 tap-list convolution), CUDA events around every launch --------
     peaks, peak_kind = read_peaks()
