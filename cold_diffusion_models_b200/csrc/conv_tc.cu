@@ -16,6 +16,7 @@
 //              128-byte row stores; 4 warps per TMEM lane quarter, each taking every 4th column chunk
 // so the epilogue of tile i overlaps the mainloop of tile i+1.
 #include "tc_common.cuh"
+#include "conv_epilogue.cuh"
 
 namespace {
 
@@ -59,7 +60,8 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "}\n" :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <int BN, int STAGES>
+// STG: line-coalesced epilogue through a per-warp shared-memory tile (conv_epilogue.cuh; opt-in, fewer mainloop stages)
+template <int BN, int STAGES, bool STG = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -80,6 +82,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier block is 256 bytes");
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * kStageBytes + 256);     // STG: kEpiWarps x 32 x 36 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,6 +195,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       for (int c = cg * 32; c < BN; c += 32 * (kEpiWarps / 4)) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
+        if constexpr (STG) {
+          if (co0 + c + 32 <= p.Cout) {               // warp-uniform: full 32-column chunk
+            cd_epilogue_staged32(r, epi_stage + (warp - 2) * kEpiStageFloats, lane, pix, valid, co0 + c, p);
+            continue;
+          }
+        }
         if (valid && co0 + c < p.Cout) {
           const int nvalid = min(32, p.Cout - (co0 + c));
           if (nvalid == 32 && p.vec8) {
@@ -280,16 +290,17 @@ int g_num_sms = 0;
 int g_tf32_map_dtype = 1;   // 1: TFLOAT32 tensor maps -- the TMA unit rounds fp32->tf32 (RN) on load (measured: profiles/tf32_probe_r01.txt); 0: FLOAT32 (MMA truncates)
 
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool STG = false>
 int launch(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
-  const size_t smem = size_t(STAGES) * (kABytes + BN * 128) + 1024 + 256;
+  constexpr size_t smem = size_t(STAGES) * (kABytes + BN * 128) + 1024 + 256 + (STG ? sizeof(float) * kEpiWarps * kEpiStageFloats : 0);
+  static_assert(smem <= 232448, "dynamic shared memory of one CTA (227 KB)");
   static bool attr_done = false;
   if (!attr_done) {
-    CD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_tc_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  conv_tc_kernel<BN, STAGES, STG><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   CD_LAUNCH_CHECK();
   return 0;
 }
@@ -301,6 +312,11 @@ extern "C" int cd_conv_tc_set_tf32_maps(int enable) { g_tf32_map_dtype = enable 
 int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st);   // conv_tc2.cu: SM-pair (cta_group::2) variant
 static int g_use_2cta = 1;
 extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   // 0 off, 1 where the cost model prefers it, 2 wherever eligible
+// line-coalesced epilogue (conv_epilogue.cuh): 0 = off (default: not validated on a B200 yet), 1 = for the short-K launches that
+// are bound by their output stores (at most kStagedMaxKIters 32-channel K chunks per tile), 2 = for every launch (tests)
+static int g_epi_staged = 0;
+constexpr int kStagedMaxKIters = 16;
+extern "C" int cd_conv_tc_set_staged_epilogue(int mode) { g_epi_staged = mode; return 0; }
 
 // Tile-shape choice.  Cost model: waves over the SMs x columns per tile / relative MMA issue rate of that tile shape.  The
 // rates are the measured TFLOP/s of the long-K convolutions of the config-3 network (profiles/conv_shapes_2cta_r01.txt):
@@ -340,7 +356,14 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   CD_REQUIRE(p.TW * d->sx <= 256 && p.TH * d->sy <= 256, "conv_tc: strided box too large");
   p.tiles_x = d->Wg / p.TW; p.tiles_y = d->Hg / p.TH; p.tiles_n = cd_cdiv(d->B, p.TN);
   int BN = (d->Cout % 256 == 0) ? 256 : (d->Cout > 64 ? 128 : 64);
-  if (BN == 256) {
+  int kiters_host = 0;
+  for (int s = 0; s < d->nsrc; ++s) kiters_host += d->s[s].ntaps * (d->s[s].C / kChunkK);
+  const bool staged = g_epi_staged == 2 || (g_epi_staged == 1 && kiters_host <= kStagedMaxKIters);
+  if (BN == 256 && staged) {
+    // short K: the narrower tile only when it saves whole waves (same rule as below), never the SM-pair kernel
+    const long long mt = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
+    if (tc_cost(mt, d->Cout, 128, false, g_num_sms) < tc_cost(mt, d->Cout, 256, false, g_num_sms)) BN = 128;
+  } else if (BN == 256) {
     // small spatial sizes (16^2, 32^2) give few M tiles: take the narrower N tile only when it saves whole waves
     const long long mt = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
     double best = tc_cost(mt, d->Cout, 256, false, g_num_sms);
@@ -398,6 +421,11 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       CD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B%d) failed: %d", s, (int)r);
     }
+  }
+  if (staged) {          // 72 KB of epilogue staging: 3 / 4 / 5 mainloop stages instead of 4 / 6 / 8
+    if (BN == 256) return launch<256, 3, true>(maps, p, st);
+    if (BN == 128) return launch<128, 4, true>(maps, p, st);
+    return launch<64, 5, true>(maps, p, st);
   }
   if (BN == 256) return launch<256, 4>(maps, p, st);
   if (BN == 128) return launch<128, 6>(maps, p, st);

@@ -141,10 +141,11 @@ def build(units, tag=None, extra_flags=(), extra_sources=()):
     os.makedirs(OUT, exist_ok=True)
     if 'api.cu' not in units:
         units = ['api.cu'] + list(units)
-    tag = tag or '_'.join(os.path.splitext(u)[0] for u in units)
+    tag = tag or '_'.join(os.path.splitext(os.path.basename(u))[0] for u in units)
     texts = {}
     for name in list(units) + [f for f in os.listdir(CSRC) if f.endswith('.cuh')]:
-        texts[name] = rewrite(open(os.path.join(CSRC, name)).read())
+        # a unit given as an absolute path (test-only kernels next to this file) keeps its base name in the build directory
+        texts[os.path.basename(name)] = rewrite(open(os.path.join(CSRC, name)).read())
     runtime = ''.join(open(f).read() for f in [os.path.join(HERE, 'simt.cpp'), os.path.join(HERE, 'shim', 'cuda_runtime.h')] + list(extra_sources))
     digest = hashlib.sha1(('\0'.join(k + v for k, v in sorted(texts.items())) + runtime + ' '.join(extra_flags)).encode()).hexdigest()[:16]
     lib = os.path.join(OUT, 'lib%s_%s.so' % (tag, digest))

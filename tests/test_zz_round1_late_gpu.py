@@ -269,3 +269,37 @@ def test_linattn_staged_kernels_match_the_default_ones():
         for i in range(4):
             assert torch.equal(res[0][i], res[1][i]), (B, dim, i)
         assert rel(res[1][4], res[0][4]) < 1e-5, (B, dim)
+
+
+def test_conv_staged_epilogue_matches_the_row_epilogue():
+    """csrc/conv_epilogue.cuh (cd_conv_tc_set_staged_epilogue; off by default until this test has passed on a B200): every tcgen05
+    convolution case of tests/test_conv_gpu.py again with the line-coalesced epilogue forced on all launches (mode 2: 3/4/5-stage
+    kernels with the per-warp staging tiles), then bit-exact against the row epilogue on the store-bound 1x1 shapes in mode 1"""
+    import test_conv_gpu as T
+    from cold_diffusion_models_b200 import ops
+    from cold_diffusion_models_b200._lib import lib
+    try:
+        lib.cd_conv_tc_set_staged_epilogue(2)
+        for case in T.CASES:
+            T.test_conv_stride1(ops, case, 'tc')
+        T.test_conv_two_sources_channel_slices(ops, 'tc')
+        T.test_conv_4x4_stride2_and_transpose(ops, 'tc')
+        T.test_conv_per_batch_weights(ops, 'tc')
+        gen = torch.Generator().manual_seed(9)
+        for (B, Ci, Co, H, W) in ((2, 64, 384, 64, 64), (1, 128, 384, 32, 32), (3, 256, 64, 16, 16), (2, 512, 384, 16, 16)):
+            x = torch.randn(B, H, W, Ci, generator=gen).cuda()
+            w = (torch.randn(Co, Ci, 1, 1, generator=gen) / Ci ** 0.5).cuda()
+            b, r = torch.randn(Co, generator=gen).cuda(), torch.randn(B, H, W, Co, generator=gen).cuda()
+            taps = ops.taps_conv(1, 0)
+            pw = ops.pack_weight(w, taps, round_tf32=False)
+            outs = []
+            for mode in (0, 1):
+                lib.cd_conv_tc_set_staged_epilogue(mode)
+                out, pre = torch.full((B, H, W, Co), 7.0, device='cuda'), torch.full((B, H, W, Co), 7.0, device='cuda')
+                d = ops.make_conv_desc([(ops.View(x), taps, pw, False)], ops.View(out), (B, H, W), Cout=Co, bias=b, resid=ops.View(r),
+                                       act=ops.ACT_GELU, out2=ops.View(pre), round_tf32=True)
+                T.run_conv(ops, d, 'tc')
+                outs.append((out, pre))
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (B, Ci, Co, H, W)
+    finally:
+        lib.cd_conv_tc_set_staged_epilogue(0)

@@ -21,5 +21,9 @@ TMO=200 step op_profile_batched_repack env COLDDIFF_BATCHED_REPACK=1 python tool
 # shared-memory-staged per-(batch element, head) LinearAttention kernels (csrc/linattn_small.cu), alone and with the batched repacks
 TMO=200 step op_profile_linattn_staged env COLDDIFF_LINATTN_STAGED=1 python tools/op_profile.py
 TMO=300 step bench_all_switches        env COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 python bench.py
-grep -h '"metric"' $out/bench.log $out/eager_comparator.log $out/bench_batched_repack.log $out/bench_all_switches.log > $out/bench_lines.json 2>/dev/null
+# line-coalesced epilogue of the tcgen05 convolution (csrc/conv_epilogue.cuh): per-shape table rows / mode 1 / mode 2, then the bench
+TMO=300 step conv_shapes_epilogue      python tools/conv_shapes_epilogue.py
+TMO=300 step bench_staged_epilogue     env COLDDIFF_CONV_STAGED_EPILOGUE=1 python bench.py
+TMO=300 step bench_everything_on       env COLDDIFF_CONV_STAGED_EPILOGUE=1 COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 python bench.py
+grep -h '"metric"' $out/bench.log $out/eager_comparator.log $out/bench_batched_repack.log $out/bench_all_switches.log $out/bench_staged_epilogue.log $out/bench_everything_on.log > $out/bench_lines.json 2>/dev/null
 cat $out/summary.txt
