@@ -272,6 +272,23 @@ def test_linattn_staged_kernels_match_the_default_ones():
 
 
 def test_conv_staged_epilogue_matches_the_row_epilogue():
+    """runs _conv_staged_epilogue_body in a child process with a time limit: the kernel variant it enables has never run on a
+    B200, and a tcgen05 / mbarrier pipeline that went wrong would spin instead of failing -- that must not take the session's
+    CUDA context (and the tests after it) with it"""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]; import test_zz_round1_late_gpu as t; t._conv_staged_epilogue_body(); print('STAGED_OK')"
+            % (os.path.dirname(here), os.path.join(os.path.dirname(here), 'oracle'), here))
+    try:
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    except subprocess.TimeoutExpired as e:
+        pytest.fail('staged-epilogue child process hung (killed after 600 s): %s' % str(e.stdout)[-500:])
+    assert r.returncode == 0 and 'STAGED_OK' in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+def _conv_staged_epilogue_body():
     """csrc/conv_epilogue.cuh (cd_conv_tc_set_staged_epilogue; off by default until this test has passed on a B200): every tcgen05
     convolution case of tests/test_conv_gpu.py again with the line-coalesced epilogue forced on all launches (mode 2: 3/4/5-stage
     kernels with the per-warp staging tiles), then bit-exact against the row epilogue on the store-bound 1x1 shapes in mode 1"""
