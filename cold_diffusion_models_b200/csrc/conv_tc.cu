@@ -422,10 +422,10 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
       CD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B%d) failed: %d", s, (int)r);
     }
   }
-  if (staged) {          // 72 KB of epilogue staging: 3 / 4 / 5 mainloop stages instead of 4 / 6 / 8
+  if (staged) {          // 72 KB of epilogue staging: 3 / 4 / 6 mainloop stages instead of 4 / 6 / 8
     if (BN == 256) return launch<256, 3, true>(maps, p, st);
     if (BN == 128) return launch<128, 4, true>(maps, p, st);
-    return launch<64, 5, true>(maps, p, st);
+    return launch<64, 6, true>(maps, p, st);
   }
   if (BN == 256) return launch<256, 4>(maps, p, st);
   if (BN == 128) return launch<128, 6>(maps, p, st);

@@ -290,7 +290,7 @@ def test_conv_staged_epilogue_matches_the_row_epilogue():
 
 def _conv_staged_epilogue_body():
     """csrc/conv_epilogue.cuh (cd_conv_tc_set_staged_epilogue; off by default until this test has passed on a B200): every tcgen05
-    convolution case of tests/test_conv_gpu.py again with the line-coalesced epilogue forced on all launches (mode 2: 3/4/5-stage
+    convolution case of tests/test_conv_gpu.py again with the line-coalesced epilogue forced on all launches (mode 2: 3/4/6-stage
     kernels with the per-warp staging tiles), then bit-exact against the row epilogue on the store-bound 1x1 shapes in mode 1"""
     import test_conv_gpu as T
     from cold_diffusion_models_b200 import ops

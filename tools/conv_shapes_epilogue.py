@@ -1,6 +1,6 @@
 """Per-launch time of every tensor-core convolution of one Unet forward (config 3 network), grouped by GEMM shape, with the row
 epilogue (default) and the line-coalesced epilogue of csrc/conv_epilogue.cuh side by side: mode 1 = only launches with <= 16 K
-chunks per tile (the store-bound 1x1 projections), mode 2 = every launch (3/4/5 mainloop stages instead of 4/6/8).
+chunks per tile (the store-bound 1x1 projections), mode 2 = every launch (3/4/6 mainloop stages instead of 4/6/8).
 Usage: python tools/conv_shapes_epilogue.py [batch]"""
 import sys, io, contextlib, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
