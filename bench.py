@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sample-steps', type=int, default=10, help='reverse steps timed for the sampling half of the metric')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-autotune', action='store_true', help='keep every opt-in kernel variant off (cold_diffusion_models_b200.tuning)')
     ap.add_argument('--reference-device', default='cpu', choices=['cpu', 'cuda'],
                     help="--impl reference only: 'cpu' (the contract) or 'cuda' = the same eager-PyTorch restatement on the GPU (informational)")
     args = ap.parse_args()
@@ -196,6 +197,23 @@ def main():
                               results_folder='/tmp/colddiff_bench_results', dataset='synthetic')
     B, A = C3['batch'], C3['accum']
     img_per_step = B * A
+
+    # ---- guarded start-up selection of the opt-in kernel variants (cold_diffusion_models_b200/tuning.py): rank 0 lets a child
+    # process check each variant against the default kernels on this very network and batch and time it; only variants that
+    # reproduce the default results and are faster get switched on, in every rank.  They stay on for the headline measurements
+    # (train step, e2e, sampling, roofline) and are switched off again around the other configs, whose shapes the child did not see.
+    from cold_diffusion_models_b200 import tuning
+    tuned = {'accepted': {}, 'report': {'skipped': True}}
+    if not args.no_autotune:
+        if rank == 0:
+            tuned = tuning.autotune(dim=C3['dim'], dim_mults=C3['dim_mults'], channels=C3['channels'], image_size=C3['image_size'],
+                                    batch=B, device=local, timeout=300)
+        if world > 1:
+            box = [tuned]
+            dist.broadcast_object_list(box, src=0)
+            tuned = box[0]
+            if rank != 0:
+                tuning.apply(tuned['accepted'])
 
     # distinct batches so consecutive steps never re-read the same inputs; activations (>3 GB/step) exceed the 126 MB L2
     g = torch.Generator().manual_seed(1234 + rank)
@@ -272,6 +290,7 @@ def main():
 
     # ---- the other BASELINE configs that fit one GPU, as context (rank 0 only; not the headline, bounded to a few steps) ----
     others = {}
+    tuning.apply(tuning.DEFAULTS)             # the other configs run the default kernels (see the autotune comment above)
     if rank == 0:
         try:
             with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
@@ -354,6 +373,8 @@ def main():
         except Exception as e:
             others['error_C4'] = repr(e)[:200]
 
+    tuning.apply(dict(tuning.DEFAULTS, **tuned['accepted']))
+
     # ---- roofline of the dominant kernel (tcgen05 tap-list convolution), CUDA events around every launch --------
     peaks, peak_kind = read_peaks()
     roof = None
@@ -406,7 +427,17 @@ def main():
             "clocks": sampler.summary() if sampler else None,
             "train_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
             "other_configs": others,
+            "tuning": {"accepted": tuned['accepted'],
+                       "report": {k: v for k, v in tuned['report'].items() if k in ('default_ms', 'best_ms', 'noise', 'tolerance', 'seconds', 'error',
+                                                                                    'error_after', 'skipped', 'complete', 'child_exit', 'stderr_tail')},
+                       "candidates": [{k: c.get(k) for k in ('name', 'ms', 'err_output', 'err_grad', 'accepted', 'rejected')}
+                                      for c in tuned['report'].get('candidates', [])],
+                       "how": "cold_diffusion_models_b200/tuning.py: a child process checks each opt-in kernel variant against the default "
+                              "kernels (output + every gradient of one micro-step of this network and batch) and times it; accepted = same "
+                              "results and faster.  other_configs run the default kernels."},
         }
+        if roof is not None and tuned['accepted'].get('conv_staged_epilogue'):
+            roof['traffic_note'] = 'traffic comes from the round-1 ncu capture of the row-epilogue kernels'
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

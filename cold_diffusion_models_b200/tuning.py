@@ -1,0 +1,216 @@
+"""Guarded start-up selection of the opt-in kernel variants (`autotune()`).
+
+Some kernel variants of libcolddiff are written and checked from source on the CPU but ship OFF because they have not been
+validated on a B200 (NOTES.md, "Code that exists but has not run on a B200 yet"): the line-coalesced epilogue of the tcgen05
+convolution (`cd_conv_tc_set_staged_epilogue`), the shared-memory-staged LinearAttention kernels (`cd_linattn_set_staged`) and the
+one-launch weight repacks (`engine.batched_repack`).  `autotune()` decides about them the way a BLAS library picks kernels at
+start-up, but without trusting them: a CHILD process (so that a faulting or spinning kernel can neither poison this process'
+CUDA context nor hang it -- the child is killed after `timeout` seconds) builds the network the caller is about to run, executes
+one training micro-step (p_losses forward + backward) per candidate, and a candidate is accepted only if
+
+  * the network output and EVERY parameter gradient agree with the default kernels' to within a small multiple of the
+    run-to-run noise of the default kernels themselves (float atomics in the LinearAttention context and the weight-gradient
+    split-K make two default runs differ in the last bits), and
+  * the step is measurably faster than the best accepted configuration so far.
+
+The parent applies the accepted switches to its own library instance and returns the child's report; if the child fails, hangs,
+or finds nothing faster, every switch stays at its default.  Nothing here touches the arithmetic: every candidate computes the
+same sums in the same order as the default kernel it replaces (see the kernels' headers).
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+
+# (name, {switch: value}) in the order they are tried; each is tried on top of what has been accepted so far
+CANDIDATES = [
+    ('conv_staged_epilogue_short_k', {'conv_staged_epilogue': 1}),
+    ('conv_staged_epilogue_all', {'conv_staged_epilogue': 2}),
+    ('linattn_staged', {'linattn_staged': 1}),
+    ('batched_repack', {'batched_repack': 1}),
+]
+DEFAULTS = {'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0}
+
+
+def apply(settings):
+    """set the library / engine switches named in `settings` (missing keys: unchanged)"""
+    from . import _lib, engine
+    if 'conv_staged_epilogue' in settings:
+        _lib.lib.cd_conv_tc_set_staged_epilogue(int(settings['conv_staged_epilogue']))
+    if 'linattn_staged' in settings:
+        _lib.lib.cd_linattn_set_staged(int(settings['linattn_staged']))
+    if 'batched_repack' in settings:
+        engine.batched_repack(bool(settings['batched_repack']))
+
+
+def autotune(dim=64, dim_mults=(1, 2, 4, 8), channels=3, image_size=128, batch=32, device=0, timeout=300, steps=3, verbose=False):
+    """-> {'accepted': {switch: value}, 'report': {...}}; the accepted switches are applied to this process.  See the module text."""
+    cmd = [sys.executable, '-m', 'cold_diffusion_models_b200.tuning', '--child', json.dumps(dict(
+        dim=dim, dim_mults=list(dim_mults), channels=channels, image_size=image_size, batch=batch, device=device, steps=steps))]
+    env = dict(os.environ)
+    env['PYTHONPATH'] = ROOT + os.pathsep + env.get('PYTHONPATH', '')
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'GROUP_RANK', 'LOCAL_WORLD_SIZE', 'TORCHELASTIC_RUN_ID',
+              'COLDDIFF_CONV_STAGED_EPILOGUE', 'COLDDIFF_LINATTN_STAGED', 'COLDDIFF_BATCHED_REPACK'):
+        env.pop(k, None)                       # the child is a plain single-GPU process starting from the library defaults
+    t0 = time.time()
+    report = None
+    def last_report(text):
+        """the child prints a cumulative report after every candidate: the last complete one counts (what was accepted BEFORE a
+        candidate that crashed or hung the child has been validated)"""
+        rep = None
+        if isinstance(text, bytes):
+            text = text.decode(errors='replace')
+        for line in (text or '').splitlines():
+            if line.startswith('AUTOTUNE_REPORT '):
+                try:
+                    rep = json.loads(line[len('AUTOTUNE_REPORT '):])
+                except ValueError:
+                    pass
+        return rep
+
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        report = last_report(r.stdout)
+        if report is None:
+            report = {'error': 'child exited %d without a report' % r.returncode, 'stderr_tail': r.stderr[-600:]}
+        elif r.returncode != 0:
+            report['child_exit'] = r.returncode
+    except subprocess.TimeoutExpired as e:
+        report = last_report(e.stdout) or {}
+        report['error_after'] = 'child killed after %d s' % timeout
+    except Exception as e:  # pragma: no cover - spawn failures
+        report = {'error': repr(e)[:300]}
+    report['seconds'] = round(time.time() - t0, 1)
+    accepted = dict(report.get('accepted', {})) if 'error' not in report else {}
+    if accepted:
+        apply(accepted)
+    if verbose:
+        print('autotune:', json.dumps(report), file=sys.stderr)
+    return {'accepted': accepted, 'report': report}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# child process
+# ----------------------------------------------------------------------------------------------------------------------
+def _child(cfg):
+    import contextlib
+    import io
+    import torch
+    import cold_diffusion_models_b200 as cdm
+    dev = torch.device('cuda', int(cfg['device']))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        unet = cdm.Unet(dim=cfg['dim'], dim_mults=tuple(cfg['dim_mults']), channels=cfg['channels']).to(dev)
+    B, S, Cc = cfg['batch'], cfg['image_size'], cfg['channels']
+    g = torch.Generator().manual_seed(7)
+    x = (torch.rand(B, Cc, S, S, generator=g) * 2 - 1).to(dev)
+    target = (torch.rand(B, Cc, S, S, generator=g) * 2 - 1).to(dev)
+    t = torch.randint(0, 200, (B,), generator=g).to(dev)
+
+    def timer(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    run_candidates(unet, x, target, t, torch.cuda.synchronize, timer, int(cfg.get('steps', 3)),
+                   emit=lambda rep: print('AUTOTUNE_REPORT ' + json.dumps(rep), flush=True))
+
+
+def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None, min_gain=0.005):
+    """the child's decision procedure (device-agnostic so that tests can drive it on the emulated C ABI): tries CANDIDATES in
+    order on top of what has been accepted, calls emit(cumulative report) after every decision; returns the final report"""
+    import torch
+    from cold_diffusion_models_b200.deblurring import _LossFn
+    candidates = CANDIDATES if candidates is None else candidates
+
+    def step():
+        y = unet(x, t)
+        _LossFn.apply(target, y, 1).backward()
+        return y
+
+    def run():
+        """one micro-step with the smooth L2 loss (an L1 loss' sign() gradient would turn 1e-4-level output noise into
+        O(1) gradient differences) -> (output, flat gradient)"""
+        for p in unet.parameters():
+            p.grad = None
+        if getattr(unet.engine, 'flat_grad', None) is not None:
+            unet.engine.flat_grad.zero_()
+        y = step()
+        sync()
+        return y.detach().clone(), unet.engine.flat_grad.detach().clone()
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+    def block_errors(ga, gb):
+        """worst relative error over the per-parameter slices of the flat gradient (a wrong small tensor must not hide
+        behind the norm of the big ones)"""
+        worst = 0.0
+        for n, (off, k) in unet.engine._offsets.items():
+            a, b = ga[off:off + k], gb[off:off + k]
+            nb = b.double().norm().item()
+            if nb > 0:
+                worst = max(worst, (a.double() - b.double()).norm().item() / nb)
+        return worst
+
+    apply(DEFAULTS)
+    run()                                               # warm-up: buffers, packed weights, function attributes
+    y0, g0 = run()
+    y1, g1 = run()
+    noise_y, noise_g = rel(y1, y0), block_errors(g1, g0)
+    tol_y, tol_g = max(1e-4, 8 * noise_y), max(2e-3, 8 * noise_g)
+    timer(step, 1)
+    base_ms = timer(step, steps)
+    report = {'noise': {'output': noise_y, 'grad': noise_g}, 'tolerance': {'output': tol_y, 'grad': tol_g}, 'default_ms': base_ms,
+              'candidates': [], 'accepted': {}, 'best_ms': base_ms}
+    emit(report)
+    accepted, best_ms = {}, base_ms
+    for name, sw in candidates:
+        trial = dict(accepted)
+        trial.update(sw)
+        row = {'name': name, 'switches': sw}
+        try:
+            apply(dict(DEFAULTS, **trial))
+            run()                                       # first use of the variant: attributes, job tables
+            y, gr = run()
+            ey, eg = rel(y, y0), block_errors(gr, g0)
+            row.update(err_output=ey, err_grad=eg, finite=bool(torch.isfinite(y).all().item() and torch.isfinite(gr).all().item()))
+            if row['finite'] and ey <= tol_y and eg <= tol_g:
+                timer(step, 1)
+                ms = timer(step, steps)
+                row['ms'] = ms
+                if ms < (1.0 - min_gain) * best_ms:
+                    accepted, best_ms = trial, ms
+                    row['accepted'] = True
+            else:
+                row['rejected'] = 'results differ from the default kernels'
+        except Exception as e:
+            row['rejected'] = 'raised: ' + repr(e)[:200]
+            report['candidates'].append(row)
+            report['accepted'], report['best_ms'] = accepted, best_ms
+            emit(report)
+            return report                               # a CUDA error is sticky: nothing after it can be trusted
+        report['candidates'].append(row)
+        report['accepted'], report['best_ms'] = accepted, best_ms
+        emit(report)
+    apply(dict(DEFAULTS, **accepted))
+    report['complete'] = True
+    emit(report)
+    return report
+
+
+if __name__ == '__main__':
+    if len(sys.argv) >= 3 and sys.argv[1] == '--child':
+        _child(json.loads(sys.argv[2]))
+    else:
+        print(json.dumps(autotune(verbose=True)))

@@ -8,9 +8,12 @@ out=gpurun_out/pending
 step() { name=$1; shift; echo "== $name"; ( timeout "$TMO" "$@" ) > $out/$name.log 2>&1; echo "$name exit $?" | tee -a $out/summary.txt; tail -n 3 $out/$name.log; }
 : > $out/summary.txt
 TMO=600 step gpu_tests           python -m pytest tests -q -m gpu
+# the guarded start-up selection itself: prints the child's report (which opt-in variants reproduce the default kernels and are faster)
+TMO=400 step autotune            python -m cold_diffusion_models_b200.tuning
 TMO=300 step model_training      env COLDDIFF_MODEL_TRAINING=1 python -m pytest tests/test_model2_train_gpu.py -q
 TMO=200 step wgrad_bias_fusion   env COLDDIFF_EXPERIMENTAL=1 python -m pytest tests/test_conv_gpu.py -q -k fused_bias
-TMO=300 step bench               python bench.py
+TMO=400 step bench               python bench.py
+TMO=300 step bench_no_autotune   python bench.py --no-autotune
 TMO=300 step eager_comparator    python bench.py --impl reference --reference-device cuda --steps 3 --warmup 2
 # wgrad with the bias column sums folded in (one extra N = 32 MMA per tile) against the separate cd_colsum launches
 TMO=200 step op_profile_default  python tools/op_profile.py
@@ -25,5 +28,5 @@ TMO=300 step bench_all_switches        env COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BA
 TMO=300 step conv_shapes_epilogue      python tools/conv_shapes_epilogue.py
 TMO=300 step bench_staged_epilogue     env COLDDIFF_CONV_STAGED_EPILOGUE=1 python bench.py
 TMO=300 step bench_everything_on       env COLDDIFF_CONV_STAGED_EPILOGUE=1 COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 python bench.py
-grep -h '"metric"' $out/bench.log $out/eager_comparator.log $out/bench_batched_repack.log $out/bench_all_switches.log $out/bench_staged_epilogue.log $out/bench_everything_on.log > $out/bench_lines.json 2>/dev/null
+grep -h '"metric"' $out/bench.log $out/bench_no_autotune.log $out/eager_comparator.log $out/bench_batched_repack.log $out/bench_all_switches.log $out/bench_staged_epilogue.log $out/bench_everything_on.log > $out/bench_lines.json 2>/dev/null
 cat $out/summary.txt
