@@ -320,3 +320,18 @@ def _conv_staged_epilogue_body():
             assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (B, Ci, Co, H, W)
     finally:
         lib.cd_conv_tc_set_staged_epilogue(0)
+
+
+def test_autotune_child_validates_every_opt_in_variant_on_this_gpu():
+    """cold_diffusion_models_b200.tuning.autotune on the small network: the child must complete, and every opt-in variant must
+    reproduce the default kernels' output and gradients (whether it is also faster, i.e. accepted, depends on the sizes)"""
+    from cold_diffusion_models_b200 import tuning
+    try:
+        r = tuning.autotune(dim=32, dim_mults=(1, 2), channels=3, image_size=32, batch=4, device=torch.cuda.current_device(), timeout=400)
+    finally:
+        tuning.apply(tuning.DEFAULTS)
+    rep = r['report']
+    assert 'error' not in rep and 'error_after' not in rep and rep.get('complete'), rep
+    assert [c['name'] for c in rep['candidates']] == [n for n, _ in tuning.CANDIDATES]
+    for c in rep['candidates']:
+        assert 'rejected' not in c and c['finite'], c
