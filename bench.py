@@ -271,6 +271,9 @@ def main():
     ema = trainer.ema_model
     S = args.sample_steps
     ema.denoise_fn.eval()
+    graph_sampling = bool(tuned['report'].get('sampling_cuda_graph'))
+    if graph_sampling:                       # the child found the CUDA-graph replay of the inference forward equal and faster
+        ema.denoise_fn.engine.enable_cuda_graph(True)
     xs = resident[0]
     with torch.no_grad():
         img = ema.opt(xs)                                    # x_T = D(x, T)
@@ -286,6 +289,8 @@ def main():
             rev(s)
         ms_s = timed(rev, S)
     sample_ms_per_rev_step = ms_s / S
+    if graph_sampling:
+        ema.denoise_fn.engine.enable_cuda_graph(False)
     sample_img_s = B * world / (sample_ms_per_rev_step * C3['timesteps'] / 1e3)
 
     # ---- the other BASELINE configs that fit one GPU, as context (rank 0 only; not the headline, bounded to a few steps) ----
@@ -420,6 +425,7 @@ def main():
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": losses[-1] if losses else None},
             "sample": {"value": sample_img_s, "unit": "images/s (200-step x0_step_down, batch 32/GPU)",
                        "ms_per_reverse_step": sample_ms_per_rev_step, "reverse_steps_timed": S,
+                       "cuda_graph": graph_sampling,
                        "note": "per-step cost is t-independent (cumulative-operator degradation), so 200 steps = 200 x this"},
             "gpu_launches": launches,
             "roofline": roof,
@@ -428,7 +434,7 @@ def main():
             "train_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
             "other_configs": others,
             "tuning": {"accepted": tuned['accepted'],
-                       "report": {k: v for k, v in tuned['report'].items() if k in ('default_ms', 'best_ms', 'noise', 'tolerance', 'seconds', 'error',
+                       "report": {k: v for k, v in tuned['report'].items() if k in ('default_ms', 'best_ms', 'sampling', 'sampling_cuda_graph', 'noise', 'tolerance', 'seconds', 'error',
                                                                                     'error_after', 'skipped', 'complete', 'child_exit', 'stderr_tail')},
                        "candidates": [{k: c.get(k) for k in ('name', 'ms', 'err_output', 'err_grad', 'accepted', 'rejected')}
                                       for c in tuned['report'].get('candidates', [])],

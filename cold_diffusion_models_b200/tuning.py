@@ -2,8 +2,9 @@
 
 Some kernel variants of libcolddiff are written and checked from source on the CPU but ship OFF because they have not been
 validated on a B200 (NOTES.md, "Code that exists but has not run on a B200 yet"): the line-coalesced epilogue of the tcgen05
-convolution (`cd_conv_tc_set_staged_epilogue`), the shared-memory-staged LinearAttention kernels (`cd_linattn_set_staged`) and the
-one-launch weight repacks (`engine.batched_repack`).  `autotune()` decides about them the way a BLAS library picks kernels at
+convolution (`cd_conv_tc_set_staged_epilogue`), the shared-memory-staged LinearAttention kernels (`cd_linattn_set_staged`), the
+one-launch weight repacks (`engine.batched_repack`) and the bias gradient folded into the tcgen05 weight gradient
+(`cd_wgrad_tc_set_bias_fusion`).  `autotune()` decides about them the way a BLAS library picks kernels at
 start-up, but without trusting them: a CHILD process (so that a faulting or spinning kernel can neither poison this process'
 CUDA context nor hang it -- the child is killed after `timeout` seconds) builds the network the caller is about to run, executes
 one training micro-step (p_losses forward + backward) per candidate, and a candidate is accepted only if
@@ -32,8 +33,10 @@ CANDIDATES = [
     ('conv_staged_epilogue_all', {'conv_staged_epilogue': 2}),
     ('linattn_staged', {'linattn_staged': 1}),
     ('batched_repack', {'batched_repack': 1}),
+    # last, because it is tcgen05 code that has never run: if it takes the child down, everything above has been decided
+    ('wgrad_bias_fusion', {'wgrad_bias_fusion': 1}),
 ]
-DEFAULTS = {'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0}
+DEFAULTS = {'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'wgrad_bias_fusion': 0}
 
 
 def apply(settings):
@@ -45,6 +48,8 @@ def apply(settings):
         _lib.lib.cd_linattn_set_staged(int(settings['linattn_staged']))
     if 'batched_repack' in settings:
         engine.batched_repack(bool(settings['batched_repack']))
+    if 'wgrad_bias_fusion' in settings:
+        _lib.lib.cd_wgrad_tc_set_bias_fusion(int(settings['wgrad_bias_fusion']))
 
 
 def autotune(dim=64, dim_mults=(1, 2, 4, 8), channels=3, image_size=128, batch=32, device=0, timeout=300, steps=3, verbose=False):
@@ -123,10 +128,10 @@ def _child(cfg):
         return e0.elapsed_time(e1) / n
 
     run_candidates(unet, x, target, t, torch.cuda.synchronize, timer, int(cfg.get('steps', 3)),
-                   emit=lambda rep: print('AUTOTUNE_REPORT ' + json.dumps(rep), flush=True))
+                   emit=lambda rep: print('AUTOTUNE_REPORT ' + json.dumps(rep), flush=True), sampling_graph=True)
 
 
-def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None, min_gain=0.005):
+def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None, min_gain=0.005, sampling_graph=False):
     """the child's decision procedure (device-agnostic so that tests can drive it on the emulated C ABI): tries CANDIDATES in
     order on top of what has been accepted, calls emit(cumulative report) after every decision; returns the final report"""
     import torch
@@ -204,6 +209,37 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
         report['accepted'], report['best_ms'] = accepted, best_ms
         emit(report)
     apply(dict(DEFAULTS, **accepted))
+    # ---- inference forward (sampling loops): CUDA-graph replay (engine.enable_cuda_graph) against the eager launches -----
+    if sampling_graph:
+        row = {'name': 'sampling_cuda_graph'}
+        try:
+            with torch.no_grad():
+                fwd = lambda: unet(x, t)
+                ye = fwd().clone()
+                ye2 = fwd().clone()
+                sync()
+                tol = max(1e-4, 8 * rel(ye2, ye))
+                timer(fwd, 1)
+                ms_eager = timer(fwd, steps)
+                unet.engine.enable_cuda_graph(True)
+                try:
+                    yg = fwd().clone()                 # captures
+                    yg = fwd().clone()                 # replays
+                    sync()
+                    row.update(err_output=rel(yg, ye), ms_eager=ms_eager)
+                    if row['err_output'] <= tol and bool(torch.isfinite(yg).all().item()):
+                        timer(fwd, 1)
+                        row['ms'] = timer(fwd, steps)
+                        if row['ms'] < (1.0 - min_gain) * ms_eager:
+                            row['accepted'] = True
+                            report['sampling_cuda_graph'] = True
+                    else:
+                        row['rejected'] = 'results differ from the eager launches'
+                finally:
+                    unet.engine.enable_cuda_graph(False)
+        except Exception as e:
+            row['rejected'] = 'raised: ' + repr(e)[:200]
+        report['sampling'] = row
     report['complete'] = True
     emit(report)
     return report

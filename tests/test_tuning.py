@@ -41,7 +41,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
         u = cdm.Unet(dim=32, dim_mults=(1, 2), channels=3)
     u.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd:')})
 
-    state = {'conv_staged_epilogue': 0, 'linattn_staged': 0}
+    state = {'conv_staged_epilogue': 0, 'linattn_staged': 0, 'wgrad_bias_fusion': 0}
 
     class FakeLib:                                       # the emulator has no kernel variants: record the switches instead
         def cd_conv_tc_set_staged_epilogue(self, v):
@@ -50,6 +50,10 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
 
         def cd_linattn_set_staged(self, v):
             state['linattn_staged'] = v
+            return 0
+
+        def cd_wgrad_tc_set_bias_fusion(self, v):
+            state['wgrad_bias_fusion'] = v
             return 0
     monkeypatch.setattr(_lib, 'lib', FakeLib())
 
@@ -85,7 +89,8 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     assert not rows['linattn_staged'].get('accepted') and rows['linattn_staged']['ms'] == 95.0               # right but slower
     assert rows['batched_repack'].get('accepted')
     assert rep['accepted'] == {'conv_staged_epilogue': 1, 'batched_repack': 1} and rep['best_ms'] == 87.0
-    assert state == {'conv_staged_epilogue': 1, 'linattn_staged': 0} and engine.batched_repack() is True      # left applied
+    assert not rows['wgrad_bias_fusion'].get('accepted') and rows['wgrad_bias_fusion']['ms'] == 87.0        # right, no gain
+    assert state == {'conv_staged_epilogue': 1, 'linattn_staged': 0, 'wgrad_bias_fusion': 0} and engine.batched_repack() is True      # left applied
 
     # a candidate that raises ends the search; what was accepted before it stands
     def boom(v):
