@@ -207,7 +207,7 @@ def main():
     if not args.no_autotune:
         if rank == 0:
             tuned = tuning.autotune(dim=C3['dim'], dim_mults=C3['dim_mults'], channels=C3['channels'], image_size=C3['image_size'],
-                                    batch=B, device=local, timeout=300)
+                                    batch=B, accum=A, device=local, timeout=300)
         if world > 1:
             box = [tuned]
             dist.broadcast_object_list(box, src=0)
@@ -420,6 +420,9 @@ def main():
             "config": {"workload": "C3: CelebA-128 deblur train step = 2 micro-batches x 32 img/GPU (p_losses fwd+bwd) + grad all-reduce + Adam + EMA",
                        "net": "Unet(dim=64, dim_mults=(1,2,4,8), channels=3)", "T": 200, "blur": "Exponential_reflect k=15 std=0.01",
                        "global_batch": img_per_step * world, "parallelism": "dp%d" % world,
+                       "micro_batches": ("one pass over the %d concatenated micro-batches of %d (same gradient: the loss is their mean; "
+                                         "accepted by the start-up check, see `tuning`)" % (A, B)) if tuned['accepted'].get('merge_micro_batches')
+                                        else "%d x %d, gradients accumulated" % (A, B),
                        "l2": "inputs rotate over 4 distinct batch sets; per-step activations (>3 GB) exceed the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": img_per_step * 3 * 128 * 128 * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": losses[-1] if losses else None},

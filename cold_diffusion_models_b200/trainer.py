@@ -163,6 +163,26 @@ class FusedAdamEMA:
         self.t = sd['t']; self.m.copy_(sd['m']); self.v.copy_(sd['v'])
 
 
+_MERGE_MICRO_BATCHES = None
+
+
+def merge_micro_batches(enable=None):
+    """switch: run the gradient_accumulate_every micro-batches of one optimizer step as ONE pass over their concatenation.
+    The loss is a mean over equally sized micro-batches (DB:1190-1196: `backwards(loss / accumulate)`), so the gradient is the
+    same sum of per-sample terms; what changes is the order of the floating-point additions, the number of launches per step
+    (weight repacks, per-launch fixed costs and the per-(batch element, head) kernels run once instead of twice) and the
+    wave count of the small-resolution layers.  Needs a network without batch-coupled layers (every Unet / Model here) and
+    single-tensor batches of one shape; off by default (COLDDIFF_MERGE_MICRO_BATCHES=1, or tuning.autotune() when it
+    reproduces the accumulated gradient and is faster)."""
+    global _MERGE_MICRO_BATCHES
+    if enable is not None:
+        _MERGE_MICRO_BATCHES = bool(enable)
+    if _MERGE_MICRO_BATCHES is None:
+        import os
+        _MERGE_MICRO_BATCHES = os.environ.get('COLDDIFF_MERGE_MICRO_BATCHES', '0') == '1'
+    return _MERGE_MICRO_BATCHES
+
+
 class Trainer(EvaluationMixin, object):
     def __init__(self, diffusion_model, folder, *, ema_decay=0.995, image_size=128, train_batch_size=32, train_lr=2e-5,
                  train_num_steps=100000, gradient_accumulate_every=2, fp16=False, step_start_ema=2000,
@@ -263,12 +283,20 @@ class Trainer(EvaluationMixin, object):
     def train_step(self, batches=None):
         """one optimizer step = gradient_accumulate_every micro-batches (DB:1188-1204). Returns mean loss (tensor)."""
         u_loss = None
-        for i in range(self.gradient_accumulate_every):
-            d = batches[i] if batches is not None else self._next()
+        A = self.gradient_accumulate_every
+        ds = [batches[i] if batches is not None else self._next() for i in range(A)]
+        if (A > 1 and merge_micro_batches() and all(torch.is_tensor(d) for d in ds) and len({tuple(d.shape) for d in ds}) == 1):
+            # one pass over the concatenated micro-batches: mean over A * B samples == sum_i mean_i / A
+            d = torch.cat([d.cuda(non_blocking=True) for d in ds], dim=0)
+            loss = self._loss(d)
+            loss.backward()
+            u_loss = loss.detach() * A
+            ds = []
+        for d in ds:
             d = tuple(x.cuda(non_blocking=True) for x in d) if isinstance(d, (tuple, list)) else d.cuda(non_blocking=True)
             loss = self._loss(d)
             u_loss = loss.detach() if u_loss is None else u_loss + loss.detach()
-            (loss / self.gradient_accumulate_every).backward()
+            (loss / A).backward()
         eng = self._unet.engine
         from .engine_bwd import allreduce_mean_
         scale = allreduce_mean_(eng.flat_grad, self._world)      # one NCCL all-reduce per optimizer step

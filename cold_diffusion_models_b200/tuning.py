@@ -33,10 +33,11 @@ CANDIDATES = [
     ('conv_staged_epilogue_all', {'conv_staged_epilogue': 2}),
     ('linattn_staged', {'linattn_staged': 1}),
     ('batched_repack', {'batched_repack': 1}),
+    ('merge_micro_batches', {'merge_micro_batches': 1}),
     # last, because it is tcgen05 code that has never run: if it takes the child down, everything above has been decided
     ('wgrad_bias_fusion', {'wgrad_bias_fusion': 1}),
 ]
-DEFAULTS = {'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'wgrad_bias_fusion': 0}
+DEFAULTS = {'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
 
 
 def apply(settings):
@@ -48,14 +49,17 @@ def apply(settings):
         _lib.lib.cd_linattn_set_staged(int(settings['linattn_staged']))
     if 'batched_repack' in settings:
         engine.batched_repack(bool(settings['batched_repack']))
+    if 'merge_micro_batches' in settings:
+        from . import trainer
+        trainer.merge_micro_batches(bool(settings['merge_micro_batches']))
     if 'wgrad_bias_fusion' in settings:
         _lib.lib.cd_wgrad_tc_set_bias_fusion(int(settings['wgrad_bias_fusion']))
 
 
-def autotune(dim=64, dim_mults=(1, 2, 4, 8), channels=3, image_size=128, batch=32, device=0, timeout=300, steps=3, verbose=False):
+def autotune(dim=64, dim_mults=(1, 2, 4, 8), channels=3, image_size=128, batch=32, accum=2, device=0, timeout=300, steps=3, verbose=False):
     """-> {'accepted': {switch: value}, 'report': {...}}; the accepted switches are applied to this process.  See the module text."""
     cmd = [sys.executable, '-m', 'cold_diffusion_models_b200.tuning', '--child', json.dumps(dict(
-        dim=dim, dim_mults=list(dim_mults), channels=channels, image_size=image_size, batch=batch, device=device, steps=steps))]
+        dim=dim, dim_mults=list(dim_mults), channels=channels, image_size=image_size, batch=batch, accum=accum, device=device, steps=steps))]
     env = dict(os.environ)
     env['PYTHONPATH'] = ROOT + os.pathsep + env.get('PYTHONPATH', '')
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'GROUP_RANK', 'LOCAL_WORLD_SIZE', 'TORCHELASTIC_RUN_ID',
@@ -113,9 +117,10 @@ def _child(cfg):
         unet = cdm.Unet(dim=cfg['dim'], dim_mults=tuple(cfg['dim_mults']), channels=cfg['channels']).to(dev)
     B, S, Cc = cfg['batch'], cfg['image_size'], cfg['channels']
     g = torch.Generator().manual_seed(7)
-    x = (torch.rand(B, Cc, S, S, generator=g) * 2 - 1).to(dev)
-    target = (torch.rand(B, Cc, S, S, generator=g) * 2 - 1).to(dev)
-    t = torch.randint(0, 200, (B,), generator=g).to(dev)
+    A = int(cfg.get('accum', 2))
+    x = [(torch.rand(B, Cc, S, S, generator=g) * 2 - 1).to(dev) for _ in range(A)]
+    target = [(torch.rand(B, Cc, S, S, generator=g) * 2 - 1).to(dev) for _ in range(A)]
+    t = [torch.randint(0, 200, (B,), generator=g).to(dev) for _ in range(A)]
 
     def timer(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -138,10 +143,25 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
     from cold_diffusion_models_b200.deblurring import _LossFn
     candidates = CANDIDATES if candidates is None else candidates
 
+    from cold_diffusion_models_b200 import trainer as _trainer
+    if torch.is_tensor(x):                              # one micro-batch given: a list of one
+        x, target, t = [x], [target], [t]
+    A = len(x)
+    xc, tc, tgc = (torch.cat(x), torch.cat(t), torch.cat(target)) if A > 1 else (x[0], t[0], target[0])
+
     def step():
-        y = unet(x, t)
-        _LossFn.apply(target, y, 1).backward()
-        return y
+        """the gradient of one optimizer step, the way Trainer.train_step accumulates it: A micro-batches with loss / A each, or
+        (merge_micro_batches) one pass over their concatenation"""
+        if A > 1 and _trainer.merge_micro_batches():
+            y = unet(xc, tc)
+            _LossFn.apply(tgc, y, 1).backward()
+            return y
+        ys = []
+        for xi, ti, gi in zip(x, t, target):
+            y = unet(xi, ti)
+            (_LossFn.apply(gi, y, 1) / A).backward()
+            ys.append(y)
+        return torch.cat(ys) if A > 1 else ys[0]
 
     def run():
         """one micro-step with the smooth L2 loss (an L1 loss' sign() gradient would turn 1e-4-level output noise into
@@ -214,7 +234,7 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
         row = {'name': 'sampling_cuda_graph'}
         try:
             with torch.no_grad():
-                fwd = lambda: unet(x, t)
+                fwd = lambda: unet(x[0], t[0])
                 ye = fwd().clone()
                 ye2 = fwd().clone()
                 sync()

@@ -30,11 +30,14 @@ def emu(monkeypatch):
     with abi_emulator.patched():
         yield
     engine.batched_repack(False)
+    from cold_diffusion_models_b200 import trainer
+    trainer.merge_micro_batches(False)
 
 
 def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     import cold_diffusion_models_b200 as cdm
     from cold_diffusion_models_b200 import tuning, engine, _lib
+    from cold_diffusion_models_b200 import trainer as trainer_mod
     z = np.load(os.path.join(G, 'unet_small.npz'))
     g = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
     with contextlib.redirect_stdout(io.StringIO()):
@@ -79,17 +82,23 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
             ms += 5
         if engine.batched_repack():
             ms -= 3
+        if trainer_mod.merge_micro_batches():
+            ms -= 7
         return ms
     reports = []
-    rep = tuning.run_candidates(u, g['x'], g['target'], g['t'], lambda: None, timer, 1, reports.append)
+    xs = [g['x'], g['x'].flip(0) * 0.5]
+    tgs = [g['target'], g['target'].flip(0)]
+    ts = [g['t'], g['t'].flip(0)]
+    rep = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports.append)
     assert rep['complete'] and len(reports) == len(tuning.CANDIDATES) + 2
     rows = {r['name']: r for r in rep['candidates']}
     assert rows['conv_staged_epilogue_short_k'].get('accepted') and rows['conv_staged_epilogue_short_k']['err_grad'] == 0.0
     assert 'rejected' in rows['conv_staged_epilogue_all'] and 'ms' not in rows['conv_staged_epilogue_all']      # wrong result: never timed
     assert not rows['linattn_staged'].get('accepted') and rows['linattn_staged']['ms'] == 95.0               # right but slower
     assert rows['batched_repack'].get('accepted')
-    assert rep['accepted'] == {'conv_staged_epilogue': 1, 'batched_repack': 1} and rep['best_ms'] == 87.0
-    assert not rows['wgrad_bias_fusion'].get('accepted') and rows['wgrad_bias_fusion']['ms'] == 87.0        # right, no gain
+    assert rows['merge_micro_batches'].get('accepted') and rows['merge_micro_batches']['err_grad'] < 1e-5    # same gradient, other summation order
+    assert rep['accepted'] == {'conv_staged_epilogue': 1, 'batched_repack': 1, 'merge_micro_batches': 1} and rep['best_ms'] == 80.0
+    assert not rows['wgrad_bias_fusion'].get('accepted') and rows['wgrad_bias_fusion']['ms'] == 80.0        # right, no gain
     assert state == {'conv_staged_epilogue': 1, 'linattn_staged': 0, 'wgrad_bias_fusion': 0} and engine.batched_repack() is True      # left applied
 
     # a candidate that raises ends the search; what was accepted before it stands
@@ -97,6 +106,50 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
         raise RuntimeError('CUDA error: an illegal memory access was encountered')
     monkeypatch.setattr(_lib.lib, 'cd_linattn_set_staged', lambda v: boom(v) if v else 0, raising=False)
     reports2 = []
-    rep2 = tuning.run_candidates(u, g['x'], g['target'], g['t'], lambda: None, timer, 1, reports2.append)
+    rep2 = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports2.append)
     assert 'complete' not in rep2 and rep2['accepted'] == {'conv_staged_epilogue': 1}
     assert rep2['candidates'][-1]['name'] == 'linattn_staged' and 'raised' in rep2['candidates'][-1]['rejected']
+
+
+def test_trainer_step_over_merged_micro_batches_equals_the_accumulated_one(emu, monkeypatch, tmp_path):
+    """Trainer.train_step with merge_micro_batches(): one pass over the concatenated micro-batches gives the parameters (Adam +
+    EMA) of the two accumulated passes (DB:1188-1204); on the CPU generator one randint(2B) equals two randint(B) draws"""
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200 import trainer as trainer_mod
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    z = np.load(os.path.join(G, 'unet_small.npz'))
+    g = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+    out, calls = [], []
+    for merged in (False, True):
+        trainer_mod.merge_micro_batches(merged)
+        with contextlib.redirect_stdout(io.StringIO()):
+            u = cdm.Unet(dim=32, dim_mults=(1, 2), channels=3)
+        u.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd:')})
+        gd = cdm.GaussianDiffusion(u, image_size=32, device_of_kernel='cpu', channels=3, timesteps=4, kernel_std=0.15, kernel_size=7,
+                                   blur_routine='Exponential_reflect', sampling_routine='x0_step_down', loss_type='l2')
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = cdm.Trainer(gd, None, image_size=32, train_batch_size=2, train_lr=1e-3, gradient_accumulate_every=2,
+                             results_folder=str(tmp_path), dataset='synthetic', step_start_ema=0, update_ema_every=1, ema_decay=0.9)
+        n = [0]
+        real = type(u.engine).forward
+
+        def counting(self, *a, _real=real, **k):
+            n[0] += 1
+            return _real(self, *a, **k)
+        monkeypatch.setattr(type(u.engine), 'forward', counting)
+        gen = torch.Generator().manual_seed(5)
+        torch.manual_seed(11)
+        losses = []
+        for step in range(2):
+            bs = [torch.rand(2, 3, 32, 32, generator=gen) * 2 - 1 for _ in range(2)]
+            losses.append(float(tr.train_step(batches=bs)))
+            tr.step += 1
+        monkeypatch.setattr(type(u.engine), 'forward', real)
+        calls.append(n[0])
+        out.append(({k: v.clone() for k, v in gd.denoise_fn.state_dict().items()}, losses))
+    assert calls == [4, 2]                                   # two optimizer steps: 2 x 2 forward passes against 2 x 1
+    for a, b in zip(out[0][1], out[1][1]):
+        assert abs(a - b) < 1e-6 * max(1.0, abs(a))
+    for k in out[0][0]:
+        r = ((out[0][0][k].double() - out[1][0][k].double()).norm() / (out[0][0][k].double().norm() + 1e-30)).item()
+        assert r < 1e-5, (k, r)
