@@ -266,6 +266,17 @@ def main():
         sampler.stop_flag = True
     value = img_per_step * world * K / (ms / 1e3)
     e2e = img_per_step * world * K / (ms_e2e / 1e3)
+    accumulated = None
+    if tuned['accepted'].get('merge_micro_batches'):
+        # the same K steps with the micro-batches accumulated one after the other (everything else as tuned), for comparison
+        from cold_diffusion_models_b200 import trainer as _trainer_mod
+        _trainer_mod.merge_micro_batches(False)
+        for s in range(2):
+            step_resident(s)
+        ms_acc = timed(step_resident, K)
+        _trainer_mod.merge_micro_batches(True)
+        accumulated = {"value": img_per_step * world * K / (ms_acc / 1e3), "unit": "images/s", "ms_per_step": ms_acc / K,
+                       "note": "%d x %d micro-batches one after the other, other switches as in `tuning.accepted`" % (A, B)}
 
     # ---- sampling half of the metric: x0_step_down reverse steps (UNet forward + Algorithm-2 update) -----------
     ema = trainer.ema_model
@@ -430,6 +441,7 @@ def main():
                        "ms_per_reverse_step": sample_ms_per_rev_step, "reverse_steps_timed": S,
                        "cuda_graph": graph_sampling,
                        "note": "per-step cost is t-independent (cumulative-operator degradation), so 200 steps = 200 x this"},
+            "accumulated_micro_batches": accumulated,
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
