@@ -61,7 +61,7 @@ def apply(settings):
         _lib.lib.cd_wgrad_tc_set_bias_fusion(int(settings['wgrad_bias_fusion']))
 
 
-def autotune(dim=64, dim_mults=(1, 2, 4, 8), channels=3, image_size=128, batch=32, accum=2, device=0, timeout=300, steps=3, verbose=False):
+def autotune(dim=64, dim_mults=(1, 2, 4, 8), channels=3, image_size=128, batch=32, accum=2, device=0, timeout=300, steps=5, verbose=False):
     """-> {'accepted': {switch: value}, 'report': {...}}; the accepted switches are applied to this process.  See the module text."""
     cmd = [sys.executable, '-m', 'cold_diffusion_models_b200.tuning', '--child', json.dumps(dict(
         dim=dim, dim_mults=list(dim_mults), channels=channels, image_size=image_size, batch=batch, accum=accum, device=device, steps=steps))]
