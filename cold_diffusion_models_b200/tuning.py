@@ -233,8 +233,29 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
         report['candidates'].append(row)
         report['accepted'], report['best_ms'] = accepted, best_ms
         emit(report)
+    # ---- inference forward (sampling loops run it under no_grad: no saved tensors, other epilogue variants): the accepted
+    # switches must reproduce the default kernels there too, or nothing is accepted at all
+    if accepted:
+        try:
+            with torch.no_grad():
+                apply(DEFAULTS)
+                yd = unet(x[0], t[0]).clone()
+                yd2 = unet(x[0], t[0]).clone()
+                apply(dict(DEFAULTS, **accepted))
+                ya = unet(x[0], t[0]).clone()
+                sync()
+            err, tol = rel(ya, yd), max(1e-4, 8 * rel(yd2, yd))
+            report['inference_forward'] = {'err_output': err, 'tolerance': tol}
+            if not (err <= tol and bool(torch.isfinite(ya).all().item())):
+                report['inference_forward']['rejected'] = 'accepted switches change the no_grad forward: all switches dropped'
+                accepted, best_ms = {}, base_ms
+        except Exception as e:
+            report['inference_forward'] = {'rejected': 'raised: ' + repr(e)[:200]}
+            accepted, best_ms = {}, base_ms
+        report['accepted'], report['best_ms'] = accepted, best_ms
+        emit(report)
     apply(dict(DEFAULTS, **accepted))
-    # ---- inference forward (sampling loops): CUDA-graph replay (engine.enable_cuda_graph) against the eager launches -----
+    # ---- CUDA-graph replay of that forward (engine.enable_cuda_graph) against the eager launches -----
     if sampling_graph:
         row = {'name': 'sampling_cuda_graph'}
         try:
