@@ -247,6 +247,12 @@ attn_bwd_small_kernel(const float* __restrict__ dweff, const float* __restrict__
 constexpr int kKvPix = 32;
 constexpr int kKvTiles = 8;
 constexpr int kKvStride = 36;         // floats per channel row of the transposed tiles (16-byte aligned, 4-way store conflicts)
+// REMAP (opt-in, cd_linattn_set_staged): a warp owns ONE head and 4 pixel quads (lane = 8 channel quads x 4 pixel quads) instead of
+// all four heads of one pixel quad.  The heads' rows of every shared array are a multiple of 32 floats apart, so in the default
+// mapping the four heads of a warp hit the same banks: each of the four LDS.128 of a step costs 4 wavefronts (16 per 32 FMAs,
+// shared-memory bound at one wavefront per clock and SM); remapped, each is one 64- or 128-byte wavefront.  Same sums in the
+// same order -> bit-identical results.
+template <bool REMAP>
 __global__ void __launch_bounds__(256)
 attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __restrict__ kmax,
                    const float* __restrict__ ksum, const float* __restrict__ dctxn, const float* __restrict__ rowdot,
@@ -264,8 +270,10 @@ attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __
     dcA[i] = v;
     dcB[((hd & ~31) + e) * 32 + (hd & 31)] = v;
   }
-  const int cq = tid & 31, pq = tid >> 5;           // channel quad (h = cq/8, j4 = (cq%8)*4), pixel quad
-  const int h = cq >> 3, j4 = (cq & 7) * 4;
+  // default: channel quad cq = lane (h = cq/8, j4 = (cq%8)*4), pixel quad = warp;  REMAP: head = warp % 4, pixel quad = 4 (warp / 4) + lane / 8
+  const int h = REMAP ? ((tid >> 5) & 3) : ((tid & 31) >> 3);
+  const int j4 = (tid & 7) * 4;
+  const int pq = REMAP ? ((tid >> 7) * 4 + ((tid & 31) >> 3)) : (tid >> 5);
   const int c4 = h * 32 + j4;
   const float4 rd = *reinterpret_cast<const float4*>(rowdot + b * 128 + c4);
   const int lc = tid & 127, lhalf = tid >> 7;
@@ -509,13 +517,20 @@ extern "C" int cd_linattn_bwd_kv(const float* qkv, int ld, int B, int n, const f
   CD_REQUIRE(dld % 4 == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, "cd_linattn_bwd_kv: dqkv must be 16-byte aligned with dld %% 4 == 0");
   const size_t smem = sizeof(float) * (2 * 4096 + 2 * 128 * kKvStride);
   static bool attr = false;
-  if (!attr) { CD_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  if (!attr) {
+    CD_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CD_CUDA(cudaFuncSetAttribute(attn_bwd_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
   // tiles per block: up to kKvTiles (amortises the 32 KB dctxn staging), fewer when that would leave SMs idle
   int tiles = static_cast<int>(static_cast<long long>(cd_cdiv(n, kKvPix)) * B / (148 * 2));
   if (tiles > kKvTiles) tiles = kKvTiles;
   if (tiles < 1) tiles = 1;
   dim3 grid(cd_cdiv(n, kKvPix * tiles), B);
-  attn_bwd_kv_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(qkv, ld, n, kmax, ksum, dctxn, rowdot, dqkv, dld, tiles);
+  if (cd_linattn_staged_enabled(nullptr, nullptr))
+    attn_bwd_kv_kernel<true><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(qkv, ld, n, kmax, ksum, dctxn, rowdot, dqkv, dld, tiles);
+  else
+    attn_bwd_kv_kernel<false><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(qkv, ld, n, kmax, ksum, dctxn, rowdot, dqkv, dld, tiles);
   CD_LAUNCH_CHECK();
   return 0;
 }

@@ -5,6 +5,7 @@
 // every operand once, 64 channel rows per pass with all loads of a pass in flight (one float4 per thread and array), and keep
 // the arithmetic ORDER of the originals (sums over co / d / e ascending, one fmaf per term), so their results are bit-identical
 // up to the order of the float atomics that were already there.
+// The same switch selects the bank-conflict-free thread mapping of attn_bwd_kv_kernel<REMAP> (backward.cu).
 // Off by default until they have run on a B200: cd_linattn_set_staged(1) / COLDDIFF_LINATTN_STAGED=1.
 #include "cd_common.cuh"
 

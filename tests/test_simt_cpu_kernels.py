@@ -225,3 +225,30 @@ def test_linattn_staged_kernels_equal_the_default_ones(cpulib, B, dim):
     dw_out, dctxn, rowdot = 0.5 * torch.ones(dim, 128), torch.zeros(B, 4, 32, 32), torch.zeros(B, 128)
     assert E.cd_linattn_bwd_small(P(dweff), P(ctx), P(ksum), P(w_out), B, dim, C.c_float(0.17), P(dw_out), P(dctxn), P(rowdot), None) == 0
     assert close(res[('bwd', 0, 1, 0)], torch.cat([dw_out.reshape(-1), dctxn.reshape(-1), rowdot.reshape(-1)]), 1e-4)
+
+
+@pytest.mark.parametrize('B,n,ld,dld', [(2, 256, 384, 384), (1, 1000, 392, 388), (3, 40, 384, 384)])
+def test_linattn_bwd_kv_remapped_equals_the_default_mapping(cpulib, B, n, ld, dld):
+    """attn_bwd_kv_kernel<REMAP> (cd_linattn_set_staged): a warp owns one head and four pixel quads instead of four heads and one
+    pixel quad (4x fewer shared-memory wavefronts); the same sums in the same order -> bit-identical, also for a ragged last tile"""
+    g = torch.Generator().manual_seed(n)
+    qkv = torch.randn(B, n, ld, generator=g)
+    kmax = qkv[:, :, 128:256].max(dim=1).values.contiguous()
+    ksum = torch.exp(qkv[:, :, 128:256] - kmax[:, None, :]).sum(dim=1).contiguous()
+    dctxn, rowdot = torch.randn(B, 4, 32, 32, generator=g), torch.randn(B, 128, generator=g)
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for staged in (0, 1):
+            cpulib.cd_linattn_set_staged(staged)
+            dqkv = torch.full((B, n, dld), 7.0)
+            assert cpulib.cd_linattn_bwd_kv(P(qkv), ld, B, n, P(kmax), P(ksum), P(dctxn), P(rowdot), P(dqkv), dld, C.c_void_p(0)) == 0
+            res.append(dqkv)
+    cpulib.cd_linattn_set_staged(0)
+    cpulib.simt_set_reverse_order(0)
+    for r in res[1:]:
+        assert torch.equal(r, res[0])
+    want = torch.full((B, n, dld), 7.0)
+    assert E.cd_linattn_bwd_kv(P(qkv), ld, B, n, P(kmax), P(ksum), P(dctxn), P(rowdot), P(want), dld, None) == 0
+    assert close(res[1][:, :, 128:384], want[:, :, 128:384], 2e-5)
+    assert bool((res[1][:, :, :128] == 7.0).all()) and bool((res[1][:, :, 384:] == 7.0).all())

@@ -269,6 +269,23 @@ def test_linattn_staged_kernels_match_the_default_ones():
         for i in range(4):
             assert torch.equal(res[0][i], res[1][i]), (B, dim, i)
         assert rel(res[1][4], res[0][4]) < 1e-5, (B, dim)
+    # attn_bwd_kv_kernel<REMAP>: one head and four pixel quads per warp; same sums in the same order
+    for B, n in ((4, 4096), (2, 1000), (3, 40)):
+        qkv = torch.randn(B, n, 384, generator=gen).cuda()
+        kmax = qkv[:, :, 128:256].max(dim=1).values.contiguous()
+        ksum = torch.exp(qkv[:, :, 128:256] - kmax[:, None, :]).sum(dim=1).contiguous()
+        dctxn, rowdot = torch.randn(B, 4, 32, 32, generator=gen).cuda(), torch.randn(B, 128, generator=gen).cuda()
+        outs = []
+        try:
+            for staged in (0, 1):
+                lib.cd_linattn_set_staged(staged)
+                dqkv = torch.full((B, n, 384), 7.0, device='cuda')
+                _check(lib.cd_linattn_bwd_kv(ptr(qkv), 384, B, n, ptr(kmax), ptr(ksum), ptr(dctxn), ptr(rowdot), ptr(dqkv), 384, stream()), 'bwd_kv')
+                torch.cuda.synchronize()
+                outs.append(dqkv)
+        finally:
+            lib.cd_linattn_set_staged(0)
+        assert torch.equal(outs[0], outs[1]), (B, n)
 
 
 def test_conv_staged_epilogue_matches_the_row_epilogue():
