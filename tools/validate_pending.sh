@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call that runs everything written after the round-1 GPU budget was spent (NOTES.md, "Code that exists but has not
-# run on a B200 yet") plus the two measurements round 1 still owes.  Usage (about 12 GPU-minutes):
-#   gpurun --timeout 1500 -- 'bash tools/validate_pending.sh'
+# run on a B200 yet") plus the two measurements round 1 still owes.  Usage (about 25 GPU-minutes):
+#   gpurun --timeout 2400 -- 'bash tools/validate_pending.sh'
 # Every step has its own timeout and log under gpurun_out/pending/; a failing step does not stop the next one.
 mkdir -p gpurun_out/pending
 out=gpurun_out/pending
