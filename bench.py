@@ -419,6 +419,29 @@ def main():
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 rate)" % peak_kind, "launches_timed": n_launch,
                 "share_of_step_ms": tot_ms / (ms / K)}
 
+    # ---- where one optimizer step goes, in situ (CUDA events around every C-ABI call, tools/op_profile.py's mechanism), as tuned ----
+    op_profile = None
+    try:
+        if rank == 0:
+            _lib.profile_start()
+        step_resident(1)                  # every rank takes part (all-reduce)
+        if rank == 0:
+            prof = _lib.profile_stop()
+            agg = {}
+            for name, (calls, tms) in prof.items():
+                base = name.split('(')[0]
+                c0, t0_ = agg.get(base, (0, 0.0))
+                agg[base] = (c0 + calls, t0_ + tms)
+            top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]
+            op_profile = {"total_ms_with_events": round(sum(v[1] for v in agg.values()), 3),
+                          "entry_points": {k: {"calls": v[0], "ms": round(v[1], 3)} for k, v in top}}
+    except Exception as e:
+        op_profile = {"error": repr(e)[:200]}
+        try:
+            _lib._prof = None
+        except Exception:
+            pass
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -448,6 +471,7 @@ def main():
             "clocks": sampler.summary() if sampler else None,
             "train_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
             "other_configs": others,
+            "op_profile": op_profile,
             "tuning": {"accepted": tuned['accepted'],
                        "report": {k: v for k, v in tuned['report'].items() if k in ('default_ms', 'best_ms', 'sampling', 'sampling_cuda_graph', 'noise', 'tolerance', 'seconds', 'error',
                                                                                     'error_after', 'skipped', 'complete', 'child_exit', 'stderr_tail')},

@@ -313,9 +313,11 @@ int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st);   // conv_tc2.cu: SM-
 static int g_use_2cta = 1;
 extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   // 0 off, 1 where the cost model prefers it, 2 wherever eligible
 // line-coalesced epilogue (conv_epilogue.cuh): 0 = off (default: not validated on a B200 yet), 1 = for the short-K launches that
-// are bound by their output stores (at most kStagedMaxKIters 32-channel K chunks per tile), 2 = for every launch (tests)
+// are bound by their output stores (at most kStagedMaxKIters 32-channel K chunks per tile), 2 = for every launch (tests),
+// 3 = up to kStagedMidKIters chunks (where the row epilogue of a 128-pixel tile, ~6 us per 64 KB, still outlasts the tile's MMAs)
 static int g_epi_staged = 0;
 constexpr int kStagedMaxKIters = 16;
+constexpr int kStagedMidKIters = 48;
 extern "C" int cd_conv_tc_set_staged_epilogue(int mode) { g_epi_staged = mode; return 0; }
 
 // Tile-shape choice.  Cost model: waves over the SMs x columns per tile / relative MMA issue rate of that tile shape.  The
@@ -358,7 +360,8 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   int BN = (d->Cout % 256 == 0) ? 256 : (d->Cout > 64 ? 128 : 64);
   int kiters_host = 0;
   for (int s = 0; s < d->nsrc; ++s) kiters_host += d->s[s].ntaps * (d->s[s].C / kChunkK);
-  const bool staged = g_epi_staged == 2 || (g_epi_staged == 1 && kiters_host <= kStagedMaxKIters);
+  const bool staged = g_epi_staged == 2 || (g_epi_staged == 1 && kiters_host <= kStagedMaxKIters) ||
+                      (g_epi_staged == 3 && kiters_host <= kStagedMidKIters);
   if (BN == 256 && staged) {
     // short K: the narrower tile only when it saves whole waves (same rule as below), never the SM-pair kernel
     const long long mt = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;

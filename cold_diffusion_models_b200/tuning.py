@@ -30,6 +30,7 @@ ROOT = os.path.dirname(_HERE)
 # (name, {switch: value}) in the order they are tried; each is tried on top of what has been accepted so far
 CANDIDATES = [
     ('conv_staged_epilogue_short_k', {'conv_staged_epilogue': 1}),
+    ('conv_staged_epilogue_mid_k', {'conv_staged_epilogue': 3}),
     ('conv_staged_epilogue_all', {'conv_staged_epilogue': 2}),
     ('linattn_staged', {'linattn_staged': 1}),
     ('batched_repack', {'batched_repack': 1}),

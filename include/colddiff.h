@@ -183,7 +183,7 @@ int cd_wgrad_tc_set_split(int policy, int over_clk);
 int cd_wgrad_tc_set_bias_fusion(int enable);
 /* opt-in (default 0, not yet validated on a B200): line-coalesced epilogue of the tcgen05 convolution (csrc/conv_epilogue.cuh;
  * bit-identical results): 1 = for launches with at most 16 K chunks of 32 channels per tile (the store-bound 1x1 projections),
- * 2 = for every launch */
+ * 2 = for every launch, 3 = at most 48 K chunks */
 int cd_conv_tc_set_staged_epilogue(int mode);
 /* opt-in (default 0, not yet validated on a B200): shared-memory-staged kernels behind cd_linattn_weff / cd_linattn_bwd_small
  * (csrc/linattn_small.cu; same arithmetic order as the default kernels) */

@@ -15,7 +15,7 @@ x = torch.rand(B, 3, 128, 128, device='cuda') * 2 - 1
 t = torch.randint(0, 200, (B,), device='cuda')
 res = {}
 with torch.no_grad():
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 3, 2):
         lib.cd_conv_tc_set_staged_epilogue(mode)
         for _ in range(2):
             u(x, t)
@@ -30,12 +30,13 @@ with torch.no_grad():
         u.engine.profile_convs = u.engine.profile_shapes = None
         res[mode] = acc
 lib.cd_conv_tc_set_staged_epilogue(0)
-print("%-44s %5s %9s %9s %9s %8s %8s %8s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n", "rows us", "mode1 us", "mode2 us", "TF/s", "TF/s 1", "TF/s 2"))
-tot = [0.0, 0.0, 0.0]
+MODES = (0, 1, 3, 2)
+print("%-44s %5s %9s %9s %9s %9s %8s %8s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n", "rows us", "<=16 us", "<=48 us", "all us", "TF/s", "TF/s all"))
+tot = {m: 0.0 for m in MODES}
 for shp, (n, ms, f) in res[0].items():
     n //= 5
-    us = [res[m][shp][1] / 5 / n * 1e3 for m in (0, 1, 2)]
-    for m in range(3):
+    us = {m: res[m][shp][1] / 5 / n * 1e3 for m in MODES}
+    for m in MODES:
         tot[m] += res[m][shp][1] / 5
-    print("%-44s %5d %9.1f %9.1f %9.1f %8.1f %8.1f %8.1f" % (str(shp), n, us[0], us[1], us[2], f / us[0] / 1e6, f / us[1] / 1e6, f / us[2] / 1e6))
-print("total conv ms per forward: rows %.3f   mode 1 %.3f   mode 2 %.3f" % tuple(tot))
+    print("%-44s %5d %9.1f %9.1f %9.1f %9.1f %8.1f %8.1f" % (str(shp), n, us[0], us[1], us[3], us[2], f / us[0] / 1e6, f / us[2] / 1e6))
+print("total conv ms per forward: rows %.3f   <=16 chunks %.3f   <=48 chunks %.3f   all %.3f" % (tot[0], tot[1], tot[3], tot[2]))
