@@ -24,6 +24,9 @@ void cd_set_error(const char* fmt, ...);
 
 static inline int cd_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// layernorm_multi.cu: C <= 128 LayerNorm forward with several pixels per lane group in flight (opt-in); returns 1 when not taken
+int cd_layernorm_fwd_multi(const float* x, int x_ld, long long npix, int C, const float* g, const float* beta, float eps,
+                           float* y, int y_ld, float* stats, int round_tf32, cudaStream_t st);
 // linattn_small.cu: shared-memory-staged variants of the two per-(batch element, head) LinearAttention kernels (opt-in)
 int cd_linattn_staged_enabled(const void* a, const void* b);
 int cd_linattn_weff_staged(const float* ctx, const float* ksum, const float* w_out, int B, int dim, float scale,

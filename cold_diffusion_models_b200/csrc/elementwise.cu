@@ -721,6 +721,10 @@ extern "C" int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, c
   const int G = nq < 32 ? nq : 32, ppw = 32 / G, slots = nq <= 32 ? 1 : cd_cdiv(nq, 32);
   const int blocks = cd_cdiv(npix, 8 * ppw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (slots == 1 && g != nullptr && beta != nullptr) {
+    const int rc = cd_layernorm_fwd_multi(x, x_ld, npix, C, g, beta, eps, y, y_ld, stats, round_tf32, st);   // opt-in, layernorm_multi.cu
+    if (rc <= 0) return rc;
+  }
 #define CD_LNF(N) layernorm_kernel<N><<<blocks, 256, 0, st>>>(x, x_ld, npix, C, g, beta, eps, y, y_ld, stats, round_tf32)
   if (slots == 1) CD_LNF(1); else if (slots == 2) CD_LNF(2); else if (slots <= 4) CD_LNF(4); else CD_LNF(8);
 #undef CD_LNF

@@ -34,6 +34,7 @@ CANDIDATES = [
     ('conv_staged_epilogue_all', {'conv_staged_epilogue': 2}),
     ('linattn_staged', {'linattn_staged': 1}),
     ('batched_repack', {'batched_repack': 1}),
+    ('layernorm_multi', {'layernorm_multi': 4}),
     ('merge_micro_batches', {'merge_micro_batches': 1}),
     # the SM-pair convolution kernel is validated; its default (1) follows a tile cost model fitted to batch 32 -- try the extremes
     ('conv_2cta_everywhere', {'conv_2cta': 2}),
@@ -41,7 +42,7 @@ CANDIDATES = [
     # last, because it is tcgen05 code that has never run: if it takes the child down, everything above has been decided
     ('wgrad_bias_fusion', {'wgrad_bias_fusion': 1}),
 ]
-DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
+DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'layernorm_multi': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
 
 
 def apply(settings):
@@ -53,6 +54,8 @@ def apply(settings):
         _lib.lib.cd_conv_tc_set_staged_epilogue(int(settings['conv_staged_epilogue']))
     if 'linattn_staged' in settings:
         _lib.lib.cd_linattn_set_staged(int(settings['linattn_staged']))
+    if 'layernorm_multi' in settings:
+        _lib.lib.cd_layernorm_set_multi(int(settings['layernorm_multi']))
     if 'batched_repack' in settings:
         engine.batched_repack(bool(settings['batched_repack']))
     if 'merge_micro_batches' in settings:

@@ -185,6 +185,9 @@ int cd_wgrad_tc_set_bias_fusion(int enable);
  * bit-identical results): 1 = for launches with at most 16 K chunks of 32 channels per tile (the store-bound 1x1 projections),
  * 2 = for every launch, 3 = at most 48 K chunks */
 int cd_conv_tc_set_staged_epilogue(int mode);
+/* opt-in (default 0, not yet validated on a B200): channel LayerNorm forward for C <= 128 with 2 or 4 pixels per lane group in
+ * flight (csrc/layernorm_multi.cu; same per-pixel arithmetic) */
+int cd_layernorm_set_multi(int pixels_per_group);
 /* opt-in (default 0, not yet validated on a B200): shared-memory-staged kernels behind cd_linattn_weff / cd_linattn_bwd_small
  * (csrc/linattn_small.cu; same arithmetic order as the default kernels) */
 int cd_linattn_set_staged(int enable);

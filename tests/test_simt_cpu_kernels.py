@@ -4,6 +4,7 @@ compared with the numpy statement of the same entry point in tests/abi_emulator.
 goldens by tests/test_model2_host_logic.py.  Catches indexing, reduction and launch-geometry mistakes in the kernels themselves;
 says nothing about performance or about tcgen05 / TMA code (not executable this way)."""
 import ctypes as C
+import ctypes as ctypes_mod
 import os
 import sys
 
@@ -252,3 +253,32 @@ def test_linattn_bwd_kv_remapped_equals_the_default_mapping(cpulib, B, n, ld, dl
     assert E.cd_linattn_bwd_kv(P(qkv), ld, B, n, P(kmax), P(ksum), P(dctxn), P(rowdot), P(want), dld, None) == 0
     assert close(res[1][:, :, 128:384], want[:, :, 128:384], 2e-5)
     assert bool((res[1][:, :, :128] == 7.0).all()) and bool((res[1][:, :, 384:] == 7.0).all())
+
+
+@pytest.mark.parametrize('npix,C,pad,stats,rnd', [(4096, 64, 0, True, 1), (5000, 128, 8, False, 0), (4099, 32, 4, True, 0), (70000, 64, 0, True, 0)])
+def test_layernorm_multi_pixel_forward_equals_the_default_kernel(cpulib, npix, C, pad, stats, rnd):
+    """csrc/layernorm_multi.cu (cd_layernorm_set_multi): 2 / 4 pixels per lane group in flight, same per-pixel arithmetic ->
+    bit-identical to layernorm_kernel<1>, ragged pixel counts and padded rows included"""
+    g = torch.Generator().manual_seed(npix + C)
+    ld = C + pad
+    x = torch.randn(npix, ld, generator=g) * 3 + 0.5
+    gam, bet = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for pp in (0, 2, 4):
+            cpulib.cd_layernorm_set_multi(pp)
+            y, st = torch.full((npix, ld), 7.0), (torch.full((npix, 2), 7.0) if stats else None)
+            assert cpulib.cd_layernorm_fwd(P(x), ld, ctypes_mod.c_int64(npix), C, P(gam), P(bet),
+                                           ctypes_mod.c_float(1e-5), P(y), ld, P(st), rnd, None) == 0
+            res.append((y, st))
+    cpulib.cd_layernorm_set_multi(0)
+    cpulib.simt_set_reverse_order(0)
+    for y, st in res[1:]:
+        assert torch.equal(y, res[0][0])
+        if stats:
+            assert torch.equal(st, res[0][1])
+    assert bool((res[0][0][:, C:] == 7.0).all())
+    xm = x[:, :C].double()
+    want = (xm - xm.mean(1, keepdim=True)) / torch.sqrt(xm.var(1, unbiased=False, keepdim=True) + 1e-5) * gam.double() + bet.double()
+    assert close(res[2][0][:, :C], want.float(), 2e-3 if rnd else 2e-5)

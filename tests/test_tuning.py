@@ -44,7 +44,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
         u = cdm.Unet(dim=32, dim_mults=(1, 2), channels=3)
     u.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd:')})
 
-    state = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'wgrad_bias_fusion': 0}
+    state = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'wgrad_bias_fusion': 0, 'layernorm_multi': 0}
 
     class FakeLib:                                       # the emulator has no kernel variants: record the switches instead
         def cd_conv_tc_set_staged_epilogue(self, v):
@@ -53,6 +53,10 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
 
         def cd_linattn_set_staged(self, v):
             state['linattn_staged'] = v
+            return 0
+
+        def cd_layernorm_set_multi(self, v):
+            state['layernorm_multi'] = v
             return 0
 
         def cd_conv_tc_set_2cta(self, v):
@@ -104,14 +108,14 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     assert rows['merge_micro_batches'].get('accepted') and rows['merge_micro_batches']['err_grad'] < 1e-5    # same gradient, other summation order
     assert rep['accepted'] == {'conv_staged_epilogue': 1, 'batched_repack': 1, 'merge_micro_batches': 1} and rep['best_ms'] == 80.0
     assert not rows['wgrad_bias_fusion'].get('accepted') and rows['wgrad_bias_fusion']['ms'] == 80.0        # right, no gain
-    assert state == {'conv_2cta': 1, 'conv_staged_epilogue': 1, 'linattn_staged': 0, 'wgrad_bias_fusion': 0} and engine.batched_repack() is True      # left applied
+    assert state == {'conv_2cta': 1, 'conv_staged_epilogue': 1, 'linattn_staged': 0, 'wgrad_bias_fusion': 0, 'layernorm_multi': 0} and engine.batched_repack() is True      # left applied
 
     # a candidate that raises ends the search; what was accepted before it stands
     def boom(v):
         raise RuntimeError('CUDA error: an illegal memory access was encountered')
     monkeypatch.setattr(_lib.lib, 'cd_linattn_set_staged', lambda v: boom(v) if v else 0, raising=False)
     reports2 = []
-    rep2 = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports2.append, candidates=[cands[0], cands[2], cands[3]])
+    rep2 = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports2.append, candidates=[c for c in cands if c[0] in ('conv_staged_epilogue_short_k', 'linattn_staged', 'batched_repack')])
     assert 'complete' not in rep2 and rep2['accepted'] == {'conv_staged_epilogue': 1}
     assert rep2['candidates'][-1]['name'] == 'linattn_staged' and 'raised' in rep2['candidates'][-1]['rejected']
 

@@ -356,3 +356,27 @@ def test_autotune_child_validates_every_opt_in_variant_on_this_gpu():
         else:
             assert 'rejected' not in c and c['finite'], c
     assert 'rejected' not in rep.get('sampling', {}), rep.get('sampling')
+
+
+def test_layernorm_multi_pixel_forward_matches_the_default_kernel():
+    """csrc/layernorm_multi.cu (cd_layernorm_set_multi; off by default until this test has passed on a B200): same per-pixel
+    arithmetic as layernorm_kernel<1> -> bit-identical output and statistics"""
+    import ctypes as C
+    from cold_diffusion_models_b200._lib import lib, ptr, stream, _check
+    gen = torch.Generator().manual_seed(4)
+    for npix, Cc, pad in ((32 * 128 * 128, 64, 0), (32 * 64 * 64 + 3, 128, 8), (5000, 32, 4)):
+        ld = Cc + pad
+        x = (torch.randn(npix, ld, generator=gen) * 3 + 0.5).cuda()
+        gam, bet = (1 + 0.2 * torch.randn(Cc, generator=gen)).cuda(), (0.1 * torch.randn(Cc, generator=gen)).cuda()
+        res = []
+        try:
+            for pp in (0, 2, 4):
+                lib.cd_layernorm_set_multi(pp)
+                y, st = torch.full((npix, ld), 7.0, device='cuda'), torch.full((npix, 2), 7.0, device='cuda')
+                _check(lib.cd_layernorm_fwd(ptr(x), ld, C.c_int64(npix), Cc, ptr(gam), ptr(bet), C.c_float(1e-5), ptr(y), ld, ptr(st), 1, stream()), 'ln')
+                torch.cuda.synchronize()
+                res.append((y, st))
+        finally:
+            lib.cd_layernorm_set_multi(0)
+        for y, st in res[1:]:
+            assert torch.equal(y, res[0][0]) and torch.equal(st, res[0][1]), (npix, Cc)
