@@ -177,7 +177,7 @@ def main():
             from cold_diffusion_models_b200 import _lib as _loaded       # this process loads libcolddiff.so too (it runs the fallback)
             assert _loaded.lib.cd_version() == 1
             env = dict(os.environ, COLDDIFF_BENCH_INNER='1')
-            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], capture_output=True, text=True, timeout=1500, env=env)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], capture_output=True, text=True, timeout=900, env=env)
             sys.stderr.write(r.stderr[-4000:])
             for ln in r.stdout.splitlines():
                 if ln.startswith('{') and '"metric"' in ln:
