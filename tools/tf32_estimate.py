@@ -9,6 +9,8 @@ for p in ('', 'tests'):
 import numpy as np, torch
 import abi_emulator
 abi_emulator.TF32_EMULATION = True
+if os.environ.get('COLDDIFF_OPERAND_FORMAT') == 'fp16':      # same estimate with FP16 operands (NOTES.md: FP16-operand option)
+    abi_emulator._tf32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).astype(np.float16).astype(np.float32)
 torch.Tensor.is_cuda = property(lambda self: True)
 torch.Tensor.cuda = lambda self, *a, **k: self
 import cold_diffusion_models_b200 as cdm
