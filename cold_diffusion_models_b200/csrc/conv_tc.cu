@@ -60,8 +60,19 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "}\n" :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
+// kind::f16 (FP16 operands, fp32 accumulate): same descriptors, K = 16 elements = 32 bytes per instruction
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+
 // STG: line-coalesced epilogue through a per-warp shared-memory tile (conv_epilogue.cuh; opt-in, fewer mainloop stages)
-template <int BN, int STAGES, bool STG = false>
+// F16: operand-format probe (cd_conv_fwd_f16_probe): sources and packed weights are FP16 arrays, one 128-byte swizzle row = 64 channels
+template <int BN, int STAGES, bool STG = false, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -70,7 +81,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
-  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(kTileM >> 4) << 24);
+  constexpr uint32_t kFmt = F16 ? 0u : 2u;           // a_format / b_format: 0 = F16 (kind::f16), 2 = TF32 (kind::tf32)
+  constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(kTileM >> 4) << 24);
+  constexpr int kChunkElems = F16 ? 64 : kChunkK;   // elements per 128-byte row
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -128,8 +141,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               mbar_wait(&empty_bar[stage], ph ^ 1u);
               mbar_expect_tx(&full_bar[stage], kStageBytes);
               const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-              tma_load_4d(sa, mA, &full_bar[stage], kc * kChunkK, xin, yin, n0);
-              tma_load_3d(sa + kABytes, mB, &full_bar[stage], kc * kChunkK, co0, wbase + tap);
+              tma_load_4d(sa, mA, &full_bar[stage], kc * kChunkElems, xin, yin, n0);
+              tma_load_3d(sa + kABytes, mB, &full_bar[stage], kc * kChunkElems, co0, wbase + tap);
             }
           }
         }
@@ -153,7 +166,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {          // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row
-            mma_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
+            if constexpr (F16) mma_f16(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
+            else mma_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);             // frees the smem slot once these MMAs retire
         }
@@ -290,17 +304,17 @@ int g_num_sms = 0;
 int g_tf32_map_dtype = 1;   // 1: TFLOAT32 tensor maps -- the TMA unit rounds fp32->tf32 (RN) on load (measured: profiles/tf32_probe_r01.txt); 0: FLOAT32 (MMA truncates)
 
 
-template <int BN, int STAGES, bool STG = false>
+template <int BN, int STAGES, bool STG = false, bool F16 = false>
 int launch(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = size_t(STAGES) * (kABytes + BN * 128) + 1024 + 256 + (STG ? sizeof(float) * kEpiWarps * kEpiStageFloats : 0);
   static_assert(smem <= 232448, "dynamic shared memory of one CTA (227 KB)");
   static bool attr_done = false;
   if (!attr_done) {
-    CD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_tc_kernel<BN, STAGES, STG><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  conv_tc_kernel<BN, STAGES, STG, F16><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   CD_LAUNCH_CHECK();
   return 0;
 }
@@ -333,7 +347,19 @@ static double tc_cost(long long m_tiles, int Cout, int BN, bool pair, int sms) {
   return double((tiles + sms - 1) / sms) * BN / rate;
 }
 
-int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
+static int conv_fwd_tc_impl(const CdConvDesc* d, cudaStream_t st, bool f16);
+int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) { return conv_fwd_tc_impl(d, st, false); }
+
+// Operand-format probe (tools/conv_f16_probe.py; not used by the engine): the same convolution with FP16 sources and FP16 packed
+// weights (src / w point to __half arrays, ld and the weight strides count elements), fp32 accumulate and the fp32 epilogue.
+extern "C" int cd_conv_fwd_f16_probe(const CdConvDesc* d, void* stream) {
+  CD_REQUIRE(d != nullptr && d->nsrc >= 1 && d->nsrc <= 2, "cd_conv_fwd_f16_probe: bad descriptor");
+  return conv_fwd_tc_impl(d, static_cast<cudaStream_t>(stream), true);
+}
+
+static int conv_fwd_tc_impl(const CdConvDesc* d, cudaStream_t st, bool f16) {
+  const int chunk_elems = f16 ? 64 : kChunkK;
+  const int esz = f16 ? 2 : 4;
   EncodeTiledFn enc = get_encode();
   CD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   if (!g_num_sms) {
@@ -359,9 +385,10 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   p.tiles_x = d->Wg / p.TW; p.tiles_y = d->Hg / p.TH; p.tiles_n = cd_cdiv(d->B, p.TN);
   int BN = (d->Cout % 256 == 0) ? 256 : (d->Cout > 64 ? 128 : 64);
   int kiters_host = 0;
-  for (int s = 0; s < d->nsrc; ++s) kiters_host += d->s[s].ntaps * (d->s[s].C / kChunkK);
-  const bool staged = g_epi_staged == 2 || (g_epi_staged == 1 && kiters_host <= kStagedMaxKIters) ||
-                      (g_epi_staged == 3 && kiters_host <= kStagedMidKIters);
+  for (int s = 0; s < d->nsrc; ++s) kiters_host += d->s[s].ntaps * (d->s[s].C / chunk_elems);
+  const bool staged = !f16 &&
+                      ( g_epi_staged == 2 || (g_epi_staged == 1 && kiters_host <= kStagedMaxKIters) ||
+                      (g_epi_staged == 3 && kiters_host <= kStagedMidKIters));
   if (BN == 256 && staged) {
     // short K: the narrower tile only when it saves whole waves (same rule as below), never the SM-pair kernel
     const long long mt = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
@@ -371,7 +398,7 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
     const long long mt = static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n;
     double best = tc_cost(mt, d->Cout, 256, false, g_num_sms);
     if (tc_cost(mt, d->Cout, 128, false, g_num_sms) < best) { BN = 128; best = tc_cost(mt, d->Cout, 128, false, g_num_sms); }
-    if (g_use_2cta && g_tf32_map_dtype && mt >= 2 && (g_use_2cta == 2 || tc_cost(mt, d->Cout, 256, true, g_num_sms) < best)) {
+    if (!f16 && g_use_2cta && g_tf32_map_dtype && mt >= 2 && (g_use_2cta == 2 || tc_cost(mt, d->Cout, 256, true, g_num_sms) < best)) {
       const int r2 = cd_conv_fwd_tc2(d, st);
       if (r2 <= 0) return r2;                                 // 1 = not eligible: stay on the 1-CTA kernel
     }
@@ -393,20 +420,20 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
   CD_REQUIRE(!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "conv_tc: bias alignment");
 
   CUtensorMap maps[4];
-  const CUtensorMapDataType dt = g_tf32_map_dtype ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : (g_tf32_map_dtype ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   for (int s = 0; s < 2; ++s) {
     const CdConvSrc& cs = d->s[s < d->nsrc ? s : 0];
-    CD_REQUIRE(cs.C % kChunkK == 0 && cs.C > 0, "conv_tc: source channels %d not a multiple of 32", cs.C);
+    CD_REQUIRE(cs.C % chunk_elems == 0 && cs.C > 0, "conv_tc: source channels %d not a multiple of %d", cs.C, chunk_elems);
     CD_REQUIRE(cs.ntaps >= 1 && cs.ntaps <= CD_MAX_TAPS, "conv_tc: bad ntaps");
-    CD_REQUIRE((reinterpret_cast<uintptr_t>(cs.src) & 15) == 0 && cs.ld % 4 == 0, "conv_tc: src must be 16B aligned");
+    CD_REQUIRE((reinterpret_cast<uintptr_t>(cs.src) & 15) == 0 && (cs.ld * esz) % 16 == 0, "conv_tc: src must be 16B aligned");
     CD_REQUIRE((reinterpret_cast<uintptr_t>(cs.w) & 15) == 0, "conv_tc: weights must be 16B aligned");
     CD_REQUIRE(!cs.w_per_batch || p.TN == 1, "conv_tc: per-batch weights need >=128 pixels per image");
-    p.ntaps[s] = cs.ntaps; p.kchunks[s] = cs.C / kChunkK; p.wpb[s] = cs.w_per_batch;
+    p.ntaps[s] = cs.ntaps; p.kchunks[s] = cs.C / chunk_elems; p.wpb[s] = cs.w_per_batch;
     for (int t = 0; t < cs.ntaps; ++t) { p.dy[s][t] = (int8_t)cs.dy[t]; p.dx[s][t] = (int8_t)cs.dx[t]; }
     {   // A: NHWC activations, dims {C, W, H, N}
       cuuint64_t dims[4] = {(cuuint64_t)cs.C, (cuuint64_t)cs.W, (cuuint64_t)cs.H, (cuuint64_t)d->B};
-      cuuint64_t strides[3] = {(cuuint64_t)cs.ld * 4, (cuuint64_t)cs.ld * 4 * cs.W, (cuuint64_t)cs.ld * 4 * cs.W * cs.H};
-      cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)(p.TW * d->sx), (cuuint32_t)(p.TH * d->sy), (cuuint32_t)p.TN};
+      cuuint64_t strides[3] = {(cuuint64_t)cs.ld * esz, (cuuint64_t)cs.ld * esz * cs.W, (cuuint64_t)cs.ld * esz * cs.W * cs.H};
+      cuuint32_t box[4] = {(cuuint32_t)chunk_elems, (cuuint32_t)(p.TW * d->sx), (cuuint32_t)(p.TH * d->sy), (cuuint32_t)p.TN};
       cuuint32_t estr[4] = {1, (cuuint32_t)d->sx, (cuuint32_t)d->sy, 1};
       CUresult r = enc(&maps[s], dt, 4, const_cast<float*>(cs.src), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -416,14 +443,19 @@ int cd_conv_fwd_tc(const CdConvDesc* d, cudaStream_t st) {
     {   // B: packed weights, dims {Cin, Cout, ntaps * (per-batch ? B : 1)}
       const int BNl = BN;
       cuuint64_t dims[3] = {(cuuint64_t)cs.C, (cuuint64_t)d->Cout, (cuuint64_t)cs.ntaps * (cs.w_per_batch ? d->B : 1)};
-      cuuint64_t strides[2] = {(cuuint64_t)cs.C * 4, (cuuint64_t)cs.C * 4 * d->Cout};
-      cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)BNl, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)cs.C * esz, (cuuint64_t)cs.C * esz * d->Cout};
+      cuuint32_t box[3] = {(cuuint32_t)chunk_elems, (cuuint32_t)BNl, 1};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = enc(&maps[2 + s], dt, 3, const_cast<float*>(cs.w), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       CD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B%d) failed: %d", s, (int)r);
     }
+  }
+  if (f16) {
+    if (BN == 256) return launch<256, 4, false, true>(maps, p, st);
+    if (BN == 128) return launch<128, 6, false, true>(maps, p, st);
+    return launch<64, 8, false, true>(maps, p, st);
   }
   if (staged) {          // 72 KB of epilogue staging: 3 / 4 / 6 mainloop stages instead of 4 / 6 / 8
     if (BN == 256) return launch<256, 3, true>(maps, p, st);

@@ -181,6 +181,10 @@ int cd_wgrad_tc_set_mode(int mode);
 int cd_wgrad_tc_set_split(int policy, int over_clk);
 /* opt-in (default 0, not yet validated on a B200): fold the bias gradient (column sums of dY) into the tcgen05 weight gradient */
 int cd_wgrad_tc_set_bias_fusion(int enable);
+/* EXPERIMENTAL operand-format probe, not used by the engine (tools/conv_f16_probe.py): cd_conv_fwd with impl = CD_CONV_TC on FP16
+ * operands -- d->s[i].src and d->s[i].w point to __half arrays (ld and the packed-weight layout count elements, C % 64 == 0),
+ * tcgen05.mma.kind::f16 with fp32 accumulation, fp32 epilogue and outputs as usual. */
+int cd_conv_fwd_f16_probe(const CdConvDesc* d, void* stream);
 /* opt-in (default 0, not yet validated on a B200): line-coalesced epilogue of the tcgen05 convolution (csrc/conv_epilogue.cuh;
  * bit-identical results): 1 = for launches with at most 16 K chunks of 32 channels per tile (the store-bound 1x1 projections),
  * 2 = for every launch, 3 = at most 48 K chunks */

@@ -380,3 +380,18 @@ def test_layernorm_multi_pixel_forward_matches_the_default_kernel():
             lib.cd_layernorm_set_multi(0)
         for y, st in res[1:]:
             assert torch.equal(y, res[0][0]) and torch.equal(st, res[0][1]), (npix, Cc)
+
+
+def test_fp16_operand_probe_agrees_with_the_tf32_kernel():
+    """cd_conv_fwd_f16_probe (experimental, not used by the engine; tools/conv_f16_probe.py): kind::f16 MMAs on FP16 operands give
+    the TF32 kernel's result when both multiply the same (FP16-representable) values.  Child process with a time limit: tcgen05
+    code that has never run."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'conv_f16_probe.py'), '--check'], capture_output=True, text=True, timeout=600)
+    except subprocess.TimeoutExpired as e:
+        pytest.fail('fp16 probe hung (killed after 600 s): %s' % str(e.stdout)[-500:])
+    assert r.returncode == 0 and 'F16_PROBE_OK' in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])

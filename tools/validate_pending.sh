@@ -32,5 +32,7 @@ TMO=300 step bench_everything_on       env COLDDIFF_CONV_STAGED_EPILOGUE=1 COLDD
 # convolution launches (source-level: does the epilogue still dominate?).  Copy the summaries into profiles/ (see profiles/README.md)
 TMO=400 step ncu_launches_staged env COLDDIFF_CONV_STAGED_EPILOGUE=2 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $out/launches_step_staged.csv python tools/one_step.py
 TMO=400 step ncu_full_staged     env COLDDIFF_CONV_STAGED_EPILOGUE=2 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:conv_tc_kernel -c 6 -o $out/conv_staged_full -f python tools/one_step.py
+# FP16-operand probe: per-shape time of the kind::f16 instantiation against the TF32 kernel on the same values (NOTES.md, FP16 option)
+TMO=300 step conv_f16_probe      python tools/conv_f16_probe.py
 grep -h '"metric"' $out/bench.log $out/bench_no_autotune.log $out/eager_comparator.log $out/bench_batched_repack.log $out/bench_all_switches.log $out/bench_staged_epilogue.log $out/bench_everything_on.log > $out/bench_lines.json 2>/dev/null
 cat $out/summary.txt
