@@ -10,6 +10,11 @@ from test_unet_gpu import load, rel, make_unet
 
 pytestmark = pytest.mark.gpu
 
+# Opt-in kernel variants that ship OFF and have never run on a B200 (NOTES.md): their outcome is recorded (XPASS = validated on this
+# run, XFAIL = see the assertion) without turning the suite of the default, validated kernels red.  bench.py's `tuning` report records
+# the same per-variant verdicts independently.
+OPT_IN = pytest.mark.xfail(reason='opt-in kernel variant, default off, not yet validated on a B200', strict=False)
+
 
 @pytest.fixture(scope='module')
 def small():
@@ -193,6 +198,7 @@ def test_evaluation_routines_on_the_gpu(unet, tmp_path, monkeypatch):
     assert float(ssim(a.cuda(), b.cuda(), data_range=1)) == pytest.approx(float(ssim(a, b, data_range=1)), abs=1e-5)
 
 
+@OPT_IN
 def test_batched_repack_matches_the_single_launches():
     """csrc/repack.cu (one launch for all weight repacks / packed-gradient unpacks, COLDDIFF_BATCHED_REPACK; off by default until
     this test has passed on a B200): bit-exact against the single-weight entry points on a job table that takes every branch,
@@ -242,6 +248,7 @@ def test_batched_repack_matches_the_single_launches():
         assert rel(grads[1][n], grads[0][n]) < 2e-3, n
 
 
+@OPT_IN
 def test_linattn_staged_kernels_match_the_default_ones():
     """csrc/linattn_small.cu (cd_linattn_set_staged / COLDDIFF_LINATTN_STAGED; off by default until this test has passed on a
     B200): same arithmetic order as the default kernels, so weff / dctxn / rowdot are bit-identical and dW_out (float atomics over
@@ -288,6 +295,32 @@ def test_linattn_staged_kernels_match_the_default_ones():
         assert torch.equal(outs[0], outs[1]), (B, n)
 
 
+@OPT_IN
+def test_layernorm_multi_pixel_forward_matches_the_default_kernel():
+    """csrc/layernorm_multi.cu (cd_layernorm_set_multi; off by default until this test has passed on a B200): same per-pixel
+    arithmetic as layernorm_kernel<1> -> bit-identical output and statistics"""
+    import ctypes as C
+    from cold_diffusion_models_b200._lib import lib, ptr, stream, _check
+    gen = torch.Generator().manual_seed(4)
+    for npix, Cc, pad in ((32 * 128 * 128, 64, 0), (32 * 64 * 64 + 3, 128, 8), (5000, 32, 4)):
+        ld = Cc + pad
+        x = (torch.randn(npix, ld, generator=gen) * 3 + 0.5).cuda()
+        gam, bet = (1 + 0.2 * torch.randn(Cc, generator=gen)).cuda(), (0.1 * torch.randn(Cc, generator=gen)).cuda()
+        res = []
+        try:
+            for pp in (0, 2, 4):
+                lib.cd_layernorm_set_multi(pp)
+                y, st = torch.full((npix, ld), 7.0, device='cuda'), torch.full((npix, 2), 7.0, device='cuda')
+                _check(lib.cd_layernorm_fwd(ptr(x), ld, C.c_int64(npix), Cc, ptr(gam), ptr(bet), C.c_float(1e-5), ptr(y), ld, ptr(st), 1, stream()), 'ln')
+                torch.cuda.synchronize()
+                res.append((y, st))
+        finally:
+            lib.cd_layernorm_set_multi(0)
+        for y, st in res[1:]:
+            assert torch.equal(y, res[0][0]) and torch.equal(st, res[0][1]), (npix, Cc)
+
+
+@OPT_IN
 def test_conv_staged_epilogue_matches_the_row_epilogue():
     """runs _conv_staged_epilogue_body in a child process with a time limit: the kernel variant it enables has never run on a
     B200, and a tcgen05 / mbarrier pipeline that went wrong would spin instead of failing -- that must not take the session's
@@ -339,6 +372,24 @@ def _conv_staged_epilogue_body():
         lib.cd_conv_tc_set_staged_epilogue(0)
 
 
+@OPT_IN
+def test_fp16_operand_probe_agrees_with_the_tf32_kernel():
+    """cd_conv_fwd_f16_probe (experimental, not used by the engine; tools/conv_f16_probe.py): kind::f16 MMAs on FP16 operands give
+    the TF32 kernel's result when both multiply the same (FP16-representable) values.  Child process with a time limit: tcgen05
+    code that has never run."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'conv_f16_probe.py'), '--check'], capture_output=True, text=True, timeout=600)
+    except subprocess.TimeoutExpired as e:
+        pytest.fail('fp16 probe hung (killed after 600 s): %s' % str(e.stdout)[-500:])
+    assert r.returncode == 0 and 'F16_PROBE_OK' in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+
+@OPT_IN
 def test_autotune_child_validates_every_opt_in_variant_on_this_gpu():
     """cold_diffusion_models_b200.tuning.autotune on the small network: the child must complete, and every opt-in variant must
     reproduce the default kernels' output and gradients (whether it is also faster, i.e. accepted, depends on the sizes)"""
@@ -356,42 +407,3 @@ def test_autotune_child_validates_every_opt_in_variant_on_this_gpu():
         else:
             assert 'rejected' not in c and c['finite'], c
     assert 'rejected' not in rep.get('sampling', {}), rep.get('sampling')
-
-
-def test_layernorm_multi_pixel_forward_matches_the_default_kernel():
-    """csrc/layernorm_multi.cu (cd_layernorm_set_multi; off by default until this test has passed on a B200): same per-pixel
-    arithmetic as layernorm_kernel<1> -> bit-identical output and statistics"""
-    import ctypes as C
-    from cold_diffusion_models_b200._lib import lib, ptr, stream, _check
-    gen = torch.Generator().manual_seed(4)
-    for npix, Cc, pad in ((32 * 128 * 128, 64, 0), (32 * 64 * 64 + 3, 128, 8), (5000, 32, 4)):
-        ld = Cc + pad
-        x = (torch.randn(npix, ld, generator=gen) * 3 + 0.5).cuda()
-        gam, bet = (1 + 0.2 * torch.randn(Cc, generator=gen)).cuda(), (0.1 * torch.randn(Cc, generator=gen)).cuda()
-        res = []
-        try:
-            for pp in (0, 2, 4):
-                lib.cd_layernorm_set_multi(pp)
-                y, st = torch.full((npix, ld), 7.0, device='cuda'), torch.full((npix, 2), 7.0, device='cuda')
-                _check(lib.cd_layernorm_fwd(ptr(x), ld, C.c_int64(npix), Cc, ptr(gam), ptr(bet), C.c_float(1e-5), ptr(y), ld, ptr(st), 1, stream()), 'ln')
-                torch.cuda.synchronize()
-                res.append((y, st))
-        finally:
-            lib.cd_layernorm_set_multi(0)
-        for y, st in res[1:]:
-            assert torch.equal(y, res[0][0]) and torch.equal(st, res[0][1]), (npix, Cc)
-
-
-def test_fp16_operand_probe_agrees_with_the_tf32_kernel():
-    """cd_conv_fwd_f16_probe (experimental, not used by the engine; tools/conv_f16_probe.py): kind::f16 MMAs on FP16 operands give
-    the TF32 kernel's result when both multiply the same (FP16-representable) values.  Child process with a time limit: tcgen05
-    code that has never run."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    try:
-        r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'conv_f16_probe.py'), '--check'], capture_output=True, text=True, timeout=600)
-    except subprocess.TimeoutExpired as e:
-        pytest.fail('fp16 probe hung (killed after 600 s): %s' % str(e.stdout)[-500:])
-    assert r.returncode == 0 and 'F16_PROBE_OK' in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
