@@ -223,8 +223,12 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
             if row['finite'] and ey <= tol_y and eg <= tol_g:
                 timer(step, 1)
                 ms = timer(step, steps)
-                row['ms'] = ms
-                if ms < (1.0 - min_gain) * best_ms:
+                # A/B: the configuration accepted so far is timed again right after the candidate (clocks drift over the run)
+                apply(dict(DEFAULTS, **accepted))
+                timer(step, 1)
+                ref = timer(step, steps)
+                row['ms'], row['ms_reference'] = ms, ref
+                if ms < (1.0 - min_gain) * ref:
                     accepted, best_ms = trial, ms
                     row['accepted'] = True
             else:
