@@ -310,6 +310,9 @@ def main():
     S = args.sample_steps
     ema.denoise_fn.eval()
     graph_sampling = bool(tuned['report'].get('sampling_cuda_graph'))
+    samp_sw = dict(tuned['report'].get('accepted_sampling') or {})      # forward-only variants accepted on the inference forward
+    if samp_sw:
+        tuning.apply(dict(tuning.DEFAULTS, **dict(tuned['accepted'], **samp_sw)))
     if graph_sampling:                       # the child found the CUDA-graph replay of the inference forward equal and faster
         ema.denoise_fn.engine.enable_cuda_graph(True)
     xs = resident[0]
@@ -329,6 +332,8 @@ def main():
     sample_ms_per_rev_step = ms_s / S
     if graph_sampling:
         ema.denoise_fn.engine.enable_cuda_graph(False)
+    if samp_sw:
+        tuning.apply(dict(tuning.DEFAULTS, **tuned['accepted']))
     sample_img_s = B * world / (sample_ms_per_rev_step * C3['timesteps'] / 1e3)
 
     # ---- the other BASELINE configs that fit one GPU, as context (rank 0 only; not the headline, bounded to a few steps) ----
@@ -498,7 +503,8 @@ def main():
             "other_configs": others,
             "op_profile": op_profile,
             "tuning": {"accepted": tuned['accepted'], "merge_micro_batches_validated": merge_ok,
-                       "report": {k: v for k, v in tuned['report'].items() if k in ('default_ms', 'best_ms', 'sampling', 'sampling_cuda_graph', 'noise', 'tolerance', 'seconds', 'error',
+                       "report": {k: v for k, v in tuned['report'].items() if k in ('default_ms', 'best_ms', 'sampling', 'sampling_cuda_graph', 'accepted_sampling', 'sampling_candidates',
+                                                                                    'sampling_candidates_error', 'inference_forward', 'noise', 'tolerance', 'seconds', 'error',
                                                                                     'error_after', 'skipped', 'complete', 'child_exit', 'stderr_tail')},
                        "candidates": [{k: c.get(k) for k in ('name', 'ms', 'err_output', 'err_grad', 'accepted', 'rejected')}
                                       for c in tuned['report'].get('candidates', [])],

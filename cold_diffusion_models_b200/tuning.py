@@ -43,6 +43,9 @@ CANDIDATES = [
     # evaluated on top of everything else and reported separately by bench.py (it changes the shape of the step, not a kernel)
     ('merge_micro_batches', {'merge_micro_batches': 1}),
 ]
+# candidates that change forward kernels (tried again on the inference forward alone)
+FORWARD_CANDIDATES = ('conv_staged_epilogue_short_k', 'conv_staged_epilogue_mid_k', 'conv_staged_epilogue_all', 'linattn_staged', 'layernorm_multi',
+                      'conv_2cta_everywhere', 'conv_2cta_off')
 DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'layernorm_multi': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
 
 
@@ -264,6 +267,50 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
         report['accepted'], report['best_ms'] = accepted, best_ms
         emit(report)
     apply(dict(DEFAULTS, **accepted))
+    # ---- forward-only decisions for the sampling loops: a variant that only touches forward kernels can be worth 3 % of a reverse
+    # step and still disappear in the noise of a training step; candidates not accepted above are tried again on the no_grad forward
+    samp = {}
+    if sampling_graph:
+        try:
+            with torch.no_grad():
+                fwd = lambda: unet(x[0], t[0])
+                apply(DEFAULTS)
+                yd = fwd().clone()
+                yd2 = fwd().clone()
+                sync()
+                tol = max(1e-4, 8 * rel(yd2, yd))
+                rows = []
+                for name, sw in candidates:
+                    if name not in FORWARD_CANDIDATES or all(accepted.get(k) == v for k, v in sw.items()):
+                        continue
+                    row = {'name': name}
+                    trial = dict(accepted, **samp)
+                    trial.update(sw)
+                    apply(dict(DEFAULTS, **trial))
+                    ya = fwd().clone()
+                    ya = fwd().clone()
+                    sync()
+                    row['err_output'] = rel(ya, yd)
+                    if row['err_output'] <= tol and bool(torch.isfinite(ya).all().item()):
+                        timer(fwd, 1)
+                        ms = timer(fwd, 2 * steps)
+                        apply(dict(DEFAULTS, **dict(accepted, **samp)))
+                        timer(fwd, 1)
+                        ref = timer(fwd, 2 * steps)
+                        row['ms'], row['ms_reference'] = ms, ref
+                        if ms < (1.0 - min_gain) * ref:
+                            samp.update(sw)
+                            row['accepted'] = True
+                    else:
+                        row['rejected'] = 'results differ from the default kernels'
+                    rows.append(row)
+                report['sampling_candidates'] = rows
+        except Exception as e:
+            report['sampling_candidates_error'] = repr(e)[:200]
+            samp = {}
+        report['accepted_sampling'] = samp
+        emit(report)
+    apply(dict(DEFAULTS, **dict(accepted, **samp)))
     # ---- CUDA-graph replay of that forward (engine.enable_cuda_graph) against the eager launches -----
     if sampling_graph:
         row = {'name': 'sampling_cuda_graph'}
@@ -295,6 +342,7 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
         except Exception as e:
             row['rejected'] = 'raised: ' + repr(e)[:200]
         report['sampling'] = row
+    apply(dict(DEFAULTS, **accepted))
     report['complete'] = True
     emit(report)
     return report

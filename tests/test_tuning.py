@@ -161,3 +161,38 @@ def test_trainer_step_over_merged_micro_batches_equals_the_accumulated_one(emu, 
     for k in out[0][0]:
         r = ((out[0][0][k].double() - out[1][0][k].double()).norm() / (out[0][0][k].double().norm() + 1e-30)).item()
         assert r < 1e-5, (k, r)
+
+
+def test_forward_only_variants_get_a_second_chance_on_the_inference_forward(emu, monkeypatch):
+    """a variant that is in the noise of a training step but measurably faster on the no_grad forward is accepted for sampling
+    only (`accepted_sampling`); the CUDA-graph check cannot run on the CPU and is recorded as rejected, nothing else is affected"""
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200 import tuning, _lib
+    z = np.load(os.path.join(G, 'unet_small.npz'))
+    g = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+    with contextlib.redirect_stdout(io.StringIO()):
+        u = cdm.Unet(dim=32, dim_mults=(1, 2), channels=3)
+    u.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd:')})
+    state = {}
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def setter(v, _n=name):
+                state[_n] = v
+                return 0
+            return setter
+    monkeypatch.setattr(_lib, 'lib', FakeLib())
+
+    def timer(fn, n):
+        if torch.is_grad_enabled():
+            return 100.0 - (10 if state.get('cd_conv_tc_set_staged_epilogue') == 1 else 0)      # layernorm_multi: no visible gain
+        return 10.0 - (1 if state.get('cd_layernorm_set_multi') else 0) + (2 if state.get('cd_linattn_set_staged') else 0)
+    cands = [c for c in tuning.CANDIDATES if c[0] in ('conv_staged_epilogue_short_k', 'linattn_staged', 'layernorm_multi')]
+    rep = tuning.run_candidates(u, [g['x']], [g['target']], [g['t']], lambda: None, timer, 1, lambda r: None, candidates=cands,
+                                sampling_graph=True)
+    assert rep['complete'] and rep['accepted'] == {'conv_staged_epilogue': 1}
+    assert rep['accepted_sampling'] == {'layernorm_multi': 4}
+    names = [r['name'] for r in rep['sampling_candidates']]
+    assert names == ['linattn_staged', 'layernorm_multi']            # the one accepted for training is not tried again
+    assert 'rejected' in rep['sampling'] and not rep.get('sampling_cuda_graph')
+    assert state['cd_layernorm_set_multi'] == 0 and state['cd_conv_tc_set_staged_epilogue'] == 1       # training switches left applied
