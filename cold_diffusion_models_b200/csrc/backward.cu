@@ -282,6 +282,25 @@ attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __
     const int p0 = (blockIdx.x * tiles + tile) * kKvPix;
     if (p0 >= n) break;
     __syncthreads();                                 // previous tile consumed (and dc staged)
+    if constexpr (REMAP) {        // all 32 loads of the tile in flight before the first use (see context_kernel<PRELOAD>)
+      float kr[kKvPix / 2], vr[kKvPix / 2];
+#pragma unroll
+      for (int u = 0; u < kKvPix / 2; ++u) {
+        const int p = p0 + lhalf + 2 * u;
+        kr[u] = 0.f; vr[u] = 0.f;
+        if (p < n) {
+          const float* row = qkv + (static_cast<long long>(b) * n + p) * ld;
+          kr[u] = row[128 + lc];
+          vr[u] = row[256 + lc];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kKvPix / 2; ++u) {
+        const int pp = lhalf + 2 * u;
+        psT[lc * kKvStride + pp] = (p0 + pp < n) ? __expf(kr[u] - kmx) * kinv : 0.f;
+        vsT[lc * kKvStride + pp] = vr[u];
+      }
+    } else {
     for (int pp = lhalf; pp < kKvPix; pp += 2) {
       const int p = p0 + pp;
       float pv = 0.f, vv = 0.f;
@@ -291,6 +310,7 @@ attn_bwd_kv_kernel(const float* __restrict__ qkv, int ld, int n, const float* __
         vv = row[256 + lc];
       }
       psT[lc * kKvStride + pp] = pv; vsT[lc * kKvStride + pp] = vv;
+    }
     }
     __syncthreads();
     float dk[4][4] = {}, dv[4][4] = {};               // [pixel][channel]

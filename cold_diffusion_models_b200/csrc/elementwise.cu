@@ -587,6 +587,10 @@ kmax_kernel(const float* __restrict__ qkv, int ld, int n, int pix_per_block, flo
 }
 
 constexpr int kCtxP = 32;   // pixels per smem chunk
+// PRELOAD (opt-in, cd_linattn_set_staged): the 16 k and 16 v values a thread stages per chunk are all requested before the first
+// exp / store instead of one dependent load -> exp -> store round trip per pixel (the loop is not unrolled by the compiler because of
+// its bounds check: ~16 exposed memory latencies per chunk).  Same values, same order of the ksum partial sums.
+template <bool PRELOAD>
 __global__ void __launch_bounds__(256)
 context_kernel(const float* __restrict__ qkv, int ld, int n, int pix_per_block, const float* __restrict__ kmax,
                float* __restrict__ ksum, float* __restrict__ ctx) {
@@ -602,6 +606,25 @@ context_kernel(const float* __restrict__ qkv, int ld, int n, int pix_per_block, 
   float acc[4][4] = {};
   float esum = 0.f;
   for (int q0 = p0; q0 < p1; q0 += kCtxP) {
+    if constexpr (PRELOAD) {
+      float kr[kCtxP / 2], vr[kCtxP / 2];
+#pragma unroll
+      for (int u = 0; u < kCtxP / 2; ++u) {
+        const int p = q0 + lhalf + 2 * u;
+        kr[u] = 0.f; vr[u] = 0.f;
+        if (p < p1) {
+          const float* row = qkv + (static_cast<long long>(b) * n + p) * ld;
+          kr[u] = row[128 + lc];
+          vr[u] = row[256 + lc];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kCtxP / 2; ++u) {
+        const int pp = lhalf + 2 * u;
+        const float e = (q0 + pp < p1) ? __expf(kr[u] - mx) : 0.f;
+        es[pp][lc] = e; vs[pp][lc] = vr[u]; esum += e;
+      }
+    } else {
     for (int pp = lhalf; pp < kCtxP; pp += 2) {
       const int p = q0 + pp;
       float e = 0.f, v = 0.f;
@@ -611,6 +634,7 @@ context_kernel(const float* __restrict__ qkv, int ld, int n, int pix_per_block, 
         v = row[256 + lc];
       }
       es[pp][lc] = e; vs[pp][lc] = v; esum += e;
+    }
     }
     __syncthreads();
 #pragma unroll 4
@@ -829,7 +853,7 @@ extern "C" int cd_linattn_context(const float* qkv, int ld, int B, int n, float*
     int dev = 0, sms = 0, occ = 0;
     CD_CUDA(cudaGetDevice(&dev));
     CD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, context_kernel, 256, 0));
+    CD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, context_kernel<false>, 256, 0));
     slots = sms * (occ > 0 ? occ : 1);
   }
   int per_img = slots / (B > 0 ? B : 1); if (per_img < 1) per_img = 1;
@@ -838,7 +862,8 @@ extern "C" int cd_linattn_context(const float* qkv, int ld, int B, int n, float*
   dim3 grid(cd_cdiv(n, ppb), B);
   kmax_kernel<<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax);
   CD_LAUNCH_CHECK();
-  context_kernel<<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax, ksum, ctx);
+  if (cd_linattn_staged_enabled(nullptr, nullptr)) context_kernel<true><<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax, ksum, ctx);
+  else context_kernel<false><<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax, ksum, ctx);
   CD_LAUNCH_CHECK();
   return 0;
 }

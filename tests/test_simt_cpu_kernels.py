@@ -282,3 +282,26 @@ def test_layernorm_multi_pixel_forward_equals_the_default_kernel(cpulib, npix, C
     xm = x[:, :C].double()
     want = (xm - xm.mean(1, keepdim=True)) / torch.sqrt(xm.var(1, unbiased=False, keepdim=True) + 1e-5) * gam.double() + bet.double()
     assert close(res[2][0][:, :C], want.float(), 2e-3 if rnd else 2e-5)
+
+
+@pytest.mark.parametrize('B,n,ld', [(2, 256, 384), (1, 1000, 392), (3, 40, 384)])
+def test_linattn_context_preload_variant_equals_the_default(cpulib, B, n, ld):
+    """context_kernel<PRELOAD> (cd_linattn_set_staged): all loads of a chunk requested before the first use; the same values and
+    the same order of partial sums -> kmax / ksum / ctx bit-identical on the CPU executor (deterministic block order)"""
+    g = torch.Generator().manual_seed(n + ld)
+    qkv = torch.randn(B, n, ld, generator=g)
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for staged in (0, 1):
+            cpulib.cd_linattn_set_staged(staged)
+            kmax, ksum, ctx = torch.full((B, 128), 7.0), torch.full((B, 128), 7.0), torch.full((B, 4, 32, 32), 7.0)
+            assert cpulib.cd_linattn_context(P(qkv), ld, B, n, P(kmax), P(ksum), P(ctx), C.c_void_p(0)) == 0
+            res.append(torch.cat([kmax.reshape(-1), ksum.reshape(-1), ctx.reshape(-1)]))
+    cpulib.cd_linattn_set_staged(0)
+    cpulib.simt_set_reverse_order(0)
+    assert torch.equal(res[0], res[1]) and torch.equal(res[2], res[3])          # per thread order: staged == default
+    assert close(res[1], res[3], 1e-5)                                           # across thread orders the float atomics reorder
+    kmax, ksum, ctx = torch.zeros(B, 128), torch.zeros(B, 128), torch.zeros(B, 4, 32, 32)
+    assert E.cd_linattn_context(P(qkv), ld, B, n, P(kmax), P(ksum), P(ctx), None) == 0
+    assert close(res[1], torch.cat([kmax.reshape(-1), ksum.reshape(-1), ctx.reshape(-1)]), 2e-5)

@@ -293,6 +293,18 @@ def test_linattn_staged_kernels_match_the_default_ones():
         finally:
             lib.cd_linattn_set_staged(0)
         assert torch.equal(outs[0], outs[1]), (B, n)
+        # context_kernel<PRELOAD>: same values and partial sums; float atomics across blocks -> agreement to rounding
+        cres = []
+        try:
+            for staged in (0, 1):
+                lib.cd_linattn_set_staged(staged)
+                km, ks, cx = torch.empty(B, 128, device='cuda'), torch.empty(B, 128, device='cuda'), torch.empty(B, 4, 32, 32, device='cuda')
+                _check(lib.cd_linattn_context(ptr(qkv), 384, B, n, ptr(km), ptr(ks), ptr(cx), stream()), 'context')
+                torch.cuda.synchronize()
+                cres.append((km, ks, cx))
+        finally:
+            lib.cd_linattn_set_staged(0)
+        assert torch.equal(cres[0][0], cres[1][0]) and rel(cres[1][1], cres[0][1]) < 1e-5 and rel(cres[1][2], cres[0][2]) < 1e-5, (B, n)
 
 
 @OPT_IN
