@@ -848,21 +848,24 @@ extern "C" int cd_linattn_context(const float* qkv, int ld, int B, int n, float*
   }
   // pixels per block: one wave of resident blocks over the whole batch (a fixed 512 left the 64x64 level with 256 blocks
   // and the 128x128 level with 1.15 waves); any value is correct, the kernels clamp to n and zero-fill the last chunk
-  static int slots = 0;
-  if (!slots) {
+  const int variant = cd_linattn_staged_enabled(nullptr, nullptr) ? 1 : 0;     // the PRELOAD kernel holds 32 more registers
+  static int slots_v[2] = {0, 0};
+  if (!slots_v[variant]) {
     int dev = 0, sms = 0, occ = 0;
     CD_CUDA(cudaGetDevice(&dev));
     CD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, context_kernel<false>, 256, 0));
-    slots = sms * (occ > 0 ? occ : 1);
+    if (variant) CD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, context_kernel<true>, 256, 0));
+    else CD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, context_kernel<false>, 256, 0));
+    slots_v[variant] = sms * (occ > 0 ? occ : 1);
   }
+  const int slots = slots_v[variant];
   int per_img = slots / (B > 0 ? B : 1); if (per_img < 1) per_img = 1;
   int ppb = cd_cdiv(cd_cdiv(n, per_img), kCtxP) * kCtxP;
   if (ppb < kCtxP) ppb = kCtxP;
   dim3 grid(cd_cdiv(n, ppb), B);
   kmax_kernel<<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax);
   CD_LAUNCH_CHECK();
-  if (cd_linattn_staged_enabled(nullptr, nullptr)) context_kernel<true><<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax, ksum, ctx);
+  if (variant) context_kernel<true><<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax, ksum, ctx);
   else context_kernel<false><<<grid, 256, 0, st>>>(qkv, ld, n, ppb, kmax, ksum, ctx);
   CD_LAUNCH_CHECK();
   return 0;

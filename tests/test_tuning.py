@@ -96,7 +96,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     xs = [g['x'], g['x'].flip(0) * 0.5]
     tgs = [g['target'], g['target'].flip(0)]
     ts = [g['t'], g['t'].flip(0)]
-    cands = [c for c in tuning.CANDIDATES if not c[0].startswith('conv_2cta')]          # (the SM-pair candidates add nothing to the logic)
+    cands = [c for c in tuning.CANDIDATES if not c[0].startswith('conv_2cta') and c[0] not in ('conv_staged_epilogue_mid_k', 'layernorm_multi')]   # (these add nothing to the logic)
     rep = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports.append, candidates=cands)
     assert rep['complete'] and len(reports) == len(cands) + 3 and rep['inference_forward']['err_output'] <= rep['inference_forward']['tolerance']
     rows = {r['name']: r for r in rep['candidates']}
