@@ -57,6 +57,8 @@ if os.environ.get('COLDDIFF_2CTA') in ('0', '1', '2'):   # SM-pair (cta_group::2
 lib.cd_last_error.argtypes = [C.c_char_p, C.c_size_t]
 if os.environ.get('COLDDIFF_CONV_STAGED_EPILOGUE') in ('0', '1', '2', '3'):   # line-coalesced conv epilogue (csrc/conv_epilogue.cuh); default 0
     lib.cd_conv_tc_set_staged_epilogue(int(os.environ['COLDDIFF_CONV_STAGED_EPILOGUE']))
+if os.environ.get('COLDDIFF_CONV_SIMT_PRELOAD') in ('0', '1'):   # image-edge kernels stage a chunk's receptive fields with all loads in flight; default 0
+    lib.cd_conv_simt_set_preload(int(os.environ['COLDDIFF_CONV_SIMT_PRELOAD']))
 if os.environ.get('COLDDIFF_LAYERNORM_MULTI') in ('0', '2', '4'):   # C <= 128 LayerNorm forward with 2 / 4 pixels per lane group in flight (csrc/layernorm_multi.cu); default 0
     lib.cd_layernorm_set_multi(int(os.environ['COLDDIFF_LAYERNORM_MULTI']))
 if os.environ.get('COLDDIFF_LINATTN_STAGED') in ('0', '1'):   # shared-memory-staged cd_linattn_weff / cd_linattn_bwd_small (csrc/linattn_small.cu); default 0

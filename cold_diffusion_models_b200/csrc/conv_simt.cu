@@ -151,6 +151,44 @@ conv_smallc_kernel(const SimtParams p) {
 // K = ntaps*C weights in registers; 256 threads cover 256/(Cout/4) pixels at a time, the receptive fields of a 64-pixel
 // chunk are staged in shared memory and read as broadcast LDS.128; a warp writes whole contiguous output rows.
 // (16*KQ FMAs per KQ LDS.128 instead of 4 per LDS.128, and coalesced stores instead of one pixel row per thread.)
+// opt-in (cd_conv_simt_set_preload): the register-tiled image-edge kernels run ONE block of 8 warps per SM (~185-227 registers per
+// thread), so nothing hides the memory latency of the staging loop below; with the switch on, the (at most three) receptive-field
+// entries a thread stages per 64-pixel chunk are all loaded before the first one is stored.  Same values in the same places.
+static int g_simt_preload = 0;
+__device__ __forceinline__ void stage_patches_preload(float* patch_f, int KP, long long q0, long long pend, const float* __restrict__ src,
+                                                      int ld, int C, int H, int W, int Hg, int Wg, int sy, int sx, int ntaps,
+                                                      const int* dyv, const int* dxv) {
+  const int hw = Hg * Wg;
+  float v[3][4];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = threadIdx.x + u * 256;
+    v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+    if (i < 64 * ntaps) {
+      const int pp = i / ntaps, tap = i - pp * ntaps;
+      const long long q = q0 + pp;
+      if (q < pend) {
+        const int qi = static_cast<int>(q);
+        const int b = qi / hw, rem = qi - b * hw;
+        const int gy = rem / Wg, gx = rem - gy * Wg;
+        const int iy = gy * sy + dyv[tap], ix = gx * sx + dxv[tap];
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          const float* row = src + ((static_cast<long long>(b) * H + iy) * W + ix) * ld;
+          for (int c = 0; c < C; ++c) v[u][c] = row[c];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = threadIdx.x + u * 256;
+    if (i < 64 * ntaps) {
+      const int pp = i / ntaps, tap = i - pp * ntaps;
+      for (int c = 0; c < C; ++c) patch_f[pp * KP + tap * C + c] = v[u][c];
+    }
+  }
+}
+
 __device__ __forceinline__ void stage_patches(float* patch_f, int KP, long long q0, long long pend, const float* __restrict__ src,
                                               int ld, int C, int H, int W, int Hg, int Wg, int sy, int sx, int ntaps,
                                               const int* dyv, const int* dxv) {
@@ -175,7 +213,7 @@ __device__ __forceinline__ void stage_patches(float* patch_f, int KP, long long 
 
 template <int KQ>
 __global__ void __launch_bounds__(256, 1)
-conv_smallc4_kernel(const SimtParams p, int chunks_per_block) {
+conv_smallc4_kernel(const SimtParams p, int chunks_per_block, int preload) {
   constexpr int KP = 4 * KQ;
   __shared__ float4 patch[64][KQ];
   const SimtSrc& S = p.s[0];
@@ -200,7 +238,8 @@ conv_smallc4_kernel(const SimtParams p, int chunks_per_block) {
     if (q0 >= total) break;
     const long long pend = q0 + 64 < total ? q0 + 64 : total;
     __syncthreads();
-    stage_patches(patch_f, KP, q0, pend, S.src, S.ld, S.C, S.H, S.W, p.Hg, p.Wg, p.sy, p.sx, S.ntaps, S.dy, S.dx);
+    if (preload) stage_patches_preload(patch_f, KP, q0, pend, S.src, S.ld, S.C, S.H, S.W, p.Hg, p.Wg, p.sy, p.sx, S.ntaps, S.dy, S.dx);
+    else stage_patches(patch_f, KP, q0, pend, S.src, S.ld, S.C, S.H, S.W, p.Hg, p.Wg, p.sy, p.sx, S.ntaps, S.dy, S.dx);
     __syncthreads();
     const int np = static_cast<int>(pend - q0);
     for (int pp = pg; pp < np; pp += PG) {
@@ -372,7 +411,7 @@ wgrad_smallc_kernel(const WgradParams p) {
 // ran ~9x off the HBM roofline on the 3->128 3x3 / 3->64 1x1 image-edge convolutions of the Unet.)
 template <int KQ>
 __global__ void __launch_bounds__(256, 1)
-wgrad_smallc4_kernel(const WgradParams p) {
+wgrad_smallc4_kernel(const WgradParams p, int preload) {
   constexpr int KP = 4 * KQ;
   __shared__ float4 patch[64][KQ];
   __shared__ float red[256 * 4 * 4];                       // [pixel group][cq][4 co][4 k] of one k-quad
@@ -409,7 +448,8 @@ wgrad_smallc4_kernel(const WgradParams p) {
       }
     }
     __syncthreads();
-    stage_patches(patch_f, KP, q0, pend, p.src, p.ld, p.C, p.H, p.W, p.Hg, p.Wg, p.sy, p.sx, p.ntaps, p.dy, p.dx);
+    if (preload) stage_patches_preload(patch_f, KP, q0, pend, p.src, p.ld, p.C, p.H, p.W, p.Hg, p.Wg, p.sy, p.sx, p.ntaps, p.dy, p.dx);
+    else stage_patches(patch_f, KP, q0, pend, p.src, p.ld, p.C, p.H, p.W, p.Hg, p.Wg, p.sy, p.sx, p.ntaps, p.dy, p.dx);
     __syncthreads();
     const int np = static_cast<int>(pend - q0 < 64 ? pend - q0 : 64);
 #pragma unroll
@@ -656,10 +696,11 @@ static int conv_fwd_simt(const CdConvDesc* d, cudaStream_t st) {
       const int cpb = cd_cdiv(chunks, blocks);
       const int grid = cd_cdiv(chunks, cpb);
       const int KQ = cd_cdiv(c0.ntaps * c0.C, 4);
-      if (KQ <= 1) conv_smallc4_kernel<1><<<grid, 256, 0, st>>>(p, cpb);
-      else if (KQ <= 3) conv_smallc4_kernel<3><<<grid, 256, 0, st>>>(p, cpb);
-      else if (KQ <= 7) conv_smallc4_kernel<7><<<grid, 256, 0, st>>>(p, cpb);
-      else conv_smallc4_kernel<9><<<grid, 256, 0, st>>>(p, cpb);
+      const int pre = (g_simt_preload && 64 * c0.ntaps <= 768) ? 1 : 0;
+      if (KQ <= 1) conv_smallc4_kernel<1><<<grid, 256, 0, st>>>(p, cpb, pre);
+      else if (KQ <= 3) conv_smallc4_kernel<3><<<grid, 256, 0, st>>>(p, cpb, pre);
+      else if (KQ <= 7) conv_smallc4_kernel<7><<<grid, 256, 0, st>>>(p, cpb, pre);
+      else conv_smallc4_kernel<9><<<grid, 256, 0, st>>>(p, cpb, pre);
       CD_LAUNCH_CHECK();
       return 0;
     }
@@ -715,10 +756,11 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
     p.pix_per_split = cd_cdiv(total, blocks);
     const int grid = cd_cdiv(total, p.pix_per_split);
     const int KQ = cd_cdiv(Ksm, 4);
-    if (KQ <= 1) wgrad_smallc4_kernel<1><<<grid, 256, 0, st>>>(p);
-    else if (KQ <= 3) wgrad_smallc4_kernel<3><<<grid, 256, 0, st>>>(p);
-    else if (KQ <= 7) wgrad_smallc4_kernel<7><<<grid, 256, 0, st>>>(p);
-    else wgrad_smallc4_kernel<9><<<grid, 256, 0, st>>>(p);
+    const int wpre = (g_simt_preload && 64 * c.ntaps <= 768) ? 1 : 0;
+    if (KQ <= 1) wgrad_smallc4_kernel<1><<<grid, 256, 0, st>>>(p, wpre);
+    else if (KQ <= 3) wgrad_smallc4_kernel<3><<<grid, 256, 0, st>>>(p, wpre);
+    else if (KQ <= 7) wgrad_smallc4_kernel<7><<<grid, 256, 0, st>>>(p, wpre);
+    else wgrad_smallc4_kernel<9><<<grid, 256, 0, st>>>(p, wpre);
     CD_LAUNCH_CHECK();
   } else if (c.C <= 4 && c.ntaps * c.C <= kSmallK && !c.w_per_batch) {
     int splits = cd_cdiv(total, 512); if (splits > 148 * 16) splits = 148 * 16; if (splits < 1) splits = 1;
@@ -757,6 +799,8 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
   }
   return 0;
 }
+
+extern "C" int cd_conv_simt_set_preload(int enable) { g_simt_preload = enable ? 1 : 0; return 0; }
 
 extern "C" int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* stream) {
   launch_colsum(x, ld, rows, C, out, static_cast<cudaStream_t>(stream));

@@ -35,6 +35,7 @@ CANDIDATES = [
     ('linattn_staged', {'linattn_staged': 1}),
     ('batched_repack', {'batched_repack': 1}),
     ('layernorm_multi', {'layernorm_multi': 4}),
+    ('conv_simt_preload', {'conv_simt_preload': 1}),
     # the SM-pair convolution kernel is validated; its default (1) follows a tile cost model fitted to batch 32 -- try the extremes
     ('conv_2cta_everywhere', {'conv_2cta': 2}),
     ('conv_2cta_off', {'conv_2cta': 0}),
@@ -45,8 +46,8 @@ CANDIDATES = [
 ]
 # candidates that change forward kernels (tried again on the inference forward alone)
 FORWARD_CANDIDATES = ('conv_staged_epilogue_short_k', 'conv_staged_epilogue_mid_k', 'conv_staged_epilogue_all', 'linattn_staged', 'layernorm_multi',
-                      'conv_2cta_everywhere', 'conv_2cta_off')
-DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'layernorm_multi': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
+                      'conv_simt_preload', 'conv_2cta_everywhere', 'conv_2cta_off')
+DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'layernorm_multi': 0, 'conv_simt_preload': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
 
 
 def apply(settings):
@@ -58,6 +59,8 @@ def apply(settings):
         _lib.lib.cd_conv_tc_set_staged_epilogue(int(settings['conv_staged_epilogue']))
     if 'linattn_staged' in settings:
         _lib.lib.cd_linattn_set_staged(int(settings['linattn_staged']))
+    if 'conv_simt_preload' in settings:
+        _lib.lib.cd_conv_simt_set_preload(int(settings['conv_simt_preload']))
     if 'layernorm_multi' in settings:
         _lib.lib.cd_layernorm_set_multi(int(settings['layernorm_multi']))
     if 'batched_repack' in settings:

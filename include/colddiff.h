@@ -189,6 +189,9 @@ int cd_conv_fwd_f16_probe(const CdConvDesc* d, void* stream);
  * bit-identical results): 1 = for launches with at most 16 K chunks of 32 channels per tile (the store-bound 1x1 projections),
  * 2 = for every launch, 3 = at most 48 K chunks */
 int cd_conv_tc_set_staged_epilogue(int mode);
+/* opt-in (default 0, not yet validated on a B200): the register-tiled image-edge convolution / weight-gradient kernels (Cin <= 4)
+ * load all receptive-field entries of a 64-pixel chunk before storing the first (csrc/conv_simt.cu: stage_patches_preload) */
+int cd_conv_simt_set_preload(int enable);
 /* opt-in (default 0, not yet validated on a B200): channel LayerNorm forward for C <= 128 with 2 or 4 pixels per lane group in
  * flight (csrc/layernorm_multi.cu; same per-pixel arithmetic) */
 int cd_layernorm_set_multi(int pixels_per_group);

@@ -305,3 +305,37 @@ def test_linattn_context_preload_variant_equals_the_default(cpulib, B, n, ld):
     kmax, ksum, ctx = torch.zeros(B, 128), torch.zeros(B, 128), torch.zeros(B, 4, 32, 32)
     assert E.cd_linattn_context(P(qkv), ld, B, n, P(kmax), P(ksum), P(ctx), None) == 0
     assert close(res[1], torch.cat([kmax.reshape(-1), ksum.reshape(-1), ctx.reshape(-1)]), 2e-5)
+
+
+@pytest.mark.parametrize('Cout,k', [(128, 3), (64, 1)])
+def test_image_edge_kernels_with_preloaded_staging_equal_the_default(cpulib, Cout, k):
+    """cd_conv_simt_set_preload: conv_smallc4_kernel / wgrad_smallc4_kernel (3-channel image edge) with all receptive-field
+    entries of a chunk loaded before the first store -> bit-identical outputs and weight gradients"""
+    from cold_diffusion_models_b200 import ops
+    g = torch.Generator().manual_seed(Cout + k)
+    B, H = 2, 24                                            # 1152 pixels: 18 chunks of 64
+    x = torch.zeros(B, H, H, 4)
+    x[..., :3] = torch.randn(B, H, H, 3, generator=g)
+    taps = ops.taps_conv(k, k // 2)
+    wp = torch.randn(len(taps), Cout, 3, generator=g) / 3
+    bias, dy = torch.randn(Cout, generator=g), torch.randn(B, H, H, Cout, generator=g)
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for pre in (0, 1):
+            cpulib.cd_conv_simt_set_preload(pre)
+            out, pre_act = torch.full((B, H, H, Cout), 7.0), torch.full((B, H, H, Cout), 7.0)
+            d = ops.make_conv_desc([(ops.View(x, 0, 3), taps, wp, False)], ops.View(out), (B, H, H), Cout=Cout, bias=bias, act=ops.ACT_GELU,
+                                   out2=ops.View(pre_act))
+            assert cpulib.cd_conv_fwd(C.byref(d), 0, None) == 0
+            dw, db = torch.zeros(len(taps), Cout, 3), torch.zeros(Cout)
+            dd = ops.make_conv_desc([(ops.View(x, 0, 3), taps, dw, False)], ops.View(dy), (B, H, H), Cout=Cout)
+            assert cpulib.cd_conv_wgrad(C.byref(dd), P(dy), Cout, P(dw), P(db), 0, None) == 0
+            res.append((out, pre_act, dw, db))
+    cpulib.cd_conv_simt_set_preload(0)
+    cpulib.simt_set_reverse_order(0)
+    for i in (0, 2):                                        # same thread order: preload == default, bit for bit
+        for a, b in zip(res[i], res[i + 1]):
+            assert torch.equal(a, b)
+    want = torch.einsum('bhwtc,toc->bhwo', torch.stack([torch.roll(torch.nn.functional.pad(x[..., :3], (0, 0, 1, 1, 1, 1)), (-tp[2], -tp[3]), (1, 2))[:, 1:-1, 1:-1] if k == 3 else x[..., :3] for tp in taps], dim=3), wp) + bias
+    assert close(res[1][1], want, 2e-5)

@@ -44,7 +44,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
         u = cdm.Unet(dim=32, dim_mults=(1, 2), channels=3)
     u.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith('sd:')})
 
-    state = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'wgrad_bias_fusion': 0, 'layernorm_multi': 0}
+    state = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'wgrad_bias_fusion': 0, 'layernorm_multi': 0, 'conv_simt_preload': 0}
 
     class FakeLib:                                       # the emulator has no kernel variants: record the switches instead
         def cd_conv_tc_set_staged_epilogue(self, v):
@@ -53,6 +53,10 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
 
         def cd_linattn_set_staged(self, v):
             state['linattn_staged'] = v
+            return 0
+
+        def cd_conv_simt_set_preload(self, v):
+            state['conv_simt_preload'] = v
             return 0
 
         def cd_layernorm_set_multi(self, v):
@@ -96,7 +100,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     xs = [g['x'], g['x'].flip(0) * 0.5]
     tgs = [g['target'], g['target'].flip(0)]
     ts = [g['t'], g['t'].flip(0)]
-    cands = [c for c in tuning.CANDIDATES if not c[0].startswith('conv_2cta') and c[0] not in ('conv_staged_epilogue_mid_k', 'layernorm_multi')]   # (these add nothing to the logic)
+    cands = [c for c in tuning.CANDIDATES if not c[0].startswith('conv_2cta') and c[0] not in ('conv_staged_epilogue_mid_k', 'layernorm_multi', 'conv_simt_preload')]   # (these add nothing to the logic)
     rep = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports.append, candidates=cands)
     assert rep['complete'] and len(reports) == len(cands) + 3 and rep['inference_forward']['err_output'] <= rep['inference_forward']['tolerance']
     rows = {r['name']: r for r in rep['candidates']}
@@ -107,7 +111,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     assert rows['merge_micro_batches'].get('accepted') and rows['merge_micro_batches']['err_grad'] < 1e-5    # same gradient, other summation order
     assert rep['accepted'] == {'conv_staged_epilogue': 1, 'batched_repack': 1, 'merge_micro_batches': 1} and rep['best_ms'] == 80.0
     assert not rows['wgrad_bias_fusion'].get('accepted') and rows['wgrad_bias_fusion']['ms'] == 87.0        # right, no gain
-    assert state == {'conv_2cta': 1, 'conv_staged_epilogue': 1, 'linattn_staged': 0, 'wgrad_bias_fusion': 0, 'layernorm_multi': 0} and engine.batched_repack() is True      # left applied
+    assert state == {'conv_2cta': 1, 'conv_staged_epilogue': 1, 'linattn_staged': 0, 'wgrad_bias_fusion': 0, 'layernorm_multi': 0, 'conv_simt_preload': 0} and engine.batched_repack() is True      # left applied
 
     # a candidate that raises ends the search; what was accepted before it stands
     def boom(v):

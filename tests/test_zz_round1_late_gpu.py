@@ -333,6 +333,40 @@ def test_layernorm_multi_pixel_forward_matches_the_default_kernel():
 
 
 @OPT_IN
+def test_image_edge_kernels_with_preloaded_staging_match_the_default():
+    """cd_conv_simt_set_preload (off by default until this test has passed on a B200): the 3-channel image-edge convolution and its
+    weight gradient with all receptive-field loads of a chunk in flight; outputs bit-identical, weight gradients (float atomics over
+    blocks) to rounding"""
+    from cold_diffusion_models_b200 import ops
+    from cold_diffusion_models_b200._lib import lib
+    gen = torch.Generator().manual_seed(8)
+    for Cout, k, B, H in ((128, 3, 8, 128), (64, 1, 8, 128), (128, 3, 3, 32)):
+        x = torch.zeros(B, H, H, 4)
+        x[..., :3] = torch.randn(B, H, H, 3, generator=gen)
+        x = x.cuda()
+        taps = ops.taps_conv(k, k // 2)
+        wp, bias = (torch.randn(len(taps), Cout, 3, generator=gen) / 3).cuda(), torch.randn(Cout, generator=gen).cuda()
+        dy = torch.randn(B, H, H, Cout, generator=gen).cuda()
+        res = []
+        try:
+            for pre in (0, 1):
+                lib.cd_conv_simt_set_preload(pre)
+                out, pa = torch.full((B, H, H, Cout), 7.0, device='cuda'), torch.full((B, H, H, Cout), 7.0, device='cuda')
+                d = ops.make_conv_desc([(ops.View(x, 0, 3), taps, wp, False)], ops.View(out), (B, H, H), Cout=Cout, bias=bias, act=ops.ACT_GELU,
+                                       out2=ops.View(pa))
+                ops.conv_fwd(d, ops.CONV_SIMT)
+                dw, db = torch.zeros(len(taps), Cout, 3, device='cuda'), torch.zeros(Cout, device='cuda')
+                dd = ops.make_conv_desc([(ops.View(x, 0, 3), taps, dw, False)], ops.View(dy), (B, H, H), Cout=Cout)
+                ops.conv_wgrad(dd, ops.View(dy), dw, db, impl=ops.CONV_SIMT)
+                torch.cuda.synchronize()
+                res.append((out, pa, dw, db))
+        finally:
+            lib.cd_conv_simt_set_preload(0)
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), (Cout, k)
+        assert rel(res[1][2], res[0][2]) < 1e-5 and rel(res[1][3], res[0][3]) < 1e-5, (Cout, k)
+
+
+@OPT_IN
 def test_conv_staged_epilogue_matches_the_row_epilogue():
     """runs _conv_staged_epilogue_body in a child process with a time limit: the kernel variant it enables has never run on a
     B200, and a tcgen05 / mbarrier pipeline that went wrong would spin instead of failing -- that must not take the session's
