@@ -19,15 +19,15 @@ TMO=300 step eager_comparator    python bench.py --impl reference --reference-de
 TMO=200 step op_profile_default  python tools/op_profile.py
 # one-launch weight repacks (csrc/repack.cu): same bench and op profile with the switch on; flip the default in engine.batched_repack
 # when the late GPU test (gpu_tests above: test_batched_repack_matches_the_single_launches) is green and this bench is not slower
-TMO=300 step bench_batched_repack      env COLDDIFF_BATCHED_REPACK=1 python bench.py
+TMO=300 step bench_batched_repack      env COLDDIFF_BATCHED_REPACK=1 python bench.py --no-autotune
 TMO=200 step op_profile_batched_repack env COLDDIFF_BATCHED_REPACK=1 python tools/op_profile.py
 # shared-memory-staged per-(batch element, head) LinearAttention kernels (csrc/linattn_small.cu), alone and with the batched repacks
 TMO=200 step op_profile_linattn_staged env COLDDIFF_LINATTN_STAGED=1 python tools/op_profile.py
-TMO=300 step bench_all_switches        env COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 python bench.py
+TMO=300 step bench_all_switches        env COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 python bench.py --no-autotune
 # line-coalesced epilogue of the tcgen05 convolution (csrc/conv_epilogue.cuh): per-shape table rows / mode 1 / mode 2, then the bench
 TMO=300 step conv_shapes_epilogue      python tools/conv_shapes_epilogue.py
-TMO=300 step bench_staged_epilogue     env COLDDIFF_CONV_STAGED_EPILOGUE=1 python bench.py
-TMO=300 step bench_everything_on       env COLDDIFF_CONV_STAGED_EPILOGUE=1 COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 python bench.py
+TMO=300 step bench_staged_epilogue     env COLDDIFF_CONV_STAGED_EPILOGUE=1 python bench.py --no-autotune
+TMO=300 step bench_everything_on       env COLDDIFF_CONV_STAGED_EPILOGUE=3 COLDDIFF_LINATTN_STAGED=1 COLDDIFF_BATCHED_REPACK=1 COLDDIFF_LAYERNORM_MULTI=4 COLDDIFF_CONV_SIMT_PRELOAD=1 python bench.py --no-autotune
 # ncu: launch list with DRAM bytes of one optimizer step with the staged epilogue on every launch, and a full capture of six staged
 # convolution launches (source-level: does the epilogue still dominate?).  Copy the summaries into profiles/ (see profiles/README.md)
 TMO=400 step ncu_launches_staged env COLDDIFF_CONV_STAGED_EPILOGUE=2 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $out/launches_step_staged.csv python tools/one_step.py
