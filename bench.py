@@ -240,7 +240,8 @@ def main():
     # their concatenation (same gradient) is measured separately below when the start-up check accepted it.
     merge_ok = bool(tuned['accepted'].pop('merge_micro_batches', None))
     from cold_diffusion_models_b200 import trainer as _trainer_mod
-    _trainer_mod.merge_micro_batches(False)
+    if not args.no_autotune:
+        _trainer_mod.merge_micro_batches(False)
 
     # distinct batches so consecutive steps never re-read the same inputs; activations (>3 GB/step) exceed the 126 MB L2
     g = torch.Generator().manual_seed(1234 + rank)
@@ -338,7 +339,8 @@ def main():
 
     # ---- the other BASELINE configs that fit one GPU, as context (rank 0 only; not the headline, bounded to a few steps) ----
     others = {}
-    tuning.apply(tuning.DEFAULTS)             # the other configs run the default kernels (see the autotune comment above)
+    if not args.no_autotune:
+        tuning.apply(tuning.DEFAULTS)         # the other configs run the default kernels (see the autotune comment above)
     if rank == 0:
         try:
             with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
@@ -421,7 +423,8 @@ def main():
         except Exception as e:
             others['error_C4'] = repr(e)[:200]
 
-    tuning.apply(dict(tuning.DEFAULTS, **tuned['accepted']))
+    if not args.no_autotune:
+        tuning.apply(dict(tuning.DEFAULTS, **tuned['accepted']))
 
     # ---- roofline of the dominant kernel (tcgen05 tap-list convolution), CUDA events around every launch --------
     peaks, peak_kind = read_peaks()
