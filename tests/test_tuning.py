@@ -100,7 +100,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     xs = [g['x'], g['x'].flip(0) * 0.5]
     tgs = [g['target'], g['target'].flip(0)]
     ts = [g['t'], g['t'].flip(0)]
-    cands = [c for c in tuning.CANDIDATES if not c[0].startswith('conv_2cta') and c[0] not in ('conv_staged_epilogue_mid_k', 'layernorm_multi', 'conv_simt_preload')]   # (these add nothing to the logic)
+    cands = [c for c in tuning.CANDIDATES if not c[0].startswith('conv_2cta') and c[0] not in ('conv_staged_epilogue_mid_k', 'layernorm_multi', 'conv_simt_preload', 'wgrad_bias_fusion')]   # (these add nothing to the logic)
     rep = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports.append, candidates=cands)
     assert rep['complete'] and len(reports) == len(cands) + 3 and rep['inference_forward']['err_output'] <= rep['inference_forward']['tolerance']
     rows = {r['name']: r for r in rep['candidates']}
@@ -110,7 +110,6 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
     assert rows['batched_repack'].get('accepted')
     assert rows['merge_micro_batches'].get('accepted') and rows['merge_micro_batches']['err_grad'] < 1e-5    # same gradient, other summation order
     assert rep['accepted'] == {'conv_staged_epilogue': 1, 'batched_repack': 1, 'merge_micro_batches': 1} and rep['best_ms'] == 80.0
-    assert not rows['wgrad_bias_fusion'].get('accepted') and rows['wgrad_bias_fusion']['ms'] == 87.0        # right, no gain
     assert state == {'conv_2cta': 1, 'conv_staged_epilogue': 1, 'linattn_staged': 0, 'wgrad_bias_fusion': 0, 'layernorm_multi': 0, 'conv_simt_preload': 0} and engine.batched_repack() is True      # left applied
 
     # a candidate that raises ends the search; what was accepted before it stands
@@ -118,7 +117,7 @@ def test_decision_procedure_on_the_emulated_abi(emu, monkeypatch):
         raise RuntimeError('CUDA error: an illegal memory access was encountered')
     monkeypatch.setattr(_lib.lib, 'cd_linattn_set_staged', lambda v: boom(v) if v else 0, raising=False)
     reports2 = []
-    rep2 = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports2.append, candidates=[c for c in cands if c[0] in ('conv_staged_epilogue_short_k', 'linattn_staged', 'batched_repack')])
+    rep2 = tuning.run_candidates(u, xs, tgs, ts, lambda: None, timer, 1, reports2.append, candidates=[c for c in cands if c[0] in ('conv_staged_epilogue_short_k', 'linattn_staged')])
     assert 'complete' not in rep2 and rep2['accepted'] == {'conv_staged_epilogue': 1}
     assert rep2['candidates'][-1]['name'] == 'linattn_staged' and 'raised' in rep2['candidates'][-1]['rejected']
 
