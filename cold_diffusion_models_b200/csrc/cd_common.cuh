@@ -24,6 +24,10 @@ void cd_set_error(const char* fmt, ...);
 
 static inline int cd_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// conv_simt.cu / final_proj.cu: opt-in variants of the image-edge kernels (cd_conv_simt_set_preload)
+int cd_conv_simt_preload_enabled();
+int cd_conv1x1_to_nchw_tiled(const float* x, int ld, long long npix, int HW, int C, const float* w, const float* bias, int Co,
+                             const float* resid, float* out, cudaStream_t st);
 // layernorm_multi.cu: C <= 128 LayerNorm forward with several pixels per lane group in flight (opt-in); returns 1 when not taken
 int cd_layernorm_fwd_multi(const float* x, int x_ld, long long npix, int C, const float* g, const float* beta, float eps,
                            float* y, int y_ld, float* stats, int round_tf32, cudaStream_t st);

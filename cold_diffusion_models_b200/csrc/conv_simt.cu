@@ -801,6 +801,7 @@ extern "C" int cd_conv_wgrad(const CdConvDesc* d, const float* dout, int dout_ld
 }
 
 extern "C" int cd_conv_simt_set_preload(int enable) { g_simt_preload = enable ? 1 : 0; return 0; }
+int cd_conv_simt_preload_enabled() { return g_simt_preload; }
 
 extern "C" int cd_colsum(const float* x, int ld, int64_t rows, int C, float* out, void* stream) {
   launch_colsum(x, ld, rows, C, out, static_cast<cudaStream_t>(stream));

@@ -884,6 +884,10 @@ extern "C" int cd_conv1x1_to_nchw(const float* x, int ld, int B, int H, int W, i
                                   const float* b, int Co, const float* resid_nchw, float* out_nchw, void* stream) {
   CD_REQUIRE(C % 4 == 0 && ld % 4 == 0, "cd_conv1x1_to_nchw: C must be a multiple of 4");
   const long long npix = static_cast<long long>(B) * H * W;
+  if (cd_conv_simt_preload_enabled()) {                  // opt-in: tile through shared memory (final_proj.cu)
+    const int rc = cd_conv1x1_to_nchw_tiled(x, ld, npix, H * W, C, w, b, Co, resid_nchw, out_nchw, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   conv1x1_to_nchw_kernel<<<cd_cdiv(npix, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, B, H * W, C, w, b, Co, resid_nchw, out_nchw);
   CD_LAUNCH_CHECK();
   return 0;

@@ -339,3 +339,28 @@ def test_image_edge_kernels_with_preloaded_staging_equal_the_default(cpulib, Cou
             assert torch.equal(a, b)
     want = torch.einsum('bhwtc,toc->bhwo', torch.stack([torch.roll(torch.nn.functional.pad(x[..., :3], (0, 0, 1, 1, 1, 1)), (-tp[2], -tp[3]), (1, 2))[:, 1:-1, 1:-1] if k == 3 else x[..., :3] for tp in taps], dim=3), wp) + bias
     assert close(res[1][1], want, 2e-5)
+
+
+@pytest.mark.parametrize('B,H,Cc,pad,Co,resid', [(2, 24, 64, 0, 3, True), (1, 17, 64, 8, 3, False), (3, 8, 32, 0, 1, True), (1, 16, 128, 0, 5, False)])
+def test_tiled_final_projection_equals_the_default_kernel(cpulib, B, H, Cc, pad, Co, resid):
+    """csrc/final_proj.cu (behind cd_conv_simt_set_preload): the NHWC -> NCHW 1x1 projection through a shared-memory tile, same order
+    of the dot products -> bit-identical, ragged last tile and padded rows included"""
+    g = torch.Generator().manual_seed(B * H + Cc)
+    ld = Cc + pad
+    x = torch.randn(B, H, H, ld, generator=g)
+    w, bias = torch.randn(Co, Cc, generator=g) / 8, torch.randn(Co, generator=g)
+    r = torch.randn(B, Co, H, H, generator=g) if resid else None
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for pre in (0, 1):
+            cpulib.cd_conv_simt_set_preload(pre)
+            out = torch.full((B, Co, H, H), 7.0)
+            assert cpulib.cd_conv1x1_to_nchw(P(x), ld, B, H, H, Cc, P(w), P(bias), Co, P(r), P(out), None) == 0
+            res.append(out)
+    cpulib.cd_conv_simt_set_preload(0)
+    cpulib.simt_set_reverse_order(0)
+    for o in res[1:]:
+        assert torch.equal(o, res[0])
+    want = torch.einsum('bhwc,oc->bohw', x[..., :Cc].double(), w.double()) + bias.double()[None, :, None, None] + (r.double() if resid else 0)
+    assert close(res[1], want.float(), 2e-5)

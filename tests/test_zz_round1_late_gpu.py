@@ -364,6 +364,24 @@ def test_image_edge_kernels_with_preloaded_staging_match_the_default():
             lib.cd_conv_simt_set_preload(0)
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), (Cout, k)
         assert rel(res[1][2], res[0][2]) < 1e-5 and rel(res[1][3], res[0][3]) < 1e-5, (Cout, k)
+    # the same switch: final 1x1 projection NHWC -> NCHW through a shared-memory tile (csrc/final_proj.cu), bit-identical
+    import ctypes as C
+    from cold_diffusion_models_b200._lib import ptr, stream, _check
+    for B, H, Cc, Co in ((32, 128, 64, 3), (3, 17, 64, 3), (2, 16, 32, 1)):
+        x = torch.randn(B, H, H, Cc, generator=gen).cuda()
+        w, bias = (torch.randn(Co, Cc, generator=gen) / 8).cuda(), torch.randn(Co, generator=gen).cuda()
+        r = torch.randn(B, Co, H, H, generator=gen).cuda()
+        outs = []
+        try:
+            for pre in (0, 1):
+                lib.cd_conv_simt_set_preload(pre)
+                o = torch.full((B, Co, H, H), 7.0, device='cuda')
+                _check(lib.cd_conv1x1_to_nchw(ptr(x), Cc, B, H, H, Cc, ptr(w), ptr(bias), Co, ptr(r), ptr(o), stream()), 'final projection')
+                torch.cuda.synchronize()
+                outs.append(o)
+        finally:
+            lib.cd_conv_simt_set_preload(0)
+        assert torch.equal(outs[0], outs[1]), (B, H, Cc, Co)
 
 
 @OPT_IN
