@@ -359,6 +359,10 @@ __global__ void transpose_weff_kernel(const float* __restrict__ w, int dim, floa
 // final 1x1 projection backward: dx[pix][c] = sum_co dout[b][co][pix] w[co][c]; dw[co][c], db[co]
 // ---------------------------------------------------------------------------------------------
 // thread = (pixel group, channel): x reads are coalesced over channels, dout is a warp broadcast
+// U = 4 (opt-in, the image-edge switch cd_conv_simt_set_preload): four pixels per trip with their loads issued first -- the default
+// keeps one 4-byte load per thread in flight (8 KB per SM) and is latency-bound at ~7x its HBM time.  Pixels are still consumed in
+// ascending order per thread, so every sum is formed in the same order.
+template <int U>
 __global__ void __launch_bounds__(256)
 conv1x1_to_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int ld, int B, int HW, int C,
                            const float* __restrict__ w, int Co, float* __restrict__ dx, int dx_ld,
@@ -372,7 +376,30 @@ conv1x1_to_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restri
   float wv[8], acc[8], accb[8];
   for (int co = 0; co < Co; ++co) { wv[co] = w[co * C + c]; acc[co] = 0.f; accb[co] = 0.f; }
   if (gq < groups) {
-    for (long long pix = p0 + gq; pix < p1; pix += groups) {
+    long long pix = p0 + gq;
+    if (U > 1) {
+      for (; pix + static_cast<long long>(U - 1) * groups < p1; pix += static_cast<long long>(U) * groups) {
+        float xv[U], dv[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long pu = pix + static_cast<long long>(u) * groups;
+          const int b = static_cast<int>(pu / HW), p = static_cast<int>(pu % HW);
+          xv[u] = x[pu * ld + c];
+          for (int co = 0; co < Co; ++co) dv[u][co] = dout[(static_cast<long long>(b) * Co + co) * HW + p];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float d = 0.f;
+          for (int co = 0; co < Co; ++co) {
+            d = fmaf(dv[u][co], wv[co], d);
+            acc[co] = fmaf(dv[u][co], xv[u], acc[co]);
+            accb[co] += dv[u][co];
+          }
+          dx[(pix + static_cast<long long>(u) * groups) * dx_ld + c] = d;
+        }
+      }
+    }
+    for (; pix < p1; pix += groups) {
       const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
       const float xv = x[pix * ld + c];
       float d = 0.f;
@@ -569,8 +596,12 @@ extern "C" int cd_conv1x1_to_nchw_bwd(const float* dout_nchw, const float* x, in
   const int groups = 256 / C;
   const size_t smem = sizeof(float) * size_t(groups) * Co * C;
   const int ppb = 1024;
-  conv1x1_to_nchw_bwd_kernel<<<cd_cdiv(npix, ppb), 256, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
-                                                                                                 dx, dx_ld, dw, db, ppb);
+  if (cd_conv_simt_preload_enabled())
+    conv1x1_to_nchw_bwd_kernel<4><<<cd_cdiv(npix, ppb), 256, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
+                                                                                                      dx, dx_ld, dw, db, ppb);
+  else
+    conv1x1_to_nchw_bwd_kernel<1><<<cd_cdiv(npix, ppb), 256, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
+                                                                                                      dx, dx_ld, dw, db, ppb);
   CD_LAUNCH_CHECK();
   return 0;
 }

@@ -364,3 +364,27 @@ def test_tiled_final_projection_equals_the_default_kernel(cpulib, B, H, Cc, pad,
         assert torch.equal(o, res[0])
     want = torch.einsum('bhwc,oc->bohw', x[..., :Cc].double(), w.double()) + bias.double()[None, :, None, None] + (r.double() if resid else 0)
     assert close(res[1], want.float(), 2e-5)
+
+
+@pytest.mark.parametrize('B,H,Cc,Co', [(2, 24, 64, 3), (1, 17, 64, 3), (3, 40, 32, 1)])
+def test_final_projection_backward_with_four_pixels_in_flight_equals_the_default(cpulib, B, H, Cc, Co):
+    """conv1x1_to_nchw_bwd_kernel<4> (behind cd_conv_simt_set_preload): four pixels per trip, loads first; pixels are consumed in the
+    same order per thread -> dx, dW, db bit-identical"""
+    g = torch.Generator().manual_seed(B + H + Cc)
+    x, dout = torch.randn(B, H, H, Cc, generator=g), torch.randn(B, Co, H, H, generator=g)
+    w = torch.randn(Co, Cc, generator=g) / 8
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for pre in (0, 1):
+            cpulib.cd_conv_simt_set_preload(pre)
+            dx, dw, db = torch.full((B, H, H, Cc), 7.0), torch.zeros(Co, Cc), torch.zeros(Co)
+            assert cpulib.cd_conv1x1_to_nchw_bwd(P(dout), P(x), Cc, B, H, H, Cc, P(w), Co, P(dx), Cc, P(dw), P(db), None) == 0
+            res.append(torch.cat([dx.reshape(-1), dw.reshape(-1), db.reshape(-1)]))
+    cpulib.cd_conv_simt_set_preload(0)
+    cpulib.simt_set_reverse_order(0)
+    assert torch.equal(res[0], res[1]) and torch.equal(res[2], res[3])
+    want_dx = torch.einsum('bohw,oc->bhwc', dout.double(), w.double())
+    want_dw = torch.einsum('bohw,bhwc->oc', dout.double(), x.double())
+    want = torch.cat([want_dx.reshape(-1), want_dw.reshape(-1), dout.double().sum(dim=(0, 2, 3))]).float()
+    assert close(res[1], want, 1e-4)

@@ -382,6 +382,18 @@ def test_image_edge_kernels_with_preloaded_staging_match_the_default():
         finally:
             lib.cd_conv_simt_set_preload(0)
         assert torch.equal(outs[0], outs[1]), (B, H, Cc, Co)
+        # ... and its backward with four pixels per trip in flight: same order of every sum per thread; dW / db go through float atomics
+        bres = []
+        try:
+            for pre in (0, 1):
+                lib.cd_conv_simt_set_preload(pre)
+                dx, dw, db = torch.full((B, H, H, Cc), 7.0, device='cuda'), torch.zeros(Co, Cc, device='cuda'), torch.zeros(Co, device='cuda')
+                _check(lib.cd_conv1x1_to_nchw_bwd(ptr(r), ptr(x), Cc, B, H, H, Cc, ptr(w), Co, ptr(dx), Cc, ptr(dw), ptr(db), stream()), 'final projection bwd')
+                torch.cuda.synchronize()
+                bres.append((dx, dw, db))
+        finally:
+            lib.cd_conv_simt_set_preload(0)
+        assert torch.equal(bres[0][0], bres[1][0]) and rel(bres[1][1], bres[0][1]) < 1e-5 and rel(bres[1][2], bres[0][2]) < 1e-5, (B, H, Cc, Co)
 
 
 @OPT_IN
