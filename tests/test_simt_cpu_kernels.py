@@ -388,3 +388,27 @@ def test_final_projection_backward_with_four_pixels_in_flight_equals_the_default
     want_dw = torch.einsum('bohw,bhwc->oc', dout.double(), x.double())
     want = torch.cat([want_dx.reshape(-1), want_dw.reshape(-1), dout.double().sum(dim=(0, 2, 3))]).float()
     assert close(res[1], want, 1e-4)
+
+
+@pytest.mark.parametrize('B,rows,Cc,pad,out_ld', [(2, 1024, 64, 0, 80), (3, 300, 128, 8, 128), (1, 5000, 32, 0, 32), (2, 256, 512, 0, 600)])
+def test_batched_column_sums_float4_variant(cpulib, B, rows, Cc, pad, out_ld):
+    """colsum_batched_vec_kernel (behind cd_conv_simt_set_preload): float4 loads, four in flight; accumulates into `out` like the
+    scalar kernel, to fp32 rounding (another summation order)"""
+    g = torch.Generator().manual_seed(rows + Cc)
+    ld = Cc + pad
+    x = torch.randn(B, rows, ld, generator=g)
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        for pre in (0, 1):
+            cpulib.cd_conv_simt_set_preload(pre)
+            out = torch.full((B, out_ld), 0.5)
+            assert cpulib.cd_colsum_batched(P(x), ld, B, ctypes_mod.c_int64(rows), Cc, P(out), out_ld, None) == 0
+            res.append(out)
+    cpulib.cd_conv_simt_set_preload(0)
+    cpulib.simt_set_reverse_order(0)
+    want = torch.full((B, out_ld), 0.5)
+    want[:, :Cc] += x[:, :, :Cc].double().sum(dim=1).float()
+    for o in res:
+        assert close(o, want, 2e-5)
+        assert bool((o[:, Cc:] == 0.5).all())

@@ -394,6 +394,20 @@ def test_image_edge_kernels_with_preloaded_staging_match_the_default():
         finally:
             lib.cd_conv_simt_set_preload(0)
         assert torch.equal(bres[0][0], bres[1][0]) and rel(bres[1][1], bres[0][1]) < 1e-5 and rel(bres[1][2], bres[0][2]) < 1e-5, (B, H, Cc, Co)
+    # ... and the float4 variant of the batched column sums (time-conditioning gradient): another summation order, fp32 rounding
+    for B, rows, Cc in ((32, 16384, 64), (3, 300, 128), (2, 256, 512)):
+        x = torch.randn(B, rows, Cc, generator=gen).cuda()
+        cres = []
+        try:
+            for pre in (0, 1):
+                lib.cd_conv_simt_set_preload(pre)
+                o = torch.full((B, Cc + 16), 0.5, device='cuda')
+                _check(lib.cd_colsum_batched(ptr(x), Cc, B, C.c_int64(rows), Cc, ptr(o), Cc + 16, stream()), 'colsum_batched')
+                torch.cuda.synchronize()
+                cres.append(o)
+        finally:
+            lib.cd_conv_simt_set_preload(0)
+        assert rel(cres[1], cres[0]) < 1e-5 and bool((cres[1][:, Cc:] == 0.5).all()), (B, rows, Cc)
 
 
 @OPT_IN
