@@ -191,7 +191,8 @@ int cd_conv_fwd_f16_probe(const CdConvDesc* d, void* stream);
 int cd_conv_tc_set_staged_epilogue(int mode);
 /* opt-in (default 0, not yet validated on a B200): the register-tiled image-edge convolution / weight-gradient kernels (Cin <= 4)
  * load all receptive-field entries of a 64-pixel chunk before storing the first (csrc/conv_simt.cu: stage_patches_preload), and
- * cd_conv1x1_to_nchw goes through a shared-memory tile (csrc/final_proj.cu) */
+ * cd_conv1x1_to_nchw goes through a shared-memory tile (csrc/final_proj.cu), cd_conv1x1_to_nchw_bwd keeps four pixels per trip in
+ * flight and cd_colsum_batched uses float4 loads (csrc/backward.cu): more bytes in flight, same arithmetic */
 int cd_conv_simt_set_preload(int enable);
 /* opt-in (default 0, not yet validated on a B200): channel LayerNorm forward for C <= 128 with 2 or 4 pixels per lane group in
  * flight (csrc/layernorm_multi.cu; same per-pixel arithmetic) */
