@@ -409,11 +409,14 @@ __global__ void transpose_weff_kernel(const float* __restrict__ w, int dim, floa
 // U = 4 (opt-in, the image-edge switch cd_conv_simt_set_preload): four pixels per trip with their loads issued first -- the default
 // keeps one 4-byte load per thread in flight (8 KB per SM) and is latency-bound at ~7x its HBM time.  Pixels are still consumed in
 // ascending order per thread, so every sum is formed in the same order.
-template <int U>
+// CO > 0 fixes the number of image channels at compile time (3 for RGB): every per-channel array then lives in registers instead
+// of local memory (the run-time Co of the default instantiation indexes them dynamically).
+template <int U, int CO = 0>
 __global__ void __launch_bounds__(256)
 conv1x1_to_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int ld, int B, int HW, int C,
-                           const float* __restrict__ w, int Co, float* __restrict__ dx, int dx_ld,
+                           const float* __restrict__ w, int Co_rt, float* __restrict__ dx, int dx_ld,
                            float* __restrict__ dw, float* __restrict__ db, int pix_per_block) {
+  const int Co = CO > 0 ? CO : Co_rt;
   extern __shared__ float red[];      // [groups][Co][C]
   const int groups = blockDim.x / C;
   const int c = threadIdx.x % C, gq = threadIdx.x / C;
@@ -432,15 +435,20 @@ conv1x1_to_nchw_bwd_kernel(const float* __restrict__ dout, const float* __restri
           const long long pu = pix + static_cast<long long>(u) * groups;
           const int b = static_cast<int>(pu / HW), p = static_cast<int>(pu % HW);
           xv[u] = x[pu * ld + c];
-          for (int co = 0; co < Co; ++co) dv[u][co] = dout[(static_cast<long long>(b) * Co + co) * HW + p];
+#pragma unroll
+          for (int co = 0; co < (CO > 0 ? CO : 8); ++co)
+            if (co < Co) dv[u][co] = dout[(static_cast<long long>(b) * Co + co) * HW + p];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           float d = 0.f;
-          for (int co = 0; co < Co; ++co) {
-            d = fmaf(dv[u][co], wv[co], d);
-            acc[co] = fmaf(dv[u][co], xv[u], acc[co]);
-            accb[co] += dv[u][co];
+#pragma unroll
+          for (int co = 0; co < (CO > 0 ? CO : 8); ++co) {
+            if (co < Co) {
+              d = fmaf(dv[u][co], wv[co], d);
+              acc[co] = fmaf(dv[u][co], xv[u], acc[co]);
+              accb[co] += dv[u][co];
+            }
           }
           dx[(pix + static_cast<long long>(u) * groups) * dx_ld + c] = d;
         }
@@ -655,7 +663,10 @@ extern "C" int cd_conv1x1_to_nchw_bwd(const float* dout_nchw, const float* x, in
   const int groups = 256 / C;
   const size_t smem = sizeof(float) * size_t(groups) * Co * C;
   const int ppb = 1024;
-  if (cd_conv_simt_preload_enabled())
+  if (cd_conv_simt_preload_enabled() && Co == 3)
+    conv1x1_to_nchw_bwd_kernel<4, 3><<<cd_cdiv(npix, ppb), 256, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
+                                                                                                         dx, dx_ld, dw, db, ppb);
+  else if (cd_conv_simt_preload_enabled())
     conv1x1_to_nchw_bwd_kernel<4><<<cd_cdiv(npix, ppb), 256, smem, static_cast<cudaStream_t>(stream)>>>(dout_nchw, x, ld, B, H * W, C, w, Co,
                                                                                                       dx, dx_ld, dw, db, ppb);
   else
