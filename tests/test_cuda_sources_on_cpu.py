@@ -18,11 +18,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 SUBSET = [
     'test_unet_host_logic.py::test_unet_forward_and_every_gradient_on_the_emulated_abi',      # ConvNeXt Unet forward + backward kernels
-    'test_unet_host_logic.py::test_p_losses_through_the_public_class_on_the_emulated_abi',    # blur q_sample + loss kernels
-    'test_unet_host_logic.py::test_trainer_step_equals_torch_adam_and_ema_on_the_emulated_abi',   # fused Adam + EMA
+    'test_unet_host_logic.py::test_trainer_step_equals_torch_adam_and_ema_on_the_emulated_abi',   # blur q_sample, loss, fused Adam + EMA
     'test_model2_host_logic.py::test_backward_schedule_reproduces_every_reference_gradient',  # Model (DDPM UNet) training kernels
     'test_model2_host_logic.py::test_inference_forward_and_sampling_on_the_emulated_abi',     # GroupNorm / softmax attention / step-down
-    'test_model2_host_logic.py::test_dropout_plumbing_of_the_training_path',
     'test_packages_host_logic.py::test_defading_all_sample',                                  # fade masks, random windows, reverse loop
     'test_packages_host_logic.py::test_device_resident_dataset_matches_the_torchvision_pipeline',
 ]

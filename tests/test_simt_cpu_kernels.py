@@ -24,7 +24,7 @@ def P(t):
 def m2lib(request):
     """threads of a block resumed in ascending / descending order: a missing barrier shows under at least one of them"""
     import build
-    lib = C.CDLL(build.build(['model2_bwd.cu']))
+    lib = C.CDLL(build.build_all())              # one CPU library for the whole module (a second g++ build costs ~20 s)
     lib.simt_set_reverse_order(int(request.param == 'descending'))
     yield lib
     lib.simt_set_reverse_order(0)
