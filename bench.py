@@ -14,6 +14,13 @@ GPUs with the batches already resident in HBM; `e2e` = the same through the publ
 pinned-host batches copied H2D and the loss read back D2H inside the timed region.  The second half of the
 metric (200-step sample images/sec) is measured on a bounded number of reverse steps and reported in
 `sample`; nothing is skipped inside a timed region.
+
+Before timing, cold_diffusion_models_b200.tuning.autotune() lets a child process validate the opt-in kernel variants (all default
+off) against the default kernels on this network and batch and time them; accepted variants are switched on for the headline
+measurements and listed in `tuning` (--no-autotune: defaults only).  A single-GPU run performs that whole tuned measurement in a
+child process of its own and falls back to measuring the default kernels in-process if the child fails.  `op_profile` is the in-situ
+time per C-ABI entry point of one step, `merged_micro_batches` the throughput with the two micro-batches concatenated into one pass
+(validated by the same check, not the headline).
 """
 import argparse
 import json
