@@ -47,6 +47,7 @@ CANDIDATES = [
 # candidates that change forward kernels (tried again on the inference forward alone)
 FORWARD_CANDIDATES = ('conv_staged_epilogue_short_k', 'conv_staged_epilogue_mid_k', 'conv_staged_epilogue_all', 'linattn_staged', 'layernorm_multi',
                       'conv_simt_preload', 'conv_2cta_everywhere', 'conv_2cta_off')
+FORWARD_SWITCHES = ('conv_staged_epilogue', 'linattn_staged', 'layernorm_multi', 'conv_simt_preload', 'conv_2cta')
 DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'layernorm_multi': 0, 'conv_simt_preload': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
 
 
@@ -306,6 +307,22 @@ def run_candidates(unet, x, target, t, sync, timer, steps, emit, candidates=None
                             row['accepted'] = True
                     else:
                         row['rejected'] = 'results differ from the default kernels'
+                    rows.append(row)
+                # ... and the other way round: a switch accepted on the training step that slows the bare forward down is put back
+                # to its default for sampling
+                for key in sorted(k for k in accepted if k in FORWARD_SWITCHES and k not in samp):
+                    row = {'name': 'revert_' + key}
+                    cur = dict(accepted, **samp)
+                    apply(dict(DEFAULTS, **dict(cur, **{key: DEFAULTS[key]})))
+                    timer(fwd, 1)
+                    ms = timer(fwd, 2 * steps)
+                    apply(dict(DEFAULTS, **cur))
+                    timer(fwd, 1)
+                    ref = timer(fwd, 2 * steps)
+                    row['ms'], row['ms_reference'] = ms, ref
+                    if ms < (1.0 - min_gain) * ref:
+                        samp[key] = DEFAULTS[key]
+                        row['accepted'] = True
                     rows.append(row)
                 report['sampling_candidates'] = rows
         except Exception as e:

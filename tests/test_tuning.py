@@ -196,6 +196,16 @@ def test_forward_only_variants_get_a_second_chance_on_the_inference_forward(emu,
     assert rep['complete'] and rep['accepted'] == {'conv_staged_epilogue': 1}
     assert rep['accepted_sampling'] == {'layernorm_multi': 4}
     names = [r['name'] for r in rep['sampling_candidates']]
-    assert names == ['linattn_staged', 'layernorm_multi']            # the one accepted for training is not tried again
+    assert names == ['linattn_staged', 'layernorm_multi', 'revert_conv_staged_epilogue']      # the accepted one is not tried again, only its revert
     assert 'rejected' in rep['sampling'] and not rep.get('sampling_cuda_graph')
     assert state['cd_layernorm_set_multi'] == 0 and state['cd_conv_tc_set_staged_epilogue'] == 1       # training switches left applied
+
+    # the other direction: a switch accepted on the training step that slows the bare forward is reverted for sampling only
+    def timer2(fn, n):
+        if torch.is_grad_enabled():
+            return 100.0 - (10 if state.get('cd_conv_tc_set_staged_epilogue') == 1 else 0)
+        return 10.0 + (0.5 if state.get('cd_conv_tc_set_staged_epilogue') == 1 else 0)
+    rep = tuning.run_candidates(u, [g['x']], [g['target']], [g['t']], lambda: None, timer2, 1, lambda r: None, candidates=cands[:1],
+                                sampling_graph=True)
+    assert rep['accepted'] == {'conv_staged_epilogue': 1} and rep['accepted_sampling'] == {'conv_staged_epilogue': 0}
+    assert state['cd_conv_tc_set_staged_epilogue'] == 1                                                # training configuration left applied
