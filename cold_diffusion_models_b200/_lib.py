@@ -82,12 +82,12 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-_LAUNCHES = {'cd_linattn_context': 2, 'cd_conv_wgrad': 2, 'cd_time_mlp_fwd': 2, 'cd_time_mlp2_fwd': 2, 'cd_version': 0, 'cd_last_error': 0}
+_LAUNCHES = {'cd_linattn_context': 2, 'cd_linattn_context_det': 2, 'cd_conv_wgrad': 2, 'cd_time_mlp_fwd': 2, 'cd_time_mlp2_fwd': 2, 'cd_version': 0, 'cd_last_error': 0}
 _launch_count = 0
 
 
 _PROF_SHAPE_ARGS = {'cd_dwconv7_fwd': (2, 3, 4, 5), 'cd_dwconv7_wgrad': (4, 5, 6, 7), 'cd_layernorm_bwd': (6, 7),
-                    'cd_layernorm_fwd': (2, 3), 'cd_linattn_context': (2, 3), 'cd_linattn_bwd_kv': (2, 3)}
+                    'cd_layernorm_fwd': (2, 3), 'cd_linattn_context': (2, 3), 'cd_linattn_context_det': (2, 3), 'cd_linattn_bwd_kv': (2, 3)}
 _prof = None          # tools/op_profile.py: list of (name, event0, event1) while profiling, else None
 
 

@@ -59,6 +59,12 @@ __device__ __forceinline__ void cd_cp_async4(float* smem_dst, const float* gsrc,
   const int sz = valid ? 4 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
+// asynchronous 16-byte global->shared copy (LDGSTS.128, L2 only); !valid zero-fills the destination
+__device__ __forceinline__ void cd_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cd_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float cd_warp_sum(float v) {
 #pragma unroll

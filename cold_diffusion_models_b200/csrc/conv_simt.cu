@@ -154,7 +154,7 @@ conv_smallc_kernel(const SimtParams p) {
 // opt-in (cd_conv_simt_set_preload): the register-tiled image-edge kernels run ONE block of 8 warps per SM (~185-227 registers per
 // thread), so nothing hides the memory latency of the staging loop below; with the switch on, the (at most three) receptive-field
 // entries a thread stages per 64-pixel chunk are all loaded before the first one is stored.  Same values in the same places.
-static int g_simt_preload = 0;
+static int g_simt_preload = 1;   // validated on a B200 in round 2
 __device__ __forceinline__ void stage_patches_preload(float* patch_f, int KP, long long q0, long long pend, const float* __restrict__ src,
                                                       int ld, int C, int H, int W, int Hg, int Wg, int sy, int sx, int ntaps,
                                                       const int* dyv, const int* dxv) {

@@ -224,11 +224,6 @@ dwconv7_tile_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, 
 // resident blocks per SM cannot cover it) and ran at ~22 % of the FMA rate it is bound by.
 // ---------------------------------------------------------------------------------------------
 constexpr int kDwPTY = 16;
-__device__ __forceinline__ void cd_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
 // stage one (TY+6) x (TX+6) x 32-channel input tile (zero outside the image) with 16-byte LDGSTS; 8 lanes per pixel
 template <int TX>
 __device__ __forceinline__ void dw_issue_tile(float* buf, const float* __restrict__ base, int x_ld, int H, int W, int x0, int y0) {
@@ -911,12 +906,10 @@ __global__ void __launch_bounds__(512)
 groupnorm_kernel(const float* __restrict__ x, int x_ld, int HW, int C, int groups, const float* __restrict__ cond, int cond_ld,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int swish,
                  float* __restrict__ y, int y_ld) {
-  extern __shared__ float sm[];                 // sum[groups] | sq[groups]
-  float* gsum = sm; float* gsq = sm + groups;
+  extern __shared__ float sm[];                 // sum[groups] | sq[groups] | part[8][blockDim]
+  float* gsum = sm; float* gsq = sm + groups; float* part = sm + 2 * groups;
   const int b = blockIdx.x;
   const int nq = C >> 2, cg = C / groups;
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const long long base = static_cast<long long>(b) * HW;
   // thread -> (pixel lane, channel quad): consecutive threads walk consecutive quads of one pixel (coalesced)
   const int q = threadIdx.x % nq, pl = threadIdx.x / nq, np = blockDim.x / nq;
@@ -930,12 +923,19 @@ groupnorm_kernel(const float* __restrict__ x, int x_ld, int HW, int C, int group
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;
     }
-    if (cg >= 4) {                               // the whole quad lies in one group
-      atomicAdd(&gsum[(q * 4) / cg], s[0] + s[1] + s[2] + s[3]);
-      atomicAdd(&gsq[(q * 4) / cg], s2[0] + s2[1] + s2[2] + s2[3]);
-    } else {
-      for (int j = 0; j < 4; ++j) { atomicAdd(&gsum[(q * 4 + j) / cg], s[j]); atomicAdd(&gsq[(q * 4 + j) / cg], s2[j]); }
+    // per-thread partial sums go to shared memory and are added per group in a FIXED order below (shared-memory atomics made the
+    // statistics, and through the TF32 roundings downstream the network output, differ from run to run)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { part[j * blockDim.x + threadIdx.x] = s[j]; part[(4 + j) * blockDim.x + threadIdx.x] = s2[j]; }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, a2 = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      const int qq = c >> 2, j = c & 3;
+      for (int pp = 0; pp < np; ++pp) { a += part[j * blockDim.x + pp * nq + qq]; a2 += part[(4 + j) * blockDim.x + pp * nq + qq]; }
     }
+    gsum[g] = a; gsq[g] = a2;
   }
   __syncthreads();
   const float inv_n = 1.f / (static_cast<float>(HW) * cg);
@@ -1081,7 +1081,7 @@ extern "C" int cd_groupnorm_fwd(const float* x, int x_ld, int B, int64_t HW, int
                                 const float* gamma, const float* beta, float eps, int swish, float* y, int y_ld, void* stream) {
   CD_REQUIRE(C % 4 == 0 && C % groups == 0 && C / 4 <= 512 && x_ld % 4 == 0 && y_ld % 4 == 0 && (!cond || cond_ld % 4 == 0),
              "cd_groupnorm_fwd: unsupported C=%d groups=%d", C, groups);
-  groupnorm_kernel<<<B, 512, sizeof(float) * 2 * groups, static_cast<cudaStream_t>(stream)>>>(x, x_ld, (int)HW, C, groups, cond, cond_ld,
+  groupnorm_kernel<<<B, 512, sizeof(float) * (2 * groups + 8 * 512), static_cast<cudaStream_t>(stream)>>>(x, x_ld, (int)HW, C, groups, cond, cond_ld,
                                                                                            gamma, beta, eps, swish, y, y_ld);
   CD_LAUNCH_CHECK();
   return 0;

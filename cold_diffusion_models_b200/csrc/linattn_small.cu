@@ -11,7 +11,7 @@
 
 namespace {
 
-int g_staged = 0;
+int g_staged = 1;        // validated on a B200 in round 2
 constexpr int kRows = 64;            // channel rows (co) staged per pass
 
 // weff[b][co][h*32+d] = sum_e w_out[co][h*32+e] * ctxn[d][e],  ctxn[d][e] = ctx[b][h][d][e] * scale / ksum[b][h*32+d]

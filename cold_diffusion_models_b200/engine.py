@@ -112,8 +112,16 @@ class UnetEngine(_BackwardHolder):
         self.cond_blocks = [b for b in self.blocks.values() if b.cond_off is not None]
 
     # ------------------------------------------------------------------------------------------
+    _epoch = 0            # bumped by every in-place parameter update that bypasses torch's version counters
+
     def mark_weights_dirty(self):
+        """the parameters changed behind torch's back (fused Adam / EMA kernels write the flat buffer through raw pointers, so
+        `p._version` stays put): every packed operand -- forward, data-gradient and graph-captured -- is stale."""
         self._dirty = True
+        self._epoch += 1
+
+    def _weights_key(self):
+        return (self._epoch, self._params_version())
 
     def param_list(self):
         return [p for p in self.unet.parameters()]
@@ -305,7 +313,9 @@ class UnetEngine(_BackwardHolder):
         ksum = self.buf('ksum.' + uniq, (B, 128))
         ctx = self.buf('ctx.' + uniq, (B, 4, 32, 32))
         weff = self.buf('weff.' + uniq, (B, dim, 128))
-        call('cd_linattn_context', ptr(qkv), 384, B, n, ptr(kmax), ptr(ksum), ptr(ctx), stream())
+        nblk, ppb = ops.linattn_ctx_plan(B, n, self.dev)
+        ws = self.buf('ctxws.' + uniq, (B, nblk, 4352))
+        call('cd_linattn_context_det', ptr(qkv), 384, B, n, nblk, ppb, ptr(ws), ptr(kmax), ptr(ksum), ptr(ctx), stream())
         call('cd_linattn_weff', ptr(ctx), ptr(ksum), ptr(spec.attn.to_out.weight), B, dim, C.c_float(spec.attn.scale), 0,
              ptr(weff), stream())
         do = ops.make_conv_desc([(View(qkv, 0, 128), T1, weff, True)], outv, (B, H, W), Cout=dim,
@@ -326,10 +336,12 @@ class UnetEngine(_BackwardHolder):
         self._graphs = {}
 
     def forward_graphed(self, x, time):
-        key = (tuple(x.shape), self._params_version())
+        # the packs write into persistent buffers, so a captured graph stays valid across weight updates: repack before
+        # every replay (no-op when nothing changed) instead of keying the graph on the weights
+        self.prepare_weights()
+        key = tuple(x.shape)
         g = self._graphs.get(key)
         if g is None:
-            self.prepare_weights()
             sx = x.contiguous().float().clone()
             st = time.to(device=x.device, dtype=torch.int64).contiguous().clone()
             side = torch.cuda.Stream()
@@ -356,6 +368,14 @@ class UnetEngine(_BackwardHolder):
         x = x.contiguous().float()
         time = time.to(device=x.device, dtype=torch.int64).contiguous()
         self.prepare_weights()
+        # activations live in engine buffers keyed by (layer, shape): a later forward at the same shape overwrites what an
+        # earlier training forward saved for its backward.  Stamp every forward; backward() refuses a stale `save`.
+        self._fwd_gen = getattr(self, '_fwd_gen', 0) + 1
+        if getattr(self, '_gen_by_shape', None) is None:
+            self._gen_by_shape = {}
+        self._gen_by_shape[tuple(x.shape)] = self._fwd_gen
+        if save is not None:
+            save['_gen'] = (tuple(x.shape), self._fwd_gen)
         P = self._packed
         ld0 = Cc if Cc % 4 == 0 else 4
         x0 = self.buf('x0', (B, H, W, ld0))

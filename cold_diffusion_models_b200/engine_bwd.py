@@ -79,7 +79,7 @@ class BackwardMixin:
 
     def prepare_weights_bwd(self):
         """packed operands of the data-gradient convolutions (mode 1: N = in-channels, K = out-channels)."""
-        ver = self._params_version()
+        ver = self._weights_key()
         if getattr(self, '_bwd_version', None) == ver:
             return
         batch = self._repack_batch('pack_bwd', 'pack')
@@ -252,6 +252,11 @@ class BackwardMixin:
     def backward(self, save, dout):
         """dout: (B, out_dim, H, W) NCHW gradient of the network output.  Accumulates into self.G."""
         unet = self.unet
+        shape, gen = save.get('_gen', (None, None))
+        if shape is not None and self._gen_by_shape.get(shape) != gen:
+            raise RuntimeError("Unet backward: another forward with input shape %r ran on this network after the forward being "
+                               "differentiated; the engine keeps one set of saved activations per input shape -- call "
+                               "backward() before the next forward (e.g. accumulate micro-batches one at a time)" % (shape,))
         self._setup_grads()
         self.prepare_weights_bwd()
         P, G = self._packed, self.G

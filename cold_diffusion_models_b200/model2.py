@@ -302,9 +302,6 @@ class Model(nn.Module):
             raise RuntimeError("cold_diffusion_models_b200.Model runs on a B200 (CUDA) device only; got %s" % x.device)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from . import model2_train
-            if not model2_train.enabled():
-                raise NotImplementedError("Model (DDPM UNet) is inference/sampling-only in this round; wrap calls in torch.no_grad() "
-                                          "(the training path of model2_train.py is not validated on a B200 yet: COLDDIFF_MODEL_TRAINING=1)")
             return model2_train.ModelFunction.apply(self, x, t, *self.engine.param_list())
         assert x.shape[2] == x.shape[3] == self.resolution
         self._prepare()

@@ -2,9 +2,9 @@
 backward schedule, on the same sm_100a kernels as the ConvNeXt Unet (tap-list convolutions for every dense conv and for the
 four batched matmuls of the AttnBlock backward; model2_bwd.cu for GroupNorm / softmax / upsample / dropout).
 
-STATUS: written at the end of round 1 after the GPU budget was spent -- compiled, imported and unit-checked on the CPU side
-only.  It is reachable solely with COLDDIFF_MODEL_TRAINING=1 (otherwise `Model.forward` keeps raising under autograd);
-tests/test_model2_train_gpu.py compares every parameter gradient with the reference (tests/golden/model2_grads_small.npz).
+STATUS: validated on a B200 in round 2 (profiles/gpu_tests_r02a.txt): tests/test_model2_train_gpu.py compares every parameter
+gradient with the reference (tests/golden/model2_grads_small.npz) on the fp32 and the tcgen05 path, checks the dropout mask
+consistency and one Trainer step.
 
 Gradient routing: every activation that the forward writes into a (slice of a) buffer has a gradient buffer of the same shape;
 consumers ADD into it (dense data-gradient convolutions accumulate through their `resid` input, the rest through cd_add) and the
@@ -25,7 +25,7 @@ T3D = ops.taps_conv_dgrad(3, 1)
 
 
 def enabled():
-    return os.environ.get('COLDDIFF_MODEL_TRAINING') == '1'
+    return True
 
 
 def taps_down_dgrad(py, px):
@@ -80,7 +80,9 @@ class ModelEngine:
                 p.grad = g
 
     def mark_weights_dirty(self):
+        # the fused Adam / EMA kernels write through raw pointers (p._version does not move): drop both pack generations
         self.model._version = None
+        self.model._bwd_version = None
 
     def param_list(self):
         return list(self.model.parameters())

@@ -194,3 +194,22 @@ def conv_fwd(desc, impl=CONV_TC):
 
 def conv_wgrad(desc, dout, dw_packed, db=None, impl=CONV_SIMT):
     call('cd_conv_wgrad', C.byref(desc), C.c_void_p(dout.addr()), dout.ld, ptr(dw_packed), ptr(db), impl, stream())
+
+
+_SM_COUNT = {}
+
+
+def linattn_ctx_plan(B, n, device=None):
+    """how cd_linattn_context_det cuts the pixel axis of one image: -> (nblk, ppb) with ppb a multiple of 32 and
+    nblk = ceil(n / ppb) partials per image; about one wave of resident blocks (3 per SM) over the whole batch"""
+    key = str(device)
+    sms = _SM_COUNT.get(key)
+    if sms is None:
+        try:
+            sms = torch.cuda.get_device_properties(device).multi_processor_count if (device is not None and torch.device(device).type == 'cuda') else 148
+        except Exception:
+            sms = 148
+        _SM_COUNT[key] = sms
+    per_img = max(1, (3 * sms) // max(B, 1))
+    ppb = max(64, -(-(-(-n // per_img)) // 32) * 32)
+    return -(-n // ppb), ppb

@@ -202,6 +202,9 @@ class Trainer(EvaluationMixin, object):
         self.gradient_accumulate_every = gradient_accumulate_every
         self.train_num_steps = train_num_steps
 
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self._world = torch.distributed.get_world_size() if dist_on else 1
+        self._rank = torch.distributed.get_rank() if dist_on else 0
         core = _unwrap(self.model)
         self.ds, self.dl = self._make_loader(folder, dataset, shuffle, seed=1234)
         # the restoration network is `denoise_fn` in every package except defading (`defade_fn`, DFG:303)
@@ -216,18 +219,30 @@ class Trainer(EvaluationMixin, object):
         self.reset_parameters()
         if load_path is not None:
             self.load(load_path)
-        self._world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self._sync_replicas()
 
     _aug_datasets = ('mnist', 'cifar10', 'flower', 'celebA', 'AFHQ')     # `dataset` values that select Dataset_Aug1
 
+    def _sync_replicas(self):
+        """one process per GPU: every replica starts from rank 0's parameters and EMA weights (the reference's nn.DataParallel
+        re-broadcasts them every micro-step, celebA_128.py:102); Adam + EMA then stay bit-identical on all ranks because they
+        consume the same all-reduced gradient."""
+        if self._world <= 1:
+            return
+        for eng in (self._unet.engine, self._ema_unet.engine):
+            torch.distributed.broadcast(eng.flat_param, src=0)
+            eng.mark_weights_dirty()
+
     def _make_loader(self, folder, dataset, shuffle, seed):
         channels = getattr(_unwrap(self.model), 'channels', 3)
+        world, rank = self._world, self._rank
         if folder is None or dataset == 'synthetic':
-            ds = SyntheticImages(self.image_size, channels, seed=seed)
+            # every rank reads its own stream of images (DataParallel scatters one batch; here the global batch is world x B)
+            ds = SyntheticImages(self.image_size, channels, seed=seed + 1000003 * rank)
             return ds, cycle(data.DataLoader(ds, batch_size=self.batch_size, shuffle=False, pin_memory=True, num_workers=0,
                                              drop_last=True))
         if dataset in ('device', 'device_aug'):            # images resident in HBM, batches gathered by cd_augment_u8
-            ds = DeviceImageDataset(folder, self.image_size, augment=(dataset == 'device_aug'))
+            ds = DeviceImageDataset(folder, self.image_size, augment=(dataset == 'device_aug'), seed=rank)
 
             def gen():
                 while True:
@@ -236,6 +251,10 @@ class Trainer(EvaluationMixin, object):
         aug = dataset in self._aug_datasets
         print(dataset, "DA used" if aug else "")
         ds = ImageFolderDataset(folder, self.image_size, augment=aug)
+        if world > 1:                                      # disjoint shards of every epoch, one per rank
+            sampler = data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=shuffle, seed=seed)
+            return ds, cycle(data.DataLoader(ds, batch_size=self.batch_size, sampler=sampler, pin_memory=True,
+                                             num_workers=8 if aug else 16, drop_last=True))
         return ds, cycle(data.DataLoader(ds, batch_size=self.batch_size, shuffle=shuffle, pin_memory=True,
                                          num_workers=8 if aug else 16, drop_last=True))
 
@@ -254,6 +273,8 @@ class Trainer(EvaluationMixin, object):
         e.mark_weights_dirty()
 
     def save(self, itrs=None):
+        if getattr(self, '_rank', 0) != 0:                 # replicas are identical: rank 0 writes the checkpoint
+            return
         d = {'step': self.step, 'model': self.model.state_dict(), 'ema': self.ema_model.state_dict()}
         name = 'model.pt' if itrs is None else f'model_{itrs}.pt'
         torch.save(d, str(self.results_folder / name))
@@ -264,6 +285,8 @@ class Trainer(EvaluationMixin, object):
         self.step = d['step']
         self.model.load_state_dict(_match_prefix(d['model'], self.model))
         self.ema_model.load_state_dict(_match_prefix(d['ema'], self.ema_model))
+        if getattr(self, '_world', 1) > 1 and hasattr(self, 'opt'):
+            self._sync_replicas()
 
     # ---- hot loop --------------------------------------------------------------------------------------
     def _next(self):
@@ -311,7 +334,7 @@ class Trainer(EvaluationMixin, object):
         acc_loss = 0
         while self.step < self.train_num_steps:
             loss = self.train_step()
-            if self.step % 100 == 0:
+            if self.step % 100 == 0 and self._rank == 0:
                 print(f'{self.step}: {loss.item()}')
             acc_loss = acc_loss + loss
             if self.step != 0 and self.step % self.save_and_sample_every == 0:
@@ -320,9 +343,11 @@ class Trainer(EvaluationMixin, object):
                 og_img = self._sample_start()
                 xt, direct_recons, all_images = self._periodic_sample(og_img)
                 for name, img in (('og', og_img), ('recon', all_images), ('direct_recons', direct_recons), ('xt', xt)):
-                    utils.save_image((img + 1) * 0.5, str(self.results_folder / f'sample-{name}-{milestone}.png'), nrow=6)
+                    if self._rank == 0:
+                        utils.save_image((img + 1) * 0.5, str(self.results_folder / f'sample-{name}-{milestone}.png'), nrow=6)
                 acc_loss = acc_loss / (self.save_and_sample_every + 1)
-                print(f'Mean of last {self.step}: {float(acc_loss)}')
+                if self._rank == 0:
+                    print(f'Mean of last {self.step}: {float(acc_loss)}')
                 acc_loss = 0
                 self.save()
                 if self.step % (self.save_and_sample_every * 100) == 0:

@@ -48,7 +48,7 @@ CANDIDATES = [
 FORWARD_CANDIDATES = ('conv_staged_epilogue_short_k', 'conv_staged_epilogue_mid_k', 'conv_staged_epilogue_all', 'linattn_staged', 'layernorm_multi',
                       'conv_simt_preload', 'conv_2cta_everywhere', 'conv_2cta_off')
 FORWARD_SWITCHES = ('conv_staged_epilogue', 'linattn_staged', 'layernorm_multi', 'conv_simt_preload', 'conv_2cta')
-DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 0, 'batched_repack': 0, 'layernorm_multi': 0, 'conv_simt_preload': 0, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
+DEFAULTS = {'conv_2cta': 1, 'conv_staged_epilogue': 0, 'linattn_staged': 1, 'batched_repack': 0, 'layernorm_multi': 4, 'conv_simt_preload': 1, 'merge_micro_batches': 0, 'wgrad_bias_fusion': 0}
 
 
 def apply(settings):

@@ -166,6 +166,14 @@ int cd_linattn_context(const float* qkv, int ld, int B, int n, float* kmax, floa
                        float* ctx /*[B][4][32][32]*/, void* stream);
 int cd_linattn_weff(const float* ctx, const float* ksum, const float* w_out /*[dim][128]*/, int B, int dim,
                     float scale, int round_tf32, float* weff /*[B][dim][128]*/, void* stream);
+/* The same kmax / ksum / ctx as cd_linattn_context, DETERMINISTIC (bit-identical run to run) and in one pass over k and v
+ * (csrc/linattn_ctx.cu): blocks walk spans of `ppb` pixels with a running max (flash-attention recurrence), the per-head E^T V
+ * products run as 3xTF32 mma.sync, each block writes one partial (ctx[4][32][32] | m[128] | s[128] = 4352 floats) to `ws`
+ * ([B][nblk][4352] floats, caller-allocated) and a second kernel merges the partials of an image in block order.
+ * The caller picks ppb (a multiple of 32; about one wave of blocks at 3 blocks per SM over the batch) and nblk = ceil(n / ppb).
+ * This is what the engine calls; cd_linattn_context (float atomics) stays for A/B comparisons. */
+int cd_linattn_context_det(const float* qkv, int ld, int B, int n, int nblk, int ppb, float* ws, float* kmax, float* ksum,
+                           float* ctx /*[B][4][32][32]*/, void* stream);
 
 /* final 1x1 conv to image channels + optional residual, NHWC -> reference NCHW (DB:253,279-282) */
 int cd_conv1x1_to_nchw(const float* x, int ld, int B, int H, int W, int C, const float* w /*[Co][C]*/,

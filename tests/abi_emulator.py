@@ -490,6 +490,13 @@ def cd_linattn_context(qkv, ld, B, n, kmax, ksum, ctx, stream):
     return 0
 
 
+def cd_linattn_context_det(qkv, ld, B, n, nblk, ppb, ws, kmax, ksum, ctx, stream):
+    nblk, ppb = _v(nblk), _v(ppb)
+    assert ppb % 32 == 0 and nblk == -(-_v(n) // ppb)
+    _arr(ws, (_v(B), nblk, 4352), (nblk * 4352, 4352, 1))[:] = np.float32(0)        # the workspace is caller-owned and writable
+    return cd_linattn_context(qkv, ld, B, n, kmax, ksum, ctx, stream)
+
+
 def cd_linattn_weff(ctx, ksum, w_out, B, dim, scale, round_tf32, weff, stream):
     c = _arr(ctx, (B, 4, 32, 32), (4096, 1024, 32, 1)).astype(np.float64)
     ks = _arr(ksum, (B, 4, 32), (128, 32, 1)).astype(np.float64)

@@ -79,6 +79,18 @@ def _kernel_expr_start(s, end):
 _PTX_HELPER_BODIES = {
     'cd_cp_async4': '{ if (valid) memcpy(smem_dst, gsrc, 4); else memset(smem_dst, 0, 4); }',
     'cd_cp_async16': '{ if (valid) memcpy(smem_dst, gsrc, 16); else memset(smem_dst, 0, 16); }',
+    # warp-level m16n8k8 MMA (PTX fragment layout) through lane exchanges: D[g][2t+j] += sum_k A[g][k] B[k][2t+j]
+    'cd_mma_m16n8k8_tf32': '''{ const int lane_ = threadIdx.x & 31, g_ = lane_ >> 2, t_ = lane_ & 3;
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+      for (int k_ = 0; k_ < 8; ++k_) {
+        const int kk_ = k_ & 3, hi_ = k_ >> 2;
+        const float ag = __shfl_sync(0xffffffffu, hi_ ? a[2] : a[0], g_ * 4 + kk_);
+        const float ah = __shfl_sync(0xffffffffu, hi_ ? a[3] : a[1], g_ * 4 + kk_);
+        const float b0_ = __shfl_sync(0xffffffffu, hi_ ? b[1] : b[0], (2 * t_) * 4 + kk_);
+        const float b1_ = __shfl_sync(0xffffffffu, hi_ ? b[1] : b[0], (2 * t_ + 1) * 4 + kk_);
+        c0 += ag * b0_; c1 += ag * b1_; c2 += ah * b0_; c3 += ah * b1_;
+      }
+      d[0] += c0; d[1] += c1; d[2] += c2; d[3] += c3; }''',
     'cd_round_tf32': '{ unsigned u = __float_as_uint(x); u = (u + 0x1000u) & ~0x1FFFu; return __uint_as_float(u); }',
 }
 
@@ -125,7 +137,7 @@ def rewrite(src):
     return out + src[i:]
 
 
-SIMT_UNITS = ['api.cu', 'elementwise.cu', 'backward.cu', 'degrade.cu', 'conv_simt.cu', 'model2_bwd.cu', 'repack.cu', 'linattn_small.cu', 'layernorm_multi.cu', 'final_proj.cu']
+SIMT_UNITS = ['api.cu', 'elementwise.cu', 'backward.cu', 'degrade.cu', 'conv_simt.cu', 'model2_bwd.cu', 'repack.cu', 'linattn_small.cu', 'layernorm_multi.cu', 'final_proj.cu', 'linattn_ctx.cu']
 
 
 def build_all():

@@ -288,8 +288,6 @@ def test_wgrad_per_batch(ops, impl, hw):
     assert rel(dweff.cpu(), ref) < 1e-5
 
 
-@pytest.mark.skipif(__import__('os').environ.get('COLDDIFF_EXPERIMENTAL') != '1',
-                    reason='opt-in kernels written after the round-1 GPU budget was spent (cd_wgrad_tc_set_bias_fusion)')
 @pytest.mark.parametrize('case', [(2, 64, 128, 32, 32, 3), (3, 128, 256, 16, 16, 3), (2, 64, 192, 32, 32, 1), (4, 256, 64, 16, 16, 3)])
 def test_wgrad_tc_fused_bias_gradient(ops, case):
     """bias gradient folded into the tcgen05 weight gradient (one extra 128x32x8 MMA per k-step against a tile of ones):

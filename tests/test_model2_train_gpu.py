@@ -2,15 +2,13 @@
 reference (tests/golden/model2_grads_small.npz), fp32 CUDA-core convolutions tight and tcgen05 (TF32) within the north-star
 tolerance, plus dropout consistency and one Trainer step.
 
-Skipped unless COLDDIFF_MODEL_TRAINING=1: model2_train.py / csrc/model2_bwd.cu were written after the round-1 GPU budget was
-spent; their host logic is checked on CPU (tests/test_model2_host_logic.py), the kernels have not run on a B200 yet."""
+The host logic of the same schedule is checked on CPU by tests/test_model2_host_logic.py."""
 import os
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('COLDDIFF_MODEL_TRAINING') != '1', reason='Model training path not validated yet (set COLDDIFF_MODEL_TRAINING=1)')]
+pytestmark = [pytest.mark.gpu]
 G = os.path.join(os.path.dirname(__file__), 'golden')
 
 

@@ -307,6 +307,29 @@ def test_linattn_context_preload_variant_equals_the_default(cpulib, B, n, ld):
     assert close(res[1], torch.cat([kmax.reshape(-1), ksum.reshape(-1), ctx.reshape(-1)]), 2e-5)
 
 
+@pytest.mark.parametrize('B,n,ld,ppb', [(2, 256, 384, 64), (1, 1000, 392, 96), (3, 40, 384, 64), (1, 16, 384, 64)])
+def test_linattn_context_deterministic_one_pass_kernel(cpulib, B, n, ld, ppb):
+    """cd_linattn_context_det (csrc/linattn_ctx.cu): running-max recurrence + 3xTF32 mma fragments + ordered merge of the
+    per-block partials -> kmax exact, ksum / ctx at fp32 accuracy against the float64 statement, and bit-identical under both
+    thread orders of the CPU executor (no atomics anywhere)"""
+    g = torch.Generator().manual_seed(n + ld)
+    qkv = torch.randn(B, n, ld, generator=g) * 3.0
+    nblk = -(-n // ppb)
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        kmax, ksum, ctx = torch.full((B, 128), 7.0), torch.full((B, 128), 7.0), torch.full((B, 4, 32, 32), 7.0)
+        ws = torch.full((B, nblk, 4352), float('nan'))
+        assert cpulib.cd_linattn_context_det(P(qkv), ld, B, n, nblk, ppb, P(ws), P(kmax), P(ksum), P(ctx), C.c_void_p(0)) == 0
+        res.append(torch.cat([kmax.reshape(-1), ksum.reshape(-1), ctx.reshape(-1)]))
+    cpulib.simt_set_reverse_order(0)
+    assert torch.equal(res[0], res[1])
+    kmax, ksum, ctx = torch.zeros(B, 128), torch.zeros(B, 128), torch.zeros(B, 4, 32, 32)
+    assert E.cd_linattn_context(P(qkv), ld, B, n, P(kmax), P(ksum), P(ctx), None) == 0
+    assert torch.equal(res[0][:B * 128], kmax.reshape(-1))
+    assert close(res[0], torch.cat([kmax.reshape(-1), ksum.reshape(-1), ctx.reshape(-1)]), 3e-6)
+
+
 @pytest.mark.parametrize('Cout,k', [(128, 3), (64, 1)])
 def test_image_edge_kernels_with_preloaded_staging_equal_the_default(cpulib, Cout, k):
     """cd_conv_simt_set_preload: conv_smallc4_kernel / wgrad_smallc4_kernel (3-channel image edge) with all receptive-field
