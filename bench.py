@@ -15,12 +15,14 @@ pinned-host batches copied H2D and the loss read back D2H inside the timed regio
 metric (200-step sample images/sec) is measured on a bounded number of reverse steps and reported in
 `sample`; nothing is skipped inside a timed region.
 
-Before timing, cold_diffusion_models_b200.tuning.autotune() lets a child process validate the opt-in kernel variants (all default
-off) against the default kernels on this network and batch and time them; accepted variants are switched on for the headline
-measurements and listed in `tuning` (--no-autotune: defaults only).  A single-GPU run performs that whole tuned measurement in a
-child process of its own and falls back to measuring the default kernels in-process if the child fails.  `op_profile` is the in-situ
-time per C-ABI entry point of one step, `merged_micro_batches` the throughput with the two micro-batches concatenated into one pass
-(validated by the same check, not the headline).
+Both arms print the SAME `metric` string, unit and workload so that the driver can divide them.  The reference arm
+(`--impl reference`) times the reference algorithm (oracle/: the eager-PyTorch restatement of the reference's p_losses, 200-step
+Python q_sample loop included; the reference itself is Python under /root/reference and does not exist on the GPU box) on the host
+cores at a bounded batch per step.  The same restatement on cuda:0 at the full micro-batch of 32 -- how the reference is deployed,
+cuDNN / cuBLAS eager -- is measured once per single-GPU run and reported as `reference_eager_b200` (the comparator SURVEY 8d
+calls the real bar).  The sampling half of the metric is one complete `GaussianDiffusion.sample(batch_size=32, img=...)` call of
+200 reverse steps through the public API (`sample`).  `op_profile` is the in-situ time per C-ABI entry point of one step.
+All kernels run in their default configuration (no start-up tuning).
 """
 import argparse
 import json
@@ -141,22 +143,43 @@ def cpu_train_sample(batch=2, steps=1, warmup=0, threads=None, device='cpu'):
                              ms_per_step=sec * 1e3)
 
 
+METRIC = "training-step images/sec (CelebA-128 deblur UNet, config 3)"
+WORKLOAD = "C3: CelebA-128 deblur train step = 2 micro-batches x 32 img/GPU (p_losses fwd+bwd) + grad all-reduce + Adam + EMA"
+REF_CPU_BATCH = 4          # images per reference step on the host cores (a full 64-image step takes ~20 s of CPU)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     on_gpu = args.reference_device == 'cuda'
-    v, info = cpu_train_sample(batch=32 if on_gpu else 2, steps=max(1, args.steps), warmup=max(1, args.warmup) if on_gpu else min(1, args.warmup),
+    nb = 32 if on_gpu else REF_CPU_BATCH
+    v, info = cpu_train_sample(batch=nb, steps=max(1, args.steps), warmup=max(1, args.warmup) if on_gpu else min(1, args.warmup),
                                device=args.reference_device)
-    line = {"impl": "reference", "metric": "training-step images/sec (CelebA-128 deblur UNet)", "value": v, "unit": "images/s",
+    where = "cuda:0" if on_gpu else "the host cores"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info['ms_per_step'],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("C3 micro-batch (32 images), eager PyTorch restatement on cuda:0" if on_gpu else
-                                    "C3 train step (bounded sample: batch 2 per step on host cores)"), "image": "3x128x128", "T": 200,
+            "config": {"workload": WORKLOAD, "net": "Unet(dim=64, dim_mults=(1,2,4,8), channels=3)", "T": 200,
+                       "blur": "Exponential_reflect k=15 std=0.01",
+                       "reference_sample": "bounded sample of that workload: %d images per step (p_losses fwd+bwd+Adam, same network, T=200 "
+                                           "q_sample loop); eager PyTorch restatement of the reference on %s" % (nb, where),
                        "device": args.reference_device},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": info['cores'], "kind": "port", "sample": info['sample']},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def _timed_loop(fn, n, sync):
+    import torch
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(n):
+        fn(s)
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -166,36 +189,15 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--sample-steps', type=int, default=10, help='reverse steps timed for the sampling half of the metric')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-autotune', action='store_true', help='keep every opt-in kernel variant off (cold_diffusion_models_b200.tuning)')
+    ap.add_argument('--no-sample', action='store_true', help='skip the 200-step sample() measurement (quick runs)')
+    ap.add_argument('--no-others', action='store_true', help='skip the other BASELINE configs and the eager comparator (quick runs)')
+    ap.add_argument('--no-autotune', action='store_true', help='accepted for compatibility; there is no start-up tuning any more')
     ap.add_argument('--reference-device', default='cpu', choices=['cpu', 'cuda'],
                     help="--impl reference only: 'cpu' (the contract) or 'cuda' = the same eager-PyTorch restatement on the GPU (informational)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
-
-    # Single-GPU runs measure the TUNED configuration in a child process first: the opt-in kernel variants the start-up check may
-    # switch on have passed that check on this network and batch, but they have never gone through a whole bench run on a B200;
-    # if the child dies, hangs or prints no line, this process measures the default kernels instead (nothing else changes).
-    if (int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.no_autotune and os.environ.get('COLDDIFF_BENCH_INNER') != '1'):
-        line = None
-        try:
-            from cold_diffusion_models_b200 import _lib as _loaded       # this process loads libcolddiff.so too (it runs the fallback)
-            assert _loaded.lib.cd_version() == 1
-            env = dict(os.environ, COLDDIFF_BENCH_INNER='1')
-            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], capture_output=True, text=True, timeout=900, env=env)
-            sys.stderr.write(r.stderr[-4000:])
-            for ln in r.stdout.splitlines():
-                if ln.startswith('{') and '"metric"' in ln:
-                    json.loads(ln)
-                    line = ln
-        except Exception as e:
-            sys.stderr.write('bench: tuned child failed (%s); measuring the default kernels\n' % repr(e)[:200])
-        if line is not None:
-            print(line)
-            return
-        args.no_autotune = True
 
     import io
     import contextlib
@@ -227,29 +229,6 @@ def main():
     B, A = C3['batch'], C3['accum']
     img_per_step = B * A
 
-    # ---- guarded start-up selection of the opt-in kernel variants (cold_diffusion_models_b200/tuning.py): rank 0 lets a child
-    # process check each variant against the default kernels on this very network and batch and time it; only variants that
-    # reproduce the default results and are faster get switched on, in every rank.  They stay on for the headline measurements
-    # (train step, e2e, sampling, roofline) and are switched off again around the other configs, whose shapes the child did not see.
-    from cold_diffusion_models_b200 import tuning
-    tuned = {'accepted': {}, 'report': {'skipped': True}}
-    if not args.no_autotune:
-        if rank == 0:
-            tuned = tuning.autotune(dim=C3['dim'], dim_mults=C3['dim_mults'], channels=C3['channels'], image_size=C3['image_size'],
-                                    batch=B, accum=A, device=local, timeout=300)
-        if world > 1:
-            box = [tuned]
-            dist.broadcast_object_list(box, src=0)
-            tuned = box[0]
-            if rank != 0:
-                tuning.apply(tuned['accepted'])
-    # The headline keeps the reference's step structure (2 micro-batches of 32, gradients accumulated).  Running them as one pass over
-    # their concatenation (same gradient) is measured separately below when the start-up check accepted it.
-    merge_ok = bool(tuned['accepted'].pop('merge_micro_batches', None))
-    from cold_diffusion_models_b200 import trainer as _trainer_mod
-    if not args.no_autotune:
-        _trainer_mod.merge_micro_batches(False)
-
     # distinct batches so consecutive steps never re-read the same inputs; activations (>3 GB/step) exceed the 126 MB L2
     g = torch.Generator().manual_seed(1234 + rank)
     nb = 4
@@ -263,14 +242,7 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for s in range(steps):
-            fn(s)
-        e1.record()
-        sync_all()
-        ms = e0.elapsed_time(e1)
+        ms = _timed_loop(fn, steps, sync_all)
         if world > 1:
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -297,141 +269,40 @@ def main():
     ms = timed(step_resident, K)
     launches = _lib.launch_count()
     ms_e2e = timed(step_e2e, K)
-    if sampler:
-        sampler.stop_flag = True
     value = img_per_step * world * K / (ms / 1e3)
     e2e = img_per_step * world * K / (ms_e2e / 1e3)
-    merged = None
-    if merge_ok:
-        # the same K optimizer steps with the micro-batches concatenated into one pass (trainer.merge_micro_batches; same gradient)
-        _trainer_mod.merge_micro_batches(True)
-        for s in range(2):
-            step_resident(s)
-        ms_mrg = timed(step_resident, K)
-        _trainer_mod.merge_micro_batches(False)
-        merged = {"value": img_per_step * world * K / (ms_mrg / 1e3), "unit": "images/s", "ms_per_step": ms_mrg / K,
-                  "note": "one pass over the %d concatenated micro-batches of %d per optimizer step (the loss is their mean: same gradient); "
-                          "not the headline, which accumulates them one after the other like the reference" % (A, B)}
 
-    # ---- sampling half of the metric: x0_step_down reverse steps (UNet forward + Algorithm-2 update) -----------
+    # ---- sampling half of the metric: ONE complete 200-step x0_step_down sample() through the public API per rank
+    # (degradation of the input to x_T + 200 x [UNet forward + Algorithm-2 update]); CUDA-graph replay of the inference forward on
     ema = trainer.ema_model
-    S = args.sample_steps
-    ema.denoise_fn.eval()
-    graph_sampling = bool(tuned['report'].get('sampling_cuda_graph'))
-    samp_sw = dict(tuned['report'].get('accepted_sampling') or {})      # forward-only variants accepted on the inference forward
-    if samp_sw:
-        tuning.apply(dict(tuning.DEFAULTS, **dict(tuned['accepted'], **samp_sw)))
-    if graph_sampling:                       # the child found the CUDA-graph replay of the inference forward equal and faster
+    sample = None
+    if not args.no_sample:
         ema.denoise_fn.engine.enable_cuda_graph(True)
-    xs = resident[0]
-    with torch.no_grad():
-        img = ema.opt(xs)                                    # x_T = D(x, T)
-        t = C3['timesteps']
-
-        def rev(s):
-            nonlocal img, t
-            step = torch.full((B,), t - 1, dtype=torch.long, device=dev)
-            x0 = ema.denoise_fn(img, step)
-            img = ema._reverse_step(img, x0, t)
-            t -= 1
-        for s in range(3):
-            rev(s)
-        ms_s = timed(rev, S)
-    sample_ms_per_rev_step = ms_s / S
-    if graph_sampling:
+        xs = resident[0]
+        with torch.no_grad():
+            ema.sample(batch_size=B, img=xs, t=3)                 # warm-up: graph capture, workspaces (3 reverse steps)
+            ms_s = timed(lambda s_: ema.sample(batch_size=B, img=resident[1]), 1)
         ema.denoise_fn.engine.enable_cuda_graph(False)
-    if samp_sw:
-        tuning.apply(dict(tuning.DEFAULTS, **tuned['accepted']))
-    sample_img_s = B * world / (sample_ms_per_rev_step * C3['timesteps'] / 1e3)
+        sample = {"value": B * world / (ms_s / 1e3), "unit": "images/s", "what": "GaussianDiffusion.sample(batch_size=32, img=...) per GPU: "
+                  "200-step x0_step_down through the public API, timed whole (max over ranks)", "seconds_per_call": ms_s / 1e3,
+                  "ms_per_reverse_step": ms_s / C3['timesteps'], "cuda_graph": True, "batch_per_gpu": B,
+                  "tflops": B * world * 200 * FWD_GFLOP_PER_IMG / (ms_s / 1e3) / 1e3}
+    if sampler:
+        sampler.stop_flag = True
 
-    # ---- the other BASELINE configs that fit one GPU, as context (rank 0 only; not the headline, bounded to a few steps) ----
-    others = {}
-    if not args.no_autotune:
-        tuning.apply(tuning.DEFAULTS)         # the other configs run the default kernels (see the autotune comment above)
-    if rank == 0:
+    # ---- context, rank 0 of a single-GPU run only: the other BASELINE configs that fit one GPU and the eager-PyTorch comparator
+    others, eager = {}, None
+    if rank == 0 and world == 1 and not args.no_others:
+        others = other_configs(cdm, trainer, resident, dev, B)
         try:
-            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-                # config 2: CIFAR-10 32x32 deblur, DDPM `Model`, T=50 Special_6_routine, x0_step_down sampling, batch 128
-                m2 = cdm.Model(resolution=32, in_channels=3, out_ch=3, ch=128, ch_mult=(1, 2, 2, 2), num_res_blocks=2,
-                               attn_resolutions=(16,), dropout=0.1).to(dev).eval()
-                g2 = cdm.GaussianDiffusion(m2, image_size=32, device_of_kernel='cuda', channels=3, timesteps=50, loss_type='l1',
-                                           kernel_std=0.1, kernel_size=3, blur_routine='Special_6_routine', train_routine='Final',
-                                           sampling_routine='x0_step_down').to(dev)
-                xb = torch.rand(128, 3, 32, 32, device=dev) * 2 - 1
-                img2 = g2.opt(xb)
-                t2 = [50]
-
-                def rev2(s_):
-                    nonlocal img2
-                    st = torch.full((128,), t2[0] - 1, dtype=torch.long, device=dev)
-                    img2 = g2._reverse_step(img2, m2(img2, st), t2[0])
-                    t2[0] -= 1
-                for s_ in range(3):
-                    rev2(s_)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for s_ in range(5):
-                    rev2(s_)
-                e1.record(); torch.cuda.synchronize()
-                ms2 = e0.elapsed_time(e1) / 5
-                others['C2_cifar10_Model_sample'] = {"ms_per_reverse_step": ms2, "images_per_sec_50_step_sample": 128 / (ms2 * 50 / 1e3), "batch": 128}
-                del m2, g2
-                # config 5: AFHQ-128 denoising baseline, cosine T=200, ddim sampling, batch 32 (same Unet, reverse step = 1 fused kernel)
-                from cold_diffusion_models_b200.denoising_diffusion_pytorch import GaussianDiffusion as DNGD
-                g5 = DNGD(trainer.ema_model.denoise_fn, image_size=128, channels=3, timesteps=200, loss_type='l1', sampling_routine='ddim').to(dev)
-                im5 = torch.randn(B, 3, 128, 128, device=dev)
-                t5 = [200]
-
-                def rev5(s_):
-                    nonlocal im5
-                    st = torch.full((B,), t5[0] - 1, dtype=torch.long, device=dev)
-                    im5 = g5._step(im5, g5.denoise_fn(im5, st), None, 0, t5[0])
-                    t5[0] -= 1
-                for s_ in range(2):
-                    rev5(s_)
-                torch.cuda.synchronize()
-                e0.record()
-                for s_ in range(5):
-                    rev5(s_)
-                e1.record(); torch.cuda.synchronize()
-                ms5 = e0.elapsed_time(e1) / 5
-                others['C5_afhq_denoise_ddim_sample'] = {"ms_per_reverse_step": ms5, "images_per_sec_200_step_sample": B / (ms5 * 200 / 1e3), "batch": B}
-        except Exception as e:  # context only: never let it break the headline line
-            others['error'] = repr(e)[:200]
-        try:
-            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
-                # config 4: CelebA-128 resolution diffusion (avg-pool pixelate D), x0_step_down, batch 32, same Unet.  BASELINE's
-                # time_steps=200 is not constructible (RS:389-414: `Incremental*` shrinks by one pixel per step, <= 127 steps at
-                # 128x128), so T = 100 here
-                from cold_diffusion_models_b200.resolution_diffusion_pytorch import GaussianDiffusion as RSGD
-                T4 = 100
-                g4 = RSGD(trainer.ema_model.denoise_fn, image_size=128, device_of_kernel='cuda', channels=3, timesteps=T4, loss_type='l1',
-                          resolution_routine='Incremental_area', train_routine='Final', sampling_routine='x0_step_down').to(dev)
-                im4 = g4.opt(resident[0])
-                t4 = [T4]
-
-                def rev4(s_):
-                    nonlocal im4
-                    st = torch.full((B,), t4[0] - 1, dtype=torch.long, device=dev)
-                    im4 = g4._reverse_step(im4, g4.denoise_fn(im4, st), t4[0])
-                    t4[0] -= 1
-                for s_ in range(2):
-                    rev4(s_)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for s_ in range(5):
-                    rev4(s_)
-                e1.record(); torch.cuda.synchronize()
-                ms4 = e0.elapsed_time(e1) / 5
-                others['C4_celeba_resolution_sample'] = {"ms_per_reverse_step": ms4, "images_per_sec_100_step_sample": B / (ms4 * T4 / 1e3), "batch": B,
-                                                         "routine": "Incremental_area, T=100 (200 steps are not constructible at 128x128)"}
+            v, info = cpu_train_sample(batch=32, steps=2, warmup=1, device='cuda')
+            eager = {"value": v, "unit": "images/s", "ms_per_micro_batch": info['ms_per_step'],
+                     "what": "the reference algorithm as eager PyTorch (cuDNN / cuBLAS, TF32 convolutions allowed like torch's default) on this GPU: "
+                             "p_losses fwd+bwd+Adam at micro-batch 32, 200-step Python q_sample loop included (oracle/ restatement)",
+                     "ours_over_eager": value / v}
         except Exception as e:
-            others['error_C4'] = repr(e)[:200]
-
-    if not args.no_autotune:
-        tuning.apply(dict(tuning.DEFAULTS, **tuned['accepted']))
+            eager = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
 
     # ---- roofline of the dominant kernel (tcgen05 tap-list convolution), CUDA events around every launch --------
     peaks, peak_kind = read_peaks()
@@ -448,20 +319,21 @@ def main():
         eng.profile_convs = None
         tf32_peak = peaks['bf16_tflops_sustained'] / 2.0     # kind::tf32 runs at half the bf16 rate
         ach = tot_fl / (tot_ms / 1e3) / 1e12
-        # DRAM bytes per launch of the same kernels from the committed ncu capture (profiles/conv_tc_traffic_r01.json)
-        traffic = None
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'conv_tc_traffic_r01.json')) as f:
-                traffic = json.load(f)['dram_bytes_per_launch']
-        except Exception:
-            pass
+        traffic, traffic_src = None, None
+        for name in ('conv_tc_traffic_r02.json', 'conv_tc_traffic_r01.json'):
+            try:
+                with open(os.path.join(ROOT, 'profiles', name)) as f:
+                    traffic, traffic_src = json.load(f)['dram_bytes_per_launch'], name
+                break
+            except Exception:
+                pass
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel (tcgen05 kind::tf32 implicit GEMM; fwd + dgrad launches)",
                 "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
-                "traffic_unit": "DRAM bytes per launch (ncu capture of one step, profiles/launches_step_r01_final.csv)",
+                "traffic_unit": "DRAM bytes per launch (ncu capture of one step, profiles/%s)" % traffic_src,
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 rate)" % peak_kind, "launches_timed": n_launch,
                 "share_of_step_ms": tot_ms / (ms / K)}
 
-    # ---- where one optimizer step goes, in situ (CUDA events around every C-ABI call, tools/op_profile.py's mechanism), as tuned ----
+    # ---- where one optimizer step goes, in situ (CUDA events around every C-ABI call, tools/op_profile.py's mechanism) ----
     op_profile = None
     try:
         if rank == 0:
@@ -487,46 +359,126 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            v, info = cpu_train_sample(batch=2, steps=1, warmup=0)
+            v, info = cpu_train_sample(batch=REF_CPU_BATCH, steps=2, warmup=0)
             cpu = {"value": v, "unit": "images/s", "cores": info['cores'], "kind": "port", "sample": info['sample']}
         line = {
-            "metric": "training-step images/sec (CelebA-128 deblur UNet; 200-step sample images/sec in `sample`)",
+            "metric": METRIC,
             "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": "C3: CelebA-128 deblur train step = 2 micro-batches x 32 img/GPU (p_losses fwd+bwd) + grad all-reduce + Adam + EMA",
+            "config": {"workload": WORKLOAD,
                        "net": "Unet(dim=64, dim_mults=(1,2,4,8), channels=3)", "T": 200, "blur": "Exponential_reflect k=15 std=0.01",
                        "global_batch": img_per_step * world, "parallelism": "dp%d" % world,
                        "micro_batches": "%d x %d, gradients accumulated" % (A, B),
                        "l2": "inputs rotate over 4 distinct batch sets; per-step activations (>3 GB) exceed the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": img_per_step * 3 * 128 * 128 * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K, "last_loss": losses[-1] if losses else None},
-            "sample": {"value": sample_img_s, "unit": "images/s (200-step x0_step_down, batch 32/GPU)",
-                       "ms_per_reverse_step": sample_ms_per_rev_step, "reverse_steps_timed": S,
-                       "cuda_graph": graph_sampling,
-                       "note": "per-step cost is t-independent (cumulative-operator degradation), so 200 steps = 200 x this"},
-            "merged_micro_batches": merged,
+            "sample": sample,
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "reference_eager_b200": eager,
             "clocks": sampler.summary() if sampler else None,
             "train_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3,
             "other_configs": others,
             "op_profile": op_profile,
-            "tuning": {"accepted": tuned['accepted'], "merge_micro_batches_validated": merge_ok,
-                       "report": {k: v for k, v in tuned['report'].items() if k in ('default_ms', 'best_ms', 'sampling', 'sampling_cuda_graph', 'accepted_sampling', 'sampling_candidates',
-                                                                                    'sampling_candidates_error', 'inference_forward', 'noise', 'tolerance', 'seconds', 'error',
-                                                                                    'error_after', 'skipped', 'complete', 'child_exit', 'stderr_tail')},
-                       "candidates": [{k: c.get(k) for k in ('name', 'ms', 'err_output', 'err_grad', 'accepted', 'rejected')}
-                                      for c in tuned['report'].get('candidates', [])],
-                       "how": "cold_diffusion_models_b200/tuning.py: a child process checks each opt-in kernel variant against the default "
-                              "kernels (output + every gradient of one micro-step of this network and batch) and times it; accepted = same "
-                              "results and faster.  other_configs run the default kernels."},
         }
-        if roof is not None and tuned['accepted'].get('conv_staged_epilogue'):
-            roof['traffic_note'] = 'traffic comes from the round-1 ncu capture of the row-epilogue kernels'
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(cdm, trainer, resident, dev, B):
+    """the other BASELINE configs that fit one GPU, as context (not the headline, bounded to a few steps; default kernels)"""
+    import io
+    import contextlib
+    import torch
+    others = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def per_step(fn, warm, n):
+        for s_ in range(warm):
+            fn(s_)
+        torch.cuda.synchronize()
+        e0.record()
+        for s_ in range(n):
+            fn(s_)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            # config 2: CIFAR-10 32x32 deblur, DDPM `Model`, T=50 Special_6_routine, batch 128: train step (dropout 0.1 on) and sampling
+            m2 = cdm.Model(resolution=32, in_channels=3, out_ch=3, ch=128, ch_mult=(1, 2, 2, 2), num_res_blocks=2,
+                           attn_resolutions=(16,), dropout=0.1).to(dev)
+            g2 = cdm.GaussianDiffusion(m2, image_size=32, device_of_kernel='cuda', channels=3, timesteps=50, loss_type='l1',
+                                       kernel_std=0.1, kernel_size=3, blur_routine='Special_6_routine', train_routine='Final',
+                                       sampling_routine='x0_step_down').to(dev)
+            tr2 = cdm.Trainer(g2, None, image_size=32, train_batch_size=128, train_lr=2e-5, train_num_steps=10 ** 9,
+                              gradient_accumulate_every=2, results_folder='/tmp/colddiff_bench_results_c2', dataset='synthetic')
+        xb = [torch.rand(128, 3, 32, 32, device=dev) * 2 - 1 for _ in range(2)]
+
+        def st2(s_):
+            tr2.train_step(batches=xb)
+            tr2.step += 1
+        ms2t = per_step(st2, 2, 5)
+        others['C2_cifar10_Model_train'] = {"ms_per_step": ms2t, "images_per_sec": 256 / (ms2t / 1e3), "batch": "2 x 128",
+                                            "tflops": 256 * 3 * 12.44 / ms2t}
+        with torch.no_grad():
+            m2.eval()
+            img2 = g2.opt(xb[0])
+            t2 = [50]
+
+            def rev2(s_):
+                nonlocal img2
+                st = torch.full((128,), t2[0] - 1, dtype=torch.long, device=dev)
+                img2 = g2._reverse_step(img2, m2(img2, st), t2[0])
+                t2[0] -= 1
+            ms2 = per_step(rev2, 3, 5)
+        others['C2_cifar10_Model_sample'] = {"ms_per_reverse_step": ms2, "images_per_sec_50_step_sample": 128 / (ms2 * 50 / 1e3), "batch": 128}
+        del m2, g2, tr2
+    except Exception as e:  # context only: never let it break the headline line
+        others['error_C2'] = repr(e)[:200]
+    try:
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            # config 5: AFHQ-128 denoising baseline, cosine T=200, ddim sampling, batch 32 (same Unet, reverse step = 1 fused kernel)
+            from cold_diffusion_models_b200.denoising_diffusion_pytorch import GaussianDiffusion as DNGD
+            g5 = DNGD(trainer.ema_model.denoise_fn, image_size=128, channels=3, timesteps=200, loss_type='l1', sampling_routine='ddim').to(dev)
+            im5 = torch.randn(B, 3, 128, 128, device=dev)
+            t5 = [200]
+
+            def rev5(s_):
+                nonlocal im5
+                st = torch.full((B,), t5[0] - 1, dtype=torch.long, device=dev)
+                im5 = g5._step(im5, g5.denoise_fn(im5, st), None, 0, t5[0])
+                t5[0] -= 1
+            ms5 = per_step(rev5, 2, 5)
+            others['C5_afhq_denoise_ddim_sample'] = {"ms_per_reverse_step": ms5, "images_per_sec_200_step_sample": B / (ms5 * 200 / 1e3), "batch": B}
+    except Exception as e:
+        others['error_C5'] = repr(e)[:200]
+    try:
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            # config 4: CelebA-128 resolution diffusion (avg-pool pixelate D), x0_step_down, batch 32, same Unet.  BASELINE's
+            # time_steps=200 is not constructible (RS:389-414: `Incremental*` shrinks by one pixel per step, <= 127 steps at
+            # 128x128; SURVEY section 0.3), so T = 100 here
+            from cold_diffusion_models_b200.resolution_diffusion_pytorch import GaussianDiffusion as RSGD
+            T4 = 100
+            g4 = RSGD(trainer.ema_model.denoise_fn, image_size=128, device_of_kernel='cuda', channels=3, timesteps=T4, loss_type='l1',
+                      resolution_routine='Incremental_area', train_routine='Final', sampling_routine='x0_step_down').to(dev)
+            im4 = g4.opt(resident[0])
+            t4 = [T4]
+
+            def rev4(s_):
+                nonlocal im4
+                st = torch.full((B,), t4[0] - 1, dtype=torch.long, device=dev)
+                im4 = g4._reverse_step(im4, g4.denoise_fn(im4, st), t4[0])
+                t4[0] -= 1
+            ms4 = per_step(rev4, 2, 5)
+            others['C4_celeba_resolution_sample'] = {"ms_per_reverse_step": ms4, "images_per_sec_100_step_sample": B / (ms4 * T4 / 1e3), "batch": B,
+                                                     "routine": "Incremental_area, T=100 (200 steps are not constructible at 128x128)"}
+    except Exception as e:
+        others['error_C4'] = repr(e)[:200]
+    return others
 
 
 if __name__ == '__main__':

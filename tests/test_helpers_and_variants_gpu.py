@@ -1,6 +1,7 @@
-"""GPU parity tests added after the round-1 GPU budget was spent: every path below is checked on CPU against the same reference
-goldens through the emulated C ABI (tests/test_*_host_logic.py) but has not run on a B200 yet.  The file sorts last so that the
-already-validated GPU tests run first under `pytest -x`."""
+"""GPU parity of the API helpers (Individual_Incremental, resolution Step routine / t = -1 rows, sample_from_blur, all_sample /
+forward_and_backward of every package, Unet constructor options, the evaluation routines) against the reference goldens, and of
+the kernel variants behind library switches against the kernels they replace (all validated on a B200 in round 2:
+profiles/gpu_tests_r02a.txt)."""
 import io
 import contextlib
 import pytest
@@ -10,10 +11,7 @@ from test_unet_gpu import load, rel, make_unet
 
 pytestmark = pytest.mark.gpu
 
-# Opt-in kernel variants that ship OFF and have never run on a B200 (NOTES.md): their outcome is recorded (XPASS = validated on this
-# run, XFAIL = see the assertion) without turning the suite of the default, validated kernels red.  bench.py's `tuning` report records
-# the same per-variant verdicts independently.
-OPT_IN = lambda f: f          # the variants below were validated on a B200 in round 2 (profiles/gpu_tests_r02a.txt): plain tests now
+OPT_IN = lambda f: f          # kernel-variant tests (switch on / off comparisons)
 
 
 @pytest.fixture(scope='module')
@@ -419,7 +417,7 @@ def test_conv_staged_epilogue_matches_the_row_epilogue():
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    code = ("import sys; sys.path[:0] = [%r, %r, %r]; import test_zz_round1_late_gpu as t; t._conv_staged_epilogue_body(); print('STAGED_OK')"
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]; import test_helpers_and_variants_gpu as t; t._conv_staged_epilogue_body(); print('STAGED_OK')"
             % (os.path.dirname(here), os.path.join(os.path.dirname(here), 'oracle'), here))
     try:
         r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
@@ -476,24 +474,3 @@ def test_fp16_operand_probe_agrees_with_the_tf32_kernel():
     except subprocess.TimeoutExpired as e:
         pytest.fail('fp16 probe hung (killed after 600 s): %s' % str(e.stdout)[-500:])
     assert r.returncode == 0 and 'F16_PROBE_OK' in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
-
-
-
-@OPT_IN
-def test_autotune_child_validates_every_opt_in_variant_on_this_gpu():
-    """cold_diffusion_models_b200.tuning.autotune on the small network: the child must complete, and every opt-in variant must
-    reproduce the default kernels' output and gradients (whether it is also faster, i.e. accepted, depends on the sizes)"""
-    from cold_diffusion_models_b200 import tuning
-    try:
-        r = tuning.autotune(dim=32, dim_mults=(1, 2), channels=3, image_size=32, batch=4, device=torch.cuda.current_device(), timeout=400)
-    finally:
-        tuning.apply(tuning.DEFAULTS)
-    rep = r['report']
-    assert 'error' not in rep and 'error_after' not in rep and rep.get('complete'), rep
-    assert [c['name'] for c in rep['candidates']] == [n for n, _ in tuning.CANDIDATES]
-    for c in rep['candidates']:
-        if c['name'] == 'wgrad_bias_fusion':               # sums TF32-rounded dY on the tensor cores: may sit outside the tolerance
-            assert 'raised' not in c.get('rejected', '') and c['finite'], c
-        else:
-            assert 'rejected' not in c and c['finite'], c
-    assert 'rejected' not in rep.get('sampling', {}), rep.get('sampling')

@@ -5,7 +5,7 @@ COLDDIFF_BATCHED_REPACK switch of engine.py / engine_bwd.py), checked on the CPU
     operand, partial tap lists, accumulate on and off, source clearing);
   * the host logic: with the switch on, the Unet's output, every parameter gradient (also after two accumulated backward
     passes and after a backward that raised half-way) and one Trainer step are the same as with the switch off.
-The `-m gpu` counterpart is tests/test_zz_round1_late_gpu.py::test_batched_repack_matches_the_single_launches."""
+The `-m gpu` counterpart is tests/test_helpers_and_variants_gpu.py::test_batched_repack_matches_the_single_launches."""
 import contextlib
 import ctypes as C
 import io

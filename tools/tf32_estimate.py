@@ -1,4 +1,4 @@
-"""CPU estimate of the TF32-path error of the multi-step GPU parity tests (tests/test_zz_round1_late_gpu.py): runs the same
+"""CPU estimate of the TF32-path error of the multi-step GPU parity tests (tests/test_helpers_and_variants_gpu.py): runs the same
 calls on CPU tensors through tests/abi_emulator.py with both operands of every tensor-core convolution rounded to TF32 (RN,
 like the TFLOAT32 tensor maps), and prints the relative errors against the reference goldens.  Used to set tolerances before a
 test first runs on a B200.  Conservative: single forward of the small net 5.8e-4 here, 3e-4 measured on the GPU.  Usage: python tools/tf32_estimate.py"""
