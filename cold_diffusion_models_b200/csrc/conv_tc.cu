@@ -120,50 +120,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int kiters = p.ntaps[0] * p.kchunks[0] + (p.nsrc > 1 ? p.ntaps[1] * p.kchunks[1] : 0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int co_t = tile % p.tiles_co;
-        int mt = tile / p.tiles_co;
-        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int tn = mt / p.tiles_y;
-        const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN, co0 = co_t * BN;
-        for (int s = 0; s < p.nsrc; ++s) {
-          const CUtensorMap* mA = s ? &mapA1 : &mapA0;
-          const CUtensorMap* mB = s ? &mapB1 : &mapB0;
-          const int wbase = p.wpb[s] ? n0 * p.ntaps[s] : 0;
-          for (int tap = 0; tap < p.ntaps[s]; ++tap) {
-            const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
-            for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it) {
-              const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-              mbar_wait(&empty_bar[stage], ph ^ 1u);
+    // ===================== TMA producer (whole warp walks the schedule, one elected lane issues) =====================
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int co_t = tile % p.tiles_co;
+      int mt = tile / p.tiles_co;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int tn = mt / p.tiles_y;
+      const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN, co0 = co_t * BN;
+      for (int s = 0; s < p.nsrc; ++s) {
+        const CUtensorMap* mA = s ? &mapA1 : &mapA0;
+        const CUtensorMap* mB = s ? &mapB1 : &mapB0;
+        const int wbase = p.wpb[s] ? n0 * p.ntaps[s] : 0;
+        for (int tap = 0; tap < p.ntaps[s]; ++tap) {
+          const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
+          for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it) {
+            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+            mbar_wait(&empty_bar[stage], ph ^ 1u);
+            if (elect_one()) {
               mbar_expect_tx(&full_bar[stage], kStageBytes);
               const uint32_t sa = smem_u32(smem + stage * kStageBytes);
               tma_load_4d(sa, mA, &full_bar[stage], kc * kChunkElems, xin, yin, n0);
               tma_load_3d(sa + kABytes, mB, &full_bar[stage], kc * kChunkElems, co0, wbase + tap);
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-        mbar_wait(&tmem_empty[acc], accph ^ 1u);
+    // ===================== MMA issuer (whole warp waits on the barriers, one elected lane issues) =====================
+    uint32_t it = 0, tcount = 0;
+    const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(smem));
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
+      mbar_wait(&tmem_empty[acc], accph ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int k = 0; k < kiters; ++k, ++it) {
+        const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+        mbar_wait(&full_bar[stage], ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int k = 0; k < kiters; ++k, ++it) {
-          const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-          mbar_wait(&full_bar[stage], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t da = make_kmajor_sw128_desc(sa);
-          const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+        if (elect_one()) {
+          // descriptors of this stage = descriptor of stage 0 + a multiple of the stage size (the 14-bit address field cannot
+          // carry: shared memory ends below 256 KB); everything the single issuing thread executes per chunk is on the critical path
+          const uint64_t da = desc0 + static_cast<uint64_t>(stage * uint32_t(kStageBytes >> 4));
+          const uint64_t db = da + uint64_t(kABytes >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {          // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row
             if constexpr (F16) mma_f16(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
@@ -171,8 +174,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           tc_commit(&empty_bar[stage]);             // frees the smem slot once these MMAs retire
         }
-        tc_commit(&tmem_full[acc]);                 // accumulator complete -> epilogue
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..17) =====================

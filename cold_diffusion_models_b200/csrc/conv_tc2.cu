@@ -116,38 +116,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;   // clusters and this cluster's index
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer (both CTAs; completion lands on the leader's full barrier) =====================
-      uint32_t it = 0;
-      for (int tile = cl; tile < p.total_tiles; tile += ncl) {
-        const int co_t = tile % p.tiles_co;
-        int mt = (tile / p.tiles_co) * 2 + static_cast<int>(rank);        // this CTA's 128-pixel tile (may be past the end: zero fill)
-        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int tn = mt / p.tiles_y;
-        const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN;
-        const int co0 = co_t * BN + static_cast<int>(rank) * (BN / 2);     // this CTA's half of the weight rows
-        for (int s = 0; s < p.nsrc; ++s) {
-          const CUtensorMap* mA = s ? &mapA1 : &mapA0;
-          const CUtensorMap* mB = s ? &mapB1 : &mapB0;
-          for (int tap = 0; tap < p.ntaps[s]; ++tap) {
-            const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
-            for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it) {
-              const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-              mbar_wait(&empty_bar[stage], ph ^ 1u);
+    // ===================== TMA producer (both CTAs; completion lands on the leader's full barrier) =====================
+    // the whole warp walks the schedule and waits on the barriers, one elected lane issues (see elect_one in tc_common.cuh)
+    uint32_t it = 0;
+    for (int tile = cl; tile < p.total_tiles; tile += ncl) {
+      const int co_t = tile % p.tiles_co;
+      int mt = (tile / p.tiles_co) * 2 + static_cast<int>(rank);        // this CTA's 128-pixel tile (may be past the end: zero fill)
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int tn = mt / p.tiles_y;
+      const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN;
+      const int co0 = co_t * BN + static_cast<int>(rank) * (BN / 2);     // this CTA's half of the weight rows
+      for (int s = 0; s < p.nsrc; ++s) {
+        const CUtensorMap* mA = s ? &mapA1 : &mapA0;
+        const CUtensorMap* mB = s ? &mapB1 : &mapB0;
+        for (int tap = 0; tap < p.ntaps[s]; ++tap) {
+          const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
+          for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it) {
+            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+            mbar_wait(&empty_bar[stage], ph ^ 1u);
+            if (elect_one()) {
               if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
               const uint32_t sa = smem_u32(smem + stage * kStageBytes);
               tma2_load_4d(sa, mA, &full_bar[stage], kc * kChunkK, xin, yin, n0);
               tma2_load_3d(sa + kABytes, mB, &full_bar[stage], kc * kChunkK, co0, tap);
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only; whole warp waits, one elected lane issues) =====================
       uint32_t it = 0, tcount = 0;
+      const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(smem));
       for (int tile = cl; tile < p.total_tiles; tile += ncl, ++tcount) {
         const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
         mbar_wait(&tmem_empty[acc], accph ^ 1u);
@@ -157,15 +160,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
           const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
           mbar_wait(&full_bar[stage], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t da = make_kmajor_sw128_desc(sa);
-          const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+          if (elect_one()) {
+            const uint64_t da = desc0 + static_cast<uint64_t>(stage * uint32_t(kStageBytes >> 4));   // the 14-bit address field cannot carry
+            const uint64_t db = da + uint64_t(kABytes >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma2_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
-          tc_commit_pair(&empty_bar[stage]);
+            for (int kk = 0; kk < 4; ++kk)
+              mma2_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
+            tc_commit_pair(&empty_bar[stage]);
+          }
+          __syncwarp();
         }
-        tc_commit_pair(&tmem_full[acc]);
+        if (elect_one()) tc_commit_pair(&tmem_full[acc]);
+        __syncwarp();
       }
     }
   } else {

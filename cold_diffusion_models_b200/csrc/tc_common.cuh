@@ -9,6 +9,20 @@ namespace {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// one elected lane of a converged warp (elect.sync): ptxas treats the guarded region as single-threaded and issues the
+// uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) directly; `if (lane == 0)` makes it wrap every such instruction in a
+// waterfall loop (ELECT / PLOP3 / BRA.U.ANY: ~5 extra issue slots each, ~270 clk per K chunk of 4 MMAs on the single issuing
+// thread -- more than the 128 clk the MMAs of a 128x64 tile take; profiles/ncu_conv_fwd_r02_source_notes.txt)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred px;\n"
+      "elect.sync _|px, 0xffffffff;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n" : "+r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }

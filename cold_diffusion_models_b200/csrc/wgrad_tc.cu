@@ -129,15 +129,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
   const bool bias_cta = BIAS && p.db != nullptr && (tile / p.tiles_co) == 0 && g == 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < nchunks; ++it) {
-        const int c = c_beg + it;
-        const int cx = c % p.chunks_x;
-        const int cy = (c / p.chunks_x) % p.chunks_y;
-        const int n = c / (p.chunks_x * p.chunks_y);
-        const int gx0 = cx * p.CW, gy0 = cy * p.R;
-        const uint32_t stage = it % stages, ph = (it / stages) & 1u;
-        mbar_wait(&empty_bar[stage], ph ^ 1u);
+    // TMA producer: the whole warp walks the chunks and waits on the barriers, one elected lane issues (elect_one, tc_common.cuh)
+    for (int it = 0; it < nchunks; ++it) {
+      const int c = c_beg + it;
+      const int cx = c % p.chunks_x;
+      const int cy = (c / p.chunks_x) % p.chunks_y;
+      const int n = c / (p.chunks_x * p.chunks_y);
+      const int gx0 = cx * p.CW, gy0 = cy * p.R;
+      const uint32_t stage = it % stages, ph = (it / stages) & 1u;
+      mbar_wait(&empty_bar[stage], ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], a_bytes + nl * b_tx_bytes);
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
 #pragma unroll
@@ -150,6 +151,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
             tma_load_4d(sb + ch * (b_bytes / NCH), &mapX, &full_bar[stage], ci0 + ch * 32, xin, yin, n);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ---- MMA issuer.  The operand offsets of the MMAs of one chunk do not depend on the chunk: tabulate them once
@@ -178,32 +180,36 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant
                                  static_cast<uint32_t>(t * BN) | ((r | j) != 0 ? 0x10000u : 0u));
     }
     __syncwarp();
-    if (lane == 0) {
+    {
       const uint64_t da_t = make_mnmajor_sw128_desc(0, a_lbo, 0);
       const uint32_t da_hi = static_cast<uint32_t>(da_t >> 32), da_lo = static_cast<uint32_t>(da_t);
       const uint32_t db_lo = static_cast<uint32_t>(make_mnmajor_sw128_desc(0, b_lbo, 0));
       const uint64_t ones_desc = make_mnmajor_sw128_desc(smem_u32(ones), 1024, 0);
       for (int it = 0; it < nchunks; ++it) {
         const uint32_t stage = it % stages, ph = (it / stages) & 1u;
-        mbar_wait(&full_bar[stage], ph);
+        mbar_wait(&full_bar[stage], ph);            // whole warp waits, one elected lane issues (elect_one, tc_common.cuh)
         tc_fence_after();
-        const uint32_t sa16 = smem_u32(smem + stage * stage_bytes) >> 4;     // < 2^14: no carry into the LBO field
-        const uint32_t alo = da_lo + sa16, blo = db_lo + sa16 + (a_bytes >> 4);
-        const uint32_t first = it == 0 ? 0u : 0x10000u;
-        uint4 e = mma_tab[0];
+        if (elect_one()) {
+          const uint32_t sa16 = smem_u32(smem + stage * stage_bytes) >> 4;     // < 2^14: no carry into the LBO field
+          const uint32_t alo = da_lo + sa16, blo = db_lo + sa16 + (a_bytes >> 4);
+          const uint32_t first = it == 0 ? 0u : 0x10000u;
+          uint4 e = mma_tab[0];
 #pragma unroll 4
-        for (int i = 0; i < nmma; ++i) {
-          const uint4 en = mma_tab[i + 1];          // table has one spare entry; prefetched so the LDS latency is off the issue path
-          const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (alo + e.x);
-          uint64_t db = (static_cast<uint64_t>(e.z) << 32) | (blo + e.y);
-          uint32_t idesc = kIdesc;
-          if (BIAS && (e.w & 0x20000u)) { db = ones_desc; idesc = kIdescBias; }
-          mma_tf32_nomem(tmem_base + (e.w & 0xFFFFu), da, db, idesc, (e.w | first) & 0x10000u);
-          e = en;
+          for (int i = 0; i < nmma; ++i) {
+            const uint4 en = mma_tab[i + 1];          // table has one spare entry; prefetched so the LDS latency is off the issue path
+            const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (alo + e.x);
+            uint64_t db = (static_cast<uint64_t>(e.z) << 32) | (blo + e.y);
+            uint32_t idesc = kIdesc;
+            if (BIAS && (e.w & 0x20000u)) { db = ones_desc; idesc = kIdescBias; }
+            mma_tf32_nomem(tmem_base + (e.w & 0xFFFFu), da, db, idesc, (e.w | first) & 0x10000u);
+            e = en;
+          }
+          tc_commit(&empty_bar[stage]);
         }
-        tc_commit(&empty_bar[stage]);
+        __syncwarp();
       }
-      tc_commit(done_bar);
+      if (elect_one()) tc_commit(done_bar);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -94,10 +94,16 @@ def _trainer_worker(rank, world, port, out):
     torch.Tensor.is_cuda = property(lambda self: True)
     torch.Tensor.cuda = lambda self, *a, **k: self
     with abi_emulator.patched(), contextlib.redirect_stdout(io.StringIO()):
-        gd = _small_gd()
+        gd = _small_gd(seed_sd=3 + rank)                    # ranks start from DIFFERENT weights ...
         tr = cdm.Trainer(gd, None, image_size=32, train_batch_size=2, train_lr=1e-3, gradient_accumulate_every=1,
                          results_folder=os.path.dirname(out), dataset='synthetic')
-        assert tr._world == world
+        assert tr._world == world and tr._rank == rank
+        assert tr.ds.seed == 1234 + 1000003 * rank          # ... read different images ...
+        import unet_oracle as UO                            # ... and the Trainer broadcasts rank 0's parameters and EMA weights
+        want = UO.make_unet_state_dict(32, (1, 2), 3, seed=3)
+        for net in (gd.denoise_fn, tr.ema_model.denoise_fn):
+            have = net.state_dict()
+            assert all(torch.equal(have[k], want[k]) for k in want)
         torch.manual_seed(100 + rank)                       # forward() draws t ~ randint(0, T, (B,)) from the global generator
         tr.train_step(batches=[_batches()[rank]])
     if rank == 0:

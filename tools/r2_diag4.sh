@@ -1,0 +1,11 @@
+#!/bin/bash
+out=gpurun_out/r2d; mkdir -p $out
+step() { sname=$1; shift; echo "== $sname"; ( timeout "$TMO" "$@" ) > $out/$sname.log 2>&1; echo "$sname exit $?" | tee -a $out/summary.txt; tail -n 3 $out/$sname.log; }
+: > $out/summary.txt
+TMO=900 step gpu_tests python -m pytest tests -x -q -m gpu --timeout 300
+TMO=300 step conv_shapes python tools/conv_shapes.py
+TMO=300 step wgrad_shapes python tools/wgrad_shapes.py
+TMO=300 step op_profile python tools/op_profile.py
+TMO=300 step op_profile_batched env COLDDIFF_BATCHED_REPACK=1 python tools/op_profile.py
+TMO=600 step bench python bench.py --no-others --steps 10
+cat $out/summary.txt
