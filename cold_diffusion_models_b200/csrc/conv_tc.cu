@@ -328,9 +328,12 @@ int launch(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
 
 extern "C" int cd_conv_tc_set_tf32_maps(int enable) { g_tf32_map_dtype = enable ? 1 : 0; return 0; }
 
-int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st);   // conv_tc2.cu: SM-pair (cta_group::2) variant
+int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st, int BN);   // conv_tc2.cu: SM-pair (cta_group::2) variant
 static int g_use_2cta = 1;
 extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   // 0 off, 1 where the cost model prefers it, 2 wherever eligible
+// narrower pair tiles: bit mask of the N tiles below 256 (128 | 64) that go to the SM-pair kernel when the problem is eligible
+static int g_2cta_bn = 0;
+extern "C" int cd_conv_tc_set_2cta_bn(int mask) { g_2cta_bn = mask & (128 | 64); return 0; }
 // line-coalesced epilogue (conv_epilogue.cuh): 0 = off (default: not validated on a B200 yet), 1 = for the short-K launches that
 // are bound by their output stores (at most kStagedMaxKIters 32-channel K chunks per tile), 2 = for every launch (tests),
 // 3 = up to kStagedMidKIters chunks (where the row epilogue of a 128-pixel tile, ~6 us per 64 KB, still outlasts the tile's MMAs)
@@ -404,9 +407,13 @@ static int conv_fwd_tc_impl(const CdConvDesc* d, cudaStream_t st, bool f16) {
     double best = tc_cost(mt, d->Cout, 256, false, g_num_sms);
     if (tc_cost(mt, d->Cout, 128, false, g_num_sms) < best) { BN = 128; best = tc_cost(mt, d->Cout, 128, false, g_num_sms); }
     if (!f16 && g_use_2cta && g_tf32_map_dtype && mt >= 2 && (g_use_2cta == 2 || tc_cost(mt, d->Cout, 256, true, g_num_sms) < best)) {
-      const int r2 = cd_conv_fwd_tc2(d, st);
+      const int r2 = cd_conv_fwd_tc2(d, st, 256);
       if (r2 <= 0) return r2;                                 // 1 = not eligible: stay on the 1-CTA kernel
     }
+  } else if (!f16 && !staged && g_use_2cta && g_tf32_map_dtype && (g_2cta_bn & BN) && d->Cout % BN == 0 &&
+             (g_use_2cta == 2 || static_cast<long long>(p.tiles_x) * p.tiles_y * p.tiles_n >= 2 * g_num_sms)) {
+    const int r2 = cd_conv_fwd_tc2(d, st, BN);                // narrow pair tile: only with at least one pair tile per SM pair
+    if (r2 <= 0) return r2;
   }
   p.tiles_co = cd_cdiv(d->Cout, BN);
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_co;

@@ -300,7 +300,7 @@ int launch2(const CUtensorMap* maps, const Tc2Params& p, cudaStream_t st) {
 }  // namespace
 
 // returns 1 when the problem is not eligible for the SM-pair kernel (caller uses the 1-CTA kernel), 0 on success, <0 on error
-int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st) {
+int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st, int BN) {
   if (d->nsrc < 1 || d->nsrc > 2) return 1;
   for (int s = 0; s < d->nsrc; ++s) if (d->s[s].w_per_batch) return 1;       // the pair shares ONE weight tile
   EncodeTiledFn enc = get_encode();
@@ -322,8 +322,8 @@ int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st) {
   p.tiles_x = d->Wg / p.TW; p.tiles_y = d->Hg / p.TH; p.tiles_n = cd_cdiv(d->B, p.TN);
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   if (p.m_tiles < 2) return 1;
-  // only the 256-wide tile: measured, the pair kernel loses to the 1-CTA kernel at N = 128 / 64 (profiles/conv_shapes_2cta_r01.txt)
-  const int BN = 256;
+  // BN = 256 by default; 128 / 64 (each CTA stages 64 / 32 weight rows) are chosen by the caller's switch (cd_conv_tc_set_2cta_bn)
+  if (BN != 256 && BN != 128 && BN != 64) return 1;
   if (d->Cout % BN != 0) return 1;
   p.tiles_co = d->Cout / BN;
   p.total_tiles = ((p.m_tiles + 1) / 2) * p.tiles_co;
@@ -368,5 +368,7 @@ int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st) {
       CD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B%d) failed: %d", s, (int)r);
     }
   }
-  return launch2<256, 7>(maps, p, st);
+  if (BN == 256) return launch2<256, 7>(maps, p, st);
+  if (BN == 128) return launch2<128, 8>(maps, p, st);
+  return launch2<64, 8>(maps, p, st);
 }

@@ -133,7 +133,43 @@ unpack_wgrad_batched_kernel(const CdRepackJob* __restrict__ jobs, int njobs, int
   }
 }
 
+// data-gradient operands straight from PACKED forward operands (the engine keeps dense conv weights packed [tap][O][I] as the
+// master copy: DESIGN.md section 3): dst[t][i][o] = src[tap_t][o][i] with tap_t = ky[t] * KW + kx[t].  One 32x32 transpose tile
+// per block through shared memory (both sides coalesced); job.nblocks = ntaps * ceil(O/32) * ceil(I/32).
+__global__ void __launch_bounds__(256)
+transpose_taps_batched_kernel(const CdRepackJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][33];
+  const JobRef jr = find_job(jobs, njobs);
+  const CdRepackJob& jb = jobs[jr.j];
+  if (jr.lb >= jb.nblocks) return;
+  const int O = jb.O, I = jb.I;
+  const int to = (O + 31) >> 5, ti = (I + 31) >> 5;
+  const int t = jr.lb / (to * ti), rem = jr.lb - t * (to * ti);
+  const int o0 = (rem / ti) * 32, i0 = (rem % ti) * 32;
+  const float* __restrict__ src = jb.src + static_cast<long long>(jb.ky[t] * jb.KW + jb.kx[t]) * O * I;
+  float* __restrict__ dst = jb.dst + static_cast<long long>(t) * O * I;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int o = o0 + r, i = i0 + tx;
+    tile[r][tx] = (o < O && i < I) ? src[static_cast<long long>(o) * I + i] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, o = o0 + tx;
+    if (i < I && o < O) dst[static_cast<long long>(i) * O + o] = tile[tx][r];
+  }
+}
+
 }  // namespace
+
+extern "C" int cd_transpose_taps_batched(const CdRepackJob* jobs, int njobs, int total_blocks, void* stream) {
+  CD_REQUIRE(jobs != nullptr && njobs >= 1 && total_blocks >= 1, "cd_transpose_taps_batched: empty job table");
+  transpose_taps_batched_kernel<<<total_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs, njobs);
+  CD_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int cd_pack_weight_batched(const CdRepackJob* jobs, int njobs, int total_blocks, void* stream) {
   CD_REQUIRE(jobs != nullptr && njobs >= 1 && total_blocks >= 1, "cd_pack_weight_batched: empty job table");

@@ -110,6 +110,14 @@ class UnetEngine(_BackwardHolder):
         self.final_proj = unet.final_conv[1]
         self.sumC = off
         self.cond_blocks = [b for b in self.blocks.values() if b.cond_off is not None]
+        # dense nn.Conv2d weights (3x3 of the blocks, 4x4 stride-2 Downsample, every 1x1): their master copy can live PACKED
+        # [KH*KW][O][I] -- the forward operand of the tap-list convolution and the layout the tcgen05 weight gradient writes --
+        # with the nn.Parameter a permuted (O, I, KH, KW) view of it (flatten_params / _setup_grads in engine_bwd.py)
+        self.dense_convs = {}
+        for mn, mod in unet.named_modules():
+            if isinstance(mod, torch.nn.Conv2d) and not isinstance(mod, torch.nn.ConvTranspose2d) and mod.groups == 1:
+                self.dense_convs[mn + '.weight'] = tuple(mod.weight.shape)
+        self._pname = {id(p): n for n, p in unet.named_parameters()}
 
     # ------------------------------------------------------------------------------------------
     _epoch = 0            # bumped by every in-place parameter update that bypasses torch's version counters
@@ -136,6 +144,27 @@ class UnetEngine(_BackwardHolder):
 
     def _params_version(self):
         return tuple(p._version for p in self.unet.parameters())
+
+    @staticmethod
+    def packed_view(w):
+        """(KH*KW, O, I) view of a dense conv weight whose storage is the packed master layout (a permuted view created by
+        flatten_params), or of any 1x1 weight (packed == OIHW); None for a contiguous OIHW weight with KH*KW > 1"""
+        O, I, KH, KW = w.shape
+        if KH * KW == 1 and w.is_contiguous():
+            return w.detach().view(1, O, I)
+        if w.stride() == (I, 1, KW * O * I, O * I):
+            return torch.as_strided(w.detach(), (KH * KW, O, I), (O * I, I, 1))
+        return None
+
+    def _pack_fwd(self, batch, key, w, taps):
+        """forward operand of a dense Conv2d: the weight itself when it is stored packed (no launch), else a repack"""
+        pv = self.packed_view(w)
+        if pv is not None and len(taps) == pv.shape[0]:
+            self._packed[key] = pv
+            return
+        if self._packed.get(key) is not None and self._packed[key].data_ptr() == w.data_ptr():
+            self._packed[key] = None               # was an alias of a weight that has since been re-laid out
+        self._pack(batch, key, w, taps)
 
     def _pack(self, batch, key, w, taps, mode=0, transposed_conv=False):
         """packed operand P[key] of weight `w`: launched at once, or queued on `batch` (ops.RepackBatch) when batching is on"""
@@ -173,10 +202,10 @@ class UnetEngine(_BackwardHolder):
         with torch.no_grad():
             for name, bs in self.blocks.items():
                 m = bs.mod
-                self._pack(batch, name + '.w1', m.net[1].weight, T3)
-                self._pack(batch, name + '.w2', m.net[3].weight, T3)
+                self._pack_fwd(batch, name + '.w1', m.net[1].weight, T3)
+                self._pack_fwd(batch, name + '.w2', m.net[3].weight, T3)
                 if bs.has_res:
-                    self._pack(batch, name + '.wr', m.res_conv.weight, T1)
+                    self._pack_fwd(batch, name + '.wr', m.res_conv.weight, T1)
                     # bias of the fused [conv2 | res_conv] GEMM
                     b = P.get(name + '.b2r')
                     if b is None:
@@ -184,10 +213,10 @@ class UnetEngine(_BackwardHolder):
                     torch.add(m.net[3].bias, m.res_conv.bias, out=b)
             for spec in self._attn_specs():
                 a = spec.attn
-                self._pack(batch, spec.name + '.wqkv', a.to_qkv.weight, T1)
+                self._pack_fwd(batch, spec.name + '.wqkv', a.to_qkv.weight, T1)
             for i, lv in enumerate(self.levels_down):
                 if lv[3] is not None:
-                    self._pack(batch, 'downs.%d.3' % i, lv[3].weight, T4)
+                    self._pack_fwd(batch, 'downs.%d.3' % i, lv[3].weight, T4)
             for i, lv in enumerate(self.levels_up):
                 if lv[3] is not None:
                     for k, tp in TPAR.items():

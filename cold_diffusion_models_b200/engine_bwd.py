@@ -46,9 +46,18 @@ class BackwardMixin:
         self._offsets, total = flat_offsets([(n, p.numel()) for n, p in params])
         self.flat_grad = torch.zeros(total, device=self.dev, dtype=torch.float32)
         self.G = {}
+        self.Gp = {}                # data_ptr of G[n] -> packed (KH*KW, O, I) view: what the weight-gradient kernels accumulate into
         for n, p in params:
             off, k = self._offsets[n]
-            self.G[n] = self.flat_grad[off:off + k].view_as(p)
+            sl = self.flat_grad[off:off + k]
+            if n in self.dense_convs:
+                # gradients of dense Conv2d weights are STORED packed [KH*KW][O][I] (the tcgen05 weight gradient writes that
+                # layout: no per-step unpack); .grad is the permuted reference-shaped view of the same memory
+                O, I, KH, KW = p.shape
+                self.G[n] = sl.view(KH, KW, O, I).permute(2, 3, 0, 1)
+                self.Gp[self.G[n].data_ptr()] = sl.view(KH * KW, O, I)
+            else:
+                self.G[n] = sl.view_as(p)
 
     def flatten_params(self):
         """rebind every parameter's storage to a slice of ONE flat fp32 buffer (same offsets as flat_grad) so the
@@ -60,9 +69,21 @@ class BackwardMixin:
         with torch.no_grad():
             for n, p in self.unet.named_parameters():
                 off, k = self._offsets[n]
-                v = self.flat_param[off:off + k].view_as(p)
+                sl = self.flat_param[off:off + k]
+                if n in self.dense_convs:
+                    # master copy packed [KH*KW][O][I] == the forward operand of the convolution kernels (no per-step repack);
+                    # the parameter keeps its reference shape (O, I, KH, KW) as a permuted view, so state_dict() /
+                    # load_state_dict() / checkpoints are unchanged.  Adam, EMA and the all-reduce are elementwise over the flat
+                    # buffers, whose layouts (parameters, gradients, moments, EMA copy) are identical.
+                    O, I, KH, KW = p.shape
+                    v = sl.view(KH, KW, O, I).permute(2, 3, 0, 1)
+                else:
+                    v = sl.view_as(p)
                 v.copy_(p.data)
                 p.data = v
+        self._packed = {}              # operands that aliased the old parameter storage
+        if getattr(self, '_graphs', None):
+            self._graphs = {}
         self.mark_weights_dirty()
 
     def attach_grads(self):
@@ -83,24 +104,43 @@ class BackwardMixin:
         if getattr(self, '_bwd_version', None) == ver:
             return
         batch = self._repack_batch('pack_bwd', 'pack')
+        tb = getattr(self, '_tapT', None)
+        if tb is None:
+            tb = self._tapT = ops.TapTransposeBatch()
+        tb.clear()
+
+        def packT(key, w, taps):
+            """data-gradient operand [tap][I][O]: one job of the single batched transpose when the weight is stored packed,
+            else a repack from the reference layout"""
+            pv = self.packed_view(w)
+            if pv is None:
+                self._pack(batch, key, w, taps, mode=1)
+                return
+            O, I, KH, KW = w.shape
+            out = self._packed.get(key)
+            if out is None or tuple(out.shape) != (len(taps), I, O):
+                out = self._packed[key] = torch.empty((len(taps), I, O), device=w.device, dtype=torch.float32)
+            tb.add(pv, O, I, KW, taps, out)
+
         with torch.no_grad():
             for name, bs in self.blocks.items():
                 m = bs.mod
-                self._pack(batch, name + '.w1T', m.net[1].weight, T3D, mode=1)
-                self._pack(batch, name + '.w2T', m.net[3].weight, T3D, mode=1)
+                packT(name + '.w1T', m.net[1].weight, T3D)
+                packT(name + '.w2T', m.net[3].weight, T3D)
                 if bs.has_res:
-                    self._pack(batch, name + '.wrT', m.res_conv.weight, T1, mode=1)
+                    packT(name + '.wrT', m.res_conv.weight, T1)
             for spec in self._attn_specs():
-                self._pack(batch, spec.name + '.wqkvT', spec.attn.to_qkv.weight, T1, mode=1)
+                packT(spec.name + '.wqkvT', spec.attn.to_qkv.weight, T1)
             for i, lv in enumerate(self.levels_down):
                 if lv[3] is not None:
                     for k, tp in TPAR.items():
-                        self._pack(batch, 'downs.%d.3T.%d%d' % (i, k[0], k[1]), lv[3].weight, tp, mode=1)
+                        packT('downs.%d.3T.%d%d' % (i, k[0], k[1]), lv[3].weight, tp)
             for i, lv in enumerate(self.levels_up):
                 if lv[3] is not None:
                     self._pack(batch, 'ups.%d.3T' % i, lv[3].weight, T4, mode=1, transposed_conv=True)
             if batch is not None:
                 batch.run()
+            tb.run()
         self._bwd_version = ver
 
     # ------------------------------------------------------------------------------------------
@@ -112,10 +152,11 @@ class BackwardMixin:
                transposed_conv=False, key=None):
         """accumulate the weight (and bias) gradient of one tap-list convolution into reference-layout grads."""
         nt = len(taps)
-        direct = (nt == 1 and not transposed_conv)          # 1x1: packed layout == OIHW layout
+        pk = self.Gp.get(wgrad_param.data_ptr())            # gradients of dense Conv2d weights are stored packed [KH*KW][O][I]
+        direct = (not transposed_conv) and ((pk is not None and pk.shape[0] == nt) or (nt == 1 and wgrad_param.is_contiguous()))
         ub = self._unpack_batch
         if direct:
-            dwp = wgrad_param
+            dwp = pk if pk is not None else wgrad_param
         else:
             dwp = self.buf('dwp.' + key, (nt, Cout, src.C))
             # batched mode: the one-launch unpack at the end of backward() clears what it read, so a buffer is zero-filled

@@ -125,6 +125,43 @@ class RepackBatch:
             call('cd_unpack_wgrad_batched', ptr(self._table), len(self._jobs), self._total, int(accumulate), int(clear_src), stream())
 
 
+class TapTransposeBatch:
+    """data-gradient operands of many dense convolutions in ONE launch (cd_transpose_taps_batched), from forward operands that
+    are already packed [KH*KW][O][I] -- the engine's master layout of dense conv weights.  add(src, O, I, KW, taps, dst):
+    dst[t][i][o] = src[ky_t * KW + kx_t][o][i].  The job table is built once (all buffers are persistent)."""
+
+    def __init__(self):
+        self._jobs, self._key, self._table, self._total = [], None, None, 0
+
+    def __len__(self):
+        return len(self._jobs)
+
+    def clear(self):
+        self._jobs = []
+
+    def add(self, src, O, I, KW, taps, dst):
+        assert 1 <= len(taps) <= _lib.CD_MAX_TAPS and dst.numel() == len(taps) * O * I
+        self._jobs.append((src, dst, int(O), int(I), int(KW), tuple((t[0], t[1]) for t in taps)))
+
+    def run(self):
+        if not self._jobs:
+            return
+        key = tuple((j[0].data_ptr(), j[1].data_ptr()) + j[2:] for j in self._jobs)
+        if key != self._key:
+            arr = (_lib.RepackJob * len(self._jobs))()
+            b0 = 0
+            for j, (src, dst, O, I, KW, taps) in enumerate(self._jobs):
+                r = arr[j]
+                r.src, r.dst, r.O, r.I, r.KH, r.KW, r.ntaps = src.data_ptr(), dst.data_ptr(), O, I, 1, KW, len(taps)
+                for t, (ky, kx) in enumerate(taps):
+                    r.ky[t], r.kx[t] = ky, kx
+                r.block0, r.nblocks = b0, len(taps) * ((O + 31) // 32) * ((I + 31) // 32)
+                b0 += r.nblocks
+            self._table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self._jobs[0][0].device)
+            self._total, self._key = b0, key
+        call('cd_transpose_taps_batched', ptr(self._table), len(self._jobs), self._total, stream())
+
+
 # --------------------------------------------------------------------------------------------
 # NHWC views: (tensor, channel offset, channels).  tensor is [B, H, W, ld] contiguous.
 # --------------------------------------------------------------------------------------------

@@ -122,6 +122,10 @@ typedef struct {
 int cd_pack_weight_batched(const CdRepackJob* jobs, int njobs, int total_blocks, void* stream);
 int cd_unpack_wgrad_batched(const CdRepackJob* jobs, int njobs, int total_blocks, int accumulate, int clear_src,
                             void* stream);
+/* data-gradient operands of ALL dense convolutions in one launch, from forward operands that are already packed [KH*KW][O][I]
+ * (the engine's master layout of dense conv weights): dst[t][i][o] = src[ky[t]*KW + kx[t]][o][i]; a job covers
+ * nblocks = ntaps * ceil(O/32) * ceil(I/32) transpose tiles (mode / transposed_conv / round_tf32 are ignored) */
+int cd_transpose_taps_batched(const CdRepackJob* jobs, int njobs, int total_blocks, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * ConvNeXt block front half (DB:145, 140-143/159-162, 111-121/148):
@@ -213,6 +217,9 @@ int cd_conv_tc_set_tf32_maps(int enable);
 /* SM-pair (tcgen05 cta_group::2, 256 pixels x 256 channels per pair) variant of the tap-list convolution:
  * 0 = off, 1 = where the tile cost model prefers it, 2 = wherever the problem is eligible (tests) */
 int cd_conv_tc_set_2cta(int mode);
+/* N tiles below 256 that also go to the SM-pair kernel (bit mask: 128 | 64; default 0): each CTA of the pair then stages 64 / 32
+ * weight rows, which takes the shared-memory reads per MMA from 128 / 192 B/clk (one CTA) down to 96 / 160 B/clk */
+int cd_conv_tc_set_2cta_bn(int mask);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of the HBM-bound pieces (autograd of the reference modules restated as kernels).

@@ -211,6 +211,17 @@ def cd_unpack_wgrad_batched(jobs, njobs, total_blocks, accumulate, clear_src, st
     return 0
 
 
+def cd_transpose_taps_batched(jobs, njobs, total_blocks, stream):
+    for j in _jobs(jobs, njobs, total_blocks):
+        assert j.nblocks == j.ntaps * ((j.O + 31) // 32) * ((j.I + 31) // 32)
+        ntap_src = max(j.ky[t] * j.KW + j.kx[t] for t in range(j.ntaps)) + 1
+        S = _arr(j.src, (ntap_src, j.O, j.I), (j.O * j.I, j.I, 1))
+        D = _arr(j.dst, (j.ntaps, j.I, j.O), (j.I * j.O, j.O, 1))
+        for t in range(j.ntaps):
+            D[t] = S[j.ky[t] * j.KW + j.kx[t]].T
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GroupNorm, dropout, softmax, resampling, small dense pieces
 # ------------------------------------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@ int cd_conv_fwd_tc2(const CdConvDesc*, cudaStream_t) { return 1; }
 int cd_conv_wgrad_tc(const CdConvDesc*, const float*, int, float*, float*, int* bias_done, cudaStream_t) { *bias_done = 0; return 1; }
 extern "C" int cd_conv_tc_set_tf32_maps(int) { return 0; }
 extern "C" int cd_conv_tc_set_2cta(int) { return 0; }
+extern "C" int cd_conv_tc_set_2cta_bn(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_mode(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_bias_fusion(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_split(int, int) { return 0; }

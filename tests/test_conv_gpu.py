@@ -31,15 +31,20 @@ def ops():
 
 
 def run_conv(ops, d, impl):
-    """impl: 'simt' | 'tc' (1-CTA tcgen05) | 'tc2' (SM-pair cta_group::2 kernel where eligible)."""
+    """impl: 'simt' | 'tc' (1-CTA tcgen05) | 'tc2' (SM-pair cta_group::2 kernel where eligible, 256-wide tiles) | 'tc2n' (the
+    pair kernel also for the 128- and 64-wide N tiles)."""
     from cold_diffusion_models_b200._lib import lib
-    lib.cd_conv_tc_set_2cta(2 if impl == 'tc2' else 0)
+    lib.cd_conv_tc_set_2cta(2 if impl in ('tc2', 'tc2n') else 0)
+    lib.cd_conv_tc_set_2cta_bn(192 if impl == 'tc2n' else 0)
     try:
         ops.conv_fwd(d, ops.CONV_SIMT if impl == 'simt' else ops.CONV_TC)
         torch.cuda.synchronize()
     finally:
         lib.cd_conv_tc_set_2cta(1)      # library default: pair kernel where the tile cost model prefers it
+        lib.cd_conv_tc_set_2cta_bn(_DEFAULT_2CTA_BN)
 
+
+_DEFAULT_2CTA_BN = 0         # library default of cd_conv_tc_set_2cta_bn (narrow pair tiles)
 
 CASES = [
     # (B, Cin, Cout, H, W, k, pad)
@@ -56,7 +61,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc2n'])
 @pytest.mark.parametrize('case', CASES)
 def test_conv_stride1(ops, case, impl):
     B, Ci, Co, H, W, k, pad = case

@@ -126,3 +126,47 @@ def test_checkpoint_roundtrip_and_train_loop(tmp_path):
     torch.save(pref, os.path.join(str(tmp_path), 'dp.pt'))
     tr2.load(os.path.join(str(tmp_path), 'dp.pt'))
     assert tr2.step == 1
+
+
+def test_device_resident_input_pipeline_on_the_gpu(tmp_path):
+    """DeviceImageDataset keeps the decoded, resized uint8 images in HBM and builds every batch with one gather
+    kernel (cd_augment_u8): bit-exact against the reference's torchvision pipeline (DB:990-996: Resize 1.12 x S, CenterCrop,
+    ToTensor()*2-1), explicit crop windows / flips against crop + hflip of the resized image, and a Trainer that trains from it
+    (`dataset='device_aug'`) without a DataLoader or an H2D copy of fp32 images."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    import unet_oracle as UO
+    import cold_diffusion_models_b200 as cdm
+    from cold_diffusion_models_b200.trainer import DeviceImageDataset
+    rng = np.random.RandomState(0)
+    folder = tmp_path / 'imgs'
+    folder.mkdir()
+    for i in range(7):
+        Image.fromarray(rng.randint(0, 256, (40 + i, 44, 3), dtype=np.uint8)).save(str(folder / ('im%d.png' % i)))
+    S = 32
+    ds = DeviceImageDataset(str(folder), S, augment=False, device='cuda')
+    assert ds.src.is_cuda and ds.src.dtype == torch.uint8
+    ref_tf = transforms.Compose([transforms.Resize((int(S * 1.12), int(S * 1.12))), transforms.CenterCrop(S), transforms.ToTensor(),
+                                 transforms.Lambda(lambda t: (t * 2) - 1)])
+    idx = torch.tensor([3, 0, 6, 4])
+    got = ds.batch(4, index=idx)
+    assert got.is_cuda
+    ref = torch.stack([ref_tf(Image.open(ds.paths[int(i)]).convert('RGB')) for i in idx])
+    assert torch.equal(got.cpu(), ref)
+    resized = [transforms.Resize((ds.rs, ds.rs))(Image.open(p).convert('RGB')) for p in ds.paths]
+    oy, ox, fl = torch.tensor([0, 2, 3, 1]), torch.tensor([3, 1, 0, 2]), torch.tensor([True, False, True, False])
+    got = ds.batch(4, index=idx, oy=oy, ox=ox, flip=fl).cpu()
+    for b in range(4):
+        im = transforms.functional.crop(resized[int(idx[b])], int(oy[b]), int(ox[b]), S, S)
+        if fl[b]:
+            im = transforms.functional.hflip(im)
+        assert torch.equal(got[b], transforms.ToTensor()(im) * 2 - 1)
+    gd = build(UO.make_unet_state_dict(32, (1, 2), 3, seed=2))
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = cdm.Trainer(gd, str(folder), image_size=S, train_batch_size=4, train_lr=2e-5, train_num_steps=2,
+                         gradient_accumulate_every=2, results_folder=str(tmp_path / 'res'), dataset='device_aug')
+        b = tr._next()
+        assert b.is_cuda and tuple(b.shape) == (4, 3, S, S) and float(b.min()) >= -1.0 and float(b.max()) <= 1.0
+        tr.train()
+    assert tr.step == 2

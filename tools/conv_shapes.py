@@ -13,8 +13,9 @@ x = torch.rand(B, 3, 128, 128, device='cuda') * 2 - 1
 t = torch.randint(0, 200, (B,), device='cuda')
 res = {}
 with torch.no_grad():
-    for mode in (0, 1):
-        lib.cd_conv_tc_set_2cta(mode)
+    for mode in (0, 1, 2):
+        lib.cd_conv_tc_set_2cta(min(mode, 1))
+        lib.cd_conv_tc_set_2cta_bn(192 if mode == 2 else 0)      # mode 2: the pair kernel also for the 128- / 64-wide N tiles
         for _ in range(2):
             u(x, t)
         acc = collections.OrderedDict()
@@ -27,13 +28,14 @@ with torch.no_grad():
                 e[0] += 1; e[1] += a.elapsed_time(b)
         u.engine.profile_convs = u.engine.profile_shapes = None
         res[mode] = acc
-lib.cd_conv_tc_set_2cta(0)
-print("%-44s %5s %9s %9s %8s %8s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n", "1cta us", "2cta us", "TF/s 1", "TF/s 2"))
-tot = [0.0, 0.0]
+lib.cd_conv_tc_set_2cta(1)
+lib.cd_conv_tc_set_2cta_bn(0)
+print("%-44s %5s %9s %9s %9s %8s %8s %8s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n", "1cta us", "2cta us", "2cta-n us", "TF/s 1", "TF/s 2", "TF/s 2n"))
+tot = [0.0, 0.0, 0.0]
 for shp, (n, ms, f) in res[0].items():
-    n2, ms2, _ = res[1][shp]
     n //= 5
-    a, b = ms / 5 / n * 1e3, ms2 / 5 / n * 1e3
-    tot[0] += ms / 5; tot[1] += ms2 / 5
-    print("%-44s %5d %9.1f %9.1f %8.1f %8.1f" % (str(shp), n, a, b, f / a / 1e6, f / b / 1e6))
-print("total conv ms per forward: 1cta %.3f   2cta %.3f" % (tot[0], tot[1]))
+    us = [res[m][shp][1] / 5 / n * 1e3 for m in (0, 1, 2)]
+    for m in range(3):
+        tot[m] += res[m][shp][1] / 5
+    print("%-44s %5d %9.1f %9.1f %9.1f %8.1f %8.1f %8.1f" % (str(shp), n, us[0], us[1], us[2], f / us[0] / 1e6, f / us[1] / 1e6, f / us[2] / 1e6))
+print("total conv ms per forward: 1cta %.3f   2cta (256-wide tiles, cost model) %.3f   2cta also for 128/64-wide tiles %.3f" % tuple(tot))
