@@ -629,6 +629,10 @@ extern "C" int cd_linattn_bwd_small(const float* dweff, const float* ctx, const 
 extern "C" int cd_linattn_bwd_kv(const float* qkv, int ld, int B, int n, const float* kmax, const float* ksum,
                                  const float* dctxn, const float* rowdot, float* dqkv, int dld, void* stream) {
   CD_REQUIRE(dld % 4 == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, "cd_linattn_bwd_kv: dqkv must be 16-byte aligned with dld %% 4 == 0");
+  {
+    const int rc = cd_linattn_bwd_kv_mma(qkv, ld, B, n, kmax, ksum, dctxn, rowdot, dqkv, dld, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;                      // 1: switch off (cd_linattn_set_bwd_mma) or unaligned operands -> CUDA-core kernel
+  }
   const size_t smem = sizeof(float) * (2 * 4096 + 2 * 128 * kKvStride);
   static bool attr = false;
   if (!attr) {

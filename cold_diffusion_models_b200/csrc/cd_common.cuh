@@ -38,6 +38,10 @@ int cd_linattn_weff_staged(const float* ctx, const float* ksum, const float* w_o
 int cd_linattn_bwd_small_staged(const float* dweff, const float* ctx, const float* ksum, const float* w_out, int B, int dim,
                                 float scale, float* dw_out, float* dctxn, float* rowdot, cudaStream_t st);
 
+// linattn_bwd.cu: per-pixel LinearAttention backward on mma.sync (default); returns 1 when the CUDA-core kernel should run
+int cd_linattn_bwd_kv_mma(const float* qkv, int ld, int B, int n, const float* kmax, const float* ksum, const float* dctxn,
+                          const float* rowdot, float* dqkv, int dld, cudaStream_t st);
+
 #ifdef __CUDACC__
 // ---- small device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float cd_gelu(float x) {           // exact erf GELU == nn.GELU()

@@ -331,8 +331,12 @@ extern "C" int cd_conv_tc_set_tf32_maps(int enable) { g_tf32_map_dtype = enable 
 int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st, int BN);   // conv_tc2.cu: SM-pair (cta_group::2) variant
 static int g_use_2cta = 1;
 extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   // 0 off, 1 where the cost model prefers it, 2 wherever eligible
+// halo-tile kernel (conv_tc3.cu) for stride-1 convolutions with taps in [-1, 1]^2: 0 = off, 1 = wherever eligible
+int cd_conv_fwd_tc3(const CdConvDesc* d, cudaStream_t st);
+static int g_use_halo = 0;
+extern "C" int cd_conv_tc_set_halo(int enable) { g_use_halo = enable; return 0; }
 // narrower pair tiles: bit mask of the N tiles below 256 (128 | 64) that go to the SM-pair kernel when the problem is eligible
-static int g_2cta_bn = 0;
+static int g_2cta_bn = 128;     // measured (profiles/conv_shapes_r02*.txt): the pair kernel wins at N = 128 (+3..6 %), loses at N = 64
 extern "C" int cd_conv_tc_set_2cta_bn(int mask) { g_2cta_bn = mask & (128 | 64); return 0; }
 // line-coalesced epilogue (conv_epilogue.cuh): 0 = off (default: not validated on a B200 yet), 1 = for the short-K launches that
 // are bound by their output stores (at most kStagedMaxKIters 32-channel K chunks per tile), 2 = for every launch (tests),
@@ -366,6 +370,10 @@ extern "C" int cd_conv_fwd_f16_probe(const CdConvDesc* d, void* stream) {
 }
 
 static int conv_fwd_tc_impl(const CdConvDesc* d, cudaStream_t st, bool f16) {
+  if (!f16 && g_use_halo && g_tf32_map_dtype && g_epi_staged == 0) {
+    const int r3 = cd_conv_fwd_tc3(d, st);
+    if (r3 <= 0) return r3;                                   // 1 = not eligible: the per-tap kernels below
+  }
   const int chunk_elems = f16 ? 64 : kChunkK;
   const int esz = f16 ? 2 : 4;
   EncodeTiledFn enc = get_encode();

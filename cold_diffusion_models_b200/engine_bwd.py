@@ -18,12 +18,13 @@ NULL = C.c_void_p(0)
 
 
 def flat_offsets(named_numels):
-    """[(name, numel)] -> ({name: (offset, numel)}, total) with every slice 16-byte aligned: the layout shared by the
-    flat parameter / gradient / Adam-moment / EMA buffers and by the single NCCL all-reduce."""
+    """[(name, numel)] -> ({name: (offset, numel)}, total) with every slice 128-byte aligned (dense conv weights are TMA
+    operands straight out of the flat parameter buffer: rows of 32 channels must not straddle two 128-byte lines): the layout
+    shared by the flat parameter / gradient / Adam-moment / EMA buffers and by the single NCCL all-reduce."""
     table, off = {}, 0
     for n, k in named_numels:
         table[n] = (off, k)
-        off += (k + 3) // 4 * 4
+        off += (k + 31) // 32 * 32
     return table, off
 
 

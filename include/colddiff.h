@@ -220,6 +220,10 @@ int cd_conv_tc_set_2cta(int mode);
 /* N tiles below 256 that also go to the SM-pair kernel (bit mask: 128 | 64; default 0): each CTA of the pair then stages 64 / 32
  * weight rows, which takes the shared-memory reads per MMA from 128 / 192 B/clk (one CTA) down to 96 / 160 B/clk */
 int cd_conv_tc_set_2cta_bn(int mask);
+/* halo-tile kernel (csrc/conv_tc3.cu) for stride-1 convolutions whose taps lie in [-1, 1]^2 (dense 3x3 forward / data gradient,
+ * fused [3x3 | 1x1] pairs): 128 GEMM rows = a 16 x 8 pixel patch whose 18 x 10 halo patch is fetched ONCE per channel chunk and
+ * read by all nine taps through row-shifted shared-memory descriptors (6x less activation traffic from L2).  0 = off, 1 = on */
+int cd_conv_tc_set_halo(int enable);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of the HBM-bound pieces (autograd of the reference modules restated as kernels).
@@ -238,6 +242,9 @@ int cd_linattn_bwd_small(const float* dweff, const float* ctx, const float* ksum
                          int B, int dim, float scale, float* dw_out, float* dctxn, float* rowdot, void* stream);
 int cd_linattn_bwd_kv(const float* qkv, int ld, int B, int n, const float* kmax, const float* ksum,
                       const float* dctxn, const float* rowdot, float* dqkv, int dld, void* stream);
+/* cd_linattn_bwd_kv runs its two [pixels x 32] x [32 x 32] products per head on warp-level tensor-core MMAs (csrc/linattn_bwd.cu:
+ * 3xTF32: fp32-grade products); 0 selects the CUDA-core kernel of round 1 (A/B comparisons) */
+int cd_linattn_set_bwd_mma(int enable);
 int cd_transpose_weff(const float* weff, int B, int dim, float* weff_t, void* stream);
 int cd_conv1x1_to_nchw_bwd(const float* dout_nchw, const float* x, int ld, int B, int H, int W, int C,
                            const float* w, int Co, float* dx, int dx_ld, float* dw, float* db, void* stream);

@@ -11,6 +11,7 @@ int cd_conv_wgrad_tc(const CdConvDesc*, const float*, int, float*, float*, int* 
 extern "C" int cd_conv_tc_set_tf32_maps(int) { return 0; }
 extern "C" int cd_conv_tc_set_2cta(int) { return 0; }
 extern "C" int cd_conv_tc_set_2cta_bn(int) { return 0; }
+extern "C" int cd_conv_tc_set_halo(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_mode(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_bias_fusion(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_split(int, int) { return 0; }

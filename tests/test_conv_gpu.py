@@ -1,5 +1,6 @@
 """GPU parity of the tap-list convolution (tcgen05 TC path and fp32 SIMT path) through the C ABI,
 against torch's fp64 CPU convolution on identical inputs."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -36,15 +37,18 @@ def run_conv(ops, d, impl):
     from cold_diffusion_models_b200._lib import lib
     lib.cd_conv_tc_set_2cta(2 if impl in ('tc2', 'tc2n') else 0)
     lib.cd_conv_tc_set_2cta_bn(192 if impl == 'tc2n' else 0)
+    lib.cd_conv_tc_set_halo(1 if impl == 'tc3' else 0)       # 'tc3': halo-tile kernel (csrc/conv_tc3.cu) where eligible
     try:
         ops.conv_fwd(d, ops.CONV_SIMT if impl == 'simt' else ops.CONV_TC)
         torch.cuda.synchronize()
     finally:
         lib.cd_conv_tc_set_2cta(1)      # library default: pair kernel where the tile cost model prefers it
         lib.cd_conv_tc_set_2cta_bn(_DEFAULT_2CTA_BN)
+        lib.cd_conv_tc_set_halo(_DEFAULT_HALO)
 
 
-_DEFAULT_2CTA_BN = 0         # library default of cd_conv_tc_set_2cta_bn (narrow pair tiles)
+_DEFAULT_HALO = 0               # library default of cd_conv_tc_set_halo
+_DEFAULT_2CTA_BN = 128         # library default of cd_conv_tc_set_2cta_bn (narrow pair tiles)
 
 CASES = [
     # (B, Cin, Cout, H, W, k, pad)
@@ -61,7 +65,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc2n'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc2n', 'tc3'])
 @pytest.mark.parametrize('case', CASES)
 def test_conv_stride1(ops, case, impl):
     B, Ci, Co, H, W, k, pad = case
@@ -84,7 +88,7 @@ def test_conv_stride1(ops, case, impl):
     assert rel(nchw(out.cpu()), ref_act) < 1e-5
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc3'])
 def test_conv_two_sources_channel_slices(ops, impl):
     """3x3 over h plus the 1x1 res_conv over x accumulated in one GEMM (ConvNextBlock tail, DB:151-154,164);
     sources/outputs are channel slices of wider NHWC buffers."""
@@ -110,6 +114,44 @@ def test_conv_two_sources_channel_slices(ops, impl):
     got = o[..., Co:].permute(0, 3, 1, 2)
     assert rel(got, ref) < 4e-4                      # output rounded to TF32
     assert torch.equal(got, tf32_rn(got))
+
+
+@pytest.mark.parametrize('case', [(2, 64, 64, 16, 8, 3), (1, 128, 128, 32, 24, 3), (3, 96, 320, 16, 16, 3), (2, 64, 64, 64, 64, 3),
+                                  (1, 32, 64, 128, 128, 3), (2, 256, 256, 16, 16, 3)])
+def test_conv_halo_tile_kernel_forward_and_data_gradient(ops, case):
+    """csrc/conv_tc3.cu: one 18 x 10 halo patch per channel chunk read by all nine taps through row-shifted descriptors with a
+    1280-byte group stride -- forward taps, flipped (data-gradient) taps with the GELU' epilogue, single patch (16 x 8 image),
+    non-square grids, Cout that is not a tile multiple, all three N tiles; against fp64 and against the per-tap kernel"""
+    B, Ci, Co, H, W, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = tf32_rn(torch.randn(B, Ci, H, W, generator=g))
+    w = tf32_rn(torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5)
+    b = torch.randn(Co, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    xd = nhwc(x).cuda()
+    outs = []
+    for impl in ('tc', 'tc3'):
+        out = torch.full((B, H, W, Co), 7.0, device='cuda')
+        d = ops.make_conv_desc([(ops.View(xd), ops.taps_conv(3, 1), ops.pack_weight(w.cuda(), ops.taps_conv(3, 1), round_tf32=False), False)],
+                               ops.View(out), (B, H, W), Cout=Co, bias=b.cuda())
+        run_conv(ops, d, impl)
+        assert rel(nchw(out.cpu()), ref) < 1e-5, impl
+        outs.append(out)
+    assert rel(outs[1], outs[0]) < 1e-6
+    # data gradient: dX = conv(dY, flipped W^T), multiplied by GELU'(pre) in the epilogue
+    dy = tf32_rn(torch.randn(B, Co, H, W, generator=g))
+    pre = torch.randn(B, Ci, H, W, generator=g)
+    refd = F.conv_transpose2d(dy.double(), w.double(), padding=1)
+    cdf = 0.5 * (1 + torch.erf(pre.double() / 2 ** 0.5)); pdf = torch.exp(-0.5 * pre.double() ** 2) / (2 * np.pi) ** 0.5
+    refd = refd * (cdf + pre.double() * pdf)
+    dyd, pred = nhwc(dy).cuda(), nhwc(pre).cuda()
+    pwT = ops.pack_weight(w.cuda(), ops.taps_conv_dgrad(3, 1), mode=1, round_tf32=False)
+    for impl in ('tc', 'tc3'):
+        dx = torch.full((B, H, W, Ci), 7.0, device='cuda')
+        d = ops.make_conv_desc([(ops.View(dyd), ops.taps_conv_dgrad(3, 1), pwT, False)], ops.View(dx), (B, H, W), Cout=Ci,
+                               act=ops.ACT_GELU_BWD, aux=ops.View(pred))
+        run_conv(ops, d, impl)
+        assert rel(nchw(dx.cpu()), refd) < 1e-5, impl
 
 
 @pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2'])

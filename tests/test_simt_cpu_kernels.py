@@ -238,6 +238,7 @@ def test_linattn_bwd_kv_remapped_equals_the_default_mapping(cpulib, B, n, ld, dl
     ksum = torch.exp(qkv[:, :, 128:256] - kmax[:, None, :]).sum(dim=1).contiguous()
     dctxn, rowdot = torch.randn(B, 4, 32, 32, generator=g), torch.randn(B, 128, generator=g)
     res = []
+    cpulib.cd_linattn_set_bwd_mma(0)                 # the CUDA-core kernels (the tensor-core one is the default: next test)
     for order in (0, 1):
         cpulib.simt_set_reverse_order(order)
         for staged in (0, 1):
@@ -246,6 +247,7 @@ def test_linattn_bwd_kv_remapped_equals_the_default_mapping(cpulib, B, n, ld, dl
             assert cpulib.cd_linattn_bwd_kv(P(qkv), ld, B, n, P(kmax), P(ksum), P(dctxn), P(rowdot), P(dqkv), dld, C.c_void_p(0)) == 0
             res.append(dqkv)
     cpulib.cd_linattn_set_staged(0)
+    cpulib.cd_linattn_set_bwd_mma(1)
     cpulib.simt_set_reverse_order(0)
     for r in res[1:]:
         assert torch.equal(r, res[0])
@@ -253,6 +255,30 @@ def test_linattn_bwd_kv_remapped_equals_the_default_mapping(cpulib, B, n, ld, dl
     assert E.cd_linattn_bwd_kv(P(qkv), ld, B, n, P(kmax), P(ksum), P(dctxn), P(rowdot), P(want), dld, None) == 0
     assert close(res[1][:, :, 128:384], want[:, :, 128:384], 2e-5)
     assert bool((res[1][:, :, :128] == 7.0).all()) and bool((res[1][:, :, 384:] == 7.0).all())
+
+
+@pytest.mark.parametrize('B,n,ld,dld', [(2, 256, 384, 384), (1, 1000, 392, 388), (3, 40, 384, 384), (1, 16, 384, 384)])
+def test_linattn_bwd_kv_tensor_core_kernel(cpulib, B, n, ld, dld):
+    """attn_bwd_kv_mma_kernel (csrc/linattn_bwd.cu, the default behind cd_linattn_bwd_kv): mma.sync fragments in the 3xTF32 split
+    -> dk / dv at fp32 accuracy against the float64 statement; ragged spans; q columns and row padding untouched; identical
+    under both thread orders"""
+    g = torch.Generator().manual_seed(n + 1)
+    qkv = torch.randn(B, n, ld, generator=g)
+    kmax = qkv[:, :, 128:256].max(dim=1).values.contiguous()
+    ksum = torch.exp(qkv[:, :, 128:256] - kmax[:, None, :]).sum(dim=1).contiguous()
+    dctxn, rowdot = torch.randn(B, 4, 32, 32, generator=g), torch.randn(B, 128, generator=g)
+    res = []
+    for order in (0, 1):
+        cpulib.simt_set_reverse_order(order)
+        dqkv = torch.full((B, n, dld), 7.0)
+        assert cpulib.cd_linattn_bwd_kv(P(qkv), ld, B, n, P(kmax), P(ksum), P(dctxn), P(rowdot), P(dqkv), dld, C.c_void_p(0)) == 0
+        res.append(dqkv)
+    cpulib.simt_set_reverse_order(0)
+    assert torch.equal(res[0], res[1])
+    want = torch.full((B, n, dld), 7.0)
+    assert E.cd_linattn_bwd_kv(P(qkv), ld, B, n, P(kmax), P(ksum), P(dctxn), P(rowdot), P(want), dld, None) == 0
+    assert close(res[0][:, :, 128:256], want[:, :, 128:256], 2e-5) and close(res[0][:, :, 256:384], want[:, :, 256:384], 2e-5)
+    assert bool((res[0][:, :, :128] == 7.0).all()) and bool((res[0][:, :, 384:] == 7.0).all())
 
 
 @pytest.mark.parametrize('npix,C,pad,stats,rnd', [(4096, 64, 0, True, 1), (5000, 128, 8, False, 0), (4099, 32, 4, True, 0), (70000, 64, 0, True, 0)])

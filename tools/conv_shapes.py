@@ -13,9 +13,10 @@ x = torch.rand(B, 3, 128, 128, device='cuda') * 2 - 1
 t = torch.randint(0, 200, (B,), device='cuda')
 res = {}
 with torch.no_grad():
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         lib.cd_conv_tc_set_2cta(min(mode, 1))
-        lib.cd_conv_tc_set_2cta_bn(192 if mode == 2 else 0)      # mode 2: the pair kernel also for the 128- / 64-wide N tiles
+        lib.cd_conv_tc_set_2cta_bn(192 if mode == 2 else (128 if mode == 3 else 0))      # mode 2: the pair kernel also for the 128- / 64-wide N tiles
+        lib.cd_conv_tc_set_halo(1 if mode == 3 else 0)                                   # mode 3: halo-tile kernel for the 3x3 convolutions
         for _ in range(2):
             u(x, t)
         acc = collections.OrderedDict()
@@ -29,13 +30,14 @@ with torch.no_grad():
         u.engine.profile_convs = u.engine.profile_shapes = None
         res[mode] = acc
 lib.cd_conv_tc_set_2cta(1)
-lib.cd_conv_tc_set_2cta_bn(0)
-print("%-44s %5s %9s %9s %9s %8s %8s %8s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n", "1cta us", "2cta us", "2cta-n us", "TF/s 1", "TF/s 2", "TF/s 2n"))
-tot = [0.0, 0.0, 0.0]
+lib.cd_conv_tc_set_2cta_bn(128)      # library default
+lib.cd_conv_tc_set_halo(0)
+print("%-44s %5s %9s %9s %9s %9s %8s %8s %8s %8s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n", "1cta us", "2cta us", "2cta-n us", "halo us", "TF/s 1", "TF/s 2", "TF/s 2n", "TF/s halo"))
+tot = [0.0, 0.0, 0.0, 0.0]
 for shp, (n, ms, f) in res[0].items():
     n //= 5
-    us = [res[m][shp][1] / 5 / n * 1e3 for m in (0, 1, 2)]
-    for m in range(3):
+    us = [res[m][shp][1] / 5 / n * 1e3 for m in (0, 1, 2, 3)]
+    for m in range(4):
         tot[m] += res[m][shp][1] / 5
-    print("%-44s %5d %9.1f %9.1f %9.1f %8.1f %8.1f %8.1f" % (str(shp), n, us[0], us[1], us[2], f / us[0] / 1e6, f / us[1] / 1e6, f / us[2] / 1e6))
-print("total conv ms per forward: 1cta %.3f   2cta (256-wide tiles, cost model) %.3f   2cta also for 128/64-wide tiles %.3f" % tuple(tot))
+    print("%-44s %5d %9.1f %9.1f %9.1f %9.1f %8.1f %8.1f %8.1f %8.1f" % ((str(shp), n) + tuple(us) + tuple(f / u / 1e6 for u in us)))
+print("total conv ms per forward: 1cta %.3f   2cta (256-wide tiles, cost model) %.3f   2cta also for 128/64-wide tiles %.3f   halo-tile kernel for 3x3 (+ 2cta 256/128) %.3f" % tuple(tot))
