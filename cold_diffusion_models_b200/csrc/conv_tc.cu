@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int kEpiWarps = 16;                // 4 TMEM lane quarters x 4 column groups
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                 // fp32 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kTileM * 128;       // 16 KiB per stage
@@ -72,8 +72,11 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t d
 
 // STG: line-coalesced epilogue through a per-warp shared-memory tile (conv_epilogue.cuh; opt-in, fewer mainloop stages)
 // F16: operand-format probe (cd_conv_fwd_f16_probe): sources and packed weights are FP16 arrays, one 128-byte swizzle row = 64 channels
-template <int BN, int STAGES, bool STG = false, bool F16 = false>
-__global__ void __launch_bounds__(kThreads, 1)
+// EPI: epilogue warps (16, or 8 for the two-CTAs-per-SM configuration: the single MMA-issuing thread needs ~8 clk per SASS
+// instruction with nobody to hide its latencies, ~340 clk per K chunk against 128 clk of MMAs at N = 64 -- ncu source page,
+// profiles/ncu_conv_fwd_r02b_*.txt; two co-resident CTAs interleave two such instruction streams on one tensor core)
+template <int BN, int STAGES, bool STG = false, bool F16 = false, int EPI = 16>
+__global__ void __launch_bounds__(64 + 32 * EPI, EPI == 16 ? 1 : 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const TcParams p) {
@@ -96,7 +99,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier block is 256 bytes");
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * kStageBytes + 256);     // STG: kEpiWarps x 32 x 36 floats
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * kStageBytes + 256);     // STG: EPI x 32 x 36 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,7 +107,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], kEpiWarps); mbar_init(&tmem_empty[1], kEpiWarps);
+    mbar_init(&tmem_empty[0], EPI); mbar_init(&tmem_empty[1], EPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -211,7 +214,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = cg * 32; c < BN; c += 32 * (kEpiWarps / 4)) {
+      for (int c = cg * 32; c < BN; c += 32 * (EPI / 4)) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         if constexpr (STG) {
@@ -309,17 +312,19 @@ int g_num_sms = 0;
 int g_tf32_map_dtype = 1;   // 1: TFLOAT32 tensor maps -- the TMA unit rounds fp32->tf32 (RN) on load (measured: profiles/tf32_probe_r01.txt); 0: FLOAT32 (MMA truncates)
 
 
-template <int BN, int STAGES, bool STG = false, bool F16 = false>
+template <int BN, int STAGES, bool STG = false, bool F16 = false, int EPI = 16>
 int launch(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
-  constexpr size_t smem = size_t(STAGES) * (kABytes + BN * 128) + 1024 + 256 + (STG ? sizeof(float) * kEpiWarps * kEpiStageFloats : 0);
+  constexpr size_t smem = size_t(STAGES) * (kABytes + BN * 128) + 1024 + 256 + (STG ? sizeof(float) * EPI * kEpiStageFloats : 0);
   static_assert(smem <= 232448, "dynamic shared memory of one CTA (227 KB)");
+  static_assert(EPI == 16 || 2 * (smem + 1024) <= 233472, "two CTAs per SM must fit the 228 KB of shared memory");
   static bool attr_done = false;
   if (!attr_done) {
-    CD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, STG, F16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_tc_kernel<BN, STAGES, STG, F16><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  const int slots = g_num_sms * (EPI == 16 ? 1 : 2);
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  conv_tc_kernel<BN, STAGES, STG, F16, EPI><<<grid, 64 + 32 * EPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   CD_LAUNCH_CHECK();
   return 0;
 }
@@ -335,6 +340,10 @@ extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   
 int cd_conv_fwd_tc3(const CdConvDesc* d, cudaStream_t st);
 static int g_use_halo = 0;
 extern "C" int cd_conv_tc_set_halo(int enable) { g_use_halo = enable; return 0; }
+// two CTAs per SM (8 epilogue warps, half the stages each) for the 1-CTA kernels with N <= 128: bit mask of N tiles (128 | 64)
+static int g_ctas2 = 0;
+extern "C" int cd_conv_tc_set_two_ctas(int mask) { g_ctas2 = mask & (128 | 64); return 0; }
+int cd_conv_tc_two_ctas_mask() { return g_ctas2; }
 // narrower pair tiles: bit mask of the N tiles below 256 (128 | 64) that go to the SM-pair kernel when the problem is eligible
 static int g_2cta_bn = 128;     // measured (profiles/conv_shapes_r02*.txt): the pair kernel wins at N = 128 (+3..6 %), loses at N = 64
 extern "C" int cd_conv_tc_set_2cta_bn(int mask) { g_2cta_bn = mask & (128 | 64); return 0; }
@@ -483,6 +492,6 @@ static int conv_fwd_tc_impl(const CdConvDesc* d, cudaStream_t st, bool f16) {
     return launch<64, 6, true>(maps, p, st);
   }
   if (BN == 256) return launch<256, 4>(maps, p, st);
-  if (BN == 128) return launch<128, 6>(maps, p, st);
-  return launch<64, 8>(maps, p, st);
+  if (BN == 128) return (g_ctas2 & 128) ? launch<128, 3, false, false, 8>(maps, p, st) : launch<128, 6>(maps, p, st);
+  return (g_ctas2 & 64) ? launch<64, 4, false, false, 8>(maps, p, st) : launch<64, 8>(maps, p, st);
 }

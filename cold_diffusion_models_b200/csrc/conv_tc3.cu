@@ -16,13 +16,10 @@
 
 namespace {
 
-constexpr int kEpiWarps = 16;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kPH = 16, kPW = 8;                     // pixel patch = 128 GEMM rows
 constexpr int kHH = kPH + 2, kHW = kPW + 2;          // halo patch
 constexpr int kABytesTx = kHH * kHW * 128;           // 23040 bytes per TMA box
 constexpr int kAStage = 24 * 1024;                   // stage pitch (1024-byte aligned)
-constexpr int kAStages = 3;
 
 struct Tc3Params {
   int B, H, W;
@@ -64,8 +61,9 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_b
   return d;
 }
 
-template <int BN, int BSTAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+// ASTAGES / BSTAGES: halo-patch and weight-tile rings; EPI: epilogue warps (16, or 8 with two CTAs per SM: conv_tc.cu explains)
+template <int BN, int BSTAGES, int ASTAGES = 3, int EPI = 16>
+__global__ void __launch_bounds__(64 + 32 * EPI, EPI == 16 ? 1 : 2)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                 const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                 const Tc3Params p) {
@@ -77,31 +75,36 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smemA = smem;
-  uint8_t* smemB = smem + kAStages * kAStage;
+  uint8_t* smemB = smem + ASTAGES * kAStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + BSTAGES * kBBytes);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + kAStages;
-  uint64_t* b_full = bars + 2 * kAStages;
+  uint64_t* a_empty = bars + ASTAGES;
+  uint64_t* b_full = bars + 2 * ASTAGES;
   uint64_t* b_empty = b_full + BSTAGES;
   uint64_t* tmem_full = b_empty + BSTAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  static_assert((2 * kAStages + 2 * BSTAGES + 4) * 8 + 4 <= 512, "barrier block is 512 bytes");
+  uint32_t* arow_tab = tmem_slot + 1;                    // [2][CD_MAX_TAPS + 1]: first patch row of every tap, in 16-byte units
+  static_assert((2 * ASTAGES + 2 * BSTAGES + 4) * 8 + 4 + 4 * 2 * (CD_MAX_TAPS + 1) <= 512, "barrier block is 512 bytes");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < ASTAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], kEpiWarps); mbar_init(&tmem_empty[1], kEpiWarps);
+    mbar_init(&tmem_empty[0], EPI); mbar_init(&tmem_empty[1], EPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 2 && lane < 2 * (CD_MAX_TAPS + 1)) {
+    const int s = lane / (CD_MAX_TAPS + 1), t = lane % (CD_MAX_TAPS + 1);
+    arow_tab[lane] = (t < CD_MAX_TAPS && t < p.ntaps[s]) ? static_cast<uint32_t>(((1 + p.dy[s][t]) * kHW + 1 + p.dx[s][t]) * 8) : 0u;
   }
   tc_fence_before();
   __syncthreads();
@@ -110,7 +113,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer: one halo patch per channel chunk, one weight tile per (chunk, tap) =====================
-    uint32_t ia = 0, ib = 0;
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int co_t = tile % p.tiles_co;
       int mt = tile / p.tiles_co;
@@ -121,29 +124,33 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       for (int s = 0; s < p.nsrc; ++s) {
         const CUtensorMap* mA = s ? &mapA1 : &mapA0;
         const CUtensorMap* mB = s ? &mapB1 : &mapB0;
-        for (int kc = 0; kc < p.kchunks[s]; ++kc, ++ia) {
-          const uint32_t sa = ia % kAStages, pha = (ia / kAStages) & 1u;
+        const int nt = p.ntaps[s];
+        for (int kc = 0; kc < p.kchunks[s]; ++kc) {
           mbar_wait(&a_empty[sa], pha ^ 1u);
           if (elect_one()) {
             mbar_expect_tx(&a_full[sa], kABytesTx);
             tma_load_4d(smem_u32(smemA + sa * kAStage), mA, &a_full[sa], kc * 32, x0, y0, n);
           }
           __syncwarp();
-          for (int tap = 0; tap < p.ntaps[s]; ++tap, ++ib) {
-            const uint32_t sb = ib % BSTAGES, phb = (ib / BSTAGES) & 1u;
+          if (++sa == ASTAGES) { sa = 0; pha ^= 1u; }
+          for (int tap = 0; tap < nt; ++tap) {
             mbar_wait(&b_empty[sb], phb ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(&b_full[sb], kBBytes);
               tma_load_3d(smem_u32(smemB + sb * kBBytes), mB, &b_full[sb], kc * 32, co0, tap);
             }
             __syncwarp();
+            if (++sb == BSTAGES) { sb = 0; phb ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    uint32_t ia = 0, ib = 0, tcount = 0;
+    // Everything this warp executes per tap is on the critical path of a 128-clk (N = 64) MMA group: ring positions are
+    // incremented (no division by the stage count), and the first patch row of every tap comes from a shared-memory table whose
+    // next entry is fetched before the barrier wait (an indexed load of the kernel parameters costs a constant-cache round trip).
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tcount = 0;
     const uint64_t descA0 = make_desc_sbo(smem_u32(smemA), kHW * 128);      // 8-row groups (one patch row) are 10 rows apart
     const uint64_t descB0 = make_desc_sbo(smem_u32(smemB), 1024);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -153,26 +160,31 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       const uint32_t tmem_d = tmem_base + acc * BN;
       uint32_t first = 0;
       for (int s = 0; s < p.nsrc; ++s) {
-        for (int kc = 0; kc < p.kchunks[s]; ++kc, ++ia) {
-          const uint32_t sa = ia % kAStages, pha = (ia / kAStages) & 1u;
+        const int nt = p.ntaps[s];
+        const uint32_t* tab = arow_tab + s * (CD_MAX_TAPS + 1);
+        for (int kc = 0; kc < p.kchunks[s]; ++kc) {
           mbar_wait(&a_full[sa], pha);
-          for (int tap = 0; tap < p.ntaps[s]; ++tap, ++ib) {
-            const uint32_t sb = ib % BSTAGES, phb = (ib / BSTAGES) & 1u;
+          const uint64_t da0 = descA0 + static_cast<uint64_t>(sa * uint32_t(kAStage >> 4));
+          uint32_t arow8 = tab[0];
+          for (int tap = 0; tap < nt; ++tap) {
+            const uint32_t arow8_next = tab[tap + 1];                  // table has a spare entry
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
-            const uint32_t arow = static_cast<uint32_t>((1 + p.dy[s][tap]) * kHW + 1 + p.dx[s][tap]);   // first patch row of this tap
             if (elect_one()) {
-              const uint64_t da = descA0 + static_cast<uint64_t>(sa * uint32_t(kAStage >> 4) + arow * 8u);
+              const uint64_t da = da0 + static_cast<uint64_t>(arow8);
               const uint64_t db = descB0 + static_cast<uint64_t>(sb * uint32_t(kBBytes >> 4));
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 mma_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (first | uint32_t(kk)) != 0 ? 1u : 0u);
               tc_commit(&b_empty[sb]);
-              if (tap == p.ntaps[s] - 1) tc_commit(&a_empty[sa]);      // the halo patch is free once its last tap retired
+              if (tap == nt - 1) tc_commit(&a_empty[sa]);              // the halo patch is free once its last tap retired
             }
             __syncwarp();
             first = 1;
+            arow8 = arow8_next;
+            if (++sb == BSTAGES) { sb = 0; phb ^= 1u; }
           }
+          if (++sa == ASTAGES) { sa = 0; pha ^= 1u; }
         }
       }
       if (elect_one()) tc_commit(&tmem_full[acc]);
@@ -204,7 +216,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = cg * 32; c < BN; c += 32 * (kEpiWarps / 4)) {
+      for (int c = cg * 32; c < BN; c += 32 * (EPI / 4)) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         if (co0 + c < p.Cout) {
@@ -265,18 +277,23 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 }
 
 int g_sms3 = 0;
+}  // namespace
+int cd_conv_tc_two_ctas_mask();        // conv_tc.cu (cd_conv_tc_set_two_ctas)
+namespace {
 
-template <int BN, int BSTAGES>
+template <int BN, int BSTAGES, int ASTAGES = 3, int EPI = 16>
 int launch3(const CUtensorMap* maps, const Tc3Params& p, cudaStream_t st) {
-  constexpr size_t smem = size_t(kAStages) * kAStage + size_t(BSTAGES) * BN * 128 + 1024 + 512;
+  constexpr size_t smem = size_t(ASTAGES) * kAStage + size_t(BSTAGES) * BN * 128 + 1024 + 512;
   static_assert(smem <= 232448, "dynamic shared memory of one CTA (227 KB)");
+  static_assert(EPI == 16 || 2 * (smem + 1024) <= 233472, "two CTAs per SM must fit the 228 KB of shared memory");
   static bool attr_done = false;
   if (!attr_done) {
-    CD_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BN, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CD_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BN, BSTAGES, ASTAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int grid = p.total_tiles < g_sms3 ? p.total_tiles : g_sms3;
-  conv_tc3_kernel<BN, BSTAGES><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  const int slots = g_sms3 * (EPI == 16 ? 1 : 2);
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  conv_tc3_kernel<BN, BSTAGES, ASTAGES, EPI><<<grid, 64 + 32 * EPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   CD_LAUNCH_CHECK();
   return 0;
 }
@@ -353,7 +370,8 @@ int cd_conv_fwd_tc3(const CdConvDesc* d, cudaStream_t st) {
     }
   }
   (void)ktotal;
+  const int two = cd_conv_tc_two_ctas_mask();
   if (BN == 256) return launch3<256, 4>(maps, p, st);
-  if (BN == 128) return launch3<128, 8>(maps, p, st);
-  return launch3<64, 12>(maps, p, st);
+  if (BN == 128) return (two & 128) ? launch3<128, 3, 2, 8>(maps, p, st) : launch3<128, 8>(maps, p, st);
+  return (two & 64) ? launch3<64, 6, 2, 8>(maps, p, st) : launch3<64, 12>(maps, p, st);
 }

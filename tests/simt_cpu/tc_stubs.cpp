@@ -12,6 +12,7 @@ extern "C" int cd_conv_tc_set_tf32_maps(int) { return 0; }
 extern "C" int cd_conv_tc_set_2cta(int) { return 0; }
 extern "C" int cd_conv_tc_set_2cta_bn(int) { return 0; }
 extern "C" int cd_conv_tc_set_halo(int) { return 0; }
+extern "C" int cd_conv_tc_set_two_ctas(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_mode(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_bias_fusion(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_split(int, int) { return 0; }

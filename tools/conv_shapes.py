@@ -1,5 +1,5 @@
-"""Per-launch time of every tensor-core convolution of one Unet forward (config 3 network), grouped by GEMM
-shape, with the 1-CTA kernel and the SM-pair (cta_group::2) kernel side by side."""
+"""Per-launch time of every tensor-core convolution of one Unet forward (config 3 network), grouped by GEMM shape, under the
+library's kernel-selection switches side by side."""
 import sys, io, contextlib, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,16 +7,30 @@ import cold_diffusion_models_b200 as cdm
 from cold_diffusion_models_b200._lib import lib
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+# name: (2cta mode, 2cta N-tile mask, halo, two-CTAs-per-SM mask)
+CONFIGS = collections.OrderedDict([
+    ('1cta', (0, 0, 0, 0)),
+    ('pair256+128', (1, 128, 0, 0)),
+    ('twoCTA', (1, 128, 0, 192)),
+    ('halo', (1, 128, 1, 0)),
+    ('halo+twoCTA', (1, 128, 1, 192)),
+    ('halo+two64', (1, 128, 1, 64)),
+])
+DEFAULT = (1, 128, 0, 0)
+
+
+def apply(cfg):
+    lib.cd_conv_tc_set_2cta(cfg[0]); lib.cd_conv_tc_set_2cta_bn(cfg[1]); lib.cd_conv_tc_set_halo(cfg[2]); lib.cd_conv_tc_set_two_ctas(cfg[3])
+
+
 with contextlib.redirect_stdout(io.StringIO()):
     u = cdm.Unet(dim=64, dim_mults=(1, 2, 4, 8), channels=3).cuda()
 x = torch.rand(B, 3, 128, 128, device='cuda') * 2 - 1
 t = torch.randint(0, 200, (B,), device='cuda')
 res = {}
 with torch.no_grad():
-    for mode in (0, 1, 2, 3):
-        lib.cd_conv_tc_set_2cta(min(mode, 1))
-        lib.cd_conv_tc_set_2cta_bn(192 if mode == 2 else (128 if mode == 3 else 0))      # mode 2: the pair kernel also for the 128- / 64-wide N tiles
-        lib.cd_conv_tc_set_halo(1 if mode == 3 else 0)                                   # mode 3: halo-tile kernel for the 3x3 convolutions
+    for name, cfg in CONFIGS.items():
+        apply(cfg)
         for _ in range(2):
             u(x, t)
         acc = collections.OrderedDict()
@@ -28,16 +42,15 @@ with torch.no_grad():
                 e = acc.setdefault(shp, [0, 0.0, f])
                 e[0] += 1; e[1] += a.elapsed_time(b)
         u.engine.profile_convs = u.engine.profile_shapes = None
-        res[mode] = acc
-lib.cd_conv_tc_set_2cta(1)
-lib.cd_conv_tc_set_2cta_bn(128)      # library default
-lib.cd_conv_tc_set_halo(0)
-print("%-44s %5s %9s %9s %9s %9s %8s %8s %8s %8s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n", "1cta us", "2cta us", "2cta-n us", "halo us", "TF/s 1", "TF/s 2", "TF/s 2n", "TF/s halo"))
-tot = [0.0, 0.0, 0.0, 0.0]
-for shp, (n, ms, f) in res[0].items():
+        res[name] = acc
+apply(DEFAULT)
+names = list(CONFIGS)
+print("%-42s %3s" % ("(B,Hg,Wg,Cout,K,nsrc,per_batch)", "n") + ''.join(' %12s' % n for n in names) + '   | TFLOP/s: ' + ' '.join(names))
+tot = {n: 0.0 for n in names}
+for shp, (n, ms, f) in res[names[0]].items():
     n //= 5
-    us = [res[m][shp][1] / 5 / n * 1e3 for m in (0, 1, 2, 3)]
-    for m in range(4):
+    us = [res[m][shp][1] / 5 / n * 1e3 for m in names]
+    for m in names:
         tot[m] += res[m][shp][1] / 5
-    print("%-44s %5d %9.1f %9.1f %9.1f %9.1f %8.1f %8.1f %8.1f %8.1f" % ((str(shp), n) + tuple(us) + tuple(f / u / 1e6 for u in us)))
-print("total conv ms per forward: 1cta %.3f   2cta (256-wide tiles, cost model) %.3f   2cta also for 128/64-wide tiles %.3f   halo-tile kernel for 3x3 (+ 2cta 256/128) %.3f" % tuple(tot))
+    print("%-42s %3d" % (str(shp), n) + ''.join(' %12.1f' % v for v in us) + '   | ' + ' '.join('%6.0f' % (f / v / 1e6) for v in us))
+print("total conv ms per forward: " + '   '.join('%s %.3f' % (m, tot[m]) for m in names))

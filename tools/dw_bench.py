@@ -12,6 +12,7 @@ b = torch.randn(Cc, device='cuda')
 out = torch.empty_like(x)
 dw = torch.zeros(Cc, 49, device='cuda')
 NULL = C.c_void_p(0)
+outs = {}
 for pipe in (1, 0):
     lib.cd_dwconv7_set_pipe(pipe)
     for it in range(3):
@@ -22,5 +23,6 @@ for pipe in (1, 0):
         call('cd_dwconv7_wgrad', ptr(dh), Cc, ptr(x), Cc, B, H, W, Cc, ptr(dw), stream())
         e2.record()
         torch.cuda.synchronize()
+    outs[pipe] = out.clone()
     print("pipe=%d fwd %.1f us   wgrad %.1f us" % (pipe, e0.elapsed_time(e1) * 1e3, e1.elapsed_time(e2) * 1e3))
 lib.cd_dwconv7_set_pipe(1)
