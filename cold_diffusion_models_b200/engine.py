@@ -156,6 +156,14 @@ class UnetEngine(_BackwardHolder):
             return torch.as_strided(w.detach(), (KH * KW, O, I), (O * I, I, 1))
         return None
 
+    def _pack_padded(self, key, w):
+        """[KH*KW][O][pad32(I)] copy of a dense conv weight with the extra input channels zero (a data-movement copy)"""
+        O, I, KH, KW = w.shape
+        out = self._packed.get(key)
+        if out is None:
+            out = self._packed[key] = torch.zeros((KH * KW, O, self._pad32(I)), device=w.device, dtype=torch.float32)
+        out[:, :, :I].copy_(w.detach().permute(2, 3, 0, 1).reshape(KH * KW, O, I))
+
     def _pack_fwd(self, batch, key, w, taps):
         """forward operand of a dense Conv2d: the weight itself when it is stored packed (no launch), else a repack"""
         pv = self.packed_view(w)
@@ -211,6 +219,10 @@ class UnetEngine(_BackwardHolder):
                     if b is None:
                         b = P[name + '.b2r'] = torch.empty_like(m.net[3].bias)
                     torch.add(m.net[3].bias, m.res_conv.bias, out=b)
+                if bs.din % 32 != 0:          # image-edge block: forward operands with K zero-padded to 32 channels
+                    self._pack_padded(name + '.w1p', m.net[1].weight)
+                    if bs.has_res:
+                        self._pack_padded(name + '.wrp', m.res_conv.weight)
             for spec in self._attn_specs():
                 a = spec.attn
                 self._pack_fwd(batch, spec.name + '.wqkv', a.to_qkv.weight, T1)
@@ -271,18 +283,28 @@ class UnetEngine(_BackwardHolder):
             return
         ops.conv_fwd(desc, impl)
 
-    def _block(self, bs, xv, outv, cond_all, save, tag):
+    @staticmethod
+    def _pad32(c):
+        return (c + 31) // 32 * 32
+
+    def _block(self, bs, xv, outv, cond_all, save, tag, xpad=None):
+        """xpad: the block input as a zero-padded 32-channel-multiple view (image-edge block: tensor-core K padded with zeros)"""
         B, H, W = xv.B, xv.H, xv.W
         m = bs.mod
         P = self._packed
         uniq = bs.name if save is not None else tag
-        ld_in = bs.din if bs.din % 4 == 0 else 4
-        hn = self.buf('hn.' + uniq, (B, H, W, ld_in))
+        # image-edge block (din = 1 / 3 image channels): its two convolutions over `din` channels run on the tensor cores with K
+        # padded to 32 zero-filled channels (activations and packed weights) instead of the register-tiled CUDA-core kernels,
+        # which ran ~10x off their HBM bound (480 us forward / 367 us weight gradient per 128x128 micro-batch)
+        edge = bs.din % 32 != 0 and xpad is not None
+        ld_h = bs.din if bs.din % 4 == 0 else 4
+        ld_in = self._pad32(bs.din) if edge else ld_h
+        hn = self.buf('hn.' + uniq, (B, H, W, ld_in), zero=edge)
         stats = hpre = None
         if save is not None:
             if bs.has_norm:
                 stats = self.buf('st.' + bs.name, (B, H, W, 2))
-                hpre = self.buf('hp.' + bs.name, (B, H, W, ld_in))
+                hpre = self.buf('hp.' + bs.name, (B, H, W, ld_h))
         cond = None
         if bs.cond_off is not None:
             cond = C.c_void_p(cond_all.data_ptr() + 4 * bs.cond_off)
@@ -300,17 +322,19 @@ class UnetEngine(_BackwardHolder):
         else:
             call('cd_dwconv7_ln_fwd', C.c_void_p(xv.addr()), xv.ld, B, H, W, bs.din, ptr(m.ds_conv.weight), ptr(m.ds_conv.bias),
                  condp, self.sumC, ptr(g), ptr(be), C.c_float(1e-5), ptr(hn), ld_in,
-                 ptr(stats), ptr(hpre), ld_in, 0, 0, C.c_void_p(0), 0, stream())
-        hv = View(hn, 0, bs.din)
+                 ptr(stats), ptr(hpre), ld_h, 0, 0, C.c_void_p(0), 0, stream())
+        hv = View(hn, 0, ld_in if edge else bs.din)
         u = self.buf('u.' + uniq, (B, H, W, bs.dmid))
         pre = self.buf('pre.' + bs.name, (B, H, W, bs.dmid)) if save is not None else None
-        d1 = ops.make_conv_desc([(hv, T3, P[bs.name + '.w1'], False)], View(u), (B, H, W), Cout=bs.dmid,
+        w1 = P[bs.name + ('.w1p' if edge else '.w1')]
+        d1 = ops.make_conv_desc([(hv, T3, w1, False)], View(u), (B, H, W), Cout=bs.dmid,
                                 bias=m.net[1].bias, act=ACT_GELU, out2=View(pre) if pre is not None else None)
-        self._conv(d1, _tc_ok(bs.din))
+        self._conv(d1, edge or _tc_ok(bs.din))
         uv = View(u)
         if bs.has_res:
-            if _tc_ok(bs.din):
-                d2 = ops.make_conv_desc([(uv, T3, P[bs.name + '.w2'], False), (xv, T1, P[bs.name + '.wr'], False)],
+            if edge or _tc_ok(bs.din):
+                xs, wr = (xpad, P[bs.name + '.wrp']) if edge else (xv, P[bs.name + '.wr'])
+                d2 = ops.make_conv_desc([(uv, T3, P[bs.name + '.w2'], False), (xs, T1, wr, False)],
                                         outv, (B, H, W), Cout=bs.dout, bias=P[bs.name + '.b2r'])
                 self._conv(d2, True)
             else:
@@ -324,7 +348,8 @@ class UnetEngine(_BackwardHolder):
                                     bias=m.net[3].bias, resid=xv)
             self._conv(d2, True)
         if save is not None:
-            save[bs.name] = dict(x=xv, hn=hv, u=uv, pre=View(pre), stats=stats, hpre=hpre, out=outv)
+            save[bs.name] = dict(x=xv, hn=hv, u=uv, pre=View(pre), stats=stats, hpre=hpre, out=outv, ld_h=ld_h,
+                                 xpad=xpad if edge else None)
 
     def _attn(self, spec, xv, outv, save, tag):
         B, H, W = xv.B, xv.H, xv.W
@@ -406,7 +431,7 @@ class UnetEngine(_BackwardHolder):
         if save is not None:
             save['_gen'] = (tuple(x.shape), self._fwd_gen)
         P = self._packed
-        ld0 = Cc if Cc % 4 == 0 else 4
+        ld0 = Cc if Cc % 32 == 0 else self._pad32(Cc)      # image channels zero-padded to a tensor-core K chunk
         x0 = self.buf('x0', (B, H, W, ld0))
         call('cd_nchw_to_nhwc', ptr(x), B, Cc, H, W, ptr(x0), ld0, stream())
         cond_all = None
@@ -430,7 +455,7 @@ class UnetEngine(_BackwardHolder):
         for i, (b0, b1, at, dn) in enumerate(self.levels_down):
             c = b0.dout
             a = self.buf('d%d.a' % i, (B, h, w, c))
-            self._block(b0, xv, View(a), cond_all, save, 'L%d' % i)
+            self._block(b0, xv, View(a), cond_all, save, 'L%d' % i, xpad=View(x0, 0, ld0) if (i == 0 and Cc % 32 != 0) else None)
             bb = self.buf('d%d.b' % i, (B, h, w, c))
             self._block(b1, View(a), View(bb), cond_all, save, 'L%d' % i)
             # attention output = skip connection: lives in the concat buffer of the consuming up level

@@ -150,9 +150,19 @@ class BackwardMixin:
     _dwp_clean = None
 
     def _wgrad(self, src, taps, Cout, grid, dout, wgrad_param, bias_param, *, stride=1, out_map=(1, 1, 0, 0),
-               transposed_conv=False, key=None):
-        """accumulate the weight (and bias) gradient of one tap-list convolution into reference-layout grads."""
+               transposed_conv=False, key=None, real_c=None):
+        """accumulate the weight (and bias) gradient of one tap-list convolution into reference-layout grads.
+        real_c: `src` is a zero-padded view of an activation with only real_c channels (image-edge block): the tensor-core
+        kernel writes the padded gradient into a scratch buffer whose first real_c columns are then added to the packed gradient."""
         nt = len(taps)
+        if real_c is not None:
+            pk = self.Gp[wgrad_param.data_ptr()]
+            tmp = self.buf('dwp.pad.' + key, (nt, Cout, src.C))
+            tmp.zero_()
+            d = ops.make_conv_desc([(src, taps, tmp, False)], dout, grid, stride=stride, Cout=Cout, out_map=out_map)
+            ops.conv_wgrad(d, dout, tmp, bias_param, impl=self.conv_impl)
+            call('cd_add', ptr(pk), real_c, ptr(tmp), src.C, ptr(pk), real_c, C.c_int64(nt * Cout), real_c, stream())
+            return
         pk = self.Gp.get(wgrad_param.data_ptr())            # gradients of dense Conv2d weights are stored packed [KH*KW][O][I]
         direct = (not transposed_conv) and ((pk is not None and pk.shape[0] == nt) or (nt == 1 and wgrad_param.is_contiguous()))
         ub = self._unpack_batch
@@ -196,12 +206,15 @@ class BackwardMixin:
         pn = bs.name
         grid = (B, H, W)
         # ---- conv2 (+ res_conv) ----
+        xpad = sv.get('xpad')                      # image-edge block: zero-padded 32-channel views feed the tensor-core kernels
+        edge_c = bs.din if xpad is not None else None
         if bs.has_res:
             # conv2 and res_conv add into the same output: one column sum of dy feeds both bias gradients
             tmp = self.buf('g.dbias', (max(b_.dout for b_ in self.blocks.values()),))
             tmp.zero_()
             self._wgrad(uv, T3, bs.dout, grid, dyv, G[pn + '.net.3.weight'], tmp, key=pn + '.w2')
-            self._wgrad(xv, T1, bs.dout, grid, dyv, G[pn + '.res_conv.weight'], None, key=pn + '.wr')
+            self._wgrad(xpad if xpad is not None else xv, T1, bs.dout, grid, dyv, G[pn + '.res_conv.weight'], None, key=pn + '.wr',
+                        real_c=edge_c)
             for leaf in ('.net.3.bias', '.res_conv.bias'):
                 call('cd_add', ptr(G[pn + leaf]), bs.dout, ptr(tmp), bs.dout, ptr(G[pn + leaf]), bs.dout, C.c_int64(1), bs.dout, stream())
         else:
@@ -211,8 +224,8 @@ class BackwardMixin:
                                act=ACT_GELU_BWD, aux=prev)
         self._conv(d, _tc_ok(bs.dout))
         # ---- conv1 ----
-        self._wgrad(hv, T3, bs.dmid, grid, View(dpre), G[pn + '.net.1.weight'], G[pn + '.net.1.bias'], key=pn + '.w1')
-        ld_in = hv.ld
+        self._wgrad(hv, T3, bs.dmid, grid, View(dpre), G[pn + '.net.1.weight'], G[pn + '.net.1.bias'], key=pn + '.w1', real_c=edge_c)
+        ld_in = sv.get('ld_h', hv.ld)
         dhn = self.buf('g.hn.%dx%dx%d' % (H, W, ld_in), (B, H, W, ld_in))
         d = ops.make_conv_desc([(View(dpre), T3D, P[pn + '.w1T'], False)], View(dhn, 0, bs.din), grid, Cout=bs.din)
         self._conv(d, True)

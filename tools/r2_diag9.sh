@@ -1,0 +1,8 @@
+#!/bin/bash
+out=gpurun_out/r2i; mkdir -p $out
+step() { local sname=$1; shift; echo "== $sname"; ( timeout "$TMO" "$@" ) > $out/$sname.log 2>&1; echo "$sname exit $?" | tee -a $out/summary.txt; tail -n 3 $out/$sname.log; }
+: > $out/summary.txt
+TMO=900 step gpu_tests python -m pytest tests -x -q -m gpu --timeout 300
+TMO=300 step op_profile python tools/op_profile.py
+TMO=900 step bench python bench.py --steps 10
+cat $out/summary.txt
