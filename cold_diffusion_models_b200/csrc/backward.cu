@@ -12,8 +12,8 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // lanes are split into groups of G = min(32, C/4) (a power of two): each group owns one pixel per iteration, each lane
 // C/(4G) float4 slots; two iterations are in flight per warp so the load->reduce->store chain is not latency-bound.
-template <int NQ>     // float4 slots per lane
-__global__ void __launch_bounds__(256)
+template <int NQ, int PP>     // float4 slots per lane, pixel groups per trip
+__global__ void __launch_bounds__(256, NQ == 1 ? 3 : 1)
 layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ h, int h_ld,
                      const float* __restrict__ stats, const float* __restrict__ g, long long npix, int C,
                      const float* __restrict__ addend, int addend_ld, float* __restrict__ dh, int dh_ld,
@@ -33,42 +33,66 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __res
   }
   const long long p0 = static_cast<long long>(blockIdx.x) * pix_per_block;
   long long p1 = p0 + pix_per_block; if (p1 > npix) p1 = npix;
-  for (long long base = p0 + static_cast<long long>(warp) * ppw; base < p1; base += static_cast<long long>(nwarp) * ppw) {
-    const long long pix = base + sub;
-    const bool valid = pix < p1;
-    float mean = 0.f, rstd = 0.f;
-    if (valid) { mean = stats[pix * 2]; rstd = stats[pix * 2 + 1]; }
-    float4 dv[NQ], xh[NQ];
-    float s1 = 0.f, s2 = 0.f;
+  // PP pixel groups per trip: all 2 * PP * NQ 16-byte loads of a trip are requested before the first use (one load pair per
+  // thread in flight left the kernel at 0.67 of the HBM rate); pixels are visited in the same order as with PP = 1, so the
+  // parameter-gradient partial sums and dh are bit-identical
+  const long long stride = static_cast<long long>(nwarp) * ppw;
+  for (long long base = p0 + static_cast<long long>(warp) * ppw; base < p1; base += stride * PP) {
+    float4 dl[PP][NQ], hl[PP][NQ];
+    float mean[PP], rstd[PP];
+    bool valid[PP];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      const int qd = gl + i * G;
-      dv[i] = make_float4(0, 0, 0, 0); xh[i] = make_float4(0, 0, 0, 0);
-      if (valid && qd < nq) {
-        const float4 d = *reinterpret_cast<const float4*>(dy + pix * dy_ld + qd * 4);
-        const float4 hv = *reinterpret_cast<const float4*>(h + pix * h_ld + qd * 4);
-        xh[i] = make_float4((hv.x - mean) * rstd, (hv.y - mean) * rstd, (hv.z - mean) * rstd, (hv.w - mean) * rstd);
-        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
-        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-        dv[i] = make_float4(d.x * gv[i].x, d.y * gv[i].y, d.z * gv[i].z, d.w * gv[i].w);
-        s1 += dv[i].x + dv[i].y + dv[i].z + dv[i].w;
-        s2 += dv[i].x * xh[i].x + dv[i].y * xh[i].y + dv[i].z * xh[i].z + dv[i].w * xh[i].w;
+    for (int k = 0; k < PP; ++k) {
+      const long long pix = base + k * stride + sub;
+      valid[k] = (base + k * stride < p1) && pix < p1;
+      mean[k] = 0.f; rstd[k] = 0.f;
+      if (valid[k]) { mean[k] = stats[pix * 2]; rstd[k] = stats[pix * 2 + 1]; }
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int qd = gl + i * G;
+        dl[k][i] = make_float4(0, 0, 0, 0); hl[k][i] = make_float4(0, 0, 0, 0);
+        if (valid[k] && qd < nq) {
+          dl[k][i] = *reinterpret_cast<const float4*>(dy + pix * dy_ld + qd * 4);
+          hl[k][i] = *reinterpret_cast<const float4*>(h + pix * h_ld + qd * 4);
+        }
       }
     }
-    for (int o = G >> 1; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-    s1 /= C; s2 /= C;
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      const int qd = gl + i * G;
-      if (valid && qd < nq) {
-        float4 o;
-        o.x = rstd * (dv[i].x - s1 - xh[i].x * s2); o.y = rstd * (dv[i].y - s1 - xh[i].y * s2);
-        o.z = rstd * (dv[i].z - s1 - xh[i].z * s2); o.w = rstd * (dv[i].w - s1 - xh[i].w * s2);
-        if (addend) {
-          const float4 a = *reinterpret_cast<const float4*>(addend + pix * addend_ld + qd * 4);
-          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    for (int k = 0; k < PP; ++k) {
+      if (base + k * stride >= p1) break;                   // warp-uniform
+      const long long pix = base + k * stride + sub;
+      float4 dv[NQ], xh[NQ];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int qd = gl + i * G;
+        dv[i] = make_float4(0, 0, 0, 0); xh[i] = make_float4(0, 0, 0, 0);
+        if (valid[k] && qd < nq) {
+          const float4 d = dl[k][i];
+          const float4 hv = hl[k][i];
+          xh[i] = make_float4((hv.x - mean[k]) * rstd[k], (hv.y - mean[k]) * rstd[k], (hv.z - mean[k]) * rstd[k], (hv.w - mean[k]) * rstd[k]);
+          ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+          ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+          dv[i] = make_float4(d.x * gv[i].x, d.y * gv[i].y, d.z * gv[i].z, d.w * gv[i].w);
+          s1 += dv[i].x + dv[i].y + dv[i].z + dv[i].w;
+          s2 += dv[i].x * xh[i].x + dv[i].y * xh[i].y + dv[i].z * xh[i].z + dv[i].w * xh[i].w;
         }
-        *reinterpret_cast<float4*>(dh + pix * dh_ld + qd * 4) = o;
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      s1 /= C; s2 /= C;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int qd = gl + i * G;
+        if (valid[k] && qd < nq) {
+          float4 o;
+          o.x = rstd[k] * (dv[i].x - s1 - xh[i].x * s2); o.y = rstd[k] * (dv[i].y - s1 - xh[i].y * s2);
+          o.z = rstd[k] * (dv[i].z - s1 - xh[i].z * s2); o.w = rstd[k] * (dv[i].w - s1 - xh[i].w * s2);
+          if (addend) {
+            const float4 a = *reinterpret_cast<const float4*>(addend + pix * addend_ld + qd * 4);
+            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+          }
+          *reinterpret_cast<float4*>(dh + pix * dh_ld + qd * 4) = o;
+        }
       }
     }
   }
@@ -564,8 +588,8 @@ extern "C" int cd_layernorm_bwd(const float* dy, int dy_ld, const float* h, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = sizeof(float) * 2 * C;
   const int slots = nq <= 32 ? 1 : cd_cdiv(nq, 32);
-#define CD_LNB(N) layernorm_bwd_kernel<N><<<blocks, 256, smem, st>>>(dy, dy_ld, h, h_ld, stats, g, npix, C, addend, addend_ld, dh, dh_ld, dg, dbeta, ppb)
-  if (slots == 1) CD_LNB(1); else if (slots == 2) CD_LNB(2); else if (slots <= 4) CD_LNB(4); else CD_LNB(8);
+#define CD_LNB(N, P) layernorm_bwd_kernel<N, P><<<blocks, 256, smem, st>>>(dy, dy_ld, h, h_ld, stats, g, npix, C, addend, addend_ld, dh, dh_ld, dg, dbeta, ppb)
+  if (slots == 1) CD_LNB(1, 4); else if (slots == 2) CD_LNB(2, 2); else if (slots <= 4) CD_LNB(4, 1); else CD_LNB(8, 1);
 #undef CD_LNB
   CD_LAUNCH_CHECK();
   return 0;
