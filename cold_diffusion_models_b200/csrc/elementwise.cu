@@ -756,7 +756,17 @@ int cd_dwconv7_wgrad_pipe(const float* dh, int dh_ld, const float* x, int x_ld, 
 static int g_dw_pipe = 1;     // 1: persistent double-buffered depthwise kernels where eligible; 0: one tile per block
 extern "C" int cd_dwconv7_set_pipe(int enable) { g_dw_pipe = enable; return 0; }
 
+// dwconv_tma.cu: the same kernels with TMA-staged tiles; 1 = not eligible / switched off
+int cd_dwconv7_fwd_tma(const float* x, int x_ld, int B, int H, int W, int C, const float* w_dw, const float* b_dw,
+                       const float* cond, int cond_ld, float* out, int out_ld, int flip, const float* addend, int addend_ld,
+                       cudaStream_t st);
+int cd_dwconv7_wgrad_tma(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C, float* dw, cudaStream_t st);
+
 int cd_dwconv7_wgrad_pipe(const float* dh, int dh_ld, const float* x, int x_ld, int B, int H, int W, int C, float* dw, cudaStream_t st) {
+  if (g_dw_pipe) {
+    const int rc = cd_dwconv7_wgrad_tma(dh, dh_ld, x, x_ld, B, H, W, C, dw, st);
+    if (rc <= 0) return rc;
+  }
   if (!g_dw_pipe || C % 32 != 0 || H % kDwPTY != 0 || W % kDwWTX != 0 || x_ld % 4 != 0 || dh_ld % 4 != 0 ||
       (reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(dh) & 15) != 0) return 1;
   const size_t smem = sizeof(float) * 2 * 32 * (size_t(kDwPTY + 6) * (kDwWTX + 6) + size_t(kDwPTY) * kDwWTX);
@@ -774,6 +784,11 @@ int cd_dwconv7_wgrad_pipe(const float* dh, int dh_ld, const float* x, int x_ld, 
 extern "C" int cd_dwconv7_fwd(const float* x, int x_ld, int B, int H, int W, int C, const float* w_dw, const float* b_dw,
                               const float* cond, int cond_ld, float* out, int out_ld, int flip, const float* addend,
                               int addend_ld, void* stream) {
+  if (g_dw_pipe) {
+    const int rc = cd_dwconv7_fwd_tma(x, x_ld, B, H, W, C, w_dw, b_dw, cond, cond_ld, out, out_ld, flip, addend, addend_ld,
+                                      static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   if (C % 32 == 0 && H % kDwPTY == 0 && W % 16 == 0 && x_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && g_dw_pipe) {
     const int TXp = W % 32 == 0 ? 32 : 16;
     const size_t smem = sizeof(float) * 2 * 32 * size_t(kDwPTY + 6) * (TXp + 6);

@@ -148,6 +148,9 @@ int cd_dwconv7_fwd(const float* x, int x_ld, int B, int H, int W, int C, const f
                    int addend_ld, void* stream);
 /* diagnostic switch: 1 (default) = persistent double-buffered depthwise kernel where eligible, 0 = one tile per block */
 int cd_dwconv7_set_pipe(int enable);
+/* diagnostic switch: 1 (default) = the persistent depthwise kernels stage their tiles with TMA (one bulk tensor copy per tile,
+ * border zero fill by the tensor map: dwconv_tma.cu), 0 = with 16-byte LDGSTS (elementwise.cu) */
+int cd_dwconv7_set_tma(int enable);
 /* channel LayerNorm alone (PreNorm in front of LinearAttention, DB:123-131; also the ConvNextBlock norm) */
 int cd_layernorm_fwd(const float* x, int x_ld, int64_t npix, int C, const float* g, const float* beta,
                      float eps, float* y, int y_ld, float* stats, int round_tf32, void* stream);

@@ -16,3 +16,7 @@ extern "C" int cd_conv_tc_set_two_ctas(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_mode(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_bias_fusion(int) { return 0; }
 extern "C" int cd_wgrad_tc_set_split(int, int) { return 0; }
+int cd_dwconv7_fwd_tma(const float*, int, int, int, int, int, const float*, const float*, const float*, int, float*, int, int, const float*, int,
+                       cudaStream_t) { return 1; }
+int cd_dwconv7_wgrad_tma(const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t) { return 1; }
+extern "C" int cd_dwconv7_set_tma(int) { return 0; }

@@ -474,3 +474,44 @@ def test_fp16_operand_probe_agrees_with_the_tf32_kernel():
     except subprocess.TimeoutExpired as e:
         pytest.fail('fp16 probe hung (killed after 600 s): %s' % str(e.stdout)[-500:])
     assert r.returncode == 0 and 'F16_PROBE_OK' in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+def test_depthwise_kernels_with_tma_staged_tiles_match_the_ldgsts_kernels_and_torch():
+    """csrc/dwconv_tma.cu (cd_dwconv7_set_tma, the default): the depthwise 7x7 forward / data gradient (flip) / weight gradient
+    with tiles staged by one bulk tensor copy (border zero fill by the tensor map) against the LDGSTS kernels of elementwise.cu
+    (same per-thread arithmetic: forward bit-identical) and against torch's depthwise convolution (DB:145) in fp32"""
+    import torch.nn.functional as F
+    from cold_diffusion_models_b200._lib import lib, ptr, stream, _check
+    gen = torch.Generator().manual_seed(11)
+    for (B, H, W, Cc, pad) in ((2, 32, 32, 64, 0), (3, 16, 48, 32, 4), (1, 128, 128, 64, 0), (2, 16, 16, 96, 32)):
+        ld = Cc + pad
+        x = torch.randn(B, H, W, ld, generator=gen).cuda()
+        dh = torch.randn(B, H, W, ld, generator=gen).cuda()
+        add = torch.randn(B, H, W, ld, generator=gen).cuda()
+        w = (torch.randn(Cc, 1, 7, 7, generator=gen) / 7).cuda()
+        bias, cond = torch.randn(Cc, generator=gen).cuda(), torch.randn(B, Cc, generator=gen).cuda()
+        xc = x[..., :Cc].permute(0, 3, 1, 2).contiguous()
+        ref_f = (F.conv2d(xc, w, bias, padding=3, groups=Cc) + cond[:, :, None, None]).permute(0, 2, 3, 1) + add[..., :Cc]
+        ref_d = F.conv_transpose2d(dh[..., :Cc].permute(0, 3, 1, 2).contiguous(), w, padding=3, groups=Cc).permute(0, 2, 3, 1)
+        xg = xc.clone().requires_grad_(True); wg = w.clone().requires_grad_(True)
+        F.conv2d(xg, wg, None, padding=3, groups=Cc).backward(dh[..., :Cc].permute(0, 3, 1, 2).contiguous())
+        ref_w = wg.grad.reshape(Cc, 49)
+        res = []
+        try:
+            for tma in (1, 0):
+                lib.cd_dwconv7_set_tma(tma)
+                out = torch.full((B, H, W, ld), 7.0, device='cuda'); dx = torch.full((B, H, W, ld), 7.0, device='cuda')
+                dw = torch.zeros(Cc, 49, device='cuda')
+                _check(lib.cd_dwconv7_fwd(ptr(x), ld, B, H, W, Cc, ptr(w), ptr(bias), ptr(cond), Cc, ptr(out), ld, 0, ptr(add), ld, stream()), 'dw')
+                _check(lib.cd_dwconv7_fwd(ptr(dh), ld, B, H, W, Cc, ptr(w), ptr(None), ptr(None), 0, ptr(dx), ld, 1, ptr(None), 0, stream()), 'dw flip')
+                for _ in range(2):                      # accumulates (+=)
+                    _check(lib.cd_dwconv7_wgrad(ptr(dh), ld, ptr(x), ld, B, H, W, Cc, ptr(dw), stream()), 'dw wgrad')
+                torch.cuda.synchronize()
+                res.append((out, dx, dw))
+        finally:
+            lib.cd_dwconv7_set_tma(1)
+        case = (B, H, W, Cc, pad)
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), case
+        assert torch.all(res[0][0][..., Cc:] == 7.0) and torch.all(res[0][1][..., Cc:] == 7.0), case     # padding columns untouched
+        assert rel(res[0][0][..., :Cc], ref_f) < 2e-6 and rel(res[0][1][..., :Cc], ref_d) < 2e-6, case
+        assert rel(res[0][2], 2 * ref_w) < 1e-5 and rel(res[1][2], 2 * ref_w) < 1e-5, case
