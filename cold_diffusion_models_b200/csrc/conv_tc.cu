@@ -336,8 +336,10 @@ extern "C" int cd_conv_tc_set_tf32_maps(int enable) { g_tf32_map_dtype = enable 
 int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st, int BN);   // conv_tc2.cu: SM-pair (cta_group::2) variant
 static int g_use_2cta = 1;
 extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   // 0 off, 1 where the cost model prefers it, 2 wherever eligible
-// halo-tile kernel (conv_tc3.cu) for stride-1 convolutions with taps in [-1, 1]^2: 0 = off, 1 = wherever eligible
+// halo-tile kernels for stride-1 convolutions with taps in [-1, 1]^2, bit mask: 1 = conv_tc3.cu (16 x 8 patch) wherever eligible,
+// 2 = conv_tc4.cu (16 x 16 patch, two accumulators per weight tile) for Cout <= 128
 int cd_conv_fwd_tc3(const CdConvDesc* d, cudaStream_t st);
+int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st);
 static int g_use_halo = 0;
 extern "C" int cd_conv_tc_set_halo(int enable) { g_use_halo = enable; return 0; }
 // two CTAs per SM (8 epilogue warps, half the stages each) for the 1-CTA kernels with N <= 128: bit mask of N tiles (128 | 64)
@@ -379,7 +381,11 @@ extern "C" int cd_conv_fwd_f16_probe(const CdConvDesc* d, void* stream) {
 }
 
 static int conv_fwd_tc_impl(const CdConvDesc* d, cudaStream_t st, bool f16) {
-  if (!f16 && g_use_halo && g_tf32_map_dtype && g_epi_staged == 0) {
+  if (!f16 && (g_use_halo & 2) && g_tf32_map_dtype && g_epi_staged == 0) {
+    const int r4 = cd_conv_fwd_tc4(d, st);
+    if (r4 <= 0) return r4;
+  }
+  if (!f16 && (g_use_halo & 1) && g_tf32_map_dtype && g_epi_staged == 0) {
     const int r3 = cd_conv_fwd_tc3(d, st);
     if (r3 <= 0) return r3;                                   // 1 = not eligible: the per-tap kernels below
   }

@@ -3,9 +3,11 @@ snowification/diffusion/diffusion.py:110-447 "SN", snowification/diffusion/forwa
 
 * `DeColorization` (FP:131-218): every step is the per-pixel channel mix f_i I + (1-f_i)/C 11^T; the cumulative mix is a
   [T][C][C] table and D(x, t_b) is ONE kernel with a per-sample step index (cd_chanmix).
-* `Snow` (FP:221-372): D depends on the clean image only; the T snow layers are generated once on the host exactly as
-  the reference does (numpy RNG seed 123321, scipy zoom, motion blur) and applied by cd_snow.  `random_snow=True`
-  regenerates them on the host in `reset_parameters`, as upstream does.
+* `Snow` (FP:221-372): D depends on the clean image only; the T snow layers are generated on the device (cd_snow_layers:
+  scipy.ndimage.zoom's order-1 arithmetic bit for bit, threshold, clip, motion blur of all steps in two launches) from the
+  random numbers the host draws exactly as the reference does (numpy generator, seed 123321 unless `random_snow`), and
+  applied by cd_snow.  `random_snow=True` regenerates them in `reset_parameters`, as upstream does -- there on the host
+  with scipy and T CPU convolutions per p_losses call.
 * per-sample masked stepping (`sample_one_step`, `sample_multi_step`, SN:195-256) and the `t == -1` pass-through rows
   of `q_sample` (SN:344-388) become per-sample indices handed to the kernels -- no Python loop over steps, no
   `torch.where` scatter per step.  `sample()` returns the reference's dict {'xt','direct_recons','recon'}.
@@ -68,17 +70,6 @@ class DeColorization(ForwardProcessBase):
         return out
 
 
-def _clipped_zoom(img, zoom_factor):
-    # FP:32-42 (scipy.ndimage.zoom, order 1, centre crop)
-    from scipy.ndimage import zoom as scizoom
-    h = img.shape[0]
-    ch = int(np.ceil(h / zoom_factor))
-    top = (h - ch) // 2
-    img = scizoom(img[top:top + ch, top:top + ch], (zoom_factor, zoom_factor, 1), order=1)
-    trim = (img.shape[0] - h) // 2
-    return img[trim:trim + h, trim:trim + h]
-
-
 _SNOW_LEVELS = {   # FP:261-293: c, (thres start,end), (motion-blur sigma start,end), (brightness start,end)
     1: ((0.1, 0.3, 3, 0.5, 5, 4, 0.8), (0.7, 0.3), (0.5, 5.0), (0.95, 0.7)),
     2: ((0.55, 0.3, 2.5, 0.85, 11, 12, 0.55), (1.15, 0.7), (0.05, 12), (0.95, 0.55)),
@@ -104,7 +95,10 @@ class Snow(ForwardProcessBase):
 
     @torch.no_grad()
     def generate_snow_layer(self):
-        """FP:252-355, host side (numpy RNG + scipy zoom + motion blur), -> self.snow_t [T][SB][3][H][W]"""
+        """FP:252-355.  The host draws the random numbers exactly as the reference does (numpy global generator: one normal field
+        per snow sample, then one uniform for the direction; torch.randperm per step for `single_snow`; seed 123321 unless
+        `random_snow`) and keeps only the centre crop that clipped_zoom reads (FP:32-38).  Zoom, threshold, clip and motion blur
+        of all T steps run on the device (cd_snow_layers) the first time the layers are needed there: `layers(device)`."""
         if not self.random_snow:
             rstate = np.random.get_state()
             np.random.seed(123321)
@@ -113,42 +107,62 @@ class Snow(ForwardProcessBase):
         self.snow_thres_list = torch.linspace(thr[0], thr[1], T).tolist()
         self.mb_sigma_list = torch.linspace(mbs[0], mbs[1], T).tolist()
         self.br_coef_list = torch.linspace(brc[0], brc[1], T).tolist()
-        if self.single_snow:
-            sb = []
-            for _ in range(self.batch_size):
-                cs = np.random.normal(size=self.image_size, loc=c[0], scale=c[1])[..., np.newaxis]
-                sb.append(_clipped_zoom(cs, c[2]))
-            base = np.concatenate(sb, axis=2)
-        else:
-            base = _clipped_zoom(np.random.normal(size=self.image_size, loc=c[0], scale=c[1])[..., np.newaxis], c[2])
+        h = self.image_size[0]
+        if self.image_size[1] != h:
+            raise ValueError("snow layers are square upstream (clipped_zoom crops both axes with shape[0]); got %r" % (self.image_size,))
+        ch = int(np.ceil(h / c[2]))                                  # clipped_zoom, FP:33-41
+        top = (h - ch) // 2
+        m = int(round(ch * c[2]))                                    # scipy.ndimage.zoom output size
+        self._geom = (ch, m, (m - h) // 2, h)
+        nsb = self.batch_size if self.single_snow else 1
+        crops = [np.random.normal(size=self.image_size, loc=c[0], scale=c[1])[top:top + ch, top:top + ch] for _ in range(nsb)]
+        self._noise = torch.from_numpy(np.ascontiguousarray(np.stack(crops)))          # [SB][ch][ch] float64
         vertical_snow = bool(np.random.uniform() > 0.5)
-        self.snow, self.snow_rot = [], []
+        flags = torch.full((T, nsb), int(vertical_snow), dtype=torch.uint8)
+        taps = []
         for i in range(T):
-            layer = torch.Tensor(base).clone()
-            layer[layer < self.snow_thres_list[i]] = 0
-            layer = torch.clip(layer, 0, 1).permute((2, 0, 1)).unsqueeze(1)          # [SB][1][H][W]
-            taps = gaussian_taps(c[4], self.mb_sigma_list[i])
-            mk = torch.zeros((c[4], c[4]))
-            mk[int(c[4] / 2)] = taps
-            hk = mk[None, None, :].repeat(3, 1, 1, 1)
-            vk = torch.rot90(mk, k=1, dims=[0, 1])[None, None, :].repeat(3, 1, 1, 1)
-            vs = F.conv2d(layer, vk, padding='same')
-            hs = F.conv2d(layer, hk, padding='same')
-            if self.single_snow:
-                vidx = torch.randperm(layer.shape[0])[:int(layer.shape[0] / 2)]
-                layer = hs
-                layer[vidx] = vs[vidx]
-            elif vertical_snow:
-                layer = vs
-            else:
-                layer = hs
-            self.snow.append(layer)
-            self.snow_rot.append(torch.rot90(layer, k=2, dims=[2, 3]))
+            taps.append(gaussian_taps(c[4], self.mb_sigma_list[i]))
+            if self.single_snow:                                     # FP:340-344: a fresh half of the samples goes vertical
+                vidx = torch.randperm(nsb)[:int(nsb / 2)]
+                flags[i] = 0
+                flags[i, vidx] = 1
         if not self.random_snow:
             np.random.set_state(rstate)
-        self.snow_t = torch.stack(self.snow).contiguous()                              # [T][SB][3][H][W]
+        self._taps = torch.stack(taps).float().contiguous()          # [T][k]
+        self._vertical = flags.contiguous()
+        self._thres = torch.tensor(self.snow_thres_list, dtype=torch.float32)
         self.br_t = torch.tensor(self.br_coef_list, dtype=torch.float32)
+        self._layers = None
         self._dev = None
+
+    def layers(self, dev):
+        """[T][SB][3][H][W] fp32 on `dev` (cd_snow's layout), generated there"""
+        dev = torch.device(dev)
+        if self._layers is None or self._layers.device != dev:
+            ch, m, trim, h = self._geom
+            T, nsb = self._vertical.shape
+            noise, thres, taps, vert = (t.to(dev) for t in (self._noise, self._thres, self._taps, self._vertical))
+            base = torch.empty((nsb, h, h), dtype=torch.float32, device=dev)
+            out = torch.empty((T, nsb, 3, h, h), dtype=torch.float32, device=dev)
+            call('cd_snow_layers', ptr(noise), nsb, ch, m, trim, h, ptr(thres), ptr(taps), int(taps.shape[1]), ptr(vert), T,
+                 ptr(base), ptr(out), stream())
+            self._layers = out
+        return self._layers
+
+    # the reference's attributes (FP:305-306, 349-350: lists of CPU tensors), materialised on request
+    @property
+    def snow_t(self):
+        if self._layers is None:
+            self.layers('cuda' if torch.cuda.is_available() else 'cpu')
+        return self._layers
+
+    @property
+    def snow(self):
+        return [l.cpu() for l in self.snow_t]
+
+    @property
+    def snow_rot(self):
+        return [torch.rot90(l.cpu(), k=2, dims=[2, 3]) for l in self.snow_t]
 
 
 class GaussianDiffusion(nn.Module):
@@ -190,7 +204,7 @@ class GaussianDiffusion(nn.Module):
             if isinstance(fp, DeColorization):
                 self._tables = (dev, fp.mats_cum.to(dev))
             else:
-                self._tables = (dev, fp.snow_t.to(dev), fp.br_t.to(dev))
+                self._tables = (dev, fp.layers(dev), fp.br_t.to(dev))
                 fp._dev = dev
         return self._tables
 

@@ -323,6 +323,14 @@ int cd_chanmix(const float* xt, const float* xsrc, float* out, const float* mats
 int cd_snow(const float* xt, const float* og, float* out, const float* snow, const float* br_coef, const int64_t* t_hi,
             const int64_t* t_lo, int hi_off, int lo_off, int B, int H, int W, int snow_batch, int fix_brightness,
             int mode, void* stream);
+/* Snow-layer generation (FP:32-42 clipped_zoom + FP:252-355 generate_snow_layer), everything after the host's random draws:
+ *   base[s]  = fp32( trim( zoom_order1( noise[s] : ch x ch fp64 -> m x m ) ) )  : H x H, scipy.ndimage.zoom arithmetic, bit-exact
+ *   snow[t][s][0..2] = motion_blur_t( clip( base[s] < thres[t] ? 0 : base[s], 0, 1 ) )
+ * noise [SB][ch][ch] (the centre crop FP:36-38), thres [T], taps [T][k] (1-D Gaussian, k odd), vertical [T][SB] (0: blur along x,
+ * 1: along y with reversed taps = torch.rot90 of the horizontal kernel), base [SB][H][H] (workspace / output),
+ * snow [T][SB][3][H][H] in the layout cd_snow reads.  Square images only (upstream crops with shape[0] on both axes). */
+int cd_snow_layers(const double* noise, int SB, int ch, int m, int trim, int H, const float* thres, const float* taps,
+                   int k, const unsigned char* vertical, int T, float* base, float* snow, void* stream);
 /* ------------------------------------------------------------------------------------------
  * DDPM-style `Model` (deblurring-diffusion-pytorch/deblurring_diffusion_pytorch/Model2.py, "M2") forward pieces; the dense
  * convolutions (3x3, 1x1 q/k/v/proj/nin_shortcut, asymmetric-pad stride-2 Downsample, and the two batched matmuls of AttnBlock

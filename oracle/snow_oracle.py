@@ -3,10 +3,79 @@
 steps (FP:150-195) and Snow.forward (FP:361-372) applied SEQUENTIALLY with the reference's masked stepping loops
 (q_sample SN:344-388, sample_one_step SN:195-245, sample SN:259-295).  kornia's rgb_to_grayscale (absent, un-pinned
 upstream) is restated as 0.299 R + 0.587 G + 0.114 B: parity unpinned at that single constant triple.
-Snow layers are taken from the engine-independent generator restated in cold_diffusion_models_b200.snowification
-(host code, pinned against the reference's layers by tests/test_oracle_golden.py)."""
+Snow layers: `generate_snow_layers` below restates Snow.generate_snow_layer (FP:252-355) with the reference's own tools
+(numpy generator, scipy.ndimage.zoom, torch CPU convolutions); it is pinned against layers recorded from the reference
+(tests/golden/snow_small.npz) by tests/test_oracle_golden.py and is what the device generator (cd_snow_layers) is checked
+against."""
+import numpy as np
 import torch
 import torch.nn.functional as F
+
+SNOW_LEVELS = {   # FP:261-293: c, (thres start,end), (motion-blur sigma start,end), (brightness start,end)
+    1: ((0.1, 0.3, 3, 0.5, 5, 4, 0.8), (0.7, 0.3), (0.5, 5.0), (0.95, 0.7)),
+    2: ((0.55, 0.3, 2.5, 0.85, 11, 12, 0.55), (1.15, 0.7), (0.05, 12), (0.95, 0.55)),
+    3: ((0.55, 0.3, 2.5, 0.7, 11, 16, 0.4), (1.15, 0.7), (0.05, 16), (0.95, 0.4)),
+    4: ((0.55, 0.3, 2.5, 0.55, 11, 20, 0.3), (1.15, 0.55), (0.05, 20), (0.95, 0.3)),
+}
+
+
+def clipped_zoom(img, zoom_factor):
+    # FP:32-42 (scipy.ndimage.zoom, order 1, centre crop, centre trim)
+    from scipy.ndimage import zoom as scizoom
+    h = img.shape[0]
+    ch = int(np.ceil(h / zoom_factor))
+    top = (h - ch) // 2
+    img = scizoom(img[top:top + ch, top:top + ch], (zoom_factor, zoom_factor, 1), order=1)
+    trim = (img.shape[0] - h) // 2
+    return img[trim:trim + h, trim:trim + h]
+
+
+def gaussian_taps(ksize, sigma):
+    # torchgeometry.image.get_gaussian_kernel: exponent in Python double -> fp32 exp -> fp32 normalise
+    g = torch.stack([torch.exp(torch.tensor(-(x - ksize // 2) ** 2 / float(2 * sigma ** 2))) for x in range(ksize)])
+    return g / g.sum()
+
+
+def generate_snow_layers(image_size, snow_level=1, num_timesteps=50, random_snow=False, single_snow=False, batch_size=32):
+    """FP:252-355 on the host -> (snow [T][SB][3][H][W], brightness coefficients [T]).  Consumes the numpy / torch global
+    generators exactly as the reference does."""
+    if not random_snow:
+        rstate = np.random.get_state()
+        np.random.seed(123321)
+    c, thr, mbs, brc = SNOW_LEVELS[snow_level]
+    T = num_timesteps
+    thres = torch.linspace(thr[0], thr[1], T).tolist()
+    sigmas = torch.linspace(mbs[0], mbs[1], T).tolist()
+    br = torch.linspace(brc[0], brc[1], T).tolist()
+    if single_snow:
+        sb = [clipped_zoom(np.random.normal(size=image_size, loc=c[0], scale=c[1])[..., np.newaxis], c[2]) for _ in range(batch_size)]
+        base = np.concatenate(sb, axis=2)
+    else:
+        base = clipped_zoom(np.random.normal(size=image_size, loc=c[0], scale=c[1])[..., np.newaxis], c[2])
+    vertical_snow = bool(np.random.uniform() > 0.5)
+    snow = []
+    for i in range(T):
+        layer = torch.Tensor(base).clone()
+        layer[layer < thres[i]] = 0
+        layer = torch.clip(layer, 0, 1).permute((2, 0, 1)).unsqueeze(1)          # [SB][1][H][W]
+        mk = torch.zeros((c[4], c[4]))
+        mk[int(c[4] / 2)] = gaussian_taps(c[4], sigmas[i])
+        hk = mk[None, None, :].repeat(3, 1, 1, 1)
+        vk = torch.rot90(mk, k=1, dims=[0, 1])[None, None, :].repeat(3, 1, 1, 1)
+        vs = F.conv2d(layer, vk, padding='same')
+        hs = F.conv2d(layer, hk, padding='same')
+        if single_snow:
+            vidx = torch.randperm(layer.shape[0])[:int(layer.shape[0] / 2)]
+            layer = hs
+            layer[vidx] = vs[vidx]
+        elif vertical_snow:
+            layer = vs
+        else:
+            layer = hs
+        snow.append(layer)
+    if not random_snow:
+        np.random.set_state(rstate)
+    return torch.stack(snow).contiguous(), br
 
 
 class DecolorFP:

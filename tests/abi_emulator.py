@@ -753,6 +753,41 @@ def cd_snow(xt, og, out, snow, br_coef, t_hi, t_lo, hi_off, lo_off, B, H, W, sno
     return 0
 
 
+def cd_snow_layers(noise, SB, ch, m, trim, H, thres, taps, k, vertical, T, base, snow, stream):
+    N = np.ctypeslib.as_array((C.c_double * (SB * ch * ch)).from_address(_v(noise))).reshape(SB, ch, ch)
+    V = np.ctypeslib.as_array((C.c_uint8 * (T * SB)).from_address(_v(vertical))).reshape(T, SB)
+    TH, TP = _arr(thres, (T,), (1,)), _arr(taps, (T, k), (k, 1))
+    Bs = _arr(base, (SB, H, H), (H * H, H, 1))
+    S = _arr(snow, (T, SB, 3, H, H), (SB * 3 * H * H, 3 * H * H, H * H, H, 1))
+    scale = (ch - 1) / (m - 1)
+    cc = (np.arange(H, dtype=np.float64) + trim) * scale
+    ok = cc <= ch - 1
+    f = np.floor(cc)
+    w0 = 1.0 - (cc - f); w1 = 1.0 - w0
+    i0 = np.minimum(f.astype(np.int64), ch - 1); i1 = i0 + 1
+    i1 = np.where(i1 > ch - 1, 2 * (ch - 1) - i1, i1)
+    W, I = (w0, w1), (i0, i1)
+    for s in range(SB):
+        terms = [(N[s][np.ix_(I[a], I[b])] * W[a][:, None]) * W[b][None, :] for a in range(2) for b in range(2)]
+        z = ((terms[0] + terms[1]) + terms[2]) + terms[3]
+        z[~ok, :] = 0.0; z[:, ~ok] = 0.0
+        Bs[s] = z.astype(np.float32)
+    half = k // 2
+    for t in range(T):
+        L = np.where(Bs < TH[t], np.float32(0), np.clip(Bs, 0, 1)).astype(np.float32)
+        P = np.zeros((SB, H + 2 * half, H + 2 * half), np.float32)
+        P[:, half:half + H, half:half + H] = L
+        for s in range(SB):
+            acc = np.zeros((H, H), np.float32)
+            for j in range(k):
+                if V[t, s]:
+                    acc += TP[t, k - 1 - j] * P[s, j:j + H, half:half + H]
+                else:
+                    acc += TP[t, j] * P[s, half:half + H, j:j + H]
+            S[t, s, :] = acc[None]
+    return 0
+
+
 def cd_augment_u8(src, N, Hs, Ws, index, oy, ox, flip, B, S, out, stream):
     U = np.ctypeslib.as_array((C.c_uint8 * (N * Hs * Ws * 3)).from_address(_v(src))).reshape(N, Hs, Ws, 3)
     idx = _i64(index, B)

@@ -137,7 +137,7 @@ def rewrite(src):
     return out + src[i:]
 
 
-SIMT_UNITS = ['api.cu', 'elementwise.cu', 'backward.cu', 'degrade.cu', 'conv_simt.cu', 'model2_bwd.cu', 'repack.cu', 'linattn_small.cu', 'layernorm_multi.cu', 'final_proj.cu', 'linattn_ctx.cu', 'linattn_bwd.cu']
+SIMT_UNITS = ['api.cu', 'elementwise.cu', 'backward.cu', 'degrade.cu', 'conv_simt.cu', 'model2_bwd.cu', 'repack.cu', 'linattn_small.cu', 'layernorm_multi.cu', 'final_proj.cu', 'linattn_ctx.cu', 'linattn_bwd.cu', 'snow_gen.cu']
 
 
 def build_all():

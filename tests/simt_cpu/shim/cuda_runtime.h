@@ -157,6 +157,9 @@ static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frsqrt_rn(float x) { return 1.0f / sqrtf(x); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }    // volatile: no contraction into an FMA
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }

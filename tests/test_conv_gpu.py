@@ -37,7 +37,7 @@ def run_conv(ops, d, impl):
     from cold_diffusion_models_b200._lib import lib
     lib.cd_conv_tc_set_2cta(2 if impl in ('tc2', 'tc2n') else 0)
     lib.cd_conv_tc_set_2cta_bn(192 if impl == 'tc2n' else 0)
-    lib.cd_conv_tc_set_halo(1 if impl in ('tc3', 'tc3x2') else 0)       # 'tc3': halo-tile kernel (csrc/conv_tc3.cu) where eligible
+    lib.cd_conv_tc_set_halo(1 if impl in ('tc3', 'tc3x2') else (2 if impl == 'tc4' else 0))   # 'tc3' / 'tc4': halo-tile kernels (csrc/conv_tc3.cu, conv_tc4.cu) where eligible
     lib.cd_conv_tc_set_two_ctas(192 if impl in ('tcx2', 'tc3x2') else 0)  # '..x2': two CTAs per SM for the N <= 128 tiles
     try:
         ops.conv_fwd(d, ops.CONV_SIMT if impl == 'simt' else ops.CONV_TC)
@@ -68,7 +68,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc2n', 'tc3', 'tcx2', 'tc3x2'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc2n', 'tc3', 'tc4', 'tcx2', 'tc3x2'])
 @pytest.mark.parametrize('case', CASES)
 def test_conv_stride1(ops, case, impl):
     B, Ci, Co, H, W, k, pad = case
@@ -91,7 +91,7 @@ def test_conv_stride1(ops, case, impl):
     assert rel(nchw(out.cpu()), ref_act) < 1e-5
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc3'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2', 'tc3', 'tc4'])
 def test_conv_two_sources_channel_slices(ops, impl):
     """3x3 over h plus the 1x1 res_conv over x accumulated in one GEMM (ConvNextBlock tail, DB:151-154,164);
     sources/outputs are channel slices of wider NHWC buffers."""
@@ -157,6 +157,48 @@ def test_conv_halo_tile_kernel_forward_and_data_gradient(ops, case):
                                act=ops.ACT_GELU_BWD, aux=ops.View(pred))
         run_conv(ops, d, impl)
         assert rel(nchw(dx.cpu()), refd) < 1e-5, impl
+
+
+@pytest.mark.parametrize('case', [(2, 64, 64, 16, 16, 3), (1, 128, 128, 32, 48, 3), (3, 96, 100, 16, 32, 3), (2, 128, 64, 64, 64, 3),
+                                  (1, 32, 64, 128, 128, 3), (2, 256, 128, 32, 32, 3), (5, 64, 128, 16, 16, 3)])
+def test_conv_wide_halo_tile_kernel_forward_and_data_gradient(ops, case):
+    """csrc/conv_tc4.cu: one 18 x 18 halo patch per channel chunk, two 128-row blocks (left / right patch half, two TMEM accumulators)
+    per weight tile, 2304-byte group stride -- forward taps and flipped (data-gradient) taps with the GELU' epilogue, single patch,
+    non-square grids, Cout that is not a tile multiple, both N tiles, more tiles than SMs; against fp64 and the per-tap kernel"""
+    B, Ci, Co, H, W, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = tf32_rn(torch.randn(B, Ci, H, W, generator=g))
+    w = tf32_rn(torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5)
+    b = torch.randn(Co, generator=g)
+    r = torch.randn(B, H, W, Co, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1) + nchw(r).double()
+    xd = nhwc(x).cuda()
+    outs = []
+    pow2 = lambda v: v & (v - 1) == 0
+    impls = ('tc', 'tc4') if (pow2(W) and pow2(H)) else ('tc4',)      # the per-tap kernel tiles power-of-two grids only
+    for impl in impls:
+        out, out2 = torch.full((B, H, W, Co), 7.0, device='cuda'), torch.full((B, H, W, Co), 7.0, device='cuda')
+        d = ops.make_conv_desc([(ops.View(xd), ops.taps_conv(3, 1), ops.pack_weight(w.cuda(), ops.taps_conv(3, 1), round_tf32=False), False)],
+                               ops.View(out), (B, H, W), Cout=Co, bias=b.cuda(), resid=ops.View(r.cuda()), act=ops.ACT_GELU, out2=ops.View(out2))
+        run_conv(ops, d, impl)
+        assert rel(nchw(out2.cpu()), ref) < 1e-5, impl
+        assert rel(nchw(out.cpu()), F.gelu(ref)) < 1e-5, impl
+        outs.append(out2)
+    assert rel(outs[-1], outs[0]) < 1e-5                    # same products, other summation order
+    dy = tf32_rn(torch.randn(B, Co, H, W, generator=g))
+    pre = torch.randn(B, Ci, H, W, generator=g)
+    refd = F.conv_transpose2d(dy.double(), w.double(), padding=1)
+    cdf = 0.5 * (1 + torch.erf(pre.double() / 2 ** 0.5)); pdf = torch.exp(-0.5 * pre.double() ** 2) / (2 * np.pi) ** 0.5
+    refd = refd * (cdf + pre.double() * pdf)
+    dyd, pred = nhwc(dy).cuda(), nhwc(pre).cuda()
+    pwT = ops.pack_weight(w.cuda(), ops.taps_conv_dgrad(3, 1), mode=1, round_tf32=False)
+    if Ci <= 128:
+        for impl in impls:
+            dx = torch.full((B, H, W, Ci), 7.0, device='cuda')
+            d = ops.make_conv_desc([(ops.View(dyd), ops.taps_conv_dgrad(3, 1), pwT, False)], ops.View(dx), (B, H, W), Cout=Ci,
+                                   act=ops.ACT_GELU_BWD, aux=ops.View(pred))
+            run_conv(ops, d, impl)
+            assert rel(nchw(dx.cpu()), refd) < 1e-5, impl
 
 
 @pytest.mark.parametrize('impl', ['simt', 'tc', 'tc2'])

@@ -161,7 +161,7 @@ def _snow_cfg(key):
 
 def test_snow_decolor_oracle_and_host_tables_match_reference():
     import snow_oracle as SO
-    from cold_diffusion_models_b200.snowification import DeColorization, Snow
+    from cold_diffusion_models_b200.snowification import DeColorization
     g = load('snow_small')
     u = load('unet_small')
     sd = {k[3:]: v for k, v in u.items() if k.startswith('sd:')}
@@ -172,10 +172,10 @@ def test_snow_decolor_oracle_and_host_tables_match_reference():
             host = DeColorization(num_timesteps=T, **kw)
             fp = SO.DecolorFP(host.factors)
         else:
-            host = Snow(image_size=(32, 32), num_timesteps=T, snow_level=kw.get('snow_level', 1), fix_brightness=kw.get('fix_brightness', False))
-            assert torch.allclose(host.snow_t, g['snow:' + key], atol=1e-6), key     # host snow-layer generator == reference layers
-            assert torch.allclose(host.br_t, g['br:' + key], atol=1e-7)
-            fp = SO.SnowFP(host.snow_t, host.br_coef_list, fix_brightness=host.fix_brightness)
+            layers, br = SO.generate_snow_layers((32, 32), snow_level=kw.get('snow_level', 1), num_timesteps=T)
+            assert torch.allclose(layers, g['snow:' + key], atol=1e-6), key     # oracle snow-layer generator == reference layers
+            assert torch.allclose(torch.tensor(br), g['br:' + key], atol=1e-7)
+            fp = SO.SnowFP(layers, br, fix_brightness=kw.get('fix_brightness', False))
         o = SO.SnowOracle(fn, fp, timesteps=T, sampling_routine=samp)
         assert torch.allclose(o.q_sample(g['x'], torch.tensor([T - 1, -1, 1])), g['q:' + key], atol=2e-6), key
         with torch.no_grad():

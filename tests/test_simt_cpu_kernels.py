@@ -461,3 +461,36 @@ def test_batched_column_sums_float4_variant(cpulib, B, rows, Cc, pad, out_ld):
     for o in res:
         assert close(o, want, 2e-5)
         assert bool((o[:, Cc:] == 0.5).all())
+
+
+@pytest.mark.parametrize('h,level,T,single,SB', [(32, 1, 6, False, 1), (32, 2, 5, True, 4), (87, 3, 3, False, 1), (128, 4, 3, True, 2),
+                                                 (150, 1, 2, False, 1), (64, 2, 4, True, 3)])
+def test_snow_layer_generator_source_against_scipy_and_torch(cpulib, h, level, T, single, SB):
+    """cd_snow_layers (csrc/snow_gen.cu) from its CUDA source: the zoomed base field is BIT-IDENTICAL to scipy.ndimage.zoom + centre
+    trim (FP:32-42; sizes 87 and 150 include the coordinate that rounds past the last sample, where scipy returns the constant 0),
+    the layers equal oracle/snow_oracle.py's restatement of FP:252-355 (threshold, clip, conv2d motion blur) to 1e-6, and the numpy
+    emulator agrees with both"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    import snow_oracle as SO
+    from cold_diffusion_models_b200.snowification import Snow
+    np.random.seed(1000 + h); torch.manual_seed(h)
+    st_np, st_t = np.random.get_state(), torch.get_rng_state()
+    ref, _ = SO.generate_snow_layers((h, h), snow_level=level, num_timesteps=T, random_snow=True, single_snow=single, batch_size=SB)
+    c = SO.SNOW_LEVELS[level][0]
+    np.random.set_state(st_np)
+    ref_base = np.stack([SO.clipped_zoom(np.random.normal(size=(h, h), loc=c[0], scale=c[1])[..., None], c[2])[..., 0]
+                         for _ in range(SB if single else 1)]).astype(np.float32)
+    np.random.set_state(st_np); torch.set_rng_state(st_t)
+    sn = Snow(image_size=(h, h), snow_level=level, num_timesteps=T, random_snow=True, single_snow=single, batch_size=SB)   # same draws
+    ch, m, trim, hh = sn._geom
+    nsb = sn._vertical.shape[1]
+    outs = []
+    for impl in (cpulib.cd_snow_layers, E.cd_snow_layers):
+        base, out = torch.full((nsb, h, h), 7.0), torch.full((T, nsb, 3, h, h), 7.0)
+        rc = impl(P(sn._noise), nsb, ch, m, trim, hh, P(sn._thres), P(sn._taps), int(sn._taps.shape[1]), P(sn._vertical), T, P(base), P(out), None)
+        assert rc == 0
+        outs.append((base, out))
+    for base, out in outs:
+        assert np.array_equal(base.numpy(), ref_base), (h, level)
+        assert float((out - ref).abs().max()) < 1e-6, (h, level)
+    assert float((outs[0][1] - outs[1][1]).abs().max()) < 1e-6

@@ -7,14 +7,12 @@ import cold_diffusion_models_b200 as cdm
 from cold_diffusion_models_b200._lib import lib
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-# name: (2cta mode, 2cta N-tile mask, halo, two-CTAs-per-SM mask)
+# name: (2cta mode, 2cta N-tile mask, halo-kernel mask (1: conv_tc3, 2: conv_tc4), two-CTAs-per-SM mask)
 CONFIGS = collections.OrderedDict([
     ('1cta', (0, 0, 0, 0)),
     ('pair256+128', (1, 128, 0, 0)),
-    ('twoCTA', (1, 128, 0, 192)),
-    ('halo', (1, 128, 1, 0)),
-    ('halo+twoCTA', (1, 128, 1, 192)),
-    ('halo+two64', (1, 128, 1, 64)),
+    ('wide-halo', (1, 128, 2, 0)),
+    ('halo16x8', (1, 128, 1, 0)),
 ])
 DEFAULT = (1, 128, 0, 0)
 
