@@ -150,6 +150,78 @@ umma1_kernel(int iters, int stages, long long* cycles, const float* __restrict__
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
 }
 
+// A faithful miniature of the convolution main loop: a producer warp refills stage s with ONE bulk copy (A + B bytes, L2-resident
+// source) as soon as the MMAs that read it have retired (tcgen05.commit -> empty[s]); the MMA warp waits for full[s], issues
+// MPS MMAs (4 = one 32-channel chunk; 8 = the two row blocks of conv_tc4.cu) and commits.  clk / MMA against the number of
+// stages gives the refill latency: with S stages of one chunk each, clk per chunk = max(MMA time, latency / S).
+template <int BN, int MPS>
+__global__ void __launch_bounds__(128, 1)
+pipe_kernel(int iters, int stages, long long* cycles, const float* __restrict__ gsrc) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  __shared__ uint64_t full[16], empty[16], bar;
+  __shared__ uint32_t slot;
+  constexpr int kA = 128 * 128 * (MPS / 4), kB = BN * 128;
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = slot;
+  const uint32_t base = smem_u32(smem);
+  const uint32_t bytes = kA + kB;
+  if (warp == 0) {
+    const char* src = reinterpret_cast<const char*>(gsrc) + static_cast<size_t>(blockIdx.x) * 8 * bytes;
+    uint32_t s = 0, ph = 0;
+    for (int c = 0; c < iters; ++c) {
+      mbar_wait(&empty[s], ph ^ 1u);
+      if (elect_one()) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&full[s])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(base + s * bytes), "l"(src + (c & 7) * bytes), "r"(bytes), "r"(smem_u32(&full[s])) : "memory");
+      }
+      __syncwarp();
+      if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    uint32_t s = 0, ph = 0;
+    const long long t0 = clock64();
+    for (int c = 0; c < iters; ++c) {
+      mbar_wait(&full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t a = base + s * bytes, b = a + kA;
+        const uint64_t da0 = kmajor_sw128_desc(a), db0 = kmajor_sw128_desc(b);
+#pragma unroll
+        for (int k = 0; k < MPS; ++k)
+          asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                       :: "r"(tmem + (k / 4) * BN), "l"(da0 + (k / 4) * 1024 + 2 * (k % 4)), "l"(db0 + 2 * (k % 4)), "r"(idesc), "r"((c | (k % 4)) ? 1u : 0u));
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty[s])) : "memory");
+      }
+      __syncwarp();
+      if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+    }
+    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (elect_one()) cycles[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+}
+
 // SM pair: M = 256 (128 rows per CTA), each CTA holds BN/2 rows of B
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
@@ -233,6 +305,29 @@ static int run_copy(const char* name, K kernel, int grid, int bn, int a_bytes, i
 }
 
 template <typename K>
+static int run_pipe(const char* name, K kernel, int grid, int bn, int mps, int stages) {
+  const int iters = 4000;
+  const int bytes = 128 * 128 * (mps / 4) + bn * 128;
+  const size_t smem = static_cast<size_t>(stages) * bytes + 1024;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long* d = nullptr;
+  float* src = nullptr;
+  CK(cudaMalloc(&d, sizeof(long long) * grid));
+  CK(cudaMalloc(&src, static_cast<size_t>(grid) * 8 * bytes));
+  CK(cudaMemset(src, 0, static_cast<size_t>(grid) * 8 * bytes));
+  for (int rep = 0; rep < 3; ++rep) kernel<<<grid, 128, smem>>>(iters, stages, d, src);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(grid);
+  CK(cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+  std::sort(h.begin(), h.end());
+  const double clk = static_cast<double>(h[grid / 2]) / (iters * (double)mps);
+  printf("%-34s N=%3d  %2d stages x %5.1f KB, %d MMAs per stage: %7.1f clk/MMA  %6.1f B/clk/SM delivered, %6.0f clk per stage\n",
+         name, bn, stages, bytes / 1024.0, mps, clk, bytes / (clk * mps), clk * mps);
+  CK(cudaFree(d)); CK(cudaFree(src));
+  return 0;
+}
+
+template <typename K>
 static int run(const char* name, K kernel, int grid, int ncycles, int bn, int m, int kper, int a_bytes, int b_bytes, int stages) {
   const int iters = 4000;
   const size_t smem = static_cast<size_t>(stages) * (a_bytes + b_bytes) + 1024;
@@ -287,6 +382,11 @@ int main() {
   // the halo-tile addressing of conv_tc3.cu
   rc |= run("tf32 K-major halo rows, 1 CTA", umma1_kernel<64, 3>, g_sms, g_sms, 64, 128, 8, 24 * 1024, 64 * 128, 4);
   rc |= run("tf32 K-major halo rows, 1 CTA", umma1_kernel<128, 3>, g_sms, g_sms, 128, 128, 8, 24 * 1024, 128 * 128, 4);
+  // producer / consumer ring fed by bulk copies
+  for (int st : {2, 4, 8}) rc |= run_pipe("ring: copy -> 4 MMAs -> commit", pipe_kernel<64, 4>, g_sms, 64, 4, st);
+  for (int st : {2, 4, 6}) rc |= run_pipe("ring: copy -> 4 MMAs -> commit", pipe_kernel<128, 4>, g_sms, 128, 4, st);
+  for (int st : {2, 4}) rc |= run_pipe("ring: copy -> 4 MMAs -> commit", pipe_kernel<256, 4>, g_sms, 256, 4, st);
+  for (int st : {2, 4, 5}) rc |= run_pipe("ring: copy -> 8 MMAs -> commit", pipe_kernel<64, 8>, g_sms, 64, 8, st);
   // MMAs + a producer writing shared memory at the same time
   rc |= run_copy("tf32 K-major + bulk copies", umma1_kernel<64, 0, true>, g_sms, 64, 128 * 128, 64 * 128, 4);
   rc |= run_copy("tf32 K-major + bulk copies", umma1_kernel<128, 0, true>, g_sms, 128, 128 * 128, 128 * 128, 4);
