@@ -123,65 +123,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int kiters = p.ntaps[0] * p.kchunks[0] + (p.nsrc > 1 ? p.ntaps[1] * p.kchunks[1] : 0);
 
   if (warp == 0) {
-    // ===================== TMA producer (whole warp walks the schedule, one elected lane issues) =====================
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int co_t = tile % p.tiles_co;
-      int mt = tile / p.tiles_co;
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int tn = mt / p.tiles_y;
-      const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN, co0 = co_t * BN;
-      for (int s = 0; s < p.nsrc; ++s) {
-        const CUtensorMap* mA = s ? &mapA1 : &mapA0;
-        const CUtensorMap* mB = s ? &mapB1 : &mapB0;
-        const int wbase = p.wpb[s] ? n0 * p.ntaps[s] : 0;
-        for (int tap = 0; tap < p.ntaps[s]; ++tap) {
-          const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
-          for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it) {
-            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-            mbar_wait(&empty_bar[stage], ph ^ 1u);
-            if (elect_one()) {
+    // ===================== TMA producer: ONE elected thread runs the whole schedule =====================
+    if (elect_one()) {
+      uint32_t stage = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int co_t = tile % p.tiles_co;
+        int mt = tile / p.tiles_co;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int tn = mt / p.tiles_y;
+        const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN, co0 = co_t * BN;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const CUtensorMap* mA = s ? &mapA1 : &mapA0;
+          const CUtensorMap* mB = s ? &mapB1 : &mapB0;
+          const int wbase = p.wpb[s] ? n0 * p.ntaps[s] : 0;
+          for (int tap = 0; tap < p.ntaps[s]; ++tap) {
+            const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
+            for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+              mbar_wait(&empty_bar[stage], ph ^ 1u);
               mbar_expect_tx(&full_bar[stage], kStageBytes);
               const uint32_t sa = smem_u32(smem + stage * kStageBytes);
               tma_load_4d(sa, mA, &full_bar[stage], kc * kChunkElems, xin, yin, n0);
               tma_load_3d(sa + kABytes, mB, &full_bar[stage], kc * kChunkElems, co0, wbase + tap);
+              if (++stage == STAGES) { stage = 0; ph ^= 1u; }
             }
-            __syncwarp();
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp waits on the barriers, one elected lane issues) =====================
-    uint32_t it = 0, tcount = 0;
-    const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(smem));
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-      mbar_wait(&tmem_empty[acc], accph ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int k = 0; k < kiters; ++k, ++it) {
-        const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-        mbar_wait(&full_bar[stage], ph);
-        tc_fence_after();
-        if (elect_one()) {
+    // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+    // tools/micro/umma_rate.cu (profiles/umma_rate_r02.txt): barrier polls, commits and MMAs go through one in-order queue.  A
+    // loop of the form { wait full[s]; 4 MMAs; commit } leaves the tensor core idle from the moment the last MMA is handed over
+    // until the next poll has returned and the next descriptors are built (77 clk per 128x64x8 MMA instead of 50; the per-chunk
+    // elect / reconverge of a whole-warp loop adds to it).  Here the barrier of the NEXT chunk is polled in the MIDDLE of this
+    // chunk's MMAs: its result comes back while the first two MMAs execute and the last two are queued behind it, so the tensor
+    // core always has work while the thread commits, advances the ring and builds descriptors (53 clk / MMA in the same test).
+    // The poll is a single non-blocking test: when the data is late (L2-bound layers) the chunk is finished and committed first.
+    if (elect_one()) {
+      uint32_t stage = 0, ph = 0, tcount = 0;
+      const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(smem));
+      if (static_cast<int>(blockIdx.x) < p.total_tiles) {
+        mbar_wait(&tmem_empty[0], 1u);
+        mbar_wait(&full_bar[0], 0u);
+      }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        const bool more_tiles = tile + static_cast<int>(gridDim.x) < p.total_tiles;
+        for (int k = 0; k < kiters; ++k) {
+          tc_fence_after();
           // descriptors of this stage = descriptor of stage 0 + a multiple of the stage size (the 14-bit address field cannot
-          // carry: shared memory ends below 256 KB); everything the single issuing thread executes per chunk is on the critical path
+          // carry: shared memory ends below 256 KB)
           const uint64_t da = desc0 + static_cast<uint64_t>(stage * uint32_t(kStageBytes >> 4));
           const uint64_t db = da + uint64_t(kABytes >> 4);
+          uint32_t sn = stage + 1, phn = ph;
+          if (sn == STAGES) { sn = 0; phn ^= 1u; }
+          const bool last = k == kiters - 1;
+          const bool more = !last || more_tiles;
+          uint32_t ready = 0;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {          // 4 x (K = 8 tf32 = 32 bytes) per 128-byte row
+            if (kk == 2 && more) {                  // ONE poll of the next chunk's barrier (of this tile or of the next one)
+              ready = mbar_test(&full_bar[sn], phn);
+              if (last) ready &= mbar_test(&tmem_empty[acc ^ 1u], (((tcount + 1) >> 1) & 1u) ^ 1u);   // next tile's accumulator drained
+            }
             if constexpr (F16) mma_f16(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
             else mma_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);             // frees the smem slot once these MMAs retire
+          if (more && !ready) {                     // data not there yet: nothing to overlap, wait in the open
+            mbar_wait(&full_bar[sn], phn);
+            if (last) mbar_wait(&tmem_empty[acc ^ 1u], (((tcount + 1) >> 1) & 1u) ^ 1u);
+          }
+          stage = sn; ph = phn;
         }
-        __syncwarp();
+        tc_commit(&tmem_full[acc]);                 // accumulator complete -> epilogue
       }
-      if (elect_one()) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..17) =====================
     // The epilogue (TMEM -> regs -> bias/GELU/residual -> global) costs about as many issue slots per tile as the
@@ -337,11 +358,13 @@ int cd_conv_fwd_tc2(const CdConvDesc* d, cudaStream_t st, int BN);   // conv_tc2
 static int g_use_2cta = 1;
 extern "C" int cd_conv_tc_set_2cta(int mode) { g_use_2cta = mode; return 0; }   // 0 off, 1 where the cost model prefers it, 2 wherever eligible
 // halo-tile kernels for stride-1 convolutions with taps in [-1, 1]^2, bit mask: 1 = conv_tc3.cu (16 x 8 patch) wherever eligible,
-// 2 = conv_tc4.cu (16 x 16 patch, two accumulators per weight tile) for Cout <= 128
+// 2 = conv_tc4.cu (16 x 16 patch, two accumulators per weight tile) for Cout <= 128 where its tile count model says so (default),
+// 4 (with 2) = conv_tc4.cu for every eligible problem (tests)
 int cd_conv_fwd_tc3(const CdConvDesc* d, cudaStream_t st);
 int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st);
-static int g_use_halo = 0;
-extern "C" int cd_conv_tc_set_halo(int enable) { g_use_halo = enable; return 0; }
+void cd_conv_tc4_force(int on);
+static int g_use_halo = 2;
+extern "C" int cd_conv_tc_set_halo(int enable) { g_use_halo = enable; cd_conv_tc4_force((enable & 4) ? 1 : 0); return 0; }
 // two CTAs per SM (8 epilogue warps, half the stages each) for the 1-CTA kernels with N <= 128: bit mask of N tiles (128 | 64)
 static int g_ctas2 = 0;
 extern "C" int cd_conv_tc_set_two_ctas(int mask) { g_ctas2 = mask & (128 | 64); return 0; }

@@ -117,63 +117,77 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; completion lands on the leader's full barrier) =====================
-    // the whole warp walks the schedule and waits on the barriers, one elected lane issues (see elect_one in tc_common.cuh)
-    uint32_t it = 0;
-    for (int tile = cl; tile < p.total_tiles; tile += ncl) {
-      const int co_t = tile % p.tiles_co;
-      int mt = (tile / p.tiles_co) * 2 + static_cast<int>(rank);        // this CTA's 128-pixel tile (may be past the end: zero fill)
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int tn = mt / p.tiles_y;
-      const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN;
-      const int co0 = co_t * BN + static_cast<int>(rank) * (BN / 2);     // this CTA's half of the weight rows
-      for (int s = 0; s < p.nsrc; ++s) {
-        const CUtensorMap* mA = s ? &mapA1 : &mapA0;
-        const CUtensorMap* mB = s ? &mapB1 : &mapB0;
-        for (int tap = 0; tap < p.ntaps[s]; ++tap) {
-          const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
-          for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it) {
-            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-            mbar_wait(&empty_bar[stage], ph ^ 1u);
-            if (elect_one()) {
+    // one elected thread runs the whole schedule
+    if (elect_one()) {
+      uint32_t stage = 0, ph = 0;
+      for (int tile = cl; tile < p.total_tiles; tile += ncl) {
+        const int co_t = tile % p.tiles_co;
+        int mt = (tile / p.tiles_co) * 2 + static_cast<int>(rank);        // this CTA's 128-pixel tile (may be past the end: zero fill)
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int tn = mt / p.tiles_y;
+        const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy, n0 = tn * p.TN;
+        const int co0 = co_t * BN + static_cast<int>(rank) * (BN / 2);     // this CTA's half of the weight rows
+        for (int s = 0; s < p.nsrc; ++s) {
+          const CUtensorMap* mA = s ? &mapA1 : &mapA0;
+          const CUtensorMap* mB = s ? &mapB1 : &mapB0;
+          for (int tap = 0; tap < p.ntaps[s]; ++tap) {
+            const int xin = x0 + p.dx[s][tap], yin = y0 + p.dy[s][tap];
+            for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+              mbar_wait(&empty_bar[stage], ph ^ 1u);
               if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
               const uint32_t sa = smem_u32(smem + stage * kStageBytes);
               tma2_load_4d(sa, mA, &full_bar[stage], kc * kChunkK, xin, yin, n0);
               tma2_load_3d(sa + kABytes, mB, &full_bar[stage], kc * kChunkK, co0, tap);
+              if (++stage == STAGES) { stage = 0; ph ^= 1u; }
             }
-            __syncwarp();
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (leader) {
-      // ===================== MMA issuer (leader CTA only; whole warp waits, one elected lane issues) =====================
-      uint32_t it = 0, tcount = 0;
+    if (leader && elect_one()) {
+      // ===================== MMA issuer (leader CTA only): one elected thread runs the whole loop =====================
+      // the barrier of the NEXT chunk is polled between this chunk's MMAs (conv_tc.cu explains; tools/micro/umma_rate.cu)
+      uint32_t stage = 0, ph = 0, tcount = 0;
       const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(smem));
+      if (cl < p.total_tiles) {
+        mbar_wait(&tmem_empty[0], 1u);
+        mbar_wait(&full_bar[0], 0u);
+      }
       for (int tile = cl; tile < p.total_tiles; tile += ncl, ++tcount) {
-        const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-        mbar_wait(&tmem_empty[acc], accph ^ 1u);
-        tc_fence_after();
+        const uint32_t acc = tcount & 1u;
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int k = 0; k < kiters; ++k, ++it) {
-          const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-          mbar_wait(&full_bar[stage], ph);
+        const bool more_tiles = tile + ncl < p.total_tiles;
+        for (int k = 0; k < kiters; ++k) {
           tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da = desc0 + static_cast<uint64_t>(stage * uint32_t(kStageBytes >> 4));   // the 14-bit address field cannot carry
-            const uint64_t db = da + uint64_t(kABytes >> 4);
+          const uint64_t da = desc0 + static_cast<uint64_t>(stage * uint32_t(kStageBytes >> 4));   // the 14-bit address field cannot carry
+          const uint64_t db = da + uint64_t(kABytes >> 4);
+          uint32_t sn = stage + 1, phn = ph;
+          if (sn == STAGES) { sn = 0; phn ^= 1u; }
+          const bool last = k == kiters - 1;
+          const bool more = !last || more_tiles;
+          uint32_t ready = 0;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma2_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
-            tc_commit_pair(&empty_bar[stage]);
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk == 2 && more) {                  // one non-blocking poll
+              ready = mbar_test(&full_bar[sn], phn);
+              if (last) ready &= mbar_test(&tmem_empty[acc ^ 1u], (((tcount + 1) >> 1) & 1u) ^ 1u);
+            }
+            mma2_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (k | kk) != 0 ? 1u : 0u);
           }
-          __syncwarp();
+          tc_commit_pair(&empty_bar[stage]);
+          if (more && !ready) {
+            mbar_wait(&full_bar[sn], phn);
+            if (last) mbar_wait(&tmem_empty[acc ^ 1u], (((tcount + 1) >> 1) & 1u) ^ 1u);
+          }
+          stage = sn; ph = phn;
         }
-        if (elect_one()) tc_commit_pair(&tmem_full[acc]);
-        __syncwarp();
+        tc_commit_pair(&tmem_full[acc]);
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..17 of both CTAs, each on its own 128 accumulator rows) =====================
     const int q = warp & 3;

@@ -41,6 +41,7 @@ struct Tc4Params {
   float* out2; int out2_ld;
   const float* aux; int aux_ld;
   int vec8;
+  int dbg;                        // timing experiments only (cd_conv_tc_set_debug): 1 = epilogue without global accesses, 2 = without TMEM loads either
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -118,87 +119,113 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer: one halo patch per channel chunk, one weight tile per (chunk, tap) =====================
-    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int co_t = tile % p.tiles_co;
-      int mt = tile / p.tiles_co;
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int n = mt / p.tiles_y;
-      const int x0 = tx * kPW - 1, y0 = ty * kPH - 1, co0 = co_t * BN;
-      for (int s = 0; s < p.nsrc; ++s) {
-        const CUtensorMap* mA = s ? &mapA1 : &mapA0;
-        const CUtensorMap* mB = s ? &mapB1 : &mapB0;
-        const int nt = p.ntaps[s];
-        for (int kc = 0; kc < p.kchunks[s]; ++kc) {
-          mbar_wait(&a_empty[sa], pha ^ 1u);
-          if (elect_one()) {
+    // one elected thread runs the whole schedule
+    if (elect_one()) {
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int co_t = tile % p.tiles_co;
+        int mt = tile / p.tiles_co;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int n = mt / p.tiles_y;
+        const int x0 = tx * kPW - 1, y0 = ty * kPH - 1, co0 = co_t * BN;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const CUtensorMap* mA = s ? &mapA1 : &mapA0;
+          const CUtensorMap* mB = s ? &mapB1 : &mapB0;
+          const int nt = p.ntaps[s];
+          for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+            mbar_wait(&a_empty[sa], pha ^ 1u);
             mbar_expect_tx(&a_full[sa], kABytesTx);
             tma_load_4d(smem_u32(smemA + sa * kAStage), mA, &a_full[sa], kc * 32, x0, y0, n);
-          }
-          __syncwarp();
-          if (++sa == ASTAGES) { sa = 0; pha ^= 1u; }
-          for (int tap = 0; tap < nt; ++tap) {
-            mbar_wait(&b_empty[sb], phb ^ 1u);
-            if (elect_one()) {
+            if (++sa == ASTAGES) { sa = 0; pha ^= 1u; }
+            for (int tap = 0; tap < nt; ++tap) {
+              mbar_wait(&b_empty[sb], phb ^ 1u);
               mbar_expect_tx(&b_full[sb], kBBytes);
               tma_load_3d(smem_u32(smemB + sb * kBBytes), mB, &b_full[sb], kc * 32, co0, tap);
+              if (++sb == BSTAGES) { sb = 0; phb ^= 1u; }
             }
-            __syncwarp();
-            if (++sb == BSTAGES) { sb = 0; phb ^= 1u; }
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // Everything this warp executes per tap is on the critical path of a 128-clk (N = 64) MMA group: ring positions are
-    // incremented (no division by the stage count), and the first patch row of every tap comes from a shared-memory table whose
-    // next entry is fetched before the barrier wait (an indexed load of the kernel parameters costs a constant-cache round trip).
-    uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tcount = 0;
-    const uint64_t descA0 = make_desc_sbo(smem_u32(smemA), kHW * 128);      // 8-row groups (8 pixels of a patch row) are 18 rows apart
-    const uint64_t descB0 = make_desc_sbo(smem_u32(smemB), 1024);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t acc = tcount & 1u, accph = (tcount >> 1) & 1u;
-      mbar_wait(&tmem_empty[acc], accph ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * (2 * BN);
-      uint32_t first = 0;
-      for (int s = 0; s < p.nsrc; ++s) {
-        const int nt = p.ntaps[s];
-        const uint32_t* tab = arow_tab + s * (CD_MAX_TAPS + 1);
-        for (int kc = 0; kc < p.kchunks[s]; ++kc) {
-          mbar_wait(&a_full[sa], pha);
-          const uint64_t da0 = descA0 + static_cast<uint64_t>(sa * uint32_t(kAStage >> 4));
-          uint32_t arow8 = tab[0];
-          for (int tap = 0; tap < nt; ++tap) {
-            const uint32_t arow8_next = tab[tap + 1];                  // table has a spare entry
-            mbar_wait(&b_full[sb], phb);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t da = da0 + static_cast<uint64_t>(arow8);
-              const uint64_t db = descB0 + static_cast<uint64_t>(sb * uint32_t(kBBytes >> 4));
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {                   // right half: 8 pixels = 8 rows of 128 bytes further
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  mma_tf32(tmem_d + half * BN, da + uint64_t(half * 64 + kk * 2), db + uint64_t(kk * 2), kIdesc,
-                           (first | uint32_t(kk)) != 0 ? 1u : 0u);
-              }
-              tc_commit(&b_empty[sb]);
-              if (tap == nt - 1) tc_commit(&a_empty[sa]);              // the halo patch is free once its last tap retired
-            }
-            __syncwarp();
-            first = 1;
-            arow8 = arow8_next;
-            if (++sb == BSTAGES) { sb = 0; phb ^= 1u; }
-          }
-          if (++sa == ASTAGES) { sa = 0; pha ^= 1u; }
-        }
+    // ===================== MMA issuer: one elected thread runs the whole loop =====================
+    // Barrier polls, commits and MMAs pass through one in-order queue (tools/micro/umma_rate.cu): the barriers the NEXT tap needs
+    // (its weight tile; the next halo patch when a chunk ends; the next accumulator pair when the tile ends) are polled between
+    // the two row blocks of THIS tap, so the tensor core has four queued MMAs to execute while the thread commits, advances the
+    // rings and builds the next descriptors.  The first patch row of every tap comes from a shared-memory table.
+    if (elect_one()) {
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tcount = 0;
+      const uint64_t descA0 = make_desc_sbo(smem_u32(smemA), kHW * 128);      // 8-row groups (8 pixels of a patch row) are 18 rows apart
+      const uint64_t descB0 = make_desc_sbo(smem_u32(smemB), 1024);
+      if (static_cast<int>(blockIdx.x) < p.total_tiles) {
+        mbar_wait(&tmem_empty[0], 1u);
+        mbar_wait(&a_full[0], 0u);
+        mbar_wait(&b_full[0], 0u);
       }
-      if (elect_one()) tc_commit(&tmem_full[acc]);
-      __syncwarp();
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u;
+        const uint32_t tmem_d = tmem_base + acc * (2 * BN);
+        const bool more_tiles = tile + static_cast<int>(gridDim.x) < p.total_tiles;
+        uint32_t first = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const int nt = p.ntaps[s];
+          const bool last_src = s == p.nsrc - 1;
+          // first patch row of every tap in REGISTERS: a shared-memory load in the loop would sit in the same in-order queue as the
+          // MMAs and return only after the MMAs in front of it have been handed to the tensor core
+          uint32_t arow[9];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) arow[t] = arow_tab[s * (CD_MAX_TAPS + 1) + (t < nt ? t : 0)];
+          for (int kc = 0; kc < p.kchunks[s]; ++kc) {
+            const uint64_t da0 = descA0 + static_cast<uint64_t>(sa * uint32_t(kAStage >> 4));
+            uint32_t san = sa + 1, phan = pha;
+            if (san == ASTAGES) { san = 0; phan ^= 1u; }
+            const bool last_chunk = last_src && kc == p.kchunks[s] - 1;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              if (tap < nt) {
+                tc_fence_after();
+                const uint64_t da = da0 + static_cast<uint64_t>(arow[tap]);
+                const uint64_t db = descB0 + static_cast<uint64_t>(sb * uint32_t(kBBytes >> 4));
+                uint32_t sbn = sb + 1, phbn = phb;
+                if (sbn == BSTAGES) { sbn = 0; phbn ^= 1u; }
+                const bool last_tap = tap == nt - 1;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)                             // left patch half
+                  mma_tf32(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdesc, (first | uint32_t(kk)) != 0 ? 1u : 0u);
+                const bool more = !(last_tap && last_chunk) || more_tiles;
+                uint32_t ready = 0;
+                if (more) {                                                // one non-blocking poll of what the next tap needs
+                  ready = mbar_test(&b_full[sbn], phbn);
+                  if (last_tap) {
+                    ready &= mbar_test(&a_full[san], phan);
+                    if (last_chunk) ready &= mbar_test(&tmem_empty[acc ^ 1u], (((tcount + 1) >> 1) & 1u) ^ 1u);
+                  }
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)                             // right half: 8 pixels = 8 rows of 128 bytes further
+                  mma_tf32(tmem_d + BN, da + uint64_t(64 + kk * 2), db + uint64_t(kk * 2), kIdesc, (first | uint32_t(kk)) != 0 ? 1u : 0u);
+                tc_commit(&b_empty[sb]);
+                if (last_tap) tc_commit(&a_empty[sa]);                    // the halo patch is free once its last tap retired
+                if (more && !ready) {                                      // late data: wait in the open, after the commit
+                  mbar_wait(&b_full[sbn], phbn);
+                  if (last_tap) {
+                    mbar_wait(&a_full[san], phan);
+                    if (last_chunk) mbar_wait(&tmem_empty[acc ^ 1u], (((tcount + 1) >> 1) & 1u) ^ 1u);
+                  }
+                }
+                first = 1;
+                sb = sbn; phb = phbn;
+              }
+            }
+            sa = san; pha = phan;
+          }
+        }
+        tc_commit(&tmem_full[acc]);
+      }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..17): same fused epilogue as conv_tc.cu, rows = 16 x 8 pixel patch =====================
     const int q = warp & 3;
@@ -228,7 +255,9 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         float* o2row = p.out2 ? p.out2 + pix * p.out2_ld : nullptr;
         const float* arow = p.aux ? p.aux + pix * p.aux_ld : nullptr;
         uint32_t r[32];
+        if (p.dbg >= 2) continue;
         tmem_ld32(taddr + half * BN + c, r);
+        if (p.dbg == 1) continue;
         if (co0 + c < p.Cout) {
           const int nvalid = min(32, p.Cout - (co0 + c));
           if (nvalid == 32 && p.vec8) {
@@ -287,6 +316,8 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 }
 
 int g_sms4 = 0;
+int g_dbg4 = 0;
+int g_force4 = 0;                  // cd_conv_tc_set_halo(6): take every eligible problem (tests)
 }  // namespace
 namespace {
 
@@ -307,6 +338,9 @@ int launch4(const CUtensorMap* maps, const Tc4Params& p, cudaStream_t st) {
 
 }  // namespace
 
+extern "C" int cd_conv_tc_set_debug(int mode) { g_dbg4 = mode; return 0; }
+void cd_conv_tc4_force(int on) { g_force4 = on; }
+
 // returns 1 when the problem is not eligible (caller continues with conv_tc.cu), 0 on success, < 0 on error
 int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st) {
   if (d->nsrc < 1 || d->nsrc > 2) return 1;
@@ -316,7 +350,7 @@ int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st) {
   bool any3x3 = false;
   for (int s = 0; s < d->nsrc; ++s) {
     const CdConvSrc& cs = d->s[s];
-    if (cs.w_per_batch || cs.C % 32 != 0 || cs.C <= 0 || cs.H != d->Hg || cs.W != d->Wg || cs.ntaps < 1 || cs.ntaps > CD_MAX_TAPS) return 1;
+    if (cs.w_per_batch || cs.C % 32 != 0 || cs.C <= 0 || cs.H != d->Hg || cs.W != d->Wg || cs.ntaps < 1 || cs.ntaps > 9) return 1;
     if ((reinterpret_cast<uintptr_t>(cs.src) & 15) || cs.ld % 4 || (reinterpret_cast<uintptr_t>(cs.w) & 15)) return 1;
     for (int t = 0; t < cs.ntaps; ++t) if (cs.dy[t] < -1 || cs.dy[t] > 1 || cs.dx[t] < -1 || cs.dx[t] > 1) return 1;
     if (cs.ntaps > 1) any3x3 = true;
@@ -324,6 +358,13 @@ int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st) {
   }
   if (!any3x3) return 1;                      // pure 1x1: the halo would only add traffic
   if (d->Cout > 128) return 1;                // 4 x BN TMEM columns; the wide layers run on SM pairs (conv_tc2.cu)
+  if (!g_sms4) { int dev = 0; CD_CUDA(cudaGetDevice(&dev)); CD_CUDA(cudaDeviceGetAttribute(&g_sms4, cudaDevAttrMultiProcessorCount, dev)); }
+  {
+    // 256-pixel tiles need many of them: measured per shape (profiles/conv_shapes_r02e_wide_halo.txt) the kernel wins on the
+    // 128 x 128 level at batch 32 (2048 tiles: 147-163 us against 182-216) and is mixed at 64 x 64 (512 tiles = 3.5 waves)
+    const long long tiles256 = static_cast<long long>(d->B) * (d->Hg / kPH) * (d->Wg / kPW);
+    if (!g_force4 && tiles256 < 6LL * g_sms4) return 1;
+  }
   if ((reinterpret_cast<uintptr_t>(d->out) & 15) || d->out_ld % 4) return 1;
   if (d->resid && ((reinterpret_cast<uintptr_t>(d->resid) & 15) || d->resid_ld % 4)) return 1;
   if (d->out2 && ((reinterpret_cast<uintptr_t>(d->out2) & 15) || d->out2_ld % 4)) return 1;
@@ -331,11 +372,10 @@ int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st) {
   if (d->act == CD_ACT_GELU_BWD && (!d->aux || (reinterpret_cast<uintptr_t>(d->aux) & 15) || d->aux_ld % 4)) return 1;
   EncodeTiledFn enc = get_encode();
   CD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
-  if (!g_sms4) { int dev = 0; CD_CUDA(cudaGetDevice(&dev)); CD_CUDA(cudaDeviceGetAttribute(&g_sms4, cudaDevAttrMultiProcessorCount, dev)); }
-
   Tc4Params p{};
   p.B = d->B; p.H = d->Hg; p.W = d->Wg; p.Cout = d->Cout; p.nsrc = d->nsrc;
   p.tiles_x = d->Wg / kPW; p.tiles_y = d->Hg / kPH;
+  p.dbg = g_dbg4;
   const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * d->B;
   const int BN = d->Cout > 64 ? 128 : 64;
   p.tiles_co = cd_cdiv(d->Cout, BN);

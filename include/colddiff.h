@@ -227,6 +227,9 @@ int cd_conv_tc_set_2cta_bn(int mask);
  * fused [3x3 | 1x1] pairs): 128 GEMM rows = a 16 x 8 pixel patch whose 18 x 10 halo patch is fetched ONCE per channel chunk and
  * read by all nine taps through row-shifted shared-memory descriptors (6x less activation traffic from L2).  0 = off, 1 = on */
 int cd_conv_tc_set_halo(int enable);
+/* timing experiments on the wide halo-tile kernel only (results are NOT written): 1 = epilogue without global accesses, 2 = without
+ * TMEM loads either, 0 = normal */
+int cd_conv_tc_set_debug(int mode);
 /* two co-resident CTAs per SM (8 epilogue warps and half the pipeline stages each) for the one-CTA kernels with N <= 128: the single
  * MMA-issuing thread of a CTA is latency-bound (~8 clk per SASS instruction); two CTAs interleave two instruction streams on the
  * SM's tensor core.  Bit mask of N tiles (128 | 64); 0 = one CTA per SM */

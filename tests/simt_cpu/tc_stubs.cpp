@@ -20,3 +20,4 @@ int cd_dwconv7_fwd_tma(const float*, int, int, int, int, int, const float*, cons
                        cudaStream_t) { return 1; }
 int cd_dwconv7_wgrad_tma(const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t) { return 1; }
 extern "C" int cd_dwconv7_set_tma(int) { return 0; }
+extern "C" int cd_conv_tc_set_debug(int) { return 0; }

@@ -37,7 +37,7 @@ def run_conv(ops, d, impl):
     from cold_diffusion_models_b200._lib import lib
     lib.cd_conv_tc_set_2cta(2 if impl in ('tc2', 'tc2n') else 0)
     lib.cd_conv_tc_set_2cta_bn(192 if impl == 'tc2n' else 0)
-    lib.cd_conv_tc_set_halo(1 if impl in ('tc3', 'tc3x2') else (2 if impl == 'tc4' else 0))   # 'tc3' / 'tc4': halo-tile kernels (csrc/conv_tc3.cu, conv_tc4.cu) where eligible
+    lib.cd_conv_tc_set_halo(1 if impl in ('tc3', 'tc3x2') else (6 if impl == 'tc4' else 0))   # 'tc3' / 'tc4': halo-tile kernels (csrc/conv_tc3.cu, conv_tc4.cu) where eligible
     lib.cd_conv_tc_set_two_ctas(192 if impl in ('tcx2', 'tc3x2') else 0)  # '..x2': two CTAs per SM for the N <= 128 tiles
     try:
         ops.conv_fwd(d, ops.CONV_SIMT if impl == 'simt' else ops.CONV_TC)
@@ -50,7 +50,7 @@ def run_conv(ops, d, impl):
 
 
 _DEFAULT_TWO_CTAS = 0           # library default of cd_conv_tc_set_two_ctas
-_DEFAULT_HALO = 0               # library default of cd_conv_tc_set_halo
+_DEFAULT_HALO = 2               # library default of cd_conv_tc_set_halo (wide halo-tile kernel where its tile count model says so)
 _DEFAULT_2CTA_BN = 128         # library default of cd_conv_tc_set_2cta_bn (narrow pair tiles)
 
 CASES = [

@@ -67,7 +67,7 @@ umma1_kernel(int iters, int stages, long long* cycles, const float* __restrict__
   __shared__ uint64_t cbar;
   __shared__ uint32_t slot;
   __shared__ volatile int done;
-  constexpr int kA = KIND == 3 ? 24 * 1024 : 128 * 128, kB = BN * 128;
+  constexpr int kA = KIND == 4 ? 41 * 1024 : KIND == 3 ? 24 * 1024 : 128 * 128, kB = BN * 128;
   constexpr uint32_t fmt = KIND == 1 ? 1u : 2u;
   constexpr uint32_t major = KIND == 2 ? ((1u << 15) | (1u << 16)) : 0u;
   constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | major | (uint32_t(BN >> 3) << 17) | (uint32_t(128 >> 4) << 24);
@@ -98,6 +98,17 @@ umma1_kernel(int iters, int stages, long long* cycles, const float* __restrict__
             asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                          :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"((c | k) ? 1u : 0u));
           }
+        } else if (KIND == 4) {
+          // conv_tc4.cu: 18-pixel-wide halo tile, tap (dy, dx) starts at row dy * 18 + dx, 8-row groups 2304 bytes apart, two row
+          // blocks (patch halves, 1024 bytes apart) per weight tile with their own accumulators
+          const int tap = c % 9;
+          uint64_t da0 = kmajor_sw128_desc(a + ((tap / 3) * 18 + tap % 3) * 128);
+          da0 = (da0 & ~(static_cast<uint64_t>(0x3FFF) << 32)) | (static_cast<uint64_t>(2304 >> 4) << 32);
+          const uint64_t db0 = kmajor_sw128_desc(b);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                         :: "r"(tmem + (c & 1) * BN), "l"(da0 + (c & 1) * 64 + 2 * k), "l"(db0 + 2 * k), "r"(idesc), "r"(((c >> 1) | k) ? 1u : 0u));
         } else if (KIND == 3) {
           // tap (dy, dx) of a 3x3 kernel: start row = dy * 10 + dx of the halo tile
           const int tap = c % 9;
@@ -154,7 +165,7 @@ umma1_kernel(int iters, int stages, long long* cycles, const float* __restrict__
 // source) as soon as the MMAs that read it have retired (tcgen05.commit -> empty[s]); the MMA warp waits for full[s], issues
 // MPS MMAs (4 = one 32-channel chunk; 8 = the two row blocks of conv_tc4.cu) and commits.  clk / MMA against the number of
 // stages gives the refill latency: with S stages of one chunk each, clk per chunk = max(MMA time, latency / S).
-template <int BN, int MPS>
+template <int BN, int MPS, int COPYB = 0, bool AHEAD = false>
 __global__ void __launch_bounds__(128, 1)
 pipe_kernel(int iters, int stages, long long* cycles, const float* __restrict__ gsrc) {
   extern __shared__ uint8_t smem_raw[];
@@ -181,15 +192,16 @@ pipe_kernel(int iters, int stages, long long* cycles, const float* __restrict__ 
   const uint32_t tmem = slot;
   const uint32_t base = smem_u32(smem);
   const uint32_t bytes = kA + kB;
+  const uint32_t cbytes = COPYB ? COPYB : bytes;          // COPYB: refill only that many bytes per stage (conv_tc4.cu: 8 KB of weights per 8 MMAs)
   if (warp == 0) {
     const char* src = reinterpret_cast<const char*>(gsrc) + static_cast<size_t>(blockIdx.x) * 8 * bytes;
     uint32_t s = 0, ph = 0;
     for (int c = 0; c < iters; ++c) {
       mbar_wait(&empty[s], ph ^ 1u);
       if (elect_one()) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&full[s])), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&full[s])), "r"(cbytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(base + s * bytes), "l"(src + (c & 7) * bytes), "r"(bytes), "r"(smem_u32(&full[s])) : "memory");
+                     :: "r"(base + s * bytes), "l"(src + (c & 7) * bytes), "r"(cbytes), "r"(smem_u32(&full[s])) : "memory");
       }
       __syncwarp();
       if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
@@ -197,22 +209,47 @@ pipe_kernel(int iters, int stages, long long* cycles, const float* __restrict__ 
   } else if (warp == 1) {
     uint32_t s = 0, ph = 0;
     const long long t0 = clock64();
-    for (int c = 0; c < iters; ++c) {
-      mbar_wait(&full[s], ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
+    if (!AHEAD) {
+      for (int c = 0; c < iters; ++c) {
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t a = base + s * bytes, b = a + kA;
+          const uint64_t da0 = kmajor_sw128_desc(a), db0 = kmajor_sw128_desc(b);
+#pragma unroll
+          for (int k = 0; k < MPS; ++k)
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                         :: "r"(tmem + (k / 4) * BN), "l"(da0 + (k / 4) * 1024 + 2 * (k % 4)), "l"(db0 + 2 * (k % 4)), "r"(idesc), "r"((c | (k % 4)) ? 1u : 0u));
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty[s])) : "memory");
+        }
+        __syncwarp();
+        if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+      __syncwarp();
+    } else if (elect_one()) {
+      // ONE thread runs the whole loop (no per-stage elect / reconvergence), and the barrier of the NEXT stage is polled in the
+      // middle of this stage's MMAs: the poll is a queued (MIO) operation like the MMAs, its result returns once the MMAs in
+      // front of it have been handed to the tensor core, and the MMAs issued right after it keep the tensor core busy while the
+      // thread commits, advances the ring and builds the next descriptors.
+      mbar_wait(&full[0], 0);
+      for (int c = 0; c < iters; ++c) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a = base + s * bytes, b = a + kA;
         const uint64_t da0 = kmajor_sw128_desc(a), db0 = kmajor_sw128_desc(b);
+        uint32_t sn = s + 1, phn = ph;
+        if (sn == (uint32_t)stages) { sn = 0; phn ^= 1u; }
 #pragma unroll
-        for (int k = 0; k < MPS; ++k)
+        for (int k = 0; k < MPS; ++k) {
+          if (k == MPS / 2 && c + 1 < iters) mbar_wait(&full[sn], phn);
           asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                        :: "r"(tmem + (k / 4) * BN), "l"(da0 + (k / 4) * 1024 + 2 * (k % 4)), "l"(db0 + 2 * (k % 4)), "r"(idesc), "r"((c | (k % 4)) ? 1u : 0u));
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&empty[s])) : "memory");
+        s = sn; ph = phn;
       }
-      __syncwarp();
-      if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
     }
-    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
     __syncwarp();
     mbar_wait(&bar, 0);
     if (elect_one()) cycles[blockIdx.x] = clock64() - t0;
@@ -382,11 +419,25 @@ int main() {
   // the halo-tile addressing of conv_tc3.cu
   rc |= run("tf32 K-major halo rows, 1 CTA", umma1_kernel<64, 3>, g_sms, g_sms, 64, 128, 8, 24 * 1024, 64 * 128, 4);
   rc |= run("tf32 K-major halo rows, 1 CTA", umma1_kernel<128, 3>, g_sms, g_sms, 128, 128, 8, 24 * 1024, 128 * 128, 4);
+  rc |= run("tf32 K-major 18-wide halo rows", umma1_kernel<64, 4>, g_sms, g_sms, 64, 128, 8, 41 * 1024, 64 * 128, 2);
+  rc |= run("tf32 K-major 18-wide halo rows", umma1_kernel<128, 4>, g_sms, g_sms, 128, 128, 8, 41 * 1024, 128 * 128, 2);
   // producer / consumer ring fed by bulk copies
   for (int st : {2, 4, 8}) rc |= run_pipe("ring: copy -> 4 MMAs -> commit", pipe_kernel<64, 4>, g_sms, 64, 4, st);
   for (int st : {2, 4, 6}) rc |= run_pipe("ring: copy -> 4 MMAs -> commit", pipe_kernel<128, 4>, g_sms, 128, 4, st);
   for (int st : {2, 4}) rc |= run_pipe("ring: copy -> 4 MMAs -> commit", pipe_kernel<256, 4>, g_sms, 256, 4, st);
   for (int st : {2, 4, 5}) rc |= run_pipe("ring: copy -> 8 MMAs -> commit", pipe_kernel<64, 8>, g_sms, 64, 8, st);
+  rc |= run_pipe("ring: 8 KB copy -> 8 MMAs -> commit", pipe_kernel<64, 8, 8192>, g_sms, 64, 8, 5);
+  rc |= run_pipe("ring: 8 KB copy -> 4 MMAs -> commit", pipe_kernel<64, 4, 8192>, g_sms, 64, 4, 8);
+  rc |= run_pipe("ring: 16 KB copy -> 8 MMAs -> commit", pipe_kernel<128, 8, 16384>, g_sms, 128, 8, 4);
+  rc |= run_pipe("ring: 16 KB copy -> 4 MMAs -> commit", pipe_kernel<128, 4, 16384>, g_sms, 128, 4, 6);
+  rc |= run_pipe("ring: 8 KB copy -> 16 MMAs -> commit", pipe_kernel<64, 16, 8192>, g_sms, 64, 16, 3);
+  // the same rings with one issuing thread for the whole loop and the next stage's barrier polled between the MMAs
+  rc |= run_pipe("ring/1thread: 8 KB -> 8 MMAs", pipe_kernel<64, 8, 8192, true>, g_sms, 64, 8, 5);
+  rc |= run_pipe("ring/1thread: 8 KB -> 4 MMAs", pipe_kernel<64, 4, 8192, true>, g_sms, 64, 4, 8);
+  rc |= run_pipe("ring/1thread: 16 KB -> 8 MMAs", pipe_kernel<128, 8, 16384, true>, g_sms, 128, 8, 4);
+  rc |= run_pipe("ring/1thread: 16 KB -> 4 MMAs", pipe_kernel<128, 4, 16384, true>, g_sms, 128, 4, 6);
+  rc |= run_pipe("ring/1thread: full copy -> 4 MMAs", pipe_kernel<64, 4, 0, true>, g_sms, 64, 4, 8);
+  rc |= run_pipe("ring/1thread: full copy -> 4 MMAs", pipe_kernel<128, 4, 0, true>, g_sms, 128, 4, 6);
   // MMAs + a producer writing shared memory at the same time
   rc |= run_copy("tf32 K-major + bulk copies", umma1_kernel<64, 0, true>, g_sms, 64, 128 * 128, 64 * 128, 4);
   rc |= run_copy("tf32 K-major + bulk copies", umma1_kernel<128, 0, true>, g_sms, 128, 128 * 128, 128 * 128, 4);
