@@ -339,7 +339,7 @@ def main():
                 break
             except Exception:
                 pass
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel (tcgen05 kind::tf32 implicit GEMM; fwd + dgrad launches)",
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel / conv_tc4_kernel (tcgen05 kind::tf32 implicit GEMM; fwd + dgrad launches)",
                 "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
                 "traffic_unit": "DRAM bytes per launch (ncu capture of one step, profiles/%s)" % traffic_src,
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 rate)" % peak_kind, "launches_timed": n_launch,

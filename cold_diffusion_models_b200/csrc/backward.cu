@@ -59,7 +59,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __res
     }
 #pragma unroll
     for (int k = 0; k < PP; ++k) {
-      if (base + k * stride >= p1) break;                   // warp-uniform
+      if (base + k * stride >= p1) continue;                // warp-uniform (`continue`, not `break`: the unrolled loop keeps static indices)
       const long long pix = base + k * stride + sub;
       float4 dv[NQ], xh[NQ];
       float s1 = 0.f, s2 = 0.f;

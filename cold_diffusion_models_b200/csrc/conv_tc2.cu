@@ -267,7 +267,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
               *reinterpret_cast<float4*>(orow + co0 + c + j) = v;
             }
           } else {
-            for (int j = 0; j < nvalid; ++j) {
+            // fully unrolled with a predicate: a run-time index into r[] would move the whole accumulator chunk to local memory
+            // (8 STL.128 + reloads per chunk on every path, also the vector one)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j >= nvalid) break;
               float v = __uint_as_float(r[j]);
               if (p.bias) v += p.bias[co0 + c + j];
               if (rrow) v += rrow[co0 + c + j];

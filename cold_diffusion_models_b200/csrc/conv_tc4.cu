@@ -41,7 +41,7 @@ struct Tc4Params {
   float* out2; int out2_ld;
   const float* aux; int aux_ld;
   int vec8;
-  int dbg;                        // timing experiments only (cd_conv_tc_set_debug): 1 = epilogue without global accesses, 2 = without TMEM loads either
+  int dbg;                        // timing experiments only (cd_conv_tc_set_debug): 1 = epilogue without global accesses and math, 2 = without TMEM loads either, 3 = math but no output stores, 4 = stores but no GELU
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -255,7 +255,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         float* o2row = p.out2 ? p.out2 + pix * p.out2_ld : nullptr;
         const float* arow = p.aux ? p.aux + pix * p.aux_ld : nullptr;
         uint32_t r[32];
-        if (p.dbg >= 2) continue;
+        if (p.dbg == 2) continue;
         tmem_ld32(taddr + half * BN + c, r);
         if (p.dbg == 1) continue;
         if (co0 + c < p.Cout) {
@@ -273,7 +273,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] += t[e]; }
               if (o2row) stg8(o2row + co0 + c + j, v);
-              if (p.act == CD_ACT_GELU) {
+              if (p.act == CD_ACT_GELU && p.dbg != 4) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = cd_gelu(v[e]);
               } else if (p.act == CD_ACT_GELU_BWD) {
@@ -285,10 +285,14 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = cd_round_tf32(v[e]);
               }
-              stg8(orow + co0 + c + j, v);
+              if (p.dbg != 3 || v[0] == 12345.678f) stg8(orow + co0 + c + j, v);
             }
           } else {
-            for (int j = 0; j < nvalid; ++j) {
+            // fully unrolled with a predicate: a run-time index into r[] would move the whole accumulator chunk to local memory
+            // (8 STL.128 + reloads per chunk on every path, also the vector one)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j >= nvalid) break;
               float v = __uint_as_float(r[j]);
               if (p.bias) v += p.bias[co0 + c + j];
               if (rrow) v += rrow[co0 + c + j];
@@ -360,9 +364,11 @@ int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st) {
   if (d->Cout > 128) return 1;                // 4 x BN TMEM columns; the wide layers run on SM pairs (conv_tc2.cu)
   if (!g_sms4) { int dev = 0; CD_CUDA(cudaGetDevice(&dev)); CD_CUDA(cudaDeviceGetAttribute(&g_sms4, cudaDevAttrMultiProcessorCount, dev)); }
   {
-    // 256-pixel tiles need many of them: measured per shape (profiles/conv_shapes_r02e_wide_halo.txt) the kernel wins on the
-    // 128 x 128 level at batch 32 (2048 tiles: 147-163 us against 182-216) and is mixed at 64 x 64 (512 tiles = 3.5 waves)
+    // 256-pixel tiles need many of them: measured per shape (profiles/conv_shapes_r02f_final.txt) the kernel wins on the
+    // 128 x 128 level at batch 32 (2048 tiles: N = 64 layers 144-162 us against 205-207, N = 128 K = 576 157 against 162) and is
+    // mixed at 64 x 64 (512 tiles = 3.5 waves); short-K N = 128 layers (K = 288: 139 against 132) stay on the pair kernel
     const long long tiles256 = static_cast<long long>(d->B) * (d->Hg / kPH) * (d->Wg / kPW);
+    if (!g_force4 && d->Cout > 64 && ktotal < 18) return 1;
     if (!g_force4 && tiles256 < 6LL * g_sms4) return 1;
   }
   if ((reinterpret_cast<uintptr_t>(d->out) & 15) || d->out_ld % 4) return 1;

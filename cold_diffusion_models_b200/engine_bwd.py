@@ -44,8 +44,23 @@ class BackwardMixin:
         if getattr(self, 'flat_grad', None) is not None:
             return
         params = list(self.unet.named_parameters())
-        self._offsets, total = flat_offsets([(n, p.numel()) for n, p in params])
+        # Flat layout = registration order, except that the parameters whose gradients are produced at the very END of the
+        # backward (the time MLP and every block's conditioning projection `mlp.1.*`: _time_bwd) come first.  The rest closes
+        # level by level while the backward walks final -> ups -> mid -> downs, so the gradient all-reduce of a finished suffix
+        # of the buffer can run while the remaining levels are still being differentiated (`grad_ready_hook`).
+        late = [(n, p) for n, p in params if n.startswith('time_mlp.') or '.mlp.1.' in n]
+        late_names = {n for n, _ in late}
+        order = late + [(n, p) for n, p in params if n not in late_names]
+        self._offsets, total = flat_offsets([(n, p.numel()) for n, p in order])
         self.flat_grad = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self._grad_total = total
+        starts = {}
+        for n, _ in order:
+            if n in late_names:
+                continue
+            grp = '.'.join(n.split('.')[:2]) if n.startswith(('downs.', 'ups.')) else n.split('.')[0]
+            starts.setdefault(grp, self._offsets[n][0])
+        self._group_start = starts           # first element of every top-level group; groups are contiguous and in registration order
         self.G = {}
         self.Gp = {}                # data_ptr of G[n] -> packed (KH*KW, O, I) view: what the weight-gradient kernels accumulate into
         for n, p in params:
@@ -362,6 +377,7 @@ class BackwardMixin:
         d = self._block_bwd(self.mid2, save, d)
         d = self._attn_bwd(self.mid_attn, save, d)
         d = self._block_bwd(self.mid1, save, d)
+        self._grads_ready_from('ups.0')                    # ups.*, mid_block1, mid_attn, mid_block2, final_conv: 57 % of the buffer
         # ---- down path ----
         for i in reversed(range(nd)):
             b0, b1, at, dn = self.levels_down[i]
@@ -387,12 +403,27 @@ class BackwardMixin:
             d = self._attn_bwd(at, save, d)
             d = self._block_bwd(b1, save, d)
             d = self._block_bwd(b0, save, d, need_dx=(i > 0))
+            if i >= 2:
+                self._grads_ready_from('downs.%d' % i)     # the two coarsest levels carry 22 of the 24 M down-path parameters
         # ---- time MLP ----
         if unet.time_mlp is not None:
             self._time_bwd(save)
         if self._unpack_batch is not None:
             self._unpack_batch.run(accumulate=True, clear_src=True)
             self._dwp_pending = False
+
+    def _grads_ready_from(self, group):
+        """tell the trainer that flat_grad[start of `group` : previous mark) holds final values (multi-GPU: the all-reduce of
+        that range is issued now and overlaps the rest of the backward).  Marks move from the end of the buffer to the front."""
+        hook = getattr(self, 'grad_ready_hook', None)
+        if hook is None or self._unpack_batch is not None:     # batched unpack writes the reference-layout gradients at the end
+            return
+        lo = self._group_start.get(group)
+        hi = getattr(self, '_ready_mark', self._grad_total)
+        if lo is None or lo >= hi:
+            return
+        self._ready_mark = lo
+        hook(lo, hi)
 
     def _time_bwd(self, save):
         sv = save['time']

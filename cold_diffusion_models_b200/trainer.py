@@ -315,14 +315,34 @@ class Trainer(EvaluationMixin, object):
             loss.backward()
             u_loss = loss.detach() * A
             ds = []
-        for d in ds:
+        eng = self._unet.engine
+        works, low = [], [None]
+        overlap = self._world > 1 and hasattr(eng, '_grads_ready_from')
+        for i, d in enumerate(ds):
             d = tuple(x.cuda(non_blocking=True) for x in d) if isinstance(d, (tuple, list)) else d.cuda(non_blocking=True)
             loss = self._loss(d)
             u_loss = loss.detach() if u_loss is None else u_loss + loss.detach()
-            (loss / A).backward()
-        eng = self._unet.engine
+            if overlap and i == len(ds) - 1:
+                # last micro-batch: every finished suffix of the flat gradient is all-reduced while the backward continues
+                # (NCCL runs on its own stream behind the kernels enqueued so far; section 5 of DESIGN.md)
+                def ready(lo, hi):
+                    works.append(torch.distributed.all_reduce(eng.flat_grad[lo:hi], async_op=True))
+                    low[0] = lo
+                    self.overlapped_ranges.append((lo, hi))
+                self.overlapped_ranges = []                  # introspection / tests: the ranges reduced during the backward
+                eng._ready_mark = eng._grad_total
+                eng.grad_ready_hook = ready
+            try:
+                (loss / A).backward()
+            finally:
+                eng.grad_ready_hook = None
         from .engine_bwd import allreduce_mean_
-        scale = allreduce_mean_(eng.flat_grad, self._world)      # one NCCL all-reduce per optimizer step
+        if works:
+            scale = allreduce_mean_(eng.flat_grad[:low[0]], self._world)   # what the backward closed last: conditioning MLPs, finest levels
+            for w in works:
+                w.wait()
+        else:
+            scale = allreduce_mean_(eng.flat_grad, self._world)            # one NCCL all-reduce per optimizer step
         ema_mode = 0
         if self.step % self.update_ema_every == 0:
             ema_mode = 1 if self.step < self.step_start_ema else 2

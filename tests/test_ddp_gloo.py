@@ -106,6 +106,14 @@ def _trainer_worker(rank, world, port, out):
             assert all(torch.equal(have[k], want[k]) for k in want)
         torch.manual_seed(100 + rank)                       # forward() draws t ~ randint(0, T, (B,)) from the global generator
         tr.train_step(batches=[_batches()[rank]])
+        # the all-reduce of the finished suffix of the flat gradient (ups, mid, final: issued while the down path is still being
+        # differentiated) + the rest at the end cover the buffer exactly once
+        eng = gd.denoise_fn.engine
+        rng = tr.overlapped_ranges
+        assert len(rng) >= 1 and rng[0][1] == eng._grad_total and all(a[0] == b[1] for a, b in zip(rng, rng[1:])), rng
+        assert 0 < rng[-1][0] < eng._grad_total // 2 and rng[-1][0] == eng._group_start['ups.0']
+        late = [n for n, _ in gd.denoise_fn.named_parameters() if n.startswith('time_mlp.') or '.mlp.1.' in n]
+        assert late and all(eng._offsets[n][0] < eng._group_start['downs.0'] for n in late)     # end-of-backward gradients sit first
     if rank == 0:
         torch.save({k: v.clone() for k, v in gd.denoise_fn.state_dict().items()}, out)
     else:

@@ -13,6 +13,9 @@ CONFIGS = collections.OrderedDict([
     ('pair256+128', (1, 128, 0, 0)),           # round-2 default before conv_tc4
     ('wide-halo', (1, 128, 2, 0)),             # the default: conv_tc4 where its tile-count rule takes the layer
     ('wide-halo-all', (1, 128, 6, 0)),         # conv_tc4 for every eligible layer
+    ('wh/noEpi', (1, 128, 2, 0, 1)),
+    ('wh/noStore', (1, 128, 2, 0, 3)),
+    ('wh/noGELU', (1, 128, 2, 0, 4)),
 ])
 DEFAULT = (1, 128, 2, 0)
 

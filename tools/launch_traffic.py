@@ -35,7 +35,7 @@ conv = [(c, us, by) for k, (c, us, by) in agg.items() if k.startswith('conv_tc')
 n = sum(c for c, _, _ in conv)
 if n and len(sys.argv) > 2:
     out = {"source": "%s (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum of tools/one_step.py)" % sys.argv[1],
-           "kernels": "conv_tc_kernel<*> + conv_tc2_kernel<*> + conv_tc3_kernel<*> (fwd + dgrad launches of one optimizer step, config 3)",
+           "kernels": "conv_tc_kernel<*> + conv_tc2_kernel<*> + conv_tc4_kernel<*> (fwd + dgrad launches of one optimizer step, config 3)",
            "launches": n, "dram_bytes_per_launch": sum(by for _, _, by in conv) / n,
            "avg_us_per_launch_under_ncu": sum(us for _, us, _ in conv) / n,
            "share_of_step_under_ncu": sum(us for _, us, _ in conv) / tot}
