@@ -84,10 +84,11 @@ def test_unet_gradients_tf32_path_vs_oracle_autograd():
         f.write('median %.3e  p90 %.3e  max %.3e\n' % (errs[len(errs) // 2][0], errs[int(len(errs) * 0.9)][0], errs[-1][0]))
         for e, n in errs[-10:]:
             f.write('%.3e %s\n' % (e, n))
-    # measured on a B200 (profiles/grad_errors_tf32_r01.txt): median 9.6e-4, p90 1.19e-3, max 1.49e-3 per tensor -- the TF32 operand
+    # measured on a B200: round 1 (profiles/grad_errors_tf32_r01.txt) median 9.6e-4, p90 1.19e-3, max 1.49e-3 per tensor; end of round 2
+    # (profiles/grad_errors_tf32_r02.txt) median 9.3e-4, p90 1.08e-3, max 1.35e-3 -- the TF32 operand
     # rounding (2^-11 relative per operand, what cuDNN's default path does too) accumulated over the ~70 convolutions between the
     # loss and the first block; the fp32 CUDA-core path of the same schedule is at 2e-6 (test above)
-    assert errs[len(errs) // 2][0] < 1.2e-3 and errs[-1][0] < 2e-3, errs[-3:]
+    assert errs[len(errs) // 2][0] < 1.1e-3 and errs[-1][0] < 1.5e-3, errs[-3:]
 
 
 def test_gradient_accumulation_and_flat_buffer():
