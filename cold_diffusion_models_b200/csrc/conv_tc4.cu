@@ -420,5 +420,5 @@ int cd_conv_fwd_tc4(const CdConvDesc* d, cudaStream_t st) {
   }
   (void)ktotal;
   if (BN == 128) return launch4<128, 8>(maps, p, st);
-  return launch4<64, 12>(maps, p, st);
+  return launch4<64, 12, 3>(maps, p, st);
 }
