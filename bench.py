@@ -280,6 +280,12 @@ def main():
     _lib.reset_launch_count()
     ms = timed(step_resident, K)
     launches = _lib.launch_count()
+    for s in range(2):                      # untimed: first use of the pinned batches / loss buffers / events of the end-to-end path
+        wl = trainer.train_step(batches=[host[(s * A + i) % (nb * A)] for i in range(A)])
+        trainer.step += 1
+        loss_host[s & 1].copy_(wl.detach(), non_blocking=True)
+        loss_ev[s & 1].record()
+    sync_all()
     ms_e2e = timed(step_e2e, K)
     value = img_per_step * world * K / (ms / 1e3)
     e2e = img_per_step * world * K / (ms_e2e / 1e3)
