@@ -11,9 +11,9 @@ T=200, Exponential_reflect k=15 std=0.01, x0_step_down; synthetic U(-1,1) images
 A "step" is ONE optimizer step of Trainer.train (DB:1188-1204): 2 micro-batches x 32 images per GPU of
 p_losses forward + backward, one gradient all-reduce (N>1), fused Adam + EMA.  `value` = images/sec over all
 GPUs with the batches already resident in HBM; `e2e` = the same through the public Trainer.train_step call with
-pinned-host batches copied H2D and the loss read back D2H inside the timed region.  The second half of the
-metric (200-step sample images/sec) is measured on a bounded number of reverse steps and reported in
-`sample`; nothing is skipped inside a timed region.
+pinned-host batches copied H2D and the loss read back D2H inside the timed region (two untimed steps of that path first).  At
+N > 1 the all-reduce of every finished suffix of the flat gradient buffer overlaps the rest of the backward.  Nothing is skipped
+inside a timed region.
 
 Both arms print the SAME `metric` string, unit and workload so that the driver can divide them.  The reference arm
 (`--impl reference`) times the reference algorithm (oracle/: the eager-PyTorch restatement of the reference's p_losses, 200-step
